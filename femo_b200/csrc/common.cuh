@@ -1,0 +1,131 @@
+// common.cuh -- shared device helpers and the problem object.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/femo_b200.h"
+#include "layout.hpp"
+
+namespace femo {
+
+extern thread_local std::string g_err;
+int set_err(int code, const std::string &msg);
+
+#define FEMO_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return femo::set_err(FEMO_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+#define FEMO_CHECK_LAUNCH() FEMO_CUDA(cudaGetLastError())
+
+constexpr int kThreads = 256;
+constexpr int kMaxPartials = 4096;   // upper bound on CTAs of any reducing kernel
+constexpr int kMaxSlots = 12;
+
+// device scalar slots (doubles) used by the Krylov / Newton drivers
+enum Scalar { S_ALPHA = 0, S_BETA, S_RZ, S_RR, S_PQ, S_TMP0, S_TMP1, S_TMP2, S_BB, S_COUNT = 16 };
+
+// ---- reductions (deterministic: fixed assignment, fixed tree) ---------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// result valid in thread 0 of the block; safe to call repeatedly
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+    if (wid == 0) v = warp_sum(v);
+    __syncthreads();
+    return v;
+}
+
+// streaming loads for data touched once per kernel (matrix values / indices):
+// keep L1/L2 for the gathered vector instead
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ int32_t ld_stream(const int32_t *p) { return __ldcs(p); }
+
+struct DevPattern {
+    int32_t *rowptr = nullptr, *col = nullptr, *gptr = nullptr, *gsrc = nullptr;
+    int32_t *t_rowptr = nullptr, *t_col = nullptr, *t_perm = nullptr;
+    uint8_t *bcflag = nullptr;
+    int lanes = 8;  // SpMV lanes per row, chosen from mean nnz/row
+    int t_lanes = 8;
+};
+struct DevVecMap {
+    int32_t *ptr = nullptr, *src = nullptr;
+};
+
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    void reset(void *b, size_t c) { base = (char *)b; cap = c; used = 0; }
+    template <class T>
+    T *take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+        if (used + bytes > cap) return nullptr;
+        T *p = (T *)(base + used);
+        used += bytes;
+        return p;
+    }
+    static size_t need(size_t count, size_t elem) { return (count * elem + 255) & ~size_t(255); }
+};
+
+}  // namespace femo
+
+struct femo_mesh {
+    femo::Mesh m;
+};
+
+struct femo_problem {
+    femo::Mesh mesh;
+    int family = 0;
+    double params[8] = {0};
+    femo::Space state, in[4], aux[4];
+    int nin = 0, naux = 0, nout = 0;
+    bool facet_terms = false;
+    std::vector<femo::IntegralBlock> blk_cells, blk_full;
+    femo::Pattern pat[5];
+    femo::VecMap vm_state_full, vm_state_cells, vm_in[4];
+    // Dirichlet data (host)
+    bool has_bc = false;
+    std::vector<uint8_t> bc_mark, bcflag;
+    std::vector<double> bc_g, bc_diag;
+    std::vector<int32_t> lift_rows;
+    // device
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    bool uploaded = false;
+    int num_sms = 148;
+    femo::Arena st, wk;
+    double *d_coords = nullptr;
+    int32_t *d_cellsT = nullptr, *d_bf_cell = nullptr, *d_bf_local = nullptr;
+    femo::DevPattern dpat[5];
+    femo::DevVecMap dvm_state_full, dvm_state_cells, dvm_in[4];
+    uint8_t *d_bc_mark = nullptr;
+    double *d_bc_g = nullptr, *d_bc_diag = nullptr;
+    int32_t *d_lift_rows = nullptr;
+    // work
+    double *d_scratch = nullptr, *d_partials = nullptr, *d_scalars = nullptr;
+    double *kr_r = nullptr, *kr_p = nullptr, *kr_q = nullptr, *kr_dinv = nullptr, *kr_z = nullptr, *kr_w = nullptr;
+    double *nt_b = nullptr, *nt_dx = nullptr, *nt_vals = nullptr, *nt_vals_bc = nullptr, *d_tvals = nullptr;
+    double *h_pinned = nullptr;  // small pinned staging for scalars
+    size_t scratch_len = 0, tvals_len = 0;
+    // coefficients
+    const double *coef[femo::kMaxSlots] = {nullptr};
+    int64_t coefn[femo::kMaxSlots] = {0};
+    // counters (bench: how many of our kernels were launched)
+    long long launches = 0;
+};

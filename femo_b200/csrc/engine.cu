@@ -1,0 +1,1056 @@
+// engine.cu -- device kernels shared by all families (segmented reduction,
+// boundary conditions, SpMV, fused Krylov vector kernels) and the C ABI.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "families.cuh"
+
+namespace femo {
+
+thread_local std::string g_err;
+int set_err(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+// ===========================================================================
+// sorted segmented reduction (K12): out[t] = sum_{s in [ptr[t],ptr[t+1])} scratch[src[s]]
+// src is ascending inside every segment, so the summation order is fixed.
+// ===========================================================================
+__global__ void __launch_bounds__(kThreads) k_segreduce(const int32_t *__restrict__ ptr, const int32_t *__restrict__ src,
+                                                        const double *__restrict__ scratch, double *__restrict__ out,
+                                                        int64_t n) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int32_t s0 = ptr[t], s1 = ptr[t + 1];
+    double acc = 0.0;
+    for (int32_t s = s0; s < s1; ++s) acc += scratch[ld_stream(src + s)];
+    out[t] = acc;
+}
+
+// Jacobian variant: one pass writes the un-BC'd values and/or the BC'd copy
+// (rows and columns of Dirichlet dofs zeroed, diagonal = bc multiplicity;
+// SURVEY.md Appendix A.2).  bcflag: 0 keep, 1 zero, 2 diagonal of a bc row.
+__global__ void __launch_bounds__(kThreads)
+    k_segreduce_jac(const int32_t *__restrict__ ptr, const int32_t *__restrict__ src, const double *__restrict__ scratch,
+                    const uint8_t *__restrict__ bcflag, const int32_t *__restrict__ col,
+                    const double *__restrict__ bc_diag, double *__restrict__ out, double *__restrict__ out_bc, int64_t n) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int32_t s0 = ptr[t], s1 = ptr[t + 1];
+    double acc = 0.0;
+    for (int32_t s = s0; s < s1; ++s) acc += scratch[ld_stream(src + s)];
+    if (out) out[t] = acc;
+    if (out_bc) {
+        const uint8_t fl = bcflag ? bcflag[t] : 0;
+        out_bc[t] = (fl == 0) ? acc : (fl == 1 ? 0.0 : bc_diag[col[t]]);
+    }
+}
+
+// NonlinearProblem.F boundary treatment: for rows touching a
+// Dirichlet column  b_i -= scale * sum_{j in bc} A_ij (g_j - x_j); then
+// b[bc] = scale * (g - x).
+__global__ void __launch_bounds__(kThreads)
+    k_newton_rhs(const int32_t *__restrict__ rows, int64_t nrows, const int32_t *__restrict__ rowptr,
+                 const int32_t *__restrict__ col, const double *__restrict__ vals, const uint8_t *__restrict__ mark,
+                 const double *__restrict__ g, const double *__restrict__ x, double *__restrict__ b, double scale) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= nrows) return;
+    const int32_t i = rows[k];
+    if (mark[i]) {
+        b[i] = scale * (g[i] - x[i]);
+        return;
+    }
+    double acc = 0.0;
+    for (int32_t t = rowptr[i]; t < rowptr[i + 1]; ++t) {
+        const int32_t j = col[t];
+        if (mark[j]) acc += vals[t] * (g[j] - x[j]);
+    }
+    b[i] -= scale * acc;
+}
+
+// ===========================================================================
+// reductions
+// ===========================================================================
+__global__ void __launch_bounds__(kThreads) k_sum(const double *__restrict__ a, int64_t n, double *__restrict__ partials) {
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc += a[i];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_dot(const double *__restrict__ a, const double *__restrict__ b, int64_t n, double *__restrict__ partials) {
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc += a[i] * b[i];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// one CTA: fixed-order sum of np partials -> scalars[slot]
+__global__ void __launch_bounds__(kThreads) k_finalize(const double *__restrict__ partials, int np, double *scalars, int slot) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) acc += partials[i];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) scalars[slot] = acc;
+}
+
+// ===========================================================================
+// SpMV (K7): LANES threads cooperate on one row of a CSR matrix; a warp covers
+// 32/LANES consecutive rows so values/columns stream in contiguous chunks.
+// Optional fused dot(x, y) for CG (square matrices only).
+// ===========================================================================
+template <int LANES, bool DOT>
+__global__ void __launch_bounds__(kThreads)
+    k_spmv(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ vals,
+           const double *__restrict__ x, double *__restrict__ y, int64_t n, double *__restrict__ partials) {
+    constexpr int GPW = 32 / LANES;  // row groups per warp
+    const int lane = threadIdx.x & (LANES - 1);
+    const int gw = (threadIdx.x & 31) / LANES;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double dot = 0.0;
+    for (int64_t base = warp * GPW; base < n; base += nwarps * GPW) {
+        const int64_t r = base + gw;
+        int32_t s = 0, e = 0;
+        if (r < n) {
+            s = rowptr[r];
+            e = rowptr[r + 1];
+        }
+        double acc = 0.0;
+        for (int32_t t = s + lane; t < e; t += LANES) acc += ld_stream(vals + t) * __ldg(x + ld_stream(col + t));
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0 && r < n) {
+            y[r] = acc;
+            if (DOT) dot += acc * __ldg(x + r);
+        }
+    }
+    if (DOT) {
+        dot = block_sum(dot);
+        if (threadIdx.x == 0) partials[blockIdx.x] = dot;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_permute(const int32_t *__restrict__ perm, const double *__restrict__ in, double *__restrict__ out, int64_t n) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) out[t] = in[perm[t]];
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_diag_inv(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ vals,
+               double *__restrict__ dinv, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double d = 1.0;
+    for (int32_t t = rowptr[i]; t < rowptr[i + 1]; ++t)
+        if (col[t] == i) d = vals[t];
+    dinv[i] = (d != 0.0) ? 1.0 / d : 1.0;
+}
+
+// ===========================================================================
+// fused CG vector kernels (K8).  Scalars live on the device: no host sync
+// inside an iteration.
+// ===========================================================================
+// r = b - q ; p = dinv*r ; partials: rz, rr
+__global__ void __launch_bounds__(kThreads)
+    k_cg_init(const double *__restrict__ b, const double *__restrict__ q, const double *__restrict__ dinv,
+              double *__restrict__ r, double *__restrict__ p, int64_t n, double *__restrict__ prz,
+              double *__restrict__ prr) {
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = b[i] - q[i];
+        const double zi = dinv[i] * ri;
+        r[i] = ri;
+        p[i] = zi;
+        rz += ri * zi;
+        rr += ri * ri;
+    }
+    rz = block_sum(rz);
+    rr = block_sum(rr);
+    if (threadIdx.x == 0) {
+        prz[blockIdx.x] = rz;
+        prr[blockIdx.x] = rr;
+    }
+}
+
+// x += alpha p ; r -= alpha q ; partials of r.(dinv r) and r.r
+__global__ void __launch_bounds__(kThreads)
+    k_cg_update(const double *__restrict__ sc, const double *__restrict__ p, const double *__restrict__ q,
+                const double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r, int64_t n,
+                double *__restrict__ prz, double *__restrict__ prr) {
+    const double alpha = sc[S_ALPHA];
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        rz += ri * ri * dinv[i];
+        rr += ri * ri;
+    }
+    rz = block_sum(rz);
+    rr = block_sum(rr);
+    if (threadIdx.x == 0) {
+        prz[blockIdx.x] = rz;
+        prr[blockIdx.x] = rr;
+    }
+}
+
+// p = dinv*r + beta p
+__global__ void __launch_bounds__(kThreads)
+    k_cg_dir(const double *__restrict__ sc, const double *__restrict__ r, const double *__restrict__ dinv,
+             double *__restrict__ p, int64_t n) {
+    const double beta = sc[S_BETA];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = dinv[i] * r[i] + beta * p[i];
+}
+
+// phase 0: alpha = rz / sum(pq partials)
+// phase 1: rz' = sum(A), rr = sum(B); beta = rz'/rz ; rz = rz'
+// phase 2: rz = sum(A), rr = sum(B)   (initialisation)
+__global__ void __launch_bounds__(kThreads)
+    k_cg_scalars(int phase, double *sc, const double *__restrict__ pa, const double *__restrict__ pb, int np) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        a += pa[i];
+        if (pb) b += pb[i];
+    }
+    a = block_sum(a);
+    b = block_sum(b);
+    if (threadIdx.x == 0) {
+        if (phase == 0) {
+            sc[S_PQ] = a;
+            sc[S_ALPHA] = (a != 0.0) ? sc[S_RZ] / a : 0.0;
+        } else if (phase == 1) {
+            sc[S_BETA] = (sc[S_RZ] != 0.0) ? a / sc[S_RZ] : 0.0;
+            sc[S_RZ] = a;
+            sc[S_RR] = b;
+        } else {
+            sc[S_RZ] = a;
+            sc[S_RR] = b;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_axpy(double a, const double *__restrict__ x, double *__restrict__ y, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] += a * x[i];
+}
+
+__global__ void __launch_bounds__(kThreads) k_fill(double a, double *__restrict__ y, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = a;
+}
+
+}  // namespace femo
+
+using namespace femo;
+
+// ===========================================================================
+// helpers
+// ===========================================================================
+static inline int grid_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
+static inline int red_grid(const femo_problem *p, int64_t n) {
+    int64_t g = (n + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)p->num_sms * 8;
+    if (cap > kMaxPartials) cap = kMaxPartials;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
+}
+
+static int need_device(femo_problem *p) {
+    if (!p) return set_err(FEMO_EINVAL, "null problem");
+    if (!p->uploaded) return set_err(FEMO_ESTATE, "problem not uploaded to a CUDA device (femo_problem_upload); there is no CPU path");
+    cudaError_t e = cudaSetDevice(p->device);
+    if (e != cudaSuccess) return set_err(FEMO_ECUDA, cudaGetErrorString(e));
+    return FEMO_OK;
+}
+
+static int need_coef(femo_problem *p, int slot, int64_t n, const char *what) {
+    if (!p->coef[slot] || p->coefn[slot] != n)
+        return set_err(FEMO_ESTATE, std::string("coefficient not set or wrong size: ") + what);
+    return FEMO_OK;
+}
+
+static TriArgs tri_args(femo_problem *p, double *out) {
+    TriArgs A;
+    A.coords = p->d_coords;
+    A.cellsT = p->d_cellsT;
+    A.ncells = p->mesh.ncells;
+    A.bf_cell = p->d_bf_cell;
+    A.bf_local = p->d_bf_local;
+    A.nfacets = (int64_t)p->mesh.bf_cell.size();
+    A.u = p->coef[0];
+    A.f = p->coef[1];
+    A.uex = p->coef[2];
+    A.alpha = p->params[0];
+    A.beta = p->params[1];
+    A.out = out;
+    return A;
+}
+
+// run the element kernels of `op` into scratch (cells, then facets when the op has them)
+static int run_elements(femo_problem *p, int op) {
+    const int64_t nc = p->mesh.ncells;
+    const int64_t nf = (int64_t)p->mesh.bf_cell.size();
+    cudaStream_t st = p->stream;
+    int rc;
+    if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
+    if ((rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
+    switch (p->family) {
+        case FEMO_FAMILY_POISSON_P1: {
+            if (op == OP_OUT || op == OP_OUT_DU)
+                if ((rc = need_coef(p, 2, p->aux[0].ndofs, "u_ex"))) return rc;
+            TriArgs A = tri_args(p, p->d_scratch);
+            const int g = grid_for(nc);
+            switch (op) {
+                case OP_RES: k_poisson_p1_cell<OP_RES><<<g, kThreads, 0, st>>>(A); break;
+                case OP_JAC: k_poisson_p1_cell<OP_JAC><<<g, kThreads, 0, st>>>(A); break;
+                case OP_DRDM: k_poisson_p1_cell<OP_DRDM><<<g, kThreads, 0, st>>>(A); break;
+                case OP_OUT: k_poisson_p1_cell<OP_OUT><<<g, kThreads, 0, st>>>(A); break;
+                case OP_OUT_DU: k_poisson_p1_cell<OP_OUT_DU><<<g, kThreads, 0, st>>>(A); break;
+                case OP_OUT_DM: k_poisson_p1_cell<OP_OUT_DM><<<g, kThreads, 0, st>>>(A); break;
+            }
+            p->launches++;
+            break;
+        }
+        case FEMO_FAMILY_NLPOISSON_P1: {
+            TriArgs A = tri_args(p, p->d_scratch);
+            const int g = grid_for(nc);
+            switch (op) {
+                case OP_RES: k_nlpoisson_p1_cell<OP_RES><<<g, kThreads, 0, st>>>(A); break;
+                case OP_JAC: k_nlpoisson_p1_cell<OP_JAC><<<g, kThreads, 0, st>>>(A); break;
+                case OP_DRDM: k_nlpoisson_p1_cell<OP_DRDM><<<g, kThreads, 0, st>>>(A); break;
+                case OP_OUT: k_nlpoisson_p1_cell<OP_OUT><<<g, kThreads, 0, st>>>(A); break;
+                case OP_OUT_DU: k_nlpoisson_p1_cell<OP_OUT_DU><<<g, kThreads, 0, st>>>(A); break;
+                case OP_OUT_DM: k_nlpoisson_p1_cell<OP_OUT_DM><<<g, kThreads, 0, st>>>(A); break;
+            }
+            p->launches++;
+            if (op == OP_RES) {
+                TriArgs F = tri_args(p, p->d_scratch + nc * 3);
+                k_nlpoisson_p1_facet<OP_RES><<<grid_for(nf), kThreads, 0, st>>>(F);
+                p->launches++;
+            } else if (op == OP_JAC) {
+                TriArgs F = tri_args(p, p->d_scratch + nc * 9);
+                k_nlpoisson_p1_facet<OP_JAC><<<grid_for(nf), kThreads, 0, st>>>(F);
+                p->launches++;
+            }
+            break;
+        }
+        default:
+            return set_err(FEMO_EINVAL, "family has no device kernels in this build");
+    }
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
+static int segreduce(femo_problem *p, const DevVecMap &m, int64_t n, double *d_out) {
+    k_segreduce<<<grid_for(n), kThreads, 0, p->stream>>>(m.ptr, m.src, p->d_scratch, d_out, n);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
+template <bool DOT>
+static int launch_spmv(femo_problem *p, int lanes, const int32_t *rowptr, const int32_t *col, const double *vals,
+                       const double *x, double *y, int64_t n, int *np_out) {
+    // persistent-style grid: 8 CTAs of 256 threads per SM keeps the active row window contiguous
+    int64_t rows_per_cta = (int64_t)kThreads / lanes;
+    int64_t g = (n + rows_per_cta - 1) / rows_per_cta;
+    int64_t cap = std::min<int64_t>((int64_t)p->num_sms * 8, kMaxPartials);
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
+    double *pp = p->d_partials;
+    cudaStream_t st = p->stream;
+    switch (lanes) {
+        case 2: k_spmv<2, DOT><<<grid, kThreads, 0, st>>>(rowptr, col, vals, x, y, n, pp); break;
+        case 4: k_spmv<4, DOT><<<grid, kThreads, 0, st>>>(rowptr, col, vals, x, y, n, pp); break;
+        case 8: k_spmv<8, DOT><<<grid, kThreads, 0, st>>>(rowptr, col, vals, x, y, n, pp); break;
+        case 16: k_spmv<16, DOT><<<grid, kThreads, 0, st>>>(rowptr, col, vals, x, y, n, pp); break;
+        default: k_spmv<32, DOT><<<grid, kThreads, 0, st>>>(rowptr, col, vals, x, y, n, pp); break;
+    }
+    p->launches++;
+    if (np_out) *np_out = grid;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
+static int pick_lanes(int64_t nnz, int64_t nrows) {
+    double avg = nrows ? (double)nnz / (double)nrows : 1.0;
+    if (avg <= 2.5) return 2;
+    if (avg <= 5.0) return 4;
+    if (avg <= 12.0) return 8;
+    if (avg <= 24.0) return 16;
+    return 32;
+}
+
+static int read_scalars(femo_problem *p, int first, int count, double *h) {
+    FEMO_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_scalars + first, sizeof(double) * count, cudaMemcpyDeviceToHost, p->stream));
+    FEMO_CUDA(cudaStreamSynchronize(p->stream));
+    for (int i = 0; i < count; ++i) h[i] = p->h_pinned[i];
+    return FEMO_OK;
+}
+
+// ||a||^2 -> host
+static int norm2_sq(femo_problem *p, const double *a, int64_t n, double *out) {
+    int g = red_grid(p, n);
+    k_dot<<<g, kThreads, 0, p->stream>>>(a, a, n, p->d_partials);
+    k_finalize<<<1, kThreads, 0, p->stream>>>(p->d_partials, g, p->d_scalars, S_TMP0);
+    p->launches += 2;
+    FEMO_CHECK_LAUNCH();
+    return read_scalars(p, S_TMP0, 1, out);
+}
+
+template <class T>
+static int up(femo_problem *p, T *&dst, const std::vector<T> &src) {
+    dst = p->st.take<T>(std::max<size_t>(1, src.size()));
+    if (!dst) return set_err(FEMO_EINVAL, "static arena too small");
+    if (!src.empty())
+        FEMO_CUDA(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, p->stream));
+    return FEMO_OK;
+}
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int femo_version(void) { return 100; }
+const char *femo_last_error(void) { return g_err.c_str(); }
+
+int femo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ---- meshes ---------------------------------------------------------------
+int femo_mesh_create_unit_square(int nx, int ny, const double lo[2], const double hi[2], femo_mesh **out) {
+    if (!out || nx < 1 || ny < 1 || !lo || !hi) return set_err(FEMO_EINVAL, "femo_mesh_create_unit_square: bad arguments");
+    if ((int64_t)(nx + 1) * (ny + 1) > 2147483647LL) return set_err(FEMO_ELIMIT, "mesh exceeds int32 vertices");
+    femo_mesh *m = new femo_mesh();
+    make_unit_square_tri(nx, ny, lo, hi, m->m);
+    *out = m;
+    return FEMO_OK;
+}
+int femo_mesh_create_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2], femo_mesh **out) {
+    if (!out || nx < 1 || ny < 1 || !lo || !hi) return set_err(FEMO_EINVAL, "femo_mesh_create_rectangle_quad: bad arguments");
+    femo_mesh *m = new femo_mesh();
+    make_rectangle_quad(nx, ny, lo, hi, m->m);
+    *out = m;
+    return FEMO_OK;
+}
+int femo_mesh_create_interval(int n, double x0, double x1, femo_mesh **out) {
+    if (!out || n < 1) return set_err(FEMO_EINVAL, "femo_mesh_create_interval: bad arguments");
+    femo_mesh *m = new femo_mesh();
+    make_interval(n, x0, x1, m->m);
+    *out = m;
+    return FEMO_OK;
+}
+int femo_mesh_sizes(const femo_mesh *m, int64_t s[6]) {
+    if (!m || !s) return set_err(FEMO_EINVAL, "femo_mesh_sizes: null");
+    s[0] = m->m.ncells; s[1] = m->m.nverts; s[2] = m->m.nvpc; s[3] = m->m.gdim;
+    s[4] = (int64_t)m->m.bf_cell.size(); s[5] = m->m.kind;
+    return FEMO_OK;
+}
+int femo_mesh_copy(const femo_mesh *m, int what, void *out) {
+    if (!m || !out) return set_err(FEMO_EINVAL, "femo_mesh_copy: null");
+    const Mesh &M = m->m;
+    switch (what) {
+        case 0: memcpy(out, M.coords.data(), M.coords.size() * sizeof(double)); break;
+        case 1: memcpy(out, M.cells.data(), M.cells.size() * sizeof(int32_t)); break;
+        case 2: memcpy(out, M.bf_cell.data(), M.bf_cell.size() * sizeof(int32_t)); break;
+        case 3: memcpy(out, M.bf_local.data(), M.bf_local.size() * sizeof(int32_t)); break;
+        default: return set_err(FEMO_EINVAL, "femo_mesh_copy: bad selector");
+    }
+    return FEMO_OK;
+}
+void femo_mesh_destroy(femo_mesh *m) { delete m; }
+
+// ---- problem layout -------------------------------------------------------
+int femo_problem_create(const femo_mesh *m, int family, const double *params, int nparams, femo_problem **out) {
+    if (!m || !out) return set_err(FEMO_EINVAL, "femo_problem_create: null");
+    if (nparams < 0 || nparams > 8) return set_err(FEMO_EINVAL, "femo_problem_create: nparams out of range");
+    femo_problem *p = new femo_problem();
+    p->mesh = m->m;
+    p->family = family;
+    for (int i = 0; i < nparams; ++i) p->params[i] = params[i];
+    const Mesh &M = p->mesh;
+    try {
+        switch (family) {
+            case FEMO_FAMILY_POISSON_P1:
+            case FEMO_FAMILY_NLPOISSON_P1:
+                if (M.kind != MESH_TRI) throw LayoutError{FEMO_EINVAL, "family needs a triangle mesh"};
+                p->state.init(M, EL_VERTEX, 1);
+                p->nin = 1;
+                p->in[0].init(M, EL_DG0, 1);
+                p->nout = 1;
+                if (family == FEMO_FAMILY_POISSON_P1) {
+                    p->naux = 1;  // u_ex in CG1 (run_poisson_opt.py:108)
+                    p->aux[0].init(M, EL_VERTEX, 1);
+                    if (nparams < 1) p->params[0] = 1e-6;
+                } else {
+                    p->facet_terms = true;
+                    if (nparams < 1) p->params[0] = 6e-7;
+                    if (nparams < 2) p->params[1] = 10.0;
+                }
+                break;
+            default:
+                throw LayoutError{FEMO_EINVAL, "unknown form family"};
+        }
+        IntegralBlock cells;
+        cells.ne = M.ncells;
+        p->blk_cells = {cells};
+        p->blk_full = p->blk_cells;
+        if (p->facet_terms) {
+            IntegralBlock fb;
+            fb.ne = (int64_t)M.bf_cell.size();
+            fb.ent_cell = M.bf_cell.data();
+            p->blk_full.push_back(fb);
+        }
+        build_pattern(M, p->state, p->state, p->blk_full, p->pat[0]);
+        for (int s = 0; s < p->nin; ++s) build_pattern(M, p->state, p->in[s], p->blk_cells, p->pat[1 + s]);
+        build_vecmap(M, p->state, p->blk_full, p->vm_state_full);
+        if (p->facet_terms) build_vecmap(M, p->state, p->blk_cells, p->vm_state_cells);
+        for (int s = 0; s < p->nin; ++s) build_vecmap(M, p->in[s], p->blk_cells, p->vm_in[s]);
+    } catch (const LayoutError &e) {
+        delete p;
+        return set_err(e.code, e.msg);
+    } catch (const std::exception &e) {
+        delete p;
+        return set_err(FEMO_EINVAL, e.what());
+    }
+    *out = p;
+    return FEMO_OK;
+}
+
+void femo_problem_destroy(femo_problem *p) {
+    if (!p) return;
+    if (p->h_pinned) cudaFreeHost(p->h_pinned);
+    delete p;
+}
+
+int femo_problem_sizes(const femo_problem *p, int64_t s[16]) {
+    if (!p || !s) return set_err(FEMO_EINVAL, "femo_problem_sizes: null");
+    for (int i = 0; i < 16; ++i) s[i] = 0;
+    s[0] = p->state.ndofs; s[1] = p->nin; s[2] = p->naux; s[3] = p->nout;
+    for (int i = 0; i < p->nin; ++i) s[4 + i] = p->in[i].ndofs;
+    for (int i = 0; i < p->naux; ++i) s[8 + i] = p->aux[i].ndofs;
+    s[12] = (int64_t)p->mesh.bf_cell.size();
+    return FEMO_OK;
+}
+
+static const Pattern *get_pat(const femo_problem *p, int which) {
+    if (!p || which < 0 || which > p->nin) return nullptr;
+    return &p->pat[which];
+}
+
+int femo_problem_pattern_info(const femo_problem *p, int which, int64_t info[4]) {
+    const Pattern *P = get_pat(p, which);
+    if (!P || !info) return set_err(FEMO_EINVAL, "femo_problem_pattern_info: bad selector");
+    info[0] = P->nrows; info[1] = P->ncols; info[2] = P->nnz; info[3] = P->ncontrib;
+    return FEMO_OK;
+}
+int femo_problem_pattern(const femo_problem *p, int which, int32_t *rowptr, int32_t *col) {
+    const Pattern *P = get_pat(p, which);
+    if (!P) return set_err(FEMO_EINVAL, "femo_problem_pattern: bad selector");
+    if (rowptr) memcpy(rowptr, P->rowptr.data(), P->rowptr.size() * sizeof(int32_t));
+    if (col) memcpy(col, P->col.data(), P->col.size() * sizeof(int32_t));
+    return FEMO_OK;
+}
+int femo_problem_gather_map(const femo_problem *p, int which, int32_t *ptr, int32_t *src) {
+    const Pattern *P = get_pat(p, which);
+    if (!P) return set_err(FEMO_EINVAL, "femo_problem_gather_map: bad selector");
+    if (ptr) memcpy(ptr, P->gptr.data(), P->gptr.size() * sizeof(int32_t));
+    if (src) memcpy(src, P->gsrc.data(), P->gsrc.size() * sizeof(int32_t));
+    return FEMO_OK;
+}
+
+int femo_problem_set_bc(femo_problem *p, const int32_t *dofs, const int32_t *list_ptr, int nlists, const double *g) {
+    if (!p || nlists < 0 || (nlists > 0 && (!dofs || !list_ptr))) return set_err(FEMO_EINVAL, "femo_problem_set_bc: bad arguments");
+    if (p->uploaded) return set_err(FEMO_ESTATE, "femo_problem_set_bc must precede femo_problem_upload");
+    const int64_t N = p->state.ndofs;
+    p->bc_mark.assign(N, 0);
+    p->bc_diag.assign(N, 0.0);
+    p->bc_g.assign(N, 0.0);
+    for (int l = 0; l < nlists; ++l)
+        for (int32_t k = list_ptr[l]; k < list_ptr[l + 1]; ++k) {
+            int32_t d = dofs[k];
+            if (d < 0 || d >= N) return set_err(FEMO_EINVAL, "femo_problem_set_bc: dof out of range");
+            p->bc_mark[d] = 1;
+            p->bc_diag[d] += 1.0;  // dolfinx set_diagonal adds once per dirichletbc object
+        }
+    if (g)
+        for (int64_t i = 0; i < N; ++i)
+            if (p->bc_mark[i]) p->bc_g[i] = g[i];
+    const Pattern &P = p->pat[0];
+    p->bcflag.assign(P.nnz, 0);
+    std::vector<uint8_t> lift(N, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i) {
+        bool any = p->bc_mark[i];
+        for (int32_t t = P.rowptr[i]; t < P.rowptr[i + 1]; ++t) {
+            int32_t j = P.col[t];
+            if (p->bc_mark[i] || p->bc_mark[j]) p->bcflag[t] = (i == j) ? 2 : 1;
+            any = any || p->bc_mark[j];
+        }
+        lift[i] = any;
+    }
+    p->lift_rows.clear();
+    for (int64_t i = 0; i < N; ++i)
+        if (lift[i]) p->lift_rows.push_back((int32_t)i);
+    p->has_bc = nlists > 0 && !p->lift_rows.empty();
+    return FEMO_OK;
+}
+
+// ---- device residency -----------------------------------------------------
+static size_t pattern_bytes(const Pattern &P, bool bc) {
+    size_t b = 0;
+    b += Arena::need(P.rowptr.size(), 4) + Arena::need(P.col.size(), 4);
+    b += Arena::need(P.gptr.size(), 4) + Arena::need(P.gsrc.size(), 4);
+    b += Arena::need(P.t_rowptr.size(), 4) + Arena::need(P.t_col.size(), 4) + Arena::need(P.t_perm.size(), 4);
+    if (bc) b += Arena::need(P.nnz, 1);
+    return b;
+}
+static size_t vecmap_bytes(const VecMap &V) { return Arena::need(V.ptr.size(), 4) + Arena::need(V.src.size(), 4); }
+
+int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_t *work_bytes) {
+    if (!p || !static_bytes || !work_bytes) return set_err(FEMO_EINVAL, "femo_problem_device_bytes: null");
+    const Mesh &M = p->mesh;
+    const int64_t N = p->state.ndofs;
+    size_t s = 0;
+    s += Arena::need(M.coords.size(), 8) + Arena::need(M.cells.size(), 4);
+    s += Arena::need(M.bf_cell.size(), 4) + Arena::need(M.bf_local.size(), 4);
+    for (int w = 0; w <= p->nin; ++w) s += pattern_bytes(p->pat[w], w == 0);
+    s += vecmap_bytes(p->vm_state_full) + vecmap_bytes(p->vm_state_cells);
+    for (int i = 0; i < p->nin; ++i) s += vecmap_bytes(p->vm_in[i]);
+    s += Arena::need(N, 1) + 2 * Arena::need(N, 8) + Arena::need(std::max<size_t>(1, p->lift_rows.size()), 4);
+    s += 4096;
+    size_t scratch = 0, tv = 0;
+    for (int w = 0; w <= p->nin; ++w) {
+        scratch = std::max<size_t>(scratch, p->pat[w].scratch_len);
+        tv = std::max<size_t>(tv, p->pat[w].nnz);
+    }
+    scratch = std::max<size_t>(scratch, p->vm_state_full.scratch_len);
+    for (int i = 0; i < p->nin; ++i) scratch = std::max<size_t>(scratch, p->vm_in[i].scratch_len);
+    scratch = std::max<size_t>(scratch, (size_t)M.ncells);
+    size_t w = 0;
+    w += Arena::need(scratch, 8);
+    w += Arena::need(3 * kMaxPartials, 8) + Arena::need(S_COUNT, 8);
+    w += 8 * Arena::need(N, 8);                    // r p q dinv z w b dx
+    w += 2 * Arena::need(p->pat[0].nnz, 8);        // Newton's Jacobian values (plain, BC'd)
+    w += Arena::need(tv, 8);                       // transposed values
+    w += 4096;
+    *static_bytes = s;
+    *work_bytes = w;
+    return FEMO_OK;
+}
+
+int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_static, size_t static_bytes, void *d_work,
+                        size_t work_bytes) {
+    if (!p || !d_static || !d_work) return set_err(FEMO_EINVAL, "femo_problem_upload: null");
+    if (femo_device_count() <= device || device < 0)
+        return set_err(FEMO_ENODEVICE, "femo_problem_upload: no such CUDA device; this engine has no CPU path");
+    size_t sb, wb;
+    femo_problem_device_bytes(p, &sb, &wb);
+    if (static_bytes < sb || work_bytes < wb) return set_err(FEMO_EINVAL, "femo_problem_upload: arenas smaller than femo_problem_device_bytes");
+    FEMO_CUDA(cudaSetDevice(device));
+    p->device = device;
+    p->stream = (cudaStream_t)stream;
+    cudaDeviceProp prop;
+    FEMO_CUDA(cudaGetDeviceProperties(&prop, device));
+    p->num_sms = prop.multiProcessorCount;
+    p->st.reset(d_static, static_bytes);
+    p->wk.reset(d_work, work_bytes);
+    const Mesh &M = p->mesh;
+    const int64_t N = p->state.ndofs;
+    int rc;
+    if ((rc = up(p, p->d_coords, M.coords))) return rc;
+    {   // cells as SoA planes
+        std::vector<int32_t> T(M.cells.size());
+        for (int64_t c = 0; c < M.ncells; ++c)
+            for (int a = 0; a < M.nvpc; ++a) T[a * M.ncells + c] = M.cells[c * M.nvpc + a];
+        if ((rc = up(p, p->d_cellsT, T))) return rc;
+        FEMO_CUDA(cudaStreamSynchronize(p->stream));  // T goes out of scope
+    }
+    if ((rc = up(p, p->d_bf_cell, M.bf_cell))) return rc;
+    if ((rc = up(p, p->d_bf_local, M.bf_local))) return rc;
+    for (int w = 0; w <= p->nin; ++w) {
+        const Pattern &P = p->pat[w];
+        DevPattern &D = p->dpat[w];
+        if ((rc = up(p, D.rowptr, P.rowptr))) return rc;
+        if ((rc = up(p, D.col, P.col))) return rc;
+        if ((rc = up(p, D.gptr, P.gptr))) return rc;
+        if ((rc = up(p, D.gsrc, P.gsrc))) return rc;
+        if ((rc = up(p, D.t_perm, P.t_perm))) return rc;
+        if (P.square_symmetric) {
+            D.t_rowptr = D.rowptr;
+            D.t_col = D.col;
+        } else {
+            if ((rc = up(p, D.t_rowptr, P.t_rowptr))) return rc;
+            if ((rc = up(p, D.t_col, P.t_col))) return rc;
+        }
+        D.lanes = pick_lanes(P.nnz, P.nrows);
+        D.t_lanes = pick_lanes(P.nnz, P.ncols);
+    }
+    if (p->has_bc) {
+        if ((rc = up(p, p->dpat[0].bcflag, p->bcflag))) return rc;
+    }
+    if ((rc = up(p, p->dvm_state_full.ptr, p->vm_state_full.ptr))) return rc;
+    if ((rc = up(p, p->dvm_state_full.src, p->vm_state_full.src))) return rc;
+    if (p->facet_terms) {
+        if ((rc = up(p, p->dvm_state_cells.ptr, p->vm_state_cells.ptr))) return rc;
+        if ((rc = up(p, p->dvm_state_cells.src, p->vm_state_cells.src))) return rc;
+    } else {
+        p->dvm_state_cells = p->dvm_state_full;
+    }
+    for (int i = 0; i < p->nin; ++i) {
+        if ((rc = up(p, p->dvm_in[i].ptr, p->vm_in[i].ptr))) return rc;
+        if ((rc = up(p, p->dvm_in[i].src, p->vm_in[i].src))) return rc;
+    }
+    if (p->bc_mark.empty()) {
+        p->bc_mark.assign(N, 0);
+        p->bc_g.assign(N, 0.0);
+        p->bc_diag.assign(N, 0.0);
+    }
+    if ((rc = up(p, p->d_bc_mark, p->bc_mark))) return rc;
+    if ((rc = up(p, p->d_bc_g, p->bc_g))) return rc;
+    if ((rc = up(p, p->d_bc_diag, p->bc_diag))) return rc;
+    if ((rc = up(p, p->d_lift_rows, p->lift_rows))) return rc;
+
+    // quadrature tables
+    {
+        double tri6[6][3];
+        const double s10 = std::sqrt(10.0), tt = std::sqrt(38.0 - 44.0 * std::sqrt(2.0 / 5.0));
+        const double a[2] = {(8.0 - s10 + tt) / 18.0, (8.0 - s10 - tt) / 18.0};
+        const double sw = std::sqrt(213125.0 - 53320.0 * s10);
+        const double wgt[2] = {(620.0 + sw) / 3720.0, (620.0 - sw) / 3720.0};
+        for (int k = 0; k < 2; ++k) {
+            const double b = 1.0 - 2.0 * a[k];
+            const double pts[3][2] = {{a[k], a[k]}, {a[k], b}, {b, a[k]}};
+            for (int j = 0; j < 3; ++j) {
+                tri6[3 * k + j][0] = pts[j][0];
+                tri6[3 * k + j][1] = pts[j][1];
+                tri6[3 * k + j][2] = 0.5 * wgt[k];
+            }
+        }
+        FEMO_CUDA(cudaMemcpyToSymbolAsync(c_tri6, tri6, sizeof(tri6), 0, cudaMemcpyHostToDevice, p->stream));
+        std::vector<double> x, w;
+        gauss_legendre_01(5, x, w);
+        double gl5[5][2];
+        for (int i = 0; i < 5; ++i) { gl5[i][0] = x[i]; gl5[i][1] = w[i]; }
+        FEMO_CUDA(cudaMemcpyToSymbolAsync(c_gl5, gl5, sizeof(gl5), 0, cudaMemcpyHostToDevice, p->stream));
+        gauss_legendre_01(7, x, w);
+        double t49[49][3];
+        for (int i = 0; i < 7; ++i)
+            for (int j = 0; j < 7; ++j) {
+                t49[7 * i + j][0] = x[i];
+                t49[7 * i + j][1] = x[j] * (1.0 - x[i]);
+                t49[7 * i + j][2] = w[i] * w[j] * (1.0 - x[i]);
+            }
+        FEMO_CUDA(cudaMemcpyToSymbolAsync(c_tri49, t49, sizeof(t49), 0, cudaMemcpyHostToDevice, p->stream));
+        FEMO_CUDA(cudaStreamSynchronize(p->stream));
+    }
+
+    // work arena
+    size_t scratch = 0, tv = 0;
+    for (int w = 0; w <= p->nin; ++w) {
+        scratch = std::max<size_t>(scratch, p->pat[w].scratch_len);
+        tv = std::max<size_t>(tv, p->pat[w].nnz);
+    }
+    scratch = std::max<size_t>(scratch, p->vm_state_full.scratch_len);
+    for (int i = 0; i < p->nin; ++i) scratch = std::max<size_t>(scratch, p->vm_in[i].scratch_len);
+    scratch = std::max<size_t>(scratch, (size_t)M.ncells);
+    p->scratch_len = scratch;
+    p->tvals_len = tv;
+    p->d_scratch = p->wk.take<double>(scratch);
+    p->d_partials = p->wk.take<double>(3 * kMaxPartials);
+    p->d_scalars = p->wk.take<double>(S_COUNT);
+    p->kr_r = p->wk.take<double>(N);
+    p->kr_p = p->wk.take<double>(N);
+    p->kr_q = p->wk.take<double>(N);
+    p->kr_dinv = p->wk.take<double>(N);
+    p->kr_z = p->wk.take<double>(N);
+    p->kr_w = p->wk.take<double>(N);
+    p->nt_b = p->wk.take<double>(N);
+    p->nt_dx = p->wk.take<double>(N);
+    p->nt_vals = p->wk.take<double>(p->pat[0].nnz);
+    p->nt_vals_bc = p->wk.take<double>(p->pat[0].nnz);
+    p->d_tvals = p->wk.take<double>(tv);
+    if (!p->d_tvals) return set_err(FEMO_EINVAL, "work arena too small");
+    FEMO_CUDA(cudaMemsetAsync(p->d_scalars, 0, sizeof(double) * S_COUNT, p->stream));
+    if (!p->h_pinned) FEMO_CUDA(cudaMallocHost((void **)&p->h_pinned, sizeof(double) * 64));
+    FEMO_CUDA(cudaStreamSynchronize(p->stream));
+    p->uploaded = true;
+    return FEMO_OK;
+}
+
+int femo_set_coefficient(femo_problem *p, int slot, const double *d_values, int64_t n) {
+    if (!p || slot < 0 || slot > p->nin + p->naux) return set_err(FEMO_EINVAL, "femo_set_coefficient: bad slot");
+    int64_t want = (slot == 0) ? p->state.ndofs : (slot <= p->nin ? p->in[slot - 1].ndofs : p->aux[slot - 1 - p->nin].ndofs);
+    if (n != want) return set_err(FEMO_EINVAL, "femo_set_coefficient: size does not match the slot's space");
+    p->coef[slot] = d_values;
+    p->coefn[slot] = n;
+    return FEMO_OK;
+}
+
+int femo_problem_launch_count(const femo_problem *p, long long *count) {
+    if (!p || !count) return set_err(FEMO_EINVAL, "femo_problem_launch_count: null");
+    *count = p->launches;
+    return FEMO_OK;
+}
+
+// ---- assembly -------------------------------------------------------------
+int femo_assemble_residual(femo_problem *p, double *d_out) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!d_out) return set_err(FEMO_EINVAL, "femo_assemble_residual: null output");
+    if ((rc = run_elements(p, OP_RES))) return rc;
+    return segreduce(p, p->dvm_state_full, p->state.ndofs, d_out);
+}
+
+int femo_assemble_jacobian(femo_problem *p, double *d_vals, double *d_vals_bc) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!d_vals && !d_vals_bc) return set_err(FEMO_EINVAL, "femo_assemble_jacobian: both outputs null");
+    if ((rc = run_elements(p, OP_JAC))) return rc;
+    const DevPattern &D = p->dpat[0];
+    const int64_t nnz = p->pat[0].nnz;
+    k_segreduce_jac<<<grid_for(nnz), kThreads, 0, p->stream>>>(D.gptr, D.gsrc, p->d_scratch,
+                                                               p->has_bc ? D.bcflag : nullptr, D.col, p->d_bc_diag,
+                                                               d_vals, d_vals_bc, nnz);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
+int femo_assemble_dRdm(femo_problem *p, int slot, double *d_vals) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (slot < 0 || slot >= p->nin || !d_vals) return set_err(FEMO_EINVAL, "femo_assemble_dRdm: bad slot/output");
+    if ((rc = run_elements(p, OP_DRDM))) return rc;
+    const DevPattern &D = p->dpat[1 + slot];
+    const int64_t nnz = p->pat[1 + slot].nnz;
+    k_segreduce<<<grid_for(nnz), kThreads, 0, p->stream>>>(D.gptr, D.gsrc, p->d_scratch, d_vals, nnz);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
+int femo_newton_rhs(femo_problem *p, const double *d_vals, double *d_b) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!d_b) return set_err(FEMO_EINVAL, "femo_newton_rhs: null output");
+    if ((rc = femo_assemble_residual(p, d_b))) return rc;
+    if (p->has_bc) {
+        if (!d_vals) return set_err(FEMO_EINVAL, "femo_newton_rhs: Jacobian values required for lifting");
+        const int64_t nl = (int64_t)p->lift_rows.size();
+        const DevPattern &D = p->dpat[0];
+        k_newton_rhs<<<grid_for(nl), kThreads, 0, p->stream>>>(p->d_lift_rows, nl, D.rowptr, D.col, d_vals, p->d_bc_mark,
+                                                               p->d_bc_g, p->coef[0], d_b, -1.0);
+        p->launches++;
+        FEMO_CHECK_LAUNCH();
+    }
+    return FEMO_OK;
+}
+
+int femo_assemble_output(femo_problem *p, int out_id, double *h_value) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (out_id < 0 || out_id >= p->nout || !h_value) return set_err(FEMO_EINVAL, "femo_assemble_output: bad output id");
+    if ((rc = run_elements(p, OP_OUT))) return rc;
+    const int64_t n = p->mesh.ncells;
+    int g = red_grid(p, n);
+    k_sum<<<g, kThreads, 0, p->stream>>>(p->d_scratch, n, p->d_partials);
+    k_finalize<<<1, kThreads, 0, p->stream>>>(p->d_partials, g, p->d_scalars, S_TMP1);
+    p->launches += 2;
+    FEMO_CHECK_LAUNCH();
+    return read_scalars(p, S_TMP1, 1, h_value);
+}
+
+int femo_assemble_output_grad(femo_problem *p, int out_id, int slot, double *d_out) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (out_id < 0 || out_id >= p->nout || !d_out || slot < 0 || slot > p->nin)
+        return set_err(FEMO_EINVAL, "femo_assemble_output_grad: bad arguments");
+    if (slot == 0) {
+        if ((rc = run_elements(p, OP_OUT_DU))) return rc;
+        return segreduce(p, p->dvm_state_cells, p->state.ndofs, d_out);
+    }
+    if ((rc = run_elements(p, OP_OUT_DM))) return rc;
+    return segreduce(p, p->dvm_in[slot - 1], p->in[slot - 1].ndofs, d_out);
+}
+
+// ---- linear algebra -------------------------------------------------------
+int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_x, double *d_y, int transpose) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (which < 0 || which > p->nin || !d_vals || !d_x || !d_y) return set_err(FEMO_EINVAL, "femo_spmv: bad arguments");
+    const Pattern &P = p->pat[which];
+    const DevPattern &D = p->dpat[which];
+    if (!transpose) return launch_spmv<false>(p, D.lanes, D.rowptr, D.col, d_vals, d_x, d_y, P.nrows, nullptr);
+    k_permute<<<grid_for(P.nnz), kThreads, 0, p->stream>>>(D.t_perm, d_vals, p->d_tvals, P.nnz);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    return launch_spmv<false>(p, D.t_lanes, D.t_rowptr, D.t_col, p->d_tvals, d_x, d_y, P.ncols, nullptr);
+}
+
+static void default_krylov(femo_krylov_opts &o) {
+    if (o.rtol <= 0) o.rtol = 1e-10;
+    if (o.atol < 0) o.atol = 0;
+    if (o.max_it <= 0) o.max_it = 100000;
+    if (o.check_every <= 0) o.check_every = 1;
+}
+
+// Jacobi-preconditioned CG on the dR/du pattern; vals already in the layout to multiply with
+static int cg_solve(femo_problem *p, const double *vals, const double *b, double *x, femo_krylov_opts o,
+                    femo_krylov_info *info) {
+    default_krylov(o);
+    const int64_t n = p->state.ndofs;
+    const DevPattern &D = p->dpat[0];
+    cudaStream_t st = p->stream;
+    double *pz = p->d_partials, *pr = p->d_partials + kMaxPartials;
+    const int g = red_grid(p, n);
+    int rc, np = 0, spmvs = 0;
+    k_diag_inv<<<grid_for(n), kThreads, 0, st>>>(D.rowptr, D.col, vals, p->kr_dinv, n);
+    // ||b||^2
+    k_dot<<<g, kThreads, 0, st>>>(b, b, n, pz);
+    k_finalize<<<1, kThreads, 0, st>>>(pz, g, p->d_scalars, S_BB);
+    // r = b - A x ; p = dinv r
+    if ((rc = launch_spmv<false>(p, D.lanes, D.rowptr, D.col, vals, x, p->kr_q, n, nullptr))) return rc;
+    ++spmvs;
+    k_cg_init<<<g, kThreads, 0, st>>>(b, p->kr_q, p->kr_dinv, p->kr_r, p->kr_p, n, pz, pr);
+    k_cg_scalars<<<1, kThreads, 0, st>>>(2, p->d_scalars, pz, pr, g);
+    p->launches += 5;
+    FEMO_CHECK_LAUNCH();
+    double h[2];
+    FEMO_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_scalars + S_RR, sizeof(double), cudaMemcpyDeviceToHost, st));
+    FEMO_CUDA(cudaMemcpyAsync(p->h_pinned + 1, p->d_scalars + S_BB, sizeof(double), cudaMemcpyDeviceToHost, st));
+    FEMO_CUDA(cudaStreamSynchronize(st));
+    h[0] = p->h_pinned[0];
+    h[1] = p->h_pinned[1];
+    const double bnorm = std::sqrt(h[1]);
+    double rnorm = std::sqrt(h[0]);
+    const double tol = std::max(o.rtol * bnorm, o.atol);
+    int it = 0;
+    bool conv = rnorm <= tol;
+    while (!conv && it < o.max_it) {
+        const int chunk = std::min(o.check_every, o.max_it - it);
+        for (int k = 0; k < chunk; ++k) {
+            if ((rc = launch_spmv<true>(p, D.lanes, D.rowptr, D.col, vals, p->kr_p, p->kr_q, n, &np))) return rc;
+            k_cg_scalars<<<1, kThreads, 0, st>>>(0, p->d_scalars, p->d_partials, nullptr, np);
+            k_cg_update<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_p, p->kr_q, p->kr_dinv, x, p->kr_r, n, pz, pr);
+            k_cg_scalars<<<1, kThreads, 0, st>>>(1, p->d_scalars, pz, pr, g);
+            k_cg_dir<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_r, p->kr_dinv, p->kr_p, n);
+            p->launches += 4;
+            ++spmvs;
+        }
+        FEMO_CHECK_LAUNCH();
+        it += chunk;
+        double rr;
+        if ((rc = read_scalars(p, S_RR, 1, &rr))) return rc;
+        rnorm = std::sqrt(rr);
+        if (!(rnorm == rnorm)) break;  // NaN
+        conv = rnorm <= tol;
+    }
+    if (info) {
+        info->iterations = it;
+        info->converged = conv ? 1 : 0;
+        info->rnorm = rnorm;
+        info->bnorm = bnorm;
+        info->spmv_count = spmvs;
+    }
+    return FEMO_OK;
+}
+
+int femo_linear_solve(femo_problem *p, const double *d_vals, const double *d_b, double *d_x, int transpose,
+                      const femo_krylov_opts *opts, femo_krylov_info *info) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!d_vals || !d_b || !d_x) return set_err(FEMO_EINVAL, "femo_linear_solve: null pointer");
+    femo_krylov_opts o;
+    memset(&o, 0, sizeof(o));
+    if (opts) o = *opts;
+    if (o.method != 0) return set_err(FEMO_EINVAL, "femo_linear_solve: only CG (method 0) is available in this build");
+    const double *vals = d_vals;
+    if (transpose) {
+        const int64_t nnz = p->pat[0].nnz;
+        k_permute<<<grid_for(nnz), kThreads, 0, p->stream>>>(p->dpat[0].t_perm, d_vals, p->d_tvals, nnz);
+        p->launches++;
+        FEMO_CHECK_LAUNCH();
+        vals = p->d_tvals;
+    }
+    return cg_solve(p, vals, d_b, d_x, o, info);
+}
+
+int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton_info *info) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!opts) return set_err(FEMO_EINVAL, "femo_newton_solve: null options");
+    if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
+    const int64_t n = p->state.ndofs;
+    double *x = const_cast<double *>(p->coef[0]);  // the state slot is updated in place
+    cudaStream_t st = p->stream;
+    const bool snes = opts->kind == 1;
+    double *vals_bc = p->has_bc ? p->nt_vals_bc : p->nt_vals;
+    int it = 0, kit = 0, spmvs = 0, reason = 0;
+    double f0 = 0, fn = 0;
+    bool jac_valid = false;
+    auto eval_F = [&]() -> int {
+        int r;
+        jac_valid = false;
+        if (p->has_bc) {  // lifting needs the element columns of Dirichlet dofs at this state
+            if ((r = femo_assemble_jacobian(p, p->nt_vals, p->nt_vals_bc))) return r;
+            jac_valid = true;
+        }
+        if ((r = femo_newton_rhs(p, p->nt_vals, p->nt_b))) return r;
+        double s;
+        if ((r = norm2_sq(p, p->nt_b, n, &s))) return r;
+        fn = std::sqrt(s);
+        return FEMO_OK;
+    };
+    if ((rc = eval_F())) return rc;
+    f0 = fn;
+    if (fn < opts->atol) reason = 1;
+    while (!reason && it < opts->max_it) {
+        if (!jac_valid && (rc = femo_assemble_jacobian(p, p->nt_vals, nullptr))) return rc;
+        k_fill<<<red_grid(p, n), kThreads, 0, st>>>(0.0, p->nt_dx, n);
+        p->launches++;
+        femo_krylov_info ki;
+        memset(&ki, 0, sizeof(ki));
+        if ((rc = cg_solve(p, vals_bc, p->nt_b, p->nt_dx, opts->krylov, &ki))) return rc;
+        kit += ki.iterations;
+        spmvs += ki.spmv_count;
+        k_axpy<<<red_grid(p, n), kThreads, 0, st>>>(-1.0, p->nt_dx, x, n);
+        p->launches++;
+        FEMO_CHECK_LAUNCH();
+        if ((rc = eval_F())) return rc;
+        ++it;
+        if (fn < opts->atol) reason = 1;
+        else if (snes ? (fn <= opts->rtol * f0) : (f0 > 0 && fn / f0 < opts->rtol)) reason = 2;
+        else if (snes) {
+            double sy, sx;
+            if ((rc = norm2_sq(p, p->nt_dx, n, &sy))) return rc;
+            if ((rc = norm2_sq(p, x, n, &sx))) return rc;
+            if (std::sqrt(sy) < opts->stol * std::sqrt(sx)) reason = 3;
+        }
+    }
+    if (info) {
+        info->iterations = it;
+        info->converged = reason;
+        info->fnorm0 = f0;
+        info->fnorm = fn;
+        info->krylov_iterations = kit;
+        info->spmv_count = spmvs;
+    }
+    if (snes && !reason) return set_err(FEMO_ENOCONV, "SNES did not converge within max_it");
+    return FEMO_OK;
+}
+
+}  // extern "C"

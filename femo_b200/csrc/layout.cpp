@@ -1,0 +1,302 @@
+// layout.cpp -- see layout.hpp.
+#include "layout.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "../../include/femo_b200.h"
+
+namespace femo {
+
+static const int64_t kInt32Max = 2147483647LL;
+
+// ---------------------------------------------------------------------------
+// meshes
+// ---------------------------------------------------------------------------
+static void lattice_coords(int nx, int ny, const double lo[2], const double hi[2], Mesh &m) {
+    m.gdim = 2;
+    m.n[0] = nx;
+    m.n[1] = ny;
+    m.lo[0] = lo[0]; m.lo[1] = lo[1];
+    m.hi[0] = hi[0]; m.hi[1] = hi[1];
+    m.nverts = (int64_t)(nx + 1) * (ny + 1);
+    m.coords.resize(m.nverts * 2);
+    for (int iy = 0; iy <= ny; ++iy)
+        for (int ix = 0; ix <= nx; ++ix) {
+            int64_t v = (int64_t)iy * (nx + 1) + ix;
+            // same expression as the oracle (lo + (hi-lo)*i/n) so coordinates agree bit for bit
+            m.coords[2 * v] = lo[0] + (hi[0] - lo[0]) * (double)ix / (double)nx;
+            m.coords[2 * v + 1] = lo[1] + (hi[1] - lo[1]) * (double)iy / (double)ny;
+        }
+}
+
+void make_unit_square_tri(int nx, int ny, const double lo[2], const double hi[2], Mesh &m) {
+    m = Mesh();
+    m.kind = MESH_TRI;
+    m.nvpc = 3;
+    lattice_coords(nx, ny, lo, hi, m);
+    m.ncells = 2LL * nx * ny;
+    m.cells.resize(m.ncells * 3);
+    for (int iy = 0; iy < ny; ++iy)
+        for (int ix = 0; ix < nx; ++ix) {
+            int32_t v0 = iy * (nx + 1) + ix, v1 = v0 + 1, v2 = v0 + nx + 1, v3 = v2 + 1;
+            int64_t c = 2LL * ((int64_t)iy * nx + ix);
+            int32_t *a = &m.cells[c * 3];
+            a[0] = v0; a[1] = v1; a[2] = v3;   // "right" diagonal v0-v3
+            a[3] = v0; a[4] = v2; a[5] = v3;
+            // exterior facets; local facet i is opposite local vertex i
+            if (ix == nx - 1) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(0); }      // v1-v3
+            if (iy == 0)      { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(2); }      // v0-v1
+            if (iy == ny - 1) { m.bf_cell.push_back((int32_t)c + 1); m.bf_local.push_back(0); }  // v2-v3
+            if (ix == 0)      { m.bf_cell.push_back((int32_t)c + 1); m.bf_local.push_back(2); }  // v0-v2
+        }
+}
+
+void make_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2], Mesh &m) {
+    m = Mesh();
+    m.kind = MESH_QUAD;
+    m.nvpc = 4;
+    lattice_coords(nx, ny, lo, hi, m);
+    m.ncells = (int64_t)nx * ny;
+    m.cells.resize(m.ncells * 4);
+    for (int iy = 0; iy < ny; ++iy)
+        for (int ix = 0; ix < nx; ++ix) {
+            int32_t v0 = iy * (nx + 1) + ix;
+            int64_t c = (int64_t)iy * nx + ix;
+            int32_t *a = &m.cells[c * 4];
+            a[0] = v0; a[1] = v0 + 1; a[2] = v0 + nx + 1; a[3] = v0 + nx + 2;
+            // basix quadrilateral facets: (v0,v1) (v0,v2) (v1,v3) (v2,v3)
+            if (iy == 0)      { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(0); }
+            if (ix == 0)      { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(1); }
+            if (ix == nx - 1) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(2); }
+            if (iy == ny - 1) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(3); }
+        }
+}
+
+void make_interval(int n, double x0, double x1, Mesh &m) {
+    m = Mesh();
+    m.kind = MESH_INTERVAL;
+    m.nvpc = 2;
+    m.gdim = 1;
+    m.n[0] = n;
+    m.lo[0] = x0;
+    m.hi[0] = x1;
+    m.nverts = n + 1;
+    m.ncells = n;
+    m.coords.resize(n + 1);
+    for (int i = 0; i <= n; ++i) m.coords[i] = x0 + (x1 - x0) * (double)i / (double)n;
+    m.cells.resize(2 * (size_t)n);
+    for (int i = 0; i < n; ++i) { m.cells[2 * i] = i; m.cells[2 * i + 1] = i + 1; }
+    // facet k of an interval is its vertex k
+    m.bf_cell.push_back(0); m.bf_local.push_back(0);
+    m.bf_cell.push_back(n - 1); m.bf_local.push_back(1);
+}
+
+void Space::init(const Mesh &m, int element_, int block_) {
+    element = element_;
+    block = block_;
+    if (element == EL_DG0) {
+        ndofs = m.ncells * block;
+        ndpc = block;
+    } else {
+        if (element == EL_HERMITE3) block = 2;  // (value, reference derivative) per vertex
+        ndofs = m.nverts * block;
+        ndpc = m.nvpc * block;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// incidences: for every dof of a space, the (block, local index, entity) triples
+// that touch it, in ascending (block, local, entity) order.
+// ---------------------------------------------------------------------------
+struct Incidence {
+    std::vector<int64_t> ptr;   // ndofs+1
+    std::vector<int32_t> ent;   // entity within its block
+    std::vector<int16_t> blk;   // block id
+    std::vector<int16_t> loc;   // local dof index
+};
+
+static void build_incidence(const Mesh &m, const Space &s, const std::vector<IntegralBlock> &blocks, Incidence &inc) {
+    const int nd = s.ndpc;
+    inc.ptr.assign(s.ndofs + 1, 0);
+    std::vector<int32_t> d(nd);
+    for (size_t b = 0; b < blocks.size(); ++b)
+        for (int64_t e = 0; e < blocks[b].ne; ++e) {
+            int64_t cell = blocks[b].ent_cell ? blocks[b].ent_cell[e] : e;
+            s.cell_dofs(m, cell, d.data());
+            for (int a = 0; a < nd; ++a) inc.ptr[d[a] + 1]++;
+        }
+    for (int64_t i = 0; i < s.ndofs; ++i) inc.ptr[i + 1] += inc.ptr[i];
+    int64_t tot = inc.ptr[s.ndofs];
+    inc.ent.resize(tot);
+    inc.blk.resize(tot);
+    inc.loc.resize(tot);
+    std::vector<int64_t> pos(inc.ptr.begin(), inc.ptr.end() - 1);
+    // (block, local, entity) loop order => every dof's list is sorted the same way
+    for (size_t b = 0; b < blocks.size(); ++b)
+        for (int a = 0; a < nd; ++a)
+            for (int64_t e = 0; e < blocks[b].ne; ++e) {
+                int64_t cell = blocks[b].ent_cell ? blocks[b].ent_cell[e] : e;
+                int32_t dof;
+                if (s.element == EL_DG0) dof = (int32_t)(cell * s.block + a);
+                else dof = m.cells[cell * m.nvpc + a / s.block] * s.block + a % s.block;
+                int64_t q = pos[dof]++;
+                inc.ent[q] = (int32_t)e;
+                inc.blk[q] = (int16_t)b;
+                inc.loc[q] = (int16_t)a;
+            }
+}
+
+void build_vecmap(const Mesh &m, const Space &s, const std::vector<IntegralBlock> &blocks, VecMap &out) {
+    Incidence inc;
+    build_incidence(m, s, blocks, inc);
+    std::vector<int64_t> off(blocks.size() + 1, 0);
+    for (size_t b = 0; b < blocks.size(); ++b) off[b + 1] = off[b] + blocks[b].ne * s.ndpc;
+    out.n = s.ndofs;
+    out.scratch_len = off[blocks.size()];
+    out.ncontrib = inc.ptr[s.ndofs];
+    if (out.scratch_len > kInt32Max || out.ncontrib > kInt32Max) throw LayoutError{FEMO_ELIMIT, "vector map exceeds int32"};
+    out.ptr.resize(s.ndofs + 1);
+    out.src.resize(out.ncontrib);
+    for (int64_t i = 0; i <= s.ndofs; ++i) out.ptr[i] = (int32_t)inc.ptr[i];
+#pragma omp parallel for schedule(static)
+    for (int64_t q = 0; q < out.ncontrib; ++q) {
+        int b = inc.blk[q];
+        out.src[q] = (int32_t)(off[b] + (int64_t)inc.loc[q] * blocks[b].ne + inc.ent[q]);
+    }
+}
+
+void build_pattern(const Mesh &m, const Space &rs, const Space &cs, const std::vector<IntegralBlock> &blocks,
+                   Pattern &out) {
+    Incidence inc;
+    build_incidence(m, rs, blocks, inc);
+    const int nr = rs.ndpc, nc = cs.ndpc;
+    const int64_t N = rs.ndofs;
+    std::vector<int64_t> off(blocks.size() + 1, 0);
+    for (size_t b = 0; b < blocks.size(); ++b) off[b + 1] = off[b] + blocks[b].ne * (int64_t)nr * nc;
+    out = Pattern();
+    out.nrows = N;
+    out.ncols = cs.ndofs;
+    out.scratch_len = off[blocks.size()];
+    out.ncontrib = inc.ptr[N] * nc;
+    if (out.scratch_len > kInt32Max || out.ncontrib > kInt32Max)
+        throw LayoutError{FEMO_ELIMIT, "matrix gather map exceeds int32 (use a smaller mesh per GPU)"};
+
+    // pass 1: nnz per row
+    std::vector<int64_t> rp(N + 1, 0);
+#pragma omp parallel
+    {
+        std::vector<int32_t> cols, d(nc);
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < N; ++i) {
+            cols.clear();
+            for (int64_t q = inc.ptr[i]; q < inc.ptr[i + 1]; ++q) {
+                const IntegralBlock &B = blocks[inc.blk[q]];
+                int64_t cell = B.ent_cell ? B.ent_cell[inc.ent[q]] : inc.ent[q];
+                cs.cell_dofs(m, cell, d.data());
+                cols.insert(cols.end(), d.begin(), d.end());
+            }
+            std::sort(cols.begin(), cols.end());
+            rp[i + 1] = std::unique(cols.begin(), cols.end()) - cols.begin();
+        }
+    }
+    for (int64_t i = 0; i < N; ++i) rp[i + 1] += rp[i];
+    out.nnz = rp[N];
+    if (out.nnz > kInt32Max) throw LayoutError{FEMO_ELIMIT, "nnz exceeds int32"};
+    out.rowptr.resize(N + 1);
+    for (int64_t i = 0; i <= N; ++i) out.rowptr[i] = (int32_t)rp[i];
+    out.col.resize(out.nnz);
+    out.gptr.resize(out.nnz + 1);
+    out.gsrc.resize(out.ncontrib);
+    out.gptr[out.nnz] = (int32_t)out.ncontrib;
+
+    // pass 2: columns + gather map; row i's contributions start at inc.ptr[i]*nc
+#pragma omp parallel
+    {
+        std::vector<int64_t> pairs;  // (col << 32) | src
+        std::vector<int32_t> d(nc);
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < N; ++i) {
+            pairs.clear();
+            for (int64_t q = inc.ptr[i]; q < inc.ptr[i + 1]; ++q) {
+                int b = inc.blk[q];
+                const IntegralBlock &B = blocks[b];
+                int64_t e = inc.ent[q];
+                int64_t cell = B.ent_cell ? B.ent_cell[e] : e;
+                cs.cell_dofs(m, cell, d.data());
+                for (int c = 0; c < nc; ++c) {
+                    int64_t src = off[b] + ((int64_t)inc.loc[q] * nc + c) * B.ne + e;
+                    pairs.push_back(((int64_t)d[c] << 32) | src);
+                }
+            }
+            std::sort(pairs.begin(), pairs.end());
+            int64_t t = rp[i] - 1, g = inc.ptr[i] * nc;
+            int32_t last = -1;
+            for (size_t k = 0; k < pairs.size(); ++k, ++g) {
+                int32_t cj = (int32_t)(pairs[k] >> 32);
+                if (cj != last) {
+                    ++t;
+                    out.col[t] = cj;
+                    out.gptr[t] = (int32_t)g;
+                    last = cj;
+                }
+                out.gsrc[g] = (int32_t)(pairs[k] & 0xffffffffLL);
+            }
+        }
+    }
+
+    // transpose bookkeeping
+    out.square_symmetric = (&rs == &cs) || (rs.element == cs.element && rs.block == cs.block && rs.ndofs == cs.ndofs);
+    out.t_perm.resize(out.nnz);
+    if (out.square_symmetric) {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < N; ++i)
+            for (int64_t t = rp[i]; t < rp[i + 1]; ++t) {
+                int32_t j = out.col[t];
+                const int32_t *b = &out.col[rp[j]], *e = &out.col[rp[j + 1]];
+                const int32_t *f = std::lower_bound(b, e, (int32_t)i);
+                out.t_perm[t] = (int32_t)(f - out.col.data());  // entry (j,i)
+            }
+    } else {
+        out.t_rowptr.assign(out.ncols + 1, 0);
+        for (int64_t t = 0; t < out.nnz; ++t) out.t_rowptr[out.col[t] + 1]++;
+        for (int64_t j = 0; j < out.ncols; ++j) out.t_rowptr[j + 1] += out.t_rowptr[j];
+        out.t_col.resize(out.nnz);
+        std::vector<int32_t> pos(out.t_rowptr.begin(), out.t_rowptr.end() - 1);
+        for (int64_t i = 0; i < N; ++i)
+            for (int64_t t = rp[i]; t < rp[i + 1]; ++t) {
+                int32_t q = pos[out.col[t]]++;
+                out.t_col[q] = (int32_t)i;
+                out.t_perm[q] = (int32_t)t;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------
+void gauss_legendre_01(int m, std::vector<double> &x, std::vector<double> &w) {
+    x.resize(m);
+    w.resize(m);
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i < m; ++i) {
+        double z = std::cos(pi * (i + 0.75) / (m + 0.5));  // Chebyshev guess on [-1,1]
+        double pp = 1.0;
+        for (int it = 0; it < 100; ++it) {
+            double p1 = 1.0, p2 = 0.0;
+            for (int j = 0; j < m; ++j) {
+                double p3 = p2;
+                p2 = p1;
+                p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0);
+            }
+            pp = m * (z * p1 - p2) / (z * z - 1.0);
+            double dz = p1 / pp;
+            z -= dz;
+            if (std::fabs(dz) < 1e-16) break;
+        }
+        // descending z -> store ascending on [0,1]
+        x[m - 1 - i] = 0.5 * (z + 1.0);
+        w[m - 1 - i] = 1.0 / ((1.0 - z * z) * pp * pp);  // = 0.5 * 2/((1-z^2) pp^2)
+    }
+}
+
+}  // namespace femo

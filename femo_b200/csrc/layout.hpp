@@ -1,0 +1,89 @@
+// layout.hpp -- host-side mesh, dofmap, sparsity pattern and segmented-reduction
+// map builders (pure C++, no CUDA; exercised by the CPU test-suite).
+//
+// Replaces what the reference obtains from dolfinx mesh creation
+// (femo/fea/utils_dolfinx.py:136-153), FunctionSpace dofmaps and
+// create_matrix / sparsity patterns (utils_dolfinx.py:390 and implicitly in
+// every assemble_matrix(form) at :185,195,575).  Numbering is the canonical
+// lattice order described in DESIGN.md; every integer array built here is
+// compared with `==` against the oracle in tests/test_layout.py.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace femo {
+
+enum MeshKind { MESH_INTERVAL = 1, MESH_TRI = 2, MESH_QUAD = 3 };
+enum Element { EL_DG0 = 0, EL_VERTEX = 1 /* P1 / Q1: one node per vertex */, EL_HERMITE3 = 2 };
+
+struct Mesh {
+    int kind = 0, gdim = 0, nvpc = 0;
+    int64_t ncells = 0, nverts = 0;
+    int n[3] = {0, 0, 0};
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    std::vector<double> coords;              // nverts*gdim, AoS
+    std::vector<int32_t> cells;              // ncells*nvpc, AoS
+    std::vector<int32_t> bf_cell, bf_local;  // exterior facets, sorted by (cell, local facet)
+};
+
+void make_unit_square_tri(int nx, int ny, const double lo[2], const double hi[2], Mesh &m);
+void make_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2], Mesh &m);
+void make_interval(int n, double x0, double x1, Mesh &m);
+
+// A finite-element space on a mesh: dof = block*node + comp, local index a*block+comp.
+struct Space {
+    int element = EL_VERTEX;
+    int block = 1;
+    int64_t ndofs = 0;
+    int ndpc = 0;  // dofs per cell
+    void init(const Mesh &m, int element_, int block_);
+    inline void cell_dofs(const Mesh &m, int64_t cell, int32_t *out) const {
+        if (element == EL_DG0) {
+            for (int c = 0; c < block; ++c) out[c] = (int32_t)(cell * block + c);
+        } else {
+            const int32_t *v = &m.cells[cell * m.nvpc];
+            for (int a = 0; a < m.nvpc; ++a)
+                for (int c = 0; c < block; ++c) out[a * block + c] = v[a] * block + c;
+        }
+    }
+};
+
+// One integral of a form: all cells, or a list of facets (each owned by a cell).
+// Element tensors of block b live in scratch at  off + k*ne + e  (SoA planes).
+struct IntegralBlock {
+    int64_t ne = 0;
+    const int32_t *ent_cell = nullptr;  // nullptr -> entity e is cell e
+};
+
+// Sorted segmented-reduction map for vectors: out[i] = sum scratch[src[ptr[i]..ptr[i+1])]
+struct VecMap {
+    int64_t n = 0, ncontrib = 0, scratch_len = 0;
+    std::vector<int32_t> ptr, src;
+};
+
+// CSR pattern + matrix gather map + transpose bookkeeping.
+struct Pattern {
+    int64_t nrows = 0, ncols = 0, nnz = 0, ncontrib = 0, scratch_len = 0;
+    std::vector<int32_t> rowptr, col;
+    std::vector<int32_t> gptr, gsrc;  // gptr has nnz+1 entries
+    bool square_symmetric = false;    // structurally symmetric: transpose shares rowptr/col
+    std::vector<int32_t> t_rowptr, t_col;  // transposed CSR (empty when square_symmetric)
+    std::vector<int32_t> t_perm;           // transposed entry tt takes vals[t_perm[tt]]
+};
+
+// Build the vector map of `space` over `blocks` (K = ndpc planes per block).
+void build_vecmap(const Mesh &m, const Space &space, const std::vector<IntegralBlock> &blocks, VecMap &out);
+// Build pattern + gather map for rows in `rs`, cols in `cs` (K = ndpc_r*ndpc_c planes per block).
+void build_pattern(const Mesh &m, const Space &rs, const Space &cs, const std::vector<IntegralBlock> &blocks,
+                   Pattern &out);
+
+// m-point Gauss-Legendre on [0,1] (own Newton iteration; no tables).
+void gauss_legendre_01(int m, std::vector<double> &x, std::vector<double> &w);
+
+struct LayoutError {
+    int code;
+    std::string msg;
+};
+
+}  // namespace femo

@@ -1,0 +1,253 @@
+"""Object wrappers over the C ABI.  torch tensors are used ONLY as device
+buffers (allocation, H2D/D2H copies, stream handles); every computation is a
+libfemo_b200 call.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, KrylovOpts, KrylovInfo, NewtonOpts, NewtonInfo
+
+FAMILY_POISSON_P1 = 1
+FAMILY_NLPOISSON_P1 = 2
+FAMILY_EB_BEAM = 3
+FAMILY_SIMP_Q1 = 4
+
+
+def device_count():
+    return lib.femo_device_count()
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class EngineMesh:
+    """Host-side structured mesh (replaces dolfinx.mesh.create_*)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        s = (C.c_int64 * 6)()
+        check(lib.femo_mesh_sizes(self._h, s))
+        self.ncells, self.nverts, self.nvpc, self.gdim, self.nbfacets, self.kind = [int(v) for v in s]
+
+    @classmethod
+    def unit_square(cls, nx, ny=None, lo=(0.0, 0.0), hi=(1.0, 1.0)):
+        ny = nx if ny is None else ny
+        h = C.c_void_p()
+        check(lib.femo_mesh_create_unit_square(int(nx), int(ny), (C.c_double * 2)(*lo), (C.c_double * 2)(*hi), C.byref(h)))
+        m = cls(h)
+        m.shape, m.lo, m.hi = (nx, ny), tuple(lo), tuple(hi)
+        return m
+
+    @classmethod
+    def rectangle_quad(cls, lo, hi, nx, ny):
+        h = C.c_void_p()
+        check(lib.femo_mesh_create_rectangle_quad(int(nx), int(ny), (C.c_double * 2)(*lo), (C.c_double * 2)(*hi), C.byref(h)))
+        m = cls(h)
+        m.shape, m.lo, m.hi = (nx, ny), tuple(lo), tuple(hi)
+        return m
+
+    @classmethod
+    def interval(cls, n, x0, x1):
+        h = C.c_void_p()
+        check(lib.femo_mesh_create_interval(int(n), float(x0), float(x1), C.byref(h)))
+        m = cls(h)
+        m.shape, m.lo, m.hi = (n,), (x0,), (x1,)
+        return m
+
+    def coords(self):
+        out = np.empty((self.nverts, self.gdim), dtype=np.float64)
+        check(lib.femo_mesh_copy(self._h, 0, _np_ptr(out)))
+        return out
+
+    def cells(self):
+        out = np.empty((self.ncells, self.nvpc), dtype=np.int32)
+        check(lib.femo_mesh_copy(self._h, 1, _np_ptr(out)))
+        return out
+
+    def exterior_facets(self):
+        c = np.empty(self.nbfacets, dtype=np.int32)
+        l = np.empty(self.nbfacets, dtype=np.int32)
+        check(lib.femo_mesh_copy(self._h, 2, _np_ptr(c)))
+        check(lib.femo_mesh_copy(self._h, 3, _np_ptr(l)))
+        return c, l
+
+    def __del__(self):
+        if getattr(self, '_h', None):
+            lib.femo_mesh_destroy(self._h)
+            self._h = None
+
+
+class EngineProblem:
+    """One form family instantiated on a mesh: dofmaps, CSR patterns and gather
+    maps on the host; after `upload()` the device-resident assembly / solve path."""
+
+    def __init__(self, mesh, family, params=()):
+        self.mesh = mesh
+        self.family = family
+        h = C.c_void_p()
+        pa = (C.c_double * max(1, len(params)))(*params)
+        check(lib.femo_problem_create(mesh._h, int(family), pa, len(params), C.byref(h)))
+        self._h = h
+        s = (C.c_int64 * 16)()
+        check(lib.femo_problem_sizes(self._h, s))
+        self.N, self.nin, self.naux, self.nout = int(s[0]), int(s[1]), int(s[2]), int(s[3])
+        self.M = [int(s[4 + i]) for i in range(self.nin)]
+        self.aux_sizes = [int(s[8 + i]) for i in range(self.naux)]
+        self.uploaded = False
+        self._keep = {}       # tensors whose pointers the engine borrows
+        self.device = None
+
+    # -- host-side layout queries ----------------------------------------
+    def pattern_info(self, which):
+        info = (C.c_int64 * 4)()
+        check(lib.femo_problem_pattern_info(self._h, which, info))
+        return dict(rows=int(info[0]), cols=int(info[1]), nnz=int(info[2]), ncontrib=int(info[3]))
+
+    def pattern(self, which):
+        i = self.pattern_info(which)
+        rowptr = np.empty(i['rows'] + 1, dtype=np.int32)
+        col = np.empty(i['nnz'], dtype=np.int32)
+        check(lib.femo_problem_pattern(self._h, which, _np_ptr(rowptr), _np_ptr(col)))
+        return rowptr, col
+
+    def gather_map(self, which):
+        i = self.pattern_info(which)
+        ptr = np.empty(i['nnz'] + 1, dtype=np.int32)
+        src = np.empty(i['ncontrib'], dtype=np.int32)
+        check(lib.femo_problem_gather_map(self._h, which, _np_ptr(ptr), _np_ptr(src)))
+        return ptr, src
+
+    def set_bc(self, dof_lists, g=None):
+        dof_lists = [np.ascontiguousarray(d, dtype=np.int32).ravel() for d in dof_lists]
+        ptr = np.zeros(len(dof_lists) + 1, dtype=np.int32)
+        ptr[1:] = np.cumsum([d.size for d in dof_lists])
+        dofs = np.concatenate(dof_lists) if dof_lists else np.zeros(0, dtype=np.int32)
+        dofs = np.ascontiguousarray(dofs, dtype=np.int32)
+        gp = None
+        if g is not None:
+            g = np.ascontiguousarray(np.broadcast_to(np.asarray(g, dtype=np.float64), (self.N,)))
+            gp = _np_ptr(g)
+        check(lib.femo_problem_set_bc(self._h, _np_ptr(dofs), _np_ptr(ptr), len(dof_lists), gp))
+
+    # -- device ------------------------------------------------------------
+    def upload(self, device=0):
+        import torch
+        if not torch.cuda.is_available() or device_count() == 0:
+            raise _lib.FemoError(-2, 'femo_b200 needs a CUDA device (sm_100a); there is no CPU path')
+        self.device = torch.device('cuda', device)
+        sb, wb = C.c_size_t(), C.c_size_t()
+        check(lib.femo_problem_device_bytes(self._h, C.byref(sb), C.byref(wb)))
+        self._static = torch.empty(sb.value, dtype=torch.uint8, device=self.device)
+        self._work = torch.empty(wb.value, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+        check(lib.femo_problem_upload(self._h, device, C.c_void_p(stream), C.c_void_p(self._static.data_ptr()),
+                                      sb.value, C.c_void_p(self._work.data_ptr()), wb.value))
+        self.uploaded = True
+        self.static_bytes, self.work_bytes = sb.value, wb.value
+        return self
+
+    def new_vector(self, n, fill=None):
+        import torch
+        if fill is None:
+            return torch.empty(n, dtype=torch.float64, device=self.device)
+        return torch.full((n,), float(fill), dtype=torch.float64, device=self.device)
+
+    def to_device(self, array):
+        import torch
+        return torch.as_tensor(np.ascontiguousarray(array, dtype=np.float64)).to(self.device)
+
+    def set_coefficient(self, slot, tensor):
+        assert tensor.dtype.is_floating_point and tensor.element_size() == 8 and tensor.is_contiguous()
+        check(lib.femo_set_coefficient(self._h, slot, C.c_void_p(tensor.data_ptr()), tensor.numel()))
+        self._keep[slot] = tensor
+
+    def coefficient(self, slot):
+        return self._keep.get(slot)
+
+    def launch_count(self):
+        n = C.c_longlong()
+        check(lib.femo_problem_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def assemble_residual(self, out=None):
+        out = self.new_vector(self.N) if out is None else out
+        check(lib.femo_assemble_residual(self._h, self._p(out)))
+        return out
+
+    def assemble_jacobian(self, plain=True, bc=False, out=None, out_bc=None):
+        nnz = self.pattern_info(0)['nnz']
+        if plain and out is None:
+            out = self.new_vector(nnz)
+        if bc and out_bc is None:
+            out_bc = self.new_vector(nnz)
+        check(lib.femo_assemble_jacobian(self._h, self._p(out), self._p(out_bc)))
+        return out, out_bc
+
+    def assemble_dRdm(self, slot, out=None):
+        out = self.new_vector(self.pattern_info(1 + slot)['nnz']) if out is None else out
+        check(lib.femo_assemble_dRdm(self._h, slot, self._p(out)))
+        return out
+
+    def newton_rhs(self, vals, out=None):
+        out = self.new_vector(self.N) if out is None else out
+        check(lib.femo_newton_rhs(self._h, self._p(vals), self._p(out)))
+        return out
+
+    def assemble_output(self, k=0):
+        v = C.c_double()
+        check(lib.femo_assemble_output(self._h, k, C.byref(v)))
+        return v.value
+
+    def assemble_output_grad(self, k, slot, out=None):
+        n = self.N if slot == 0 else self.M[slot - 1]
+        out = self.new_vector(n) if out is None else out
+        check(lib.femo_assemble_output_grad(self._h, k, slot, self._p(out)))
+        return out
+
+    def spmv(self, which, vals, x, transpose=False, out=None):
+        i = self.pattern_info(which)
+        n = i['cols'] if transpose else i['rows']
+        out = self.new_vector(n) if out is None else out
+        check(lib.femo_spmv(self._h, which, self._p(vals), self._p(x), self._p(out), 1 if transpose else 0))
+        return out
+
+    def linear_solve(self, vals, b, x=None, transpose=False, rtol=1e-10, atol=0.0, max_it=100000, check_every=1):
+        x = self.new_vector(self.N, 0.0) if x is None else x
+        o = KrylovOpts(rtol=rtol, atol=atol, max_it=max_it, precond=0, cheb_degree=0, method=0, restart=0,
+                       check_every=check_every)
+        info = KrylovInfo()
+        check(lib.femo_linear_solve(self._h, self._p(vals), self._p(b), self._p(x), 1 if transpose else 0,
+                                    C.byref(o), C.byref(info)))
+        return x, dict(iterations=info.iterations, converged=bool(info.converged), rnorm=info.rnorm,
+                       bnorm=info.bnorm, spmv_count=info.spmv_count)
+
+    def newton_solve(self, kind='Newton', atol=None, rtol=None, stol=1e-8, max_it=None, krylov_rtol=1e-10,
+                     krylov_max_it=100000, check_every=1):
+        """kind 'Newton' = dolfinx NewtonSolver defaults of the reference (3 fixed
+        iterations, utils_dolfinx.py:419-425); 'SNES' = PETSc newtonls (:376-416)."""
+        snes = (kind == 'SNES')
+        o = NewtonOpts()
+        o.kind = 1 if snes else 0
+        o.atol = (1e-13 if snes else 1e-50) if atol is None else atol
+        o.rtol = (1e-13 if snes else 1e-30) if rtol is None else rtol
+        o.stol = stol
+        o.max_it = (100 if snes else 3) if max_it is None else max_it
+        o.krylov = KrylovOpts(rtol=krylov_rtol, atol=0.0, max_it=krylov_max_it, precond=0, cheb_degree=0, method=0,
+                              restart=0, check_every=check_every)
+        info = NewtonInfo()
+        check(lib.femo_newton_solve(self._h, C.byref(o), C.byref(info)))
+        return dict(iterations=info.iterations, converged=info.converged, fnorm0=info.fnorm0, fnorm=info.fnorm,
+                    krylov_iterations=info.krylov_iterations, spmv_count=info.spmv_count)
+
+    def __del__(self):
+        if getattr(self, '_h', None):
+            lib.femo_problem_destroy(self._h)
+            self._h = None

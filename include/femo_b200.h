@@ -1,0 +1,181 @@
+/* femo_b200.h -- C ABI of libfemo_b200.so, the B200-native state/adjoint engine
+ * that backs femo's FEA / CSDL operations.
+ *
+ * The reference (RuruX/femo) has no FFI: its hot path is a set of Python
+ * one-liners that delegate to dolfinx 0.5.1 / PETSc / MUMPS.  Each entry point
+ * below names the reference call it replaces (paths relative to the reference
+ * root).  The Python host (femo_b200/fea, femo_b200/csdl_opt) binds these with
+ * ctypes; INTEGRATION.md shows the stub a femo maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative FEMO_E* code on failure;
+ *     femo_last_error() gives the message of the calling thread's last failure.
+ *   - `d_*` pointers are DEVICE pointers owned by the caller (torch tensors on
+ *     the Python side), `h_*` / unprefixed pointers are host memory.
+ *   - all floating point is IEEE fp64, all indices int32 (dolfinx/PETSc default).
+ *   - calls enqueue on the problem's stream; only functions that return a host
+ *     scalar (or are documented to) synchronise.
+ *   - there is NO CPU fallback: device entry points fail with FEMO_ENODEVICE
+ *     when no CUDA device is present.
+ */
+#ifndef FEMO_B200_H
+#define FEMO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEMO_OK 0
+#define FEMO_EINVAL -1    /* bad argument                                    */
+#define FEMO_ENODEVICE -2 /* CUDA device required but not present / not set  */
+#define FEMO_ECUDA -3     /* CUDA runtime error                              */
+#define FEMO_ESTATE -4    /* call order violated (e.g. not uploaded, no BC)  */
+#define FEMO_ENOCONV -5   /* nonlinear solve did not converge (SNES semantics) */
+#define FEMO_ELIMIT -6    /* problem exceeds int32 index range               */
+
+typedef struct femo_mesh femo_mesh;
+typedef struct femo_problem femo_problem;
+
+/* ---- form families ("Form families") ---------------- */
+#define FEMO_FAMILY_POISSON_P1 1   /* examples/poisson_opt/run_poisson_opt.py:32-38,74-76 */
+#define FEMO_FAMILY_NLPOISSON_P1 2 /* examples/nonlinear_poisson_opt/run_nonlinear_poisson_opt.py:88-116,140-142 */
+#define FEMO_FAMILY_EB_BEAM 3      /* examples/beam_thickness_opt/run_thickness_opt_cantilever_beam.py:71-85 */
+#define FEMO_FAMILY_SIMP_Q1 4      /* examples/beam_topo_opt/run_topo_opt_cantilever_beam.py:62-86 */
+
+/* matrix selector `which`: 0 = dR/du (N x N), 1+s = dR/dm_s (N x M_s) */
+
+int femo_version(void);
+const char *femo_last_error(void);
+/* number of visible CUDA devices (0 on a CPU-only box; never fails) */
+int femo_device_count(void);
+
+/* ---- meshes: host only; replace dolfinx.mesh.create_* ---------------------
+ * femo/fea/utils_dolfinx.py:136-153 (createUnitSquareMesh, createIntervalMesh,
+ * createRectangleMesh).  Canonical lattice numbering, see DESIGN.md. */
+int femo_mesh_create_unit_square(int nx, int ny, const double lo[2], const double hi[2], femo_mesh **out);
+int femo_mesh_create_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2], femo_mesh **out);
+int femo_mesh_create_interval(int n, double x0, double x1, femo_mesh **out);
+/* sizes[0..5] = ncells, nverts, verts/cell, gdim, n exterior facets, mesh kind */
+int femo_mesh_sizes(const femo_mesh *m, int64_t sizes[6]);
+/* what: 0 coords (double nverts*gdim), 1 cells (int32 ncells*nvpc),
+ *       2 exterior-facet cell (int32), 3 exterior-facet local index (int32) */
+int femo_mesh_copy(const femo_mesh *m, int what, void *out);
+void femo_mesh_destroy(femo_mesh *m);
+
+/* ---- problem layout: host only ---------------------------------------------
+ * Replaces dolfinx FunctionSpace/dofmap construction, create_matrix /
+ * sparsity-pattern build (utils_dolfinx.py:390 and every assemble_matrix(form)
+ * at :185,195,575) with a pattern and deterministic cell->nnz gather map built
+ * ONCE (reference quirk B12).  The mesh is copied; it may be destroyed after. */
+int femo_problem_create(const femo_mesh *m, int family, const double *params, int nparams, femo_problem **out);
+void femo_problem_destroy(femo_problem *p);
+/* sizes[0]=N (state dofs) [1]=n inputs [2]=n aux fields [3]=n outputs
+ * [4..7]=M_s (input s dofs) [8..11]=aux field dofs [12]=n exterior facets */
+int femo_problem_sizes(const femo_problem *p, int64_t sizes[16]);
+/* info[0]=rows [1]=cols [2]=nnz [3]=number of element contributions */
+int femo_problem_pattern_info(const femo_problem *p, int which, int64_t info[4]);
+/* CSR pattern, column-sorted: rowptr (rows+1), col (nnz) */
+int femo_problem_pattern(const femo_problem *p, int which, int32_t *rowptr, int32_t *col);
+/* sorted segmented-reduction map: entry t sums scratch[src[ptr[t]..ptr[t+1])] */
+int femo_problem_gather_map(const femo_problem *p, int which, int32_t *ptr, int32_t *src);
+/* dirichletbc objects (fea_dolfinx.py:169-176): `dofs` is the concatenation of
+ * nlists dof arrays, list_ptr (nlists+1) delimits them; a dof listed k times
+ * gets diagonal k (dolfinx set_diagonal adds once per bc object).  g (N values,
+ * or NULL for homogeneous) holds the prescribed values. */
+int femo_problem_set_bc(femo_problem *p, const int32_t *dofs, const int32_t *list_ptr, int nlists, const double *g);
+
+/* ---- device residency ------------------------------------------------------
+ * Bytes the caller must provide: static (maps, patterns) and work (scratch,
+ * Krylov vectors).  Upload copies the layout into d_static.  stream is a
+ * cudaStream_t (NULL = legacy default stream). */
+int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_t *work_bytes);
+int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_static, size_t static_bytes,
+                        void *d_work, size_t work_bytes);
+/* coefficient slots: 0 = state, 1..nin = inputs, then aux fields.  Borrowed
+ * device pointer, read at every assemble (update()/setFuncArray,
+ * utils_dolfinx.py:161-167,300-311). */
+int femo_set_coefficient(femo_problem *p, int slot, const double *d_values, int64_t n);
+
+/* number of kernels this problem has launched so far (bench.py's gpu_launches) */
+int femo_problem_launch_count(const femo_problem *p, long long *count);
+
+/* ---- assembly --------------------------------------------------------------*/
+/* assembleVector(residual_form): no BC applied (utils_dolfinx.py:175-179,
+ * state_model.py:85). */
+int femo_assemble_residual(femo_problem *p, double *d_out);
+/* assembleMatrix(dR_du) and assembleSystem(dR_du, res, bcs) in ONE pass
+ * (utils_dolfinx.py:181-202; state_model.py:132,149-151; quirk B8): writes the
+ * un-BC'd values to d_vals and/or the BC'd copy (rows+cols zeroed, diagonal =
+ * bc multiplicity) to d_vals_bc; either may be NULL. */
+int femo_assemble_jacobian(femo_problem *p, double *d_vals, double *d_vals_bc);
+/* assembleMatrix(derivative(res, m_s)), never BC'd (state_model.py:136-146). */
+int femo_assemble_dRdm(femo_problem *p, int slot, double *d_vals);
+/* NonlinearProblem.F / NonlinearSNESProblem.F (utils_dolfinx.py:352-367):
+ * b = R(x) - scale*A(:,bc)(g-x), b[bc] = scale*(g-x) with scale=-1; d_vals is
+ * the un-BC'd Jacobian at the same state. */
+int femo_newton_rhs(femo_problem *p, const double *d_vals, double *d_b);
+/* assemble(form, dim=0) (utils_dolfinx.py:169-173,204-213; output_model.py:69-75).
+ * Synchronises. */
+int femo_assemble_output(femo_problem *p, int out_id, double *h_value);
+/* assemble(derivative(form, arg), dim=1) (output_model.py:77-87); slot as in
+ * femo_set_coefficient (0 = wrt state). */
+int femo_assemble_output_grad(femo_problem *p, int out_id, int slot, double *d_out);
+
+/* ---- linear algebra --------------------------------------------------------*/
+/* computeMatVecProductFwd / Bwd (utils_dolfinx.py:256-264,275-287):
+ * y = A x (transpose=0) or y = A^T x (transpose=1). */
+int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_x, double *d_y, int transpose);
+
+typedef struct femo_krylov_opts {
+    double rtol;      /* ||r|| <= rtol*||b||   */
+    double atol;      /* or ||r|| <= atol      */
+    int max_it;
+    int precond;      /* 0 Jacobi, 1 Chebyshev(cheb_degree) on Jacobi-scaled A */
+    int cheb_degree;
+    int method;       /* 0 CG, 1 GMRES(restart) */
+    int restart;
+    int check_every;  /* residual-norm host check period (>=1) */
+} femo_krylov_opts;
+
+typedef struct femo_krylov_info {
+    int iterations;
+    int converged;
+    double rnorm, bnorm;
+    int spmv_count;
+} femo_krylov_info;
+
+/* Replaces KSP preonly + LU(MUMPS): solveKSP_mumps / setUpKSP_MUMPS and the
+ * explicit transpose(A) (utils_dolfinx.py:241-245,476-512; fea_dolfinx.py:
+ * 192-222).  Solves A x = b or A^T x = b on the dR/du pattern; x is the
+ * initial guess on entry.  Synchronises. */
+int femo_linear_solve(femo_problem *p, const double *d_vals, const double *d_b, double *d_x, int transpose,
+                      const femo_krylov_opts *opts, femo_krylov_info *info);
+
+typedef struct femo_newton_opts {
+    int kind;        /* 0 = dolfinx NewtonSolver (utils_dolfinx.py:419-449), 1 = PETSc SNES newtonls (:376-416) */
+    double atol, rtol, stol;
+    int max_it;
+    femo_krylov_opts krylov;
+} femo_newton_opts;
+
+typedef struct femo_newton_info {
+    int iterations;
+    int converged;    /* SNES: 1 abs, 2 rel, 3 stol; Newton: 1 if tolerance met */
+    double fnorm0, fnorm;
+    int krylov_iterations; /* summed over Newton steps */
+    int spmv_count;
+} femo_newton_info;
+
+/* FEA.solve -> solveNonlinear (fea_dolfinx.py:178-189, utils_dolfinx.py:319-333).
+ * The state is coefficient slot 0 (updated in place).  SNES kind returns
+ * FEMO_ENOCONV at max_it (error_on_nonconvergence, :399); Newton kind never
+ * fails (quirk B1).  Synchronises. */
+int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMO_B200_H */

@@ -1,0 +1,255 @@
+"""Form families of the reference's examples, restated as explicit quadrature
+loops the way FFCx would generate them (TEST INFRASTRUCTURE ONLY).
+
+Every family exposes integral blocks (see assembly.py) for
+  residual(u, m...)          R                       state_model.py:85
+  jacobian(u, m...)          dR/du                   state_model.py:129-132
+  dRdm(slot, u, m...)        dR/dm                   state_model.py:136-141
+  output(k, ...) / output_du / output_dm             output_model.py:69-87
+with the quadrature degrees of SURVEY.md Appendix A.3.  Gateaux derivatives
+(UFL `derivative`, utils_dolfinx.py:313-314) are derived by hand and checked
+against finite differences / sympy in tests/test_oracle_*.py.
+"""
+import numpy as np
+from . import quadrature as quad
+from .mesh import dofmap
+
+
+# --------------------------------------------------------------------------
+# P1 triangle geometry
+# --------------------------------------------------------------------------
+class _TriP1:
+    """Affine triangle geometry + P1 tabulation shared by the 2-D families."""
+
+    def __init__(self, mesh):
+        assert mesh.kind == 'triangle'
+        self.mesh = mesh
+        X = mesh.coords[mesh.cells]                       # (nc,3,2)
+        self.X = X
+        J = np.stack([X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]], axis=2)   # (nc,2,2) columns = edges
+        det = J[:, 0, 0] * J[:, 1, 1] - J[:, 0, 1] * J[:, 1, 0]
+        self.detJ = np.abs(det)                           # = 2*area
+        Jinv = np.empty_like(J)
+        Jinv[:, 0, 0], Jinv[:, 0, 1] = J[:, 1, 1] / det, -J[:, 0, 1] / det
+        Jinv[:, 1, 0], Jinv[:, 1, 1] = -J[:, 1, 0] / det, J[:, 0, 0] / det
+        gref = np.array([[-1.0, -1.0], [1.0, 0.0], [0.0, 1.0]])        # d phi_a / d xi
+        # physical gradients g[c,a,:] = Jinv^T gref[a]
+        self.G = np.einsum('ckd,ak->cad', Jinv, gref)
+        self.cell_dofs, self.N = dofmap(mesh, 'CG', 1)
+        self.dg_dofs, self.M = dofmap(mesh, 'DG', 0)
+
+    @staticmethod
+    def phi(pts):
+        return np.stack([1.0 - pts[:, 0] - pts[:, 1], pts[:, 0], pts[:, 1]], axis=1)   # (nq,3)
+
+    def xq(self, pts):
+        return np.einsum('qa,cad->cqd', self.phi(pts), self.X)                          # (nc,nq,2)
+
+
+# --------------------------------------------------------------------------
+# config 1: Poisson source-term optimisation
+# --------------------------------------------------------------------------
+class PoissonP1(_TriP1):
+    """examples/poisson_opt/run_poisson_opt.py:32-38 (residual), :74-76 (output).
+
+    R = int grad(u).grad(v) - f v dx ;  J = int 1/2 (u-u_ex)^2 + alpha/2 f^2 dx
+    u, u_ex in CG1, f in DG0, alpha = 1e-6 (:29,108).
+    """
+    name = 'poisson_p1'
+    n_outputs = 1
+
+    def __init__(self, mesh, alpha=1e-6, u_ex=None):
+        super().__init__(mesh)
+        self.alpha = alpha
+        self.u_ex = np.zeros(self.N) if u_ex is None else np.asarray(u_ex, dtype=np.float64)
+
+    def residual(self, u, f):
+        pts, w = quad.triangle(1)
+        ph = self.phi(pts)
+        ue = u[self.cell_dofs]
+        gu = np.einsum('ca,cad->cd', ue, self.G)
+        Re = np.zeros((self.mesh.ncells, 3))
+        for q in range(len(w)):
+            wq = w[q] * self.detJ
+            Re += wq[:, None] * (np.einsum('cd,cad->ca', gu, self.G) - f[:, None] * ph[q][None, :])
+        return [(self.cell_dofs, None, Re)]
+
+    def jacobian(self, u, f):
+        pts, w = quad.triangle(0)
+        Ae = np.zeros((self.mesh.ncells, 3, 3))
+        for q in range(len(w)):
+            Ae += (w[q] * self.detJ)[:, None, None] * np.einsum('cad,cbd->cab', self.G, self.G)
+        return [(self.cell_dofs, self.cell_dofs, Ae)]
+
+    def dRdm(self, slot, u, f):
+        assert slot == 0
+        pts, w = quad.triangle(1)
+        ph = self.phi(pts)
+        De = np.zeros((self.mesh.ncells, 3, 1))
+        for q in range(len(w)):
+            De[:, :, 0] -= (w[q] * self.detJ)[:, None] * ph[q][None, :]
+        return [(self.cell_dofs, self.dg_dofs, De)]
+
+    def output(self, k, u, f):
+        pts, w = quad.triangle(2)
+        ph = self.phi(pts)
+        e = (u - self.u_ex)[self.cell_dofs]
+        val = np.zeros(self.mesh.ncells)
+        for q in range(len(w)):
+            eq = e @ ph[q]
+            val += w[q] * self.detJ * (0.5 * eq * eq + 0.5 * self.alpha * f * f)
+        return [val]
+
+    def output_du(self, k, u, f):
+        pts, w = quad.triangle(2)
+        ph = self.phi(pts)
+        e = (u - self.u_ex)[self.cell_dofs]
+        ge = np.zeros((self.mesh.ncells, 3))
+        for q in range(len(w)):
+            ge += (w[q] * self.detJ * (e @ ph[q]))[:, None] * ph[q][None, :]
+        return [(self.cell_dofs, None, ge)]
+
+    def output_dm(self, k, slot, u, f):
+        pts, w = quad.triangle(0)
+        ge = np.zeros((self.mesh.ncells, 1))
+        for q in range(len(w)):
+            ge[:, 0] += w[q] * self.detJ * self.alpha * f
+        return [(self.dg_dofs, None, ge)]
+
+
+# --------------------------------------------------------------------------
+# config 2: nonlinear Poisson with symmetric Nitsche boundary terms
+# --------------------------------------------------------------------------
+def u_exact_nlp(x):
+    """examples/nonlinear_poisson_opt/run_nonlinear_poisson_opt.py:144-145."""
+    return np.sin(2.0 * np.pi * x[..., 0]) * np.sin(np.pi * x[..., 1])
+
+
+class NonlinearPoissonP1(_TriP1):
+    """examples/nonlinear_poisson_opt/run_nonlinear_poisson_opt.py.
+
+    interior (:88-95):  int grad(u).grad(v) + u^3 v - f v dx        (degree 4, 6 pts)
+    boundary (:97-116, sym=True, beta=10):
+        - int (grad(u).n) v ds + int (u_ex-u)(grad(v).n) ds
+        + beta/h_E int (u-u_ex) v ds                                (degree 9, 5-pt Gauss)
+    output (:140-142): int 1/2 (u-u_ex)^2 + alpha_1/2 f^2 dx, u_ex a UFL expression
+        (degree 12 -> collapsed Gauss rule; same rule for dJ/du)
+    """
+    name = 'nlpoisson_p1'
+    n_outputs = 1
+
+    def __init__(self, mesh, alpha=6e-7, beta=10.0):
+        super().__init__(mesh)
+        self.alpha, self.beta = alpha, beta
+        self.h = mesh.cell_diameter()
+        fc, fl = mesh.exterior_facets()
+        self.fc, self.fl = fc, fl
+        lf = mesh.local_facets[fl]                                   # (nf,2) local vertex ids
+        P = self.X[fc, lf[:, 0]]
+        Q = self.X[fc, lf[:, 1]]
+        O = self.X[fc, fl]                                           # opposite vertex
+        t = Q - P
+        self.flen = np.linalg.norm(t, axis=1)
+        nrm = np.stack([t[:, 1], -t[:, 0]], axis=1) / self.flen[:, None]
+        sgn = np.sign(np.einsum('fd,fd->f', nrm, P - O))
+        self.fn = nrm * sgn[:, None]                                 # outward unit normal
+        self.fP, self.fQ, self.flv = P, Q, lf
+        self.fdofs = self.cell_dofs[fc]
+
+    # -- facet tabulation -------------------------------------------------
+    def _facet_q(self):
+        s, w = quad.interval(9)
+        nf = self.fc.size
+        ph = np.zeros((nf, len(w), 3))
+        ar = np.arange(nf)
+        for q in range(len(w)):
+            ph[ar, q, self.flv[:, 0]] = 1.0 - s[q]
+            ph[ar, q, self.flv[:, 1]] = s[q]
+        xq = self.fP[:, None, :] + s[None, :, None] * (self.fQ - self.fP)[:, None, :]
+        return ph, xq, w
+
+    def residual(self, u, f):
+        pts, w = quad.triangle(4)
+        ph = self.phi(pts)
+        ue = u[self.cell_dofs]
+        gu = np.einsum('ca,cad->cd', ue, self.G)
+        Re = np.zeros((self.mesh.ncells, 3))
+        for q in range(len(w)):
+            uq = ue @ ph[q]
+            wq = w[q] * self.detJ
+            Re += wq[:, None] * (np.einsum('cd,cad->ca', gu, self.G)
+                                 + (uq ** 3 - f)[:, None] * ph[q][None, :])
+        # exterior facets
+        phf, xq, wf = self._facet_q()
+        uf = u[self.fdofs]
+        Gf = self.G[self.fc]
+        gn = np.einsum('fad,fd->fa', Gf, self.fn)                     # grad(phi_a).n
+        dudn = np.einsum('fa,fa->f', uf, gn)
+        bh = self.beta / self.h[self.fc]
+        Rf = np.zeros((self.fc.size, 3))
+        for q in range(len(wf)):
+            wq = wf[q] * self.flen
+            uq = np.einsum('fa,fa->f', uf, phf[:, q])
+            ex = u_exact_nlp(xq[:, q])
+            Rf += wq[:, None] * (-dudn[:, None] * phf[:, q] + (ex - uq)[:, None] * gn
+                                 + (bh * (uq - ex))[:, None] * phf[:, q])
+        return [(self.cell_dofs, None, Re), (self.fdofs, None, Rf)]
+
+    def jacobian(self, u, f):
+        pts, w = quad.triangle(4)
+        ph = self.phi(pts)
+        ue = u[self.cell_dofs]
+        K = np.einsum('cad,cbd->cab', self.G, self.G)
+        Ae = np.zeros((self.mesh.ncells, 3, 3))
+        for q in range(len(w)):
+            uq = ue @ ph[q]
+            wq = w[q] * self.detJ
+            Ae += wq[:, None, None] * (K + (3.0 * uq * uq)[:, None, None]
+                                       * np.outer(ph[q], ph[q])[None])
+        phf, xq, wf = self._facet_q()
+        Gf = self.G[self.fc]
+        gn = np.einsum('fad,fd->fa', Gf, self.fn)
+        bh = self.beta / self.h[self.fc]
+        Af = np.zeros((self.fc.size, 3, 3))
+        for q in range(len(wf)):
+            wq = wf[q] * self.flen
+            p = phf[:, q]
+            Af += wq[:, None, None] * (-p[:, :, None] * gn[:, None, :] - gn[:, :, None] * p[:, None, :]
+                                       + bh[:, None, None] * p[:, :, None] * p[:, None, :])
+        return [(self.cell_dofs, self.cell_dofs, Ae), (self.fdofs, self.fdofs, Af)]
+
+    def dRdm(self, slot, u, f):
+        assert slot == 0
+        pts, w = quad.triangle(1)
+        ph = self.phi(pts)
+        De = np.zeros((self.mesh.ncells, 3, 1))
+        for q in range(len(w)):
+            De[:, :, 0] -= (w[q] * self.detJ)[:, None] * ph[q][None, :]
+        return [(self.cell_dofs, self.dg_dofs, De)]
+
+    def output(self, k, u, f):
+        pts, w = quad.triangle(12)
+        ph = self.phi(pts)
+        xq = self.xq(pts)
+        ue = u[self.cell_dofs]
+        val = np.zeros(self.mesh.ncells)
+        for q in range(len(w)):
+            eq = ue @ ph[q] - u_exact_nlp(xq[:, q])
+            val += w[q] * self.detJ * 0.5 * eq * eq
+        val += 0.5 * self.detJ * 0.5 * self.alpha * f * f
+        return [val]
+
+    def output_du(self, k, u, f):
+        pts, w = quad.triangle(12)
+        ph = self.phi(pts)
+        xq = self.xq(pts)
+        ue = u[self.cell_dofs]
+        ge = np.zeros((self.mesh.ncells, 3))
+        for q in range(len(w)):
+            eq = ue @ ph[q] - u_exact_nlp(xq[:, q])
+            ge += (w[q] * self.detJ * eq)[:, None] * ph[q][None, :]
+        return [(self.cell_dofs, None, ge)]
+
+    def output_dm(self, k, slot, u, f):
+        ge = (0.5 * self.detJ * self.alpha * f)[:, None]
+        return [(self.dg_dofs, None, ge)]

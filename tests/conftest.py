@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def cuda_device():
+    import torch
+    from femo_b200 import engine
+    if not torch.cuda.is_available() or engine.device_count() == 0:
+        pytest.fail('gpu-marked test selected but no CUDA device is visible (no CPU fallback exists)')
+    return 0
