@@ -1,0 +1,72 @@
+"""Shared builders for the parity tests: one engine problem + the matching
+oracle family on the same canonical mesh and the same seeded inputs."""
+import numpy as np
+import scipy.sparse as sp
+
+from femo_b200 import engine as E
+from oracle import mesh as om, families as fam, assembly as asm, solvers
+
+
+def square_boundary_lists(coords):
+    """The four dof lists of examples/poisson_opt/run_poisson_opt.py:124-135."""
+    x = coords
+    return [np.nonzero(np.isclose(x[:, 0], 0.0, atol=1e-6))[0], np.nonzero(np.isclose(x[:, 0], 1.0, atol=1e-6))[0],
+            np.nonzero(np.isclose(x[:, 1], 0.0, atol=1e-6))[0], np.nonzero(np.isclose(x[:, 1], 1.0, atol=1e-6))[0]]
+
+
+class Case:
+    def __init__(self, famid, n, ny=None, seed=0, bc='auto', g=None, upload=True, device=0):
+        self.famid, self.n = famid, n
+        self.emesh = E.EngineMesh.unit_square(n, ny)
+        self.omesh = om.unit_square_tri(n, ny)
+        rng = np.random.default_rng(seed)
+        if famid == 1:
+            self.F = fam.PoissonP1(self.omesh)
+            x = self.omesh.coords
+            self.F.u_ex = 1.0 / (2 * np.pi ** 2) * np.sin(np.pi * x[:, 0]) * np.sin(np.pi * x[:, 1])
+            use_bc = bc in ('auto', True)
+        else:
+            self.F = fam.NonlinearPoissonP1(self.omesh)
+            use_bc = bc is True
+        self.p = E.EngineProblem(self.emesh, famid)
+        self.bc = None
+        if use_bc:
+            lists = square_boundary_lists(self.omesh.coords)
+            gv = 0.0 if g is None else g
+            self.bc = asm.DirichletBC(self.F.N, lists, gv)
+            self.p.set_bc(lists, None if g is None else g)
+        self.u = rng.standard_normal(self.F.N)
+        self.f = rng.standard_normal(self.F.M)
+        self.sp = solvers.StatePath(self.F, self.bc)
+        if upload:
+            self.upload(device)
+
+    def upload(self, device=0):
+        p = self.p
+        p.upload(device)
+        self.d_u = p.to_device(self.u)
+        self.d_f = p.to_device(self.f)
+        p.set_coefficient(0, self.d_u)
+        p.set_coefficient(1, self.d_f)
+        if self.famid == 1:
+            self.d_uex = p.to_device(self.F.u_ex)
+            p.set_coefficient(2, self.d_uex)
+
+    def set_state(self, u):
+        self.u = np.asarray(u, dtype=np.float64)
+        self.d_u.copy_(self.p.to_device(self.u))
+
+    def set_input(self, f):
+        self.f = np.asarray(f, dtype=np.float64)
+        self.d_f.copy_(self.p.to_device(self.f))
+
+    def csr(self, which, vals):
+        rp, col = self.p.pattern(which)
+        i = self.p.pattern_info(which)
+        return sp.csr_matrix((vals.cpu().numpy(), col, rp), shape=(i['rows'], i['cols']))
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    den = np.max(np.abs(b))
+    return np.max(np.abs(a - b)) / (den if den > 0 else 1.0)

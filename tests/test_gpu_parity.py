@@ -1,0 +1,127 @@
+"""CUDA path vs oracle on identical meshes and seeded inputs, through the C ABI.
+
+Tolerances are BASELINE.json's: assembled residual / Jacobian values within
+1e-12 relative, states within solver tolerance, dJ/dm within 1e-8 relative."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from oracle import assembly as asm
+from _cases import Case, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.mark.parametrize('famid', [1, 2])
+@pytest.mark.parametrize('n,ny', [(1, 1), (4, 4), (16, 16), (33, 7)])
+def test_assembly_matches_oracle(cuda_device, famid, n, ny):
+    c = Case(famid, n, ny, seed=n)
+    F, p, m = c.F, c.p, [c.f]
+    R = p.assemble_residual().cpu().numpy()
+    assert relerr(R, asm.assemble_vector(F.residual(c.u, *m), F.N)) < TOL
+    vals, vals_bc = p.assemble_jacobian(plain=True, bc=True)
+    A = asm.assemble_matrix(F.jacobian(c.u, *m), (F.N, F.N), None)
+    Abc = asm.assemble_matrix(F.jacobian(c.u, *m), (F.N, F.N), c.bc)
+    assert relerr(vals.cpu().numpy(), A.data) < TOL
+    assert relerr(vals_bc.cpu().numpy(), Abc.data) < TOL
+    D = asm.assemble_matrix(F.dRdm(0, c.u, *m), (F.N, F.M), None)
+    assert relerr(p.assemble_dRdm(0).cpu().numpy(), D.data) < TOL
+    J = p.assemble_output(0)
+    Jo = asm.assemble_scalar(F.output(0, c.u, *m))
+    assert abs(J - Jo) <= TOL * abs(Jo)
+    gu = p.assemble_output_grad(0, 0).cpu().numpy()
+    assert relerr(gu, asm.assemble_vector(F.output_du(0, c.u, *m), F.N)) < TOL
+    gm = p.assemble_output_grad(0, 1).cpu().numpy()
+    assert relerr(gm, asm.assemble_vector(F.output_dm(0, 0, c.u, *m), F.M)) < TOL
+
+
+@pytest.mark.parametrize('famid,bc', [(1, True), (2, True), (2, False)])
+def test_newton_rhs_lifting(cuda_device, famid, bc):
+    rng = np.random.default_rng(5)
+    g = rng.standard_normal((17 + 1) ** 2)
+    c = Case(famid, 17, seed=3, bc=bc, g=g if bc else None)
+    vals, _ = c.p.assemble_jacobian(plain=True, bc=False)
+    b = c.p.newton_rhs(vals).cpu().numpy()
+    assert relerr(b, c.sp.newton_F(c.u, [c.f])) < TOL
+
+
+@pytest.mark.parametrize('famid', [1, 2])
+def test_spmv_forward_and_transposed(cuda_device, famid):
+    c = Case(famid, 21, 13, seed=2)
+    rng = np.random.default_rng(1)
+    vals, _ = c.p.assemble_jacobian()
+    A = c.csr(0, vals)
+    x = rng.standard_normal(c.F.N)
+    assert relerr(c.p.spmv(0, vals, c.p.to_device(x)).cpu().numpy(), A @ x) < 1e-13
+    assert relerr(c.p.spmv(0, vals, c.p.to_device(x), transpose=True).cpu().numpy(), A.T @ x) < 1e-13
+    dv = c.p.assemble_dRdm(0)
+    D = c.csr(1, dv)
+    xm = rng.standard_normal(c.F.M)
+    assert relerr(c.p.spmv(1, dv, c.p.to_device(xm)).cpu().numpy(), D @ xm) < 1e-13
+    assert relerr(c.p.spmv(1, dv, c.p.to_device(x), transpose=True).cpu().numpy(), D.T @ x) < 1e-13
+
+
+def test_transposed_solve_nonsymmetric_values(cuda_device):
+    """The adjoint solve must use the true transpose (quirk B3): perturb the
+    values so A != A^T on the symmetric pattern and compare with SuperLU."""
+    c = Case(1, 12, seed=7)
+    _, vals_bc = c.p.assemble_jacobian(plain=False, bc=True)
+    rng = np.random.default_rng(0)
+    v = vals_bc.cpu().numpy()
+    rp, col = c.p.pattern(0)
+    rows = np.repeat(np.arange(c.F.N), np.diff(rp))
+    v = v * (1.0 + 0.05 * rng.random(v.size) * (rows != col))
+    d_v = c.p.to_device(v)
+    A = c.csr(0, d_v)
+    b = rng.standard_normal(c.F.N)
+    # CG needs SPD: solve with the symmetric part (explicit zeros kept so data stays aligned)
+    AT = A.T.tocsr()
+    AT.sort_indices()
+    assert np.array_equal(AT.indices, A.indices)
+    vs = 0.5 * (A.data + AT.data)
+    As = c.csr(0, c.p.to_device(vs))
+    x, info = c.p.linear_solve(c.p.to_device(vs), c.p.to_device(b), transpose=True, rtol=1e-12)
+    assert info['converged'], info
+    assert relerr(x.cpu().numpy(), spla.spsolve(As.tocsc(), b)) < 1e-9
+    # and the transposed SpMV on the genuinely nonsymmetric values
+    y = c.p.spmv(0, d_v, c.p.to_device(b), transpose=True).cpu().numpy()
+    assert relerr(y, A.T @ b) < 1e-13
+
+
+@pytest.mark.parametrize('famid,kind', [(1, 'Newton'), (2, 'SNES'), (2, 'Newton')])
+def test_state_solve_matches_oracle(cuda_device, famid, kind):
+    c = Case(famid, 16, seed=4)
+    f = 0.1 * np.ones(c.F.M) if famid == 2 else c.f
+    c.set_input(f)
+    c.set_state(np.zeros(c.F.N))
+    info = c.p.newton_solve(kind=kind, krylov_rtol=1e-13)
+    u = c.d_u.cpu().numpy()
+    if kind == 'SNES':
+        uo, oinfo = c.sp.solve_snes(np.zeros(c.F.N), [f])
+    else:
+        uo, oinfo = c.sp.solve_newton(np.zeros(c.F.N), [f])
+        assert info['iterations'] == 3          # quirk B1
+    assert relerr(u, uo) < 1e-9
+    assert info['iterations'] == oinfo['iterations']
+
+
+@pytest.mark.parametrize('famid', [1, 2])
+def test_total_derivative_matches_oracle(cuda_device, famid):
+    """dJ/dm through the reference's callback chain."""
+    c = Case(famid, 16, seed=9)
+    f = 0.1 * np.ones(c.F.M) if famid == 2 else c.f
+    c.set_input(f)
+    c.set_state(np.zeros(c.F.N))
+    c.p.newton_solve(kind='SNES' if famid == 2 else 'Newton', krylov_rtol=1e-13)
+    u = c.d_u.cpu().numpy()
+    p = c.p
+    vals, vals_bc = p.assemble_jacobian(plain=True, bc=True)
+    dv = p.assemble_dRdm(0)
+    dJdu = p.assemble_output_grad(0, 0)
+    lam, info = p.linear_solve(vals_bc if c.bc is not None else vals, dJdu, transpose=True, rtol=1e-13)
+    assert info['converged']
+    g = p.assemble_output_grad(0, 1).cpu().numpy() - p.spmv(1, dv, lam, transpose=True).cpu().numpy()
+    (go,), lamo = c.sp.total_derivative(0, u, [f])
+    assert relerr(lam.cpu().numpy(), lamo) < 1e-8
+    assert relerr(g, go) < 1e-8
