@@ -61,8 +61,8 @@ struct DevPattern {
     int32_t *rowptr = nullptr, *col = nullptr, *gptr = nullptr, *gsrc = nullptr;
     int32_t *t_rowptr = nullptr, *t_col = nullptr, *t_perm = nullptr;
     uint8_t *bcflag = nullptr;
-    int lanes = 8;  // SpMV lanes per row, chosen from mean nnz/row
-    int t_lanes = 8;
+    int32_t *rb = nullptr, *t_rb = nullptr;  // SpMV row blocks
+    int nrb = 0, t_nrb = 0;
 };
 struct DevVecMap {
     int32_t *ptr = nullptr, *src = nullptr;

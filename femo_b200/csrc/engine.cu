@@ -100,39 +100,68 @@ __global__ void __launch_bounds__(kThreads) k_finalize(const double *__restrict_
 }
 
 // ===========================================================================
-// SpMV (K7): LANES threads cooperate on one row of a CSR matrix; a warp covers
-// 32/LANES consecutive rows so values/columns stream in contiguous chunks.
-// Optional fused dot(x, y) for CG (square matrices only).
+// SpMV (K7), CSR-stream: a CTA owns a block of consecutive rows whose nnz fit in
+// shared memory.  Phase 1 streams values/columns of the whole block with fully
+// coalesced, deeply unrolled loads (the addresses do not depend on the row
+// structure, so many loads are in flight per thread) and stores val*x[col] in
+// shared memory; phase 2 sums each row's products in a fixed order (one thread
+// per row; the 7-9 entry rows of FE matrices give conflict-free strides) and
+// writes y coalesced.  Optional fused dot(x, y) for CG.  Rows longer than the
+// staging capacity are strided over by the whole CTA.
 // ===========================================================================
-template <int LANES, bool DOT>
+template <bool DOT>
 __global__ void __launch_bounds__(kThreads)
-    k_spmv(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ vals,
-           const double *__restrict__ x, double *__restrict__ y, int64_t n, double *__restrict__ partials) {
-    constexpr int GPW = 32 / LANES;  // row groups per warp
-    const int lane = threadIdx.x & (LANES - 1);
-    const int gw = (threadIdx.x & 31) / LANES;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    k_spmv(const int32_t *__restrict__ rb, int nrb, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+           const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+           double *__restrict__ partials) {
+    __shared__ double prod[kSpmvCap];
+    __shared__ int32_t rp[kSpmvRows + 1];
+    const int tid = threadIdx.x;
     double dot = 0.0;
-    for (int64_t base = warp * GPW; base < n; base += nwarps * GPW) {
-        const int64_t r = base + gw;
-        int32_t s = 0, e = 0;
-        if (r < n) {
-            s = rowptr[r];
-            e = rowptr[r + 1];
-        }
-        double acc = 0.0;
-        for (int32_t t = s + lane; t < e; t += LANES) acc += ld_stream(vals + t) * __ldg(x + ld_stream(col + t));
+    for (int blk = blockIdx.x; blk < nrb; blk += gridDim.x) {
+        const int32_t r0 = rb[blk];
+        const int nr = rb[blk + 1] - r0;
+        for (int i = tid; i <= nr; i += kThreads) rp[i] = rowptr[r0 + i];
+        __syncthreads();
+        const int32_t s = rp[0], e = rp[nr];
+        if (e - s <= kSpmvCap) {
+            constexpr int U = 4;
+            for (int32_t base = s + tid; base < e; base += kThreads * U) {
+                int32_t c[U];
+                double v[U];
 #pragma unroll
-        for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0 && r < n) {
-            y[r] = acc;
-            if (DOT) dot += acc * __ldg(x + r);
+                for (int j = 0; j < U; ++j) {
+                    const int32_t t = base + j * kThreads;
+                    c[j] = (t < e) ? ld_stream(col + t) : 0;
+                    v[j] = (t < e) ? ld_stream(vals + t) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    const int32_t t = base + j * kThreads;
+                    if (t < e) prod[t - s] = v[j] * __ldg(x + c[j]);
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < nr; i += kThreads) {
+                double acc = 0.0;
+                for (int32_t k = rp[i] - s; k < rp[i + 1] - s; ++k) acc += prod[k];
+                y[r0 + i] = acc;
+                if (DOT) dot += acc * __ldg(x + r0 + i);
+            }
+        } else {  // a single long row: CTA-wide strided reduction (fixed order)
+            double acc = 0.0;
+            for (int32_t t = s + tid; t < e; t += kThreads) acc += ld_stream(vals + t) * __ldg(x + ld_stream(col + t));
+            acc = block_sum(acc);
+            if (tid == 0) {
+                y[r0] = acc;
+                if (DOT) dot += acc * __ldg(x + r0);
+            }
         }
+        __syncthreads();
     }
     if (DOT) {
         dot = block_sum(dot);
-        if (threadIdx.x == 0) partials[blockIdx.x] = dot;
+        if (tid == 0) partials[blockIdx.x] = dot;
     }
 }
 
@@ -356,35 +385,17 @@ static int segreduce(femo_problem *p, const DevVecMap &m, int64_t n, double *d_o
 }
 
 template <bool DOT>
-static int launch_spmv(femo_problem *p, int lanes, const int32_t *rowptr, const int32_t *col, const double *vals,
-                       const double *x, double *y, int64_t n, int *np_out) {
-    // persistent-style grid: 8 CTAs of 256 threads per SM keeps the active row window contiguous
-    int64_t rows_per_cta = (int64_t)kThreads / lanes;
-    int64_t g = (n + rows_per_cta - 1) / rows_per_cta;
+static int launch_spmv(femo_problem *p, const int32_t *rb, int nrb, const int32_t *rowptr, const int32_t *col,
+                       const double *vals, const double *x, double *y, int *np_out) {
+    // persistent grid: every SM holds 8 CTAs and walks the row blocks with a grid stride, so the
+    // rows in flight form one contiguous window (x stays L2-resident) and the dot partials are bounded
     int64_t cap = std::min<int64_t>((int64_t)p->num_sms * 8, kMaxPartials);
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
-    double *pp = p->d_partials;
-    cudaStream_t st = p->stream;
-    switch (lanes) {
-        case 2: k_spmv<2, DOT><<<grid, kThreads, 0, st>>>(rowptr, col, vals, x, y, n, pp); break;
-        case 4: k_spmv<4, DOT><<<grid, kThreads, 0, st>>>(rowptr, col, vals, x, y, n, pp); break;
-        case 8: k_spmv<8, DOT><<<grid, kThreads, 0, st>>>(rowptr, col, vals, x, y, n, pp); break;
-        case 16: k_spmv<16, DOT><<<grid, kThreads, 0, st>>>(rowptr, col, vals, x, y, n, pp); break;
-        default: k_spmv<32, DOT><<<grid, kThreads, 0, st>>>(rowptr, col, vals, x, y, n, pp); break;
-    }
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nrb, cap));
+    k_spmv<DOT><<<grid, kThreads, 0, p->stream>>>(rb, nrb, rowptr, col, vals, x, y, p->d_partials);
     p->launches++;
     if (np_out) *np_out = grid;
     FEMO_CHECK_LAUNCH();
     return FEMO_OK;
-}
-
-static int pick_lanes(int64_t nnz, int64_t nrows) {
-    double avg = nrows ? (double)nnz / (double)nrows : 1.0;
-    if (avg <= 2.5) return 2;
-    if (avg <= 5.0) return 4;
-    if (avg <= 12.0) return 8;
-    if (avg <= 24.0) return 16;
-    return 32;
 }
 
 static int read_scalars(femo_problem *p, int first, int count, double *h) {
@@ -615,6 +626,7 @@ static size_t pattern_bytes(const Pattern &P, bool bc) {
     b += Arena::need(P.rowptr.size(), 4) + Arena::need(P.col.size(), 4);
     b += Arena::need(P.gptr.size(), 4) + Arena::need(P.gsrc.size(), 4);
     b += Arena::need(P.t_rowptr.size(), 4) + Arena::need(P.t_col.size(), 4) + Arena::need(P.t_perm.size(), 4);
+    b += Arena::need(P.rb.size(), 4) + Arena::need(std::max<size_t>(1, P.t_rb.size()), 4);
     if (bc) b += Arena::need(P.nnz, 1);
     return b;
 }
@@ -696,8 +708,15 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
             if ((rc = up(p, D.t_rowptr, P.t_rowptr))) return rc;
             if ((rc = up(p, D.t_col, P.t_col))) return rc;
         }
-        D.lanes = pick_lanes(P.nnz, P.nrows);
-        D.t_lanes = pick_lanes(P.nnz, P.ncols);
+        if ((rc = up(p, D.rb, P.rb))) return rc;
+        D.nrb = (int)P.rb.size() - 1;
+        if (P.square_symmetric) {
+            D.t_rb = D.rb;
+            D.t_nrb = D.nrb;
+        } else {
+            if ((rc = up(p, D.t_rb, P.t_rb))) return rc;
+            D.t_nrb = (int)P.t_rb.size() - 1;
+        }
     }
     if (p->has_bc) {
         if ((rc = up(p, p->dpat[0].bcflag, p->bcflag))) return rc;
@@ -894,11 +913,11 @@ int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_
     if (which < 0 || which > p->nin || !d_vals || !d_x || !d_y) return set_err(FEMO_EINVAL, "femo_spmv: bad arguments");
     const Pattern &P = p->pat[which];
     const DevPattern &D = p->dpat[which];
-    if (!transpose) return launch_spmv<false>(p, D.lanes, D.rowptr, D.col, d_vals, d_x, d_y, P.nrows, nullptr);
+    if (!transpose) return launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, d_vals, d_x, d_y, nullptr);
     k_permute<<<grid_for(P.nnz), kThreads, 0, p->stream>>>(D.t_perm, d_vals, p->d_tvals, P.nnz);
     p->launches++;
     FEMO_CHECK_LAUNCH();
-    return launch_spmv<false>(p, D.t_lanes, D.t_rowptr, D.t_col, p->d_tvals, d_x, d_y, P.ncols, nullptr);
+    return launch_spmv<false>(p, D.t_rb, D.t_nrb, D.t_rowptr, D.t_col, p->d_tvals, d_x, d_y, nullptr);
 }
 
 static void default_krylov(femo_krylov_opts &o) {
@@ -923,7 +942,7 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     k_dot<<<g, kThreads, 0, st>>>(b, b, n, pz);
     k_finalize<<<1, kThreads, 0, st>>>(pz, g, p->d_scalars, S_BB);
     // r = b - A x ; p = dinv r
-    if ((rc = launch_spmv<false>(p, D.lanes, D.rowptr, D.col, vals, x, p->kr_q, n, nullptr))) return rc;
+    if ((rc = launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, vals, x, p->kr_q, nullptr))) return rc;
     ++spmvs;
     k_cg_init<<<g, kThreads, 0, st>>>(b, p->kr_q, p->kr_dinv, p->kr_r, p->kr_p, n, pz, pr);
     k_cg_scalars<<<1, kThreads, 0, st>>>(2, p->d_scalars, pz, pr, g);
@@ -943,7 +962,7 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     while (!conv && it < o.max_it) {
         const int chunk = std::min(o.check_every, o.max_it - it);
         for (int k = 0; k < chunk; ++k) {
-            if ((rc = launch_spmv<true>(p, D.lanes, D.rowptr, D.col, vals, p->kr_p, p->kr_q, n, &np))) return rc;
+            if ((rc = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, &np))) return rc;
             k_cg_scalars<<<1, kThreads, 0, st>>>(0, p->d_scalars, p->d_partials, nullptr, np);
             k_cg_update<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_p, p->kr_q, p->kr_dinv, x, p->kr_r, n, pz, pr);
             k_cg_scalars<<<1, kThreads, 0, st>>>(1, p->d_scalars, pz, pr, g);

@@ -271,6 +271,20 @@ void build_pattern(const Mesh &m, const Space &rs, const Space &cs, const std::v
                 out.t_perm[q] = (int32_t)t;
             }
     }
+    build_rowblocks(out.rowptr, out.nrows, out.rb);
+    if (!out.square_symmetric) build_rowblocks(out.t_rowptr, out.ncols, out.t_rb);
+}
+
+void build_rowblocks(const std::vector<int32_t> &rowptr, int64_t nrows, std::vector<int32_t> &rb) {
+    rb.clear();
+    rb.push_back(0);
+    int64_t r = 0;
+    while (r < nrows) {
+        int64_t e = r + 1;  // a block always holds at least one row (longer rows are strided in-kernel)
+        while (e < nrows && e - r < kSpmvRows && rowptr[e + 1] - rowptr[r] <= kSpmvCap) ++e;
+        rb.push_back((int32_t)e);
+        r = e;
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -70,7 +70,13 @@ struct Pattern {
     bool square_symmetric = false;    // structurally symmetric: transpose shares rowptr/col
     std::vector<int32_t> t_rowptr, t_col;  // transposed CSR (empty when square_symmetric)
     std::vector<int32_t> t_perm;           // transposed entry tt takes vals[t_perm[tt]]
+    // SpMV row blocks: block k covers rows [rb[k], rb[k+1]) with <= kSpmvCap nnz and <= kSpmvRows rows
+    std::vector<int32_t> rb, t_rb;
 };
+
+constexpr int kSpmvCap = 2048;   // products staged in shared memory per row block
+constexpr int kSpmvRows = 512;   // rows per block (row pointers staged too)
+void build_rowblocks(const std::vector<int32_t> &rowptr, int64_t nrows, std::vector<int32_t> &rb);
 
 // Build the vector map of `space` over `blocks` (K = ndpc planes per block).
 void build_vecmap(const Mesh &m, const Space &space, const std::vector<IntegralBlock> &blocks, VecMap &out);
