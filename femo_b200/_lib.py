@@ -68,6 +68,7 @@ SIGNATURES = {
     'femo_assemble_jacobian': (C.c_int, [_P, _P, _P]),
     'femo_assemble_dRdm': (C.c_int, [_P, C.c_int, _P]),
     'femo_newton_rhs': (C.c_int, [_P, _P, _P]),
+    'femo_assemble_system_rhs': (C.c_int, [_P, _P, _P]),
     'femo_assemble_output': (C.c_int, [_P, C.c_int, _DP]),
     'femo_assemble_output_grad': (C.c_int, [_P, C.c_int, C.c_int, _P]),
     'femo_spmv': (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int]),

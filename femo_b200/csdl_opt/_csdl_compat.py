@@ -1,0 +1,225 @@
+"""Stand-ins for the slice of CSDL / python_csdl_backend the femo operations use.
+
+csdl, python_csdl_backend and modopt are not installable offline (SURVEY.md
+section 8c).  If csdl is importable its classes are used; otherwise these
+minimal bases provide `parameters.declare`, `add_input/add_output`,
+`declare_derivatives`, `Model.add/create_input/...` and a `Simulator` that
+calls the five operation callbacks in the backend's order:
+run() -> solve_residual_equations / compute; compute_totals() ->
+compute_derivatives, apply_inverse_jacobian('rev'), compute_jacvec_product('rev').
+"""
+import numpy as np
+
+try:                                    # pragma: no cover - csdl is absent in this image
+    from csdl import Model, CustomImplicitOperation, CustomExplicitOperation   # noqa: F401
+    import csdl                                                                 # noqa: F401
+    HAVE_CSDL = True
+except Exception:
+    HAVE_CSDL = False
+
+    class _Parameters(dict):
+        def declare(self, name, default=None, types=None, **kw):
+            self.setdefault(name, default)
+
+    class _Op:
+        def __init__(self, **kwargs):
+            self.parameters = _Parameters()
+            self.initialize()
+            self.parameters.update(kwargs)
+            self.input_meta, self.output_meta = {}, {}
+            self.define()
+
+        def initialize(self):
+            pass
+
+        def add_input(self, name, shape=(1,), val=1.0):
+            self.input_meta[name] = dict(shape=shape, val=val)
+
+        def add_output(self, name, shape=(1,), val=1.0):
+            self.output_meta[name] = dict(shape=shape, val=val)
+
+        def declare_derivatives(self, of, wrt, **kw):
+            pass
+
+    class CustomImplicitOperation(_Op):
+        pass
+
+    class CustomExplicitOperation(_Op):
+        pass
+
+    class _Var:
+        def __init__(self, name, shape, val):
+            self.name, self.shape, self.val = name, shape, val
+
+    class Model:
+        def __init__(self, **kwargs):
+            self.parameters = _Parameters()
+            self.initialize()
+            self.parameters.update(kwargs)
+            self.ops = []                # (op, [input names], [output names]) in execution order
+            self.inputs = {}             # created inputs: name -> value
+            self.declared = {}
+            self.design_variables, self.objectives, self.constraints = {}, {}, {}
+            self._defined = False
+
+        def initialize(self):
+            pass
+
+        def define(self):
+            pass
+
+        def _ensure_defined(self):
+            if not self._defined:
+                self._defined = True
+                self.define()
+
+        def declare_variable(self, name, shape=(1,), val=1.0):
+            v = _Var(name, shape, val)
+            self.declared[name] = v
+            return v
+
+        def create_input(self, name, shape=(1,), val=1.0):
+            shape = (shape,) if np.isscalar(shape) else tuple(shape)
+            self.inputs[name] = np.broadcast_to(np.asarray(val, dtype=np.float64), shape).copy()
+            return _Var(name, shape, val)
+
+        def register_output(self, name, var):
+            if isinstance(var, _CustomResult):
+                self.ops.append((var.op, list(var.arg_names), name))
+            return _Var(name, None, None)
+
+        def print_var(self, var):
+            pass
+
+        def add(self, submodel, name=None):
+            submodel._ensure_defined()
+            self.ops += submodel.ops
+            for k, v in submodel.inputs.items():
+                self.inputs.setdefault(k, v)
+            for k, v in submodel.declared.items():
+                self.declared.setdefault(k, v)
+
+        def add_design_variable(self, name, lower=None, upper=None, scaler=None):
+            self.design_variables[name] = dict(lower=lower, upper=upper, scaler=scaler)
+
+        def add_objective(self, name, scaler=None):
+            self.objectives[name] = dict(scaler=scaler)
+
+        def add_constraint(self, name, lower=None, upper=None, equals=None, scaler=None):
+            self.constraints[name] = dict(lower=lower, upper=upper, equals=equals, scaler=scaler)
+
+    class _CustomResult:
+        def __init__(self, op, arg_names):
+            self.op, self.arg_names = op, arg_names
+
+    class _Csdl:
+        """csdl.custom(*args, op=...) -> handle consumed by Model.register_output."""
+        @staticmethod
+        def custom(*args, op=None):
+            return _CustomResult(op, [a.name for a in args])
+
+    csdl = _Csdl()
+
+
+class Simulator:
+    """python_csdl_backend.Simulator stand-in for models made of femo operations.
+
+    Variables live in one flat (promoted) namespace, as in the reference's
+    examples; `sim['submodel.var']` resolves by the last path component.
+    """
+
+    def __init__(self, model, analytics=False, **kw):
+        model._ensure_defined()
+        self.model = model
+        self.vars = {k: np.array(v, dtype=np.float64) for k, v in model.inputs.items()}
+        for op, args, out in model.ops:
+            for a in args:
+                if a not in self.vars:
+                    shape = op.input_meta[a]['shape']
+                    d = model.declared.get(a)
+                    val = d.val if d is not None else 1.0
+                    self.vars[a] = np.broadcast_to(np.asarray(val, dtype=np.float64), shape).copy()
+            self.vars.setdefault(out, np.zeros(op.output_meta[out]['shape']))
+
+    @staticmethod
+    def _key(name):
+        return name.split('.')[-1]
+
+    def __getitem__(self, name):
+        return self.vars[self._key(name)]
+
+    def __setitem__(self, name, value):
+        k = self._key(name)
+        self.vars[k] = np.broadcast_to(np.asarray(value, dtype=np.float64), self.vars[k].shape).copy()
+
+    def run(self):
+        for op, args, out in self.model.ops:
+            inputs = {a: self.vars[a] for a in args}
+            outputs = {out: self.vars[out].copy()}
+            if isinstance(op, CustomImplicitOperation):
+                op.solve_residual_equations(inputs, outputs)
+            else:
+                op.compute(inputs, outputs)
+            self.vars[out] = np.array(outputs[out], dtype=np.float64).reshape(self.vars[out].shape)
+
+    def compute_totals(self, of, wrt):
+        """Reverse-mode totals d(of)/d(wrt) for scalar `of` (the adjoint chain of
+        SURVEY.md section 3.2-3.4)."""
+        of = [of] if isinstance(of, str) else list(of)
+        wrt = [wrt] if isinstance(wrt, str) else list(wrt)
+        totals = {}
+        lin = {}
+        for o in of:
+            bar = {self._key(o): np.ones(1)}
+            for op, args, out in reversed(self.model.ops):
+                if out not in bar:
+                    continue
+                inputs = {a: self.vars[a] for a in args}
+                if isinstance(op, CustomImplicitOperation):
+                    outputs = {out: self.vars[out]}
+                    if id(op) not in lin:
+                        op.compute_derivatives(inputs, outputs, {})
+                        lin[id(op)] = True
+                    d_res = {out: np.zeros_like(self.vars[out])}
+                    op.apply_inverse_jacobian({out: bar[out]}, d_res, 'rev')
+                    d_in = {a: np.zeros_like(self.vars[a]) for a in args}
+                    op.compute_jacvec_product(inputs, outputs, d_in, {}, {out: np.array(d_res[out])}, 'rev')
+                    for a in args:
+                        bar[a] = bar.get(a, 0.0) - d_in[a]
+                else:
+                    derivs = {}
+                    op.compute_derivatives(inputs, derivs)
+                    seed = float(np.ravel(bar[out])[0])
+                    for a in args:
+                        bar[a] = bar.get(a, 0.0) + seed * np.ravel(derivs[out, a])
+            for w in wrt:
+                totals[(o, w)] = np.array(bar.get(self._key(w), np.zeros_like(self.vars[self._key(w)])))
+        return totals
+
+    def check_totals(self, of, wrt, step=1e-6, directions=3, seed=0, compact_print=True):
+        """Directional finite-difference check of compute_totals (the reference's
+        only derivative validation, sim.check_totals)."""
+        rng = np.random.default_rng(seed)
+        self.run()
+        tot = self.compute_totals(of, wrt)
+        report = {}
+        for (o, w), g in tot.items():
+            x0 = self.vars[self._key(w)].copy()
+            errs = []
+            for _ in range(directions):
+                d = rng.standard_normal(x0.shape)
+                self[w] = x0 + step * d
+                self.run()
+                fp = float(np.ravel(self[o])[0])
+                self[w] = x0 - step * d
+                self.run()
+                fm = float(np.ravel(self[o])[0])
+                fd = (fp - fm) / (2 * step)
+                an = float(g.ravel() @ d.ravel())
+                errs.append(abs(fd - an) / max(abs(fd), 1e-300))
+            self[w] = x0
+            self.run()
+            report[(o, w)] = max(errs)
+            if compact_print:
+                print('check_totals d%s/d%s: max rel err %.3e' % (o, w, report[(o, w)]))
+        return report

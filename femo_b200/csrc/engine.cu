@@ -60,13 +60,13 @@ __global__ void __launch_bounds__(kThreads)
     if (k >= nrows) return;
     const int32_t i = rows[k];
     if (mark[i]) {
-        b[i] = scale * (g[i] - x[i]);
+        b[i] = scale * (g[i] - (x ? x[i] : 0.0));
         return;
     }
     double acc = 0.0;
     for (int32_t t = rowptr[i]; t < rowptr[i + 1]; ++t) {
         const int32_t j = col[t];
-        if (mark[j]) acc += vals[t] * (g[j] - x[j]);
+        if (mark[j]) acc += vals[t] * (g[j] - (x ? x[j] : 0.0));
     }
     b[i] -= scale * acc;
 }
@@ -424,6 +424,28 @@ static int up(femo_problem *p, T *&dst, const std::vector<T> &src) {
     return FEMO_OK;
 }
 
+// copy the Dirichlet arrays into their (always reserved) device slots
+static int push_bc(femo_problem *p) {
+    const int64_t N = p->state.ndofs;
+    FEMO_CUDA(cudaSetDevice(p->device));
+    if (p->bc_mark.empty()) {
+        p->bc_mark.assign(N, 0);
+        p->bc_g.assign(N, 0.0);
+        p->bc_diag.assign(N, 0.0);
+    }
+    if (p->bcflag.empty()) p->bcflag.assign(p->pat[0].nnz, 0);
+    cudaStream_t st = p->stream;
+    FEMO_CUDA(cudaMemcpyAsync(p->d_bc_mark, p->bc_mark.data(), N, cudaMemcpyHostToDevice, st));
+    FEMO_CUDA(cudaMemcpyAsync(p->d_bc_g, p->bc_g.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
+    FEMO_CUDA(cudaMemcpyAsync(p->d_bc_diag, p->bc_diag.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
+    FEMO_CUDA(cudaMemcpyAsync(p->dpat[0].bcflag, p->bcflag.data(), p->bcflag.size(), cudaMemcpyHostToDevice, st));
+    if (!p->lift_rows.empty())
+        FEMO_CUDA(cudaMemcpyAsync(p->d_lift_rows, p->lift_rows.data(), p->lift_rows.size() * sizeof(int32_t),
+                                  cudaMemcpyHostToDevice, st));
+    FEMO_CUDA(cudaStreamSynchronize(st));
+    return FEMO_OK;
+}
+
 // ===========================================================================
 // C ABI
 // ===========================================================================
@@ -585,7 +607,6 @@ int femo_problem_gather_map(const femo_problem *p, int which, int32_t *ptr, int3
 
 int femo_problem_set_bc(femo_problem *p, const int32_t *dofs, const int32_t *list_ptr, int nlists, const double *g) {
     if (!p || nlists < 0 || (nlists > 0 && (!dofs || !list_ptr))) return set_err(FEMO_EINVAL, "femo_problem_set_bc: bad arguments");
-    if (p->uploaded) return set_err(FEMO_ESTATE, "femo_problem_set_bc must precede femo_problem_upload");
     const int64_t N = p->state.ndofs;
     p->bc_mark.assign(N, 0);
     p->bc_diag.assign(N, 0.0);
@@ -617,6 +638,7 @@ int femo_problem_set_bc(femo_problem *p, const int32_t *dofs, const int32_t *lis
     for (int64_t i = 0; i < N; ++i)
         if (lift[i]) p->lift_rows.push_back((int32_t)i);
     p->has_bc = nlists > 0 && !p->lift_rows.empty();
+    if (p->uploaded) return push_bc(p);
     return FEMO_OK;
 }
 
@@ -642,7 +664,7 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     for (int w = 0; w <= p->nin; ++w) s += pattern_bytes(p->pat[w], w == 0);
     s += vecmap_bytes(p->vm_state_full) + vecmap_bytes(p->vm_state_cells);
     for (int i = 0; i < p->nin; ++i) s += vecmap_bytes(p->vm_in[i]);
-    s += Arena::need(N, 1) + 2 * Arena::need(N, 8) + Arena::need(std::max<size_t>(1, p->lift_rows.size()), 4);
+    s += Arena::need(N, 1) + 2 * Arena::need(N, 8) + Arena::need(N, 4);  // Dirichlet arrays (settable after upload)
     s += 4096;
     size_t scratch = 0, tv = 0;
     for (int w = 0; w <= p->nin; ++w) {
@@ -718,9 +740,6 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
             D.t_nrb = (int)P.t_rb.size() - 1;
         }
     }
-    if (p->has_bc) {
-        if ((rc = up(p, p->dpat[0].bcflag, p->bcflag))) return rc;
-    }
     if ((rc = up(p, p->dvm_state_full.ptr, p->vm_state_full.ptr))) return rc;
     if ((rc = up(p, p->dvm_state_full.src, p->vm_state_full.src))) return rc;
     if (p->facet_terms) {
@@ -733,15 +752,13 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
         if ((rc = up(p, p->dvm_in[i].ptr, p->vm_in[i].ptr))) return rc;
         if ((rc = up(p, p->dvm_in[i].src, p->vm_in[i].src))) return rc;
     }
-    if (p->bc_mark.empty()) {
-        p->bc_mark.assign(N, 0);
-        p->bc_g.assign(N, 0.0);
-        p->bc_diag.assign(N, 0.0);
-    }
-    if ((rc = up(p, p->d_bc_mark, p->bc_mark))) return rc;
-    if ((rc = up(p, p->d_bc_g, p->bc_g))) return rc;
-    if ((rc = up(p, p->d_bc_diag, p->bc_diag))) return rc;
-    if ((rc = up(p, p->d_lift_rows, p->lift_rows))) return rc;
+    p->dpat[0].bcflag = p->st.take<uint8_t>(p->pat[0].nnz);
+    p->d_bc_mark = p->st.take<uint8_t>(N);
+    p->d_bc_g = p->st.take<double>(N);
+    p->d_bc_diag = p->st.take<double>(N);
+    p->d_lift_rows = p->st.take<int32_t>(N);
+    if (!p->d_lift_rows) return set_err(FEMO_EINVAL, "static arena too small");
+    if ((rc = push_bc(p))) return rc;
 
     // quadrature tables
     {
@@ -842,7 +859,7 @@ int femo_assemble_jacobian(femo_problem *p, double *d_vals, double *d_vals_bc) {
     const DevPattern &D = p->dpat[0];
     const int64_t nnz = p->pat[0].nnz;
     k_segreduce_jac<<<grid_for(nnz), kThreads, 0, p->stream>>>(D.gptr, D.gsrc, p->d_scratch,
-                                                               p->has_bc ? D.bcflag : nullptr, D.col, p->d_bc_diag,
+                                                               D.bcflag, D.col, p->d_bc_diag,
                                                                d_vals, d_vals_bc, nnz);
     p->launches++;
     FEMO_CHECK_LAUNCH();
@@ -862,21 +879,30 @@ int femo_assemble_dRdm(femo_problem *p, int slot, double *d_vals) {
     return FEMO_OK;
 }
 
-int femo_newton_rhs(femo_problem *p, const double *d_vals, double *d_b) {
+static int lifted_rhs(femo_problem *p, const double *d_vals, double *d_b, const double *x0, double scale) {
     int rc;
     if ((rc = need_device(p))) return rc;
-    if (!d_b) return set_err(FEMO_EINVAL, "femo_newton_rhs: null output");
+    if (!d_b) return set_err(FEMO_EINVAL, "lifted rhs: null output");
     if ((rc = femo_assemble_residual(p, d_b))) return rc;
     if (p->has_bc) {
-        if (!d_vals) return set_err(FEMO_EINVAL, "femo_newton_rhs: Jacobian values required for lifting");
+        if (!d_vals) return set_err(FEMO_EINVAL, "lifted rhs: Jacobian values required for lifting");
         const int64_t nl = (int64_t)p->lift_rows.size();
         const DevPattern &D = p->dpat[0];
         k_newton_rhs<<<grid_for(nl), kThreads, 0, p->stream>>>(p->d_lift_rows, nl, D.rowptr, D.col, d_vals, p->d_bc_mark,
-                                                               p->d_bc_g, p->coef[0], d_b, -1.0);
+                                                               p->d_bc_g, x0, d_b, scale);
         p->launches++;
         FEMO_CHECK_LAUNCH();
     }
     return FEMO_OK;
+}
+
+int femo_newton_rhs(femo_problem *p, const double *d_vals, double *d_b) {
+    if (!p) return set_err(FEMO_EINVAL, "null problem");
+    return lifted_rhs(p, d_vals, d_b, p->coef[0], -1.0);
+}
+
+int femo_assemble_system_rhs(femo_problem *p, const double *d_vals, double *d_b) {
+    return lifted_rhs(p, d_vals, d_b, nullptr, 1.0);
 }
 
 int femo_assemble_output(femo_problem *p, int out_id, double *h_value) {

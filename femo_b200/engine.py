@@ -97,6 +97,8 @@ class EngineProblem:
         self.M = [int(s[4 + i]) for i in range(self.nin)]
         self.aux_sizes = [int(s[8 + i]) for i in range(self.naux)]
         self.uploaded = False
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
         self._keep = {}       # tensors whose pointers the engine borrows
         self.device = None
 
@@ -199,6 +201,11 @@ class EngineProblem:
     def newton_rhs(self, vals, out=None):
         out = self.new_vector(self.N) if out is None else out
         check(lib.femo_newton_rhs(self._h, self._p(vals), self._p(out)))
+        return out
+
+    def system_rhs(self, vals, out=None):
+        out = self.new_vector(self.N) if out is None else out
+        check(lib.femo_assemble_system_rhs(self._h, self._p(vals), self._p(out)))
         return out
 
     def assemble_output(self, k=0):

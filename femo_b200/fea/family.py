@@ -1,0 +1,95 @@
+"""Binding between femo-level Functions/forms and one engine problem.
+
+A FormFamily owns the EngineProblem (dofmaps, CSR patterns, gather maps, device
+arenas) of one closed set of forms on one mesh.  It is created lazily -- the
+first assemble/solve call needs a CUDA device; there is no CPU path -- and it
+is reused by every later call (reference quirk B12: the reference re-runs
+form()/derivative()/create_matrix on each call, utils_dolfinx.py:173-187).
+"""
+import numpy as np
+
+from .. import engine as _E
+
+
+class FormFamily:
+    def __init__(self, family_id, mesh, state, inputs, params=()):
+        self.family_id = family_id
+        self.mesh = mesh
+        self.state = state
+        self.inputs = list(inputs)
+        self.aux = []
+        self.params = list(params)
+        self._prob = None
+        self._bc_sig = None
+        self._ptrs = {}
+
+    # -- registry: forms built from the same (state, inputs) share one family --
+    @classmethod
+    def get(cls, family_id, mesh, state, inputs, params=()):
+        reg = state.__dict__.setdefault('_femo_families', {})
+        key = (family_id,) + tuple(id(f) for f in inputs)
+        fam = reg.get(key)
+        if fam is None:
+            fam = reg[key] = cls(family_id, mesh, state, inputs, params)
+        return fam
+
+    def set_aux(self, index, function):
+        while len(self.aux) <= index:
+            self.aux.append(None)
+        self.aux[index] = function
+
+    def set_param(self, index, value):
+        while len(self.params) <= index:
+            self.params.append(0.0)
+        if self._prob is not None and self.params[index] != value:
+            raise RuntimeError('family parameters cannot change after the engine problem was built')
+        self.params[index] = float(value)
+
+    def slot_of(self, function):
+        if function is self.state:
+            return 0
+        for i, f in enumerate(self.inputs):
+            if function is f:
+                return 1 + i
+        raise ValueError('function is neither the state nor an input of this form family')
+
+    def function_of(self, slot):
+        return self.state if slot == 0 else self.inputs[slot - 1]
+
+    # -- engine ---------------------------------------------------------------
+    @property
+    def problem(self):
+        if self._prob is None:
+            p = _E.EngineProblem(self.mesh._e, self.family_id, self.params)
+            p.upload(0)                      # raises FemoError without a CUDA device
+            self._prob = p
+        return self._prob
+
+    def sync(self):
+        """Make the engine's coefficient slots point at up-to-date device copies."""
+        p = self.problem
+        funcs = [self.state] + self.inputs + self.aux
+        for slot, f in enumerate(funcs):
+            if f is None:
+                continue
+            t = f.device_tensor(p)
+            if self._ptrs.get(slot) != t.data_ptr():
+                p.set_coefficient(slot, t)
+                self._ptrs[slot] = t.data_ptr()
+        return p
+
+    def apply_bcs(self, bcs):
+        """Install the dirichletbc objects of this call (fea_dolfinx.py:169-176)."""
+        p = self.problem
+        bcs = list(bcs or [])
+        sig = tuple((id(b), b.dofs.size) for b in bcs)
+        if sig == self._bc_sig:
+            return
+        if not bcs:
+            p.set_bc([], None)
+        else:
+            g = np.zeros(p.N)
+            for b in bcs:
+                g[b.dofs] = b.values(p.N)[b.dofs]
+            p.set_bc([b.dofs for b in bcs], g)
+        self._bc_sig = sig

@@ -1,0 +1,385 @@
+"""Minimal finite-element objects the femo API is written against.
+
+The reference builds its forms from dolfinx / UFL objects (Function,
+FunctionSpace, TestFunction, dirichletbc, derivative, ...; imports at
+femo/fea/fea_dolfinx.py:5-16 and femo/fea/utils_dolfinx.py:5-21).  UFL's
+symbolic algebra is replaced here by *form families*: closed sets of forms whose
+quadrature kernels exist in the CUDA engine.  A `Form` names (family, kind);
+`derivative` moves between kinds exactly where the reference calls
+ufl.derivative (utils_dolfinx.py:313-314).
+
+Host arrays are authoritative at the API boundary (numpy in / numpy out, as
+with PETSc Vec.getArray in the reference); device copies are torch tensors
+used purely as buffers and are refreshed lazily.
+"""
+import numpy as np
+
+from .. import engine as _E
+
+
+# --------------------------------------------------------------------------
+# mesh
+# --------------------------------------------------------------------------
+class _Topology:
+    def __init__(self, dim, ncells):
+        self.dim = dim
+        self._ncells = ncells
+
+    def index_map(self, dim):
+        class _IM:
+            pass
+        im = _IM()
+        im.size_local = im.size_global = self._ncells
+        return im
+
+    def create_connectivity(self, a, b):
+        return None
+
+
+class _Geometry:
+    def __init__(self, x3, gdim):
+        self.x = x3
+        self.dim = gdim
+
+
+class Mesh:
+    """Structured mesh in canonical lattice numbering ("Numbering")."""
+
+    def __init__(self, emesh, cell_type):
+        self._e = emesh
+        self.cell_type = cell_type
+        xy = emesh.coords()
+        x3 = np.zeros((emesh.nverts, 3))
+        x3[:, :emesh.gdim] = xy
+        self.geometry = _Geometry(x3, emesh.gdim)
+        self.topology = _Topology({'interval': 1}.get(cell_type, 2), emesh.ncells)
+        self.cells = emesh.cells()
+        self.num_cells = emesh.ncells
+        self.num_vertices = emesh.nverts
+
+    def h(self):
+        """Cell diameters (dolfinx.cpp.mesh.h, utils_dolfinx.py:526-530)."""
+        x = self.geometry.x[self.cells]
+        d = np.zeros(self.num_cells)
+        nv = x.shape[1]
+        for a in range(nv):
+            for b in range(a + 1, nv):
+                d = np.maximum(d, np.linalg.norm(x[:, a] - x[:, b], axis=1))
+        return d
+
+
+# --------------------------------------------------------------------------
+# spaces and functions
+# --------------------------------------------------------------------------
+class _IndexMap:
+    def __init__(self, n):
+        self.size_local = self.size_global = n
+
+
+class _DofMap:
+    def __init__(self, nnodes, bs):
+        self.index_map = _IndexMap(nnodes)
+        self.index_map_bs = bs
+
+
+class FunctionSpace:
+    """FunctionSpace(mesh, ('CG', 1) | ('DG', 0) | ('Hermite', 3)) (+ block size)."""
+
+    def __init__(self, mesh, element, block=1):
+        family, degree = element
+        family = {'Lagrange': 'CG', 'P': 'CG', 'Q': 'CG', 'Discontinuous Lagrange': 'DG'}.get(family, family)
+        if (family, degree) == ('DG', 0):
+            nnodes = mesh.num_cells
+        elif (family, degree) == ('CG', 1):
+            nnodes = mesh.num_vertices
+        elif (family, degree) == ('Hermite', 3):
+            nnodes, block = mesh.num_vertices, 2
+        else:
+            raise ValueError('femo_b200: no kernels for element %s%d' % (family, degree))
+        self.mesh = mesh
+        self.family, self.degree, self.block = family, degree, block
+        self.num_nodes = nnodes
+        self.dim = nnodes * block
+        self.dofmap = _DofMap(nnodes, block)
+        self.num_sub_spaces = block if block > 1 and family != 'Hermite' else 0
+
+    def node_coordinates(self):
+        if self.family == 'DG':
+            return self.mesh.geometry.x[self.mesh.cells].mean(axis=1)
+        return self.mesh.geometry.x
+
+    def tabulate_dof_coordinates(self):
+        return self.node_coordinates()
+
+    def __eq__(self, other):
+        return (isinstance(other, FunctionSpace) and other.mesh is self.mesh and
+                (other.family, other.degree, other.block) == (self.family, self.degree, self.block))
+
+    def __hash__(self):
+        return hash((id(self.mesh), self.family, self.degree, self.block))
+
+
+def VectorFunctionSpace(mesh, element, dim=None):
+    return FunctionSpace(mesh, element, block=mesh.geometry.dim if dim is None else dim)
+
+
+class Vector:
+    """The slice of petsc4py.Vec the reference uses on Function.vector."""
+
+    def __init__(self, func):
+        self._f = func
+
+    def getArray(self):
+        return self._f._host_array()
+
+    array = property(getArray)
+
+    def set(self, value):
+        self._f._assign(np.full(self._f.function_space.dim, float(np.ravel(value)[0])))
+
+    def setArray(self, values):
+        self._f._assign(values)
+
+    def __setitem__(self, key, values):
+        a = self._f._host_array()
+        a[key] = values
+        self._f._host_changed()
+
+    def __getitem__(self, key):
+        return self._f._host_array()[key]
+
+    def assemble(self):
+        pass
+
+    def ghostUpdate(self, *a, **k):
+        pass
+
+    def norm(self):
+        return float(np.linalg.norm(self._f._host_array()))
+
+    def __len__(self):
+        return self._f.function_space.dim
+
+
+class _XView:
+    def __init__(self, func):
+        self._f = func
+
+    @property
+    def array(self):
+        # handing out a writable view: assume the caller modifies it
+        a = self._f._host_array()
+        self._f._host_changed()
+        return a
+
+
+class Function:
+    def __init__(self, V, name=None):
+        self.function_space = V
+        self.name = name
+        self._host = np.zeros(V.dim)
+        self._dev = None            # torch tensor on the problem's device (a buffer, nothing more)
+        self._host_ver = 1          # bumped on every host write
+        self._dev_ver = 0           # host version the device copy mirrors (-1: device is newer)
+        self.vector = Vector(self)
+        self.x = _XView(self)
+
+    # -- host/device coherence ------------------------------------------------
+    def _host_array(self):
+        if self._dev is not None and self._dev_ver == -1:
+            self._host[:] = self._dev.cpu().numpy()
+            self._dev_ver = self._host_ver
+        return self._host
+
+    def _host_changed(self):
+        self._host_ver += 1
+
+    def _assign(self, values):
+        v = np.asarray(values, dtype=np.float64).ravel()
+        if v.size == 1:
+            self._host[:] = v[0]
+        else:
+            if v.size != self._host.size:
+                raise ValueError('size mismatch: function has %d dofs, got %d values' % (self._host.size, v.size))
+            self._host[:] = v
+        self._dev_ver = 0 if self._dev_ver == -1 else self._dev_ver
+        self._host_changed()
+
+    def device_tensor(self, prob):
+        """Device buffer holding the current values (H2D copy if the host is newer)."""
+        import torch
+        if self._dev is None:
+            self._dev = torch.empty(self._host.size, dtype=torch.float64, device=prob.device)
+            self._dev_ver = 0
+        if self._dev_ver != -1 and self._dev_ver != self._host_ver:
+            self._dev.copy_(torch.from_numpy(self._host), non_blocking=False)
+            self._dev_ver = self._host_ver
+            prob.h2d_bytes += self._host.nbytes
+        return self._dev
+
+    def mark_device_written(self):
+        self._dev_ver = -1
+
+    # -- dolfinx-like surface ----------------------------------------------
+    def interpolate(self, fn):
+        X = self.function_space.node_coordinates().T        # (3, nnodes) as dolfinx passes it
+        vals = np.asarray(fn(X), dtype=np.float64)
+        bs = self.function_space.block
+        if bs > 1 and self.function_space.family != 'Hermite':
+            vals = np.asarray(vals).reshape(bs, -1).T.ravel()
+        self._assign(vals)
+
+    def rename(self, name, label=None):
+        self.name = name
+
+    def copy(self):
+        g = Function(self.function_space, self.name)
+        g._assign(self._host_array())
+        return g
+
+
+class Constant:
+    def __init__(self, mesh, value):
+        self.mesh = mesh
+        self.value = np.asarray(value, dtype=np.float64)
+
+    def __float__(self):
+        return float(self.value)
+
+
+class TestFunction:
+    def __init__(self, V):
+        self.function_space = V
+
+
+class TrialFunction(TestFunction):
+    pass
+
+
+# --------------------------------------------------------------------------
+# boundary conditions
+# --------------------------------------------------------------------------
+class DirichletBC:
+    def __init__(self, value, dofs, V=None):
+        self.value = value
+        d = dofs[0] if isinstance(dofs, (list, tuple)) else dofs
+        self.dofs = np.asarray(d, dtype=np.int32).ravel()
+        self.function_space = V if V is not None else getattr(value, 'function_space', None)
+
+    def values(self, n):
+        if isinstance(self.value, Function):
+            return self.value._host_array()
+        return np.full(n, float(np.ravel(getattr(self.value, 'value', self.value))[0]))
+
+
+def dirichletbc(value, dofs, V=None):
+    """dolfinx.fem.dirichletbc as used at fea_dolfinx.py:169-176."""
+    return DirichletBC(value, dofs, V)
+
+
+def locate_dofs_geometrical(V, marker):
+    """dolfinx.fem.locate_dofs_geometrical for a (V, V) pair or a single space;
+    returns dof indices (all components of blocked spaces)."""
+    pair = isinstance(V, (tuple, list))
+    space = V[0] if pair else V
+    X = space.node_coordinates().T
+    nodes = np.nonzero(np.asarray(marker(X)))[0].astype(np.int32)
+    bs = space.block
+    if bs > 1:
+        nodes = (bs * nodes[:, None] + np.arange(bs, dtype=np.int32)[None, :]).ravel()
+    return [nodes, nodes.copy()] if pair else nodes
+
+
+def locate_entities_boundary(mesh, dim, marker):
+    """Vertices (dim 0) or facets (dim tdim-1) on the boundary satisfying `marker`.
+    Facets are returned as indices into the mesh's exterior-facet list."""
+    X = mesh.geometry.x
+    tdim = mesh.topology.dim
+    if dim == 0:
+        on = np.zeros(mesh.num_vertices, dtype=bool)
+        fc, fl = mesh._e.exterior_facets()
+        lf = _local_facets(mesh)
+        on[np.unique(mesh.cells[fc][np.arange(fc.size)[:, None], lf[fl]])] = True
+        ok = np.asarray(marker(X.T)) & on
+        return np.nonzero(ok)[0].astype(np.int32)
+    if dim != tdim - 1:
+        raise ValueError('locate_entities_boundary: only vertices and facets are supported')
+    fc, fl = mesh._e.exterior_facets()
+    lf = _local_facets(mesh)
+    fv = mesh.cells[fc][np.arange(fc.size)[:, None], lf[fl]]          # (nf, verts per facet)
+    ok = np.ones(fc.size, dtype=bool)
+    for k in range(fv.shape[1]):
+        ok &= np.asarray(marker(X[fv[:, k]].T))
+    return np.nonzero(ok)[0].astype(np.int32)
+
+
+def _local_facets(mesh):
+    if mesh.cell_type == 'triangle':
+        return np.array([[1, 2], [0, 2], [0, 1]])
+    if mesh.cell_type == 'quadrilateral':
+        return np.array([[0, 1], [0, 2], [1, 3], [2, 3]])
+    return np.array([[0], [1]])
+
+
+def locate_dofs_topological(V, dim, entities):
+    if dim != 0:
+        raise ValueError('locate_dofs_topological: only vertex entities are supported')
+    bs = V.block
+    ent = np.asarray(entities, dtype=np.int32)
+    if bs == 1:
+        return ent
+    return (bs * ent[:, None] + np.arange(bs, dtype=np.int32)[None, :]).ravel()
+
+
+class MeshTags:
+    def __init__(self, mesh, dim, indices, values):
+        self.mesh, self.dim = mesh, dim
+        self.indices = np.asarray(indices, dtype=np.int32)
+        self.values = np.asarray(values, dtype=np.int32)
+
+
+def meshtags(mesh, dim, indices, values):
+    return MeshTags(mesh, dim, indices, values)
+
+
+class Measure:
+    """ufl.Measure('ds', subdomain_data=facet_tag, metadata=...) -> ds_(tag)."""
+
+    def __init__(self, kind, domain=None, subdomain_data=None, metadata=None, tag=None):
+        self.kind, self.domain, self.subdomain_data, self.metadata, self.tag = kind, domain, subdomain_data, metadata, tag
+
+    def __call__(self, tag):
+        return Measure(self.kind, self.domain, self.subdomain_data, self.metadata, tag)
+
+    def facets(self):
+        t = self.subdomain_data
+        return t.indices[t.values == self.tag] if t is not None else None
+
+
+ds = Measure('ds')
+dx = Measure('dx')
+
+
+# --------------------------------------------------------------------------
+# forms
+# --------------------------------------------------------------------------
+class Form:
+    """(family instance, kind[, output id, slot]).  kinds: 'residual', 'dRdu',
+    'dRdm', 'output', 'output_grad', 'mass', 'mass_rhs'."""
+
+    def __init__(self, fam, kind, out_id=0, slot=0):
+        self.fam, self.kind, self.out_id, self.slot = fam, kind, out_id, slot
+
+    def __add__(self, other):
+        raise TypeError('femo_b200 forms are closed families; sums of forms are not supported')
+
+
+def derivative(form, function, direction=None):
+    """Gateaux derivative within a family (utils_dolfinx.py:313-314)."""
+    fam = form.fam
+    slot = fam.slot_of(function)
+    if form.kind == 'residual':
+        return Form(fam, 'dRdu') if slot == 0 else Form(fam, 'dRdm', slot=slot - 1)
+    if form.kind == 'output':
+        return Form(fam, 'output_grad', out_id=form.out_id, slot=slot)
+    raise TypeError('derivative of a %s form is not available' % form.kind)

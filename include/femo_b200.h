@@ -84,7 +84,8 @@ int femo_problem_gather_map(const femo_problem *p, int which, int32_t *ptr, int3
 /* dirichletbc objects (fea_dolfinx.py:169-176): `dofs` is the concatenation of
  * nlists dof arrays, list_ptr (nlists+1) delimits them; a dof listed k times
  * gets diagonal k (dolfinx set_diagonal adds once per bc object).  g (N values,
- * or NULL for homogeneous) holds the prescribed values. */
+ * or NULL for homogeneous) holds the prescribed values.  May be called before
+ * or after femo_problem_upload (after: synchronises); nlists = 0 clears. */
 int femo_problem_set_bc(femo_problem *p, const int32_t *dofs, const int32_t *list_ptr, int nlists, const double *g);
 
 /* ---- device residency ------------------------------------------------------
@@ -117,6 +118,9 @@ int femo_assemble_dRdm(femo_problem *p, int slot, double *d_vals);
  * b = R(x) - scale*A(:,bc)(g-x), b[bc] = scale*(g-x) with scale=-1; d_vals is
  * the un-BC'd Jacobian at the same state. */
 int femo_newton_rhs(femo_problem *p, const double *d_vals, double *d_b);
+/* right-hand side of assembleSystem (utils_dolfinx.py:197-201): apply_lifting with
+ * x0 = None, scale = 1, then set_bc:  b = R - A(:,bc) g, b[bc] = g. */
+int femo_assemble_system_rhs(femo_problem *p, const double *d_vals, double *d_b);
 /* assemble(form, dim=0) (utils_dolfinx.py:169-173,204-213; output_model.py:69-75).
  * Synchronises. */
 int femo_assemble_output(femo_problem *p, int out_id, double *h_value);

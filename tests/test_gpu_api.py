@@ -1,0 +1,126 @@
+"""The reference-facing API (FEA + CSDL operations) on the GPU vs the oracle:
+the tests read like the reference's example scripts."""
+import numpy as np
+import pytest
+
+from oracle import mesh as om, families as fam, assembly as asm, solvers
+from _cases import relerr, square_boundary_lists
+
+pytestmark = pytest.mark.gpu
+
+
+def _poisson_setup(n):
+    """examples/poisson_opt/run_poisson_opt.py:22-153 against the femo_b200 API."""
+    from femo_b200.fea.fea_b200 import (FEA, createUnitSquareMesh, FunctionSpace, Function, TestFunction,
+                                         locate_dofs_geometrical, getFuncArray)
+    from femo_b200.forms.poisson import pdeRes, outputForm
+    PI = np.pi
+
+    class Expression_f:
+        def eval(self, x):
+            return 1 / (1 + 1e-6 * 4 * np.power(PI, 4)) * np.sin(PI * x[0]) * np.sin(PI * x[1])
+
+    class Expression_u:
+        def eval(self, x):
+            return 1 / (2 * np.power(PI, 2)) * np.sin(PI * x[0]) * np.sin(PI * x[1])
+
+    mesh = createUnitSquareMesh(n)
+    fea = FEA(mesh)
+    Vf = FunctionSpace(mesh, ('DG', 0))
+    f = Function(Vf)
+    Vu = FunctionSpace(mesh, ('CG', 1))
+    u = Function(Vu)
+    v = TestFunction(Vu)
+    u_ex = fea.add_exact_solution(Expression_u, Vu)
+    f_ex = fea.add_exact_solution(Expression_f, Vf)
+    output_form = outputForm(u, f, u_ex)
+    ubc = Function(Vu)
+    ubc.vector.set(0.0)
+    locs = [locate_dofs_geometrical((Vu, Vu), lambda x, a=a, b=b: np.isclose(x[a], b, atol=1e-6))
+            for a, b in ((0, 0.), (0, 1.), (1, 0.), (1, 1.))]
+    fea.add_strong_bc(ubc, locs, Vu)
+    residual_form = pdeRes(u, v, f)
+    fea.add_input('f', f)
+    fea.add_state(name='u', function=u, residual_form=residual_form, arguments=['f'])
+    fea.add_output(name='l2_functional', type='scalar', form=output_form, arguments=['f', 'u'])
+    fea.PDE_SOLVER = 'Newton'
+    fea.REPORT = False
+    return fea, getFuncArray(f_ex).copy(), getFuncArray(u_ex).copy()
+
+
+def test_poisson_opt_forward_and_totals(cuda_device):
+    from femo_b200.csdl_opt import FEAModel, Simulator
+    n = 16
+    fea, f_ex, u_ex = _poisson_setup(n)
+    model = FEAModel(fea=[fea], debug_mode=False)
+    model.create_input('f', shape=fea.inputs_dict['f']['shape'], val=0.1 * np.ones(fea.inputs_dict['f']['shape']) * 0.86)
+    model.add_design_variable('f')
+    model.add_objective('l2_functional', scaler=1e5)
+    sim = Simulator(model)
+    sim['f'] = f_ex
+    sim.run()
+    # oracle
+    m = om.unit_square_tri(n)
+    F = fam.PoissonP1(m, u_ex=u_ex)
+    bc = asm.DirichletBC(F.N, square_boundary_lists(m.coords), 0.0)
+    sp = solvers.StatePath(F, bc)
+    uo, _ = sp.solve_newton(np.zeros(F.N), [f_ex])
+    assert relerr(sim['u'], uo) < 1e-9
+    Jo = asm.assemble_scalar(F.output(0, uo, f_ex))
+    assert abs(sim['l2_functional_output_model.l2_functional'][0] - Jo) < 1e-9 * abs(Jo)
+    tot = sim.compute_totals('l2_functional', 'f')[('l2_functional', 'f')]
+    (go,), _ = sp.total_derivative(0, uo, [f_ex])          # reference-faithful (quirk B2)
+    assert relerr(tot, go) < 1e-8
+    # the totals differ from finite differences only through quirk B2
+    (gc,), _ = sp.total_derivative(0, uo, [f_ex], consistent_bc=True)
+    assert relerr(gc, go) > 1e-6
+
+
+def test_nonlinear_poisson_check_totals(cuda_device):
+    """examples/nonlinear_poisson_opt: SNES state solve, then adjoint totals vs
+    central finite differences through the full callback chain (no strong BC, so
+    reference-faithful and consistent totals coincide)."""
+    from femo_b200.fea.fea_b200 import FEA, createUnitSquareMesh, FunctionSpace, Function, TestFunction
+    from femo_b200.forms.nonlinear_poisson import pdeRes, outputForm
+    from femo_b200.csdl_opt import FEAModel, Simulator
+    mesh = createUnitSquareMesh(12)
+    fea = FEA(mesh)
+    f = Function(FunctionSpace(mesh, ('DG', 0)))
+    Vu = FunctionSpace(mesh, ('CG', 1))
+    u = Function(Vu)
+    residual_form = pdeRes(u, TestFunction(Vu), f)
+    fea.add_input('f', f)
+    fea.add_state(name='u', function=u, residual_form=residual_form, arguments=['f'])
+    fea.add_output(name='l2_functional', type='scalar', form=outputForm(u, f), arguments=['f', 'u'])
+    fea.PDE_SOLVER = 'SNES'
+    fea.REPORT = False
+    model = FEAModel(fea=[fea], debug_mode=False)
+    model.create_input('f', shape=fea.inputs_dict['f']['shape'], val=0.1)
+    sim = Simulator(model)
+    rep = sim.check_totals('l2_functional', 'f', step=1e-4, compact_print=False)
+    assert max(rep.values()) < 1e-6
+    # and against the oracle's reference-ordered chain
+    m = om.unit_square_tri(12)
+    F = fam.NonlinearPoissonP1(m)
+    sp = solvers.StatePath(F, None)
+    f0 = 0.1 * np.ones(F.M)
+    uo, _ = sp.solve_snes(np.zeros(F.N), [f0])
+    assert relerr(sim['u'], uo) < 1e-9
+    (go,), _ = sp.total_derivative(0, uo, [f0])
+    assert relerr(sim.compute_totals('l2_functional', 'f')[('l2_functional', 'f')], go) < 1e-8
+
+
+def test_api_error_behaviour(cuda_device):
+    """Error conventions of the reference."""
+    from femo_b200.fea.fea_b200 import FEA, createUnitSquareMesh, FunctionSpace, Function, assemble
+    from femo_b200.forms.poisson import pdeRes
+    mesh = createUnitSquareMesh(4)
+    fea = FEA(mesh)
+    f = Function(FunctionSpace(mesh, ('DG', 0)))
+    u = Function(FunctionSpace(mesh, ('CG', 1)))
+    fea.add_input('f', f)
+    with pytest.raises(ValueError):
+        fea.add_input('f', f)                              # fea_dolfinx.py:101-102
+    assert np.all(f.x.array == 1.0)                        # quirk B5: init_val overwrite
+    r = assemble(pdeRes(u, None, f), dim=7)
+    assert isinstance(r, TypeError)                        # returned, not raised (quirk B7)
