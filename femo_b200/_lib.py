@@ -60,6 +60,8 @@ SIGNATURES = {
     'femo_problem_pattern': (C.c_int, [_P, C.c_int, _P, _P]),
     'femo_problem_gather_map': (C.c_int, [_P, C.c_int, _P, _P]),
     'femo_problem_set_bc': (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    'femo_problem_enable_multigrid': (C.c_int, [_P]),
+    'femo_problem_mg_levels': (C.c_int, [_P]),
     'femo_problem_device_bytes': (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     'femo_problem_upload': (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t]),
     'femo_set_coefficient': (C.c_int, [_P, C.c_int, _P, C.c_int64]),

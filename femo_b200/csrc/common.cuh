@@ -89,6 +89,15 @@ struct femo_mesh {
     femo::Mesh m;
 };
 
+// device work vectors of one multigrid level (level 0 is the problem itself)
+struct femo_mg_level {
+    double *vals = nullptr;   // matrix values of this level (coarse levels own theirs)
+    double *dinv = nullptr, *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr, *q = nullptr;
+    double *u = nullptr;      // restricted state used to rediscretise the coarse Jacobian
+    double *dense = nullptr, *dense_tmp = nullptr;  // coarsest level: explicit inverse
+    double lmax = 2.0;
+};
+
 struct femo_problem {
     femo::Mesh mesh;
     int family = 0;
@@ -126,6 +135,12 @@ struct femo_problem {
     // coefficients
     const double *coef[femo::kMaxSlots] = {nullptr};
     int64_t coefn[femo::kMaxSlots] = {0};
+    // geometric multigrid: coarse problems (owned), Jacobian-only layouts
+    bool jac_only = false;
+    std::vector<femo_problem *> mg;
+    femo_mg_level mgl;
+    femo_problem *parent = nullptr;
+    double *kr_d = nullptr;
     // counters (bench: how many of our kernels were launched)
     long long launches = 0;
 };

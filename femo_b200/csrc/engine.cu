@@ -113,7 +113,7 @@ template <bool DOT>
 __global__ void __launch_bounds__(kThreads)
     k_spmv(const int32_t *__restrict__ rb, int nrb, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-           double *__restrict__ partials) {
+           const double *__restrict__ bsub, double *__restrict__ partials) {
     __shared__ double prod[kSpmvCap];
     __shared__ int32_t rp[kSpmvRows + 1];
     const int tid = threadIdx.x;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kThreads)
             for (int i = tid; i < nr; i += kThreads) {
                 double acc = 0.0;
                 for (int32_t k = rp[i] - s; k < rp[i + 1] - s; ++k) acc += prod[k];
-                y[r0 + i] = acc;
+                y[r0 + i] = bsub ? bsub[r0 + i] - acc : acc;   // optional residual epilogue y = b - A x
                 if (DOT) dot += acc * __ldg(x + r0 + i);
             }
         } else {  // a single long row: CTA-wide strided reduction (fixed order)
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads)
             for (int32_t t = s + tid; t < e; t += kThreads) acc += ld_stream(vals + t) * __ldg(x + ld_stream(col + t));
             acc = block_sum(acc);
             if (tid == 0) {
-                y[r0] = acc;
+                y[r0] = bsub ? bsub[r0] - acc : acc;
                 if (DOT) dot += acc * __ldg(x + r0);
             }
         }
@@ -329,7 +329,7 @@ static int run_elements(femo_problem *p, int op) {
     cudaStream_t st = p->stream;
     int rc;
     if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
-    if ((rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
+    if (op != OP_JAC && (rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
     switch (p->family) {
         case FEMO_FAMILY_POISSON_P1: {
             if (op == OP_OUT || op == OP_OUT_DU)
@@ -386,12 +386,12 @@ static int segreduce(femo_problem *p, const DevVecMap &m, int64_t n, double *d_o
 
 template <bool DOT>
 static int launch_spmv(femo_problem *p, const int32_t *rb, int nrb, const int32_t *rowptr, const int32_t *col,
-                       const double *vals, const double *x, double *y, int *np_out) {
+                       const double *vals, const double *x, double *y, const double *bsub, int *np_out) {
     // persistent grid: every SM holds 8 CTAs and walks the row blocks with a grid stride, so the
     // rows in flight form one contiguous window (x stays L2-resident) and the dot partials are bounded
     int64_t cap = std::min<int64_t>((int64_t)p->num_sms * 8, kMaxPartials);
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nrb, cap));
-    k_spmv<DOT><<<grid, kThreads, 0, p->stream>>>(rb, nrb, rowptr, col, vals, x, y, p->d_partials);
+    k_spmv<DOT><<<grid, kThreads, 0, p->stream>>>(rb, nrb, rowptr, col, vals, x, y, bsub, p->d_partials);
     p->launches++;
     if (np_out) *np_out = grid;
     FEMO_CHECK_LAUNCH();
@@ -445,6 +445,12 @@ static int push_bc(femo_problem *p) {
     FEMO_CUDA(cudaStreamSynchronize(st));
     return FEMO_OK;
 }
+
+extern "C" {
+static int propagate_bc(femo_problem *root);
+}
+
+#include "multigrid.cuh"
 
 // ===========================================================================
 // C ABI
@@ -507,12 +513,12 @@ int femo_mesh_copy(const femo_mesh *m, int what, void *out) {
 void femo_mesh_destroy(femo_mesh *m) { delete m; }
 
 // ---- problem layout -------------------------------------------------------
-int femo_problem_create(const femo_mesh *m, int family, const double *params, int nparams, femo_problem **out) {
-    if (!m || !out) return set_err(FEMO_EINVAL, "femo_problem_create: null");
-    if (nparams < 0 || nparams > 8) return set_err(FEMO_EINVAL, "femo_problem_create: nparams out of range");
+static int create_problem_impl(const Mesh &mesh, int family, const double *params, int nparams, bool jac_only,
+                               femo_problem **out) {
     femo_problem *p = new femo_problem();
-    p->mesh = m->m;
+    p->mesh = mesh;
     p->family = family;
+    p->jac_only = jac_only;
     for (int i = 0; i < nparams; ++i) p->params[i] = params[i];
     const Mesh &M = p->mesh;
     try {
@@ -548,10 +554,12 @@ int femo_problem_create(const femo_mesh *m, int family, const double *params, in
             p->blk_full.push_back(fb);
         }
         build_pattern(M, p->state, p->state, p->blk_full, p->pat[0]);
-        for (int s = 0; s < p->nin; ++s) build_pattern(M, p->state, p->in[s], p->blk_cells, p->pat[1 + s]);
-        build_vecmap(M, p->state, p->blk_full, p->vm_state_full);
-        if (p->facet_terms) build_vecmap(M, p->state, p->blk_cells, p->vm_state_cells);
-        for (int s = 0; s < p->nin; ++s) build_vecmap(M, p->in[s], p->blk_cells, p->vm_in[s]);
+        if (!jac_only) {  // coarse multigrid levels only ever assemble dR/du
+            for (int s = 0; s < p->nin; ++s) build_pattern(M, p->state, p->in[s], p->blk_cells, p->pat[1 + s]);
+            build_vecmap(M, p->state, p->blk_full, p->vm_state_full);
+            if (p->facet_terms) build_vecmap(M, p->state, p->blk_cells, p->vm_state_cells);
+            for (int s = 0; s < p->nin; ++s) build_vecmap(M, p->in[s], p->blk_cells, p->vm_in[s]);
+        }
     } catch (const LayoutError &e) {
         delete p;
         return set_err(e.code, e.msg);
@@ -563,8 +571,39 @@ int femo_problem_create(const femo_mesh *m, int family, const double *params, in
     return FEMO_OK;
 }
 
+int femo_problem_create(const femo_mesh *m, int family, const double *params, int nparams, femo_problem **out) {
+    if (!m || !out) return set_err(FEMO_EINVAL, "femo_problem_create: null");
+    if (nparams < 0 || nparams > 8) return set_err(FEMO_EINVAL, "femo_problem_create: nparams out of range");
+    return create_problem_impl(m->m, family, params, nparams, false, out);
+}
+
+int femo_problem_enable_multigrid(femo_problem *p) {
+    if (!p) return set_err(FEMO_EINVAL, "femo_problem_enable_multigrid: null");
+    if (p->uploaded) return set_err(FEMO_ESTATE, "femo_problem_enable_multigrid must precede femo_problem_upload");
+    if (p->mesh.kind != MESH_TRI || p->state.element != EL_VERTEX || p->state.block != 1)
+        return set_err(FEMO_EINVAL, "multigrid is available for scalar P1 states on lattice triangle meshes");
+    if (!p->mg.empty()) return FEMO_OK;
+    int nx = p->mesh.n[0], ny = p->mesh.n[1];
+    while (nx > kMgCoarsest || ny > kMgCoarsest) {
+        if (nx > kMgCoarsest) nx = (nx + 1) / 2;
+        if (ny > kMgCoarsest) ny = (ny + 1) / 2;
+        Mesh cm;
+        make_unit_square_tri(nx, ny, p->mesh.lo, p->mesh.hi, cm);
+        femo_problem *c = nullptr;
+        int rc = create_problem_impl(cm, p->family, p->params, 8, true, &c);
+        if (rc) return rc;
+        c->parent = p;
+        p->mg.push_back(c);
+    }
+    if (!p->bc_mark.empty()) return propagate_bc(p);
+    return FEMO_OK;
+}
+
+int femo_problem_mg_levels(const femo_problem *p) { return p ? (int)p->mg.size() + 1 : 0; }
+
 void femo_problem_destroy(femo_problem *p) {
     if (!p) return;
+    for (femo_problem *c : p->mg) femo_problem_destroy(c);
     if (p->h_pinned) cudaFreeHost(p->h_pinned);
     delete p;
 }
@@ -605,8 +644,7 @@ int femo_problem_gather_map(const femo_problem *p, int which, int32_t *ptr, int3
     return FEMO_OK;
 }
 
-int femo_problem_set_bc(femo_problem *p, const int32_t *dofs, const int32_t *list_ptr, int nlists, const double *g) {
-    if (!p || nlists < 0 || (nlists > 0 && (!dofs || !list_ptr))) return set_err(FEMO_EINVAL, "femo_problem_set_bc: bad arguments");
+static int set_bc_impl(femo_problem *p, const int32_t *dofs, const int32_t *list_ptr, int nlists, const double *g) {
     const int64_t N = p->state.ndofs;
     p->bc_mark.assign(N, 0);
     p->bc_diag.assign(N, 0.0);
@@ -642,6 +680,33 @@ int femo_problem_set_bc(femo_problem *p, const int32_t *dofs, const int32_t *lis
     return FEMO_OK;
 }
 
+// coarse multigrid levels inherit Dirichlet rows geometrically: a coarse node is
+// constrained when the fine node nearest to it is (homogeneous correction equation)
+static int propagate_bc(femo_problem *root) {
+    const femo_problem *F = root;
+    for (femo_problem *C : root->mg) {
+        std::vector<int32_t> list;
+        const int fnx = F->mesh.n[0], fny = F->mesh.n[1], cnx = C->mesh.n[0], cny = C->mesh.n[1];
+        for (int J = 0; J <= cny; ++J)
+            for (int I = 0; I <= cnx; ++I) {
+                const int i = (int)std::llround((double)I * fnx / cnx), j = (int)std::llround((double)J * fny / cny);
+                if (!F->bc_mark.empty() && F->bc_mark[(int64_t)j * (fnx + 1) + i]) list.push_back(J * (cnx + 1) + I);
+            }
+        int32_t ptr[2] = {0, (int32_t)list.size()};
+        int rc = set_bc_impl(C, list.data(), ptr, list.empty() ? 0 : 1, nullptr);
+        if (rc) return rc;
+        F = C;
+    }
+    return FEMO_OK;
+}
+
+int femo_problem_set_bc(femo_problem *p, const int32_t *dofs, const int32_t *list_ptr, int nlists, const double *g) {
+    if (!p || nlists < 0 || (nlists > 0 && (!dofs || !list_ptr))) return set_err(FEMO_EINVAL, "femo_problem_set_bc: bad arguments");
+    int rc = set_bc_impl(p, dofs, list_ptr, nlists, g);
+    if (rc) return rc;
+    return propagate_bc(p);
+}
+
 // ---- device residency -----------------------------------------------------
 static size_t pattern_bytes(const Pattern &P, bool bc) {
     size_t b = 0;
@@ -653,6 +718,88 @@ static size_t pattern_bytes(const Pattern &P, bool bc) {
     return b;
 }
 static size_t vecmap_bytes(const VecMap &V) { return Arena::need(V.ptr.size(), 4) + Arena::need(V.src.size(), 4); }
+
+static void child_bytes(const femo_problem *c, bool coarsest, size_t *sb, size_t *wb) {
+    const Mesh &M = c->mesh;
+    const size_t N = (size_t)c->state.ndofs;
+    size_t s = 0, w = 0;
+    s += Arena::need(M.coords.size(), 8) + Arena::need(M.cells.size(), 4);
+    s += Arena::need(std::max<size_t>(1, M.bf_cell.size()), 4) * 2;
+    s += pattern_bytes(c->pat[0], true);
+    s += Arena::need(N, 1) + 2 * Arena::need(N, 8) + Arena::need(N, 4) + 1024;
+    w += Arena::need(c->pat[0].nnz, 8) + 7 * Arena::need(N, 8);
+    w += Arena::need(3 * kMaxPartials, 8) + Arena::need(S_COUNT, 8) + 1024;
+    if (coarsest) w += 2 * Arena::need(N * N, 8);
+    *sb = s;
+    *wb = w;
+}
+
+// place a coarse multigrid level in the root's arenas
+static int upload_child(femo_problem *root, femo_problem *c, bool coarsest) {
+    c->device = root->device;
+    c->stream = root->stream;
+    c->num_sms = root->num_sms;
+    const Mesh &M = c->mesh;
+    const int64_t N = c->state.ndofs;
+    auto put = [&](auto *&dst, const auto &src) -> int {
+        using T = typename std::remove_reference<decltype(src)>::type::value_type;
+        dst = root->st.take<T>(std::max<size_t>(1, src.size()));
+        if (!dst) return set_err(FEMO_EINVAL, "static arena too small (multigrid level)");
+        if (!src.empty())
+            FEMO_CUDA(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, root->stream));
+        return FEMO_OK;
+    };
+    int rc;
+    if ((rc = put(c->d_coords, M.coords))) return rc;
+    {
+        std::vector<int32_t> T(M.cells.size());
+        for (int64_t k = 0; k < M.ncells; ++k)
+            for (int a = 0; a < M.nvpc; ++a) T[a * M.ncells + k] = M.cells[k * M.nvpc + a];
+        if ((rc = put(c->d_cellsT, T))) return rc;
+        FEMO_CUDA(cudaStreamSynchronize(root->stream));
+    }
+    if ((rc = put(c->d_bf_cell, M.bf_cell))) return rc;
+    if ((rc = put(c->d_bf_local, M.bf_local))) return rc;
+    const Pattern &P = c->pat[0];
+    DevPattern &D = c->dpat[0];
+    if ((rc = put(D.rowptr, P.rowptr))) return rc;
+    if ((rc = put(D.col, P.col))) return rc;
+    if ((rc = put(D.gptr, P.gptr))) return rc;
+    if ((rc = put(D.gsrc, P.gsrc))) return rc;
+    if ((rc = put(D.t_perm, P.t_perm))) return rc;
+    if ((rc = put(D.rb, P.rb))) return rc;
+    D.nrb = (int)P.rb.size() - 1;
+    D.t_rowptr = D.rowptr; D.t_col = D.col; D.t_rb = D.rb; D.t_nrb = D.nrb;
+    D.bcflag = root->st.take<uint8_t>(P.nnz);
+    c->d_bc_mark = root->st.take<uint8_t>(N);
+    c->d_bc_g = root->st.take<double>(N);
+    c->d_bc_diag = root->st.take<double>(N);
+    c->d_lift_rows = root->st.take<int32_t>(N);
+    if (!c->d_lift_rows) return set_err(FEMO_EINVAL, "static arena too small (multigrid level)");
+    femo_mg_level &L = c->mgl;
+    L.vals = root->wk.take<double>(P.nnz);
+    L.dinv = root->wk.take<double>(N);
+    L.x = root->wk.take<double>(N);
+    L.b = root->wk.take<double>(N);
+    L.r = root->wk.take<double>(N);
+    L.d = root->wk.take<double>(N);
+    L.q = root->wk.take<double>(N);
+    L.u = root->wk.take<double>(N);
+    c->d_partials = root->wk.take<double>(3 * kMaxPartials);
+    c->d_scalars = root->wk.take<double>(S_COUNT);
+    if (coarsest) {
+        L.dense = root->wk.take<double>((size_t)N * N);
+        L.dense_tmp = root->wk.take<double>((size_t)N * N);
+        if (!L.dense_tmp) return set_err(FEMO_EINVAL, "work arena too small (multigrid level)");
+    }
+    if (!c->d_scalars) return set_err(FEMO_EINVAL, "work arena too small (multigrid level)");
+    c->d_scratch = root->d_scratch;   // element tensors of coarse levels reuse the fine level's scratch
+    c->scratch_len = root->scratch_len;
+    if (!c->h_pinned) FEMO_CUDA(cudaMallocHost((void **)&c->h_pinned, sizeof(double) * 64));
+    if ((rc = push_bc(c))) return rc;
+    c->uploaded = true;
+    return FEMO_OK;
+}
 
 int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_t *work_bytes) {
     if (!p || !static_bytes || !work_bytes) return set_err(FEMO_EINVAL, "femo_problem_device_bytes: null");
@@ -680,7 +827,14 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     w += 8 * Arena::need(N, 8);                    // r p q dinv z w b dx
     w += 2 * Arena::need(p->pat[0].nnz, 8);        // Newton's Jacobian values (plain, BC'd)
     w += Arena::need(tv, 8);                       // transposed values
+    w += Arena::need(N, 8);                        // Chebyshev direction of multigrid level 0
     w += 4096;
+    for (size_t l = 0; l < p->mg.size(); ++l) {     // coarse multigrid levels live in the same arenas
+        size_t cs, cw;
+        child_bytes(p->mg[l], l + 1 == p->mg.size(), &cs, &cw);
+        s += cs;
+        w += cw;
+    }
     *static_bytes = s;
     *work_bytes = w;
     return FEMO_OK;
@@ -819,7 +973,10 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     p->nt_vals = p->wk.take<double>(p->pat[0].nnz);
     p->nt_vals_bc = p->wk.take<double>(p->pat[0].nnz);
     p->d_tvals = p->wk.take<double>(tv);
-    if (!p->d_tvals) return set_err(FEMO_EINVAL, "work arena too small");
+    p->kr_d = p->wk.take<double>(N);
+    if (!p->d_tvals || !p->kr_d) return set_err(FEMO_EINVAL, "work arena too small");
+    for (size_t l = 0; l < p->mg.size(); ++l)
+        if ((rc = upload_child(p, p->mg[l], l + 1 == p->mg.size()))) return rc;
     FEMO_CUDA(cudaMemsetAsync(p->d_scalars, 0, sizeof(double) * S_COUNT, p->stream));
     if (!p->h_pinned) FEMO_CUDA(cudaMallocHost((void **)&p->h_pinned, sizeof(double) * 64));
     FEMO_CUDA(cudaStreamSynchronize(p->stream));
@@ -838,7 +995,7 @@ int femo_set_coefficient(femo_problem *p, int slot, const double *d_values, int6
 
 int femo_problem_launch_count(const femo_problem *p, long long *count) {
     if (!p || !count) return set_err(FEMO_EINVAL, "femo_problem_launch_count: null");
-    *count = p->launches;
+    *count = total_launches(p);
     return FEMO_OK;
 }
 
@@ -939,11 +1096,11 @@ int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_
     if (which < 0 || which > p->nin || !d_vals || !d_x || !d_y) return set_err(FEMO_EINVAL, "femo_spmv: bad arguments");
     const Pattern &P = p->pat[which];
     const DevPattern &D = p->dpat[which];
-    if (!transpose) return launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, d_vals, d_x, d_y, nullptr);
+    if (!transpose) return launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, d_vals, d_x, d_y, nullptr, nullptr);
     k_permute<<<grid_for(P.nnz), kThreads, 0, p->stream>>>(D.t_perm, d_vals, p->d_tvals, P.nnz);
     p->launches++;
     FEMO_CHECK_LAUNCH();
-    return launch_spmv<false>(p, D.t_rb, D.t_nrb, D.t_rowptr, D.t_col, p->d_tvals, d_x, d_y, nullptr);
+    return launch_spmv<false>(p, D.t_rb, D.t_nrb, D.t_rowptr, D.t_col, p->d_tvals, d_x, d_y, nullptr, nullptr);
 }
 
 static void default_krylov(femo_krylov_opts &o) {
@@ -957,6 +1114,7 @@ static void default_krylov(femo_krylov_opts &o) {
 static int cg_solve(femo_problem *p, const double *vals, const double *b, double *x, femo_krylov_opts o,
                     femo_krylov_info *info) {
     default_krylov(o);
+    if (o.precond == 2 && !p->mg.empty()) return pcg_mg_solve(p, vals, b, x, o, info);
     const int64_t n = p->state.ndofs;
     const DevPattern &D = p->dpat[0];
     cudaStream_t st = p->stream;
@@ -968,7 +1126,7 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     k_dot<<<g, kThreads, 0, st>>>(b, b, n, pz);
     k_finalize<<<1, kThreads, 0, st>>>(pz, g, p->d_scalars, S_BB);
     // r = b - A x ; p = dinv r
-    if ((rc = launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, vals, x, p->kr_q, nullptr))) return rc;
+    if ((rc = launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, vals, x, p->kr_q, nullptr, nullptr))) return rc;
     ++spmvs;
     k_cg_init<<<g, kThreads, 0, st>>>(b, p->kr_q, p->kr_dinv, p->kr_r, p->kr_p, n, pz, pr);
     k_cg_scalars<<<1, kThreads, 0, st>>>(2, p->d_scalars, pz, pr, g);
@@ -988,7 +1146,7 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     while (!conv && it < o.max_it) {
         const int chunk = std::min(o.check_every, o.max_it - it);
         for (int k = 0; k < chunk; ++k) {
-            if ((rc = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, &np))) return rc;
+            if ((rc = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, nullptr, &np))) return rc;
             k_cg_scalars<<<1, kThreads, 0, st>>>(0, p->d_scalars, p->d_partials, nullptr, np);
             k_cg_update<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_p, p->kr_q, p->kr_dinv, x, p->kr_r, n, pz, pr);
             k_cg_scalars<<<1, kThreads, 0, st>>>(1, p->d_scalars, pz, pr, g);

@@ -1,0 +1,452 @@
+// multigrid.cuh -- geometric multigrid preconditioner for vertex-based spaces on
+// lattice meshes, used by the Krylov drivers in place of the reference's direct
+// LU (KSP preonly + PC lu/MUMPS, femo/fea/utils_dolfinx.py:405-408,476-512).
+//
+//   * levels: the lattice is halved (ceil) per direction until <= kMgCoarsest
+//     cells; levels need not be nested -- transfers evaluate the coarse P1
+//     basis at the fine nodes (matrix-free, R = P^T by construction)
+//   * coarse operators: rediscretised with the family's own Jacobian kernel on
+//     the coarse mesh, state interpolated to the coarse nodes, Dirichlet rows
+//     inherited geometrically
+//   * smoother: Chebyshev polynomial on the Jacobi-scaled operator, eigenvalue
+//     bound by Gershgorin (deterministic, no power iteration), same polynomial
+//     before and after the coarse correction => symmetric preconditioner for CG
+//   * coarsest level: explicit inverse computed by one CTA (Gauss-Jordan)
+//
+// Included by engine.cu (single translation unit).
+#pragma once
+#include "common.cuh"
+
+namespace femo {
+
+constexpr int kMgCoarsest = 8;      // stop coarsening a direction at <= 8 cells
+constexpr int kMgDenseMax = 512;    // largest coarsest-level system inverted explicitly
+
+struct Lattice {
+    int nx, ny;  // cells per direction; nodes are (nx+1) x (ny+1), node id = j*(nx+1)+i
+};
+
+// P1 hat function of a node of the "right"-diagonal triangulation, lattice units
+__device__ __forceinline__ double hat_p1(double dx, double dy) {
+    const double v = 1.0 - fmax(fmax(dx, dy), 0.0) + fmin(fmin(dx, dy), 0.0);
+    return v > 0.0 ? v : 0.0;
+}
+
+// dst(node) (+)= sum_k phi^src_k(x_node) src(k): prolongation (src = coarse) and
+// state interpolation (src = fine) share this kernel.
+template <bool ADD>
+__global__ void __launch_bounds__(kThreads)
+    k_lattice_interp(Lattice s, Lattice d, const double *__restrict__ src, double *__restrict__ dst,
+                     const uint8_t *__restrict__ dst_mask) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nd = (int64_t)(d.nx + 1) * (d.ny + 1);
+    if (idx >= nd) return;
+    if (dst_mask && dst_mask[idx]) {
+        if (!ADD) dst[idx] = 0.0;
+        return;
+    }
+    const int i = (int)(idx % (d.nx + 1)), j = (int)(idx / (d.nx + 1));
+    const double X = (double)i * ((double)s.nx / (double)d.nx), Y = (double)j * ((double)s.ny / (double)d.ny);
+    const int I = min((int)X, s.nx - 1), J = min((int)Y, s.ny - 1);
+    double acc = 0.0;
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const double w = hat_p1(X - (double)(I + a), Y - (double)(J + b));
+            if (w > 0.0) acc += w * src[(int64_t)(J + b) * (s.nx + 1) + (I + a)];
+        }
+    if (ADD) dst[idx] += acc;
+    else dst[idx] = acc;
+}
+
+// rc = P^T rf with the same weights as k_lattice_interp<coarse -> fine>
+__global__ void __launch_bounds__(kThreads)
+    k_lattice_restrict(Lattice f, Lattice c, const double *__restrict__ rf, double *__restrict__ rc,
+                       const uint8_t *__restrict__ mask_f, const uint8_t *__restrict__ mask_c) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nc = (int64_t)(c.nx + 1) * (c.ny + 1);
+    if (idx >= nc) return;
+    if (mask_c && mask_c[idx]) {
+        rc[idx] = 0.0;
+        return;
+    }
+    const int I = (int)(idx % (c.nx + 1)), J = (int)(idx / (c.nx + 1));
+    const double sx = (double)c.nx / (double)f.nx, sy = (double)c.ny / (double)f.ny;
+    const int ilo = max(0, (int)floor((double)(I - 1) / sx)), ihi = min(f.nx, (int)ceil((double)(I + 1) / sx));
+    const int jlo = max(0, (int)floor((double)(J - 1) / sy)), jhi = min(f.ny, (int)ceil((double)(J + 1) / sy));
+    double acc = 0.0;
+    for (int j = jlo; j <= jhi; ++j)
+        for (int i = ilo; i <= ihi; ++i) {
+            // the fine node must see (I,J) as a corner of its enclosing coarse cell, as the prolongation does
+            const double X = (double)i * sx, Y = (double)j * sy;
+            const int I0 = min((int)X, c.nx - 1), J0 = min((int)Y, c.ny - 1);
+            if (I < I0 || I > I0 + 1 || J < J0 || J > J0 + 1) continue;
+            const double w = hat_p1(X - (double)I, Y - (double)J);
+            const int64_t fi = (int64_t)j * (f.nx + 1) + i;
+            if (w > 0.0 && !(mask_f && mask_f[fi])) acc += w * rf[fi];
+        }
+    rc[idx] = acc;
+}
+
+// Gershgorin bound of D^-1 A (max_i sum_j |a_ij| / |a_ii|) and dinv in one pass
+__global__ void __launch_bounds__(kThreads)
+    k_diag_gershgorin(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ vals,
+                      double *__restrict__ dinv, int64_t n, double *__restrict__ partials) {
+    double mx = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double d = 1.0, s = 0.0;
+        for (int32_t t = rowptr[i]; t < rowptr[i + 1]; ++t) {
+            const double v = vals[t];
+            s += fabs(v);
+            if (col[t] == i) d = v;
+        }
+        const double di = (d != 0.0) ? 1.0 / d : 1.0;
+        dinv[i] = di;
+        mx = fmax(mx, s * fabs(di));
+    }
+    // block max
+    __shared__ double sh[kThreads];
+    sh[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = kThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(kThreads) k_max_finalize(const double *__restrict__ partials, int np, double *scalars, int slot) {
+    __shared__ double sh[kThreads];
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) mx = fmax(mx, partials[i]);
+    sh[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = kThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) scalars[slot] = sh[0];
+}
+
+// Chebyshev first step: d = c * dinv * r ; x (+)= d
+template <bool ZERO_GUESS>
+__global__ void __launch_bounds__(kThreads)
+    k_cheb_first(const double *__restrict__ r, const double *__restrict__ dinv, double c, double *__restrict__ d,
+                 double *__restrict__ x, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double di = c * dinv[i] * r[i];
+        d[i] = di;
+        x[i] = ZERO_GUESS ? di : x[i] + di;
+    }
+}
+
+// Chebyshev step k>=2: rout = rin - q ; d = c1 d + c2 dinv rout ; x += d
+__global__ void __launch_bounds__(kThreads)
+    k_cheb_step(const double *__restrict__ rin, const double *__restrict__ q, const double *__restrict__ dinv, double c1,
+                double c2, double *__restrict__ rout, double *__restrict__ d, double *__restrict__ x, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = rin[i] - q[i];
+        rout[i] = ri;
+        const double di = c1 * d[i] + c2 * dinv[i] * ri;
+        d[i] = di;
+        x[i] += di;
+    }
+}
+
+// one CTA: dense inverse of a small CSR matrix by Gauss-Jordan with partial pivoting
+__global__ void __launch_bounds__(kThreads)
+    k_dense_inverse(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ vals,
+                    int n, double *__restrict__ A, double *__restrict__ Inv) {
+    __shared__ double fac[kMgDenseMax];
+    __shared__ int piv;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < n * n; idx += kThreads) {
+        A[idx] = 0.0;
+        Inv[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kThreads)
+        for (int32_t t = rowptr[i]; t < rowptr[i + 1]; ++t) A[i * n + col[t]] = vals[t];
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        if (tid == 0) {
+            int best = k;
+            double bv = fabs(A[k * n + k]);
+            for (int i = k + 1; i < n; ++i) {
+                const double v = fabs(A[i * n + k]);
+                if (v > bv) { bv = v; best = i; }
+            }
+            piv = best;
+        }
+        __syncthreads();
+        const int pr = piv;
+        if (pr != k)
+            for (int j = tid; j < n; j += kThreads) {
+                double t = A[k * n + j]; A[k * n + j] = A[pr * n + j]; A[pr * n + j] = t;
+                t = Inv[k * n + j]; Inv[k * n + j] = Inv[pr * n + j]; Inv[pr * n + j] = t;
+            }
+        __syncthreads();
+        const double pv = 1.0 / A[k * n + k];
+        __syncthreads();
+        for (int j = tid; j < n; j += kThreads) {
+            A[k * n + j] *= pv;
+            Inv[k * n + j] *= pv;
+        }
+        for (int i = tid; i < n; i += kThreads) fac[i] = (i == k) ? 0.0 : A[i * n + k];
+        __syncthreads();
+        for (int idx = tid; idx < n * n; idx += kThreads) {
+            const int i = idx / n, j = idx % n;
+            const double f = fac[i];
+            if (f != 0.0) {
+                A[idx] -= f * A[k * n + j];
+                Inv[idx] -= f * Inv[k * n + j];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// x = Inv * b (tiny system: one warp per row)
+__global__ void __launch_bounds__(kThreads) k_dense_apply(const double *__restrict__ Inv, const double *__restrict__ b,
+                                                          double *__restrict__ x, int n) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double acc = 0.0;
+    for (int j = lane; j < n; j += 32) acc += Inv[row * n + j] * b[j];
+    acc = warp_sum(acc);
+    if (lane == 0) x[row] = acc;
+}
+
+// PCG vector kernels for a general preconditioner ---------------------------
+// x += alpha p ; r -= alpha q ; partial r.r
+__global__ void __launch_bounds__(kThreads)
+    k_pcg_update(const double *__restrict__ sc, const double *__restrict__ p, const double *__restrict__ q,
+                 double *__restrict__ x, double *__restrict__ r, int64_t n, double *__restrict__ prr) {
+    const double alpha = sc[S_ALPHA];
+    double rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        rr += ri * ri;
+    }
+    rr = block_sum(rr);
+    if (threadIdx.x == 0) prr[blockIdx.x] = rr;
+}
+
+// p = z + beta p   (first=true: p = z)
+__global__ void __launch_bounds__(kThreads)
+    k_pcg_dir(const double *__restrict__ sc, const double *__restrict__ z, double *__restrict__ p, int64_t n, int first) {
+    const double beta = first ? 0.0 : sc[S_BETA];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = z[i] + beta * p[i];
+}
+
+// r = b - q ; partial r.r
+__global__ void __launch_bounds__(kThreads)
+    k_residual_rr(const double *__restrict__ b, const double *__restrict__ q, double *__restrict__ r, int64_t n,
+                  double *__restrict__ prr) {
+    double rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = b[i] - q[i];
+        r[i] = ri;
+        rr += ri * ri;
+    }
+    rr = block_sum(rr);
+    if (threadIdx.x == 0) prr[blockIdx.x] = rr;
+}
+
+}  // namespace femo
+
+using namespace femo;
+
+// ===========================================================================
+// host side
+// ===========================================================================
+static inline Lattice lattice_of(const femo_problem *p) { return Lattice{p->mesh.n[0], p->mesh.n[1]}; }
+
+static long long total_launches(const femo_problem *p) {
+    long long n = p->launches;
+    for (const femo_problem *c : p->mg) n += c->launches;
+    return n;
+}
+
+// Chebyshev smoother of degree `deg` on level problem L: x ~ A^-1 b
+static int mg_smooth(femo_problem *L, const double *b, double *x, bool zero_guess, int deg, double ratio) {
+    femo_mg_level &M = L->mgl;
+    const int64_t n = L->state.ndofs;
+    const DevPattern &D = L->dpat[0];
+    cudaStream_t st = L->stream;
+    const int g = red_grid(L, n);
+    const double lmax = M.lmax, lmin = lmax / ratio;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    int rc;
+    const double *rin = b;
+    if (!zero_guess) {
+        if ((rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, x, M.r, b, nullptr))) return rc;
+        rin = M.r;
+    }
+    if (zero_guess) k_cheb_first<true><<<g, kThreads, 0, st>>>(rin, M.dinv, 1.0 / theta, M.d, x, n);
+    else k_cheb_first<false><<<g, kThreads, 0, st>>>(rin, M.dinv, 1.0 / theta, M.d, x, n);
+    L->launches++;
+    for (int k = 2; k <= deg; ++k) {
+        if ((rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, M.d, M.q, nullptr, nullptr))) return rc;
+        const double rho_new = 1.0 / (2.0 * sigma - rho);
+        k_cheb_step<<<g, kThreads, 0, st>>>(rin, M.q, M.dinv, rho_new * rho, 2.0 * rho_new / delta, M.r, M.d, x, n);
+        L->launches++;
+        rin = M.r;
+        rho = rho_new;
+    }
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
+struct MgParams {
+    int degree = 2;
+    double ratio = 8.0;
+};
+
+// one V-cycle: level lv solves A x = b approximately from a zero initial guess
+static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, const MgParams &mp) {
+    femo_problem *L = (lv == 0) ? root : root->mg[lv - 1];
+    const int nlev = (int)root->mg.size() + 1;
+    femo_mg_level &M = L->mgl;
+    const int64_t n = L->state.ndofs;
+    cudaStream_t st = L->stream;
+    int rc;
+    if (lv == nlev - 1) {
+        k_dense_apply<<<(int)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(M.dense, b, x, (int)n);
+        L->launches++;
+        FEMO_CHECK_LAUNCH();
+        return FEMO_OK;
+    }
+    femo_problem *C = root->mg[lv];
+    femo_mg_level &MC = C->mgl;
+    const DevPattern &D = L->dpat[0];
+    if ((rc = mg_smooth(L, b, x, true, mp.degree, mp.ratio))) return rc;
+    // r = b - A x ; restrict
+    if ((rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, x, M.r, b, nullptr))) return rc;
+    const int64_t nc = C->state.ndofs;
+    const uint8_t *mf = L->has_bc ? L->d_bc_mark : nullptr, *mc = C->has_bc ? C->d_bc_mark : nullptr;
+    k_lattice_restrict<<<grid_for(nc), kThreads, 0, st>>>(lattice_of(L), lattice_of(C), M.r, MC.b, mf, mc);
+    L->launches++;
+    if ((rc = mg_vcycle(root, lv + 1, MC.b, MC.x, mp))) return rc;
+    k_lattice_interp<true><<<grid_for(n), kThreads, 0, st>>>(lattice_of(C), lattice_of(L), MC.x, x, mf);
+    L->launches++;
+    FEMO_CHECK_LAUNCH();
+    return mg_smooth(L, b, x, false, mp.degree, mp.ratio);
+}
+
+// (re)build the hierarchy for the matrix `vals` of the root at the root's current state
+static int mg_setup(femo_problem *root, const double *vals) {
+    if (root->mg.empty()) return set_err(FEMO_ESTATE, "multigrid requested but femo_problem_enable_multigrid was not called before upload");
+    const int nlev = (int)root->mg.size() + 1;
+    int rc;
+    for (int lv = 0; lv < nlev; ++lv) {
+        femo_problem *L = (lv == 0) ? root : root->mg[lv - 1];
+        femo_mg_level &M = L->mgl;
+        cudaStream_t st = L->stream;
+        const int64_t n = L->state.ndofs;
+        if (lv == 0) {
+            M.vals = const_cast<double *>(vals);
+        } else {
+            femo_problem *F = (lv == 1) ? root : root->mg[lv - 2];
+            const double *uf = (lv == 1) ? root->coef[0] : F->mgl.u;
+            if (!uf) return set_err(FEMO_ESTATE, "multigrid setup: state coefficient not set");
+            k_lattice_interp<false><<<grid_for(n), kThreads, 0, st>>>(lattice_of(F), lattice_of(L), uf, M.u, nullptr);
+            L->launches++;
+            L->coef[0] = M.u;
+            L->coefn[0] = n;
+            if ((rc = femo_assemble_jacobian(L, L->has_bc ? nullptr : M.vals, L->has_bc ? M.vals : nullptr))) return rc;
+        }
+        const DevPattern &D = L->dpat[0];
+        if (lv == nlev - 1) {
+            if (n > kMgDenseMax) return set_err(FEMO_ELIMIT, "multigrid: coarsest level too large for the dense solve");
+            k_dense_inverse<<<1, kThreads, 0, st>>>(D.rowptr, D.col, M.vals, (int)n, M.dense_tmp, M.dense);
+            L->launches++;
+        } else {
+            const int g = red_grid(L, n);
+            k_diag_gershgorin<<<g, kThreads, 0, st>>>(D.rowptr, D.col, M.vals, M.dinv, n, L->d_partials);
+            k_max_finalize<<<1, kThreads, 0, st>>>(L->d_partials, g, L->d_scalars, S_TMP2);
+            L->launches += 2;
+            FEMO_CHECK_LAUNCH();
+            double lm;
+            if ((rc = read_scalars(L, S_TMP2, 1, &lm))) return rc;
+            M.lmax = lm;
+        }
+        FEMO_CHECK_LAUNCH();
+    }
+    return FEMO_OK;
+}
+
+// PCG with the V-cycle as preconditioner
+static int pcg_mg_solve(femo_problem *p, const double *vals, const double *b, double *x, femo_krylov_opts o,
+                        femo_krylov_info *info) {
+    const int64_t n = p->state.ndofs;
+    const DevPattern &D = p->dpat[0];
+    cudaStream_t st = p->stream;
+    double *pa = p->d_partials, *pb = p->d_partials + kMaxPartials;
+    const int g = red_grid(p, n);
+    MgParams mp;
+    if (o.cheb_degree > 0) mp.degree = o.cheb_degree;
+    int rc, np = 0, spmvs = 0;
+    // level-0 work vectors: the V-cycle's x is z (kr_z); r/d/q reuse Krylov buffers free at that point
+    p->mgl.dinv = p->kr_dinv;
+    p->mgl.r = p->kr_w;
+    p->mgl.d = p->kr_d;
+    p->mgl.q = p->kr_q;
+    if ((rc = mg_setup(p, vals))) return rc;
+    k_dot<<<g, kThreads, 0, st>>>(b, b, n, pa);
+    k_finalize<<<1, kThreads, 0, st>>>(pa, g, p->d_scalars, S_BB);
+    if ((rc = launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, vals, x, p->kr_q, nullptr, nullptr))) return rc;
+    ++spmvs;
+    k_residual_rr<<<g, kThreads, 0, st>>>(b, p->kr_q, p->kr_r, n, pb);
+    k_finalize<<<1, kThreads, 0, st>>>(pb, g, p->d_scalars, S_RR);
+    p->launches += 4;
+    FEMO_CHECK_LAUNCH();
+    double h[2];
+    if ((rc = read_scalars(p, S_RR, 1, &h[0]))) return rc;
+    if ((rc = read_scalars(p, S_BB, 1, &h[1]))) return rc;
+    const double bnorm = std::sqrt(h[1]);
+    double rnorm = std::sqrt(h[0]);
+    const double tol = std::max(o.rtol * bnorm, o.atol);
+    int it = 0;
+    bool conv = rnorm <= tol;
+    while (!conv && it < o.max_it) {
+        // z = M^-1 r ; rz' = r.z
+        if ((rc = mg_vcycle(p, 0, p->kr_r, p->kr_z, mp))) return rc;
+        k_dot<<<g, kThreads, 0, st>>>(p->kr_r, p->kr_z, n, pa);
+        if (it == 0) {
+            k_finalize<<<1, kThreads, 0, st>>>(pa, g, p->d_scalars, S_RZ);
+            k_pcg_dir<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_z, p->kr_p, n, 1);
+        } else {
+            k_cg_scalars<<<1, kThreads, 0, st>>>(1, p->d_scalars, pa, nullptr, g);   // beta = rz'/rz ; rz = rz'
+            k_pcg_dir<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_z, p->kr_p, n, 0);
+        }
+        if ((rc = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, nullptr, &np))) return rc;
+        k_cg_scalars<<<1, kThreads, 0, st>>>(0, p->d_scalars, p->d_partials, nullptr, np);          // alpha = rz/pq
+        k_pcg_update<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_p, p->kr_q, x, p->kr_r, n, pb);
+        k_finalize<<<1, kThreads, 0, st>>>(pb, g, p->d_scalars, S_RR);
+        p->launches += 6;
+        ++spmvs;
+        ++it;
+        FEMO_CHECK_LAUNCH();
+        if (it % o.check_every == 0 || it >= o.max_it) {
+            double rr;
+            if ((rc = read_scalars(p, S_RR, 1, &rr))) return rc;
+            rnorm = std::sqrt(rr);
+            if (!(rnorm == rnorm)) break;
+            conv = rnorm <= tol;
+        }
+    }
+    if (info) {
+        info->iterations = it;
+        info->converged = conv ? 1 : 0;
+        info->rnorm = rnorm;
+        info->bnorm = bnorm;
+        info->spmv_count = spmvs;
+    }
+    return FEMO_OK;
+}

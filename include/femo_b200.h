@@ -88,6 +88,12 @@ int femo_problem_gather_map(const femo_problem *p, int which, int32_t *ptr, int3
  * or after femo_problem_upload (after: synchronises); nlists = 0 clears. */
 int femo_problem_set_bc(femo_problem *p, const int32_t *dofs, const int32_t *list_ptr, int nlists, const double *g);
 
+/* Build the geometric-multigrid hierarchy used by Krylov precond = 2 (coarse
+ * lattices, Jacobian-only layouts).  Host only; must precede upload.  Scalar P1
+ * states on lattice triangle meshes. */
+int femo_problem_enable_multigrid(femo_problem *p);
+int femo_problem_mg_levels(const femo_problem *p);
+
 /* ---- device residency ------------------------------------------------------
  * Bytes the caller must provide: static (maps, patterns) and work (scratch,
  * Krylov vectors).  Upload copies the layout into d_static.  stream is a
@@ -137,8 +143,8 @@ typedef struct femo_krylov_opts {
     double rtol;      /* ||r|| <= rtol*||b||   */
     double atol;      /* or ||r|| <= atol      */
     int max_it;
-    int precond;      /* 0 Jacobi, 1 Chebyshev(cheb_degree) on Jacobi-scaled A */
-    int cheb_degree;
+    int precond;      /* 0 Jacobi, 2 geometric multigrid V-cycle (Chebyshev-Jacobi smoothing) */
+    int cheb_degree;  /* smoother degree of the V-cycle (default 2) */
     int method;       /* 0 CG, 1 GMRES(restart) */
     int restart;
     int check_every;  /* residual-norm host check period (>=1) */

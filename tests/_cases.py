@@ -15,7 +15,7 @@ def square_boundary_lists(coords):
 
 
 class Case:
-    def __init__(self, famid, n, ny=None, seed=0, bc='auto', g=None, upload=True, device=0):
+    def __init__(self, famid, n, ny=None, seed=0, bc='auto', g=None, upload=True, device=0, mg=False):
         self.famid, self.n = famid, n
         self.emesh = E.EngineMesh.unit_square(n, ny)
         self.omesh = om.unit_square_tri(n, ny)
@@ -29,6 +29,8 @@ class Case:
             self.F = fam.NonlinearPoissonP1(self.omesh)
             use_bc = bc is True
         self.p = E.EngineProblem(self.emesh, famid)
+        if mg:
+            self.p.enable_multigrid()
         self.bc = None
         if use_bc:
             lists = square_boundary_lists(self.omesh.coords)
