@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- state+adjoint solves/s on BASELINE.json's configs[1]:
+nonlinear Poisson (examples/nonlinear_poisson_opt), P1 on the unit square,
+n = 4000 (16 008 001 dofs, 32 000 000 cells, 112 024 001 nnz), f = 0.1, u0 = 0.
+
+One step = what one optimiser gradient evaluation triggers:
+SNES state solve (per Newton iteration: residual + Jacobian assembly + Krylov
+solve), linearisation (dR/du, dR/dm), output J, dJ/du, dJ/dm, one transposed
+(adjoint) Krylov solve and the dR/dm^T lambda product.
+
+  value  engine-level step, every input resident in HBM, CUDA events
+  e2e    the same step through the reference-facing API (FEAModel + Simulator:
+         numpy in, numpy out), host<->device copies inside the timed region
+  --impl reference   the oracle's direct-solve path (numpy assembly + SuperLU,
+         the reference's algorithm class) on host cores, bounded sample
+
+Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 4000]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'state+adjoint solves/s'
+UNIT = 'solves/s'
+N_DEFAULT = 4000
+KRYLOV_RTOL = 1e-10
+
+
+def workload(n):
+    return dict(workload='nonlinear_poisson_opt P1 unit square n=%d (%d dofs, %d cells), SNES + adjoint, f=0.1, u0=0'
+                % (n, (n + 1) ** 2, 2 * n * n), n=n, dofs=(n + 1) ** 2, cells=2 * n * n,
+                solver='SNES newtonls atol=rtol=1e-13; GMG-preconditioned CG rtol=%g replaces LU(MUMPS)' % KRYLOV_RTOL,
+                cache='working set (>10 GB) exceeds the 126 MB L2; no explicit flush')
+
+
+# ---------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------
+# engine-level step (inputs resident in HBM)
+# ---------------------------------------------------------------------------
+class EngineStep:
+    def __init__(self, n, device):
+        import torch
+        from femo_b200 import engine as E
+        self.torch = torch
+        p = E.EngineProblem(E.EngineMesh.unit_square(n), E.FAMILY_NLPOISSON_P1)
+        p.enable_multigrid()
+        p.upload(device)
+        self.p = p
+        self.u = p.new_vector(p.N, 0.0)
+        self.f = p.new_vector(p.M[0], 0.1)
+        p.set_coefficient(0, self.u)
+        p.set_coefficient(1, self.f)
+        nnz = p.pattern_info(0)['nnz']
+        self.nnz = nnz
+        self.vals = p.new_vector(nnz)
+        self.dv = p.new_vector(p.pattern_info(1)['nnz'])
+        self.dJdu = p.new_vector(p.N)
+        self.grad = p.new_vector(p.M[0])
+        self.lam = p.new_vector(p.N)
+        self.tmp = p.new_vector(p.M[0])
+        self.info = {}
+
+    def step(self):
+        p = self.p
+        self.u.zero_()                                        # same work every step (cudaMemset, not a kernel of ours)
+        ni = p.newton_solve(kind='SNES', krylov_rtol=KRYLOV_RTOL, precond=2, cheb_degree=2)
+        p.assemble_jacobian(plain=True, bc=False, out=self.vals)          # dR/du at the converged state
+        p.assemble_dRdm(0, self.dv)                                        # dR/df
+        J = p.assemble_output(0)                                           # objective (host scalar)
+        p.assemble_output_grad(0, 0, self.dJdu)
+        p.assemble_output_grad(0, 1, self.grad)
+        self.lam.zero_()
+        _, li = p.linear_solve(self.vals, self.dJdu, self.lam, transpose=True, rtol=KRYLOV_RTOL, precond=2, cheb_degree=2)
+        p.spmv(1, self.dv, self.lam, transpose=True, out=self.tmp)
+        p.axpy(-1.0, self.tmp, self.grad)                                  # dJ/df = pJ/pf - dRdf^T lambda
+        self.info = dict(newton_its=ni['iterations'], krylov_its=ni['krylov_iterations'], adjoint_its=li['iterations'],
+                         converged=bool(ni['converged']) and li['converged'], J=J)
+        return J
+
+
+def time_spmv(es, reps=50):
+    """Average launch duration of the dominant kernel (fine-level CSR SpMV) with CUDA events."""
+    torch = es.torch
+    p = es.p
+    x = p.new_vector(p.N, 1.0)
+    y = p.new_vector(p.N)
+    for _ in range(5):
+        p.spmv(0, es.vals, x, out=y)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        p.spmv(0, es.vals, x, out=y)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+# ---------------------------------------------------------------------------
+# API-level step (host buffers): the call a femo user makes
+# ---------------------------------------------------------------------------
+class ApiStep:
+    def __init__(self, n):
+        import numpy as np
+        from femo_b200.fea.fea_b200 import FEA, createUnitSquareMesh, FunctionSpace, Function, TestFunction
+        from femo_b200.forms.nonlinear_poisson import pdeRes, outputForm
+        from femo_b200.csdl_opt import FEAModel, Simulator
+        from femo_b200.fea import utils_b200
+        utils_b200.KRYLOV['rtol'] = KRYLOV_RTOL
+        mesh = createUnitSquareMesh(n)
+        fea = FEA(mesh)
+        f = Function(FunctionSpace(mesh, ('DG', 0)))
+        Vu = FunctionSpace(mesh, ('CG', 1))
+        u = Function(Vu)
+        res = pdeRes(u, TestFunction(Vu), f)
+        fea.add_input('f', f)
+        fea.add_state(name='u', function=u, residual_form=res, arguments=['f'])
+        fea.add_output(name='l2_functional', type='scalar', form=outputForm(u, f), arguments=['f', 'u'])
+        fea.PDE_SOLVER = 'SNES'
+        fea.REPORT = False
+        model = FEAModel(fea=[fea], debug_mode=False)
+        model.create_input('f', shape=fea.inputs_dict['f']['shape'], val=0.1)
+        self.sim = Simulator(model)
+        self.f0 = np.full(fea.inputs_dict['f']['shape'], 0.1)
+        self.u0 = np.zeros(fea.states_dict['u']['shape'])
+        self.fam = res.fam
+        self.np = np
+
+    def step(self):
+        sim = self.sim
+        sim['f'] = self.f0                       # host input of this step
+        sim['u'] = self.u0                       # same initial guess every step
+        sim.run()
+        g = sim.compute_totals('l2_functional', 'f')[('l2_functional', 'f')]
+        return float(sim['l2_functional'][0]), g
+
+
+# ---------------------------------------------------------------------------
+# CPU reference arm: the oracle's direct-solve path on a bounded sample
+# ---------------------------------------------------------------------------
+def cpu_step(n_sample):
+    import numpy as np
+    from oracle import mesh as om, families as fam, assembly as asm, solvers
+    key = ('cpu', n_sample)
+    if key not in _CACHE:
+        m = om.unit_square_tri(n_sample)
+        F = fam.NonlinearPoissonP1(m)
+        _CACHE[key] = (F, solvers.StatePath(F, None))
+    F, sp = _CACHE[key]
+    f = np.full(F.M, 0.1)
+    t = time.perf_counter()
+    u, _ = sp.solve_snes(np.zeros(F.N), [f])
+    J = asm.assemble_scalar(F.output(0, u, f))
+    g, _ = sp.total_derivative(0, u, [f])
+    return time.perf_counter() - t, J
+
+
+_CACHE = {}
+
+
+def cpu_baseline(n, n_sample=256, steps=1):
+    """Oracle port (numpy assembly + SuperLU, single thread) on an n_sample mesh,
+    scaled to the n-mesh LINEARLY in dofs (generous to the CPU: sparse LU is
+    superlinear).  solves/s on the full workload = (1/t) * dofs_sample/dofs_full."""
+    ts = [cpu_step(n_sample)[0] for _ in range(steps)]
+    t = sum(ts) / len(ts)
+    scale = (n_sample + 1) ** 2 / float((n + 1) ** 2)
+    return dict(value=scale / t, unit=UNIT, cores=1, kind='port',
+                sample='oracle (numpy assembly + SuperLU direct solves) on an n=%d mesh (%d dofs): %.2f s per '
+                       'state+adjoint solve, scaled linearly in dofs to n=%d' % (n_sample, (n_sample + 1) ** 2, t, n))
+
+
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='femo_b200')
+    ap.add_argument('--n', type=int, default=N_DEFAULT)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    a = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    W = max(a.warmup, 3)
+
+    if a.impl == 'reference':
+        if rank != 0:
+            return 0
+        n_sample = 256
+        for _ in range(W):
+            cpu_step(n_sample)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            cpu_step(n_sample)
+        dt = (time.perf_counter() - t0) / a.steps
+        scale = (n_sample + 1) ** 2 / float((a.n + 1) ** 2)
+        val = scale / dt
+        sample = ('oracle direct-solve path (numpy assembly + SuperLU; the reference runs dolfinx + MUMPS, not '
+                  'installable offline) on an n=%d mesh (%d dofs), %.2f s per state+adjoint solve, scaled linearly '
+                  'in dofs to n=%d' % (n_sample, (n_sample + 1) ** 2, dt, a.n))
+        print(json.dumps(dict(metric=METRIC, value=val, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=W,
+                              ms_per_step=1e3 / val, higher_is_better=True, scaling='weak', vs_baseline=None,
+                              dtype='f64', data='synthetic', config=workload(a.n), impl='reference',
+                              cpu_baseline=dict(value=val, unit=UNIT, cores=1, kind='port', sample=sample),
+                              e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps(dict(metric=METRIC, error='no CUDA device; femo_b200 has no CPU path')))
+        return 1
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    es = EngineStep(a.n, local_rank)
+    for _ in range(W):
+        es.step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = es.p.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        es.step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = es.p.launch_count() - l0
+    t_spmv = time_spmv(es)
+    clocks = sampler.stop()
+    tt = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    value = world * a.steps / (ms * 1e-3)          # replicas: every rank solves its own n-mesh problem
+
+    # e2e through the public API (host numpy in/out)
+    e2e = None
+    if not a.no_e2e:
+        info = dict(es.info)
+        del es.vals, es.dv                      # free engine-level buffers; the API path owns its own problem
+        p_keep = es.p
+        api = ApiStep(a.n) if world == 1 or True else None
+        for _ in range(W):
+            api.step()
+        prob = api.fam.problem
+        h0, d0 = prob.h2d_bytes, prob.d2h_bytes
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            api.step()
+        barrier()
+        dt = time.perf_counter() - t0
+        td = torch.tensor([dt], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dt = float(td.item())
+        e2e = dict(value=world * a.steps / dt, unit=UNIT, h2d_bytes_per_step=(prob.h2d_bytes - h0) // a.steps,
+                   d2h_bytes_per_step=(prob.d2h_bytes - d0) // a.steps, ms_per_step=dt * 1e3 / a.steps)
+        es.info = info
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        nnz, N = es.nnz, es.p.N
+        alg = 12.0 * nnz + 20.0 * N
+        ach = alg / t_spmv / 1e9
+        out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=W,
+                   ms_per_step=ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
+                   data='synthetic', config=dict(workload(a.n), parallelism='1 GPU' if world == 1 else
+                                                 '%d independent replicas of the n=%d problem (domain decomposition '
+                                                 'not in this round)' % (world, a.n)),
+                   clocks=clocks, gpu_launches=int(launches), e2e=e2e,
+                   roofline=dict(bound='hbm', kernel='femo::k_spmv (CSR-stream SpMV, fine-level Jacobian)',
+                                 achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,
+                                 algorithmic_bytes=alg, launch_ms=t_spmv * 1e3,
+                                 peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 (of fallback)'),
+                   step_info=es.info)
+        if not a.no_cpu:
+            out['cpu_baseline'] = cpu_baseline(a.n)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1103,6 +1103,16 @@ int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_
     return launch_spmv<false>(p, D.t_rb, D.t_nrb, D.t_rowptr, D.t_col, p->d_tvals, d_x, d_y, nullptr, nullptr);
 }
 
+int femo_axpy(femo_problem *p, double a, const double *d_x, double *d_y, int64_t n) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!d_x || !d_y || n < 0) return set_err(FEMO_EINVAL, "femo_axpy: bad arguments");
+    k_axpy<<<red_grid(p, n), kThreads, 0, p->stream>>>(a, d_x, d_y, n);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
 static void default_krylov(femo_krylov_opts &o) {
     if (o.rtol <= 0) o.rtol = 1e-10;
     if (o.atol < 0) o.atol = 0;

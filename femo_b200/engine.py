@@ -75,7 +75,7 @@ class EngineMesh:
         return c, l
 
     def __del__(self):
-        if getattr(self, '_h', None):
+        if getattr(self, '_h', None) and lib is not None:
             lib.femo_mesh_destroy(self._h)
             self._h = None
 
@@ -232,6 +232,10 @@ class EngineProblem:
         check(lib.femo_spmv(self._h, which, self._p(vals), self._p(x), self._p(out), 1 if transpose else 0))
         return out
 
+    def axpy(self, a, x, y):
+        check(lib.femo_axpy(self._h, float(a), self._p(x), self._p(y), x.numel()))
+        return y
+
     def linear_solve(self, vals, b, x=None, transpose=False, rtol=1e-10, atol=0.0, max_it=100000, check_every=1,
                      precond=0, cheb_degree=0):
         x = self.new_vector(self.N, 0.0) if x is None else x
@@ -262,6 +266,6 @@ class EngineProblem:
                     krylov_iterations=info.krylov_iterations, spmv_count=info.spmv_count)
 
     def __del__(self):
-        if getattr(self, '_h', None):
+        if getattr(self, '_h', None) and lib is not None:
             lib.femo_problem_destroy(self._h)
             self._h = None

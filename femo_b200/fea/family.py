@@ -61,6 +61,8 @@ class FormFamily:
     def problem(self):
         if self._prob is None:
             p = _E.EngineProblem(self.mesh._e, self.family_id, self.params)
+            if self.family_id in (_E.FAMILY_POISSON_P1, _E.FAMILY_NLPOISSON_P1):
+                p.enable_multigrid()         # GMG-preconditioned CG replaces the reference's LU
             p.upload(0)                      # raises FemoError without a CUDA device
             self._prob = p
         return self._prob

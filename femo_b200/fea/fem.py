@@ -179,6 +179,7 @@ class Function:
         self.name = name
         self._host = np.zeros(V.dim)
         self._dev = None            # torch tensor on the problem's device (a buffer, nothing more)
+        self._prob = None
         self._host_ver = 1          # bumped on every host write
         self._dev_ver = 0           # host version the device copy mirrors (-1: device is newer)
         self.vector = Vector(self)
@@ -187,8 +188,11 @@ class Function:
     # -- host/device coherence ------------------------------------------------
     def _host_array(self):
         if self._dev is not None and self._dev_ver == -1:
-            self._host[:] = self._dev.cpu().numpy()
+            import torch
+            torch.from_numpy(self._host).copy_(self._dev)          # D2H into the (pinned) host mirror
             self._dev_ver = self._host_ver
+            if self._prob is not None:
+                self._prob.d2h_bytes += self._host.nbytes
         return self._host
 
     def _host_changed(self):
@@ -211,6 +215,10 @@ class Function:
         if self._dev is None:
             self._dev = torch.empty(self._host.size, dtype=torch.float64, device=prob.device)
             self._dev_ver = 0
+            self._prob = prob
+            pinned = torch.empty(self._host.size, dtype=torch.float64).pin_memory().numpy()
+            pinned[:] = self._host                                 # re-home the host mirror in pinned memory
+            self._host = pinned
         if self._dev_ver != -1 and self._dev_ver != self._host_ver:
             self._dev.copy_(torch.from_numpy(self._host), non_blocking=False)
             self._dev_ver = self._host_ver

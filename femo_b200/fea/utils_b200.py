@@ -19,7 +19,7 @@ DOLFIN_EPS = 3E-16
 # Krylov settings that replace the reference's direct LU (KSP preonly + MUMPS,
 # utils_dolfinx.py:405-408,476-512).  rtol is tight enough for the 1e-8
 # derivative target of BASELINE.json.
-KRYLOV = dict(rtol=1e-12, max_it=200000, check_every=25)
+KRYLOV = dict(rtol=1e-12, max_it=200000, check_every=1, precond=2, cheb_degree=2)
 
 
 # ---- meshes (utils_dolfinx.py:136-153) -------------------------------------
@@ -232,7 +232,8 @@ def solveNonlinear(res, func, bc, solver, report, initialize):
     fam.apply_bcs(bc)
     try:
         info = p.newton_solve(kind=solver, krylov_rtol=KRYLOV['rtol'], krylov_max_it=KRYLOV['max_it'],
-                              check_every=KRYLOV['check_every'])
+                              check_every=KRYLOV['check_every'], precond=KRYLOV['precond'],
+                              cheb_degree=KRYLOV['cheb_degree'])
     finally:
         func.mark_device_written()
     if solver == 'SNES':
@@ -267,7 +268,8 @@ def _solve_into(A, b, x):
     xt = xf.device_tensor(p)
     xt.zero_()
     _, info = p.linear_solve(A.vals, bf.device_tensor(p), xt, transpose=A.transposed, rtol=KRYLOV['rtol'],
-                             max_it=KRYLOV['max_it'], check_every=KRYLOV['check_every'])
+                             max_it=KRYLOV['max_it'], check_every=KRYLOV['check_every'], precond=KRYLOV['precond'],
+                             cheb_degree=KRYLOV['cheb_degree'])
     xf.mark_device_written()
     fam.last_linear_info = info
     if not info['converged']:

@@ -139,6 +139,10 @@ int femo_assemble_output_grad(femo_problem *p, int out_id, int slot, double *d_o
  * y = A x (transpose=0) or y = A^T x (transpose=1). */
 int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_x, double *d_y, int transpose);
 
+/* y += a x on the problem's stream (the d_inputs accumulation of
+ * compute_jacvec_product, state_model.py:180-199, kept on the device). */
+int femo_axpy(femo_problem *p, double a, const double *d_x, double *d_y, int64_t n);
+
 typedef struct femo_krylov_opts {
     double rtol;      /* ||r|| <= rtol*||b||   */
     double atol;      /* or ||r|| <= atol      */
