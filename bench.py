@@ -305,6 +305,10 @@ def main():
         del es.vals, es.dv                      # free engine-level buffers; the API path owns its own problem
         p_keep = es.p
         api = ApiStep(a.n) if world == 1 or True else None
+        import contextlib
+        import io
+        quiet = contextlib.redirect_stdout(io.StringIO())    # the reference prints "Converged reason" per solve
+        quiet.__enter__()
         for _ in range(W):
             api.step()
         prob = api.fam.problem
@@ -315,6 +319,7 @@ def main():
             api.step()
         barrier()
         dt = time.perf_counter() - t0
+        quiet.__exit__(None, None, None)
         td = torch.tensor([dt], dtype=torch.float64, device='cuda')
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)

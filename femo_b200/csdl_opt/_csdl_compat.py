@@ -141,6 +141,15 @@ class Simulator:
                     self.vars[a] = np.broadcast_to(np.asarray(val, dtype=np.float64), shape).copy()
             self.vars.setdefault(out, np.zeros(op.output_meta[out]['shape']))
 
+    def _scratch(self, tag, like):
+        """Zeroed work array reused across calls (the backend's d_inputs / d_residuals vectors)."""
+        buf = self.__dict__.setdefault('_work', {}).get(tag)
+        if buf is None or buf.shape != like.shape:
+            buf = self._work[tag] = np.zeros_like(like)
+        else:
+            buf.fill(0.0)
+        return buf
+
     @staticmethod
     def _key(name):
         return name.split('.')[-1]
@@ -150,17 +159,19 @@ class Simulator:
 
     def __setitem__(self, name, value):
         k = self._key(name)
-        self.vars[k] = np.broadcast_to(np.asarray(value, dtype=np.float64), self.vars[k].shape).copy()
+        np.copyto(self.vars[k], np.broadcast_to(np.asarray(value, dtype=np.float64), self.vars[k].shape))
 
     def run(self):
         for op, args, out in self.model.ops:
             inputs = {a: self.vars[a] for a in args}
-            outputs = {out: self.vars[out].copy()}
+            outputs = {out: self.vars[out]}          # the operation reads the initial guess, then assigns
             if isinstance(op, CustomImplicitOperation):
                 op.solve_residual_equations(inputs, outputs)
             else:
                 op.compute(inputs, outputs)
-            self.vars[out] = np.array(outputs[out], dtype=np.float64).reshape(self.vars[out].shape)
+            res = np.asarray(outputs[out], dtype=np.float64).reshape(self.vars[out].shape)
+            if res is not self.vars[out]:
+                np.copyto(self.vars[out], res)       # CSDL copies on assignment
 
     def compute_totals(self, of, wrt):
         """Reverse-mode totals d(of)/d(wrt) for scalar `of` (the adjoint chain of
@@ -180,18 +191,25 @@ class Simulator:
                     if id(op) not in lin:
                         op.compute_derivatives(inputs, outputs, {})
                         lin[id(op)] = True
-                    d_res = {out: np.zeros_like(self.vars[out])}
+                    d_res = {out: self._scratch('res:' + out, self.vars[out])}
                     op.apply_inverse_jacobian({out: bar[out]}, d_res, 'rev')
-                    d_in = {a: np.zeros_like(self.vars[a]) for a in args}
-                    op.compute_jacvec_product(inputs, outputs, d_in, {}, {out: np.array(d_res[out])}, 'rev')
+                    d_in = {a: self._scratch('in:' + a, self.vars[a]) for a in args}
+                    op.compute_jacvec_product(inputs, outputs, d_in, {}, {out: np.asarray(d_res[out])}, 'rev')
                     for a in args:
-                        bar[a] = bar.get(a, 0.0) - d_in[a]
+                        if a in bar:
+                            bar[a] -= d_in[a]
+                        else:
+                            bar[a] = np.negative(d_in[a])
                 else:
                     derivs = {}
                     op.compute_derivatives(inputs, derivs)
                     seed = float(np.ravel(bar[out])[0])
                     for a in args:
-                        bar[a] = bar.get(a, 0.0) + seed * np.ravel(derivs[out, a])
+                        g = np.ravel(derivs[out, a])
+                        if a in bar:
+                            bar[a] += seed * g
+                        else:
+                            bar[a] = seed * g if seed != 1.0 else np.array(g)
             for w in wrt:
                 totals[(o, w)] = np.array(bar.get(self._key(w), np.zeros_like(self.vars[self._key(w)])))
         return totals

@@ -100,6 +100,7 @@ class EngineProblem:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._keep = {}       # tensors whose pointers the engine borrows
+        self._pinned = {}
         self.device = None
 
     # -- host-side layout queries ----------------------------------------
@@ -163,6 +164,16 @@ class EngineProblem:
         if fill is None:
             return torch.empty(n, dtype=torch.float64, device=self.device)
         return torch.full((n,), float(fill), dtype=torch.float64, device=self.device)
+
+    def pinned_buffer(self, n):
+        """Pinned host staging buffer of n doubles (ring of three per size)."""
+        import torch
+        ring = self._pinned.setdefault(n, [[], 0])
+        if len(ring[0]) < 3:
+            ring[0].append(torch.empty(n, dtype=torch.float64).pin_memory().numpy())
+            return ring[0][-1]
+        ring[1] = (ring[1] + 1) % 3
+        return ring[0][ring[1]]
 
     def to_device(self, array):
         import torch

@@ -141,6 +141,9 @@ class Vector:
         self._f._assign(values)
 
     def __setitem__(self, key, values):
+        if isinstance(key, slice) and key == slice(None) and isinstance(values, np.ndarray):
+            self._f._assign(values)              # whole-vector assignment: no D2H refresh needed first
+            return
         a = self._f._host_array()
         a[key] = values
         self._f._host_changed()
@@ -205,7 +208,12 @@ class Function:
         else:
             if v.size != self._host.size:
                 raise ValueError('size mismatch: function has %d dofs, got %d values' % (self._host.size, v.size))
-            self._host[:] = v
+            if v.__array_interface__['data'][0] != self._host.__array_interface__['data'][0]:
+                if v.size >= (1 << 20) and v.flags.c_contiguous:
+                    import torch                  # multi-threaded memcpy for large vectors
+                    torch.from_numpy(self._host).copy_(torch.from_numpy(v))
+                else:
+                    self._host[:] = v
         self._dev_ver = 0 if self._dev_ver == -1 else self._dev_ver
         self._host_changed()
 

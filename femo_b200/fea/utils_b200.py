@@ -118,7 +118,12 @@ class Mat:
 
 
 def _download(prob, tensor):
-    a = tensor.cpu().numpy()
+    """Device -> host through a pinned staging buffer (a ring of three per size,
+    so a result stays valid while the next two are produced; callers that keep
+    it longer copy it, as CSDL does on assignment)."""
+    import torch
+    a = prob.pinned_buffer(tensor.numel())
+    torch.from_numpy(a).copy_(tensor)
     prob.d2h_bytes += a.nbytes
     return a
 
