@@ -157,3 +157,45 @@ def test_newton_with_multigrid(cuda_device):
     assert relerr(c.d_u.cpu().numpy(), uo) < 1e-9
     assert info['iterations'] == oinfo['iterations']
     assert info['krylov_iterations'] <= 40
+
+
+import glob as _glob
+import os as _os
+_GOLD = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), 'golden')
+
+
+@pytest.mark.parametrize('path', sorted(_glob.glob(_os.path.join(_GOLD, 'family*_n*.npz'))))
+def test_against_golden_fixtures(cuda_device, path):
+    """CUDA path vs the committed oracle dumps (tests/golden/make_golden.py)."""
+    z = np.load(path)
+    famid = int(_os.path.basename(path)[6])
+    n = int(_os.path.basename(path).split('_n')[1].split('.')[0])
+    c = Case(famid, n, mg=True)
+    c.set_state(z['u'])
+    c.set_input(z['f'])
+    p = c.p
+    rp, col = p.pattern(0)
+    assert np.array_equal(rp, z['rowptr']) and np.array_equal(col, z['col'])
+    rp, col = p.pattern(1)
+    assert np.array_equal(rp, z['d_rowptr']) and np.array_equal(col, z['d_col'])
+    assert relerr(p.assemble_residual().cpu().numpy(), z['R']) < TOL
+    vals, vals_bc = p.assemble_jacobian(plain=True, bc=True)
+    assert relerr(vals.cpu().numpy(), z['J']) < TOL
+    assert relerr(vals_bc.cpu().numpy(), z['Jbc']) < TOL
+    assert relerr(p.assemble_dRdm(0).cpu().numpy(), z['D']) < TOL
+    assert abs(p.assemble_output(0) - float(z['out'])) <= TOL * abs(float(z['out']))
+    assert relerr(p.assemble_output_grad(0, 0).cpu().numpy(), z['out_du']) < TOL
+    assert relerr(p.assemble_output_grad(0, 1).cpu().numpy(), z['out_dm']) < TOL
+    assert relerr(p.newton_rhs(vals).cpu().numpy(), z['newton_F']) < TOL
+    # state solve + adjoint total derivative
+    c.set_input(z['f_solve'])
+    c.set_state(np.zeros(c.F.N))
+    info = p.newton_solve(kind='SNES' if famid == 2 else 'Newton', krylov_rtol=1e-13, precond=2)
+    assert info['iterations'] == int(z['newton_its'])
+    assert relerr(c.d_u.cpu().numpy(), z['u_solved']) < 1e-9
+    vals, vals_bc = p.assemble_jacobian(plain=True, bc=True)
+    lam, li = p.linear_solve(vals_bc if c.bc is not None else vals, p.assemble_output_grad(0, 0), transpose=True,
+                             rtol=1e-13, precond=2)
+    g = p.assemble_output_grad(0, 1).cpu().numpy() - p.spmv(1, p.assemble_dRdm(0), lam, transpose=True).cpu().numpy()
+    assert relerr(lam.cpu().numpy(), z['lam']) < 1e-8
+    assert relerr(g, z['total']) < 1e-8
