@@ -109,11 +109,43 @@ __global__ void __launch_bounds__(kThreads) k_finalize(const double *__restrict_
 // writes y coalesced.  Optional fused dot(x, y) for CG.  Rows longer than the
 // staging capacity are strided over by the whole CTA.
 // ===========================================================================
-template <bool DOT>
+// Row epilogues fused into the SpMV (applied by the thread that owns row i, acc = (A x)_i):
+//   EPI_PLAIN   y_i = acc                      (or b_i - acc when b is given: residual)
+//   EPI_CHEB0   r_i = b_i - acc ; d_i = c1 dinv_i r_i                      (first Chebyshev step, x untouched)
+//   EPI_CHEBK   r_i = rin_i - acc ; dn = c1 x_i + c2 dinv_i r_i ; dout_i = dn   (x is the previous direction)
+//               xacc_i: mode 0 += dn ; mode 1 += x_i + dn ; mode 2 = x_i + dn
+enum SpmvEpiKind { EPI_PLAIN = 0, EPI_CHEB0 = 1, EPI_CHEBK = 2 };
+struct SpmvEpi {
+    const double *b = nullptr, *dinv = nullptr, *rin = nullptr;
+    double *rout = nullptr, *dout = nullptr, *xacc = nullptr;
+    double c1 = 0.0, c2 = 0.0;
+    int xmode = 0;
+};
+
+template <int EPI>
+__device__ __forceinline__ void spmv_row_epilogue(const SpmvEpi &E, int64_t i, double acc, double xi, double *y) {
+    if (EPI == EPI_PLAIN) {
+        y[i] = E.b ? E.b[i] - acc : acc;
+    } else if (EPI == EPI_CHEB0) {
+        const double r = E.b[i] - acc;
+        E.rout[i] = r;
+        E.dout[i] = E.c1 * E.dinv[i] * r;
+    } else {
+        const double r = E.rin[i] - acc;
+        E.rout[i] = r;
+        const double dn = E.c1 * xi + E.c2 * E.dinv[i] * r;
+        E.dout[i] = dn;
+        if (E.xmode == 0) E.xacc[i] += dn;
+        else if (E.xmode == 1) E.xacc[i] += xi + dn;
+        else E.xacc[i] = xi + dn;
+    }
+}
+
+template <bool DOT, int EPI>
 __global__ void __launch_bounds__(kThreads)
     k_spmv(const int32_t *__restrict__ rb, int nrb, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-           const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
-           const double *__restrict__ bsub, double *__restrict__ partials) {
+           const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y, SpmvEpi E,
+           double *__restrict__ partials) {
     __shared__ double prod[kSpmvCap];
     __shared__ int32_t rp[kSpmvRows + 1];
     const int tid = threadIdx.x;
@@ -145,16 +177,18 @@ __global__ void __launch_bounds__(kThreads)
             for (int i = tid; i < nr; i += kThreads) {
                 double acc = 0.0;
                 for (int32_t k = rp[i] - s; k < rp[i + 1] - s; ++k) acc += prod[k];
-                y[r0 + i] = bsub ? bsub[r0 + i] - acc : acc;   // optional residual epilogue y = b - A x
-                if (DOT) dot += acc * __ldg(x + r0 + i);
+                const double xi = (DOT || EPI == EPI_CHEBK) ? __ldg(x + r0 + i) : 0.0;
+                spmv_row_epilogue<EPI>(E, r0 + i, acc, xi, y);
+                if (DOT) dot += acc * xi;
             }
         } else {  // a single long row: CTA-wide strided reduction (fixed order)
             double acc = 0.0;
             for (int32_t t = s + tid; t < e; t += kThreads) acc += ld_stream(vals + t) * __ldg(x + ld_stream(col + t));
             acc = block_sum(acc);
             if (tid == 0) {
-                y[r0] = bsub ? bsub[r0] - acc : acc;
-                if (DOT) dot += acc * __ldg(x + r0);
+                const double xi = __ldg(x + r0);
+                spmv_row_epilogue<EPI>(E, r0, acc, xi, y);
+                if (DOT) dot += acc * xi;
             }
         }
         __syncthreads();
@@ -384,16 +418,35 @@ static int segreduce(femo_problem *p, const DevVecMap &m, int64_t n, double *d_o
     return FEMO_OK;
 }
 
-template <bool DOT>
-static int launch_spmv(femo_problem *p, const int32_t *rb, int nrb, const int32_t *rowptr, const int32_t *col,
-                       const double *vals, const double *x, double *y, const double *bsub, int *np_out) {
+static inline int spmv_grid(const femo_problem *p, int nrb) {
     // persistent grid: every SM holds 8 CTAs and walks the row blocks with a grid stride, so the
     // rows in flight form one contiguous window (x stays L2-resident) and the dot partials are bounded
     int64_t cap = std::min<int64_t>((int64_t)p->num_sms * 8, kMaxPartials);
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nrb, cap));
-    k_spmv<DOT><<<grid, kThreads, 0, p->stream>>>(rb, nrb, rowptr, col, vals, x, y, bsub, p->d_partials);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(nrb, cap));
+}
+
+template <bool DOT>
+static int launch_spmv(femo_problem *p, const int32_t *rb, int nrb, const int32_t *rowptr, const int32_t *col,
+                       const double *vals, const double *x, double *y, const double *bsub, int *np_out) {
+    const int grid = spmv_grid(p, nrb);
+    SpmvEpi E;
+    E.b = bsub;
+    k_spmv<DOT, EPI_PLAIN><<<grid, kThreads, 0, p->stream>>>(rb, nrb, rowptr, col, vals, x, y, E, p->d_partials);
     p->launches++;
     if (np_out) *np_out = grid;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
+// SpMV on pattern 0 with a fused Chebyshev epilogue (multigrid smoother)
+static int launch_spmv_cheb(femo_problem *p, int kind, const double *vals, const double *x, const SpmvEpi &E) {
+    const DevPattern &D = p->dpat[0];
+    const int grid = spmv_grid(p, D.nrb);
+    if (kind == EPI_CHEB0)
+        k_spmv<false, EPI_CHEB0><<<grid, kThreads, 0, p->stream>>>(D.rb, D.nrb, D.rowptr, D.col, vals, x, nullptr, E, nullptr);
+    else
+        k_spmv<false, EPI_CHEBK><<<grid, kThreads, 0, p->stream>>>(D.rb, D.nrb, D.rowptr, D.col, vals, x, nullptr, E, nullptr);
+    p->launches++;
     FEMO_CHECK_LAUNCH();
     return FEMO_OK;
 }
@@ -1237,7 +1290,11 @@ int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton
         p->launches++;
         femo_krylov_info ki;
         memset(&ki, 0, sizeof(ki));
-        if ((rc = cg_solve(p, vals_bc, p->nt_b, p->nt_dx, opts->krylov, &ki))) return rc;
+        // inexact Newton: a linear residual below a tenth of the nonlinear absolute tolerance cannot
+        // change the SNES convergence decision, so the Krylov solve may stop there
+        femo_krylov_opts ko = opts->krylov;
+        if (snes) ko.atol = std::max(ko.atol, 0.1 * opts->atol);
+        if ((rc = cg_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki))) return rc;
         kit += ki.iterations;
         spmvs += ki.spmv_count;
         k_axpy<<<red_grid(p, n), kThreads, 0, st>>>(-1.0, p->nt_dx, x, n);

@@ -89,6 +89,43 @@ __global__ void __launch_bounds__(kThreads)
     rc[idx] = acc;
 }
 
+// 2:1 nested lattices (the common case): integer-only versions of the two transfers above.
+// Prolongation weights of the right-diagonal P1 hat: 1 at coincident nodes, 1/2 along x, y and the (1,1) diagonal.
+__global__ void __launch_bounds__(kThreads)
+    k_prolong_nested(Lattice f, const double *__restrict__ xc, double *__restrict__ xf, const uint8_t *__restrict__ mask_f) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nf = (int64_t)(f.nx + 1) * (f.ny + 1);
+    if (idx >= nf) return;
+    if (mask_f && mask_f[idx]) return;
+    const int i = (int)(idx % (f.nx + 1)), j = (int)(idx / (f.nx + 1));
+    const int cw = f.nx / 2 + 1;
+    const int I = i >> 1, J = j >> 1, oi = i & 1, oj = j & 1;
+    // (oi,oj): (0,0) -> c(I,J); (1,0) -> c(I,J)+c(I+1,J); (0,1) -> c(I,J)+c(I,J+1); (1,1) -> c(I,J)+c(I+1,J+1)
+    const double a = xc[(int64_t)J * cw + I];
+    const double v = (oi | oj) ? 0.5 * (a + xc[(int64_t)(J + oj) * cw + (I + oi)]) : a;
+    xf[idx] += v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_restrict_nested(Lattice f, const double *__restrict__ rf, double *__restrict__ rc,
+                      const uint8_t *__restrict__ mask_f, const uint8_t *__restrict__ mask_c) {
+    const int cw = f.nx / 2 + 1, ch = f.ny / 2 + 1;
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)cw * ch) return;
+    if (mask_c && mask_c[idx]) {
+        rc[idx] = 0.0;
+        return;
+    }
+    const int I = (int)(idx % cw), J = (int)(idx / cw);
+    const int i = 2 * I, j = 2 * J, fw = f.nx + 1;
+    auto at = [&](int ii, int jj) -> double {
+        if (ii < 0 || jj < 0 || ii > f.nx || jj > f.ny) return 0.0;
+        const int64_t k = (int64_t)jj * fw + ii;
+        return (mask_f && mask_f[k]) ? 0.0 : rf[k];
+    };
+    rc[idx] = at(i, j) + 0.5 * (at(i - 1, j) + at(i + 1, j) + at(i, j - 1) + at(i, j + 1) + at(i - 1, j - 1) + at(i + 1, j + 1));
+}
+
 // Gershgorin bound of D^-1 A (max_i sum_j |a_ij| / |a_ii|) and dinv in one pass
 __global__ void __launch_bounds__(kThreads)
     k_diag_gershgorin(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ vals,
@@ -272,40 +309,68 @@ static long long total_launches(const femo_problem *p) {
     return n;
 }
 
-// Chebyshev smoother of degree `deg` on level problem L: x ~ A^-1 b
+// d = c * dinv * b   (first Chebyshev direction from a zero initial guess)
+__global__ void __launch_bounds__(kThreads)
+    k_cheb_d0(const double *__restrict__ b, const double *__restrict__ dinv, double c, double *__restrict__ d, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        d[i] = c * dinv[i] * b[i];
+}
+
+// Chebyshev smoother of degree `deg` on level problem L: x ~ A^-1 b.  Every step after the
+// first is ONE kernel: the SpMV A d with the residual/direction/solution updates in its row epilogue.
 static int mg_smooth(femo_problem *L, const double *b, double *x, bool zero_guess, int deg, double ratio) {
     femo_mg_level &M = L->mgl;
     const int64_t n = L->state.ndofs;
-    const DevPattern &D = L->dpat[0];
     cudaStream_t st = L->stream;
     const int g = red_grid(L, n);
     const double lmax = M.lmax, lmin = lmax / ratio;
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
     double rho = 1.0 / sigma;
     int rc;
-    const double *rin = b;
-    if (!zero_guess) {
-        if ((rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, x, M.r, b, nullptr))) return rc;
-        rin = M.r;
-    }
-    if (zero_guess) k_cheb_first<true><<<g, kThreads, 0, st>>>(rin, M.dinv, 1.0 / theta, M.d, x, n);
-    else k_cheb_first<false><<<g, kThreads, 0, st>>>(rin, M.dinv, 1.0 / theta, M.d, x, n);
-    L->launches++;
-    for (int k = 2; k <= deg; ++k) {
-        if ((rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, M.d, M.q, nullptr, nullptr))) return rc;
-        const double rho_new = 1.0 / (2.0 * sigma - rho);
-        k_cheb_step<<<g, kThreads, 0, st>>>(rin, M.q, M.dinv, rho_new * rho, 2.0 * rho_new / delta, M.r, M.d, x, n);
+    double *dcur = M.d, *dnext = M.q;
+    const double *rin;
+    int xmode;
+    if (zero_guess) {
+        if (deg <= 1) {
+            k_cheb_first<true><<<g, kThreads, 0, st>>>(b, M.dinv, 1.0 / theta, dcur, x, n);
+            L->launches++;
+            FEMO_CHECK_LAUNCH();
+            return FEMO_OK;
+        }
+        k_cheb_d0<<<g, kThreads, 0, st>>>(b, M.dinv, 1.0 / theta, dcur, n);
         L->launches++;
+        rin = b;
+        xmode = 2;                 // x = d0 + d1
+    } else {
+        SpmvEpi E;                 // r = b - A x ; d0 = dinv r / theta
+        E.b = b; E.dinv = M.dinv; E.rout = M.r; E.dout = dcur; E.c1 = 1.0 / theta;
+        if ((rc = launch_spmv_cheb(L, EPI_CHEB0, M.vals, x, E))) return rc;
+        if (deg <= 1) {
+            k_axpy<<<g, kThreads, 0, st>>>(1.0, dcur, x, n);
+            L->launches++;
+            FEMO_CHECK_LAUNCH();
+            return FEMO_OK;
+        }
         rin = M.r;
+        xmode = 1;                 // x += d0 + d1
+    }
+    for (int k = 2; k <= deg; ++k) {
+        const double rho_new = 1.0 / (2.0 * sigma - rho);
+        SpmvEpi E;
+        E.dinv = M.dinv; E.rin = rin; E.rout = M.r; E.dout = dnext; E.xacc = x;
+        E.c1 = rho_new * rho; E.c2 = 2.0 * rho_new / delta; E.xmode = xmode;
+        if ((rc = launch_spmv_cheb(L, EPI_CHEBK, M.vals, dcur, E))) return rc;
+        std::swap(dcur, dnext);
+        rin = M.r;
+        xmode = 0;
         rho = rho_new;
     }
-    FEMO_CHECK_LAUNCH();
     return FEMO_OK;
 }
 
 struct MgParams {
     int degree = 2;
-    double ratio = 8.0;
+    double ratio = 4.0;
 };
 
 // one V-cycle: level lv solves A x = b approximately from a zero initial guess
@@ -330,10 +395,14 @@ static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, con
     if ((rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, x, M.r, b, nullptr))) return rc;
     const int64_t nc = C->state.ndofs;
     const uint8_t *mf = L->has_bc ? L->d_bc_mark : nullptr, *mc = C->has_bc ? C->d_bc_mark : nullptr;
-    k_lattice_restrict<<<grid_for(nc), kThreads, 0, st>>>(lattice_of(L), lattice_of(C), M.r, MC.b, mf, mc);
+    const Lattice lf = lattice_of(L), lc = lattice_of(C);
+    const bool nested = (lf.nx == 2 * lc.nx) && (lf.ny == 2 * lc.ny);
+    if (nested) k_restrict_nested<<<grid_for(nc), kThreads, 0, st>>>(lf, M.r, MC.b, mf, mc);
+    else k_lattice_restrict<<<grid_for(nc), kThreads, 0, st>>>(lf, lc, M.r, MC.b, mf, mc);
     L->launches++;
     if ((rc = mg_vcycle(root, lv + 1, MC.b, MC.x, mp))) return rc;
-    k_lattice_interp<true><<<grid_for(n), kThreads, 0, st>>>(lattice_of(C), lattice_of(L), MC.x, x, mf);
+    if (nested) k_prolong_nested<<<grid_for(n), kThreads, 0, st>>>(lf, MC.x, x, mf);
+    else k_lattice_interp<true><<<grid_for(n), kThreads, 0, st>>>(lc, lf, MC.x, x, mf);
     L->launches++;
     FEMO_CHECK_LAUNCH();
     return mg_smooth(L, b, x, false, mp.degree, mp.ratio);
@@ -391,6 +460,7 @@ static int pcg_mg_solve(femo_problem *p, const double *vals, const double *b, do
     const int g = red_grid(p, n);
     MgParams mp;
     if (o.cheb_degree > 0) mp.degree = o.cheb_degree;
+    if (o.cheb_ratio > 1.0) mp.ratio = o.cheb_ratio;
     int rc, np = 0, spmvs = 0;
     // level-0 work vectors: the V-cycle's x is z (kr_z); r/d/q reuse Krylov buffers free at that point
     p->mgl.dinv = p->kr_dinv;

@@ -248,10 +248,10 @@ class EngineProblem:
         return y
 
     def linear_solve(self, vals, b, x=None, transpose=False, rtol=1e-10, atol=0.0, max_it=100000, check_every=1,
-                     precond=0, cheb_degree=0):
+                     precond=0, cheb_degree=0, cheb_ratio=0.0):
         x = self.new_vector(self.N, 0.0) if x is None else x
         o = KrylovOpts(rtol=rtol, atol=atol, max_it=max_it, precond=precond, cheb_degree=cheb_degree, method=0,
-                       restart=0, check_every=check_every)
+                       restart=0, check_every=check_every, cheb_ratio=cheb_ratio)
         info = KrylovInfo()
         check(lib.femo_linear_solve(self._h, self._p(vals), self._p(b), self._p(x), 1 if transpose else 0,
                                     C.byref(o), C.byref(info)))
@@ -259,7 +259,7 @@ class EngineProblem:
                        bnorm=info.bnorm, spmv_count=info.spmv_count)
 
     def newton_solve(self, kind='Newton', atol=None, rtol=None, stol=1e-8, max_it=None, krylov_rtol=1e-10,
-                     krylov_max_it=100000, check_every=1, precond=0, cheb_degree=0):
+                     krylov_max_it=100000, check_every=1, precond=0, cheb_degree=0, cheb_ratio=0.0):
         """kind 'Newton' = dolfinx NewtonSolver defaults of the reference (3 fixed
         iterations, utils_dolfinx.py:419-425); 'SNES' = PETSc newtonls (:376-416)."""
         snes = (kind == 'SNES')
@@ -270,7 +270,8 @@ class EngineProblem:
         o.stol = stol
         o.max_it = (100 if snes else 3) if max_it is None else max_it
         o.krylov = KrylovOpts(rtol=krylov_rtol, atol=0.0, max_it=krylov_max_it, precond=precond,
-                              cheb_degree=cheb_degree, method=0, restart=0, check_every=check_every)
+                              cheb_degree=cheb_degree, method=0, restart=0, check_every=check_every,
+                              cheb_ratio=cheb_ratio)
         info = NewtonInfo()
         check(lib.femo_newton_solve(self._h, C.byref(o), C.byref(info)))
         return dict(iterations=info.iterations, converged=info.converged, fnorm0=info.fnorm0, fnorm=info.fnorm,

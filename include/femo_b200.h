@@ -152,6 +152,7 @@ typedef struct femo_krylov_opts {
     int method;       /* 0 CG, 1 GMRES(restart) */
     int restart;
     int check_every;  /* residual-norm host check period (>=1) */
+    double cheb_ratio; /* smoother targets [lmax/ratio, lmax] of D^-1 A (default 8) */
 } femo_krylov_opts;
 
 typedef struct femo_krylov_info {

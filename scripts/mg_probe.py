@@ -24,13 +24,14 @@ if fam == 1:
 vals, vals_bc = p.assemble_jacobian(plain=True, bc=(fam == 1))
 v = vals_bc if fam == 1 else vals
 b = p.assemble_residual()
-for deg in (1, 2, 3, 4):
+import itertools
+for deg, ratio in ((1, 2.0), (1, 4.0), (2, 2.0), (2, 3.0), (2, 4.0), (2, 6.0), (3, 6.0)):
     for rep in range(2):
         x = p.new_vector(N, 0.0)
         torch.cuda.synchronize(); t = time.time()
-        x, info = p.linear_solve(v, b, x, rtol=1e-10, precond=2, cheb_degree=deg, max_it=200)
+        x, info = p.linear_solve(v, b, x, rtol=1e-10, precond=2, cheb_degree=deg, cheb_ratio=ratio, max_it=200)
         torch.cuda.synchronize(); dt = time.time() - t
-    print('deg %d: %.1f ms  %s' % (deg, dt * 1e3, info))
+    print('deg %d ratio %4.0f: %.1f ms  its %d' % (deg, ratio, dt * 1e3, info['iterations']))
 u.zero_()
 torch.cuda.synchronize(); t = time.time()
 info = p.newton_solve(kind='SNES', krylov_rtol=1e-10, precond=2)
