@@ -55,6 +55,7 @@ SIGNATURES = {
     'femo_mesh_copy': (C.c_int, [_P, C.c_int, _P]),
     'femo_mesh_destroy': (None, [_P]),
     'femo_problem_create': (C.c_int, [_P, C.c_int, _DP, C.c_int, C.POINTER(_P)]),
+    'femo_problem_create_tagged': (C.c_int, [_P, C.c_int, _DP, C.c_int, _P, C.c_int, C.POINTER(_P)]),
     'femo_problem_destroy': (None, [_P]),
     'femo_problem_sizes': (C.c_int, [_P, _I64P]),
     'femo_problem_pattern_info': (C.c_int, [_P, C.c_int, _I64P]),

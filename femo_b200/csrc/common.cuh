@@ -104,10 +104,16 @@ struct femo_problem {
     double params[8] = {0};
     femo::Space state, in[4], aux[4];
     int nin = 0, naux = 0, nout = 0;
-    bool facet_terms = false;
-    std::vector<femo::IntegralBlock> blk_cells, blk_full;
+    // integral blocks by mask: 1 = all cells, 2 = facets carrying facet integrals, 3 = both
+    int res_mask = 1, jac_mask = 1;
+    int out_mask[4] = {1, 1, 1, 1};        // blocks of output k's functional
+    int out_du_mask[4] = {1, 1, 1, 1};     // blocks of d(output k)/d(state); 0 = identically zero
+    int out_dm_mask[4] = {1, 1, 1, 1};     // same wrt input 0
+    bool symmetric = true;
+    std::vector<int32_t> fb_cell, fb_local;   // the facets of block 2 (all exterior, or the tagged subset)
+    std::vector<femo::IntegralBlock> blk[4];
     femo::Pattern pat[5];
-    femo::VecMap vm_state_full, vm_state_cells, vm_in[4];
+    femo::VecMap vm_state[4], vm_in[4];     // vm_state indexed by block mask
     // Dirichlet data (host)
     bool has_bc = false;
     std::vector<uint8_t> bc_mark, bcflag;
@@ -120,9 +126,9 @@ struct femo_problem {
     int num_sms = 148;
     femo::Arena st, wk;
     double *d_coords = nullptr;
-    int32_t *d_cellsT = nullptr, *d_bf_cell = nullptr, *d_bf_local = nullptr;
+    int32_t *d_cellsT = nullptr, *d_fb_cell = nullptr, *d_fb_local = nullptr;
     femo::DevPattern dpat[5];
-    femo::DevVecMap dvm_state_full, dvm_state_cells, dvm_in[4];
+    femo::DevVecMap dvm_state[4], dvm_in[4];
     uint8_t *d_bc_mark = nullptr;
     double *d_bc_g = nullptr, *d_bc_diag = nullptr;
     int32_t *d_lift_rows = nullptr;
@@ -141,6 +147,7 @@ struct femo_problem {
     femo_mg_level mgl;
     femo_problem *parent = nullptr;
     double *kr_d = nullptr;
+    double *d_dense = nullptr, *d_dense_tmp = nullptr;   // explicit inverse for small systems (precond 3)
     // counters (bench: how many of our kernels were launched)
     long long launches = 0;
 };

@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "families.cuh"
+#include "families2.cuh"
 
 namespace femo {
 
@@ -344,9 +345,9 @@ static TriArgs tri_args(femo_problem *p, double *out) {
     A.coords = p->d_coords;
     A.cellsT = p->d_cellsT;
     A.ncells = p->mesh.ncells;
-    A.bf_cell = p->d_bf_cell;
-    A.bf_local = p->d_bf_local;
-    A.nfacets = (int64_t)p->mesh.bf_cell.size();
+    A.bf_cell = p->d_fb_cell;
+    A.bf_local = p->d_fb_local;
+    A.nfacets = (int64_t)p->fb_cell.size();
     A.u = p->coef[0];
     A.f = p->coef[1];
     A.uex = p->coef[2];
@@ -356,50 +357,106 @@ static TriArgs tri_args(femo_problem *p, double *out) {
     return A;
 }
 
-// run the element kernels of `op` into scratch (cells, then facets when the op has them)
-static int run_elements(femo_problem *p, int op) {
+static BeamArgs beam_args(femo_problem *p, int out_id, double *out) {
+    BeamArgs A;
+    A.coords = p->d_coords; A.cellsT = p->d_cellsT; A.ncells = p->mesh.ncells;
+    A.fb_cell = p->d_fb_cell; A.fb_local = p->d_fb_local; A.nfacets = (int64_t)p->fb_cell.size();
+    A.u = p->coef[0]; A.t = p->coef[1];
+    A.E = p->params[0]; A.width = p->params[1]; A.L = p->params[2]; A.f = p->params[3];
+    A.out_id = out_id; A.out = out;
+    return A;
+}
+
+static QuadArgs quad_args(femo_problem *p, int out_id, double *out) {
+    QuadArgs A;
+    A.coords = p->d_coords; A.cellsT = p->d_cellsT; A.ncells = p->mesh.ncells;
+    A.fb_cell = p->d_fb_cell; A.fb_local = p->d_fb_local; A.nfacets = (int64_t)p->fb_cell.size();
+    A.u = p->coef[0]; A.rho = p->coef[1];
+    A.nu = p->params[0]; A.fx = p->params[1]; A.fy = p->params[2]; A.penal = p->params[3];
+    A.volume = (p->mesh.hi[0] - p->mesh.lo[0]) * (p->mesh.hi[1] - p->mesh.lo[1]);
+    A.out_id = out_id; A.out = out;
+    return A;
+}
+
+// number of scratch planes per entity of an op
+static int op_planes(const femo_problem *p, int op) {
+    const int nd = p->state.ndpc;
+    switch (op) {
+        case OP_RES: case OP_OUT_DU: return nd;
+        case OP_JAC: return nd * nd;
+        case OP_DRDM: return nd * p->in[0].ndpc;
+        case OP_OUT_DM: return p->in[0].ndpc;
+        default: return 1;
+    }
+}
+
+// Run the element kernels of `op` (for output ops: of output `out_id`) over the blocks in
+// `mask` into scratch: cells first, then the facet block at offset ncells*planes.
+static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
     const int64_t nc = p->mesh.ncells;
-    const int64_t nf = (int64_t)p->mesh.bf_cell.size();
+    const int64_t nf = (int64_t)p->fb_cell.size();
     cudaStream_t st = p->stream;
     int rc;
     if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
     if (op != OP_JAC && (rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
+    double *cells_out = p->d_scratch;
+    double *facets_out = p->d_scratch + ((mask & 1) ? nc * op_planes(p, op) : 0);
+    const int gc = grid_for(nc), gf = grid_for(std::max<int64_t>(nf, 1));
+#define FEMO_LAUNCH_OPS(KERNEL, GRID, ARGS)                                                   \
+    switch (op) {                                                                             \
+        case OP_RES: KERNEL<OP_RES><<<GRID, kThreads, 0, st>>>(ARGS); break;                  \
+        case OP_JAC: KERNEL<OP_JAC><<<GRID, kThreads, 0, st>>>(ARGS); break;                  \
+        case OP_DRDM: KERNEL<OP_DRDM><<<GRID, kThreads, 0, st>>>(ARGS); break;                \
+        case OP_OUT: KERNEL<OP_OUT><<<GRID, kThreads, 0, st>>>(ARGS); break;                  \
+        case OP_OUT_DU: KERNEL<OP_OUT_DU><<<GRID, kThreads, 0, st>>>(ARGS); break;            \
+        case OP_OUT_DM: KERNEL<OP_OUT_DM><<<GRID, kThreads, 0, st>>>(ARGS); break;            \
+    }                                                                                         \
+    p->launches++;
     switch (p->family) {
         case FEMO_FAMILY_POISSON_P1: {
             if (op == OP_OUT || op == OP_OUT_DU)
                 if ((rc = need_coef(p, 2, p->aux[0].ndofs, "u_ex"))) return rc;
-            TriArgs A = tri_args(p, p->d_scratch);
-            const int g = grid_for(nc);
-            switch (op) {
-                case OP_RES: k_poisson_p1_cell<OP_RES><<<g, kThreads, 0, st>>>(A); break;
-                case OP_JAC: k_poisson_p1_cell<OP_JAC><<<g, kThreads, 0, st>>>(A); break;
-                case OP_DRDM: k_poisson_p1_cell<OP_DRDM><<<g, kThreads, 0, st>>>(A); break;
-                case OP_OUT: k_poisson_p1_cell<OP_OUT><<<g, kThreads, 0, st>>>(A); break;
-                case OP_OUT_DU: k_poisson_p1_cell<OP_OUT_DU><<<g, kThreads, 0, st>>>(A); break;
-                case OP_OUT_DM: k_poisson_p1_cell<OP_OUT_DM><<<g, kThreads, 0, st>>>(A); break;
-            }
-            p->launches++;
+            TriArgs A = tri_args(p, cells_out);
+            FEMO_LAUNCH_OPS(k_poisson_p1_cell, gc, A)
             break;
         }
         case FEMO_FAMILY_NLPOISSON_P1: {
-            TriArgs A = tri_args(p, p->d_scratch);
-            const int g = grid_for(nc);
-            switch (op) {
-                case OP_RES: k_nlpoisson_p1_cell<OP_RES><<<g, kThreads, 0, st>>>(A); break;
-                case OP_JAC: k_nlpoisson_p1_cell<OP_JAC><<<g, kThreads, 0, st>>>(A); break;
-                case OP_DRDM: k_nlpoisson_p1_cell<OP_DRDM><<<g, kThreads, 0, st>>>(A); break;
-                case OP_OUT: k_nlpoisson_p1_cell<OP_OUT><<<g, kThreads, 0, st>>>(A); break;
-                case OP_OUT_DU: k_nlpoisson_p1_cell<OP_OUT_DU><<<g, kThreads, 0, st>>>(A); break;
-                case OP_OUT_DM: k_nlpoisson_p1_cell<OP_OUT_DM><<<g, kThreads, 0, st>>>(A); break;
+            if (mask & 1) {
+                TriArgs A = tri_args(p, cells_out);
+                FEMO_LAUNCH_OPS(k_nlpoisson_p1_cell, gc, A)
             }
-            p->launches++;
-            if (op == OP_RES) {
-                TriArgs F = tri_args(p, p->d_scratch + nc * 3);
-                k_nlpoisson_p1_facet<OP_RES><<<grid_for(nf), kThreads, 0, st>>>(F);
+            if ((mask & 2) && nf > 0) {
+                TriArgs F = tri_args(p, facets_out);
+                if (op == OP_RES) k_nlpoisson_p1_facet<OP_RES><<<gf, kThreads, 0, st>>>(F);
+                else k_nlpoisson_p1_facet<OP_JAC><<<gf, kThreads, 0, st>>>(F);
                 p->launches++;
-            } else if (op == OP_JAC) {
-                TriArgs F = tri_args(p, p->d_scratch + nc * 9);
-                k_nlpoisson_p1_facet<OP_JAC><<<grid_for(nf), kThreads, 0, st>>>(F);
+            }
+            break;
+        }
+        case FEMO_FAMILY_EB_BEAM: {
+            if (mask & 1) {
+                BeamArgs A = beam_args(p, out_id, cells_out);
+                FEMO_LAUNCH_OPS(k_beam_cell, gc, A)
+            }
+            if ((mask & 2) && nf > 0) {
+                BeamArgs F = beam_args(p, out_id, facets_out);
+                if (op == OP_RES) k_beam_facet<OP_RES><<<gf, kThreads, 0, st>>>(F);
+                else if (op == OP_OUT) k_beam_facet<OP_OUT><<<gf, kThreads, 0, st>>>(F);
+                else k_beam_facet<OP_OUT_DU><<<gf, kThreads, 0, st>>>(F);
+                p->launches++;
+            }
+            break;
+        }
+        case FEMO_FAMILY_SIMP_Q1: {
+            if (mask & 1) {
+                QuadArgs A = quad_args(p, out_id, cells_out);
+                FEMO_LAUNCH_OPS(k_simp_q1_cell, gc, A)
+            }
+            if ((mask & 2) && nf > 0) {
+                QuadArgs F = quad_args(p, out_id, facets_out);
+                if (op == OP_RES) k_simp_q1_facet<OP_RES><<<gf, kThreads, 0, st>>>(F);
+                else if (op == OP_OUT) k_simp_q1_facet<OP_OUT><<<gf, kThreads, 0, st>>>(F);
+                else k_simp_q1_facet<OP_OUT_DU><<<gf, kThreads, 0, st>>>(F);
                 p->launches++;
             }
             break;
@@ -407,6 +464,7 @@ static int run_elements(femo_problem *p, int op) {
         default:
             return set_err(FEMO_EINVAL, "family has no device kernels in this build");
     }
+#undef FEMO_LAUNCH_OPS
     FEMO_CHECK_LAUNCH();
     return FEMO_OK;
 }
@@ -567,7 +625,7 @@ void femo_mesh_destroy(femo_mesh *m) { delete m; }
 
 // ---- problem layout -------------------------------------------------------
 static int create_problem_impl(const Mesh &mesh, int family, const double *params, int nparams, bool jac_only,
-                               femo_problem **out) {
+                               const int32_t *tagged, int ntagged, femo_problem **out) {
     femo_problem *p = new femo_problem();
     p->mesh = mesh;
     p->family = family;
@@ -588,30 +646,65 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
                     p->aux[0].init(M, EL_VERTEX, 1);
                     if (nparams < 1) p->params[0] = 1e-6;
                 } else {
-                    p->facet_terms = true;
+                    p->res_mask = 3;
+                    p->jac_mask = 3;
                     if (nparams < 1) p->params[0] = 6e-7;
                     if (nparams < 2) p->params[1] = 10.0;
                 }
                 break;
+            case FEMO_FAMILY_EB_BEAM:
+                if (M.kind != MESH_INTERVAL) throw LayoutError{FEMO_EINVAL, "family needs an interval mesh"};
+                p->state.init(M, EL_HERMITE3, 2);
+                p->nin = 1;
+                p->in[0].init(M, EL_DG0, 1);
+                p->nout = 2;
+                if (nparams < 4) { p->params[0] = 1.0; p->params[1] = 0.1; p->params[2] = 1.0; p->params[3] = -1.0; }
+                p->res_mask = 3;                               // cells + tip load ds(100)
+                p->out_mask[0] = 2; p->out_du_mask[0] = 2; p->out_dm_mask[0] = 0;   // compliance
+                p->out_mask[1] = 1; p->out_du_mask[1] = 0; p->out_dm_mask[1] = 1;   // volume
+                break;
+            case FEMO_FAMILY_SIMP_Q1:
+                if (M.kind != MESH_QUAD) throw LayoutError{FEMO_EINVAL, "family needs a quadrilateral mesh"};
+                p->state.init(M, EL_VERTEX, 2);
+                p->nin = 1;
+                p->in[0].init(M, EL_DG0, 1);
+                p->nout = 2;
+                if (nparams < 4) { p->params[0] = 0.3; p->params[1] = 0.0; p->params[2] = -0.25; p->params[3] = 3.0; }
+                p->res_mask = 3;                               // cells + traction ds(100)
+                p->out_mask[0] = 1; p->out_du_mask[0] = 0; p->out_dm_mask[0] = 1;   // average density
+                p->out_mask[1] = 2; p->out_du_mask[1] = 2; p->out_dm_mask[1] = 0;   // compliance
+                break;
             default:
                 throw LayoutError{FEMO_EINVAL, "unknown form family"};
         }
-        IntegralBlock cells;
-        cells.ne = M.ncells;
-        p->blk_cells = {cells};
-        p->blk_full = p->blk_cells;
-        if (p->facet_terms) {
-            IntegralBlock fb;
-            fb.ne = (int64_t)M.bf_cell.size();
-            fb.ent_cell = M.bf_cell.data();
-            p->blk_full.push_back(fb);
+        // block 2: all exterior facets (Nitsche) or the tagged subset (ds(tag) of the examples)
+        if (family == FEMO_FAMILY_NLPOISSON_P1) {
+            p->fb_cell = M.bf_cell;
+            p->fb_local = M.bf_local;
+        } else {
+            for (int k = 0; k < ntagged; ++k) {
+                if (tagged[k] < 0 || tagged[k] >= (int32_t)M.bf_cell.size())
+                    throw LayoutError{FEMO_EINVAL, "tagged facet index out of range"};
+                p->fb_cell.push_back(M.bf_cell[tagged[k]]);
+                p->fb_local.push_back(M.bf_local[tagged[k]]);
+            }
         }
-        build_pattern(M, p->state, p->state, p->blk_full, p->pat[0]);
+        IntegralBlock cells, facets;
+        cells.ne = M.ncells;
+        facets.ne = (int64_t)p->fb_cell.size();
+        facets.ent_cell = p->fb_cell.data();
+        p->blk[1] = {cells};
+        p->blk[2] = {facets};
+        p->blk[3] = {cells, facets};
+        build_pattern(M, p->state, p->state, p->blk[p->jac_mask], p->pat[0]);
         if (!jac_only) {  // coarse multigrid levels only ever assemble dR/du
-            for (int s = 0; s < p->nin; ++s) build_pattern(M, p->state, p->in[s], p->blk_cells, p->pat[1 + s]);
-            build_vecmap(M, p->state, p->blk_full, p->vm_state_full);
-            if (p->facet_terms) build_vecmap(M, p->state, p->blk_cells, p->vm_state_cells);
-            for (int s = 0; s < p->nin; ++s) build_vecmap(M, p->in[s], p->blk_cells, p->vm_in[s]);
+            for (int s = 0; s < p->nin; ++s) build_pattern(M, p->state, p->in[s], p->blk[1], p->pat[1 + s]);
+            bool need[4] = {false, false, false, false};
+            need[p->res_mask] = true;
+            for (int k = 0; k < p->nout; ++k) need[p->out_du_mask[k]] = true;
+            for (int m = 1; m < 4; ++m)
+                if (need[m]) build_vecmap(M, p->state, p->blk[m], p->vm_state[m]);
+            for (int s = 0; s < p->nin; ++s) build_vecmap(M, p->in[s], p->blk[1], p->vm_in[s]);
         }
     } catch (const LayoutError &e) {
         delete p;
@@ -627,7 +720,14 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
 int femo_problem_create(const femo_mesh *m, int family, const double *params, int nparams, femo_problem **out) {
     if (!m || !out) return set_err(FEMO_EINVAL, "femo_problem_create: null");
     if (nparams < 0 || nparams > 8) return set_err(FEMO_EINVAL, "femo_problem_create: nparams out of range");
-    return create_problem_impl(m->m, family, params, nparams, false, out);
+    return create_problem_impl(m->m, family, params, nparams, false, nullptr, 0, out);
+}
+
+int femo_problem_create_tagged(const femo_mesh *m, int family, const double *params, int nparams,
+                               const int32_t *facet_ids, int nfacets, femo_problem **out) {
+    if (!m || !out || nfacets < 0 || (nfacets > 0 && !facet_ids)) return set_err(FEMO_EINVAL, "femo_problem_create_tagged: bad arguments");
+    if (nparams < 0 || nparams > 8) return set_err(FEMO_EINVAL, "femo_problem_create_tagged: nparams out of range");
+    return create_problem_impl(m->m, family, params, nparams, false, facet_ids, nfacets, out);
 }
 
 int femo_problem_enable_multigrid(femo_problem *p) {
@@ -643,7 +743,7 @@ int femo_problem_enable_multigrid(femo_problem *p) {
         Mesh cm;
         make_unit_square_tri(nx, ny, p->mesh.lo, p->mesh.hi, cm);
         femo_problem *c = nullptr;
-        int rc = create_problem_impl(cm, p->family, p->params, 8, true, &c);
+        int rc = create_problem_impl(cm, p->family, p->params, 8, true, nullptr, 0, &c);
         if (rc) return rc;
         c->parent = p;
         p->mg.push_back(c);
@@ -667,7 +767,7 @@ int femo_problem_sizes(const femo_problem *p, int64_t s[16]) {
     s[0] = p->state.ndofs; s[1] = p->nin; s[2] = p->naux; s[3] = p->nout;
     for (int i = 0; i < p->nin; ++i) s[4 + i] = p->in[i].ndofs;
     for (int i = 0; i < p->naux; ++i) s[8 + i] = p->aux[i].ndofs;
-    s[12] = (int64_t)p->mesh.bf_cell.size();
+    s[12] = (int64_t)p->fb_cell.size();
     return FEMO_OK;
 }
 
@@ -777,7 +877,7 @@ static void child_bytes(const femo_problem *c, bool coarsest, size_t *sb, size_t
     const size_t N = (size_t)c->state.ndofs;
     size_t s = 0, w = 0;
     s += Arena::need(M.coords.size(), 8) + Arena::need(M.cells.size(), 4);
-    s += Arena::need(std::max<size_t>(1, M.bf_cell.size()), 4) * 2;
+    s += Arena::need(std::max<size_t>(1, c->fb_cell.size()), 4) * 2;
     s += pattern_bytes(c->pat[0], true);
     s += Arena::need(N, 1) + 2 * Arena::need(N, 8) + Arena::need(N, 4) + 1024;
     w += Arena::need(c->pat[0].nnz, 8) + 7 * Arena::need(N, 8);
@@ -811,8 +911,8 @@ static int upload_child(femo_problem *root, femo_problem *c, bool coarsest) {
         if ((rc = put(c->d_cellsT, T))) return rc;
         FEMO_CUDA(cudaStreamSynchronize(root->stream));
     }
-    if ((rc = put(c->d_bf_cell, M.bf_cell))) return rc;
-    if ((rc = put(c->d_bf_local, M.bf_local))) return rc;
+    if ((rc = put(c->d_fb_cell, c->fb_cell))) return rc;
+    if ((rc = put(c->d_fb_local, c->fb_local))) return rc;
     const Pattern &P = c->pat[0];
     DevPattern &D = c->dpat[0];
     if ((rc = put(D.rowptr, P.rowptr))) return rc;
@@ -860,9 +960,9 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     const int64_t N = p->state.ndofs;
     size_t s = 0;
     s += Arena::need(M.coords.size(), 8) + Arena::need(M.cells.size(), 4);
-    s += Arena::need(M.bf_cell.size(), 4) + Arena::need(M.bf_local.size(), 4);
+    s += 2 * Arena::need(std::max<size_t>(1, p->fb_cell.size()), 4);
     for (int w = 0; w <= p->nin; ++w) s += pattern_bytes(p->pat[w], w == 0);
-    s += vecmap_bytes(p->vm_state_full) + vecmap_bytes(p->vm_state_cells);
+    for (int m = 1; m < 4; ++m) s += vecmap_bytes(p->vm_state[m]);
     for (int i = 0; i < p->nin; ++i) s += vecmap_bytes(p->vm_in[i]);
     s += Arena::need(N, 1) + 2 * Arena::need(N, 8) + Arena::need(N, 4);  // Dirichlet arrays (settable after upload)
     s += 4096;
@@ -871,7 +971,7 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
         scratch = std::max<size_t>(scratch, p->pat[w].scratch_len);
         tv = std::max<size_t>(tv, p->pat[w].nnz);
     }
-    scratch = std::max<size_t>(scratch, p->vm_state_full.scratch_len);
+    for (int m = 1; m < 4; ++m) scratch = std::max<size_t>(scratch, p->vm_state[m].scratch_len);
     for (int i = 0; i < p->nin; ++i) scratch = std::max<size_t>(scratch, p->vm_in[i].scratch_len);
     scratch = std::max<size_t>(scratch, (size_t)M.ncells);
     size_t w = 0;
@@ -881,6 +981,7 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     w += 2 * Arena::need(p->pat[0].nnz, 8);        // Newton's Jacobian values (plain, BC'd)
     w += Arena::need(tv, 8);                       // transposed values
     w += Arena::need(N, 8);                        // Chebyshev direction of multigrid level 0
+    if (N <= kMgDenseMax) w += 2 * Arena::need((size_t)N * N, 8);   // explicit inverse (precond 3)
     w += 4096;
     for (size_t l = 0; l < p->mg.size(); ++l) {     // coarse multigrid levels live in the same arenas
         size_t cs, cw;
@@ -920,8 +1021,8 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
         if ((rc = up(p, p->d_cellsT, T))) return rc;
         FEMO_CUDA(cudaStreamSynchronize(p->stream));  // T goes out of scope
     }
-    if ((rc = up(p, p->d_bf_cell, M.bf_cell))) return rc;
-    if ((rc = up(p, p->d_bf_local, M.bf_local))) return rc;
+    if ((rc = up(p, p->d_fb_cell, p->fb_cell))) return rc;
+    if ((rc = up(p, p->d_fb_local, p->fb_local))) return rc;
     for (int w = 0; w <= p->nin; ++w) {
         const Pattern &P = p->pat[w];
         DevPattern &D = p->dpat[w];
@@ -947,13 +1048,10 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
             D.t_nrb = (int)P.t_rb.size() - 1;
         }
     }
-    if ((rc = up(p, p->dvm_state_full.ptr, p->vm_state_full.ptr))) return rc;
-    if ((rc = up(p, p->dvm_state_full.src, p->vm_state_full.src))) return rc;
-    if (p->facet_terms) {
-        if ((rc = up(p, p->dvm_state_cells.ptr, p->vm_state_cells.ptr))) return rc;
-        if ((rc = up(p, p->dvm_state_cells.src, p->vm_state_cells.src))) return rc;
-    } else {
-        p->dvm_state_cells = p->dvm_state_full;
+    for (int m = 1; m < 4; ++m) {
+        if (p->vm_state[m].ptr.empty()) continue;
+        if ((rc = up(p, p->dvm_state[m].ptr, p->vm_state[m].ptr))) return rc;
+        if ((rc = up(p, p->dvm_state[m].src, p->vm_state[m].src))) return rc;
     }
     for (int i = 0; i < p->nin; ++i) {
         if ((rc = up(p, p->dvm_in[i].ptr, p->vm_in[i].ptr))) return rc;
@@ -1007,7 +1105,7 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
         scratch = std::max<size_t>(scratch, p->pat[w].scratch_len);
         tv = std::max<size_t>(tv, p->pat[w].nnz);
     }
-    scratch = std::max<size_t>(scratch, p->vm_state_full.scratch_len);
+    for (int m = 1; m < 4; ++m) scratch = std::max<size_t>(scratch, p->vm_state[m].scratch_len);
     for (int i = 0; i < p->nin; ++i) scratch = std::max<size_t>(scratch, p->vm_in[i].scratch_len);
     scratch = std::max<size_t>(scratch, (size_t)M.ncells);
     p->scratch_len = scratch;
@@ -1027,6 +1125,10 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     p->nt_vals_bc = p->wk.take<double>(p->pat[0].nnz);
     p->d_tvals = p->wk.take<double>(tv);
     p->kr_d = p->wk.take<double>(N);
+    if (N <= kMgDenseMax) {
+        p->d_dense = p->wk.take<double>((size_t)N * N);
+        p->d_dense_tmp = p->wk.take<double>((size_t)N * N);
+    }
     if (!p->d_tvals || !p->kr_d) return set_err(FEMO_EINVAL, "work arena too small");
     for (size_t l = 0; l < p->mg.size(); ++l)
         if ((rc = upload_child(p, p->mg[l], l + 1 == p->mg.size()))) return rc;
@@ -1057,15 +1159,15 @@ int femo_assemble_residual(femo_problem *p, double *d_out) {
     int rc;
     if ((rc = need_device(p))) return rc;
     if (!d_out) return set_err(FEMO_EINVAL, "femo_assemble_residual: null output");
-    if ((rc = run_elements(p, OP_RES))) return rc;
-    return segreduce(p, p->dvm_state_full, p->state.ndofs, d_out);
+    if ((rc = run_elements(p, OP_RES, p->res_mask))) return rc;
+    return segreduce(p, p->dvm_state[p->res_mask], p->state.ndofs, d_out);
 }
 
 int femo_assemble_jacobian(femo_problem *p, double *d_vals, double *d_vals_bc) {
     int rc;
     if ((rc = need_device(p))) return rc;
     if (!d_vals && !d_vals_bc) return set_err(FEMO_EINVAL, "femo_assemble_jacobian: both outputs null");
-    if ((rc = run_elements(p, OP_JAC))) return rc;
+    if ((rc = run_elements(p, OP_JAC, p->jac_mask))) return rc;
     const DevPattern &D = p->dpat[0];
     const int64_t nnz = p->pat[0].nnz;
     k_segreduce_jac<<<grid_for(nnz), kThreads, 0, p->stream>>>(D.gptr, D.gsrc, p->d_scratch,
@@ -1080,7 +1182,7 @@ int femo_assemble_dRdm(femo_problem *p, int slot, double *d_vals) {
     int rc;
     if ((rc = need_device(p))) return rc;
     if (slot < 0 || slot >= p->nin || !d_vals) return set_err(FEMO_EINVAL, "femo_assemble_dRdm: bad slot/output");
-    if ((rc = run_elements(p, OP_DRDM))) return rc;
+    if ((rc = run_elements(p, OP_DRDM, 1))) return rc;
     const DevPattern &D = p->dpat[1 + slot];
     const int64_t nnz = p->pat[1 + slot].nnz;
     k_segreduce<<<grid_for(nnz), kThreads, 0, p->stream>>>(D.gptr, D.gsrc, p->d_scratch, d_vals, nnz);
@@ -1119,8 +1221,9 @@ int femo_assemble_output(femo_problem *p, int out_id, double *h_value) {
     int rc;
     if ((rc = need_device(p))) return rc;
     if (out_id < 0 || out_id >= p->nout || !h_value) return set_err(FEMO_EINVAL, "femo_assemble_output: bad output id");
-    if ((rc = run_elements(p, OP_OUT))) return rc;
-    const int64_t n = p->mesh.ncells;
+    const int om = p->out_mask[out_id];
+    if ((rc = run_elements(p, OP_OUT, om, out_id))) return rc;
+    const int64_t n = ((om & 1) ? p->mesh.ncells : 0) + ((om & 2) ? (int64_t)p->fb_cell.size() : 0);
     int g = red_grid(p, n);
     k_sum<<<g, kThreads, 0, p->stream>>>(p->d_scratch, n, p->d_partials);
     k_finalize<<<1, kThreads, 0, p->stream>>>(p->d_partials, g, p->d_scalars, S_TMP1);
@@ -1134,12 +1237,18 @@ int femo_assemble_output_grad(femo_problem *p, int out_id, int slot, double *d_o
     if ((rc = need_device(p))) return rc;
     if (out_id < 0 || out_id >= p->nout || !d_out || slot < 0 || slot > p->nin)
         return set_err(FEMO_EINVAL, "femo_assemble_output_grad: bad arguments");
-    if (slot == 0) {
-        if ((rc = run_elements(p, OP_OUT_DU))) return rc;
-        return segreduce(p, p->dvm_state_cells, p->state.ndofs, d_out);
+    const int mask = (slot == 0) ? p->out_du_mask[out_id] : p->out_dm_mask[out_id];
+    const int64_t n = (slot == 0) ? p->state.ndofs : p->in[slot - 1].ndofs;
+    if (mask == 0) {   // the functional does not depend on this argument
+        FEMO_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * n, p->stream));
+        return FEMO_OK;
     }
-    if ((rc = run_elements(p, OP_OUT_DM))) return rc;
-    return segreduce(p, p->dvm_in[slot - 1], p->in[slot - 1].ndofs, d_out);
+    if (slot == 0) {
+        if ((rc = run_elements(p, OP_OUT_DU, mask, out_id))) return rc;
+        return segreduce(p, p->dvm_state[mask], n, d_out);
+    }
+    if ((rc = run_elements(p, OP_OUT_DM, mask, out_id))) return rc;
+    return segreduce(p, p->dvm_in[slot - 1], n, d_out);
 }
 
 // ---- linear algebra -------------------------------------------------------
@@ -1177,7 +1286,7 @@ static void default_krylov(femo_krylov_opts &o) {
 static int cg_solve(femo_problem *p, const double *vals, const double *b, double *x, femo_krylov_opts o,
                     femo_krylov_info *info) {
     default_krylov(o);
-    if (o.precond == 2 && !p->mg.empty()) return pcg_mg_solve(p, vals, b, x, o, info);
+    if ((o.precond == 2 && !p->mg.empty()) || o.precond == 3) return pcg_mg_solve(p, vals, b, x, o, info);
     const int64_t n = p->state.ndofs;
     const DevPattern &D = p->dpat[0];
     cudaStream_t st = p->stream;

@@ -467,7 +467,13 @@ static int pcg_mg_solve(femo_problem *p, const double *vals, const double *b, do
     p->mgl.r = p->kr_w;
     p->mgl.d = p->kr_d;
     p->mgl.q = p->kr_q;
-    if ((rc = mg_setup(p, vals))) return rc;
+    const bool dense = (o.precond == 3);
+    if (dense) {   // small systems: explicit inverse (the exact analogue of the reference's LU)
+        if (!p->d_dense) return set_err(FEMO_ELIMIT, "precond 3 (dense direct) needs N <= 512");
+        k_dense_inverse<<<1, kThreads, 0, st>>>(D.rowptr, D.col, vals, (int)n, p->d_dense_tmp, p->d_dense);
+        p->launches++;
+        FEMO_CHECK_LAUNCH();
+    } else if ((rc = mg_setup(p, vals))) return rc;
     k_dot<<<g, kThreads, 0, st>>>(b, b, n, pa);
     k_finalize<<<1, kThreads, 0, st>>>(pa, g, p->d_scalars, S_BB);
     if ((rc = launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, vals, x, p->kr_q, nullptr, nullptr))) return rc;
@@ -486,7 +492,10 @@ static int pcg_mg_solve(femo_problem *p, const double *vals, const double *b, do
     bool conv = rnorm <= tol;
     while (!conv && it < o.max_it) {
         // z = M^-1 r ; rz' = r.z
-        if ((rc = mg_vcycle(p, 0, p->kr_r, p->kr_z, mp))) return rc;
+        if (dense) {
+            k_dense_apply<<<(int)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(p->d_dense, p->kr_r, p->kr_z, (int)n);
+            p->launches++;
+        } else if ((rc = mg_vcycle(p, 0, p->kr_r, p->kr_z, mp))) return rc;
         k_dot<<<g, kThreads, 0, st>>>(p->kr_r, p->kr_z, n, pa);
         if (it == 0) {
             k_finalize<<<1, kThreads, 0, st>>>(pa, g, p->d_scalars, S_RZ);

@@ -84,12 +84,17 @@ class EngineProblem:
     """One form family instantiated on a mesh: dofmaps, CSR patterns and gather
     maps on the host; after `upload()` the device-resident assembly / solve path."""
 
-    def __init__(self, mesh, family, params=()):
+    def __init__(self, mesh, family, params=(), tagged=None):
         self.mesh = mesh
         self.family = family
         h = C.c_void_p()
         pa = (C.c_double * max(1, len(params)))(*params)
-        check(lib.femo_problem_create(mesh._h, int(family), pa, len(params), C.byref(h)))
+        if tagged is None:
+            check(lib.femo_problem_create(mesh._h, int(family), pa, len(params), C.byref(h)))
+        else:   # facets of a tagged measure ds(tag): indices into mesh.exterior_facets()
+            tg = np.ascontiguousarray(tagged, dtype=np.int32).ravel()
+            check(lib.femo_problem_create_tagged(mesh._h, int(family), pa, len(params), _np_ptr(tg), tg.size,
+                                                 C.byref(h)))
         self._h = h
         s = (C.c_int64 * 16)()
         check(lib.femo_problem_sizes(self._h, s))

@@ -12,25 +12,27 @@ from .. import engine as _E
 
 
 class FormFamily:
-    def __init__(self, family_id, mesh, state, inputs, params=()):
+    def __init__(self, family_id, mesh, state, inputs, params=(), tagged=None):
         self.family_id = family_id
         self.mesh = mesh
         self.state = state
         self.inputs = list(inputs)
         self.aux = []
         self.params = list(params)
+        self.tagged = None if tagged is None else np.asarray(tagged, dtype=np.int32)
+        self.precond = None
         self._prob = None
         self._bc_sig = None
         self._ptrs = {}
 
     # -- registry: forms built from the same (state, inputs) share one family --
     @classmethod
-    def get(cls, family_id, mesh, state, inputs, params=()):
+    def get(cls, family_id, mesh, state, inputs, params=(), tagged=None):
         reg = state.__dict__.setdefault('_femo_families', {})
         key = (family_id,) + tuple(id(f) for f in inputs)
         fam = reg.get(key)
         if fam is None:
-            fam = reg[key] = cls(family_id, mesh, state, inputs, params)
+            fam = reg[key] = cls(family_id, mesh, state, inputs, params, tagged)
         return fam
 
     def set_aux(self, index, function):
@@ -60,9 +62,14 @@ class FormFamily:
     @property
     def problem(self):
         if self._prob is None:
-            p = _E.EngineProblem(self.mesh._e, self.family_id, self.params)
+            p = _E.EngineProblem(self.mesh._e, self.family_id, self.params, self.tagged)
+            # what replaces the reference's LU: GMG-preconditioned CG where a lattice hierarchy exists,
+            # the explicit inverse for tiny systems, Jacobi-CG otherwise
             if self.family_id in (_E.FAMILY_POISSON_P1, _E.FAMILY_NLPOISSON_P1):
-                p.enable_multigrid()         # GMG-preconditioned CG replaces the reference's LU
+                p.enable_multigrid()
+                self.precond = 2 if p.mg_levels > 1 else (3 if p.N <= 512 else 0)
+            else:
+                self.precond = 3 if p.N <= 512 else 0
             p.upload(0)                      # raises FemoError without a CUDA device
             self._prob = p
         return self._prob

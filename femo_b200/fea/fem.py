@@ -368,8 +368,15 @@ class Measure:
         return Measure(self.kind, self.domain, self.subdomain_data, self.metadata, tag)
 
     def facets(self):
+        """Indices into the mesh's exterior-facet list carrying this tag."""
         t = self.subdomain_data
-        return t.indices[t.values == self.tag] if t is not None else None
+        if t is None:
+            return None
+        idx = t.indices[t.values == self.tag]
+        if t.mesh.cell_type == 'interval':
+            # facets of an interval are vertices: entity ids are vertex ids (0 or n) -> facet 0 / 1
+            idx = np.array([0 if v == 0 else 1 for v in idx], dtype=np.int32)
+        return idx
 
 
 ds = Measure('ds')

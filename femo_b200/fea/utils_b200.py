@@ -237,7 +237,8 @@ def solveNonlinear(res, func, bc, solver, report, initialize):
     fam.apply_bcs(bc)
     try:
         info = p.newton_solve(kind=solver, krylov_rtol=KRYLOV['rtol'], krylov_max_it=KRYLOV['max_it'],
-                              check_every=KRYLOV['check_every'], precond=KRYLOV['precond'],
+                              check_every=KRYLOV['check_every'],
+                              precond=KRYLOV['precond'] if fam.precond is None else fam.precond,
                               cheb_degree=KRYLOV['cheb_degree'])
     finally:
         func.mark_device_written()
@@ -273,7 +274,8 @@ def _solve_into(A, b, x):
     xt = xf.device_tensor(p)
     xt.zero_()
     _, info = p.linear_solve(A.vals, bf.device_tensor(p), xt, transpose=A.transposed, rtol=KRYLOV['rtol'],
-                             max_it=KRYLOV['max_it'], check_every=KRYLOV['check_every'], precond=KRYLOV['precond'],
+                             max_it=KRYLOV['max_it'], check_every=KRYLOV['check_every'],
+                             precond=KRYLOV['precond'] if fam.precond is None else fam.precond,
                              cheb_degree=KRYLOV['cheb_degree'])
     xf.mark_device_written()
     fam.last_linear_info = info

@@ -71,6 +71,10 @@ void femo_mesh_destroy(femo_mesh *m);
  * at :185,195,575) with a pattern and deterministic cell->nnz gather map built
  * ONCE (reference quirk B12).  The mesh is copied; it may be destroyed after. */
 int femo_problem_create(const femo_mesh *m, int family, const double *params, int nparams, femo_problem **out);
+/* Same, with the facets of a tagged measure ds(tag) (createCustomMeasure / meshtags,
+ * utils_dolfinx.py:532-546; examples' ds_(100)): indices into the mesh's exterior-facet list. */
+int femo_problem_create_tagged(const femo_mesh *m, int family, const double *params, int nparams,
+                               const int32_t *facet_ids, int nfacets, femo_problem **out);
 void femo_problem_destroy(femo_problem *p);
 /* sizes[0]=N (state dofs) [1]=n inputs [2]=n aux fields [3]=n outputs
  * [4..7]=M_s (input s dofs) [8..11]=aux field dofs [12]=n exterior facets */
@@ -147,7 +151,8 @@ typedef struct femo_krylov_opts {
     double rtol;      /* ||r|| <= rtol*||b||   */
     double atol;      /* or ||r|| <= atol      */
     int max_it;
-    int precond;      /* 0 Jacobi, 2 geometric multigrid V-cycle (Chebyshev-Jacobi smoothing) */
+    int precond;      /* 0 Jacobi, 2 geometric multigrid V-cycle (Chebyshev-Jacobi smoothing),
+                         3 explicit dense inverse (N <= 512; the direct-solve analogue) */
     int cheb_degree;  /* smoother degree of the V-cycle (default 2) */
     int method;       /* 0 CG, 1 GMRES(restart) */
     int restart;

@@ -253,3 +253,189 @@ class NonlinearPoissonP1(_TriP1):
     def output_dm(self, k, slot, u, f):
         ge = (0.5 * self.detJ * self.alpha * f)[:, None]
         return [(self.dg_dofs, None, ge)]
+
+
+# --------------------------------------------------------------------------
+# config 3: Euler-Bernoulli cantilever, Hermite-3 on an interval
+# --------------------------------------------------------------------------
+def _hermite_d2(xi):
+    """Second reference derivatives of the Hermite cubics, dof order
+    (value@v0, slope@v0, value@v1, slope@v1); identity push-forward as in basix 0.5
+    [upstream, SURVEY.md section 7 "Hermite push-forward"]: slope dofs are reference derivatives."""
+    return np.stack([-6.0 + 12.0 * xi, -4.0 + 6.0 * xi, 6.0 - 12.0 * xi, -2.0 + 6.0 * xi], axis=-1)
+
+
+def _hermite(xi):
+    return np.stack([1 - 3 * xi ** 2 + 2 * xi ** 3, xi - 2 * xi ** 2 + xi ** 3,
+                     3 * xi ** 2 - 2 * xi ** 3, -xi ** 2 + xi ** 3], axis=-1)
+
+
+class EBBeam:
+    """examples/beam_thickness_opt/run_thickness_opt_cantilever_beam.py.
+
+    R = int v'' (E b t^3/12) u'' dx - f v|_{ds(100)}   (:64-79,127-131), degree 2 -> 2-pt Gauss
+    outputs: 0 compliance = f u|_{ds(100)} (:84-85), 1 volume = int t b L dx (:81-82)
+    `tagged` indexes the mesh's exterior-facet list (the tip, :115-124).
+    """
+    name = 'eb_beam'
+    n_outputs = 2
+
+    def __init__(self, mesh, tagged, E=1.0, width=0.1, L=1.0, f=-1.0):
+        assert mesh.kind == 'interval'
+        self.mesh = mesh
+        self.E, self.width, self.L, self.f = E, width, L, f
+        self.cell_dofs, self.N = dofmap(mesh, 'Hermite', 3)
+        self.dg_dofs, self.M = dofmap(mesh, 'DG', 0)
+        X = mesh.coords[mesh.cells][:, :, 0]
+        self.h = X[:, 1] - X[:, 0]
+        fc, fl = mesh.exterior_facets()
+        self.fc, self.fl = fc[tagged], fl[tagged]
+        self.fdofs = self.cell_dofs[self.fc]
+        self.fphi = _hermite(self.fl.astype(np.float64))          # basis at the facet point (xi = 0 or 1)
+
+    def _khat(self):
+        s, w = quad.interval(2)
+        d2 = _hermite_d2(s)                                       # (nq,4)
+        return np.einsum('q,qa,qb->ab', w, d2, d2)
+
+    def _bend(self, u):
+        return np.einsum('ab,cb->ca', self._khat(), u[self.cell_dofs]) / self.h[:, None] ** 3
+
+    def residual(self, u, t):
+        EI = self.E * self.width * t ** 3 / 12.0
+        Re = EI[:, None] * self._bend(u)
+        Rf = -self.f * self.fphi
+        return [(self.cell_dofs, None, Re), (self.fdofs, None, Rf)]
+
+    def jacobian(self, u, t):
+        EI = self.E * self.width * t ** 3 / 12.0
+        Ae = (EI / self.h ** 3)[:, None, None] * self._khat()[None]
+        return [(self.cell_dofs, self.cell_dofs, Ae)]
+
+    def dRdm(self, slot, u, t):
+        dEI = self.E * self.width * 3.0 * t ** 2 / 12.0
+        return [(self.cell_dofs, self.dg_dofs, (dEI[:, None] * self._bend(u))[:, :, None])]
+
+    def output(self, k, u, t):
+        if k == 0:
+            return [self.f * np.einsum('fa,fa->f', self.fphi, u[self.fdofs])]
+        return [t * self.width * self.L * self.h]
+
+    def output_du(self, k, u, t):
+        if k == 0:
+            return [(self.fdofs, None, self.f * self.fphi)]
+        return [(self.cell_dofs, None, np.zeros((self.mesh.ncells, 4)))]
+
+    def output_dm(self, k, slot, u, t):
+        if k == 0:
+            return [(self.dg_dofs, None, np.zeros((self.mesh.ncells, 1)))]
+        return [(self.dg_dofs, None, (self.width * self.L * self.h)[:, None])]
+
+
+# --------------------------------------------------------------------------
+# config 4: SIMP linear elasticity, Q1 quadrilaterals, vector CG1 state
+# --------------------------------------------------------------------------
+class SimpQ1:
+    """examples/beam_topo_opt/run_topo_opt_cantilever_beam.py.
+
+    R = int sigma(u):eps(v) dx - int_{ds(100)} f.v ds          (:62-77)
+        E = rho^3, nu = 0.3, lambda = E nu/((1+nu)(1-2nu)), mu = E/(2(1+nu)); f = (0,-1/4) (:101)
+        cells degree 2 -> 2x2 Gauss (no degree reduction on quads); ds(100) degree 4 -> 3-pt Gauss
+    outputs: 0 avg_density = int rho/|Omega| dx (:79-83), 1 compliance = int_{ds(100)} u.f ds (:85-86)
+    """
+    name = 'simp_q1'
+    n_outputs = 2
+
+    def __init__(self, mesh, tagged, nu=0.3, f=(0.0, -0.25), penal=3.0):
+        assert mesh.kind == 'quadrilateral'
+        self.mesh, self.nu, self.f, self.penal = mesh, nu, np.asarray(f, dtype=np.float64), penal
+        self.cell_dofs, self.N = dofmap(mesh, 'Q', 1, block=2)
+        self.dg_dofs, self.M = dofmap(mesh, 'DG', 0)
+        self.X = mesh.coords[mesh.cells]                           # (nc,4,2)
+        fc, fl = mesh.exterior_facets()
+        self.fc, self.fl = fc[tagged], fl[tagged]
+        self.fdofs = self.cell_dofs[self.fc]
+        lf = mesh.local_facets[self.fl]
+        P, Q = self.X[self.fc, lf[:, 0]], self.X[self.fc, lf[:, 1]]
+        self.flen = np.linalg.norm(Q - P, axis=1)
+        self.flv = lf
+        self.area = self._cell_area()
+        self.volume = self.area.sum()
+
+    @staticmethod
+    def _N(p):
+        x, y = p[..., 0], p[..., 1]
+        return np.stack([(1 - x) * (1 - y), x * (1 - y), (1 - x) * y, x * y], axis=-1)
+
+    @staticmethod
+    def _dN(p):
+        x, y = p[..., 0], p[..., 1]
+        return np.stack([np.stack([-(1 - y), (1 - y), -y, y], axis=-1),
+                         np.stack([-(1 - x), -x, (1 - x), x], axis=-1)], axis=-1)      # (...,4,2)
+
+    def _geom(self, pt):
+        dN = self._dN(pt)                                           # (4,2) d/dxi
+        J = np.einsum('cad,ak->cdk', self.X, dN)                    # J[c,d,k] = dx_d/dxi_k
+        det = J[:, 0, 0] * J[:, 1, 1] - J[:, 0, 1] * J[:, 1, 0]
+        Jinv = np.empty_like(J)
+        Jinv[:, 0, 0], Jinv[:, 0, 1] = J[:, 1, 1] / det, -J[:, 0, 1] / det
+        Jinv[:, 1, 0], Jinv[:, 1, 1] = -J[:, 1, 0] / det, J[:, 0, 0] / det
+        G = np.einsum('ckd,ak->cad', Jinv, dN)                      # physical gradients (nc,4,2)
+        return G, np.abs(det)
+
+    def _cell_area(self):
+        pts, w = quad.square(2)
+        return sum(w[q] * self._geom(pts[q])[1] for q in range(len(w)))
+
+    def _khat(self):
+        """Unit-modulus element stiffness (nc,8,8), local dof a*2+c."""
+        lam = self.nu / ((1 + self.nu) * (1 - 2 * self.nu))
+        mu = 1.0 / (2 * (1 + self.nu))
+        pts, w = quad.square(2)
+        K = np.zeros((self.mesh.ncells, 4, 2, 4, 2))
+        I2 = np.eye(2)
+        for q in range(len(w)):
+            G, det = self._geom(pts[q])
+            wq = (w[q] * det)[:, None, None, None, None]
+            K += wq * (lam * np.einsum('cai,cbj->caibj', G, G)
+                       + mu * (np.einsum('caj,cbi->caibj', G, G)
+                               + np.einsum('cad,cbd->cab', G, G)[:, :, None, :, None] * I2[None, None, :, None, :]))
+        return K.reshape(self.mesh.ncells, 8, 8)
+
+    def _traction(self):
+        s, w = quad.interval(4)
+        nf = self.fc.size
+        Fe = np.zeros((nf, 4, 2))
+        ar = np.arange(nf)
+        for q in range(len(w)):
+            ph = np.zeros((nf, 4))
+            ph[ar, self.flv[:, 0]] = 1.0 - s[q]
+            ph[ar, self.flv[:, 1]] = s[q]
+            Fe += (w[q] * self.flen)[:, None, None] * ph[:, :, None] * self.f[None, None, :]
+        return Fe.reshape(nf, 8)
+
+    def residual(self, u, rho):
+        Re = (rho ** self.penal)[:, None] * np.einsum('cab,cb->ca', self._khat(), u[self.cell_dofs])
+        return [(self.cell_dofs, None, Re), (self.fdofs, None, -self._traction())]
+
+    def jacobian(self, u, rho):
+        return [(self.cell_dofs, self.cell_dofs, (rho ** self.penal)[:, None, None] * self._khat())]
+
+    def dRdm(self, slot, u, rho):
+        De = (self.penal * rho ** (self.penal - 1))[:, None] * np.einsum('cab,cb->ca', self._khat(), u[self.cell_dofs])
+        return [(self.cell_dofs, self.dg_dofs, De[:, :, None])]
+
+    def output(self, k, u, rho):
+        if k == 0:
+            return [rho * self.area / self.volume]
+        return [np.einsum('fa,fa->f', self._traction(), u[self.fdofs])]
+
+    def output_du(self, k, u, rho):
+        if k == 0:
+            return [(self.cell_dofs, None, np.zeros((self.mesh.ncells, 8)))]
+        return [(self.fdofs, None, self._traction())]
+
+    def output_dm(self, k, slot, u, rho):
+        if k == 0:
+            return [(self.dg_dofs, None, (self.area / self.volume)[:, None])]
+        return [(self.dg_dofs, None, np.zeros((self.mesh.ncells, 1)))]
