@@ -57,6 +57,15 @@ __device__ __forceinline__ double block_sum(double v) {
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int32_t ld_stream(const int32_t *p) { return __ldcs(p); }
 
+// y-slab of a global lattice owned by this rank: global cell rows [crow0, crow0+ncrows) are local,
+// local node row j is global row crow0 + j; node / cell rows [own0,own1) / [cown0,cown1) are owned
+struct SlabInfo {
+    bool active = false;
+    int rank = 0, nranks = 1;
+    int gny = 0, crow0 = 0, ncrows = 0;
+    int own0 = 0, own1 = 0, cown0 = 0, cown1 = 0;
+};
+
 struct DevPattern {
     int32_t *rowptr = nullptr, *col = nullptr, *gptr = nullptr, *gsrc = nullptr;
     int32_t *t_rowptr = nullptr, *t_col = nullptr, *t_perm = nullptr;
@@ -141,6 +150,11 @@ struct femo_problem {
     // coefficients
     const double *coef[femo::kMaxSlots] = {nullptr};
     int64_t coefn[femo::kMaxSlots] = {0};
+    // multi-GPU slab (inactive on one GPU); reductions run over the owned ranges only
+    femo::SlabInfo slab;
+    int64_t own_off = 0, own_n = 0;        // owned state dofs: [own_off, own_off + own_n)
+    int64_t cown_off = 0, cown_n = 0;      // owned cells
+    bool replicated = false;               // multigrid level held identically by every rank
     // geometric multigrid: coarse problems (owned), Jacobian-only layouts
     bool jac_only = false;
     std::vector<femo_problem *> mg;

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "families.cuh"
 #include "families2.cuh"
+#include "dist.cuh"
 
 namespace femo {
 
@@ -121,6 +122,7 @@ struct SpmvEpi {
     double *rout = nullptr, *dout = nullptr, *xacc = nullptr;
     double c1 = 0.0, c2 = 0.0;
     int xmode = 0;
+    int64_t own0 = 0, own1 = (int64_t)1 << 62;   // rows whose x_i*y_i enter the fused dot (owned dofs)
 };
 
 template <int EPI>
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kThreads)
                 for (int32_t k = rp[i] - s; k < rp[i + 1] - s; ++k) acc += prod[k];
                 const double xi = (DOT || EPI == EPI_CHEBK) ? __ldg(x + r0 + i) : 0.0;
                 spmv_row_epilogue<EPI>(E, r0 + i, acc, xi, y);
-                if (DOT) dot += acc * xi;
+                if (DOT && r0 + i >= E.own0 && r0 + i < E.own1) dot += acc * xi;
             }
         } else {  // a single long row: CTA-wide strided reduction (fixed order)
             double acc = 0.0;
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(kThreads)
             if (tid == 0) {
                 const double xi = __ldg(x + r0);
                 spmv_row_epilogue<EPI>(E, r0, acc, xi, y);
-                if (DOT) dot += acc * xi;
+                if (DOT && r0 >= E.own0 && r0 < E.own1) dot += acc * xi;
             }
         }
         __syncthreads();
@@ -215,90 +217,6 @@ __global__ void __launch_bounds__(kThreads)
     for (int32_t t = rowptr[i]; t < rowptr[i + 1]; ++t)
         if (col[t] == i) d = vals[t];
     dinv[i] = (d != 0.0) ? 1.0 / d : 1.0;
-}
-
-// ===========================================================================
-// fused CG vector kernels (K8).  Scalars live on the device: no host sync
-// inside an iteration.
-// ===========================================================================
-// r = b - q ; p = dinv*r ; partials: rz, rr
-__global__ void __launch_bounds__(kThreads)
-    k_cg_init(const double *__restrict__ b, const double *__restrict__ q, const double *__restrict__ dinv,
-              double *__restrict__ r, double *__restrict__ p, int64_t n, double *__restrict__ prz,
-              double *__restrict__ prr) {
-    double rz = 0.0, rr = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double ri = b[i] - q[i];
-        const double zi = dinv[i] * ri;
-        r[i] = ri;
-        p[i] = zi;
-        rz += ri * zi;
-        rr += ri * ri;
-    }
-    rz = block_sum(rz);
-    rr = block_sum(rr);
-    if (threadIdx.x == 0) {
-        prz[blockIdx.x] = rz;
-        prr[blockIdx.x] = rr;
-    }
-}
-
-// x += alpha p ; r -= alpha q ; partials of r.(dinv r) and r.r
-__global__ void __launch_bounds__(kThreads)
-    k_cg_update(const double *__restrict__ sc, const double *__restrict__ p, const double *__restrict__ q,
-                const double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r, int64_t n,
-                double *__restrict__ prz, double *__restrict__ prr) {
-    const double alpha = sc[S_ALPHA];
-    double rz = 0.0, rr = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        x[i] += alpha * p[i];
-        const double ri = r[i] - alpha * q[i];
-        r[i] = ri;
-        rz += ri * ri * dinv[i];
-        rr += ri * ri;
-    }
-    rz = block_sum(rz);
-    rr = block_sum(rr);
-    if (threadIdx.x == 0) {
-        prz[blockIdx.x] = rz;
-        prr[blockIdx.x] = rr;
-    }
-}
-
-// p = dinv*r + beta p
-__global__ void __launch_bounds__(kThreads)
-    k_cg_dir(const double *__restrict__ sc, const double *__restrict__ r, const double *__restrict__ dinv,
-             double *__restrict__ p, int64_t n) {
-    const double beta = sc[S_BETA];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        p[i] = dinv[i] * r[i] + beta * p[i];
-}
-
-// phase 0: alpha = rz / sum(pq partials)
-// phase 1: rz' = sum(A), rr = sum(B); beta = rz'/rz ; rz = rz'
-// phase 2: rz = sum(A), rr = sum(B)   (initialisation)
-__global__ void __launch_bounds__(kThreads)
-    k_cg_scalars(int phase, double *sc, const double *__restrict__ pa, const double *__restrict__ pb, int np) {
-    double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < np; i += blockDim.x) {
-        a += pa[i];
-        if (pb) b += pb[i];
-    }
-    a = block_sum(a);
-    b = block_sum(b);
-    if (threadIdx.x == 0) {
-        if (phase == 0) {
-            sc[S_PQ] = a;
-            sc[S_ALPHA] = (a != 0.0) ? sc[S_RZ] / a : 0.0;
-        } else if (phase == 1) {
-            sc[S_BETA] = (sc[S_RZ] != 0.0) ? a / sc[S_RZ] : 0.0;
-            sc[S_RZ] = a;
-            sc[S_RR] = b;
-        } else {
-            sc[S_RZ] = a;
-            sc[S_RR] = b;
-        }
-    }
 }
 
 __global__ void __launch_bounds__(kThreads) k_axpy(double a, const double *__restrict__ x, double *__restrict__ y, int64_t n) {
@@ -476,6 +394,8 @@ static int segreduce(femo_problem *p, const DevVecMap &m, int64_t n, double *d_o
     return FEMO_OK;
 }
 
+#include "dist_ops.cuh"
+
 static inline int spmv_grid(const femo_problem *p, int nrb) {
     // persistent grid: every SM holds 8 CTAs and walks the row blocks with a grid stride, so the
     // rows in flight form one contiguous window (x stays L2-resident) and the dot partials are bounded
@@ -485,10 +405,18 @@ static inline int spmv_grid(const femo_problem *p, int nrb) {
 
 template <bool DOT>
 static int launch_spmv(femo_problem *p, const int32_t *rb, int nrb, const int32_t *rowptr, const int32_t *col,
-                       const double *vals, const double *x, double *y, const double *bsub, int *np_out) {
+                       const double *vals, const double *x, double *y, const double *bsub, int *np_out,
+                       bool halo = true) {
+    // every SpMV on the state pattern refreshes the ghost rows of its input first (no-op on one GPU)
+    if (halo) {
+        int rc = halo_nodes(p, const_cast<double *>(x));
+        if (rc) return rc;
+    }
     const int grid = spmv_grid(p, nrb);
     SpmvEpi E;
     E.b = bsub;
+    E.own0 = p->own_off;
+    E.own1 = p->own_off + p->own_n;
     k_spmv<DOT, EPI_PLAIN><<<grid, kThreads, 0, p->stream>>>(rb, nrb, rowptr, col, vals, x, y, E, p->d_partials);
     p->launches++;
     if (np_out) *np_out = grid;
@@ -499,6 +427,8 @@ static int launch_spmv(femo_problem *p, const int32_t *rb, int nrb, const int32_
 // SpMV on pattern 0 with a fused Chebyshev epilogue (multigrid smoother)
 static int launch_spmv_cheb(femo_problem *p, int kind, const double *vals, const double *x, const SpmvEpi &E) {
     const DevPattern &D = p->dpat[0];
+    int rc = halo_nodes(p, const_cast<double *>(x));
+    if (rc) return rc;
     const int grid = spmv_grid(p, D.nrb);
     if (kind == EPI_CHEB0)
         k_spmv<false, EPI_CHEB0><<<grid, kThreads, 0, p->stream>>>(D.rb, D.nrb, D.rowptr, D.col, vals, x, nullptr, E, nullptr);
@@ -514,16 +444,6 @@ static int read_scalars(femo_problem *p, int first, int count, double *h) {
     FEMO_CUDA(cudaStreamSynchronize(p->stream));
     for (int i = 0; i < count; ++i) h[i] = p->h_pinned[i];
     return FEMO_OK;
-}
-
-// ||a||^2 -> host
-static int norm2_sq(femo_problem *p, const double *a, int64_t n, double *out) {
-    int g = red_grid(p, n);
-    k_dot<<<g, kThreads, 0, p->stream>>>(a, a, n, p->d_partials);
-    k_finalize<<<1, kThreads, 0, p->stream>>>(p->d_partials, g, p->d_scalars, S_TMP0);
-    p->launches += 2;
-    FEMO_CHECK_LAUNCH();
-    return read_scalars(p, S_TMP0, 1, out);
 }
 
 template <class T>
@@ -562,6 +482,7 @@ static int propagate_bc(femo_problem *root);
 }
 
 #include "multigrid.cuh"
+#include "krylov.cuh"
 
 // ===========================================================================
 // C ABI
@@ -689,6 +610,10 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
                 p->fb_local.push_back(M.bf_local[tagged[k]]);
             }
         }
+        p->own_off = 0;
+        p->own_n = p->state.ndofs;
+        p->cown_off = 0;
+        p->cown_n = M.ncells;
         IntegralBlock cells, facets;
         cells.ne = M.ncells;
         facets.ne = (int64_t)p->fb_cell.size();
@@ -1224,11 +1149,19 @@ int femo_assemble_output(femo_problem *p, int out_id, double *h_value) {
     const int om = p->out_mask[out_id];
     if ((rc = run_elements(p, OP_OUT, om, out_id))) return rc;
     const int64_t n = ((om & 1) ? p->mesh.ncells : 0) + ((om & 2) ? (int64_t)p->fb_cell.size() : 0);
-    int g = red_grid(p, n);
-    k_sum<<<g, kThreads, 0, p->stream>>>(p->d_scratch, n, p->d_partials);
-    k_finalize<<<1, kThreads, 0, p->stream>>>(p->d_partials, g, p->d_scalars, S_TMP1);
-    p->launches += 2;
+    // on several GPUs every cell is summed by the rank that owns it
+    const double *src = p->d_scratch;
+    int64_t cnt = n;
+    if (p->slab.active) {
+        if (om != 1) return set_err(FEMO_EINVAL, "facet functionals are not partitioned yet");
+        src += p->cown_off;
+        cnt = p->cown_n;
+    }
+    int g = red_grid(p, cnt);
+    k_sum<<<g, kThreads, 0, p->stream>>>(src, cnt, p->d_partials);
+    p->launches++;
     FEMO_CHECK_LAUNCH();
+    if ((rc = reduce_to(p, p->d_partials, nullptr, g, S_TMP1, 0))) return rc;
     return read_scalars(p, S_TMP1, 1, h_value);
 }
 
@@ -1258,11 +1191,15 @@ int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_
     if (which < 0 || which > p->nin || !d_vals || !d_x || !d_y) return set_err(FEMO_EINVAL, "femo_spmv: bad arguments");
     const Pattern &P = p->pat[which];
     const DevPattern &D = p->dpat[which];
-    if (!transpose) return launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, d_vals, d_x, d_y, nullptr, nullptr);
+    // ghost refresh of the input: node vector for dR/du and for transposed dR/dm, cell vector for dR/dm
+    if (which == 0 || transpose) {
+        if ((rc = halo_nodes(p, const_cast<double *>(d_x)))) return rc;
+    } else if ((rc = halo_cells(p, const_cast<double *>(d_x)))) return rc;
+    if (!transpose) return launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, d_vals, d_x, d_y, nullptr, nullptr, false);
     k_permute<<<grid_for(P.nnz), kThreads, 0, p->stream>>>(D.t_perm, d_vals, p->d_tvals, P.nnz);
     p->launches++;
     FEMO_CHECK_LAUNCH();
-    return launch_spmv<false>(p, D.t_rb, D.t_nrb, D.t_rowptr, D.t_col, p->d_tvals, d_x, d_y, nullptr, nullptr);
+    return launch_spmv<false>(p, D.t_rb, D.t_nrb, D.t_rowptr, D.t_col, p->d_tvals, d_x, d_y, nullptr, nullptr, false);
 }
 
 int femo_axpy(femo_problem *p, double a, const double *d_x, double *d_y, int64_t n) {
@@ -1272,75 +1209,6 @@ int femo_axpy(femo_problem *p, double a, const double *d_x, double *d_y, int64_t
     k_axpy<<<red_grid(p, n), kThreads, 0, p->stream>>>(a, d_x, d_y, n);
     p->launches++;
     FEMO_CHECK_LAUNCH();
-    return FEMO_OK;
-}
-
-static void default_krylov(femo_krylov_opts &o) {
-    if (o.rtol <= 0) o.rtol = 1e-10;
-    if (o.atol < 0) o.atol = 0;
-    if (o.max_it <= 0) o.max_it = 100000;
-    if (o.check_every <= 0) o.check_every = 1;
-}
-
-// Jacobi-preconditioned CG on the dR/du pattern; vals already in the layout to multiply with
-static int cg_solve(femo_problem *p, const double *vals, const double *b, double *x, femo_krylov_opts o,
-                    femo_krylov_info *info) {
-    default_krylov(o);
-    if ((o.precond == 2 && !p->mg.empty()) || o.precond == 3) return pcg_mg_solve(p, vals, b, x, o, info);
-    const int64_t n = p->state.ndofs;
-    const DevPattern &D = p->dpat[0];
-    cudaStream_t st = p->stream;
-    double *pz = p->d_partials, *pr = p->d_partials + kMaxPartials;
-    const int g = red_grid(p, n);
-    int rc, np = 0, spmvs = 0;
-    k_diag_inv<<<grid_for(n), kThreads, 0, st>>>(D.rowptr, D.col, vals, p->kr_dinv, n);
-    // ||b||^2
-    k_dot<<<g, kThreads, 0, st>>>(b, b, n, pz);
-    k_finalize<<<1, kThreads, 0, st>>>(pz, g, p->d_scalars, S_BB);
-    // r = b - A x ; p = dinv r
-    if ((rc = launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, vals, x, p->kr_q, nullptr, nullptr))) return rc;
-    ++spmvs;
-    k_cg_init<<<g, kThreads, 0, st>>>(b, p->kr_q, p->kr_dinv, p->kr_r, p->kr_p, n, pz, pr);
-    k_cg_scalars<<<1, kThreads, 0, st>>>(2, p->d_scalars, pz, pr, g);
-    p->launches += 5;
-    FEMO_CHECK_LAUNCH();
-    double h[2];
-    FEMO_CUDA(cudaMemcpyAsync(p->h_pinned, p->d_scalars + S_RR, sizeof(double), cudaMemcpyDeviceToHost, st));
-    FEMO_CUDA(cudaMemcpyAsync(p->h_pinned + 1, p->d_scalars + S_BB, sizeof(double), cudaMemcpyDeviceToHost, st));
-    FEMO_CUDA(cudaStreamSynchronize(st));
-    h[0] = p->h_pinned[0];
-    h[1] = p->h_pinned[1];
-    const double bnorm = std::sqrt(h[1]);
-    double rnorm = std::sqrt(h[0]);
-    const double tol = std::max(o.rtol * bnorm, o.atol);
-    int it = 0;
-    bool conv = rnorm <= tol;
-    while (!conv && it < o.max_it) {
-        const int chunk = std::min(o.check_every, o.max_it - it);
-        for (int k = 0; k < chunk; ++k) {
-            if ((rc = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, nullptr, &np))) return rc;
-            k_cg_scalars<<<1, kThreads, 0, st>>>(0, p->d_scalars, p->d_partials, nullptr, np);
-            k_cg_update<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_p, p->kr_q, p->kr_dinv, x, p->kr_r, n, pz, pr);
-            k_cg_scalars<<<1, kThreads, 0, st>>>(1, p->d_scalars, pz, pr, g);
-            k_cg_dir<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_r, p->kr_dinv, p->kr_p, n);
-            p->launches += 4;
-            ++spmvs;
-        }
-        FEMO_CHECK_LAUNCH();
-        it += chunk;
-        double rr;
-        if ((rc = read_scalars(p, S_RR, 1, &rr))) return rc;
-        rnorm = std::sqrt(rr);
-        if (!(rnorm == rnorm)) break;  // NaN
-        conv = rnorm <= tol;
-    }
-    if (info) {
-        info->iterations = it;
-        info->converged = conv ? 1 : 0;
-        info->rnorm = rnorm;
-        info->bnorm = bnorm;
-        info->spmv_count = spmvs;
-    }
     return FEMO_OK;
 }
 
@@ -1386,7 +1254,7 @@ int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton
         }
         if ((r = femo_newton_rhs(p, p->nt_vals, p->nt_b))) return r;
         double s;
-        if ((r = norm2_sq(p, p->nt_b, n, &s))) return r;
+        if ((r = norm2_sq(p, p->nt_b, &s))) return r;
         fn = std::sqrt(s);
         return FEMO_OK;
     };
@@ -1415,8 +1283,8 @@ int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton
         else if (snes ? (fn <= opts->rtol * f0) : (f0 > 0 && fn / f0 < opts->rtol)) reason = 2;
         else if (snes) {
             double sy, sx;
-            if ((rc = norm2_sq(p, p->nt_dx, n, &sy))) return rc;
-            if ((rc = norm2_sq(p, x, n, &sx))) return rc;
+            if ((rc = norm2_sq(p, p->nt_dx, &sy))) return rc;
+            if ((rc = norm2_sq(p, x, &sx))) return rc;
             if (std::sqrt(sy) < opts->stol * std::sqrt(sx)) reason = 3;
         }
     }

@@ -1,0 +1,274 @@
+// krylov.cuh -- CG drivers (K8/K9): Jacobi-preconditioned CG with fused vector
+// kernels, and PCG with a multigrid V-cycle or an explicit dense inverse as
+// preconditioner.  They replace KSP preonly + LU(MUMPS) of the reference
+// (femo/fea/utils_dolfinx.py:405-408,476-512).
+//
+// Scalars (alpha, beta, r.z, ...) live on the device; partial sums are reduced in
+// a fixed order; on several GPUs the reductions run over each rank's OWNED dofs
+// and are combined with ncclAllReduce on the same stream -- the host only reads
+// the residual norm every `check_every` iterations.
+#pragma once
+#include "common.cuh"
+#include "dist_ops.cuh"
+
+namespace femo {
+
+__device__ __forceinline__ bool owned(int64_t i, int64_t o0, int64_t o1) { return i >= o0 && i < o1; }
+
+// r = b - q ; p = dinv*r ; partials of r.(dinv r), r.r over the owned range
+__global__ void __launch_bounds__(kThreads)
+    k_cg_init(const double *__restrict__ b, const double *__restrict__ q, const double *__restrict__ dinv,
+              double *__restrict__ r, double *__restrict__ p, int64_t n, int64_t o0, int64_t o1,
+              double *__restrict__ prz, double *__restrict__ prr) {
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = b[i] - q[i];
+        const double zi = dinv[i] * ri;
+        r[i] = ri;
+        p[i] = zi;
+        if (owned(i, o0, o1)) {
+            rz += ri * zi;
+            rr += ri * ri;
+        }
+    }
+    rz = block_sum(rz);
+    rr = block_sum(rr);
+    if (threadIdx.x == 0) {
+        prz[blockIdx.x] = rz;
+        prr[blockIdx.x] = rr;
+    }
+}
+
+// x += alpha p ; r -= alpha q ; partials of r.(dinv r) [dinv may be null] and r.r
+__global__ void __launch_bounds__(kThreads)
+    k_cg_update(const double *__restrict__ sc, const double *__restrict__ p, const double *__restrict__ q,
+                const double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r, int64_t n, int64_t o0,
+                int64_t o1, double *__restrict__ prz, double *__restrict__ prr) {
+    const double alpha = sc[S_ALPHA];
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        if (owned(i, o0, o1)) {
+            if (dinv) rz += ri * ri * dinv[i];
+            rr += ri * ri;
+        }
+    }
+    rr = block_sum(rr);
+    if (dinv) rz = block_sum(rz);
+    if (threadIdx.x == 0) {
+        if (dinv) prz[blockIdx.x] = rz;
+        prr[blockIdx.x] = rr;
+    }
+}
+
+// p = z + beta p with z = dinv*r (Jacobi, zvec null) or z = zvec; first: p = z
+__global__ void __launch_bounds__(kThreads)
+    k_cg_dir(const double *__restrict__ sc, const double *__restrict__ r, const double *__restrict__ dinv,
+             const double *__restrict__ zvec, double *__restrict__ p, int64_t n, int first) {
+    const double beta = first ? 0.0 : sc[S_BETA];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double zi = zvec ? zvec[i] : dinv[i] * r[i];
+        p[i] = zi + beta * p[i];
+    }
+}
+
+// r = b - q ; partial r.r over the owned range
+__global__ void __launch_bounds__(kThreads)
+    k_residual_rr(const double *__restrict__ b, const double *__restrict__ q, double *__restrict__ r, int64_t n,
+                  int64_t o0, int64_t o1, double *__restrict__ prr) {
+    double rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = b[i] - q[i];
+        r[i] = ri;
+        if (owned(i, o0, o1)) rr += ri * ri;
+    }
+    rr = block_sum(rr);
+    if (threadIdx.x == 0) prr[blockIdx.x] = rr;
+}
+
+// one CTA: fixed-order sums of two partial arrays -> scalars[slotA], scalars[slotB] (pb may be null)
+__global__ void __launch_bounds__(kThreads)
+    k_finalize2(const double *__restrict__ pa, const double *__restrict__ pb, int np, double *sc, int slotA, int slotB) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        a += pa[i];
+        if (pb) b += pb[i];
+    }
+    a = block_sum(a);
+    b = block_sum(b);
+    if (threadIdx.x == 0) {
+        sc[slotA] = a;
+        if (pb) sc[slotB] = b;
+    }
+}
+
+// scalar recurrences on already (all-)reduced values
+//   op 0: alpha = rz / pq
+//   op 1: beta = tmp0 / rz ; rz = tmp0 ; rr = tmp1
+//   op 2: beta = tmp0 / rz ; rz = tmp0
+//   op 3: rz = tmp0
+__global__ void k_scalar_op(double *sc, int op) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (op == 0) {
+        sc[S_ALPHA] = (sc[S_PQ] != 0.0) ? sc[S_RZ] / sc[S_PQ] : 0.0;
+    } else if (op == 1 || op == 2) {
+        sc[S_BETA] = (sc[S_RZ] != 0.0) ? sc[S_TMP0] / sc[S_RZ] : 0.0;
+        sc[S_RZ] = sc[S_TMP0];
+        if (op == 1) sc[S_RR] = sc[S_TMP1];
+    } else {
+        sc[S_RZ] = sc[S_TMP0];
+    }
+}
+
+}  // namespace femo
+
+using namespace femo;
+
+static void default_krylov(femo_krylov_opts &o) {
+    if (o.rtol <= 0) o.rtol = 1e-10;
+    if (o.atol < 0) o.atol = 0;
+    if (o.max_it <= 0) o.max_it = 100000;
+    if (o.check_every <= 0) o.check_every = 1;
+}
+
+// sum of partials -> scalar slot(s) -> all ranks
+static int reduce_to(femo_problem *p, const double *pa, const double *pb, int np, int slotA, int slotB) {
+    k_finalize2<<<1, kThreads, 0, p->stream>>>(pa, pb, np, p->d_scalars, slotA, slotB);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    if (pb && slotB == slotA + 1) return allreduce_scalars(p, slotA, 2);
+    int rc = allreduce_scalars(p, slotA, 1);
+    if (rc || !pb) return rc;
+    return allreduce_scalars(p, slotB, 1);
+}
+
+static int scalar_op(femo_problem *p, int op) {
+    k_scalar_op<<<1, 32, 0, p->stream>>>(p->d_scalars, op);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
+// ||a||^2 over the owned dofs of all ranks -> host
+static int norm2_sq(femo_problem *p, const double *a, double *out) {
+    const int64_t n = p->own_n;
+    int g = red_grid(p, n);
+    k_dot<<<g, kThreads, 0, p->stream>>>(a + p->own_off, a + p->own_off, n, p->d_partials);
+    p->launches++;
+    int rc;
+    if ((rc = reduce_to(p, p->d_partials, nullptr, g, S_TMP0, 0))) return rc;
+    return read_scalars(p, S_TMP0, 1, out);
+}
+
+// Preconditioned CG on the dR/du pattern; `vals` already in the layout to multiply with.
+//   precond 0: Jacobi, 2: multigrid V-cycle, 3: explicit dense inverse
+static int cg_solve(femo_problem *p, const double *vals, const double *b, double *x, femo_krylov_opts o,
+                    femo_krylov_info *info) {
+    default_krylov(o);
+    if (o.precond == 2 && p->mg.empty()) o.precond = 0;
+    if (o.precond == 3 && !p->d_dense) return set_err(FEMO_ELIMIT, "precond 3 (dense direct) needs N <= 512 on one GPU");
+    const int pre = o.precond;
+    const int64_t n = p->state.ndofs, o0 = p->own_off, o1 = p->own_off + p->own_n;
+    const DevPattern &D = p->dpat[0];
+    cudaStream_t st = p->stream;
+    double *pa = p->d_partials, *pb = p->d_partials + kMaxPartials;
+    const int g = red_grid(p, n), go = red_grid(p, p->own_n);
+    MgParams mp;
+    if (o.cheb_degree > 0) mp.degree = o.cheb_degree;
+    if (o.cheb_ratio > 1.0) mp.ratio = o.cheb_ratio;
+    int rc, np = 0, spmvs = 0;
+    // preconditioner set-up
+    p->mgl.dinv = p->kr_dinv;
+    p->mgl.r = p->kr_w;
+    p->mgl.d = p->kr_d;
+    p->mgl.q = p->kr_q;
+    if (pre == 2) {
+        if ((rc = mg_setup(p, vals))) return rc;
+    } else if (pre == 3) {
+        k_dense_inverse<<<1, kThreads, 0, st>>>(D.rowptr, D.col, vals, (int)n, p->d_dense_tmp, p->d_dense);
+        p->launches++;
+    } else {
+        k_diag_inv<<<grid_for(n), kThreads, 0, st>>>(D.rowptr, D.col, vals, p->kr_dinv, n);
+        p->launches++;
+    }
+    FEMO_CHECK_LAUNCH();
+    // ||b||^2
+    k_dot<<<go, kThreads, 0, st>>>(b + p->own_off, b + p->own_off, p->own_n, pa);
+    p->launches++;
+    if ((rc = reduce_to(p, pa, nullptr, go, S_BB, 0))) return rc;
+    // r = b - A x
+    if ((rc = launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, vals, x, p->kr_q, nullptr, nullptr))) return rc;
+    ++spmvs;
+    if (pre == 0) {
+        k_cg_init<<<g, kThreads, 0, st>>>(b, p->kr_q, p->kr_dinv, p->kr_r, p->kr_p, n, o0, o1, pa, pb);
+        p->launches++;
+        if ((rc = reduce_to(p, pa, pb, g, S_RZ, S_RR))) return rc;
+    } else {
+        k_residual_rr<<<g, kThreads, 0, st>>>(b, p->kr_q, p->kr_r, n, o0, o1, pb);
+        p->launches++;
+        if ((rc = reduce_to(p, pb, nullptr, g, S_RR, 0))) return rc;
+    }
+    FEMO_CHECK_LAUNCH();
+    double h[2];
+    if ((rc = read_scalars(p, S_RR, 1, &h[0]))) return rc;
+    if ((rc = read_scalars(p, S_BB, 1, &h[1]))) return rc;
+    const double bnorm = std::sqrt(h[1]);
+    double rnorm = std::sqrt(h[0]);
+    const double tol = std::max(o.rtol * bnorm, o.atol);
+    int it = 0;
+    bool conv = rnorm <= tol;
+    while (!conv && it < o.max_it) {
+        if (pre != 0) {
+            // z = M^-1 r ; rz' = r.z ; p = z + beta p
+            if (pre == 3) {
+                k_dense_apply<<<(int)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(p->d_dense, p->kr_r, p->kr_z, (int)n);
+                p->launches++;
+            } else if ((rc = mg_vcycle(p, 0, p->kr_r, p->kr_z, mp))) return rc;
+            k_dot<<<go, kThreads, 0, st>>>(p->kr_r + p->own_off, p->kr_z + p->own_off, p->own_n, pa);
+            p->launches++;
+            if ((rc = reduce_to(p, pa, nullptr, go, S_TMP0, 0))) return rc;
+            if ((rc = scalar_op(p, it == 0 ? 3 : 2))) return rc;
+            k_cg_dir<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_r, nullptr, p->kr_z, p->kr_p, n, it == 0);
+            p->launches++;
+        } else if (it > 0) {
+            k_cg_dir<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_r, p->kr_dinv, nullptr, p->kr_p, n, 0);
+            p->launches++;
+        }
+        // q = A p ; alpha = rz / p.q
+        if ((rc = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, nullptr, &np))) return rc;
+        ++spmvs;
+        if ((rc = reduce_to(p, p->d_partials, nullptr, np, S_PQ, 0))) return rc;
+        if ((rc = scalar_op(p, 0))) return rc;
+        // x += alpha p ; r -= alpha q
+        if (pre == 0) {
+            k_cg_update<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_p, p->kr_q, p->kr_dinv, x, p->kr_r, n, o0, o1, pa, pb);
+            p->launches++;
+            if ((rc = reduce_to(p, pa, pb, g, S_TMP0, S_TMP1))) return rc;
+            if ((rc = scalar_op(p, 1))) return rc;
+        } else {
+            k_cg_update<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_p, p->kr_q, nullptr, x, p->kr_r, n, o0, o1, pa, pb);
+            p->launches++;
+            if ((rc = reduce_to(p, pb, nullptr, g, S_RR, 0))) return rc;
+        }
+        ++it;
+        FEMO_CHECK_LAUNCH();
+        if (it % o.check_every == 0 || it >= o.max_it) {
+            double rr;
+            if ((rc = read_scalars(p, S_RR, 1, &rr))) return rc;
+            rnorm = std::sqrt(rr);
+            if (!(rnorm == rnorm)) break;  // NaN
+            conv = rnorm <= tol;
+        }
+    }
+    if ((rc = halo_nodes(p, x))) return rc;   // hand back a solution that is valid on the ghost rows too
+    if (info) {
+        info->iterations = it;
+        info->converged = conv ? 1 : 0;
+        info->rnorm = rnorm;
+        info->bnorm = bnorm;
+        info->spmv_count = spmvs;
+    }
+    return FEMO_OK;
+}

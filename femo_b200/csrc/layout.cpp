@@ -31,7 +31,8 @@ static void lattice_coords(int nx, int ny, const double lo[2], const double hi[2
         }
 }
 
-void make_unit_square_tri(int nx, int ny, const double lo[2], const double hi[2], Mesh &m) {
+void make_unit_square_tri(int nx, int ny, const double lo[2], const double hi[2], Mesh &m, bool ext_bottom,
+                          bool ext_top) {
     m = Mesh();
     m.kind = MESH_TRI;
     m.nvpc = 3;
@@ -47,8 +48,8 @@ void make_unit_square_tri(int nx, int ny, const double lo[2], const double hi[2]
             a[3] = v0; a[4] = v2; a[5] = v3;
             // exterior facets; local facet i is opposite local vertex i
             if (ix == nx - 1) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(0); }      // v1-v3
-            if (iy == 0)      { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(2); }      // v0-v1
-            if (iy == ny - 1) { m.bf_cell.push_back((int32_t)c + 1); m.bf_local.push_back(0); }  // v2-v3
+            if (iy == 0 && ext_bottom) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(2); }      // v0-v1
+            if (iy == ny - 1 && ext_top) { m.bf_cell.push_back((int32_t)c + 1); m.bf_local.push_back(0); }  // v2-v3
             if (ix == 0)      { m.bf_cell.push_back((int32_t)c + 1); m.bf_local.push_back(2); }  // v0-v2
         }
 }

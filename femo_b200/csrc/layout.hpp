@@ -27,7 +27,10 @@ struct Mesh {
     std::vector<int32_t> bf_cell, bf_local;  // exterior facets, sorted by (cell, local facet)
 };
 
-void make_unit_square_tri(int nx, int ny, const double lo[2], const double hi[2], Mesh &m);
+// ext_bottom / ext_top: whether the y = lo / y = hi edge is a true domain boundary (false for the
+// interior interfaces of a y-slab of a partitioned mesh: no exterior facets are generated there)
+void make_unit_square_tri(int nx, int ny, const double lo[2], const double hi[2], Mesh &m, bool ext_bottom = true,
+                          bool ext_top = true);
 void make_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2], Mesh &m);
 void make_interval(int n, double x0, double x1, Mesh &m);
 

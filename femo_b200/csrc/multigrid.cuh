@@ -255,45 +255,6 @@ __global__ void __launch_bounds__(kThreads) k_dense_apply(const double *__restri
     if (lane == 0) x[row] = acc;
 }
 
-// PCG vector kernels for a general preconditioner ---------------------------
-// x += alpha p ; r -= alpha q ; partial r.r
-__global__ void __launch_bounds__(kThreads)
-    k_pcg_update(const double *__restrict__ sc, const double *__restrict__ p, const double *__restrict__ q,
-                 double *__restrict__ x, double *__restrict__ r, int64_t n, double *__restrict__ prr) {
-    const double alpha = sc[S_ALPHA];
-    double rr = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        x[i] += alpha * p[i];
-        const double ri = r[i] - alpha * q[i];
-        r[i] = ri;
-        rr += ri * ri;
-    }
-    rr = block_sum(rr);
-    if (threadIdx.x == 0) prr[blockIdx.x] = rr;
-}
-
-// p = z + beta p   (first=true: p = z)
-__global__ void __launch_bounds__(kThreads)
-    k_pcg_dir(const double *__restrict__ sc, const double *__restrict__ z, double *__restrict__ p, int64_t n, int first) {
-    const double beta = first ? 0.0 : sc[S_BETA];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        p[i] = z[i] + beta * p[i];
-}
-
-// r = b - q ; partial r.r
-__global__ void __launch_bounds__(kThreads)
-    k_residual_rr(const double *__restrict__ b, const double *__restrict__ q, double *__restrict__ r, int64_t n,
-                  double *__restrict__ prr) {
-    double rr = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double ri = b[i] - q[i];
-        r[i] = ri;
-        rr += ri * ri;
-    }
-    rr = block_sum(rr);
-    if (threadIdx.x == 0) prr[blockIdx.x] = rr;
-}
-
 }  // namespace femo
 
 using namespace femo;
@@ -450,82 +411,3 @@ static int mg_setup(femo_problem *root, const double *vals) {
     return FEMO_OK;
 }
 
-// PCG with the V-cycle as preconditioner
-static int pcg_mg_solve(femo_problem *p, const double *vals, const double *b, double *x, femo_krylov_opts o,
-                        femo_krylov_info *info) {
-    const int64_t n = p->state.ndofs;
-    const DevPattern &D = p->dpat[0];
-    cudaStream_t st = p->stream;
-    double *pa = p->d_partials, *pb = p->d_partials + kMaxPartials;
-    const int g = red_grid(p, n);
-    MgParams mp;
-    if (o.cheb_degree > 0) mp.degree = o.cheb_degree;
-    if (o.cheb_ratio > 1.0) mp.ratio = o.cheb_ratio;
-    int rc, np = 0, spmvs = 0;
-    // level-0 work vectors: the V-cycle's x is z (kr_z); r/d/q reuse Krylov buffers free at that point
-    p->mgl.dinv = p->kr_dinv;
-    p->mgl.r = p->kr_w;
-    p->mgl.d = p->kr_d;
-    p->mgl.q = p->kr_q;
-    const bool dense = (o.precond == 3);
-    if (dense) {   // small systems: explicit inverse (the exact analogue of the reference's LU)
-        if (!p->d_dense) return set_err(FEMO_ELIMIT, "precond 3 (dense direct) needs N <= 512");
-        k_dense_inverse<<<1, kThreads, 0, st>>>(D.rowptr, D.col, vals, (int)n, p->d_dense_tmp, p->d_dense);
-        p->launches++;
-        FEMO_CHECK_LAUNCH();
-    } else if ((rc = mg_setup(p, vals))) return rc;
-    k_dot<<<g, kThreads, 0, st>>>(b, b, n, pa);
-    k_finalize<<<1, kThreads, 0, st>>>(pa, g, p->d_scalars, S_BB);
-    if ((rc = launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, vals, x, p->kr_q, nullptr, nullptr))) return rc;
-    ++spmvs;
-    k_residual_rr<<<g, kThreads, 0, st>>>(b, p->kr_q, p->kr_r, n, pb);
-    k_finalize<<<1, kThreads, 0, st>>>(pb, g, p->d_scalars, S_RR);
-    p->launches += 4;
-    FEMO_CHECK_LAUNCH();
-    double h[2];
-    if ((rc = read_scalars(p, S_RR, 1, &h[0]))) return rc;
-    if ((rc = read_scalars(p, S_BB, 1, &h[1]))) return rc;
-    const double bnorm = std::sqrt(h[1]);
-    double rnorm = std::sqrt(h[0]);
-    const double tol = std::max(o.rtol * bnorm, o.atol);
-    int it = 0;
-    bool conv = rnorm <= tol;
-    while (!conv && it < o.max_it) {
-        // z = M^-1 r ; rz' = r.z
-        if (dense) {
-            k_dense_apply<<<(int)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(p->d_dense, p->kr_r, p->kr_z, (int)n);
-            p->launches++;
-        } else if ((rc = mg_vcycle(p, 0, p->kr_r, p->kr_z, mp))) return rc;
-        k_dot<<<g, kThreads, 0, st>>>(p->kr_r, p->kr_z, n, pa);
-        if (it == 0) {
-            k_finalize<<<1, kThreads, 0, st>>>(pa, g, p->d_scalars, S_RZ);
-            k_pcg_dir<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_z, p->kr_p, n, 1);
-        } else {
-            k_cg_scalars<<<1, kThreads, 0, st>>>(1, p->d_scalars, pa, nullptr, g);   // beta = rz'/rz ; rz = rz'
-            k_pcg_dir<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_z, p->kr_p, n, 0);
-        }
-        if ((rc = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, nullptr, &np))) return rc;
-        k_cg_scalars<<<1, kThreads, 0, st>>>(0, p->d_scalars, p->d_partials, nullptr, np);          // alpha = rz/pq
-        k_pcg_update<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_p, p->kr_q, x, p->kr_r, n, pb);
-        k_finalize<<<1, kThreads, 0, st>>>(pb, g, p->d_scalars, S_RR);
-        p->launches += 6;
-        ++spmvs;
-        ++it;
-        FEMO_CHECK_LAUNCH();
-        if (it % o.check_every == 0 || it >= o.max_it) {
-            double rr;
-            if ((rc = read_scalars(p, S_RR, 1, &rr))) return rc;
-            rnorm = std::sqrt(rr);
-            if (!(rnorm == rnorm)) break;
-            conv = rnorm <= tol;
-        }
-    }
-    if (info) {
-        info->iterations = it;
-        info->converged = conv ? 1 : 0;
-        info->rnorm = rnorm;
-        info->bnorm = bnorm;
-        info->spmv_count = spmvs;
-    }
-    return FEMO_OK;
-}
