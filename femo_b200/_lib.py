@@ -62,6 +62,15 @@ SIGNATURES = {
     'femo_problem_pattern': (C.c_int, [_P, C.c_int, _P, _P]),
     'femo_problem_gather_map': (C.c_int, [_P, C.c_int, _P, _P]),
     'femo_problem_set_bc': (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    'femo_comm_unique_id': (C.c_int, [C.c_char_p]),
+    'femo_comm_init': (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    'femo_comm_finalize': (C.c_int, []),
+    'femo_comm_stats': (C.c_int, [C.POINTER(C.c_longlong)]),
+    'femo_problem_create_slab': (C.c_int, [C.c_int, _DP, C.c_int, C.c_int, C.c_int, _DP, _DP, C.c_int, C.c_int, C.POINTER(_P)]),
+    'femo_problem_slab_info': (C.c_int, [_P, _I64P]),
+    'femo_halo_exchange': (C.c_int, [_P, _P, C.c_int]),
+    'femo_problem_mesh_sizes': (C.c_int, [_P, _I64P]),
+    'femo_problem_mesh_copy': (C.c_int, [_P, C.c_int, _P]),
     'femo_problem_enable_multigrid': (C.c_int, [_P]),
     'femo_problem_mg_levels': (C.c_int, [_P]),
     'femo_problem_device_bytes': (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

@@ -655,12 +655,109 @@ int femo_problem_create_tagged(const femo_mesh *m, int family, const double *par
     return create_problem_impl(m->m, family, params, nparams, false, facet_ids, nfacets, out);
 }
 
+// local problem of rank `rank` on its y-slab (one ghost cell row below, one ghost node row above)
+static int create_slab_problem(int family, const double *params, int nparams, int nx, int gny, const double lo[2],
+                               const double hi[2], int rank, int nranks, bool jac_only, femo_problem **out) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || gny % nranks != 0 || gny / nranks < 2)
+        return set_err(FEMO_EINVAL, "slab partition needs gny divisible by the number of ranks and >= 2 rows per rank");
+    SlabInfo sl = make_slab(gny, rank, nranks);
+    Mesh m;
+    make_unit_square_tri_slab(nx, gny, sl.crow0, sl.ncrows, lo, hi, m);
+    int rc = create_problem_impl(m, family, params, nparams, jac_only, nullptr, 0, out);
+    if (rc) return rc;
+    femo_problem *p = *out;
+    p->slab = sl;
+    const int64_t row_len = (int64_t)(nx + 1) * p->state.block, crow_len = m.ncells / sl.ncrows;
+    p->own_off = sl.own0 * row_len;
+    p->own_n = (int64_t)(sl.own1 - sl.own0) * row_len;
+    p->cown_off = sl.cown0 * crow_len;
+    p->cown_n = (int64_t)(sl.cown1 - sl.cown0) * crow_len;
+    return FEMO_OK;
+}
+
+int femo_problem_create_slab(int family, const double *params, int nparams, int nx, int gny, const double lo[2],
+                             const double hi[2], int rank, int nranks, femo_problem **out) {
+    if (!out || !lo || !hi || nx < 1 || nparams < 0 || nparams > 8) return set_err(FEMO_EINVAL, "femo_problem_create_slab: bad arguments");
+    if (family != FEMO_FAMILY_POISSON_P1 && family != FEMO_FAMILY_NLPOISSON_P1)
+        return set_err(FEMO_EINVAL, "slab partitioning is available for the P1 triangle families");
+    return create_slab_problem(family, params, nparams, nx, gny, lo, hi, rank, nranks, false, out);
+}
+
+int femo_problem_mesh_sizes(const femo_problem *p, int64_t s[6]) {
+    if (!p || !s) return set_err(FEMO_EINVAL, "femo_problem_mesh_sizes: null");
+    s[0] = p->mesh.ncells; s[1] = p->mesh.nverts; s[2] = p->mesh.nvpc; s[3] = p->mesh.gdim;
+    s[4] = (int64_t)p->mesh.bf_cell.size(); s[5] = p->mesh.kind;
+    return FEMO_OK;
+}
+
+int femo_problem_mesh_copy(const femo_problem *p, int what, void *out) {
+    if (!p || !out) return set_err(FEMO_EINVAL, "femo_problem_mesh_copy: null");
+    femo_mesh tmp;
+    const Mesh &M = p->mesh;
+    switch (what) {
+        case 0: memcpy(out, M.coords.data(), M.coords.size() * sizeof(double)); break;
+        case 1: memcpy(out, M.cells.data(), M.cells.size() * sizeof(int32_t)); break;
+        case 2: memcpy(out, M.bf_cell.data(), M.bf_cell.size() * sizeof(int32_t)); break;
+        case 3: memcpy(out, M.bf_local.data(), M.bf_local.size() * sizeof(int32_t)); break;
+        default: return set_err(FEMO_EINVAL, "femo_problem_mesh_copy: bad selector");
+    }
+    (void)tmp;
+    return FEMO_OK;
+}
+
+int femo_problem_slab_info(const femo_problem *p, int64_t info[16]) {
+    if (!p || !info) return set_err(FEMO_EINVAL, "femo_problem_slab_info: null");
+    const SlabInfo &s = p->slab;
+    const int64_t v[13] = {s.active, s.rank, s.nranks, s.gny, s.crow0, s.ncrows, s.own0, s.own1, s.cown0, s.cown1,
+                           p->own_off, p->own_n, p->cown_off};
+    for (int i = 0; i < 13; ++i) info[i] = v[i];
+    info[13] = p->cown_n; info[14] = p->mesh.n[0]; info[15] = p->mesh.n[1];
+    return FEMO_OK;
+}
+
+constexpr int kDistMinRows = 16;   // distributed multigrid levels keep at least this many rows per rank
+
+static int enable_multigrid_slab(femo_problem *p) {
+    int nx = p->mesh.n[0], gny = p->slab.gny;
+    const int R = p->slab.nranks, rank = p->slab.rank;
+    int rows = gny / R, rc;
+    while (rows % 2 == 0 && nx % 2 == 0 && rows / 2 >= kDistMinRows && nx / 2 >= 2) {
+        nx /= 2; gny /= 2; rows /= 2;
+        femo_problem *c = nullptr;
+        if ((rc = create_slab_problem(p->family, p->params, 8, nx, gny, p->mesh.lo, p->mesh.hi, rank, R, true, &c))) return rc;
+        c->parent = p;
+        p->mg.push_back(c);
+    }
+    if (rows % 2 != 0 || nx % 2 != 0)
+        return set_err(FEMO_EINVAL, "partitioned multigrid needs nx and rows-per-rank divisible by 2 down to the replicated level (use powers of two)");
+    // replicated levels: the whole coarse lattice on every rank
+    nx /= 2; gny /= 2;
+    bool first = true;
+    while (first || nx > kMgCoarsest || gny > kMgCoarsest) {
+        if (!first) {
+            if (nx > kMgCoarsest) nx = (nx + 1) / 2;
+            if (gny > kMgCoarsest) gny = (gny + 1) / 2;
+        }
+        first = false;
+        Mesh cm;
+        make_unit_square_tri(nx, gny, p->mesh.lo, p->mesh.hi, cm);
+        femo_problem *c = nullptr;
+        if ((rc = create_problem_impl(cm, p->family, p->params, 8, true, nullptr, 0, &c))) return rc;
+        c->parent = p;
+        c->replicated = true;
+        p->mg.push_back(c);
+    }
+    if (!p->bc_mark.empty()) return propagate_bc(p);
+    return FEMO_OK;
+}
+
 int femo_problem_enable_multigrid(femo_problem *p) {
     if (!p) return set_err(FEMO_EINVAL, "femo_problem_enable_multigrid: null");
     if (p->uploaded) return set_err(FEMO_ESTATE, "femo_problem_enable_multigrid must precede femo_problem_upload");
     if (p->mesh.kind != MESH_TRI || p->state.element != EL_VERTEX || p->state.block != 1)
         return set_err(FEMO_EINVAL, "multigrid is available for scalar P1 states on lattice triangle meshes");
     if (!p->mg.empty()) return FEMO_OK;
+    if (p->slab.active) return enable_multigrid_slab(p);
     int nx = p->mesh.n[0], ny = p->mesh.n[1];
     while (nx > kMgCoarsest || ny > kMgCoarsest) {
         if (nx > kMgCoarsest) nx = (nx + 1) / 2;
@@ -765,9 +862,13 @@ static int propagate_bc(femo_problem *root) {
     for (femo_problem *C : root->mg) {
         std::vector<int32_t> list;
         const int fnx = F->mesh.n[0], fny = F->mesh.n[1], cnx = C->mesh.n[0], cny = C->mesh.n[1];
+        const int fj0 = F->slab.active ? F->slab.crow0 : 0, cj0 = C->slab.active ? C->slab.crow0 : 0;
+        const int fg = F->slab.active ? F->slab.gny : fny, cg = C->slab.active ? C->slab.gny : cny;
         for (int J = 0; J <= cny; ++J)
             for (int I = 0; I <= cnx; ++I) {
-                const int i = (int)std::llround((double)I * fnx / cnx), j = (int)std::llround((double)J * fny / cny);
+                const int i = (int)std::llround((double)I * fnx / cnx);
+                int j = (int)std::llround((double)(J + cj0) * fg / cg) - fj0;     // nearest fine row, local index
+                j = std::min(std::max(j, 0), fny);                                 // ghost rows without a local parent: same column
                 if (!F->bc_mark.empty() && F->bc_mark[(int64_t)j * (fnx + 1) + i]) list.push_back(J * (cnx + 1) + I);
             }
         int32_t ptr[2] = {0, (int32_t)list.size()};
@@ -1077,6 +1178,57 @@ int femo_problem_launch_count(const femo_problem *p, long long *count) {
     if (!p || !count) return set_err(FEMO_EINVAL, "femo_problem_launch_count: null");
     *count = total_launches(p);
     return FEMO_OK;
+}
+
+// ---- multi-GPU communicator ------------------------------------------------
+int femo_comm_unique_id(char id[128]) {
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId u;
+    FEMO_NCCL(g_comm.api.GetUniqueId(&u));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id, &u, 128);
+    return FEMO_OK;
+}
+
+int femo_comm_init(const char id[128], int rank, int nranks, int device) {
+    if (!id || nranks < 1 || rank < 0 || rank >= nranks) return set_err(FEMO_EINVAL, "femo_comm_init: bad arguments");
+    if (g_comm.active) return set_err(FEMO_ESTATE, "femo_comm_init: communicator already initialised");
+    if (femo_device_count() <= device || device < 0) return set_err(FEMO_ENODEVICE, "femo_comm_init: no such CUDA device");
+    int rc = nccl_load();
+    if (rc) return rc;
+    FEMO_CUDA(cudaSetDevice(device));
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    FEMO_NCCL(g_comm.api.CommInitRank(&g_comm.comm, nranks, u, rank));
+    g_comm.rank = rank;
+    g_comm.nranks = nranks;
+    g_comm.active = nranks > 1;
+    return FEMO_OK;
+}
+
+int femo_comm_finalize(void) {
+    if (g_comm.comm) {
+        g_comm.api.CommDestroy(g_comm.comm);
+        g_comm.comm = nullptr;
+    }
+    g_comm.active = false;
+    return FEMO_OK;
+}
+
+int femo_comm_stats(long long stats[2]) {
+    if (!stats) return set_err(FEMO_EINVAL, "femo_comm_stats: null");
+    stats[0] = g_comm.halo_exchanges;
+    stats[1] = g_comm.allreduces;
+    return FEMO_OK;
+}
+
+/* refresh the ghost rows of a state-space (kind 0) or cell-wise input (kind 1) vector */
+int femo_halo_exchange(femo_problem *p, double *d_v, int kind) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!d_v) return set_err(FEMO_EINVAL, "femo_halo_exchange: null");
+    return kind == 0 ? halo_nodes(p, d_v) : halo_cells(p, d_v);
 }
 
 // ---- assembly -------------------------------------------------------------

@@ -54,6 +54,19 @@ void make_unit_square_tri(int nx, int ny, const double lo[2], const double hi[2]
         }
 }
 
+void make_unit_square_tri_slab(int nx, int gny, int row0, int nrows, const double lo[2], const double hi[2], Mesh &m) {
+    const double dy = hi[1] - lo[1];
+    double l2[2] = {lo[0], lo[1] + dy * (double)row0 / (double)gny};
+    double h2[2] = {hi[0], lo[1] + dy * (double)(row0 + nrows) / (double)gny};
+    make_unit_square_tri(nx, nrows, l2, h2, m, row0 == 0, row0 + nrows == gny);
+    for (int jl = 0; jl <= nrows; ++jl)
+        for (int ix = 0; ix <= nx; ++ix)
+            m.coords[2 * ((int64_t)jl * (nx + 1) + ix) + 1] = lo[1] + dy * (double)(row0 + jl) / (double)gny;
+    // the slab remembers the extent of the whole domain (functionals normalise by |Omega|)
+    m.lo[1] = lo[1];
+    m.hi[1] = hi[1];
+}
+
 void make_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2], Mesh &m) {
     m = Mesh();
     m.kind = MESH_QUAD;

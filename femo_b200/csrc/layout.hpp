@@ -31,6 +31,9 @@ struct Mesh {
 // interior interfaces of a y-slab of a partitioned mesh: no exterior facets are generated there)
 void make_unit_square_tri(int nx, int ny, const double lo[2], const double hi[2], Mesh &m, bool ext_bottom = true,
                           bool ext_top = true);
+// y-slab of the (nx x gny)-cell lattice on [lo,hi]: cell rows [row0, row0+nrows); vertex coordinates are
+// computed with the GLOBAL formula lo + (hi-lo)*j/gny so they agree bit for bit with the unpartitioned mesh
+void make_unit_square_tri_slab(int nx, int gny, int row0, int nrows, const double lo[2], const double hi[2], Mesh &m);
 void make_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2], Mesh &m);
 void make_interval(int n, double x0, double x1, Mesh &m);
 

@@ -89,47 +89,67 @@ __global__ void __launch_bounds__(kThreads)
     rc[idx] = acc;
 }
 
-// 2:1 nested lattices (the common case): integer-only versions of the two transfers above.
-// Prolongation weights of the right-diagonal P1 hat: 1 at coincident nodes, 1/2 along x, y and the (1,1) diagonal.
+// 2:1 nested lattices (the common case), integer-only, slab aware.  A local lattice holds node rows
+// [j0, j0+nrows) of the global lattice; prolongation / restriction / injection address the other
+// level through GLOBAL row indices, so the same kernels serve one GPU (j0 = 0), two distributed
+// slabs, and a distributed fine level over a replicated coarse level.  Rows that would need data
+// outside the local slab are ghost rows: they are skipped / partial and refreshed by halo exchange.
+struct LatD {
+    int nx, nrows, j0;
+};
+
+// weights of the right-diagonal P1 hat: 1 at coincident nodes, 1/2 along x, y and the (1,1) diagonal
 __global__ void __launch_bounds__(kThreads)
-    k_prolong_nested(Lattice f, const double *__restrict__ xc, double *__restrict__ xf, const uint8_t *__restrict__ mask_f) {
+    k_prolong_nested(LatD f, LatD c, const double *__restrict__ xc, double *__restrict__ xf,
+                     const uint8_t *__restrict__ mask_f) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t nf = (int64_t)(f.nx + 1) * (f.ny + 1);
-    if (idx >= nf) return;
+    const int fw = f.nx + 1, cw = c.nx + 1;
+    if (idx >= (int64_t)fw * f.nrows) return;
     if (mask_f && mask_f[idx]) return;
-    const int i = (int)(idx % (f.nx + 1)), j = (int)(idx / (f.nx + 1));
-    const int cw = f.nx / 2 + 1;
-    const int I = i >> 1, J = j >> 1, oi = i & 1, oj = j & 1;
-    // (oi,oj): (0,0) -> c(I,J); (1,0) -> c(I,J)+c(I+1,J); (0,1) -> c(I,J)+c(I,J+1); (1,1) -> c(I,J)+c(I+1,J+1)
-    const double a = xc[(int64_t)J * cw + I];
-    const double v = (oi | oj) ? 0.5 * (a + xc[(int64_t)(J + oj) * cw + (I + oi)]) : a;
-    xf[idx] += v;
+    const int i = (int)(idx % fw), jl = (int)(idx / fw);
+    const int gj = jl + f.j0;
+    const int I = i >> 1, oi = i & 1, oj = gj & 1;
+    const int Jl = (gj >> 1) - c.j0;
+    if (Jl < 0 || Jl + oj >= c.nrows) return;
+    const double a = xc[(int64_t)Jl * cw + I];
+    xf[idx] += (oi | oj) ? 0.5 * (a + xc[(int64_t)(Jl + oj) * cw + (I + oi)]) : a;
 }
 
 __global__ void __launch_bounds__(kThreads)
-    k_restrict_nested(Lattice f, const double *__restrict__ rf, double *__restrict__ rc,
+    k_restrict_nested(LatD f, LatD c, const double *__restrict__ rf, double *__restrict__ rc,
                       const uint8_t *__restrict__ mask_f, const uint8_t *__restrict__ mask_c) {
-    const int cw = f.nx / 2 + 1, ch = f.ny / 2 + 1;
+    const int cw = c.nx + 1, fw = f.nx + 1;
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)cw * ch) return;
+    if (idx >= (int64_t)cw * c.nrows) return;
     if (mask_c && mask_c[idx]) {
         rc[idx] = 0.0;
         return;
     }
-    const int I = (int)(idx % cw), J = (int)(idx / cw);
-    const int i = 2 * I, j = 2 * J, fw = f.nx + 1;
+    const int I = (int)(idx % cw), Jl = (int)(idx / cw);
+    const int i = 2 * I, j = 2 * (Jl + c.j0) - f.j0;      // fine LOCAL row of the coincident node
     auto at = [&](int ii, int jj) -> double {
-        if (ii < 0 || jj < 0 || ii > f.nx || jj > f.ny) return 0.0;
+        if (ii < 0 || jj < 0 || ii > f.nx || jj >= f.nrows) return 0.0;
         const int64_t k = (int64_t)jj * fw + ii;
         return (mask_f && mask_f[k]) ? 0.0 : rf[k];
     };
     rc[idx] = at(i, j) + 0.5 * (at(i - 1, j) + at(i + 1, j) + at(i, j - 1) + at(i, j + 1) + at(i - 1, j - 1) + at(i + 1, j + 1));
 }
 
+// coarse state = fine state at the coincident nodes (rediscretisation of the coarse Jacobian)
+__global__ void __launch_bounds__(kThreads)
+    k_inject_nested(LatD f, LatD c, const double *__restrict__ uf, double *__restrict__ uc) {
+    const int cw = c.nx + 1, fw = f.nx + 1;
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)cw * c.nrows) return;
+    const int I = (int)(idx % cw), Jl = (int)(idx / cw);
+    const int j = 2 * (Jl + c.j0) - f.j0;
+    uc[idx] = (j >= 0 && j < f.nrows) ? uf[(int64_t)j * fw + 2 * I] : 0.0;
+}
+
 // Gershgorin bound of D^-1 A (max_i sum_j |a_ij| / |a_ii|) and dinv in one pass
 __global__ void __launch_bounds__(kThreads)
     k_diag_gershgorin(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ vals,
-                      double *__restrict__ dinv, int64_t n, double *__restrict__ partials) {
+                      double *__restrict__ dinv, int64_t n, int64_t o0, int64_t o1, double *__restrict__ partials) {
     double mx = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double d = 1.0, s = 0.0;
@@ -140,7 +160,7 @@ __global__ void __launch_bounds__(kThreads)
         }
         const double di = (d != 0.0) ? 1.0 / d : 1.0;
         dinv[i] = di;
-        mx = fmax(mx, s * fabs(di));
+        if (i >= o0 && i < o1) mx = fmax(mx, s * fabs(di));
     }
     // block max
     __shared__ double sh[kThreads];
@@ -262,7 +282,6 @@ using namespace femo;
 // ===========================================================================
 // host side
 // ===========================================================================
-static inline Lattice lattice_of(const femo_problem *p) { return Lattice{p->mesh.n[0], p->mesh.n[1]}; }
 
 static long long total_launches(const femo_problem *p) {
     long long n = p->launches;
@@ -334,6 +353,15 @@ struct MgParams {
     double ratio = 4.0;
 };
 
+static inline LatD latd_of(const femo_problem *p) {
+    return LatD{p->mesh.n[0], p->mesh.n[1] + 1, p->slab.active ? p->slab.crow0 : 0};
+}
+// global cell rows of a level (slab: of the partitioned lattice)
+static inline int global_rows(const femo_problem *p) { return p->slab.active ? p->slab.gny : p->mesh.n[1]; }
+static inline bool nested_pair(const femo_problem *F, const femo_problem *C) {
+    return F->mesh.n[0] == 2 * C->mesh.n[0] && global_rows(F) == 2 * global_rows(C);
+}
+
 // one V-cycle: level lv solves A x = b approximately from a zero initial guess
 static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, const MgParams &mp) {
     femo_problem *L = (lv == 0) ? root : root->mg[lv - 1];
@@ -356,14 +384,25 @@ static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, con
     if ((rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, x, M.r, b, nullptr))) return rc;
     const int64_t nc = C->state.ndofs;
     const uint8_t *mf = L->has_bc ? L->d_bc_mark : nullptr, *mc = C->has_bc ? C->d_bc_mark : nullptr;
-    const Lattice lf = lattice_of(L), lc = lattice_of(C);
-    const bool nested = (lf.nx == 2 * lc.nx) && (lf.ny == 2 * lc.ny);
-    if (nested) k_restrict_nested<<<grid_for(nc), kThreads, 0, st>>>(lf, M.r, MC.b, mf, mc);
-    else k_lattice_restrict<<<grid_for(nc), kThreads, 0, st>>>(lf, lc, M.r, MC.b, mf, mc);
-    L->launches++;
+    const bool nested = nested_pair(L, C);
+    if (nested) {
+        if ((rc = halo_nodes(L, M.r))) return rc;                 // coarse owned rows read the fine ghost row below
+        k_restrict_nested<<<grid_for(nc), kThreads, 0, st>>>(latd_of(L), latd_of(C), M.r, MC.b, mf, mc);
+        L->launches++;
+        if (L->slab.active && !C->slab.active)                     // distributed -> replicated level
+            if ((rc = gather_rows(L, MC.b, (size_t)(C->mesh.n[0] + 1), C->mesh.n[1]))) return rc;
+    } else {
+        if (L->slab.active) return set_err(FEMO_ESTATE, "distributed multigrid levels must be 2:1 nested");
+        k_lattice_restrict<<<grid_for(nc), kThreads, 0, st>>>(Lattice{L->mesh.n[0], L->mesh.n[1]}, Lattice{C->mesh.n[0], C->mesh.n[1]}, M.r, MC.b, mf, mc);
+        L->launches++;
+    }
     if ((rc = mg_vcycle(root, lv + 1, MC.b, MC.x, mp))) return rc;
-    if (nested) k_prolong_nested<<<grid_for(n), kThreads, 0, st>>>(lf, MC.x, x, mf);
-    else k_lattice_interp<true><<<grid_for(n), kThreads, 0, st>>>(lc, lf, MC.x, x, mf);
+    if (nested) {
+        if ((rc = halo_nodes(C, MC.x))) return rc;                 // fine owned rows read the coarse ghost row above
+        k_prolong_nested<<<grid_for(n), kThreads, 0, st>>>(latd_of(L), latd_of(C), MC.x, x, mf);
+    } else {
+        k_lattice_interp<true><<<grid_for(n), kThreads, 0, st>>>(Lattice{C->mesh.n[0], C->mesh.n[1]}, Lattice{L->mesh.n[0], L->mesh.n[1]}, MC.x, x, mf);
+    }
     L->launches++;
     FEMO_CHECK_LAUNCH();
     return mg_smooth(L, b, x, false, mp.degree, mp.ratio);
@@ -374,6 +413,7 @@ static int mg_setup(femo_problem *root, const double *vals) {
     if (root->mg.empty()) return set_err(FEMO_ESTATE, "multigrid requested but femo_problem_enable_multigrid was not called before upload");
     const int nlev = (int)root->mg.size() + 1;
     int rc;
+    if (root->coef[0] && (rc = halo_nodes(root, const_cast<double *>(root->coef[0])))) return rc;
     for (int lv = 0; lv < nlev; ++lv) {
         femo_problem *L = (lv == 0) ? root : root->mg[lv - 1];
         femo_mg_level &M = L->mgl;
@@ -385,8 +425,19 @@ static int mg_setup(femo_problem *root, const double *vals) {
             femo_problem *F = (lv == 1) ? root : root->mg[lv - 2];
             const double *uf = (lv == 1) ? root->coef[0] : F->mgl.u;
             if (!uf) return set_err(FEMO_ESTATE, "multigrid setup: state coefficient not set");
-            k_lattice_interp<false><<<grid_for(n), kThreads, 0, st>>>(lattice_of(F), lattice_of(L), uf, M.u, nullptr);
-            L->launches++;
+            if (nested_pair(F, L)) {
+                k_inject_nested<<<grid_for(n), kThreads, 0, st>>>(latd_of(F), latd_of(L), uf, M.u);
+                L->launches++;
+                if (L->slab.active) {
+                    if ((rc = halo_nodes(L, M.u))) return rc;      // the ghost row below has no local fine parent
+                } else if (F->slab.active) {
+                    if ((rc = gather_rows(F, M.u, (size_t)(L->mesh.n[0] + 1), L->mesh.n[1]))) return rc;
+                }
+            } else {
+                if (F->slab.active) return set_err(FEMO_ESTATE, "distributed multigrid levels must be 2:1 nested");
+                k_lattice_interp<false><<<grid_for(n), kThreads, 0, st>>>(Lattice{F->mesh.n[0], F->mesh.n[1]}, Lattice{L->mesh.n[0], L->mesh.n[1]}, uf, M.u, nullptr);
+                L->launches++;
+            }
             L->coef[0] = M.u;
             L->coefn[0] = n;
             if ((rc = femo_assemble_jacobian(L, L->has_bc ? nullptr : M.vals, L->has_bc ? M.vals : nullptr))) return rc;
@@ -398,10 +449,11 @@ static int mg_setup(femo_problem *root, const double *vals) {
             L->launches++;
         } else {
             const int g = red_grid(L, n);
-            k_diag_gershgorin<<<g, kThreads, 0, st>>>(D.rowptr, D.col, M.vals, M.dinv, n, L->d_partials);
+            k_diag_gershgorin<<<g, kThreads, 0, st>>>(D.rowptr, D.col, M.vals, M.dinv, n, L->own_off, L->own_off + L->own_n, L->d_partials);
             k_max_finalize<<<1, kThreads, 0, st>>>(L->d_partials, g, L->d_scalars, S_TMP2);
             L->launches += 2;
             FEMO_CHECK_LAUNCH();
+            if ((rc = allreduce_scalars(L, S_TMP2, 1, true))) return rc;
             double lm;
             if ((rc = read_scalars(L, S_TMP2, 1, &lm))) return rc;
             M.lmax = lm;
@@ -410,4 +462,3 @@ static int mg_setup(femo_problem *root, const double *vals) {
     }
     return FEMO_OK;
 }
-

@@ -1,0 +1,93 @@
+"""Multi-GPU plumbing on the Python side: one process per GPU (torchrun),
+torch.distributed only ships the NCCL unique id; all data-path communication is
+issued by libfemo_b200 on its own stream (include/femo_b200.h, "multi-GPU")."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._lib import lib, check
+from . import engine as _E
+
+_state = dict(initialised=False, rank=0, nranks=1)
+
+
+def init(device=None):
+    """Create the engine's NCCL communicator from the torch.distributed world."""
+    import torch
+    import torch.distributed as dist
+    if _state['initialised']:
+        return _state['rank'], _state['nranks']
+    rank, nranks = dist.get_rank(), dist.get_world_size()
+    device = int(os.environ.get('LOCAL_RANK', rank)) if device is None else device
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        check(lib.femo_comm_unique_id(buf))
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=torch.device('cuda', device))
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().tolist())
+    check(lib.femo_comm_init(raw, rank, nranks, device))
+    _state.update(initialised=True, rank=rank, nranks=nranks)
+    return rank, nranks
+
+
+def finalize():
+    if _state['initialised']:
+        lib.femo_comm_finalize()
+        _state['initialised'] = False
+
+
+def stats():
+    s = (C.c_longlong * 2)()
+    check(lib.femo_comm_stats(s))
+    return dict(halo_exchanges=int(s[0]), allreduces=int(s[1]))
+
+
+class SlabProblem(_E.EngineProblem):
+    """The local problem of one rank: y-slab of an (nx x gny)-cell triangle lattice
+    on [lo, hi] with a one-cell ghost layer (host-side layout needs no GPU)."""
+
+    def __init__(self, family, nx, gny, rank, nranks, lo=(0.0, 0.0), hi=(1.0, 1.0), params=()):
+        h = C.c_void_p()
+        pa = (C.c_double * max(1, len(params)))(*params)
+        check(lib.femo_problem_create_slab(int(family), pa, len(params), int(nx), int(gny), (C.c_double * 2)(*lo),
+                                           (C.c_double * 2)(*hi), int(rank), int(nranks), C.byref(h)))
+        self.mesh = None
+        self.family = family
+        self._h = h
+        s = (C.c_int64 * 16)()
+        check(lib.femo_problem_sizes(self._h, s))
+        self.N, self.nin, self.naux, self.nout = int(s[0]), int(s[1]), int(s[2]), int(s[3])
+        self.M = [int(s[4 + i]) for i in range(self.nin)]
+        self.aux_sizes = [int(s[8 + i]) for i in range(self.naux)]
+        self.uploaded = False
+        self.h2d_bytes = self.d2h_bytes = 0
+        self._keep, self._pinned = {}, {}
+        self.device = None
+        i = (C.c_int64 * 16)()
+        check(lib.femo_problem_slab_info(self._h, i))
+        keys = ('active', 'rank', 'nranks', 'gny', 'crow0', 'ncrows', 'own0', 'own1', 'cown0', 'cown1', 'own_off',
+                'own_n', 'cown_off', 'cown_n', 'nx', 'ny_local')
+        self.slab = {k: int(v) for k, v in zip(keys, i)}
+
+    def local_coords(self):
+        s = (C.c_int64 * 6)()
+        check(lib.femo_problem_mesh_sizes(self._h, s))
+        out = np.empty((int(s[1]), int(s[3])), dtype=np.float64)
+        check(lib.femo_problem_mesh_copy(self._h, 0, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def local_cells(self):
+        s = (C.c_int64 * 6)()
+        check(lib.femo_problem_mesh_sizes(self._h, s))
+        out = np.empty((int(s[0]), int(s[2])), dtype=np.int32)
+        check(lib.femo_problem_mesh_copy(self._h, 1, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def halo(self, tensor, kind=0):
+        check(lib.femo_halo_exchange(self._h, C.c_void_p(tensor.data_ptr()), kind))
+        return tensor
+
+    def owned(self, tensor):
+        """The owned block of a local state-space vector."""
+        return tensor[self.slab['own_off']:self.slab['own_off'] + self.slab['own_n']]

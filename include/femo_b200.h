@@ -92,6 +92,30 @@ int femo_problem_gather_map(const femo_problem *p, int which, int32_t *ptr, int3
  * or after femo_problem_upload (after: synchronises); nlists = 0 clears. */
 int femo_problem_set_bc(femo_problem *p, const int32_t *dofs, const int32_t *list_ptr, int nlists, const double *g);
 
+/* ---- multi-GPU: one process per GPU, y-slab partition, NCCL ------------------
+ * What the reference only nominally gets from MPI/PETSc: the lattice is cut
+ * into nranks slabs of gny/nranks cell rows; each rank's local problem holds its rows plus one ghost
+ * cell row below / one ghost node row above, so assembly of owned rows needs no communication;
+ * SpMV inputs are halo-exchanged (ncclSend/Recv of whole rows) and Krylov / Newton scalars are
+ * all-reduced, all on the problem's stream.
+ * Rank 0 calls femo_comm_unique_id and ships the 128 bytes to the others (e.g. torch.distributed);
+ * every rank then calls femo_comm_init once. */
+int femo_comm_unique_id(char id[128]);
+int femo_comm_init(const char id[128], int rank, int nranks, int device);
+int femo_comm_finalize(void);
+int femo_comm_stats(long long stats[2]);   /* [halo exchanges, all-reduces] issued so far */
+/* Host only: the local problem of `rank` on the (nx x gny)-cell triangle lattice over [lo,hi]. */
+int femo_problem_create_slab(int family, const double *params, int nparams, int nx, int gny, const double lo[2],
+                             const double hi[2], int rank, int nranks, femo_problem **out);
+/* info: active, rank, nranks, gny, first local cell row, local cell rows, owned node rows [own0,own1),
+ * owned cell rows [cown0,cown1) (local indices), own_off, own_n (dofs), cown_off, cown_n (cells), nx, ny_local */
+int femo_problem_slab_info(const femo_problem *p, int64_t info[16]);
+/* the problem's own (local) mesh: same selectors as femo_mesh_sizes / femo_mesh_copy */
+int femo_problem_mesh_sizes(const femo_problem *p, int64_t sizes[6]);
+int femo_problem_mesh_copy(const femo_problem *p, int what, void *out);
+/* refresh ghost rows of a device vector: kind 0 = state-space (nodes), 1 = cell-wise input */
+int femo_halo_exchange(femo_problem *p, double *d_v, int kind);
+
 /* Build the geometric-multigrid hierarchy used by Krylov precond = 2 (coarse
  * lattices, Jacobian-only layouts).  Host only; must precede upload.  Scalar P1
  * states on lattice triangle meshes. */
