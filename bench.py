@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 METRIC = 'state+adjoint solves/s'
 UNIT = 'solves/s'
 N_DEFAULT = 4000
+N_DIST = 4096          # per-rank lattice of the multi-GPU runs (partitioned multigrid needs powers of two)
 KRYLOV_RTOL = 1e-10
 
 
@@ -89,11 +90,23 @@ class ClockSampler:
 # engine-level step (inputs resident in HBM)
 # ---------------------------------------------------------------------------
 class EngineStep:
-    def __init__(self, n, device):
+    """world == 1: the n x n unit-square problem on one GPU.
+    world > 1: ONE problem on [0,1] x [0,world] with N_DIST x (N_DIST*world) cells (weak scaling, square
+    cells), cut into y-slabs: rank r owns N_DIST cell rows + a one-cell ghost layer; halo exchange per
+    SpMV, all-reduced Krylov/Newton scalars, partitioned multigrid -- all inside libfemo_b200 over NCCL."""
+
+    def __init__(self, n, device, rank=0, world=1):
         import torch
         from femo_b200 import engine as E
         self.torch = torch
-        p = E.EngineProblem(E.EngineMesh.unit_square(n), E.FAMILY_NLPOISSON_P1)
+        if world == 1:
+            p = E.EngineProblem(E.EngineMesh.unit_square(n), E.FAMILY_NLPOISSON_P1)
+            self.global_dofs = (n + 1) ** 2
+        else:
+            from femo_b200 import dist as fd
+            p = fd.SlabProblem(E.FAMILY_NLPOISSON_P1, N_DIST, N_DIST * world, rank, world, lo=(0.0, 0.0),
+                               hi=(1.0, float(world)))
+            self.global_dofs = (N_DIST + 1) * (N_DIST * world + 1)
         p.enable_multigrid()
         p.upload(device)
         self.p = p
@@ -274,7 +287,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    es = EngineStep(a.n, local_rank)
+    if world > 1:
+        from femo_b200 import dist as fd
+        fd.init(local_rank)
+    es = EngineStep(a.n, local_rank, rank, world)
     for _ in range(W):
         es.step()
     sampler = ClockSampler(local_rank)
@@ -296,36 +312,66 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = float(tt.item())
-    value = world * a.steps / (ms * 1e-3)          # replicas: every rank solves its own n-mesh problem
+    # one partitioned problem with `world` times the dofs: normalise to solves of the N=1 workload
+    norm = es.global_dofs / float((a.n + 1) ** 2) if world > 1 else 1.0
+    value = norm * a.steps / (ms * 1e-3)
 
-    # e2e through the public API (host numpy in/out)
+    # e2e: host buffers in, host buffers out, copies inside the timed region
     e2e = None
     if not a.no_e2e:
-        info = dict(es.info)
-        del es.vals, es.dv                      # free engine-level buffers; the API path owns its own problem
-        p_keep = es.p
-        api = ApiStep(a.n) if world == 1 or True else None
         import contextlib
         import io
-        quiet = contextlib.redirect_stdout(io.StringIO())    # the reference prints "Converged reason" per solve
-        quiet.__enter__()
-        for _ in range(W):
-            api.step()
-        prob = api.fam.problem
-        h0, d0 = prob.h2d_bytes, prob.d2h_bytes
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            api.step()
-        barrier()
-        dt = time.perf_counter() - t0
-        quiet.__exit__(None, None, None)
+        info = dict(es.info)
+        if world == 1:
+            # through the reference-facing API (FEA + FEAModel + Simulator, numpy in / numpy out)
+            del es.vals, es.dv                  # the API path owns its own problem
+            api = ApiStep(a.n)
+            quiet = contextlib.redirect_stdout(io.StringIO())    # the reference prints "Converged reason" per solve
+            quiet.__enter__()
+            for _ in range(W):
+                api.step()
+            prob = api.fam.problem
+            h0, d0 = prob.h2d_bytes, prob.d2h_bytes
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                api.step()
+            barrier()
+            dt = time.perf_counter() - t0
+            quiet.__exit__(None, None, None)
+            h2d, d2h = (prob.h2d_bytes - h0) // a.steps, (prob.d2h_bytes - d0) // a.steps
+            how = 'FEAModel + Simulator (numpy in/out)'
+        else:
+            # partitioned run: every rank feeds its slab of f from pinned host memory and reads back its
+            # slab of the state, the gradient and J (the CSDL layer above is single-process in the reference)
+            p = es.p
+            hf = torch.full((p.M[0],), 0.1, dtype=torch.float64).pin_memory()
+            hu = torch.empty(p.N, dtype=torch.float64).pin_memory()
+            hg = torch.empty(p.M[0], dtype=torch.float64).pin_memory()
+
+            def host_step():
+                es.f.copy_(hf, non_blocking=True)
+                J = es.step()
+                hu.copy_(es.u, non_blocking=True)
+                hg.copy_(es.grad, non_blocking=True)
+                torch.cuda.synchronize()
+                return J
+            for _ in range(W):
+                host_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                host_step()
+            barrier()
+            dt = time.perf_counter() - t0
+            h2d, d2h = hf.numel() * 8 * world, (hu.numel() + hg.numel()) * 8 * world
+            how = 'C-ABI step per rank with pinned host slabs of f (in), u and dJ/df (out)'
         td = torch.tensor([dt], dtype=torch.float64, device='cuda')
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         dt = float(td.item())
-        e2e = dict(value=world * a.steps / dt, unit=UNIT, h2d_bytes_per_step=(prob.h2d_bytes - h0) // a.steps,
-                   d2h_bytes_per_step=(prob.d2h_bytes - d0) // a.steps, ms_per_step=dt * 1e3 / a.steps)
+        e2e = dict(value=norm * a.steps / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                   ms_per_step=dt * 1e3 / a.steps, path=how)
         es.info = info
 
     if rank == 0:
@@ -340,8 +386,10 @@ def main():
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=W,
                    ms_per_step=ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
                    data='synthetic', config=dict(workload(a.n), parallelism='1 GPU' if world == 1 else
-                                                 '%d independent replicas of the n=%d problem (domain decomposition '
-                                                 'not in this round)' % (world, a.n)),
+                                                 ('one problem on [0,1]x[0,%d], %d x %d cells (%d dofs), y-slab partition '
+                                                  'with one-cell ghost layer over %d GPUs, NCCL halo exchange + all-reduce, '
+                                                  'partitioned multigrid; value = solves/s x dofs/dofs(N=1 workload)'
+                                                  % (world, N_DIST, N_DIST * world, es.global_dofs, world))),
                    clocks=clocks, gpu_launches=int(launches), e2e=e2e,
                    roofline=dict(bound='hbm', kernel='femo::k_spmv (CSR-stream SpMV, fine-level Jacobian)',
                                  achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,

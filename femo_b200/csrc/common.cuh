@@ -155,6 +155,7 @@ struct femo_problem {
     int64_t own_off = 0, own_n = 0;        // owned state dofs: [own_off, own_off + own_n)
     int64_t cown_off = 0, cown_n = 0;      // owned cells
     bool replicated = false;               // multigrid level held identically by every rank
+    bool mg_bc_dirty = false;              // replicated levels still need the gathered Dirichlet marks
     // geometric multigrid: coarse problems (owned), Jacobian-only layouts
     bool jac_only = false;
     std::vector<femo_problem *> mg;

@@ -478,7 +478,8 @@ static int push_bc(femo_problem *p) {
 }
 
 extern "C" {
-static int propagate_bc(femo_problem *root);
+static int propagate_bc(femo_problem *root, int start = 0);
+static int set_bc_impl(femo_problem *p, const int32_t *dofs, const int32_t *list_ptr, int nlists, const double *g);
 }
 
 #include "multigrid.cuh"
@@ -857,9 +858,15 @@ static int set_bc_impl(femo_problem *p, const int32_t *dofs, const int32_t *list
 
 // coarse multigrid levels inherit Dirichlet rows geometrically: a coarse node is
 // constrained when the fine node nearest to it is (homogeneous correction equation)
-static int propagate_bc(femo_problem *root) {
-    const femo_problem *F = root;
-    for (femo_problem *C : root->mg) {
+static int propagate_bc(femo_problem *root, int start) {
+    const femo_problem *F = (start == 0) ? root : root->mg[start - 1];
+    for (size_t lv = (size_t)start; lv < root->mg.size(); ++lv) {
+        femo_problem *C = root->mg[lv];
+        if (C->replicated && F->slab.active) {
+            // the first replicated level needs the marks of every rank: gathered on the device at the next set-up
+            root->mg_bc_dirty = true;
+            return FEMO_OK;
+        }
         std::vector<int32_t> list;
         const int fnx = F->mesh.n[0], fny = F->mesh.n[1], cnx = C->mesh.n[0], cny = C->mesh.n[1];
         const int fj0 = F->slab.active ? F->slab.crow0 : 0, cj0 = C->slab.active ? C->slab.crow0 : 0;

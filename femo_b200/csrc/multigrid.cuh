@@ -408,11 +408,46 @@ static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, con
     return mg_smooth(L, b, x, false, mp.degree, mp.ratio);
 }
 
+__global__ void __launch_bounds__(kThreads) k_u8_to_f64(const uint8_t *__restrict__ a, double *__restrict__ b, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) b[i] = a[i] ? 1.0 : 0.0;
+}
+
+// Dirichlet marks of the first replicated level: injected from the finest distributed marks each rank
+// owns, gathered over the ranks, then installed (and propagated to the coarser replicated levels) on the host
+static int sync_replicated_bc(femo_problem *root) {
+    size_t g = 0;
+    while (g < root->mg.size() && !root->mg[g]->replicated) ++g;
+    root->mg_bc_dirty = false;
+    if (g == root->mg.size()) return FEMO_OK;
+    femo_problem *F = (g == 0) ? root : root->mg[g - 1];
+    femo_problem *C = root->mg[g];
+    const int64_t nf = F->state.ndofs, nc = C->state.ndofs;
+    cudaStream_t st = root->stream;
+    int rc;
+    double *tf = F->mgl.r, *tc = C->mgl.x;
+    k_u8_to_f64<<<grid_for(nf), kThreads, 0, st>>>(F->d_bc_mark, tf, nf);
+    k_inject_nested<<<grid_for(nc), kThreads, 0, st>>>(latd_of(F), latd_of(C), tf, tc);
+    root->launches += 2;
+    FEMO_CHECK_LAUNCH();
+    if ((rc = gather_rows(F, tc, (size_t)(C->mesh.n[0] + 1), C->mesh.n[1]))) return rc;
+    std::vector<double> h(nc);
+    FEMO_CUDA(cudaMemcpyAsync(h.data(), tc, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
+    FEMO_CUDA(cudaStreamSynchronize(st));
+    std::vector<int32_t> list;
+    for (int64_t i = 0; i < nc; ++i)
+        if (h[i] > 0.5) list.push_back((int32_t)i);
+    int32_t ptr[2] = {0, (int32_t)list.size()};
+    if ((rc = set_bc_impl(C, list.data(), ptr, list.empty() ? 0 : 1, nullptr))) return rc;
+    return propagate_bc(root, (int)g + 1);
+}
+
 // (re)build the hierarchy for the matrix `vals` of the root at the root's current state
 static int mg_setup(femo_problem *root, const double *vals) {
     if (root->mg.empty()) return set_err(FEMO_ESTATE, "multigrid requested but femo_problem_enable_multigrid was not called before upload");
     const int nlev = (int)root->mg.size() + 1;
     int rc;
+    if (root->mg_bc_dirty && (rc = sync_replicated_bc(root))) return rc;
     if (root->coef[0] && (rc = halo_nodes(root, const_cast<double *>(root->coef[0])))) return rc;
     for (int lv = 0; lv < nlev; ++lv) {
         femo_problem *L = (lv == 0) ? root : root->mg[lv - 1];
