@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "families.cuh"
 #include "families2.cuh"
+#include "families3.cuh"
 #include "dist.cuh"
 
 namespace femo {
@@ -224,6 +225,12 @@ __global__ void __launch_bounds__(kThreads) k_axpy(double a, const double *__res
         y[i] += a * x[i];
 }
 
+__global__ void __launch_bounds__(kThreads)
+    k_divide(double a, const double *__restrict__ num, const double *__restrict__ den, double *__restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = a * num[i] / den[i];
+}
+
 __global__ void __launch_bounds__(kThreads) k_fill(double a, double *__restrict__ y, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         y[i] = a;
@@ -316,7 +323,8 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
     cudaStream_t st = p->stream;
     int rc;
     if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
-    if (op != OP_JAC && (rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
+    const bool analytic_src = p->family == FEMO_FAMILY_MASS_P1 && p->params[1] < 1.5;
+    if (op != OP_JAC && !analytic_src && (rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
     double *cells_out = p->d_scratch;
     double *facets_out = p->d_scratch + ((mask & 1) ? nc * op_planes(p, op) : 0);
     const int gc = grid_for(nc), gf = grid_for(std::max<int64_t>(nf, 1));
@@ -349,6 +357,18 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
                 else k_nlpoisson_p1_facet<OP_JAC><<<gf, kThreads, 0, st>>>(F);
                 p->launches++;
             }
+            break;
+        }
+        case FEMO_FAMILY_MASS_P1: {
+            if (op != OP_RES && op != OP_JAC) return set_err(FEMO_EINVAL, "projection family: only residual and mass matrix");
+            MassArgs A;
+            A.coords = p->d_coords; A.cellsT = p->d_cellsT; A.ncells = nc;
+            A.u = p->coef[0]; A.src = p->coef[1];
+            A.target = (int)p->params[0]; A.source = (int)p->params[1]; A.power = p->params[2];
+            A.out = cells_out;
+            if (op == OP_RES) k_mass_cell<OP_RES><<<gc, kThreads, 0, st>>>(A);
+            else k_mass_cell<OP_JAC><<<gc, kThreads, 0, st>>>(A);
+            p->launches++;
             break;
         }
         case FEMO_FAMILY_EB_BEAM: {
@@ -574,6 +594,15 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
                     if (nparams < 2) p->params[1] = 10.0;
                 }
                 break;
+            case FEMO_FAMILY_MASS_P1: {
+                if (M.kind != MESH_TRI) throw LayoutError{FEMO_EINVAL, "family needs a triangle mesh"};
+                const int target = (int)p->params[0], source = (int)p->params[1];
+                p->state.init(M, target == 1 ? EL_DG0 : EL_VERTEX, 1);
+                p->nin = 1;
+                p->in[0].init(M, source == 3 ? EL_VERTEX : EL_DG0, 1);
+                p->nout = 0;
+                break;
+            }
             case FEMO_FAMILY_EB_BEAM:
                 if (M.kind != MESH_INTERVAL) throw LayoutError{FEMO_EINVAL, "family needs an interval mesh"};
                 p->state.init(M, EL_HERMITE3, 2);
@@ -1359,6 +1388,16 @@ int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_
     p->launches++;
     FEMO_CHECK_LAUNCH();
     return launch_spmv<false>(p, D.t_rb, D.t_nrb, D.t_rowptr, D.t_col, p->d_tvals, d_x, d_y, nullptr, nullptr, false);
+}
+
+int femo_pointwise_divide(femo_problem *p, double a, const double *d_num, const double *d_den, double *d_out, int64_t n) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!d_num || !d_den || !d_out || n < 0) return set_err(FEMO_EINVAL, "femo_pointwise_divide: bad arguments");
+    k_divide<<<red_grid(p, n), kThreads, 0, p->stream>>>(a, d_num, d_den, d_out, n);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
 }
 
 int femo_axpy(femo_problem *p, double a, const double *d_x, double *d_y, int64_t n) {

@@ -13,6 +13,7 @@ FAMILY_POISSON_P1 = 1
 FAMILY_NLPOISSON_P1 = 2
 FAMILY_EB_BEAM = 3
 FAMILY_SIMP_Q1 = 4
+FAMILY_MASS_P1 = 5
 
 
 def device_count():

@@ -248,10 +248,21 @@ class Function:
     def rename(self, name, label=None):
         self.name = name
 
+    def __pow__(self, p):
+        return Expr('pow', self, p)
+
     def copy(self):
         g = Function(self.function_space, self.name)
         g._assign(self._host_array())
         return g
+
+
+class Expr:
+    """Stand-in for the UFL expressions handed to `project`: ('u_ex'|'f_ex') analytic fields,
+    ('pow', function, exponent)."""
+
+    def __init__(self, kind, *args):
+        self.kind, self.args = kind, args
 
 
 class Constant:

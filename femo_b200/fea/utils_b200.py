@@ -296,6 +296,10 @@ def setUpKSP_MUMPS(A):
     return KSP(A)
 
 
+from .projection import project  # noqa: E402,F401  (utils_dolfinx.py:549-583)
+from .fem import Expr  # noqa: E402,F401
+
+
 # ---- errors and projection (utils_dolfinx.py:225-237,549-583) ------------------------
 def errorNorm(v, v_ex, norm='L2'):
     """L2 norm of v - v_ex for Functions on the same P1/DG0 space (degree-2 rule)."""

@@ -13,6 +13,11 @@ ALPHA_1 = 6E-7
 BETA = 1e1
 U_EX_UFL = 'sin(2*pi*x[0])*sin(pi*x[1])'
 
+# expressions for project(): u_ex and f_ex = -div(grad(u_ex)) + u_ex**3 (run_nonlinear_poisson_opt.py:165-169)
+from ..fea.fem import Expr  # noqa: E402
+u_ex_ufl = Expr('u_ex')
+f_ex_ufl = Expr('f_ex')
+
 
 def _family(u, f):
     return FormFamily.get(_E.FAMILY_NLPOISSON_P1, u.function_space.mesh, u, [f], params=[ALPHA_1, BETA])

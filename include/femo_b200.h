@@ -44,6 +44,8 @@ typedef struct femo_problem femo_problem;
 #define FEMO_FAMILY_NLPOISSON_P1 2 /* examples/nonlinear_poisson_opt/run_nonlinear_poisson_opt.py:88-116,140-142 */
 #define FEMO_FAMILY_EB_BEAM 3      /* examples/beam_thickness_opt/run_thickness_opt_cantilever_beam.py:71-85 */
 #define FEMO_FAMILY_SIMP_Q1 4      /* examples/beam_topo_opt/run_topo_opt_cantilever_beam.py:62-86 */
+#define FEMO_FAMILY_MASS_P1 5      /* L2 projection, femo/fea/utils_dolfinx.py:549-583; params: target (0 CG1, 1 DG0),
+                                      source (0 u_ex, 1 f_ex analytic; 2 DG0 input^power; 3 CG1 input), power */
 
 /* matrix selector `which`: 0 = dR/du (N x N), 1+s = dR/dm_s (N x M_s) */
 
@@ -170,6 +172,9 @@ int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_
 /* y += a x on the problem's stream (the d_inputs accumulation of
  * compute_jacvec_product, state_model.py:180-199, kept on the device). */
 int femo_axpy(femo_problem *p, double a, const double *d_x, double *d_y, int64_t n);
+
+/* out = a * num / den (Vec.pointwiseDivide of the lumped projection, utils_dolfinx.py:566-569) */
+int femo_pointwise_divide(femo_problem *p, double a, const double *d_num, const double *d_den, double *d_out, int64_t n);
 
 typedef struct femo_krylov_opts {
     double rtol;      /* ||r|| <= rtol*||b||   */

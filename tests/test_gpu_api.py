@@ -124,3 +124,32 @@ def test_api_error_behaviour(cuda_device):
     assert np.all(f.x.array == 1.0)                        # quirk B5: init_val overwrite
     r = assemble(pdeRes(u, None, f), dim=7)
     assert isinstance(r, TypeError)                        # returned, not raised (quirk B7)
+
+
+def test_project_matches_oracle(cuda_device):
+    """`project` (utils_dolfinx.py:549-583) as used at run_nonlinear_poisson_opt.py:165-169 and
+    run_topo_opt_cantilever_beam.py:264-268, against the oracle's exact mass solve."""
+    from femo_b200.fea.fea_b200 import createUnitSquareMesh, FunctionSpace, Function, project, getFuncArray
+    from femo_b200.forms.nonlinear_poisson import u_ex_ufl, f_ex_ufl
+    from oracle.projection import MassProjection
+    n = 12
+    mesh = createUnitSquareMesh(n)
+    m = om.unit_square_tri(n)
+    u_ex = Function(FunctionSpace(mesh, ('CG', 1)))
+    project(u_ex_ufl, u_ex)
+    assert relerr(getFuncArray(u_ex), MassProjection(m, 'CG', 'u_ex').project()) < 1e-10
+    f_ex = Function(FunctionSpace(mesh, ('DG', 0)))
+    project(f_ex_ufl, f_ex)
+    assert relerr(getFuncArray(f_ex), MassProjection(m, 'DG', 'f_ex').project()) < 1e-10
+    rho = Function(FunctionSpace(mesh, ('DG', 0)))
+    r = np.random.default_rng(0).random(rho.function_space.dim)
+    rho.vector.setArray(r)
+    pen = Function(FunctionSpace(mesh, ('DG', 0)))
+    project(rho ** 3, pen)
+    assert relerr(getFuncArray(pen), r ** 3) < 1e-12
+    g = Function(FunctionSpace(mesh, ('CG', 1)))
+    project(rho, g)
+    assert relerr(getFuncArray(g), MassProjection(m, 'CG', 'dg_pow', 1.0).project(r)) < 1e-10
+    gl = Function(FunctionSpace(mesh, ('CG', 1)))
+    project(u_ex_ufl, gl, lump_mass=True)
+    assert relerr(getFuncArray(gl), getFuncArray(u_ex)) < 0.2
