@@ -2,6 +2,7 @@
 // boundary conditions, SpMV, fused Krylov vector kernels) and the C ABI.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -745,12 +746,20 @@ int femo_problem_slab_info(const femo_problem *p, int64_t info[16]) {
     return FEMO_OK;
 }
 
-constexpr int kDistMinRows = 16;   // distributed multigrid levels keep at least this many rows per rank
+// Distributed multigrid levels keep at least this many lattice rows per rank; coarser levels are replicated
+// (their work is < 1% of the fine level, and every distributed level costs ~5 halo exchanges per V-cycle).
+// FEMO_DIST_MIN_ROWS overrides (the tests use 16 to exercise several distributed levels on small meshes).
+static int dist_min_rows() {
+    const char *e = getenv("FEMO_DIST_MIN_ROWS");
+    int v = e ? atoi(e) : 128;
+    return v < 2 ? 2 : v;
+}
 
 static int enable_multigrid_slab(femo_problem *p) {
     int nx = p->mesh.n[0], gny = p->slab.gny;
     const int R = p->slab.nranks, rank = p->slab.rank;
     int rows = gny / R, rc;
+    const int kDistMinRows = dist_min_rows();
     while (rows % 2 == 0 && nx % 2 == 0 && rows / 2 >= kDistMinRows && nx / 2 >= 2) {
         nx /= 2; gny /= 2; rows /= 2;
         femo_problem *c = nullptr;

@@ -53,10 +53,11 @@ def test_slab_partition_covers_global_numbering(R):
     assert np.all(owner_nodes >= 0) and np.all(owner_cells >= 0)          # every dof / cell owned exactly once
 
 
-def test_partitioned_multigrid_needs_powers_of_two():
+def test_partitioned_multigrid_needs_powers_of_two(monkeypatch):
     from femo_b200._lib import FemoError
+    monkeypatch.setenv('FEMO_DIST_MIN_ROWS', '16')
     p = SlabProblem(2, 64, 128, 0, 2)
-    assert p.enable_multigrid() >= 4
+    assert p.enable_multigrid() >= 3
     q = SlabProblem(2, 60, 100, 0, 2)                         # 50 rows per rank -> 25: cannot reach the replicated level
     with pytest.raises(FemoError):
         q.enable_multigrid()

@@ -20,6 +20,7 @@ def test_slab_partition_matches_single_gpu(cuda_device, famid):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(R),
            '--master-addr', '127.0.0.1', '--master-port', '29611', os.path.join(ROOT, 'tests', 'dist_check.py'),
            str(famid), '64', str(64 * R)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, FEMO_DIST_MIN_ROWS='16')     # several distributed levels even on this small mesh
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert 'OK' in out.stdout
