@@ -199,3 +199,61 @@ def test_against_golden_fixtures(cuda_device, path):
     g = p.assemble_output_grad(0, 1).cpu().numpy() - p.spmv(1, p.assemble_dRdm(0), lam, transpose=True).cpu().numpy()
     assert relerr(lam.cpu().numpy(), z['lam']) < 1e-8
     assert relerr(g, z['total']) < 1e-8
+
+
+def test_bitwise_reproducible_run_to_run(cuda_device):
+    """Determinism (sorted segmented reduction, fixed reduction trees): two runs give identical bits."""
+    outs = []
+    for _ in range(2):
+        c = Case(2, 40, 24, seed=11, mg=True)
+        c.set_input(0.1 * np.ones(c.F.M))
+        c.set_state(np.zeros(c.F.N))
+        c.p.newton_solve(kind='SNES', krylov_rtol=1e-12, precond=2)
+        vals, _ = c.p.assemble_jacobian()
+        outs.append((c.d_u.cpu().numpy().copy(), vals.cpu().numpy().copy(), c.p.assemble_output(0)))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] == outs[1][2]
+
+
+def test_edge_cases(cuda_device):
+    """Smallest meshes, empty Dirichlet set, BC change after upload, zero inputs."""
+    c = Case(1, 1, 1, seed=0, bc=False)                      # one square = two cells, no BC
+    R = c.p.assemble_residual().cpu().numpy()
+    assert relerr(R, asm.assemble_vector(c.F.residual(c.u, c.f), c.F.N)) < TOL
+    _, vbc = c.p.assemble_jacobian(plain=False, bc=True)     # no BC set: BC'd copy equals the plain matrix
+    assert relerr(vbc.cpu().numpy(), asm.assemble_matrix(c.F.jacobian(c.u, c.f), (c.F.N, c.F.N)).data) < TOL
+    # install Dirichlet data after upload, then clear it again
+    from _cases import square_boundary_lists
+    lists = square_boundary_lists(c.omesh.coords)
+    c.p.set_bc(lists)
+    bc = asm.DirichletBC(c.F.N, lists, 0.0)
+    _, vbc = c.p.assemble_jacobian(plain=False, bc=True)
+    assert relerr(vbc.cpu().numpy(), asm.assemble_matrix(c.F.jacobian(c.u, c.f), (c.F.N, c.F.N), bc).data) < TOL
+    c.p.set_bc([])
+    _, vbc = c.p.assemble_jacobian(plain=False, bc=True)
+    assert relerr(vbc.cpu().numpy(), asm.assemble_matrix(c.F.jacobian(c.u, c.f), (c.F.N, c.F.N)).data) < TOL
+    # all-zero state and input
+    c2 = Case(2, 5, 3, seed=1)
+    c2.set_state(np.zeros(c2.F.N))
+    c2.set_input(np.zeros(c2.F.M))
+    assert relerr(c2.p.assemble_residual().cpu().numpy(),
+                  asm.assemble_vector(c2.F.residual(np.zeros(c2.F.N), np.zeros(c2.F.M)), c2.F.N)) < TOL
+
+
+def test_hypothesis_random_fields(cuda_device):
+    """Seeded random coefficient fields of varying magnitude (SURVEY.md section 8c golden-vector plan)."""
+    from hypothesis import given, settings, strategies as st
+    c = Case(2, 9, 6, seed=0)
+
+    @settings(max_examples=15, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.floats(1e-3, 1e3))
+    def run(seed, scale):
+        rng = np.random.default_rng(seed)
+        u, f = scale * rng.standard_normal(c.F.N), rng.standard_normal(c.F.M) / scale
+        c.set_state(u)
+        c.set_input(f)
+        assert relerr(c.p.assemble_residual().cpu().numpy(), asm.assemble_vector(c.F.residual(u, f), c.F.N)) < 1e-11
+        vals, _ = c.p.assemble_jacobian()
+        assert relerr(vals.cpu().numpy(), asm.assemble_matrix(c.F.jacobian(u, f), (c.F.N, c.F.N)).data) < 1e-11
+    run()
