@@ -951,7 +951,7 @@ static void child_bytes(const femo_problem *c, bool coarsest, size_t *sb, size_t
     s += Arena::need(std::max<size_t>(1, c->fb_cell.size()), 4) * 2;
     s += pattern_bytes(c->pat[0], true);
     s += Arena::need(N, 1) + 2 * Arena::need(N, 8) + Arena::need(N, 4) + 1024;
-    w += Arena::need(c->pat[0].nnz, 8) + 7 * Arena::need(N, 8);
+    w += Arena::need(c->pat[0].nnz, 8) + 9 * Arena::need(N, 8);
     w += Arena::need(3 * kMaxPartials, 8) + Arena::need(S_COUNT, 8) + 1024;
     if (coarsest) w += 2 * Arena::need(N * N, 8);
     *sb = s;
@@ -1009,6 +1009,8 @@ static int upload_child(femo_problem *root, femo_problem *c, bool coarsest) {
     L.d = root->wk.take<double>(N);
     L.q = root->wk.take<double>(N);
     L.u = root->wk.take<double>(N);
+    L.fb = root->wk.take<double>(N);
+    L.fx = root->wk.take<double>(N);
     c->d_partials = root->wk.take<double>(3 * kMaxPartials);
     c->d_scalars = root->wk.take<double>(S_COUNT);
     if (coarsest) {

@@ -362,6 +362,9 @@ static inline bool nested_pair(const femo_problem *F, const femo_problem *C) {
     return F->mesh.n[0] == 2 * C->mesh.n[0] && global_rows(F) == 2 * global_rows(C);
 }
 
+static int mg_restrict(femo_problem *L, femo_problem *C, double *rf, double *rc_);
+static int mg_prolong_add(femo_problem *L, femo_problem *C, double *xc, double *xf);
+
 // one V-cycle: level lv solves A x = b approximately from a zero initial guess
 static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, const MgParams &mp) {
     femo_problem *L = (lv == 0) ? root : root->mg[lv - 1];
@@ -382,30 +385,90 @@ static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, con
     if ((rc = mg_smooth(L, b, x, true, mp.degree, mp.ratio))) return rc;
     // r = b - A x ; restrict
     if ((rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, x, M.r, b, nullptr))) return rc;
+    if ((rc = mg_restrict(L, C, M.r, MC.b))) return rc;
+    if ((rc = mg_vcycle(root, lv + 1, MC.b, MC.x, mp))) return rc;
+    if ((rc = mg_prolong_add(L, C, MC.x, x))) return rc;
+    return mg_smooth(L, b, x, false, mp.degree, mp.ratio);
+}
+
+// transfers between level lv (fine) and lv+1 (coarse) of the hierarchy, shared by the V-cycle and the
+// full-multigrid start: rc = P^T rf (replicated coarse levels are gathered), xf (+)= P xc
+static int mg_restrict(femo_problem *L, femo_problem *C, double *rf, double *rc_) {
     const int64_t nc = C->state.ndofs;
     const uint8_t *mf = L->has_bc ? L->d_bc_mark : nullptr, *mc = C->has_bc ? C->d_bc_mark : nullptr;
-    const bool nested = nested_pair(L, C);
-    if (nested) {
-        if ((rc = halo_nodes(L, M.r))) return rc;                 // coarse owned rows read the fine ghost row below
-        k_restrict_nested<<<grid_for(nc), kThreads, 0, st>>>(latd_of(L), latd_of(C), M.r, MC.b, mf, mc);
+    cudaStream_t st = L->stream;
+    int rc;
+    if (nested_pair(L, C)) {
+        if ((rc = halo_nodes(L, rf))) return rc;                  // coarse owned rows read the fine ghost row below
+        k_restrict_nested<<<grid_for(nc), kThreads, 0, st>>>(latd_of(L), latd_of(C), rf, rc_, mf, mc);
         L->launches++;
         if (L->slab.active && !C->slab.active)                     // distributed -> replicated level
-            if ((rc = gather_rows(L, MC.b, (size_t)(C->mesh.n[0] + 1), C->mesh.n[1]))) return rc;
+            if ((rc = gather_rows(L, rc_, (size_t)(C->mesh.n[0] + 1), C->mesh.n[1]))) return rc;
     } else {
         if (L->slab.active) return set_err(FEMO_ESTATE, "distributed multigrid levels must be 2:1 nested");
-        k_lattice_restrict<<<grid_for(nc), kThreads, 0, st>>>(Lattice{L->mesh.n[0], L->mesh.n[1]}, Lattice{C->mesh.n[0], C->mesh.n[1]}, M.r, MC.b, mf, mc);
+        k_lattice_restrict<<<grid_for(nc), kThreads, 0, st>>>(Lattice{L->mesh.n[0], L->mesh.n[1]}, Lattice{C->mesh.n[0], C->mesh.n[1]}, rf, rc_, mf, mc);
         L->launches++;
     }
-    if ((rc = mg_vcycle(root, lv + 1, MC.b, MC.x, mp))) return rc;
-    if (nested) {
-        if ((rc = halo_nodes(C, MC.x))) return rc;                 // fine owned rows read the coarse ghost row above
-        k_prolong_nested<<<grid_for(n), kThreads, 0, st>>>(latd_of(L), latd_of(C), MC.x, x, mf);
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
+static int mg_prolong_add(femo_problem *L, femo_problem *C, double *xc, double *xf) {
+    const int64_t n = L->state.ndofs;
+    const uint8_t *mf = L->has_bc ? L->d_bc_mark : nullptr;
+    cudaStream_t st = L->stream;
+    int rc;
+    if (nested_pair(L, C)) {
+        if ((rc = halo_nodes(C, xc))) return rc;                   // fine owned rows read the coarse ghost row above
+        k_prolong_nested<<<grid_for(n), kThreads, 0, st>>>(latd_of(L), latd_of(C), xc, xf, mf);
     } else {
-        k_lattice_interp<true><<<grid_for(n), kThreads, 0, st>>>(Lattice{C->mesh.n[0], C->mesh.n[1]}, Lattice{L->mesh.n[0], L->mesh.n[1]}, MC.x, x, mf);
+        k_lattice_interp<true><<<grid_for(n), kThreads, 0, st>>>(Lattice{C->mesh.n[0], C->mesh.n[1]}, Lattice{L->mesh.n[0], L->mesh.n[1]}, xc, xf, mf);
     }
     L->launches++;
     FEMO_CHECK_LAUNCH();
-    return mg_smooth(L, b, x, false, mp.degree, mp.ratio);
+    return FEMO_OK;
+}
+
+static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, const MgParams &mp);
+
+// Full-multigrid start (nested iteration): x0 ~ A^-1 b to discretisation accuracy for about 1.5 V-cycles
+// of work.  Coarsest level solved exactly; each finer level prolongs the coarser iterate and corrects
+// it with one V-cycle on its residual.
+static int mg_fmg(femo_problem *root, const double *b, double *x, const MgParams &mp) {
+    const int nlev = (int)root->mg.size() + 1;
+    int rc;
+    auto level = [&](int lv) { return lv == 0 ? root : root->mg[lv - 1]; };
+    // right-hand sides of all levels
+    for (int lv = 0; lv + 1 < nlev; ++lv) {
+        femo_problem *L = level(lv), *C = level(lv + 1);
+        double *rf = (lv == 0) ? const_cast<double *>(b) : L->mgl.fb;
+        if ((rc = mg_restrict(L, C, rf, C->mgl.fb))) return rc;
+    }
+    for (int lv = nlev - 1; lv >= 0; --lv) {
+        femo_problem *L = level(lv);
+        femo_mg_level &M = L->mgl;
+        const int64_t n = L->state.ndofs;
+        cudaStream_t st = L->stream;
+        const double *bl = (lv == 0) ? b : M.fb;
+        double *xl = (lv == 0) ? x : M.fx;
+        if (lv == nlev - 1) {
+            k_dense_apply<<<(int)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(M.dense, bl, xl, (int)n);
+            L->launches++;
+            continue;
+        }
+        femo_problem *C = level(lv + 1);
+        FEMO_CUDA(cudaMemsetAsync(xl, 0, sizeof(double) * n, st));
+        if ((rc = mg_prolong_add(L, C, C->mgl.fx, xl))) return rc;
+        // residual of the prolonged iterate into M.b (free at this level), V-cycle correction into M.x
+        const DevPattern &D = L->dpat[0];
+        double *rl = (lv == 0) ? root->kr_r : M.b, *el = (lv == 0) ? root->kr_z : M.x;
+        if ((rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, xl, rl, bl, nullptr))) return rc;
+        if ((rc = mg_vcycle(root, lv, rl, el, mp))) return rc;
+        k_axpy<<<red_grid(L, n), kThreads, 0, st>>>(1.0, el, xl, n);
+        L->launches++;
+        FEMO_CHECK_LAUNCH();
+    }
+    return FEMO_OK;
 }
 
 __global__ void __launch_bounds__(kThreads) k_u8_to_f64(const uint8_t *__restrict__ a, double *__restrict__ b, int64_t n) {

@@ -184,7 +184,7 @@ typedef struct femo_krylov_opts {
                          3 explicit dense inverse (N <= 512; the direct-solve analogue) */
     int cheb_degree;  /* smoother degree of the V-cycle (default 2) */
     int method;       /* 0 CG, 1 GMRES(restart) */
-    int restart;
+    int restart;      /* GMRES restart; with precond 2: 1 disables the full-multigrid start */
     int check_every;  /* residual-norm host check period (>=1) */
     double cheb_ratio; /* smoother targets [lmax/ratio, lmax] of D^-1 A (default 8) */
 } femo_krylov_opts;
