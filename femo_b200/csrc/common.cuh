@@ -104,6 +104,7 @@ struct femo_mg_level {
     double *dinv = nullptr, *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr, *q = nullptr;
     double *u = nullptr;      // restricted state used to rediscretise the coarse Jacobian
     double *dense = nullptr, *dense_tmp = nullptr;  // coarsest level: explicit inverse
+    double *m = nullptr;                            // restricted cell-wise input (SIMP density)
     double *fb = nullptr, *fx = nullptr;            // full-multigrid start: restricted right-hand side, nested iterate
     double lmax = 2.0;
 };

@@ -325,7 +325,8 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
     int rc;
     if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
     const bool analytic_src = p->family == FEMO_FAMILY_MASS_P1 && p->params[1] < 1.5;
-    if (op != OP_JAC && !analytic_src && (rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
+    const bool jac_reads_input = p->family == FEMO_FAMILY_SIMP_Q1 || p->family == FEMO_FAMILY_EB_BEAM;
+    if ((op != OP_JAC || jac_reads_input) && !analytic_src && (rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
     double *cells_out = p->d_scratch;
     double *facets_out = p->d_scratch + ((mask & 1) ? nc * op_planes(p, op) : 0);
     const int gc = grid_for(nc), gf = grid_for(std::max<int64_t>(nf, 1));
@@ -793,16 +794,21 @@ static int enable_multigrid_slab(femo_problem *p) {
 int femo_problem_enable_multigrid(femo_problem *p) {
     if (!p) return set_err(FEMO_EINVAL, "femo_problem_enable_multigrid: null");
     if (p->uploaded) return set_err(FEMO_ESTATE, "femo_problem_enable_multigrid must precede femo_problem_upload");
-    if (p->mesh.kind != MESH_TRI || p->state.element != EL_VERTEX || p->state.block != 1)
-        return set_err(FEMO_EINVAL, "multigrid is available for scalar P1 states on lattice triangle meshes");
+    const bool tri = p->mesh.kind == MESH_TRI && p->state.element == EL_VERTEX && p->state.block == 1;
+    const bool quad = p->mesh.kind == MESH_QUAD && p->state.element == EL_VERTEX;
+    if (!tri && !quad)
+        return set_err(FEMO_EINVAL, "multigrid is available for vertex-based states on lattice triangle / quadrilateral meshes");
     if (!p->mg.empty()) return FEMO_OK;
     if (p->slab.active) return enable_multigrid_slab(p);
     int nx = p->mesh.n[0], ny = p->mesh.n[1];
-    while (nx > kMgCoarsest || ny > kMgCoarsest) {
-        if (nx > kMgCoarsest) nx = (nx + 1) / 2;
-        if (ny > kMgCoarsest) ny = (ny + 1) / 2;
+    // coarsen until the coarsest system fits the explicit inverse (<= 512 dofs)
+    const int coarsest = (p->state.block > 1) ? 6 : kMgCoarsest;
+    while (nx > coarsest || ny > coarsest) {
+        if (nx > coarsest) nx = (nx + 1) / 2;
+        if (ny > coarsest) ny = (ny + 1) / 2;
         Mesh cm;
-        make_unit_square_tri(nx, ny, p->mesh.lo, p->mesh.hi, cm);
+        if (quad) make_rectangle_quad(nx, ny, p->mesh.lo, p->mesh.hi, cm);
+        else make_unit_square_tri(nx, ny, p->mesh.lo, p->mesh.hi, cm);
         femo_problem *c = nullptr;
         int rc = create_problem_impl(cm, p->family, p->params, 8, true, nullptr, 0, &c);
         if (rc) return rc;
@@ -914,7 +920,10 @@ static int propagate_bc(femo_problem *root, int start) {
                 const int i = (int)std::llround((double)I * fnx / cnx);
                 int j = (int)std::llround((double)(J + cj0) * fg / cg) - fj0;     // nearest fine row, local index
                 j = std::min(std::max(j, 0), fny);                                 // ghost rows without a local parent: same column
-                if (!F->bc_mark.empty() && F->bc_mark[(int64_t)j * (fnx + 1) + i]) list.push_back(J * (cnx + 1) + I);
+                const int bs = F->state.block;
+                for (int cc = 0; cc < bs; ++cc)
+                    if (!F->bc_mark.empty() && F->bc_mark[((int64_t)j * (fnx + 1) + i) * bs + cc])
+                        list.push_back((J * (cnx + 1) + I) * bs + cc);
             }
         int32_t ptr[2] = {0, (int32_t)list.size()};
         int rc = set_bc_impl(C, list.data(), ptr, list.empty() ? 0 : 1, nullptr);
@@ -951,7 +960,7 @@ static void child_bytes(const femo_problem *c, bool coarsest, size_t *sb, size_t
     s += Arena::need(std::max<size_t>(1, c->fb_cell.size()), 4) * 2;
     s += pattern_bytes(c->pat[0], true);
     s += Arena::need(N, 1) + 2 * Arena::need(N, 8) + Arena::need(N, 4) + 1024;
-    w += Arena::need(c->pat[0].nnz, 8) + 9 * Arena::need(N, 8);
+    w += Arena::need(c->pat[0].nnz, 8) + 9 * Arena::need(N, 8) + Arena::need((size_t)c->mesh.ncells, 8);
     w += Arena::need(3 * kMaxPartials, 8) + Arena::need(S_COUNT, 8) + 1024;
     if (coarsest) w += 2 * Arena::need(N * N, 8);
     *sb = s;
@@ -1009,6 +1018,7 @@ static int upload_child(femo_problem *root, femo_problem *c, bool coarsest) {
     L.d = root->wk.take<double>(N);
     L.q = root->wk.take<double>(N);
     L.u = root->wk.take<double>(N);
+    L.m = root->wk.take<double>(std::max<int64_t>(1, c->mesh.ncells));
     L.fb = root->wk.take<double>(N);
     L.fx = root->wk.take<double>(N);
     c->d_partials = root->wk.take<double>(3 * kMaxPartials);

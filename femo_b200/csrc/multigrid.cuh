@@ -32,20 +32,29 @@ __device__ __forceinline__ double hat_p1(double dx, double dy) {
     return v > 0.0 ? v : 0.0;
 }
 
-// dst(node) (+)= sum_k phi^src_k(x_node) src(k): prolongation (src = coarse) and
-// state interpolation (src = fine) share this kernel.
+// bilinear Q1 hat on the tensor lattice
+__device__ __forceinline__ double hat_q1(double dx, double dy) {
+    const double a = 1.0 - fabs(dx), b = 1.0 - fabs(dy);
+    return (a > 0.0 && b > 0.0) ? a * b : 0.0;
+}
+__device__ __forceinline__ double hat_of(int kind, double dx, double dy) { return kind ? hat_q1(dx, dy) : hat_p1(dx, dy); }
+
+// dst(dof) (+)= sum_k phi^src_k(x_node) src(k): prolongation (src = coarse) and state interpolation
+// (src = fine) share this kernel.  `block` interleaved components per node, hat 0 = P1 right-diagonal, 1 = Q1.
 template <bool ADD>
 __global__ void __launch_bounds__(kThreads)
-    k_lattice_interp(Lattice s, Lattice d, const double *__restrict__ src, double *__restrict__ dst,
+    k_lattice_interp(Lattice s, Lattice d, int block, int hat, const double *__restrict__ src, double *__restrict__ dst,
                      const uint8_t *__restrict__ dst_mask) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t nd = (int64_t)(d.nx + 1) * (d.ny + 1);
+    const int64_t nd = (int64_t)(d.nx + 1) * (d.ny + 1) * block;
     if (idx >= nd) return;
     if (dst_mask && dst_mask[idx]) {
         if (!ADD) dst[idx] = 0.0;
         return;
     }
-    const int i = (int)(idx % (d.nx + 1)), j = (int)(idx / (d.nx + 1));
+    const int64_t node = idx / block;
+    const int comp = (int)(idx % block);
+    const int i = (int)(node % (d.nx + 1)), j = (int)(node / (d.nx + 1));
     const double X = (double)i * ((double)s.nx / (double)d.nx), Y = (double)j * ((double)s.ny / (double)d.ny);
     const int I = min((int)X, s.nx - 1), J = min((int)Y, s.ny - 1);
     double acc = 0.0;
@@ -53,8 +62,8 @@ __global__ void __launch_bounds__(kThreads)
     for (int b = 0; b < 2; ++b)
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-            const double w = hat_p1(X - (double)(I + a), Y - (double)(J + b));
-            if (w > 0.0) acc += w * src[(int64_t)(J + b) * (s.nx + 1) + (I + a)];
+            const double w = hat_of(hat, X - (double)(I + a), Y - (double)(J + b));
+            if (w > 0.0) acc += w * src[((int64_t)(J + b) * (s.nx + 1) + (I + a)) * block + comp];
         }
     if (ADD) dst[idx] += acc;
     else dst[idx] = acc;
@@ -62,16 +71,18 @@ __global__ void __launch_bounds__(kThreads)
 
 // rc = P^T rf with the same weights as k_lattice_interp<coarse -> fine>
 __global__ void __launch_bounds__(kThreads)
-    k_lattice_restrict(Lattice f, Lattice c, const double *__restrict__ rf, double *__restrict__ rc,
+    k_lattice_restrict(Lattice f, Lattice c, int block, int hat, const double *__restrict__ rf, double *__restrict__ rc,
                        const uint8_t *__restrict__ mask_f, const uint8_t *__restrict__ mask_c) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t nc = (int64_t)(c.nx + 1) * (c.ny + 1);
+    const int64_t nc = (int64_t)(c.nx + 1) * (c.ny + 1) * block;
     if (idx >= nc) return;
     if (mask_c && mask_c[idx]) {
         rc[idx] = 0.0;
         return;
     }
-    const int I = (int)(idx % (c.nx + 1)), J = (int)(idx / (c.nx + 1));
+    const int64_t node = idx / block;
+    const int comp = (int)(idx % block);
+    const int I = (int)(node % (c.nx + 1)), J = (int)(node / (c.nx + 1));
     const double sx = (double)c.nx / (double)f.nx, sy = (double)c.ny / (double)f.ny;
     const int ilo = max(0, (int)floor((double)(I - 1) / sx)), ihi = min(f.nx, (int)ceil((double)(I + 1) / sx));
     const int jlo = max(0, (int)floor((double)(J - 1) / sy)), jhi = min(f.ny, (int)ceil((double)(J + 1) / sy));
@@ -82,11 +93,30 @@ __global__ void __launch_bounds__(kThreads)
             const double X = (double)i * sx, Y = (double)j * sy;
             const int I0 = min((int)X, c.nx - 1), J0 = min((int)Y, c.ny - 1);
             if (I < I0 || I > I0 + 1 || J < J0 || J > J0 + 1) continue;
-            const double w = hat_p1(X - (double)I, Y - (double)J);
-            const int64_t fi = (int64_t)j * (f.nx + 1) + i;
+            const double w = hat_of(hat, X - (double)I, Y - (double)J);
+            const int64_t fi = ((int64_t)j * (f.nx + 1) + i) * block + comp;
             if (w > 0.0 && !(mask_f && mask_f[fi])) acc += w * rf[fi];
         }
     rc[idx] = acc;
+}
+
+// coarse cell-wise coefficient for the rediscretised SIMP operator: power mean of the fine densities whose
+// cell centres lie in the coarse cell, rho_c = (mean rho_f^p)^(1/p)  (quadrilateral lattices, one value per cell)
+__global__ void __launch_bounds__(kThreads)
+    k_restrict_cells_power(Lattice f, Lattice c, double p, const double *__restrict__ rf, double *__restrict__ rc) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)c.nx * c.ny) return;
+    const int I = (int)(idx % c.nx), J = (int)(idx / c.nx);
+    const int i0 = (int)ceil(((double)I * f.nx) / c.nx - 0.5), i1 = (int)ceil(((double)(I + 1) * f.nx) / c.nx - 0.5);
+    const int j0 = (int)ceil(((double)J * f.ny) / c.ny - 0.5), j1 = (int)ceil(((double)(J + 1) * f.ny) / c.ny - 0.5);
+    double acc = 0.0;
+    int cnt = 0;
+    for (int j = max(j0, 0); j < min(j1, f.ny); ++j)
+        for (int i = max(i0, 0); i < min(i1, f.nx); ++i) {
+            acc += pow(rf[(int64_t)j * f.nx + i], p);
+            ++cnt;
+        }
+    rc[idx] = cnt ? pow(acc / cnt, 1.0 / p) : 1.0;
 }
 
 // 2:1 nested lattices (the common case), integer-only, slab aware.  A local lattice holds node rows
@@ -359,6 +389,7 @@ static inline LatD latd_of(const femo_problem *p) {
 // global cell rows of a level (slab: of the partitioned lattice)
 static inline int global_rows(const femo_problem *p) { return p->slab.active ? p->slab.gny : p->mesh.n[1]; }
 static inline bool nested_pair(const femo_problem *F, const femo_problem *C) {
+    if (F->mesh.kind != MESH_TRI || F->state.block != 1) return false;   // integer-only kernels: scalar P1
     return F->mesh.n[0] == 2 * C->mesh.n[0] && global_rows(F) == 2 * global_rows(C);
 }
 
@@ -406,7 +437,7 @@ static int mg_restrict(femo_problem *L, femo_problem *C, double *rf, double *rc_
             if ((rc = gather_rows(L, rc_, (size_t)(C->mesh.n[0] + 1), C->mesh.n[1]))) return rc;
     } else {
         if (L->slab.active) return set_err(FEMO_ESTATE, "distributed multigrid levels must be 2:1 nested");
-        k_lattice_restrict<<<grid_for(nc), kThreads, 0, st>>>(Lattice{L->mesh.n[0], L->mesh.n[1]}, Lattice{C->mesh.n[0], C->mesh.n[1]}, rf, rc_, mf, mc);
+        k_lattice_restrict<<<grid_for(nc), kThreads, 0, st>>>(Lattice{L->mesh.n[0], L->mesh.n[1]}, Lattice{C->mesh.n[0], C->mesh.n[1]}, L->state.block, L->mesh.kind == MESH_QUAD, rf, rc_, mf, mc);
         L->launches++;
     }
     FEMO_CHECK_LAUNCH();
@@ -422,7 +453,7 @@ static int mg_prolong_add(femo_problem *L, femo_problem *C, double *xc, double *
         if ((rc = halo_nodes(C, xc))) return rc;                   // fine owned rows read the coarse ghost row above
         k_prolong_nested<<<grid_for(n), kThreads, 0, st>>>(latd_of(L), latd_of(C), xc, xf, mf);
     } else {
-        k_lattice_interp<true><<<grid_for(n), kThreads, 0, st>>>(Lattice{C->mesh.n[0], C->mesh.n[1]}, Lattice{L->mesh.n[0], L->mesh.n[1]}, xc, xf, mf);
+        k_lattice_interp<true><<<grid_for(n), kThreads, 0, st>>>(Lattice{C->mesh.n[0], C->mesh.n[1]}, Lattice{L->mesh.n[0], L->mesh.n[1]}, L->state.block, L->mesh.kind == MESH_QUAD, xc, xf, mf);
     }
     L->launches++;
     FEMO_CHECK_LAUNCH();
@@ -533,11 +564,20 @@ static int mg_setup(femo_problem *root, const double *vals) {
                 }
             } else {
                 if (F->slab.active) return set_err(FEMO_ESTATE, "distributed multigrid levels must be 2:1 nested");
-                k_lattice_interp<false><<<grid_for(n), kThreads, 0, st>>>(Lattice{F->mesh.n[0], F->mesh.n[1]}, Lattice{L->mesh.n[0], L->mesh.n[1]}, uf, M.u, nullptr);
+                k_lattice_interp<false><<<grid_for(n), kThreads, 0, st>>>(Lattice{F->mesh.n[0], F->mesh.n[1]}, Lattice{L->mesh.n[0], L->mesh.n[1]}, L->state.block, L->mesh.kind == MESH_QUAD, uf, M.u, nullptr);
                 L->launches++;
             }
             L->coef[0] = M.u;
             L->coefn[0] = n;
+            if (L->family == FEMO_FAMILY_SIMP_Q1) {   // coarse density for the rediscretised stiffness
+                const double *mf_ = (lv == 1) ? root->coef[1] : F->mgl.m;
+                if (!mf_) return set_err(FEMO_ESTATE, "multigrid setup: density coefficient not set");
+                const int64_t ncell = L->mesh.ncells;
+                k_restrict_cells_power<<<grid_for(ncell), kThreads, 0, st>>>(Lattice{F->mesh.n[0], F->mesh.n[1]}, Lattice{L->mesh.n[0], L->mesh.n[1]}, L->params[3], mf_, M.m);
+                L->launches++;
+                L->coef[1] = M.m;
+                L->coefn[1] = ncell;
+            }
             if ((rc = femo_assemble_jacobian(L, L->has_bc ? nullptr : M.vals, L->has_bc ? M.vals : nullptr))) return rc;
         }
         const DevPattern &D = L->dpat[0];

@@ -65,7 +65,7 @@ class FormFamily:
             p = _E.EngineProblem(self.mesh._e, self.family_id, self.params, self.tagged)
             # what replaces the reference's LU: GMG-preconditioned CG where a lattice hierarchy exists,
             # the explicit inverse for tiny systems, Jacobi-CG otherwise
-            if self.family_id in (_E.FAMILY_POISSON_P1, _E.FAMILY_NLPOISSON_P1):
+            if self.family_id in (_E.FAMILY_POISSON_P1, _E.FAMILY_NLPOISSON_P1, _E.FAMILY_SIMP_Q1):
                 p.enable_multigrid()
                 self.precond = 2 if p.mg_levels > 1 else (3 if p.N <= 512 else 0)
             else:

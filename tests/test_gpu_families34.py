@@ -127,3 +127,26 @@ def test_beam_thickness_optimisation_reaches_reference_optimum(cuda_device):
         0.07790323, 0.07496382, 0.07190453, 0.06870925, 0.0653583, 0.06182632, 0.05808044, 0.05407658, 0.04975295,
         0.0450185, 0.03972912, 0.03363155, 0.02620192, 0.01610863])
     assert np.abs(res.x - thick_ref).max() < 2e-4, np.abs(res.x - thick_ref).max()
+
+
+@pytest.mark.parametrize('nx,ny,rho_lo', [(64, 32, 0.3), (80, 40, 1e-3), (50, 21, 0.2)])
+def test_simp_multigrid_pcg(cuda_device, nx, ny, rho_lo):
+    """GMG-preconditioned CG for the vector Q1 elasticity operator (rediscretised coarse levels with
+    power-mean densities) against SuperLU, nested and non-nested level sizes, moderate and high contrast."""
+    import scipy.sparse.linalg as spla
+    from _cases34 import csr
+    c = SimpCase(nx, ny, seed=8, upload=False, rho_lo=rho_lo)
+    levels = c.p.enable_multigrid()
+    assert levels >= 3
+    from _cases34 import _upload
+    _upload(c)
+    _, vals_bc = c.p.assemble_jacobian(plain=False, bc=True)
+    A = csr(c, 0, vals_bc)
+    b = np.random.default_rng(1).standard_normal(c.F.N)
+    b[c.bc.dofs] = 0.0
+    x, info = c.p.linear_solve(vals_bc, c.p.to_device(b), rtol=1e-11, precond=2, max_it=500)
+    assert info['converged'], info
+    xo = spla.spsolve(A.tocsc(), b)
+    assert relerr(x.cpu().numpy(), xo) < 1e-7
+    xj, ij = c.p.linear_solve(vals_bc, c.p.to_device(b), rtol=1e-11, precond=0, max_it=200000, check_every=100)
+    assert info['iterations'] < ij['iterations'] / 4, (info, ij)
