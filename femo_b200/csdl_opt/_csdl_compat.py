@@ -200,6 +200,14 @@ class Simulator:
                             bar[a] -= d_in[a]
                         else:
                             bar[a] = np.negative(d_in[a])
+                elif hasattr(op, 'vjp'):
+                    # vector-valued explicit operation with a constant Jacobian (declared sparse in CSDL)
+                    for a in args:
+                        g = op.vjp(out, a, np.asarray(bar[out]))
+                        if a in bar:
+                            bar[a] += g
+                        else:
+                            bar[a] = np.array(g)
                 else:
                     derivs = {}
                     op.compute_derivatives(inputs, derivs)

@@ -232,6 +232,47 @@ __global__ void __launch_bounds__(kThreads)
         out[i] = a * num[i] / den[i];
 }
 
+// Cone density filter on the lattice of cell centres (examples/beam_topo_opt/pre_processor/
+// general_filter_model.py:67-90): W_ij = (R - d_ij) / sum_k (R - d_ik) over centres with d <= R.
+// The neighbour search is index arithmetic on the lattice; den_i = sum_k (R - d_ik) is geometry only.
+__global__ void __launch_bounds__(kThreads)
+    k_filter_den(int nx, int ny, double dx, double dy, double R, double *__restrict__ den) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)nx * ny) return;
+    const int i = (int)(idx % nx), j = (int)(idx / nx);
+    const int kx = (int)floor(R / dx), ky = (int)floor(R / dy);
+    double s = 0.0;
+    for (int b = max(j - ky, 0); b <= min(j + ky, ny - 1); ++b)
+        for (int a = max(i - kx, 0); a <= min(i + kx, nx - 1); ++a) {
+            const double ex = (a - i) * dx, ey = (b - j) * dy;
+            const double d = sqrt(ex * ex + ey * ey);
+            if (d <= R) s += R - d;
+        }
+    den[idx] = s;
+}
+
+// out = W in (TRANSPOSE = false) or out = W^T in (true: weights normalised by the NEIGHBOUR's den)
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(kThreads)
+    k_filter_apply(int nx, int ny, double dx, double dy, double R, const double *__restrict__ den,
+                   const double *__restrict__ in, double *__restrict__ out) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)nx * ny) return;
+    const int i = (int)(idx % nx), j = (int)(idx / nx);
+    const int kx = (int)floor(R / dx), ky = (int)floor(R / dy);
+    double s = 0.0;
+    for (int b = max(j - ky, 0); b <= min(j + ky, ny - 1); ++b)
+        for (int a = max(i - kx, 0); a <= min(i + kx, nx - 1); ++a) {
+            const double ex = (a - i) * dx, ey = (b - j) * dy;
+            const double d = sqrt(ex * ex + ey * ey);
+            if (d <= R) {
+                const int64_t k = (int64_t)b * nx + a;
+                s += TRANSPOSE ? (R - d) * in[k] / den[k] : (R - d) * in[k];
+            }
+        }
+    out[idx] = TRANSPOSE ? s : s / den[idx];
+}
+
 __global__ void __launch_bounds__(kThreads) k_fill(double a, double *__restrict__ y, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         y[i] = a;
@@ -1409,6 +1450,22 @@ int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_
     p->launches++;
     FEMO_CHECK_LAUNCH();
     return launch_spmv<false>(p, D.t_rb, D.t_nrb, D.t_rowptr, D.t_col, p->d_tvals, d_x, d_y, nullptr, nullptr, false);
+}
+
+int femo_filter_apply(int device, void *stream, int nx, int ny, double dx, double dy, double radius,
+                      const double *d_in, double *d_out, double *d_den, int transpose) {
+    if (nx < 1 || ny < 1 || !(dx > 0) || !(dy > 0) || !(radius > 0) || !d_in || !d_out || !d_den)
+        return set_err(FEMO_EINVAL, "femo_filter_apply: bad arguments");
+    if (femo_device_count() <= device || device < 0)
+        return set_err(FEMO_ENODEVICE, "femo_filter_apply: no such CUDA device; this engine has no CPU path");
+    FEMO_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)nx * ny;
+    k_filter_den<<<grid_for(n), kThreads, 0, st>>>(nx, ny, dx, dy, radius, d_den);
+    if (transpose) k_filter_apply<true><<<grid_for(n), kThreads, 0, st>>>(nx, ny, dx, dy, radius, d_den, d_in, d_out);
+    else k_filter_apply<false><<<grid_for(n), kThreads, 0, st>>>(nx, ny, dx, dy, radius, d_den, d_in, d_out);
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
 }
 
 int femo_pointwise_divide(femo_problem *p, double a, const double *d_num, const double *d_den, double *d_out, int64_t n) {

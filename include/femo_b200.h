@@ -173,6 +173,11 @@ int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_
  * compute_jacvec_product, state_model.py:180-199, kept on the device). */
 int femo_axpy(femo_problem *p, double a, const double *d_x, double *d_y, int64_t n);
 
+/* Cone density filter of examples/beam_topo_opt/pre_processor/general_filter_model.py:33-90 on the lattice of
+ * cell centres (nx x ny cells of size dx x dy, cell id = j*nx + i): out = W in, W_ij = (R-d_ij)/sum_k(R-d_ik)
+ * for d <= R, or out = W^T in (the constant Jacobian's transpose action).  d_den: nx*ny doubles of scratch. */
+int femo_filter_apply(int device, void *stream, int nx, int ny, double dx, double dy, double radius,
+                      const double *d_in, double *d_out, double *d_den, int transpose);
 /* out = a * num / den (Vec.pointwiseDivide of the lumped projection, utils_dolfinx.py:566-569) */
 int femo_pointwise_divide(femo_problem *p, double a, const double *d_num, const double *d_den, double *d_out, int64_t n);
 

@@ -153,3 +153,52 @@ def test_project_matches_oracle(cuda_device):
     gl = Function(FunctionSpace(mesh, ('CG', 1)))
     project(u_ex_ufl, gl, lump_mass=True)
     assert relerr(getFuncArray(gl), getFuncArray(u_ex)) < 0.2
+
+
+def test_topology_example_with_density_filter(cuda_device):
+    """examples/beam_topo_opt with its GeneralFilterModel pre-processor: filtered density vs the oracle's
+    KD-tree weights, forward solve vs oracle, adjoint totals through filter + state vs finite differences."""
+    from femo_b200.fea.fea_b200 import (FEA, createRectangleMesh, FunctionSpace, VectorFunctionSpace, Function,
+                                         TestFunction, Constant, locate_dofs_geometrical, locate_entities_boundary,
+                                         meshtags, Measure, meshSize, DOLFIN_EPS)
+    from femo_b200.forms.topo import pdeRes, averageFunc, compliance
+    from femo_b200.csdl_opt import FEAModel, Simulator
+    from femo_b200.csdl_opt.pre_processor.general_filter_model import GeneralFilterModel
+    from oracle.filter import weight_matrix
+    nx, ny, LX, LY = 24, 12, 160., 80.
+    mesh = createRectangleMesh(np.array([0.0, 0.0]), np.array([LX, LY]), nx, ny)
+    tb = locate_entities_boundary(mesh, 1, lambda x: np.logical_and(abs(x[1] - LY / 2) < LY / ny + DOLFIN_EPS * 1e10,
+                                                                     abs(x[0] - LX) < DOLFIN_EPS * 1e10))
+    ds_ = Measure('ds', domain=mesh, subdomain_data=meshtags(mesh, 1, tb, np.full(len(tb), 100, dtype=np.int32)),
+                  metadata={"quadrature_degree": 4})
+    fea = FEA(mesh)
+    Vr = FunctionSpace(mesh, ('DG', 0))
+    rho = Function(Vr)
+    Vu = VectorFunctionSpace(mesh, ('CG', 1))
+    u = Function(Vu)
+    f = Constant(mesh, (0, -1 / 4))
+    res = pdeRes(u, TestFunction(Vu), rho, f, dss=ds_(100), method='SIMP')
+    fea.add_input('density', rho)
+    fea.add_state(name='displacements', function=u, residual_form=res, arguments=['density'])
+    fea.add_output(name='avg_density', type='scalar', form=averageFunc(rho), arguments=['density'])
+    fea.add_output(name='compliance', type='scalar', form=compliance(u, f, dss=ds_(100)), arguments=['displacements'])
+    fea.add_strong_bc(Function(Vu), [locate_dofs_geometrical((Vu, Vu), lambda x: np.isclose(x[0], 0., atol=1e-6))], Vu)
+    fea.REPORT = False
+    model = FEAModel(fea=[fea], debug_mode=False)
+    coords = Vr.tabulate_dof_coordinates()
+    h = meshSize(mesh)
+    h_avg = (h.max() + h.min()) / 2
+    nel = mesh.num_cells
+    model.add(GeneralFilterModel(nel=nel, coordinates=coords, h_avg=h_avg), name='general_filter_model')
+    np.random.seed(0)
+    x0 = 0.3 + 0.6 * np.random.random(nel)
+    model.create_input('density_unfiltered', shape=nel, val=x0)
+    sim = Simulator(model)
+    sim.run()
+    W = weight_matrix(coords[:, :2], h_avg)
+    assert relerr(sim['density'], W @ x0) < 1e-13
+    assert abs(sim['avg_density'][0] - (W @ x0).mean()) < 1e-12
+    rep = sim.check_totals('compliance', 'density_unfiltered', step=1e-5, compact_print=False)
+    assert max(rep.values()) < 1e-5, rep
+    rep = sim.check_totals('avg_density', 'density_unfiltered', step=1e-3, compact_print=False)
+    assert max(rep.values()) < 1e-8, rep
