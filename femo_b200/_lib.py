@@ -56,6 +56,9 @@ SIGNATURES = {
     'femo_mesh_destroy': (None, [_P]),
     'femo_problem_create': (C.c_int, [_P, C.c_int, _DP, C.c_int, C.POINTER(_P)]),
     'femo_problem_create_tagged': (C.c_int, [_P, C.c_int, _DP, C.c_int, _P, C.c_int, C.POINTER(_P)]),
+    'femo_problem_create_ex': (C.c_int, [_P, C.c_int, _DP, C.c_int, _P, _P, C.c_int, _P, C.POINTER(_P)]),
+    'femo_problem_set_param': (C.c_int, [_P, C.c_int, C.c_double]),
+    'femo_mesh_create_annulus': (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(_P)]),
     'femo_problem_destroy': (None, [_P]),
     'femo_problem_sizes': (C.c_int, [_P, _I64P]),
     'femo_problem_pattern_info': (C.c_int, [_P, C.c_int, _I64P]),

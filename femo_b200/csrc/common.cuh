@@ -29,7 +29,7 @@ constexpr int kMaxPartials = 4096;   // upper bound on CTAs of any reducing kern
 constexpr int kMaxSlots = 12;
 
 // device scalar slots (doubles) used by the Krylov / Newton drivers
-enum Scalar { S_ALPHA = 0, S_BETA, S_RZ, S_RR, S_PQ, S_TMP0, S_TMP1, S_TMP2, S_BB, S_COUNT = 16 };
+enum Scalar { S_ALPHA = 0, S_BETA, S_RZ, S_RR, S_PQ, S_TMP0, S_TMP1, S_TMP2, S_BB, S_GM = 16, S_COUNT = 96 };
 
 // ---- reductions (deterministic: fixed assignment, fixed tree) ---------------
 __device__ __forceinline__ double warp_sum(double v) {
@@ -112,11 +112,11 @@ struct femo_mg_level {
 struct femo_problem {
     femo::Mesh mesh;
     int family = 0;
-    double params[8] = {0};
+    double params[32] = {0};
     femo::Space state, in[4], aux[4];
     int nin = 0, naux = 0, nout = 0;
     // integral blocks by mask: 1 = all cells, 2 = facets carrying facet integrals, 3 = both
-    int res_mask = 1, jac_mask = 1;
+    int res_mask = 1, jac_mask = 1, drdm_mask = 1;
     int out_mask[4] = {1, 1, 1, 1};        // blocks of output k's functional
     int out_du_mask[4] = {1, 1, 1, 1};     // blocks of d(output k)/d(state); 0 = identically zero
     int out_dm_mask[4] = {1, 1, 1, 1};     // same wrt input 0
@@ -137,7 +137,7 @@ struct femo_problem {
     int num_sms = 148;
     femo::Arena st, wk;
     double *d_coords = nullptr;
-    int32_t *d_cellsT = nullptr, *d_fb_cell = nullptr, *d_fb_local = nullptr;
+    int32_t *d_cellsT = nullptr, *d_fb_cell = nullptr, *d_fb_local = nullptr, *d_cell_tag = nullptr;
     femo::DevPattern dpat[5];
     femo::DevVecMap dvm_state[4], dvm_in[4];
     uint8_t *d_bc_mark = nullptr;
@@ -165,6 +165,9 @@ struct femo_problem {
     femo_problem *parent = nullptr;
     double *kr_d = nullptr;
     double *d_dense = nullptr, *d_dense_tmp = nullptr;   // explicit inverse for small systems (precond 3)
+    double *gm_basis = nullptr;                          // GMRES Krylov basis, (restart+1) vectors
+    double *d_partials_big = nullptr, *wk_extra = nullptr; // multi-dot partials; spare N-vector
+    int gm_restart = 0;
     // counters (bench: how many of our kernels were launched)
     long long launches = 0;
 };

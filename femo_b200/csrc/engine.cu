@@ -9,6 +9,7 @@
 #include "families.cuh"
 #include "families2.cuh"
 #include "families3.cuh"
+#include "families4.cuh"
 #include "dist.cuh"
 
 namespace femo {
@@ -366,7 +367,8 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
     int rc;
     if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
     const bool analytic_src = p->family == FEMO_FAMILY_MASS_P1 && p->params[1] < 1.5;
-    const bool jac_reads_input = p->family == FEMO_FAMILY_SIMP_Q1 || p->family == FEMO_FAMILY_EB_BEAM;
+    const bool jac_reads_input = p->family == FEMO_FAMILY_SIMP_Q1 || p->family == FEMO_FAMILY_EB_BEAM ||
+                                 p->family == FEMO_FAMILY_MOTOR_EM;
     if ((op != OP_JAC || jac_reads_input) && !analytic_src && (rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
     double *cells_out = p->d_scratch;
     double *facets_out = p->d_scratch + ((mask & 1) ? nc * op_planes(p, op) : 0);
@@ -398,6 +400,35 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
                 TriArgs F = tri_args(p, facets_out);
                 if (op == OP_RES) k_nlpoisson_p1_facet<OP_RES><<<gf, kThreads, 0, st>>>(F);
                 else k_nlpoisson_p1_facet<OP_JAC><<<gf, kThreads, 0, st>>>(F);
+                p->launches++;
+            }
+            break;
+        }
+        case FEMO_FAMILY_MOTOR_EM: {
+            EmArgs A;
+            A.coords = p->d_coords; A.cellsT = p->d_cellsT; A.ncells = nc;
+            A.fb_cell = p->d_fb_cell; A.fb_local = p->d_fb_local; A.nfacets = nf;
+            A.tag = p->d_cell_tag; A.u = p->coef[0]; A.uh = p->coef[1];
+            for (int k = 0; k < EM_NPARAM; ++k) A.prm[k] = p->params[k];
+            A.out_id = out_id;
+            const int g1 = (int)((nc + 127) / 128), g2 = (int)((std::max<int64_t>(nf, 1) + 127) / 128);
+            if (mask & 1) {
+                A.out = cells_out;
+                switch (op) {
+                    case OP_RES: k_motor_em<OP_RES, 0><<<g1, 128, 0, st>>>(A); break;
+                    case OP_JAC: k_motor_em<OP_JAC, 0><<<g1, 128, 0, st>>>(A); break;
+                    case OP_DRDM: k_motor_em<OP_DRDM, 0><<<g1, 128, 0, st>>>(A); break;
+                    case OP_OUT: k_motor_em<OP_OUT, 0><<<g1, 128, 0, st>>>(A); break;
+                    case OP_OUT_DU: k_motor_em<OP_OUT_DU, 0><<<g1, 128, 0, st>>>(A); break;
+                    case OP_OUT_DM: k_motor_em<OP_OUT_DM, 0><<<g1, 128, 0, st>>>(A); break;
+                }
+                p->launches++;
+            }
+            if ((mask & 2) && nf > 0) {
+                A.out = facets_out;
+                if (op == OP_RES) k_motor_em<OP_RES, 1><<<g2, 128, 0, st>>>(A);
+                else if (op == OP_JAC) k_motor_em<OP_JAC, 1><<<g2, 128, 0, st>>>(A);
+                else k_motor_em<OP_DRDM, 1><<<g2, 128, 0, st>>>(A);
                 p->launches++;
             }
             break;
@@ -547,6 +578,7 @@ static int set_bc_impl(femo_problem *p, const int32_t *dofs, const int32_t *list
 
 #include "multigrid.cuh"
 #include "krylov.cuh"
+#include "gmres.cuh"
 
 // ===========================================================================
 // C ABI
@@ -581,6 +613,14 @@ int femo_mesh_create_rectangle_quad(int nx, int ny, const double lo[2], const do
     *out = m;
     return FEMO_OK;
 }
+int femo_mesh_create_annulus(int nr, int nth, double r0, double r1, femo_mesh **out) {
+    if (!out || nr < 1 || nth < 3 || !(r1 > r0) || !(r0 > 0)) return set_err(FEMO_EINVAL, "femo_mesh_create_annulus: bad arguments");
+    femo_mesh *m = new femo_mesh();
+    make_annulus_tri(nr, nth, r0, r1, m->m);
+    *out = m;
+    return FEMO_OK;
+}
+
 int femo_mesh_create_interval(int n, double x0, double x1, femo_mesh **out) {
     if (!out || n < 1) return set_err(FEMO_EINVAL, "femo_mesh_create_interval: bad arguments");
     femo_mesh *m = new femo_mesh();
@@ -610,11 +650,14 @@ void femo_mesh_destroy(femo_mesh *m) { delete m; }
 
 // ---- problem layout -------------------------------------------------------
 static int create_problem_impl(const Mesh &mesh, int family, const double *params, int nparams, bool jac_only,
-                               const int32_t *tagged, int ntagged, femo_problem **out) {
+                               const int32_t *tagged, int ntagged, femo_problem **out,
+                               const int32_t *fcell = nullptr, const int32_t *flocal = nullptr, int nfl = 0,
+                               const int32_t *cell_tags = nullptr) {
     femo_problem *p = new femo_problem();
     p->mesh = mesh;
     p->family = family;
     p->jac_only = jac_only;
+    if (cell_tags) p->mesh.cell_tag.assign(cell_tags, cell_tags + mesh.ncells);
     for (int i = 0; i < nparams; ++i) p->params[i] = params[i];
     const Mesh &M = p->mesh;
     try {
@@ -636,6 +679,17 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
                     if (nparams < 1) p->params[0] = 6e-7;
                     if (nparams < 2) p->params[1] = 10.0;
                 }
+                break;
+            case FEMO_FAMILY_MOTOR_EM:
+                if (M.kind != MESH_TRI) throw LayoutError{FEMO_EINVAL, "family needs a triangle mesh"};
+                if (M.cell_tag.empty()) throw LayoutError{FEMO_EINVAL, "motor family needs cell tags (subdomain ids)"};
+                if (nparams < EM_NPARAM) throw LayoutError{FEMO_EINVAL, "motor family needs its full parameter vector"};
+                p->state.init(M, EL_VERTEX, 1);
+                p->nin = 1;
+                p->in[0].init(M, EL_VERTEX, 2);                 // mesh displacement uhat
+                p->nout = 2;
+                p->res_mask = p->jac_mask = p->drdm_mask = 3;   // cells + exterior facets (Nitsche, Nanson normal)
+                p->symmetric = false;                            // nonlinear Nitsche coefficient
                 break;
             case FEMO_FAMILY_MASS_P1: {
                 if (M.kind != MESH_TRI) throw LayoutError{FEMO_EINVAL, "family needs a triangle mesh"};
@@ -672,7 +726,14 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
                 throw LayoutError{FEMO_EINVAL, "unknown form family"};
         }
         // block 2: all exterior facets (Nitsche) or the tagged subset (ds(tag) of the examples)
-        if (family == FEMO_FAMILY_NLPOISSON_P1) {
+        if (fcell && flocal) {                       // explicit one-sided facets (cell, local facet)
+            for (int k = 0; k < nfl; ++k) {
+                if (fcell[k] < 0 || fcell[k] >= M.ncells || flocal[k] < 0 || flocal[k] >= M.nvpc)
+                    throw LayoutError{FEMO_EINVAL, "facet (cell, local) out of range"};
+                p->fb_cell.push_back(fcell[k]);
+                p->fb_local.push_back(flocal[k]);
+            }
+        } else if (family == FEMO_FAMILY_NLPOISSON_P1 || family == FEMO_FAMILY_MOTOR_EM) {
             p->fb_cell = M.bf_cell;
             p->fb_local = M.bf_local;
         } else {
@@ -696,7 +757,7 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
         p->blk[3] = {cells, facets};
         build_pattern(M, p->state, p->state, p->blk[p->jac_mask], p->pat[0]);
         if (!jac_only) {  // coarse multigrid levels only ever assemble dR/du
-            for (int s = 0; s < p->nin; ++s) build_pattern(M, p->state, p->in[s], p->blk[1], p->pat[1 + s]);
+            for (int s = 0; s < p->nin; ++s) build_pattern(M, p->state, p->in[s], p->blk[p->drdm_mask], p->pat[1 + s]);
             bool need[4] = {false, false, false, false};
             need[p->res_mask] = true;
             for (int k = 0; k < p->nout; ++k) need[p->out_du_mask[k]] = true;
@@ -717,14 +778,28 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
 
 int femo_problem_create(const femo_mesh *m, int family, const double *params, int nparams, femo_problem **out) {
     if (!m || !out) return set_err(FEMO_EINVAL, "femo_problem_create: null");
-    if (nparams < 0 || nparams > 8) return set_err(FEMO_EINVAL, "femo_problem_create: nparams out of range");
+    if (nparams < 0 || nparams > 32) return set_err(FEMO_EINVAL, "femo_problem_create: nparams out of range");
     return create_problem_impl(m->m, family, params, nparams, false, nullptr, 0, out);
+}
+
+int femo_problem_create_ex(const femo_mesh *m, int family, const double *params, int nparams, const int32_t *facet_cell,
+                           const int32_t *facet_local, int nfacets, const int32_t *cell_tags, femo_problem **out) {
+    if (!m || !out || nfacets < 0) return set_err(FEMO_EINVAL, "femo_problem_create_ex: bad arguments");
+    if (nparams < 0 || nparams > 32) return set_err(FEMO_EINVAL, "femo_problem_create_ex: nparams out of range");
+    return create_problem_impl(m->m, family, params, nparams, false, nullptr, 0, out, facet_cell, facet_local, nfacets, cell_tags);
+}
+
+int femo_problem_set_param(femo_problem *p, int index, double value) {
+    if (!p || index < 0 || index >= 32) return set_err(FEMO_EINVAL, "femo_problem_set_param: bad index");
+    p->params[index] = value;
+    for (femo_problem *c : p->mg) c->params[index] = value;
+    return FEMO_OK;
 }
 
 int femo_problem_create_tagged(const femo_mesh *m, int family, const double *params, int nparams,
                                const int32_t *facet_ids, int nfacets, femo_problem **out) {
     if (!m || !out || nfacets < 0 || (nfacets > 0 && !facet_ids)) return set_err(FEMO_EINVAL, "femo_problem_create_tagged: bad arguments");
-    if (nparams < 0 || nparams > 8) return set_err(FEMO_EINVAL, "femo_problem_create_tagged: nparams out of range");
+    if (nparams < 0 || nparams > 32) return set_err(FEMO_EINVAL, "femo_problem_create_tagged: nparams out of range");
     return create_problem_impl(m->m, family, params, nparams, false, facet_ids, nfacets, out);
 }
 
@@ -805,7 +880,7 @@ static int enable_multigrid_slab(femo_problem *p) {
     while (rows % 2 == 0 && nx % 2 == 0 && rows / 2 >= kDistMinRows && nx / 2 >= 2) {
         nx /= 2; gny /= 2; rows /= 2;
         femo_problem *c = nullptr;
-        if ((rc = create_slab_problem(p->family, p->params, 8, nx, gny, p->mesh.lo, p->mesh.hi, rank, R, true, &c))) return rc;
+        if ((rc = create_slab_problem(p->family, p->params, 32, nx, gny, p->mesh.lo, p->mesh.hi, rank, R, true, &c))) return rc;
         c->parent = p;
         p->mg.push_back(c);
     }
@@ -823,7 +898,7 @@ static int enable_multigrid_slab(femo_problem *p) {
         Mesh cm;
         make_unit_square_tri(nx, gny, p->mesh.lo, p->mesh.hi, cm);
         femo_problem *c = nullptr;
-        if ((rc = create_problem_impl(cm, p->family, p->params, 8, true, nullptr, 0, &c))) return rc;
+        if ((rc = create_problem_impl(cm, p->family, p->params, 32, true, nullptr, 0, &c))) return rc;
         c->parent = p;
         c->replicated = true;
         p->mg.push_back(c);
@@ -835,6 +910,7 @@ static int enable_multigrid_slab(femo_problem *p) {
 int femo_problem_enable_multigrid(femo_problem *p) {
     if (!p) return set_err(FEMO_EINVAL, "femo_problem_enable_multigrid: null");
     if (p->uploaded) return set_err(FEMO_ESTATE, "femo_problem_enable_multigrid must precede femo_problem_upload");
+    if (!p->mesh.lattice) return set_err(FEMO_EINVAL, "multigrid needs a lattice mesh");
     const bool tri = p->mesh.kind == MESH_TRI && p->state.element == EL_VERTEX && p->state.block == 1;
     const bool quad = p->mesh.kind == MESH_QUAD && p->state.element == EL_VERTEX;
     if (!tri && !quad)
@@ -851,7 +927,7 @@ int femo_problem_enable_multigrid(femo_problem *p) {
         if (quad) make_rectangle_quad(nx, ny, p->mesh.lo, p->mesh.hi, cm);
         else make_unit_square_tri(nx, ny, p->mesh.lo, p->mesh.hi, cm);
         femo_problem *c = nullptr;
-        int rc = create_problem_impl(cm, p->family, p->params, 8, true, nullptr, 0, &c);
+        int rc = create_problem_impl(cm, p->family, p->params, 32, true, nullptr, 0, &c);
         if (rc) return rc;
         c->parent = p;
         p->mg.push_back(c);
@@ -993,6 +1069,8 @@ static size_t pattern_bytes(const Pattern &P, bool bc) {
 }
 static size_t vecmap_bytes(const VecMap &V) { return Arena::need(V.ptr.size(), 4) + Arena::need(V.src.size(), 4); }
 
+constexpr int kGmresRestart = 40;
+
 static void child_bytes(const femo_problem *c, bool coarsest, size_t *sb, size_t *wb) {
     const Mesh &M = c->mesh;
     const size_t N = (size_t)c->state.ndofs;
@@ -1072,7 +1150,7 @@ static int upload_child(femo_problem *root, femo_problem *c, bool coarsest) {
     if (!c->d_scalars) return set_err(FEMO_EINVAL, "work arena too small (multigrid level)");
     c->d_scratch = root->d_scratch;   // element tensors of coarse levels reuse the fine level's scratch
     c->scratch_len = root->scratch_len;
-    if (!c->h_pinned) FEMO_CUDA(cudaMallocHost((void **)&c->h_pinned, sizeof(double) * 64));
+    if (!c->h_pinned) FEMO_CUDA(cudaMallocHost((void **)&c->h_pinned, sizeof(double) * 128));
     if ((rc = push_bc(c))) return rc;
     c->uploaded = true;
     return FEMO_OK;
@@ -1084,7 +1162,7 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     const int64_t N = p->state.ndofs;
     size_t s = 0;
     s += Arena::need(M.coords.size(), 8) + Arena::need(M.cells.size(), 4);
-    s += 2 * Arena::need(std::max<size_t>(1, p->fb_cell.size()), 4);
+    s += 2 * Arena::need(std::max<size_t>(1, p->fb_cell.size()), 4) + Arena::need(std::max<size_t>(1, M.cell_tag.size()), 4);
     for (int w = 0; w <= p->nin; ++w) s += pattern_bytes(p->pat[w], w == 0);
     for (int m = 1; m < 4; ++m) s += vecmap_bytes(p->vm_state[m]);
     for (int i = 0; i < p->nin; ++i) s += vecmap_bytes(p->vm_in[i]);
@@ -1106,6 +1184,7 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     w += Arena::need(tv, 8);                       // transposed values
     w += Arena::need(N, 8);                        // Chebyshev direction of multigrid level 0
     if (N <= kMgDenseMax) w += 2 * Arena::need((size_t)N * N, 8);   // explicit inverse (precond 3)
+    if (!p->symmetric) w += (size_t)(kGmresRestart + 2) * Arena::need(N, 8) + Arena::need((size_t)(kGmresRestart + 1) * kMaxPartials, 8);
     w += 4096;
     for (size_t l = 0; l < p->mg.size(); ++l) {     // coarse multigrid levels live in the same arenas
         size_t cs, cw;
@@ -1147,6 +1226,7 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     }
     if ((rc = up(p, p->d_fb_cell, p->fb_cell))) return rc;
     if ((rc = up(p, p->d_fb_local, p->fb_local))) return rc;
+    if ((rc = up(p, p->d_cell_tag, M.cell_tag))) return rc;
     for (int w = 0; w <= p->nin; ++w) {
         const Pattern &P = p->pat[w];
         DevPattern &D = p->dpat[w];
@@ -1249,6 +1329,13 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     p->nt_vals_bc = p->wk.take<double>(p->pat[0].nnz);
     p->d_tvals = p->wk.take<double>(tv);
     p->kr_d = p->wk.take<double>(N);
+    if (!p->symmetric) {
+        p->gm_restart = kGmresRestart;
+        p->gm_basis = p->wk.take<double>((size_t)(kGmresRestart + 1) * N);
+        p->wk_extra = p->wk.take<double>(N);
+        p->d_partials_big = p->wk.take<double>((size_t)(kGmresRestart + 1) * kMaxPartials);
+        if (!p->d_partials_big) return set_err(FEMO_EINVAL, "work arena too small (GMRES)");
+    }
     if (N <= kMgDenseMax) {
         p->d_dense = p->wk.take<double>((size_t)N * N);
         p->d_dense_tmp = p->wk.take<double>((size_t)N * N);
@@ -1257,7 +1344,7 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     for (size_t l = 0; l < p->mg.size(); ++l)
         if ((rc = upload_child(p, p->mg[l], l + 1 == p->mg.size()))) return rc;
     FEMO_CUDA(cudaMemsetAsync(p->d_scalars, 0, sizeof(double) * S_COUNT, p->stream));
-    if (!p->h_pinned) FEMO_CUDA(cudaMallocHost((void **)&p->h_pinned, sizeof(double) * 64));
+    if (!p->h_pinned) FEMO_CUDA(cudaMallocHost((void **)&p->h_pinned, sizeof(double) * 128));
     FEMO_CUDA(cudaStreamSynchronize(p->stream));
     p->uploaded = true;
     return FEMO_OK;
@@ -1357,7 +1444,7 @@ int femo_assemble_dRdm(femo_problem *p, int slot, double *d_vals) {
     int rc;
     if ((rc = need_device(p))) return rc;
     if (slot < 0 || slot >= p->nin || !d_vals) return set_err(FEMO_EINVAL, "femo_assemble_dRdm: bad slot/output");
-    if ((rc = run_elements(p, OP_DRDM, 1))) return rc;
+    if ((rc = run_elements(p, OP_DRDM, p->drdm_mask))) return rc;
     const DevPattern &D = p->dpat[1 + slot];
     const int64_t nnz = p->pat[1 + slot].nnz;
     k_segreduce<<<grid_for(nnz), kThreads, 0, p->stream>>>(D.gptr, D.gsrc, p->d_scratch, d_vals, nnz);
@@ -1496,7 +1583,6 @@ int femo_linear_solve(femo_problem *p, const double *d_vals, const double *d_b, 
     femo_krylov_opts o;
     memset(&o, 0, sizeof(o));
     if (opts) o = *opts;
-    if (o.method != 0) return set_err(FEMO_EINVAL, "femo_linear_solve: only CG (method 0) is available in this build");
     const double *vals = d_vals;
     if (transpose) {
         const int64_t nnz = p->pat[0].nnz;
@@ -1505,7 +1591,7 @@ int femo_linear_solve(femo_problem *p, const double *d_vals, const double *d_b, 
         FEMO_CHECK_LAUNCH();
         vals = p->d_tvals;
     }
-    return cg_solve(p, vals, d_b, d_x, o, info);
+    return o.method == 1 ? gmres_solve(p, vals, d_b, d_x, o, info) : cg_solve(p, vals, d_b, d_x, o, info);
 }
 
 int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton_info *info) {
@@ -1547,7 +1633,7 @@ int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton
         // change the SNES convergence decision, so the Krylov solve may stop there
         femo_krylov_opts ko = opts->krylov;
         if (snes) ko.atol = std::max(ko.atol, 0.1 * opts->atol);
-        if ((rc = cg_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki))) return rc;
+        if ((rc = (ko.method == 1 ? gmres_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki) : cg_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki)))) return rc;
         kit += ki.iterations;
         spmvs += ki.spmv_count;
         k_axpy<<<red_grid(p, n), kThreads, 0, st>>>(-1.0, p->nt_dx, x, n);

@@ -88,6 +88,42 @@ void make_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2],
         }
 }
 
+void make_annulus_tri(int nr, int nth, double r0, double r1, Mesh &m) {
+    m = Mesh();
+    m.kind = MESH_TRI;
+    m.nvpc = 3;
+    m.gdim = 2;
+    m.lattice = false;
+    m.n[0] = nr;
+    m.n[1] = nth;
+    m.lo[0] = r0; m.hi[0] = r1;
+    m.lo[1] = 0.0; m.hi[1] = 2.0 * 3.141592653589793;
+    m.nverts = (int64_t)(nr + 1) * nth;
+    m.ncells = 2LL * nr * nth;
+    m.coords.resize(m.nverts * 2);
+    const double pi = 3.141592653589793;
+    for (int ir = 0; ir <= nr; ++ir)
+        for (int it = 0; it < nth; ++it) {
+            const double r = r0 + (r1 - r0) * (double)ir / (double)nr;
+            const double th = 2.0 * pi * (double)it / (double)nth;
+            const int64_t v = (int64_t)ir * nth + it;
+            m.coords[2 * v] = r * std::cos(th);
+            m.coords[2 * v + 1] = r * std::sin(th);
+        }
+    m.cells.resize(m.ncells * 3);
+    for (int ir = 0; ir < nr; ++ir)
+        for (int it = 0; it < nth; ++it) {
+            const int tp = (it + 1) % nth;
+            const int32_t v0 = ir * nth + it, v1 = (ir + 1) * nth + it, v2 = ir * nth + tp, v3 = (ir + 1) * nth + tp;
+            const int64_t c = 2LL * ((int64_t)ir * nth + it);
+            int32_t *a = &m.cells[c * 3];
+            a[0] = v0; a[1] = v1; a[2] = v3;
+            a[3] = v0; a[4] = v2; a[5] = v3;
+            if (ir == nr - 1) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(0); }      // outer circle: v1-v3
+            if (ir == 0)      { m.bf_cell.push_back((int32_t)c + 1); m.bf_local.push_back(2); }  // inner circle: v0-v2
+        }
+}
+
 void make_interval(int n, double x0, double x1, Mesh &m) {
     m = Mesh();
     m.kind = MESH_INTERVAL;

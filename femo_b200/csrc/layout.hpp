@@ -25,6 +25,8 @@ struct Mesh {
     std::vector<double> coords;              // nverts*gdim, AoS
     std::vector<int32_t> cells;              // ncells*nvpc, AoS
     std::vector<int32_t> bf_cell, bf_local;  // exterior facets, sorted by (cell, local facet)
+    std::vector<int32_t> cell_tag;           // optional subdomain id per cell (meshtags of dimension tdim)
+    bool lattice = true;                     // (n[0]+1) x (n[1]+1) vertex lattice in row-major order
 };
 
 // ext_bottom / ext_top: whether the y = lo / y = hi edge is a true domain boundary (false for the
@@ -36,6 +38,8 @@ void make_unit_square_tri(int nx, int ny, const double lo[2], const double hi[2]
 void make_unit_square_tri_slab(int nx, int gny, int row0, int nrows, const double lo[2], const double hi[2], Mesh &m);
 void make_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2], Mesh &m);
 void make_interval(int n, double x0, double x1, Mesh &m);
+// periodic polar lattice on the annulus r0 <= r <= r1: node (ir, ith) -> ir*nth + ith
+void make_annulus_tri(int nr, int nth, double r0, double r1, Mesh &m);
 
 // A finite-element space on a mesh: dof = block*node + comp, local index a*block+comp.
 struct Space {

@@ -14,6 +14,7 @@ FAMILY_NLPOISSON_P1 = 2
 FAMILY_EB_BEAM = 3
 FAMILY_SIMP_Q1 = 4
 FAMILY_MASS_P1 = 5
+FAMILY_MOTOR_EM = 7
 
 
 def device_count():
@@ -58,6 +59,14 @@ class EngineMesh:
         m.shape, m.lo, m.hi = (n,), (x0,), (x1,)
         return m
 
+    @classmethod
+    def annulus(cls, nr, nth, r0=0.06, r1=0.12):
+        h = C.c_void_p()
+        check(lib.femo_mesh_create_annulus(int(nr), int(nth), float(r0), float(r1), C.byref(h)))
+        m = cls(h)
+        m.shape, m.lo, m.hi = (nr, nth), (r0, 0.0), (r1, 2 * np.pi)
+        return m
+
     def coords(self):
         out = np.empty((self.nverts, self.gdim), dtype=np.float64)
         check(lib.femo_mesh_copy(self._h, 0, _np_ptr(out)))
@@ -85,12 +94,26 @@ class EngineProblem:
     """One form family instantiated on a mesh: dofmaps, CSR patterns and gather
     maps on the host; after `upload()` the device-resident assembly / solve path."""
 
-    def __init__(self, mesh, family, params=(), tagged=None):
+    def __init__(self, mesh, family, params=(), tagged=None, facets=None, cell_tags=None):
         self.mesh = mesh
         self.family = family
         h = C.c_void_p()
         pa = (C.c_double * max(1, len(params)))(*params)
-        if tagged is None:
+        if facets is not None or cell_tags is not None:
+            # general form: explicit one-sided facets (cell, local facet) and / or a subdomain id per cell
+            fc = fl = tg = None
+            nf = 0
+            if facets is not None:
+                fc = np.ascontiguousarray(facets[0], dtype=np.int32).ravel()
+                fl = np.ascontiguousarray(facets[1], dtype=np.int32).ravel()
+                nf = fc.size
+            if cell_tags is not None:
+                tg = np.ascontiguousarray(cell_tags, dtype=np.int32).ravel()
+                assert tg.size == mesh.ncells
+            check(lib.femo_problem_create_ex(mesh._h, int(family), pa, len(params),
+                                             None if fc is None else _np_ptr(fc), None if fl is None else _np_ptr(fl),
+                                             nf, None if tg is None else _np_ptr(tg), C.byref(h)))
+        elif tagged is None:
             check(lib.femo_problem_create(mesh._h, int(family), pa, len(params), C.byref(h)))
         else:   # facets of a tagged measure ds(tag): indices into mesh.exterior_facets()
             tg = np.ascontiguousarray(tagged, dtype=np.int32).ravel()
@@ -193,6 +216,9 @@ class EngineProblem:
     def coefficient(self, slot):
         return self._keep.get(slot)
 
+    def set_param(self, index, value):
+        check(lib.femo_problem_set_param(self._h, int(index), float(value)))
+
     def launch_count(self):
         n = C.c_longlong()
         check(lib.femo_problem_launch_count(self._h, C.byref(n)))
@@ -254,10 +280,11 @@ class EngineProblem:
         return y
 
     def linear_solve(self, vals, b, x=None, transpose=False, rtol=1e-10, atol=0.0, max_it=100000, check_every=1,
-                     precond=0, cheb_degree=0, cheb_ratio=0.0):
+                     precond=0, cheb_degree=0, cheb_ratio=0.0, method=0, restart=0):
+        """method 0 = CG, 1 = restarted GMRES (non-symmetric Jacobians)."""
         x = self.new_vector(self.N, 0.0) if x is None else x
-        o = KrylovOpts(rtol=rtol, atol=atol, max_it=max_it, precond=precond, cheb_degree=cheb_degree, method=0,
-                       restart=0, check_every=check_every, cheb_ratio=cheb_ratio)
+        o = KrylovOpts(rtol=rtol, atol=atol, max_it=max_it, precond=precond, cheb_degree=cheb_degree, method=method,
+                       restart=restart, check_every=check_every, cheb_ratio=cheb_ratio)
         info = KrylovInfo()
         check(lib.femo_linear_solve(self._h, self._p(vals), self._p(b), self._p(x), 1 if transpose else 0,
                                     C.byref(o), C.byref(info)))
@@ -265,7 +292,7 @@ class EngineProblem:
                        bnorm=info.bnorm, spmv_count=info.spmv_count)
 
     def newton_solve(self, kind='Newton', atol=None, rtol=None, stol=1e-8, max_it=None, krylov_rtol=1e-10,
-                     krylov_max_it=100000, check_every=1, precond=0, cheb_degree=0, cheb_ratio=0.0):
+                     krylov_max_it=100000, check_every=1, precond=0, cheb_degree=0, cheb_ratio=0.0, method=0):
         """kind 'Newton' = dolfinx NewtonSolver defaults of the reference (3 fixed
         iterations, utils_dolfinx.py:419-425); 'SNES' = PETSc newtonls (:376-416)."""
         snes = (kind == 'SNES')
@@ -276,7 +303,7 @@ class EngineProblem:
         o.stol = stol
         o.max_it = (100 if snes else 3) if max_it is None else max_it
         o.krylov = KrylovOpts(rtol=krylov_rtol, atol=0.0, max_it=krylov_max_it, precond=precond,
-                              cheb_degree=cheb_degree, method=0, restart=0, check_every=check_every,
+                              cheb_degree=cheb_degree, method=method, restart=0, check_every=check_every,
                               cheb_ratio=cheb_ratio)
         info = NewtonInfo()
         check(lib.femo_newton_solve(self._h, C.byref(o), C.byref(info)))

@@ -44,6 +44,7 @@ typedef struct femo_problem femo_problem;
 #define FEMO_FAMILY_NLPOISSON_P1 2 /* examples/nonlinear_poisson_opt/run_nonlinear_poisson_opt.py:88-116,140-142 */
 #define FEMO_FAMILY_EB_BEAM 3      /* examples/beam_thickness_opt/run_thickness_opt_cantilever_beam.py:71-85 */
 #define FEMO_FAMILY_SIMP_Q1 4      /* examples/beam_topo_opt/run_topo_opt_cantilever_beam.py:62-86 */
+#define FEMO_FAMILY_MOTOR_EM 7     /* examples/em_motor_opt/motor_pde.py:12-130,186-197 (nonlinear magnetostatics on a moving mesh) */
 #define FEMO_FAMILY_MASS_P1 5      /* L2 projection, femo/fea/utils_dolfinx.py:549-583; params: target (0 CG1, 1 DG0),
                                       source (0 u_ex, 1 f_ex analytic; 2 DG0 input^power; 3 CG1 input), power */
 
@@ -60,6 +61,9 @@ int femo_device_count(void);
 int femo_mesh_create_unit_square(int nx, int ny, const double lo[2], const double hi[2], femo_mesh **out);
 int femo_mesh_create_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2], femo_mesh **out);
 int femo_mesh_create_interval(int n, double x0, double x1, femo_mesh **out);
+/* synthetic stand-in for the motor meshes (git-LFS pointers in the reference): periodic polar lattice on
+ * r0 <= r <= r1, node (ir, ith) -> ir*nth + ith */
+int femo_mesh_create_annulus(int nr, int nth, double r0, double r1, femo_mesh **out);
 /* sizes[0..5] = ncells, nverts, verts/cell, gdim, n exterior facets, mesh kind */
 int femo_mesh_sizes(const femo_mesh *m, int64_t sizes[6]);
 /* what: 0 coords (double nverts*gdim), 1 cells (int32 ncells*nvpc),
@@ -77,6 +81,13 @@ int femo_problem_create(const femo_mesh *m, int family, const double *params, in
  * utils_dolfinx.py:532-546; examples' ds_(100)): indices into the mesh's exterior-facet list. */
 int femo_problem_create_tagged(const femo_mesh *m, int family, const double *params, int nparams,
                                const int32_t *facet_ids, int nfacets, femo_problem **out);
+/* General form: explicit one-sided facets (cell, local facet) of the facet integrals (NULL = the family's
+ * default) and a subdomain id per cell (meshtags of the cells, the dx(i) measures of motor_pde.py; may be NULL). */
+int femo_problem_create_ex(const femo_mesh *m, int family, const double *params, int nparams, const int32_t *facet_cell,
+                           const int32_t *facet_local, int nfacets, const int32_t *cell_tags, femo_problem **out);
+/* change one family parameter after creation (e.g. the source scaling of the incremental EM solve,
+ * run_motor_opt.py:231-250) */
+int femo_problem_set_param(femo_problem *p, int index, double value);
 void femo_problem_destroy(femo_problem *p);
 /* sizes[0]=N (state dofs) [1]=n inputs [2]=n aux fields [3]=n outputs
  * [4..7]=M_s (input s dofs) [8..11]=aux field dofs [12]=n exterior facets */

@@ -1,0 +1,108 @@
+"""Motor magnetostatics family (config 5b): oracle pins (no GPU), layout equality, and the CUDA path
+(forward-mode dual numbers) against the oracle (complex-step derivatives)."""
+import numpy as np
+import pytest
+
+from oracle import motor, assembly as asm, solvers
+from _cases import relerr
+from _cases_motor import MotorCase, em_params
+
+
+def test_mesh_tags_and_layout_bit_exact():
+    c = MotorCase(6, 24, upload=False)
+    assert np.array_equal(c.emesh.coords(), c.omesh.coords)
+    assert np.array_equal(c.emesh.cells(), c.omesh.cells)
+    fc, fl = c.emesh.exterior_facets()
+    oc, ol = c.omesh.exterior_facets()
+    assert np.array_equal(fc, oc) and np.array_equal(fl, ol)
+    ids = np.unique(c.tags)
+    assert set(range(1, 52)) <= set(ids.tolist())              # steel, 12 magnets, 36 windings, shaft all present
+    u, uh = np.zeros(c.F.N), np.zeros(c.F.M)
+    for which, blocks, shape in ((0, c.F.jacobian(u, uh), (c.F.N, c.F.N)), (1, c.F.dRdm(0, u, uh), (c.F.N, c.F.M))):
+        rp, col = c.p.pattern(which)
+        orp, ocol = asm.pattern(blocks, shape)
+        assert np.array_equal(rp, orp) and np.array_equal(col, ocol)
+
+
+def test_oracle_derivatives_vs_finite_differences():
+    c = MotorCase(8, 36, upload=False)
+    F, u, uh = c.F, c.u, c.m
+    rng = np.random.default_rng(1)
+    du, dh = rng.standard_normal(F.N), rng.standard_normal(F.M)
+    R = lambda a, b: asm.assemble_vector(F.residual(a, b), F.N)
+    A = asm.assemble_matrix(F.jacobian(u, uh), (F.N, F.N))
+    h = 1e-7
+    fd = (R(u + h * du, uh) - R(u - h * du, uh)) / (2 * h)
+    assert np.abs(A @ du - fd).max() < 1e-6 * np.abs(fd).max()
+    D = asm.assemble_matrix(F.dRdm(0, u, uh), (F.N, F.M))
+    h = 1e-9
+    fd = (R(u, uh + h * dh) - R(u, uh - h * dh)) / (2 * h)
+    assert np.abs(D @ dh - fd).max() < 1e-6 * np.abs(fd).max()
+    assert abs(A - A.T).max() > 1e-3 * abs(A).max()             # the nonlinear Nitsche coefficient breaks symmetry
+
+
+def test_oracle_load_ramp_reaches_saturation():
+    """run_motor_opt.py:231-250: five source increments, SNES each; the steel reaches the cubic/exponential branch."""
+    c = MotorCase(12, 48, upload=False)
+    x = np.zeros(c.F.N)
+    for st in range(1, 6):
+        c.F.js_scale = st / 5
+        x, info = c.sp.solve_snes(x, [np.zeros(c.F.M)])
+        assert info['reason'] in ('ABS', 'REL', 'STOL')
+    gx, _, _, _ = c.F._kin(c.F.G, x[c.F.cell_dofs], np.zeros((c.omesh.ncells, 3, 2)))
+    Bn = np.sqrt((gx ** 2).sum(axis=1))
+    assert Bn[(c.tags == 1) | (c.tags == 2)].max() > 0.8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('nr,nth,uscale', [(6, 24, 1e-2), (12, 48, 1e-2), (8, 36, 3e-2)])
+def test_gpu_assembly_matches_oracle(cuda_device, nr, nth, uscale):
+    c = MotorCase(nr, nth, seed=nr, uscale=uscale)
+    F, p = c.F, c.p
+    TOL = 1e-11
+    assert relerr(p.assemble_residual().cpu().numpy(), asm.assemble_vector(F.residual(c.u, c.m), F.N)) < TOL
+    vals, _ = p.assemble_jacobian()
+    assert relerr(vals.cpu().numpy(), asm.assemble_matrix(F.jacobian(c.u, c.m), (F.N, F.N)).data) < TOL
+    assert relerr(p.assemble_dRdm(0).cpu().numpy(), asm.assemble_matrix(F.dRdm(0, c.u, c.m), (F.N, F.M)).data) < TOL
+    for k in range(2):
+        Jo = asm.assemble_scalar(F.output(k, c.u, c.m))
+        assert abs(p.assemble_output(k) - Jo) <= TOL * abs(Jo)
+        assert relerr(p.assemble_output_grad(k, 0).cpu().numpy(), asm.assemble_vector(F.output_du(k, c.u, c.m), F.N)) < TOL
+        assert relerr(p.assemble_output_grad(k, 1).cpu().numpy(), asm.assemble_vector(F.output_dm(k, 0, c.u, c.m), F.M)) < TOL
+
+
+@pytest.mark.gpu
+def test_gpu_gmres_and_state_solve(cuda_device):
+    """Incremental nonlinear B-H solve (five source steps, SNES + GMRES) and the adjoint shape gradient
+    d(int |B|^2 J dx)/d(uhat) against the oracle's direct solves."""
+    import scipy.sparse.linalg as spla
+    c = MotorCase(12, 48, seed=2)
+    p, F = c.p, c.F
+    uh = c.m
+    # GMRES on the non-symmetric Jacobian (plain and transposed)
+    vals, _ = p.assemble_jacobian()
+    A = c.csr(0, vals)
+    b = np.random.default_rng(0).standard_normal(F.N)
+    for tr in (False, True):
+        x, info = p.linear_solve(vals, p.to_device(b), transpose=tr, rtol=1e-12, method=1, max_it=4000)
+        assert info['converged'], info
+        assert relerr(x.cpu().numpy(), spla.spsolve((A.T if tr else A).tocsc(), b)) < 1e-7
+    # load ramp
+    c.d_u.zero_()
+    x = np.zeros(F.N)
+    for st in range(1, 6):
+        p.set_param(6, st / 5)
+        F.js_scale = st / 5
+        info = p.newton_solve(kind='SNES', krylov_rtol=1e-12, krylov_max_it=4000, method=1)
+        x, oinfo = c.sp.solve_snes(x, [uh])
+        assert info['converged'] in (1, 2, 3)
+    u = c.d_u.cpu().numpy()
+    assert relerr(u, x) < 1e-7
+    # adjoint: dJ/duhat = pJ/puhat - (dR/duhat)^T A^-T pJ/pu
+    vals, _ = p.assemble_jacobian()
+    lam, li = p.linear_solve(vals, p.assemble_output_grad(0, 0), transpose=True, rtol=1e-12, method=1, max_it=4000)
+    assert li['converged']
+    g = p.assemble_output_grad(0, 1).cpu().numpy() - p.spmv(1, p.assemble_dRdm(0), lam, transpose=True).cpu().numpy()
+    (go,), lamo = c.sp.total_derivative(0, x, [uh])
+    assert relerr(lam.cpu().numpy(), lamo) < 1e-6
+    assert relerr(g, go) < 1e-6
