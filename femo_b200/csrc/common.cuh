@@ -29,7 +29,7 @@ constexpr int kMaxPartials = 4096;   // upper bound on CTAs of any reducing kern
 constexpr int kMaxSlots = 12;
 
 // device scalar slots (doubles) used by the Krylov / Newton drivers
-enum Scalar { S_ALPHA = 0, S_BETA, S_RZ, S_RR, S_PQ, S_TMP0, S_TMP1, S_TMP2, S_BB, S_GM = 16, S_COUNT = 96 };
+enum Scalar { S_ALPHA = 0, S_BETA, S_RZ, S_RR, S_PQ, S_TMP0, S_TMP1, S_TMP2, S_BB, S_GM = 16, S_COUNT = 128 };
 
 // ---- reductions (deterministic: fixed assignment, fixed tree) ---------------
 __device__ __forceinline__ double warp_sum(double v) {

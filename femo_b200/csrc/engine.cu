@@ -1069,7 +1069,7 @@ static size_t pattern_bytes(const Pattern &P, bool bc) {
 }
 static size_t vecmap_bytes(const VecMap &V) { return Arena::need(V.ptr.size(), 4) + Arena::need(V.src.size(), 4); }
 
-constexpr int kGmresRestart = 40;
+constexpr int kGmresRestart = 70;
 
 static void child_bytes(const femo_problem *c, bool coarsest, size_t *sb, size_t *wb) {
     const Mesh &M = c->mesh;

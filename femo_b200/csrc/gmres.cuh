@@ -53,7 +53,22 @@ __global__ void __launch_bounds__(kThreads) k_hadamard(const double *__restrict_
 
 using namespace femo;
 
-constexpr int kGmresMax = 60;   // S_GM .. S_GM+kGmresMax scalar slots
+constexpr int kGmresMax = 72;   // S_GM .. S_GM+kGmresMax scalar slots
+
+// Gershgorin bound + inverse diagonal of level 0 for the Chebyshev polynomial preconditioner (precond 1)
+static int cheb_setup(femo_problem *p, const double *vals) {
+    const int64_t n = p->state.ndofs;
+    const DevPattern &D = p->dpat[0];
+    const int g = red_grid(p, n);
+    int rc;
+    p->mgl.vals = const_cast<double *>(vals);
+    k_diag_gershgorin<<<g, kThreads, 0, p->stream>>>(D.rowptr, D.col, vals, p->mgl.dinv, n, p->own_off, p->own_off + p->own_n, p->d_partials);
+    k_max_finalize<<<1, kThreads, 0, p->stream>>>(p->d_partials, g, p->d_scalars, S_TMP2);
+    p->launches += 2;
+    FEMO_CHECK_LAUNCH();
+    if ((rc = allreduce_scalars(p, S_TMP2, 1, true))) return rc;
+    return read_scalars(p, S_TMP2, 1, &p->mgl.lmax);
+}
 
 static int gmres_solve(femo_problem *p, const double *vals, const double *b, double *x, femo_krylov_opts o,
                        femo_krylov_info *info) {
@@ -72,8 +87,12 @@ static int gmres_solve(femo_problem *p, const double *vals, const double *b, dou
     if (o.cheb_degree > 0) mp.degree = o.cheb_degree;
     int rc, spmvs = 0, its = 0;
     p->mgl.dinv = p->kr_dinv; p->mgl.r = p->kr_w; p->mgl.d = p->kr_d; p->mgl.q = p->wk_extra;
+    const int cdeg = o.cheb_degree > 0 ? o.cheb_degree : 12;
+    const double cratio = o.cheb_ratio > 1.0 ? o.cheb_ratio : 150.0;
     if (pre == 2) {
         if ((rc = mg_setup(p, vals))) return rc;
+    } else if (pre == 1) {
+        if ((rc = cheb_setup(p, vals))) return rc;
     } else if (pre == 3) {
         k_dense_inverse<<<1, kThreads, 0, st>>>(D.rowptr, D.col, vals, (int)n, p->d_dense_tmp, p->d_dense);
         p->launches++;
@@ -85,6 +104,7 @@ static int gmres_solve(femo_problem *p, const double *vals, const double *b, dou
     auto precond = [&](const double *in, double *out) -> int {
         if (pre == 3) k_dense_apply<<<(int)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(p->d_dense, in, out, (int)n);
         else if (pre == 2) return mg_vcycle(p, 0, in, out, mp);
+        else if (pre == 1) return mg_smooth(p, in, out, true, cdeg, cratio);
         else k_hadamard<<<g, kThreads, 0, st>>>(p->kr_dinv, in, out, n);
         p->launches++;
         FEMO_CHECK_LAUNCH();

@@ -126,6 +126,8 @@ __global__ void k_scalar_op(double *sc, int op) {
 
 using namespace femo;
 
+static int cheb_setup(femo_problem *p, const double *vals);
+
 static void default_krylov(femo_krylov_opts &o) {
     if (o.rtol <= 0) o.rtol = 1e-10;
     if (o.atol < 0) o.atol = 0;
@@ -184,8 +186,12 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     p->mgl.r = p->kr_w;
     p->mgl.d = p->kr_d;
     p->mgl.q = p->kr_q;
+    const int cdeg = o.cheb_degree > 0 ? o.cheb_degree : 8;
+    const double cratio = o.cheb_ratio > 1.0 ? o.cheb_ratio : 60.0;
     if (pre == 2) {
         if ((rc = mg_setup(p, vals))) return rc;
+    } else if (pre == 1) {
+        if ((rc = cheb_setup(p, vals))) return rc;
     } else if (pre == 3) {
         k_dense_inverse<<<1, kThreads, 0, st>>>(D.rowptr, D.col, vals, (int)n, p->d_dense_tmp, p->d_dense);
         p->launches++;
@@ -227,6 +233,8 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
             if (pre == 3) {
                 k_dense_apply<<<(int)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(p->d_dense, p->kr_r, p->kr_z, (int)n);
                 p->launches++;
+            } else if (pre == 1) {
+                if ((rc = mg_smooth(p, p->kr_r, p->kr_z, true, cdeg, cratio))) return rc;
             } else if ((rc = mg_vcycle(p, 0, p->kr_r, p->kr_z, mp))) return rc;
             k_dot<<<go, kThreads, 0, st>>>(p->kr_r + p->own_off, p->kr_z + p->own_off, p->own_n, pa);
             p->launches++;

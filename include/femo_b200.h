@@ -196,10 +196,11 @@ typedef struct femo_krylov_opts {
     double rtol;      /* ||r|| <= rtol*||b||   */
     double atol;      /* or ||r|| <= atol      */
     int max_it;
-    int precond;      /* 0 Jacobi, 2 geometric multigrid V-cycle (Chebyshev-Jacobi smoothing),
+    int precond;      /* 0 Jacobi, 1 Chebyshev polynomial of the Jacobi-scaled operator (cheb_degree, cheb_ratio),
+                         2 geometric multigrid V-cycle (Chebyshev-Jacobi smoothing),
                          3 explicit dense inverse (N <= 512; the direct-solve analogue) */
     int cheb_degree;  /* smoother degree of the V-cycle (default 2) */
-    int method;       /* 0 CG, 1 GMRES(restart) */
+    int method;       /* 0 CG, 1 restarted GMRES (right-preconditioned, CGS2; non-symmetric Jacobians) */
     int restart;      /* GMRES restart; with precond 2: 1 disables the full-multigrid start */
     int check_every;  /* residual-norm host check period (>=1) */
     double cheb_ratio; /* smoother targets [lmax/ratio, lmax] of D^-1 A (default 8) */

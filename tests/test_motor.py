@@ -84,7 +84,8 @@ def test_gpu_gmres_and_state_solve(cuda_device):
     A = c.csr(0, vals)
     b = np.random.default_rng(0).standard_normal(F.N)
     for tr in (False, True):
-        x, info = p.linear_solve(vals, p.to_device(b), transpose=tr, rtol=1e-12, method=1, max_it=4000)
+        x, info = p.linear_solve(vals, p.to_device(b), transpose=tr, rtol=1e-12, method=1, max_it=20000, precond=1,
+                                 cheb_degree=24, cheb_ratio=600.0)
         assert info['converged'], info
         assert relerr(x.cpu().numpy(), spla.spsolve((A.T if tr else A).tocsc(), b)) < 1e-7
     # load ramp
@@ -93,14 +94,16 @@ def test_gpu_gmres_and_state_solve(cuda_device):
     for st in range(1, 6):
         p.set_param(6, st / 5)
         F.js_scale = st / 5
-        info = p.newton_solve(kind='SNES', krylov_rtol=1e-12, krylov_max_it=4000, method=1)
+        info = p.newton_solve(kind='SNES', krylov_rtol=1e-12, krylov_max_it=20000, method=1, precond=1, cheb_degree=24,
+                              cheb_ratio=600.0)
         x, oinfo = c.sp.solve_snes(x, [uh])
         assert info['converged'] in (1, 2, 3)
     u = c.d_u.cpu().numpy()
     assert relerr(u, x) < 1e-7
     # adjoint: dJ/duhat = pJ/puhat - (dR/duhat)^T A^-T pJ/pu
     vals, _ = p.assemble_jacobian()
-    lam, li = p.linear_solve(vals, p.assemble_output_grad(0, 0), transpose=True, rtol=1e-12, method=1, max_it=4000)
+    lam, li = p.linear_solve(vals, p.assemble_output_grad(0, 0), transpose=True, rtol=1e-12, method=1, max_it=20000,
+                             precond=1, cheb_degree=24, cheb_ratio=600.0)
     assert li['converged']
     g = p.assemble_output_grad(0, 1).cpu().numpy() - p.spmv(1, p.assemble_dRdm(0), lam, transpose=True).cpu().numpy()
     (go,), lamo = c.sp.total_derivative(0, x, [uh])
