@@ -239,7 +239,7 @@ def solveNonlinear(res, func, bc, solver, report, initialize):
         info = p.newton_solve(kind=solver, krylov_rtol=KRYLOV['rtol'], krylov_max_it=KRYLOV['max_it'],
                               check_every=KRYLOV['check_every'],
                               precond=KRYLOV['precond'] if fam.precond is None else fam.precond,
-                              cheb_degree=KRYLOV['cheb_degree'])
+                              method=fam.method, **dict(dict(cheb_degree=KRYLOV['cheb_degree']), **fam.krylov_extra))
     finally:
         func.mark_device_written()
     if solver == 'SNES':
@@ -276,7 +276,7 @@ def _solve_into(A, b, x):
     _, info = p.linear_solve(A.vals, bf.device_tensor(p), xt, transpose=A.transposed, rtol=KRYLOV['rtol'],
                              max_it=KRYLOV['max_it'], check_every=KRYLOV['check_every'],
                              precond=KRYLOV['precond'] if fam.precond is None else fam.precond,
-                             cheb_degree=KRYLOV['cheb_degree'])
+                             method=fam.method, **dict(dict(cheb_degree=KRYLOV['cheb_degree']), **fam.krylov_extra))
     xf.mark_device_written()
     fam.last_linear_info = info
     if not info['converged']:
@@ -318,3 +318,43 @@ def errorNorm(v, v_ex, norm='L2'):
     ee = e[mesh.cells]
     s = (ee ** 2).sum(axis=1) + ee[:, 0] * ee[:, 1] + ee[:, 0] * ee[:, 2] + ee[:, 1] * ee[:, 2]
     return float(np.sqrt(np.sum(det / 12.0 * s)))
+
+
+# ---- motor helpers (utils_dolfinx.py:126-134,514-546,587-641) ------------------------
+def findNodeIndices(node_coordinates, coordinates):
+    """Indices of the mesh vertices closest to `node_coordinates` (scipy KDTree, as the reference)."""
+    from scipy.spatial import KDTree
+    dist, node_indices = KDTree(coordinates).query(node_coordinates)
+    return node_indices
+
+
+def locateDOFs(coords, V, input='polar'):
+    """Dofs (both components) of the vertices nearest to the given edge points of the mesh-motion problem."""
+    coords = np.reshape(np.array(coords, dtype=np.float64), (-1, 2))
+    if input == 'polar':
+        theta, r = coords[:, 0].copy(), coords[:, 1].copy()
+        coords = np.stack([r * np.cos(theta), r * np.sin(theta)], axis=1)
+    node_indices = findNodeIndices(coords, V.tabulate_dof_coordinates()[:, :-1])
+    edge_indices = np.empty(2 * len(node_indices))
+    edge_indices[0::2] = 2 * node_indices
+    edge_indices[1::2] = 2 * node_indices + 1
+    return edge_indices.astype('int')
+
+
+def move(mesh, u):
+    """Add the displacement function u (vector CG1) to the mesh coordinates."""
+    a = getFuncArray(u).reshape(-1, mesh.geometry.dim)
+    mesh.geometry.x[:, :mesh.geometry.dim] += a
+
+
+def moveBackward(mesh, u):
+    a = getFuncArray(u).reshape(-1, mesh.geometry.dim)
+    mesh.geometry.x[:, :mesh.geometry.dim] -= a
+
+
+def createCustomMeasure(mesh, dim, SubdomainFunc, measure: str, tag: int):
+    """Tagged measure from a geometric marker (quadrature degree 4 in the reference, :537)."""
+    metadata = {"quadrature_degree": 4}
+    subdomain = locate_entities_boundary(mesh, dim, SubdomainFunc)
+    subdomain_tag = meshtags(mesh, dim, subdomain, np.full(len(subdomain), tag, dtype=np.int32))
+    return Measure(measure, domain=mesh, subdomain_data=subdomain_tag, metadata=metadata)

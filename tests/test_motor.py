@@ -109,3 +109,59 @@ def test_gpu_gmres_and_state_solve(cuda_device):
     (go,), lamo = c.sp.total_derivative(0, x, [uh])
     assert relerr(lam.cpu().numpy(), lamo) < 1e-6
     assert relerr(g, go) < 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_motor_api_check_totals(cuda_device):
+    """The EM half of examples/em_motor_opt/run_motor_opt.py through FEA + FEAModel + Simulator:
+    custom incremental solve, B-influence outputs, adjoint totals w.r.t. the mesh displacement vs FD."""
+    from femo_b200.fea.fea_b200 import FEA, Mesh, FunctionSpace, VectorFunctionSpace, Function, TestFunction, meshtags, Measure
+    from femo_b200.fea.utils_b200 import solveNonlinear
+    from femo_b200.forms import motor as pde
+    from femo_b200.csdl_opt import FEAModel, Simulator
+    from femo_b200 import engine as E
+    nr, nth = 8, 36
+    mesh = Mesh(E.EngineMesh.annulus(nr, nth), 'triangle')
+    om_ = motor.annulus_tri(nr, nth)
+    tags = motor.motor_tags(om_)
+    dx = Measure('dx', domain=mesh, subdomain_data=meshtags(mesh, 2, np.arange(mesh.num_cells), tags))
+    Hc, p, s, vacuum_perm, angle, iq = 838.e3, 12, 36, 4e-7 * np.pi, 0., 282.2 / 0.00016231
+    fea_em = FEA(mesh)
+    fea_em.PDE_SOLVER = 'SNES'
+    fea_em.REPORT = False
+    uhat = Function(VectorFunctionSpace(mesh, ('CG', 1)))
+    V = FunctionSpace(mesh, ('CG', 1))
+    A_z = Function(V)
+    res = pde.pdeResEM(A_z, TestFunction(V), uhat, iq, dx, p, s, Hc, vacuum_perm, angle, g=Function(V), nitsche=True,
+                       sym=True)
+    js = pde.JS(res)
+
+    def solveIncrementalEM(res_, func, bc, report=False):
+        func.vector.set(0.0)
+        for i in range(5):
+            js.set_scale((i + 1) / 5)
+            solveNonlinear(res_, func, bc, 'SNES', False, False)
+    fea_em.custom_solve = solveIncrementalEM
+    fea_em.add_input('uhat', uhat, init_val=0.0)
+    fea_em.add_state(name='A_z', function=A_z, residual_form=res, arguments=['uhat'])
+    fea_em.add_output(name='B_influence_eddy_current', type='scalar',
+                      form=pde.B_power_form(A_z, uhat, 2, dx, [1, 2]), arguments=['A_z', 'uhat'])
+    fea_em.add_output(name='B_influence_hysteresis', type='scalar',
+                      form=pde.B_power_form(A_z, uhat, 1.76835, dx, [1, 2]), arguments=['A_z', 'uhat'])
+    model = FEAModel(fea=[fea_em], debug_mode=False)
+    rng = np.random.default_rng(0)
+    model.create_input('uhat', shape=fea_em.inputs_dict['uhat']['shape'], val=1e-4 * rng.standard_normal(2 * om_.nverts))
+    sim = Simulator(model)
+    sim.run()
+    # oracle forward values
+    F = motor.MotorEM(om_, tags)
+    sp_ = solvers.StatePath(F, None)
+    x = np.zeros(F.N)
+    for st in range(1, 6):
+        F.js_scale = st / 5
+        x, _ = sp_.solve_snes(x, [sim['uhat']])
+    assert relerr(sim['A_z'], x) < 1e-7
+    for k, name in enumerate(('B_influence_eddy_current', 'B_influence_hysteresis')):
+        assert abs(sim[name][0] - asm.assemble_scalar(F.output(k, x, sim['uhat']))) < 1e-7 * abs(sim[name][0])
+    rep = sim.check_totals('B_influence_eddy_current', 'uhat', step=1e-7, directions=2, compact_print=False)
+    assert max(rep.values()) < 1e-4, rep
