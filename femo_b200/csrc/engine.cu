@@ -10,6 +10,7 @@
 #include "families2.cuh"
 #include "families3.cuh"
 #include "families4.cuh"
+#include "families5.cuh"
 #include "dist.cuh"
 
 namespace femo {
@@ -368,7 +369,7 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
     if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
     const bool analytic_src = p->family == FEMO_FAMILY_MASS_P1 && p->params[1] < 1.5;
     const bool jac_reads_input = p->family == FEMO_FAMILY_SIMP_Q1 || p->family == FEMO_FAMILY_EB_BEAM ||
-                                 p->family == FEMO_FAMILY_MOTOR_EM;
+                                 p->family == FEMO_FAMILY_MOTOR_EM || p->family == FEMO_FAMILY_MOTOR_MM;
     if ((op != OP_JAC || jac_reads_input) && !analytic_src && (rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
     double *cells_out = p->d_scratch;
     double *facets_out = p->d_scratch + ((mask & 1) ? nc * op_planes(p, op) : 0);
@@ -400,6 +401,34 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
                 TriArgs F = tri_args(p, facets_out);
                 if (op == OP_RES) k_nlpoisson_p1_facet<OP_RES><<<gf, kThreads, 0, st>>>(F);
                 else k_nlpoisson_p1_facet<OP_JAC><<<gf, kThreads, 0, st>>>(F);
+                p->launches++;
+            }
+            break;
+        }
+        case FEMO_FAMILY_MOTOR_MM: {
+            MmArgs A;
+            A.coords = p->d_coords; A.cellsT = p->d_cellsT; A.ncells = nc;
+            A.fb_cell = p->d_fb_cell; A.fb_local = p->d_fb_local; A.nfacets = nf;
+            A.tag = p->d_cell_tag; A.uh = p->coef[0]; A.g = p->coef[1];
+            A.beta0 = p->params[0]; A.out_id = out_id;
+            const int g1 = (int)((nc + 63) / 64), g2 = (int)((std::max<int64_t>(nf, 1) + 63) / 64);
+            if (mask & 1) {
+                A.out = cells_out;
+                switch (op) {
+                    case OP_RES: k_motor_mm<OP_RES, 0><<<g1, 64, 0, st>>>(A); break;
+                    case OP_JAC: k_motor_mm<OP_JAC, 0><<<g1, 64, 0, st>>>(A); break;
+                    case OP_OUT: k_motor_mm<OP_OUT, 0><<<g1, 64, 0, st>>>(A); break;
+                    case OP_OUT_DU: k_motor_mm<OP_OUT_DU, 0><<<g1, 64, 0, st>>>(A); break;
+                    default: return set_err(FEMO_EINVAL, "mesh-motion family: operation has no cell integral");
+                }
+                p->launches++;
+            }
+            if ((mask & 2) && nf > 0) {
+                A.out = facets_out;
+                if (op == OP_RES) k_motor_mm<OP_RES, 1><<<g2, 64, 0, st>>>(A);
+                else if (op == OP_JAC) k_motor_mm<OP_JAC, 1><<<g2, 64, 0, st>>>(A);
+                else if (op == OP_DRDM) k_motor_mm<OP_DRDM, 1><<<g2, 64, 0, st>>>(A);
+                else return set_err(FEMO_EINVAL, "mesh-motion family: operation has no facet integral");
                 p->launches++;
             }
             break;
@@ -679,6 +708,20 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
                     if (nparams < 1) p->params[0] = 6e-7;
                     if (nparams < 2) p->params[1] = 10.0;
                 }
+                break;
+            case FEMO_FAMILY_MOTOR_MM:
+                if (M.kind != MESH_TRI) throw LayoutError{FEMO_EINVAL, "family needs a triangle mesh"};
+                if (M.cell_tag.empty()) throw LayoutError{FEMO_EINVAL, "motor family needs cell tags (subdomain ids)"};
+                if (!fcell || !flocal) throw LayoutError{FEMO_EINVAL, "mesh-motion family needs the tagged one-sided facets dS(1000)/ds(1000)"};
+                p->state.init(M, EL_VERTEX, 2);
+                p->nin = 1;
+                p->in[0].init(M, EL_VERTEX, 2);                 // prescribed edge displacement g = uhat_bc
+                p->nout = 3;
+                if (nparams < 1) p->params[0] = 5e3;
+                p->res_mask = p->jac_mask = 3;
+                p->drdm_mask = 2;                                // only the Nitsche facet terms depend on g
+                for (int k = 0; k < 3; ++k) { p->out_mask[k] = 1; p->out_du_mask[k] = 1; p->out_dm_mask[k] = 0; }
+                p->symmetric = false;
                 break;
             case FEMO_FAMILY_MOTOR_EM:
                 if (M.kind != MESH_TRI) throw LayoutError{FEMO_EINVAL, "family needs a triangle mesh"};

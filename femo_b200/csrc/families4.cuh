@@ -9,39 +9,10 @@
 // and the functional gradients come from forward-mode dual numbers seeded on the element dofs, i.e.
 // the exact Gateaux derivative UFL would form (utils_dolfinx.py:313-314), not a finite difference.
 #pragma once
+#include "dual.cuh"
 #include "families.cuh"
 
 namespace femo {
-
-template <int N>
-struct Dual {
-    double v;
-    double d[N];
-    __device__ __forceinline__ Dual() {}
-    __device__ __forceinline__ Dual(double a) : v(a) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) d[i] = 0.0;
-    }
-};
-template <int N> __device__ __forceinline__ Dual<N> operator+(const Dual<N> &a, const Dual<N> &b) { Dual<N> r; r.v = a.v + b.v; _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
-template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N> &a, const Dual<N> &b) { Dual<N> r; r.v = a.v - b.v; _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
-template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N> &a) { Dual<N> r; r.v = -a.v; _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = -a.d[i]; return r; }
-template <int N> __device__ __forceinline__ Dual<N> operator*(const Dual<N> &a, const Dual<N> &b) { Dual<N> r; r.v = a.v * b.v; _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
-template <int N> __device__ __forceinline__ Dual<N> operator/(const Dual<N> &a, const Dual<N> &b) { Dual<N> r; const double ib = 1.0 / b.v; r.v = a.v * ib; _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib; return r; }
-template <int N> __device__ __forceinline__ Dual<N> operator*(double a, const Dual<N> &b) { Dual<N> r; r.v = a * b.v; _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = a * b.d[i]; return r; }
-template <int N> __device__ __forceinline__ Dual<N> operator*(const Dual<N> &b, double a) { return a * b; }
-template <int N> __device__ __forceinline__ Dual<N> operator+(const Dual<N> &a, double b) { Dual<N> r = a; r.v += b; return r; }
-template <int N> __device__ __forceinline__ Dual<N> operator+(double b, const Dual<N> &a) { return a + b; }
-template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N> &a, double b) { Dual<N> r = a; r.v -= b; return r; }
-template <int N> __device__ __forceinline__ Dual<N> operator/(double a, const Dual<N> &b) { return Dual<N>(a) / b; }
-template <int N> __device__ __forceinline__ Dual<N> dsqrt(const Dual<N> &a) { Dual<N> r; r.v = sqrt(a.v); const double s = (r.v > 0.0) ? 0.5 / r.v : 0.0; _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = s * a.d[i]; return r; }
-template <int N> __device__ __forceinline__ Dual<N> dexp(const Dual<N> &a) { Dual<N> r; r.v = exp(a.v); _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = r.v * a.d[i]; return r; }
-template <int N> __device__ __forceinline__ Dual<N> dpow(const Dual<N> &a, double p) { Dual<N> r; r.v = pow(a.v, p); const double s = (a.v > 0.0) ? p * pow(a.v, p - 1.0) : 0.0; _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = s * a.d[i]; return r; }
-__device__ __forceinline__ double dsqrt(double a) { return sqrt(a); }
-__device__ __forceinline__ double dexp(double a) { return exp(a); }
-__device__ __forceinline__ double dpow(double a, double p) { return pow(a, p); }
-__device__ __forceinline__ double valof(double a) { return a; }
-template <int N> __device__ __forceinline__ double valof(const Dual<N> &a) { return a.v; }
 
 // parameter slots of the family (femo_problem::params)
 enum EmParam { EM_MU0 = 0, EM_HC, EM_IQ, EM_ANGLE, EM_P, EM_S, EM_JS_SCALE, EM_BETA, EM_X1, EM_X2, EM_LIN = 10, EM_CUB = 12,

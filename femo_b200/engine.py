@@ -14,6 +14,7 @@ FAMILY_NLPOISSON_P1 = 2
 FAMILY_EB_BEAM = 3
 FAMILY_SIMP_Q1 = 4
 FAMILY_MASS_P1 = 5
+FAMILY_MOTOR_MM = 6
 FAMILY_MOTOR_EM = 7
 
 

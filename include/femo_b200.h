@@ -44,6 +44,7 @@ typedef struct femo_problem femo_problem;
 #define FEMO_FAMILY_NLPOISSON_P1 2 /* examples/nonlinear_poisson_opt/run_nonlinear_poisson_opt.py:88-116,140-142 */
 #define FEMO_FAMILY_EB_BEAM 3      /* examples/beam_thickness_opt/run_thickness_opt_cantilever_beam.py:71-85 */
 #define FEMO_FAMILY_SIMP_Q1 4      /* examples/beam_topo_opt/run_topo_opt_cantilever_beam.py:62-86 */
+#define FEMO_FAMILY_MOTOR_MM 6     /* examples/em_motor_opt/motor_pde.py:134-183,199-210 (hyperelastic mesh motion, Nitsche on dS/ds(1000)) */
 #define FEMO_FAMILY_MOTOR_EM 7     /* examples/em_motor_opt/motor_pde.py:12-130,186-197 (nonlinear magnetostatics on a moving mesh) */
 #define FEMO_FAMILY_MASS_P1 5      /* L2 projection, femo/fea/utils_dolfinx.py:549-583; params: target (0 CG1, 1 DG0),
                                       source (0 u_ex, 1 f_ex analytic; 2 DG0 input^power; 3 CG1 input), power */

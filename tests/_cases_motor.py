@@ -42,3 +42,44 @@ class MotorCase:
         rp, col = self.p.pattern(which)
         i = self.p.pattern_info(which)
         return sp.csr_matrix((vals.cpu().numpy(), col, rp), shape=(i['rows'], i['cols']))
+
+
+class MotorMMCase:
+    """Mesh-motion family (config 5a) on the synthetic annulus: Nitsche facets on the inner and outer
+    boundary circles and on one interior circle (both sides)."""
+
+    def __init__(self, nr=8, nth=24, seed=0, upload=True, scale=2e-4):
+        from oracle import motor_mm
+        self.emesh = E.EngineMesh.annulus(nr, nth)
+        self.omesh = motor.annulus_tri(nr, nth)
+        self.tags = motor.motor_tags(self.omesh)
+        self.mid = nr // 2
+        parts = [motor_mm.circle_facets(self.omesh, k) for k in (0, self.mid, nr)]
+        fc = np.concatenate([p[0] for p in parts])
+        fl = np.concatenate([p[1] for p in parts])
+        o = np.lexsort((fl, fc))
+        self.facets = (fc[o], fl[o])
+        self.F = motor_mm.MotorMM(self.omesh, self.facets, self.tags)
+        self.p = E.EngineProblem(self.emesh, E.FAMILY_MOTOR_MM, [5e3], facets=self.facets, cell_tags=self.tags)
+        rng = np.random.default_rng(seed)
+        self.u = scale * rng.standard_normal(self.F.N)
+        self.m = scale * rng.standard_normal(self.F.M)
+        self.bc = None
+        self.sp = solvers.StatePath(self.F, None)
+        self.nr, self.nth = nr, nth
+        if upload:
+            self.p.upload(0)
+            self.d_u = self.p.to_device(self.u)
+            self.d_m = self.p.to_device(self.m)
+            self.p.set_coefficient(0, self.d_u)
+            self.p.set_coefficient(1, self.d_m)
+
+    def radial_bc(self, frac=0.02):
+        """Prescribed displacement: the interior circle moves radially by `frac` of its radius."""
+        g = np.zeros(self.F.N)
+        nodes = self.mid * self.nth + np.arange(self.nth)
+        xy = self.omesh.coords[nodes]
+        g[2 * nodes], g[2 * nodes + 1] = frac * xy[:, 0], frac * xy[:, 1]
+        return g
+
+    csr = MotorCase.csr

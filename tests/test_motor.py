@@ -165,3 +165,71 @@ def test_gpu_motor_api_check_totals(cuda_device):
         assert abs(sim[name][0] - asm.assemble_scalar(F.output(k, x, sim['uhat']))) < 1e-7 * abs(sim[name][0])
     rep = sim.check_totals('B_influence_eddy_current', 'uhat', step=1e-7, directions=2, compact_print=False)
     assert max(rep.values()) < 1e-4, rep
+
+
+# ---------------------------------------------------------------------------------------------
+# config 5a: hyperelastic mesh motion
+# ---------------------------------------------------------------------------------------------
+def test_mm_layout_and_oracle_derivatives():
+    from _cases_motor import MotorMMCase
+    c = MotorMMCase(6, 18, upload=False)
+    F, uh, g = c.F, c.u, c.m
+    for which, blocks, shape in ((0, F.jacobian(uh, g), (F.N, F.N)), (1, F.dRdm(0, uh, g), (F.N, F.M))):
+        rp, col = c.p.pattern(which)
+        orp, ocol = asm.pattern(blocks, shape)
+        assert np.array_equal(rp, orp) and np.array_equal(col, ocol)
+    rng = np.random.default_rng(1)
+    du = rng.standard_normal(F.N)
+    R = lambda a, b: asm.assemble_vector(F.residual(a, b), F.N)
+    h = 1e-9
+    A = asm.assemble_matrix(F.jacobian(uh, g), (F.N, F.N))
+    fd = (R(uh + h * du, g) - R(uh - h * du, g)) / (2 * h)
+    assert np.abs(A @ du - fd).max() < 1e-7 * np.abs(fd).max()
+    D = asm.assemble_matrix(F.dRdm(0, uh, g), (F.N, F.M))
+    fd = (R(uh, g + h * du) - R(uh, g - h * du)) / (2 * h)
+    assert np.abs(D @ du - fd).max() < 1e-7 * np.abs(fd).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('nr,nth', [(4, 12), (8, 24)])
+def test_gpu_mm_assembly_matches_oracle(cuda_device, nr, nth):
+    from _cases_motor import MotorMMCase
+    c = MotorMMCase(nr, nth, seed=nr)
+    F, p = c.F, c.p
+    TOL = 1e-11
+    assert relerr(p.assemble_residual().cpu().numpy(), asm.assemble_vector(F.residual(c.u, c.m), F.N)) < TOL
+    vals, _ = p.assemble_jacobian()
+    assert relerr(vals.cpu().numpy(), asm.assemble_matrix(F.jacobian(c.u, c.m), (F.N, F.N)).data) < TOL
+    assert relerr(p.assemble_dRdm(0).cpu().numpy(), asm.assemble_matrix(F.dRdm(0, c.u, c.m), (F.N, F.M)).data) < TOL
+    for k in range(3):
+        Jo = asm.assemble_scalar(F.output(k, c.u, c.m))
+        assert abs(p.assemble_output(k) - Jo) <= TOL * abs(Jo)
+        assert relerr(p.assemble_output_grad(k, 0).cpu().numpy(), asm.assemble_vector(F.output_du(k, c.u, c.m), F.N)) < TOL
+        assert np.all(p.assemble_output_grad(k, 1).cpu().numpy() == 0.0)
+
+
+@pytest.mark.gpu
+def test_gpu_mm_state_and_adjoint(cuda_device):
+    """SNES + GMRES mesh-motion solve for a prescribed radial edge displacement (weak Nitsche BC), and the
+    adjoint derivative of the steel area w.r.t. the prescribed displacement, against the oracle."""
+    from _cases_motor import MotorMMCase
+    c = MotorMMCase(8, 24, seed=3)
+    p, F = c.p, c.F
+    g = c.radial_bc(0.02)
+    c.d_m.copy_(p.to_device(g))
+    c.d_u.zero_()
+    kw = dict(method=1, precond=1, cheb_degree=24, cheb_ratio=600.0)
+    info = p.newton_solve(kind='SNES', krylov_rtol=1e-12, krylov_max_it=40000, **kw)
+    xo, oinfo = c.sp.solve_snes(np.zeros(F.N), [g])
+    x = c.d_u.cpu().numpy()
+    assert info['converged'] in (1, 2, 3)
+    assert relerr(x, xo) < 1e-7
+    nodes = c.mid * c.nth + np.arange(c.nth)
+    assert np.abs(x[2 * nodes] - g[2 * nodes]).max() < 1e-3 * np.abs(g).max()      # weakly enforced
+    vals, _ = p.assemble_jacobian()
+    lam, li = p.linear_solve(vals, p.assemble_output_grad(2, 0), transpose=True, rtol=1e-12, max_it=40000, **kw)
+    assert li['converged']
+    gr = p.assemble_output_grad(2, 1).cpu().numpy() - p.spmv(1, p.assemble_dRdm(0), lam, transpose=True).cpu().numpy()
+    (go,), lamo = c.sp.total_derivative(2, xo, [g])
+    assert relerr(lam.cpu().numpy(), lamo) < 1e-6
+    assert relerr(gr, go) < 1e-6
