@@ -24,6 +24,7 @@ class FormFamily:
         self.method = 0              # 0 CG, 1 GMRES (non-symmetric families)
         self.krylov_extra = {}
         self.cell_tags = None
+        self.facets = None           # explicit one-sided facets (cells, locals)
         self._prob = None
         self._bc_sig = None
         self._ptrs = {}
@@ -65,13 +66,14 @@ class FormFamily:
     @property
     def problem(self):
         if self._prob is None:
-            p = _E.EngineProblem(self.mesh._e, self.family_id, self.params, self.tagged, cell_tags=self.cell_tags)
+            p = _E.EngineProblem(self.mesh._e, self.family_id, self.params, self.tagged, facets=self.facets,
+                                 cell_tags=self.cell_tags)
             # what replaces the reference's LU: GMG-preconditioned CG where a lattice hierarchy exists,
             # the explicit inverse for tiny systems, Jacobi-CG otherwise
             if self.family_id in (_E.FAMILY_POISSON_P1, _E.FAMILY_NLPOISSON_P1, _E.FAMILY_SIMP_Q1):
                 p.enable_multigrid()
                 self.precond = 2 if p.mg_levels > 1 else (3 if p.N <= 512 else 0)
-            elif self.family_id == _E.FAMILY_MOTOR_EM:
+            elif self.family_id in (_E.FAMILY_MOTOR_EM, _E.FAMILY_MOTOR_MM):
                 # non-symmetric Jacobian (nonlinear Nitsche coefficient): Chebyshev-preconditioned GMRES
                 self.method = 1
                 self.precond = 3 if p.N <= 512 else 1

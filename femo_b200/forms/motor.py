@@ -54,7 +54,7 @@ class JS:
 
 
 def B_power_form(A_z, uhat, n, dx, subdomains):
-    fam = next(iter(A_z.__dict__.get('_femo_families', {}).values()), None)
+    fam = next((f for f in A_z.__dict__.get('_femo_families', {}).values() if f.family_id == _E.FAMILY_MOTOR_EM), None)
     if fam is None:
         raise ValueError('B_power_form: build pdeResEM(...) first')
     if sorted(subdomains) != [1, 2]:
@@ -63,3 +63,64 @@ def B_power_form(A_z, uhat, n, dx, subdomains):
         return Form(fam, 'output', out_id=0)
     fam.set_param(20, float(n))
     return Form(fam, 'output', out_id=1)
+
+
+# --------------------------------------------------------------------------------------------
+# mesh motion (config 5a): pdeResMM :134-183, area_form :199-210
+# --------------------------------------------------------------------------------------------
+class SideMeasure:
+    """dS(tag) / ds(tag) stand-in carrying the tagged facets as ONE-SIDED (cell, local facet) pairs:
+    an interior facet contributes one pair per side, exactly how the "+" / "-" restrictions of the
+    reference's Nitsche terms act (motor_pde.py:170-178)."""
+
+    def __init__(self, cells, locals_):
+        self.sides = (np.asarray(cells, dtype=np.int32), np.asarray(locals_, dtype=np.int32))
+
+    def __call__(self, tag):
+        return self
+
+
+def annulus_circle_sides(mesh, ir):
+    """One-sided facets on the circle of radial node index `ir` of an annulus mesh (both sides inside)."""
+    nr, nth = mesh._e.shape
+    cells, locs = [], []
+    for it in range(nth):
+        if ir < nr:
+            cells.append(2 * (ir * nth + it) + 1)
+            locs.append(2)
+        if ir > 0:
+            cells.append(2 * ((ir - 1) * nth + it))
+            locs.append(0)
+    return np.asarray(cells, dtype=np.int32), np.asarray(locs, dtype=np.int32)
+
+
+def pdeResMM(uhat, duhat, g=None, nitsche=False, sym=False, overpenalty=False, dS_=None, ds_=None, cell_tags=None):
+    if not (nitsche and sym) or g is None:
+        raise NotImplementedError('mesh-motion family: the symmetric-Nitsche form of run_motor_opt.py:190-192')
+    sides = [m.sides for m in (dS_, ds_) if m is not None]
+    if not sides:
+        raise ValueError('pdeResMM: pass the tagged facet measures dS_(1000) / ds_(1000)')
+    fc = np.concatenate([s[0] for s in sides])
+    fl = np.concatenate([s[1] for s in sides])
+    o = np.lexsort((fl, fc))
+    fam = FormFamily.get(_E.FAMILY_MOTOR_MM, uhat.function_space.mesh, uhat, [g], params=[5e3])
+    fam.facets = (fc[o], fl[o])
+    if cell_tags is not None:
+        fam.cell_tags = np.asarray(cell_tags, dtype=np.int32)
+    return Form(fam, 'residual')
+
+
+def area_form(uhat, dx, subdomains):
+    """int det(F) dx over a subdomain group: [15] winding, [3] magnet, [1, 2] steel (run_motor_opt.py:176-181)."""
+    fam = next((f for f in uhat.__dict__.get('_femo_families', {}).values() if f.family_id == _E.FAMILY_MOTOR_MM), None)
+    if fam is None:
+        raise ValueError('area_form: build pdeResMM(...) first')
+    ids = sorted([subdomains] if isinstance(subdomains, int) else list(subdomains))
+    table = {(15,): 0, (3,): 1, (1, 2): 2}
+    if tuple(ids) not in table:
+        raise NotImplementedError('area_form: subdomain groups [15], [3] and [1, 2] have kernels')
+    if fam.cell_tags is None and dx is not None and dx.subdomain_data is not None:
+        tags = np.zeros(uhat.function_space.mesh.num_cells, dtype=np.int32)
+        tags[dx.subdomain_data.indices] = dx.subdomain_data.values
+        fam.cell_tags = tags
+    return Form(fam, 'output', out_id=table[tuple(ids)])

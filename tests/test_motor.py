@@ -233,3 +233,95 @@ def test_gpu_mm_state_and_adjoint(cuda_device):
     (go,), lamo = c.sp.total_derivative(2, xo, [g])
     assert relerr(lam.cpu().numpy(), lamo) < 1e-6
     assert relerr(gr, go) < 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_motor_coupled_chain_totals(cuda_device):
+    """examples/em_motor_opt/run_motor_opt.py end to end on the synthetic annulus: edge displacement uhat_bc ->
+    mesh motion uhat (incremental SNES) -> magnetostatics A_z (incremental SNES) -> B influence; the total
+    derivative w.r.t. uhat_bc chains the EM adjoint and the mesh-motion adjoint and is checked by FD."""
+    from femo_b200.fea.fea_b200 import FEA, Mesh, FunctionSpace, VectorFunctionSpace, Function, TestFunction, meshtags, Measure
+    from femo_b200.fea.utils_b200 import solveNonlinear, getFuncArray
+    from femo_b200.forms import motor as pde
+    from femo_b200.csdl_opt import FEAModel, Simulator
+    from femo_b200 import engine as E
+    nr, nth = 8, 24
+    mesh = Mesh(E.EngineMesh.annulus(nr, nth), 'triangle')
+    om_ = motor.annulus_tri(nr, nth)
+    tags = motor.motor_tags(om_)
+    dx = Measure('dx', domain=mesh, subdomain_data=meshtags(mesh, 2, np.arange(mesh.num_cells), tags))
+    mid = nr // 2
+    dS = pde.SideMeasure(*pde.annulus_circle_sides(mesh, mid))
+    c0, c1 = pde.annulus_circle_sides(mesh, 0), pde.annulus_circle_sides(mesh, nr)
+    ds = pde.SideMeasure(np.concatenate([c0[0], c1[0]]), np.concatenate([c0[1], c1[1]]))
+    Hc, p, s, vacuum_perm, angle, iq = 838.e3, 12, 36, 4e-7 * np.pi, 0., 282.2 / 0.00016231
+    VV = VectorFunctionSpace(mesh, ('CG', 1))
+    # ---- mesh motion subproblem (run_motor_opt.py:94-208)
+    fea_mm = FEA(mesh)
+    fea_mm.PDE_SOLVER, fea_mm.REPORT = 'SNES', False
+    uhat_bc, uhat = Function(VV), Function(VV)
+    res_mm = pde.pdeResMM(uhat, TestFunction(VV), g=uhat_bc, nitsche=True, sym=True, dS_=dS(1000), ds_=ds(1000),
+                          cell_tags=tags)
+
+    def solveIncremental(res, func, bc, report=False):
+        vec = np.copy(getFuncArray(uhat_bc))
+        STEPS = 2
+        func.vector.set(0.0)
+        for i in range(STEPS):
+            uhat_bc.vector.setArray(vec * (i + 1) / STEPS)
+            solveNonlinear(res, func, bc, 'SNES', False, False)
+        uhat_bc.vector.setArray(vec)
+    fea_mm.custom_solve = solveIncremental
+    fea_mm.add_input('uhat_bc', uhat_bc, init_val=0.0)
+    fea_mm.add_state(name='uhat', function=uhat, residual_form=res_mm, arguments=['uhat_bc'])
+    fea_mm.add_output(name='steel_area', type='scalar', form=pde.area_form(uhat, dx, [1, 2]), arguments=['uhat'])
+    # ---- electromagnetic subproblem (:212-317)
+    fea_em = FEA(mesh)
+    fea_em.PDE_SOLVER, fea_em.REPORT = 'SNES', False
+    V = FunctionSpace(mesh, ('CG', 1))
+    A_z = Function(V)
+    res_em = pde.pdeResEM(A_z, TestFunction(V), uhat, iq, dx, p, s, Hc, vacuum_perm, angle, g=Function(V), nitsche=True, sym=True)
+    js = pde.JS(res_em)
+
+    def solveIncrementalEM(res, func, bc, report=False):
+        func.vector.set(0.0)
+        for i in range(5):
+            js.set_scale((i + 1) / 5)
+            solveNonlinear(res, func, bc, 'SNES', False, False)
+    fea_em.custom_solve = solveIncrementalEM
+    fea_em.add_input('uhat', uhat, init_val=0.0)
+    fea_em.add_state(name='A_z', function=A_z, residual_form=res_em, arguments=['uhat'])
+    fea_em.add_output(name='B_influence_eddy_current', type='scalar', form=pde.B_power_form(A_z, uhat, 2, dx, [1, 2]),
+                      arguments=['A_z', 'uhat'])
+    model = FEAModel(fea=[fea_mm, fea_em], debug_mode=False)
+    g0 = np.zeros(2 * om_.nverts)
+    nodes = mid * nth + np.arange(nth)
+    xy = om_.coords[nodes]
+    g0[2 * nodes], g0[2 * nodes + 1] = 0.01 * xy[:, 0], 0.01 * xy[:, 1]
+    model.create_input('uhat_bc', shape=g0.size, val=g0)
+    sim = Simulator(model)
+    sim.run()
+    # forward values against the oracle chain
+    from oracle import motor_mm
+    parts = [motor_mm.circle_facets(om_, k) for k in (0, mid, nr)]
+    fc = np.concatenate([q[0] for q in parts]); fl = np.concatenate([q[1] for q in parts]); o = np.lexsort((fl, fc))
+    Fm = motor_mm.MotorMM(om_, (fc[o], fl[o]), tags)
+    spm = solvers.StatePath(Fm, None)
+    xm = np.zeros(Fm.N)
+    for st in (0.5, 1.0):
+        xm, _ = spm.solve_snes(xm, [st * g0])
+    assert relerr(sim['uhat'], xm) < 1e-7
+    Fe = motor.MotorEM(om_, tags)
+    spe = solvers.StatePath(Fe, None)
+    xe = np.zeros(Fe.N)
+    for st in range(1, 6):
+        Fe.js_scale = st / 5
+        xe, _ = spe.solve_snes(xe, [xm])
+    assert relerr(sim['A_z'], xe) < 1e-6
+    Bo = asm.assemble_scalar(Fe.output(0, xe, xm))
+    assert abs(sim['B_influence_eddy_current'][0] - Bo) < 1e-6 * abs(Bo)
+    # chained adjoint totals vs finite differences
+    rep = sim.check_totals('B_influence_eddy_current', 'uhat_bc', step=1e-7, directions=2, compact_print=False)
+    assert max(rep.values()) < 1e-3, rep
+    rep = sim.check_totals('steel_area', 'uhat_bc', step=1e-7, directions=2, compact_print=False)
+    assert max(rep.values()) < 1e-4, rep
