@@ -10,6 +10,8 @@ compute_derivatives, apply_inverse_jacobian('rev'), compute_jacvec_product('rev'
 """
 import numpy as np
 
+from .. import _hostops as _H
+
 try:                                    # pragma: no cover - csdl is absent in this image
     from csdl import Model, CustomImplicitOperation, CustomExplicitOperation   # noqa: F401
     import csdl                                                                 # noqa: F401
@@ -131,23 +133,35 @@ class Simulator:
     def __init__(self, model, analytics=False, **kw):
         model._ensure_defined()
         self.model = model
-        self.vars = {k: np.array(v, dtype=np.float64) for k, v in model.inputs.items()}
+        self.vars = {k: self._store(np.asarray(v, dtype=np.float64)) for k, v in model.inputs.items()}
         for op, args, out in model.ops:
             for a in args:
                 if a not in self.vars:
                     shape = op.input_meta[a]['shape']
                     d = model.declared.get(a)
                     val = d.val if d is not None else 1.0
-                    self.vars[a] = np.broadcast_to(np.asarray(val, dtype=np.float64), shape).copy()
-            self.vars.setdefault(out, np.zeros(op.output_meta[out]['shape']))
+                    self.vars[a] = self._store(np.broadcast_to(np.asarray(val, dtype=np.float64), shape))
+            if out not in self.vars:
+                self.vars[out] = self._store(np.zeros(op.output_meta[out]['shape']))
+        self._work = {}
+
+    @staticmethod
+    def _store(value):
+        """Variable storage: page-locked for large vectors so the operations' uploads are plain DMA."""
+        buf = _H.pinned_empty(value.size).reshape(value.shape)
+        np.copyto(buf, value)
+        return _H.tracked(buf)
+
+    def _buffer(self, tag, like):
+        buf = self._work.get(tag)
+        if buf is None or buf.shape != like.shape:
+            buf = self._work[tag] = _H.pinned_empty(like.size).reshape(like.shape)
+        return buf
 
     def _scratch(self, tag, like):
         """Zeroed work array reused across calls (the backend's d_inputs / d_residuals vectors)."""
-        buf = self.__dict__.setdefault('_work', {}).get(tag)
-        if buf is None or buf.shape != like.shape:
-            buf = self._work[tag] = np.zeros_like(like)
-        else:
-            buf.fill(0.0)
+        buf = self._buffer(tag, like)
+        _H.fill(buf, 0.0)
         return buf
 
     @staticmethod
@@ -155,11 +169,18 @@ class Simulator:
         return name.split('.')[-1]
 
     def __getitem__(self, name):
-        return self.vars[self._key(name)]
+        v = self.vars[self._key(name)]
+        v.bump()                                 # a writable reference leaves the simulator: assume it is written
+        return v
 
     def __setitem__(self, name, value):
         k = self._key(name)
-        np.copyto(self.vars[k], np.broadcast_to(np.asarray(value, dtype=np.float64), self.vars[k].shape))
+        value = np.asarray(value, dtype=np.float64)
+        if value.size == self.vars[k].size:
+            _H.copy(self.vars[k], value)
+        else:
+            np.copyto(self.vars[k], np.broadcast_to(value, self.vars[k].shape))
+        self.vars[k].bump()
 
     def run(self):
         for op, args, out in self.model.ops:
@@ -171,11 +192,13 @@ class Simulator:
                 op.compute(inputs, outputs)
             res = np.asarray(outputs[out], dtype=np.float64).reshape(self.vars[out].shape)
             if res is not self.vars[out]:
-                np.copyto(self.vars[out], res)       # CSDL copies on assignment
+                _H.copy(self.vars[out], res)         # CSDL copies on assignment
+            self.vars[out].bump()
 
     def compute_totals(self, of, wrt):
         """Reverse-mode totals d(of)/d(wrt) for scalar `of` (the adjoint chain of
-        SURVEY.md section 3.2-3.4)."""
+        SURVEY.md section 3.2-3.4).  The returned arrays are the simulator's own accumulation buffers:
+        valid until the next compute_totals call."""
         of = [of] if isinstance(of, str) else list(of)
         wrt = [wrt] if isinstance(wrt, str) else list(wrt)
         totals = {}
@@ -191,36 +214,36 @@ class Simulator:
                     if id(op) not in lin:
                         op.compute_derivatives(inputs, outputs, {})
                         lin[id(op)] = True
-                    d_res = {out: self._scratch('res:' + out, self.vars[out])}
+                    d_res = {}                               # assigned by the operation
                     op.apply_inverse_jacobian({out: bar[out]}, d_res, 'rev')
-                    d_in = {a: self._scratch('in:' + a, self.vars[a]) for a in args}
+                    d_in = {a: self._scratch('in:%s:%s' % (o, a), self.vars[a]) for a in args}
                     op.compute_jacvec_product(inputs, outputs, d_in, {}, {out: np.asarray(d_res[out])}, 'rev')
                     for a in args:
-                        if a in bar:
-                            bar[a] -= d_in[a]
-                        else:
-                            bar[a] = np.negative(d_in[a])
+                        self._accumulate(bar, o, a, d_in[a], -1.0)
                 elif hasattr(op, 'vjp'):
                     # vector-valued explicit operation with a constant Jacobian (declared sparse in CSDL)
                     for a in args:
-                        g = op.vjp(out, a, np.asarray(bar[out]))
-                        if a in bar:
-                            bar[a] += g
-                        else:
-                            bar[a] = np.array(g)
+                        self._accumulate(bar, o, a, op.vjp(out, a, np.asarray(bar[out])), 1.0)
                 else:
                     derivs = {}
                     op.compute_derivatives(inputs, derivs)
                     seed = float(np.ravel(bar[out])[0])
                     for a in args:
-                        g = np.ravel(derivs[out, a])
-                        if a in bar:
-                            bar[a] += seed * g
-                        else:
-                            bar[a] = seed * g if seed != 1.0 else np.array(g)
+                        self._accumulate(bar, o, a, np.ravel(derivs[out, a]), seed)
             for w in wrt:
-                totals[(o, w)] = np.array(bar.get(self._key(w), np.zeros_like(self.vars[self._key(w)])))
+                k = self._key(w)
+                totals[(o, w)] = bar[k] if k in bar else np.zeros_like(self.vars[k])
         return totals
+
+    def _accumulate(self, bar, o, a, g, scale):
+        """bar[a] (+)= scale * g in a reusable buffer (one per (output, variable))."""
+        g = np.ravel(np.asarray(g, dtype=np.float64))
+        if a in bar:
+            _H.iadd(bar[a], g, scale)
+        else:
+            buf = self._buffer('bar:%s:%s' % (o, a), g)
+            _H.scaled_copy(buf, g, scale)
+            bar[a] = buf
 
     def check_totals(self, of, wrt, step=1e-6, directions=3, seed=0, compact_print=True):
         """Directional finite-difference check of compute_totals (the reference's

@@ -3,10 +3,22 @@ boundary.  Callback names, argument meaning, assignment-vs-accumulation and the
 stateful hand-over between callbacks follow the reference's
 femo/csdl_opt/state_model.py (line numbers cited per method).
 """
+import numpy as np
+
 from ..fea.fea_b200 import FEA
 from ..fea.utils_b200 import (update, getFuncArray, assembleVector, assembleMatrix, assembleSystem, computePartials,
                               createFunction, computeMatVecProductFwd, computeMatVecProductBwd, setUpKSP_MUMPS)
 from ._csdl_compat import Model, CustomImplicitOperation, csdl
+from .. import _hostops as _H
+
+
+def _iadd(container, key, values):
+    """`container[key] += values` (state_model.py:180-199) without a single-threaded pass over large vectors."""
+    dst = container[key]
+    if isinstance(dst, np.ndarray):
+        _H.iadd(dst, values)
+    else:
+        container[key] = dst + values
 
 
 class StateModel(Model):
@@ -115,19 +127,19 @@ class StateOperation(CustomImplicitOperation):
             if name in d_residuals:
                 if name in d_outputs:
                     update(self.du, d_outputs[name])
-                    d_residuals[name] += computeMatVecProductFwd(self.dRdu, self.du)
+                    _iadd(d_residuals, name, computeMatVecProductFwd(self.dRdu, self.du))
                 for arg_name, entry in self.dRdf_dict.items():
                     if arg_name in d_inputs:
                         update(entry['df'], d_inputs[arg_name])
-                        d_residuals[name] += computeMatVecProductFwd(entry['dRdf'], entry['df'])
+                        _iadd(d_residuals, name, computeMatVecProductFwd(entry['dRdf'], entry['df']))
         if mode == 'rev':
             if name in d_residuals:
                 update(self.dR, d_residuals[name])
                 if name in d_outputs:
-                    d_outputs[name] += computeMatVecProductBwd(self.dRdu, self.dR)
+                    _iadd(d_outputs, name, computeMatVecProductBwd(self.dRdu, self.dR))
                 for arg_name, entry in self.dRdf_dict.items():
                     if arg_name in d_inputs:
-                        d_inputs[arg_name] += computeMatVecProductBwd(entry['dRdf'], self.dR)
+                        _iadd(d_inputs, arg_name, computeMatVecProductBwd(entry['dRdf'], self.dR))
 
     def apply_inverse_jacobian(self, d_outputs, d_residuals, mode):     # :202-218
         self._banner('apply_inverse_jacobian()...mode ' + str(mode))

@@ -14,6 +14,8 @@ used purely as buffers and are refreshed lazily.
 """
 import numpy as np
 
+from .. import _hostops as _H
+
 from .. import engine as _E
 
 
@@ -135,7 +137,7 @@ class Vector:
     array = property(getArray)
 
     def set(self, value):
-        self._f._assign(np.full(self._f.function_space.dim, float(np.ravel(value)[0])))
+        self._f._fill(float(np.ravel(value)[0]))
 
     def setArray(self, values):
         self._f._assign(values)
@@ -184,6 +186,7 @@ class Function:
         self._dev = None            # torch tensor on the problem's device (a buffer, nothing more)
         self._prob = None
         self._host_ver = 1          # bumped on every host write
+        self._src = None            # (address, version) of the tracked array these values came from
         self._dev_ver = 0           # host version the device copy mirrors (-1: device is newer)
         self.vector = Vector(self)
         self.x = _XView(self)
@@ -200,22 +203,44 @@ class Function:
 
     def _host_changed(self):
         self._host_ver += 1
+        self._src = None
+
+    def _fill(self, value):
+        self._src = None
+        if self._dev is not None:
+            self._dev.fill_(value)              # constant fields never cross PCIe
+            self._dev_ver = -1
+        else:
+            self._host.fill(value)
+            self._host_changed()
 
     def _assign(self, values):
+        ver = values.version if isinstance(values, _H.TrackedArray) else None
         v = np.asarray(values, dtype=np.float64).ravel()
         if v.size == 1:
-            self._host[:] = v[0]
+            return self._fill(float(v[0]))
         else:
+            src = (v.__array_interface__['data'][0], ver)
+            if ver is not None and src == self._src:
+                return                           # already holds exactly this version of that storage
             if v.size != self._host.size:
                 raise ValueError('size mismatch: function has %d dofs, got %d values' % (self._host.size, v.size))
             if v.__array_interface__['data'][0] != self._host.__array_interface__['data'][0]:
-                if v.size >= (1 << 20) and v.flags.c_contiguous:
-                    import torch                  # multi-threaded memcpy for large vectors
-                    torch.from_numpy(self._host).copy_(torch.from_numpy(v))
-                else:
-                    self._host[:] = v
+                if self._dev is not None and _H.is_pinned(v):
+                    # page-locked source (the backend's variable storage): DMA straight into the device
+                    # buffer; the host mirror is refreshed lazily if somebody reads it
+                    import torch
+                    self._dev.copy_(torch.from_numpy(v))
+                    self._dev_ver = -1
+                    if self._prob is not None:
+                        self._prob.h2d_bytes += v.nbytes
+                    self._src = src if ver is not None else None
+                    return
+                _H.copy(self._host, v)
         self._dev_ver = 0 if self._dev_ver == -1 else self._dev_ver
         self._host_changed()
+        if v.size != 1 and ver is not None:
+            self._src = src
 
     def device_tensor(self, prob):
         """Device buffer holding the current values (H2D copy if the host is newer)."""
@@ -235,6 +260,7 @@ class Function:
 
     def mark_device_written(self):
         self._dev_ver = -1
+        self._src = None
 
     # -- dolfinx-like surface ----------------------------------------------
     def interpolate(self, fn):

@@ -174,7 +174,7 @@ def assembleSystem(J, F, bcs=[], rhs=True):
     else:
         vals, _ = p.assemble_jacobian(plain=True, bc=False)
         A = Mat(fam, 0, vals)
-        A.plain = A
+        A.plain = Mat(fam, 0, vals)       # same values, no reference cycle (frees promptly)
     if not rhs:
         return A, None
     b = p.system_rhs(vals) if bcs else p.assemble_residual()
