@@ -11,6 +11,7 @@
 #include "families3.cuh"
 #include "families4.cuh"
 #include "families5.cuh"
+#include "families6.cuh"
 #include "dist.cuh"
 
 namespace femo {
@@ -181,12 +182,30 @@ __global__ void __launch_bounds__(kThreads)
                 }
             }
             __syncthreads();
-            for (int i = tid; i < nr; i += kThreads) {
-                double acc = 0.0;
-                for (int32_t k = rp[i] - s; k < rp[i + 1] - s; ++k) acc += prod[k];
-                const double xi = (DOT || EPI == EPI_CHEBK) ? __ldg(x + r0 + i) : 0.0;
-                spmv_row_epilogue<EPI>(E, r0 + i, acc, xi, y);
-                if (DOT && r0 + i >= E.own0 && r0 + i < E.own1) dot += acc * xi;
+            if (e - s < 24 * nr) {             // short rows (P1 / Q1 scalar stencils): one thread per row
+                for (int i = tid; i < nr; i += kThreads) {
+                    double acc = 0.0;
+                    for (int32_t k = rp[i] - s; k < rp[i + 1] - s; ++k) acc += prod[k];
+                    const double xi = (DOT || EPI == EPI_CHEBK) ? __ldg(x + r0 + i) : 0.0;
+                    spmv_row_epilogue<EPI>(E, r0 + i, acc, xi, y);
+                    if (DOT && r0 + i >= E.own0 && r0 + i < E.own1) dot += acc * xi;
+                }
+            } else {                           // long rows (vector states in 3-D: 81 entries): 8 lanes per row,
+                constexpr int L = 8;           // strided partial sums + fixed butterfly => still deterministic
+                const int sub = tid & (L - 1);
+                for (int base = 0; base < nr; base += kThreads / L) {
+                    const int i = base + tid / L;
+                    double acc = 0.0;
+                    if (i < nr)
+                        for (int32_t k = rp[i] - s + sub; k < rp[i + 1] - s; k += L) acc += prod[k];
+#pragma unroll
+                    for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (sub == 0 && i < nr) {
+                        const double xi = (DOT || EPI == EPI_CHEBK) ? __ldg(x + r0 + i) : 0.0;
+                        spmv_row_epilogue<EPI>(E, r0 + i, acc, xi, y);
+                        if (DOT && r0 + i >= E.own0 && r0 + i < E.own1) dot += acc * xi;
+                    }
+                }
             }
         } else {  // a single long row: CTA-wide strided reduction (fixed order)
             double acc = 0.0;
@@ -347,6 +366,29 @@ static QuadArgs quad_args(femo_problem *p, int out_id, double *out) {
     return A;
 }
 
+static HexArgs hex_args(femo_problem *p, int out_id, double *out) {
+    HexArgs A;
+    A.coords = p->d_coords; A.cellsT = p->d_cellsT; A.ncells = p->mesh.ncells;
+    A.fb_cell = p->d_fb_cell; A.fb_local = p->d_fb_local; A.nfacets = (int64_t)p->fb_cell.size();
+    A.u = p->coef[0]; A.rho = p->coef[1];
+    A.nu = p->params[0]; A.f[0] = p->params[1]; A.f[1] = p->params[2]; A.f[2] = p->params[3]; A.penal = p->params[4];
+    A.volume = (p->mesh.hi[0] - p->mesh.lo[0]) * (p->mesh.hi[1] - p->mesh.lo[1]) * (p->mesh.hi[2] - p->mesh.lo[2]);
+    A.out_id = out_id; A.out = out;
+    return A;
+}
+
+// the hexahedron cell kernel stages 32 cells' gradients in > 48 KB of dynamic shared memory
+template <int OP>
+static void launch_hex_cell(const HexArgs &A, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_simp_hex_cell<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHexSmem);
+        configured = true;
+    }
+    const int grid = (int)((A.ncells + kHexCells - 1) / kHexCells);
+    k_simp_hex_cell<OP><<<grid, kThreads, kHexSmem, st>>>(A);
+}
+
 // number of scratch planes per entity of an op
 static int op_planes(const femo_problem *p, int op) {
     const int nd = p->state.ndpc;
@@ -369,6 +411,7 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
     if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
     const bool analytic_src = p->family == FEMO_FAMILY_MASS_P1 && p->params[1] < 1.5;
     const bool jac_reads_input = p->family == FEMO_FAMILY_SIMP_Q1 || p->family == FEMO_FAMILY_EB_BEAM ||
+                                 p->family == FEMO_FAMILY_SIMP_HEX8 ||
                                  p->family == FEMO_FAMILY_MOTOR_EM || p->family == FEMO_FAMILY_MOTOR_MM;
     if ((op != OP_JAC || jac_reads_input) && !analytic_src && (rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
     double *cells_out = p->d_scratch;
@@ -498,6 +541,28 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
                 if (op == OP_RES) k_simp_q1_facet<OP_RES><<<gf, kThreads, 0, st>>>(F);
                 else if (op == OP_OUT) k_simp_q1_facet<OP_OUT><<<gf, kThreads, 0, st>>>(F);
                 else k_simp_q1_facet<OP_OUT_DU><<<gf, kThreads, 0, st>>>(F);
+                p->launches++;
+            }
+            break;
+        }
+        case FEMO_FAMILY_SIMP_HEX8: {
+            if (mask & 1) {
+                HexArgs A = hex_args(p, out_id, cells_out);
+                switch (op) {
+                    case OP_RES: launch_hex_cell<OP_RES>(A, st); break;
+                    case OP_JAC: launch_hex_cell<OP_JAC>(A, st); break;
+                    case OP_DRDM: launch_hex_cell<OP_DRDM>(A, st); break;
+                    case OP_OUT: launch_hex_cell<OP_OUT>(A, st); break;
+                    case OP_OUT_DM: launch_hex_cell<OP_OUT_DM>(A, st); break;
+                    default: return set_err(FEMO_EINVAL, "hex SIMP family: no cell term for this operation");
+                }
+                p->launches++;
+            }
+            if ((mask & 2) && nf > 0) {
+                HexArgs F = hex_args(p, out_id, facets_out);
+                if (op == OP_RES) k_simp_hex_facet<OP_RES><<<gf, kThreads, 0, st>>>(F);
+                else if (op == OP_OUT) k_simp_hex_facet<OP_OUT><<<gf, kThreads, 0, st>>>(F);
+                else k_simp_hex_facet<OP_OUT_DU><<<gf, kThreads, 0, st>>>(F);
                 p->launches++;
             }
             break;
@@ -642,6 +707,14 @@ int femo_mesh_create_rectangle_quad(int nx, int ny, const double lo[2], const do
     *out = m;
     return FEMO_OK;
 }
+int femo_mesh_create_box_hex(int nx, int ny, int nz, const double lo[3], const double hi[3], femo_mesh **out) {
+    if (!out || nx < 1 || ny < 1 || nz < 1 || !lo || !hi) return set_err(FEMO_EINVAL, "femo_mesh_create_box_hex: bad arguments");
+    if ((int64_t)(nx + 1) * (ny + 1) * (nz + 1) * 3 > 2147483647LL) return set_err(FEMO_ELIMIT, "mesh exceeds int32 dofs");
+    femo_mesh *m = new femo_mesh();
+    make_box_hex(nx, ny, nz, lo, hi, m->m);
+    *out = m;
+    return FEMO_OK;
+}
 int femo_mesh_create_annulus(int nr, int nth, double r0, double r1, femo_mesh **out) {
     if (!out || nr < 1 || nth < 3 || !(r1 > r0) || !(r0 > 0)) return set_err(FEMO_EINVAL, "femo_mesh_create_annulus: bad arguments");
     femo_mesh *m = new femo_mesh();
@@ -765,13 +838,24 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
                 p->out_mask[0] = 1; p->out_du_mask[0] = 0; p->out_dm_mask[0] = 1;   // average density
                 p->out_mask[1] = 2; p->out_du_mask[1] = 2; p->out_dm_mask[1] = 0;   // compliance
                 break;
+            case FEMO_FAMILY_SIMP_HEX8:
+                if (M.kind != MESH_HEX) throw LayoutError{FEMO_EINVAL, "family needs a hexahedral mesh"};
+                p->state.init(M, EL_VERTEX, 3);
+                p->nin = 1;
+                p->in[0].init(M, EL_DG0, 1);
+                p->nout = 2;
+                if (nparams < 5) { p->params[0] = 0.3; p->params[1] = 0.0; p->params[2] = -0.25; p->params[3] = 0.0; p->params[4] = 3.0; }
+                p->res_mask = 3;                               // cells + traction ds(100)
+                p->out_mask[0] = 1; p->out_du_mask[0] = 0; p->out_dm_mask[0] = 1;   // average density
+                p->out_mask[1] = 2; p->out_du_mask[1] = 2; p->out_dm_mask[1] = 0;   // compliance
+                break;
             default:
                 throw LayoutError{FEMO_EINVAL, "unknown form family"};
         }
         // block 2: all exterior facets (Nitsche) or the tagged subset (ds(tag) of the examples)
         if (fcell && flocal) {                       // explicit one-sided facets (cell, local facet)
             for (int k = 0; k < nfl; ++k) {
-                if (fcell[k] < 0 || fcell[k] >= M.ncells || flocal[k] < 0 || flocal[k] >= M.nvpc)
+                if (fcell[k] < 0 || fcell[k] >= M.ncells || flocal[k] < 0 || flocal[k] >= (M.kind == MESH_HEX ? 6 : M.nvpc))
                     throw LayoutError{FEMO_EINVAL, "facet (cell, local) out of range"};
                 p->fb_cell.push_back(fcell[k]);
                 p->fb_local.push_back(flocal[k]);
@@ -956,18 +1040,28 @@ int femo_problem_enable_multigrid(femo_problem *p) {
     if (!p->mesh.lattice) return set_err(FEMO_EINVAL, "multigrid needs a lattice mesh");
     const bool tri = p->mesh.kind == MESH_TRI && p->state.element == EL_VERTEX && p->state.block == 1;
     const bool quad = p->mesh.kind == MESH_QUAD && p->state.element == EL_VERTEX;
-    if (!tri && !quad)
-        return set_err(FEMO_EINVAL, "multigrid is available for vertex-based states on lattice triangle / quadrilateral meshes");
+    const bool hex = p->mesh.kind == MESH_HEX && p->state.element == EL_VERTEX;
+    if (!tri && !quad && !hex)
+        return set_err(FEMO_EINVAL, "multigrid is available for vertex-based states on lattice triangle / quadrilateral / hexahedral meshes");
     if (!p->mg.empty()) return FEMO_OK;
     if (p->slab.active) return enable_multigrid_slab(p);
-    int nx = p->mesh.n[0], ny = p->mesh.n[1];
+    int nx = p->mesh.n[0], ny = p->mesh.n[1], nz = p->mesh.n[2];
     // coarsen until the coarsest system fits the explicit inverse (<= 512 dofs)
-    const int coarsest = (p->state.block > 1) ? 6 : kMgCoarsest;
-    while (nx > coarsest || ny > coarsest) {
-        if (nx > coarsest) nx = (nx + 1) / 2;
-        if (ny > coarsest) ny = (ny + 1) / 2;
+    const int coarsest = hex ? 4 : ((p->state.block > 1) ? 6 : kMgCoarsest);
+    while (nx > coarsest || ny > coarsest || nz > coarsest ||
+           (hex && (int64_t)(nx + 1) * (ny + 1) * (nz + 1) * p->state.block > kMgDenseMax)) {
+        if (hex) {   // halve every direction that still can be
+            if (nx == 1 && ny == 1 && nz == 1) break;
+            nx = std::max(1, (nx + 1) / 2);
+            ny = std::max(1, (ny + 1) / 2);
+            nz = std::max(1, (nz + 1) / 2);
+        } else {
+            if (nx > coarsest) nx = (nx + 1) / 2;
+            if (ny > coarsest) ny = (ny + 1) / 2;
+        }
         Mesh cm;
-        if (quad) make_rectangle_quad(nx, ny, p->mesh.lo, p->mesh.hi, cm);
+        if (hex) make_box_hex(nx, ny, nz, p->mesh.lo, p->mesh.hi, cm);
+        else if (quad) make_rectangle_quad(nx, ny, p->mesh.lo, p->mesh.hi, cm);
         else make_unit_square_tri(nx, ny, p->mesh.lo, p->mesh.hi, cm);
         femo_problem *c = nullptr;
         int rc = create_problem_impl(cm, p->family, p->params, 32, true, nullptr, 0, &c);
@@ -1075,15 +1169,18 @@ static int propagate_bc(femo_problem *root, int start) {
         const int fnx = F->mesh.n[0], fny = F->mesh.n[1], cnx = C->mesh.n[0], cny = C->mesh.n[1];
         const int fj0 = F->slab.active ? F->slab.crow0 : 0, cj0 = C->slab.active ? C->slab.crow0 : 0;
         const int fg = F->slab.active ? F->slab.gny : fny, cg = C->slab.active ? C->slab.gny : cny;
+        const int fnz = F->mesh.n[2], cnz = C->mesh.n[2];                          // 0 on planar lattices
+        for (int K = 0; K <= cnz; ++K)
         for (int J = 0; J <= cny; ++J)
             for (int I = 0; I <= cnx; ++I) {
                 const int i = (int)std::llround((double)I * fnx / cnx);
                 int j = (int)std::llround((double)(J + cj0) * fg / cg) - fj0;     // nearest fine row, local index
                 j = std::min(std::max(j, 0), fny);                                 // ghost rows without a local parent: same column
+                const int k = cnz ? (int)std::llround((double)K * fnz / cnz) : 0;
                 const int bs = F->state.block;
                 for (int cc = 0; cc < bs; ++cc)
-                    if (!F->bc_mark.empty() && F->bc_mark[((int64_t)j * (fnx + 1) + i) * bs + cc])
-                        list.push_back((J * (cnx + 1) + I) * bs + cc);
+                    if (!F->bc_mark.empty() && F->bc_mark[(((int64_t)k * (fny + 1) + j) * (fnx + 1) + i) * bs + cc])
+                        list.push_back((int32_t)((((int64_t)K * (cny + 1) + J) * (cnx + 1) + I) * bs + cc));
             }
         int32_t ptr[2] = {0, (int32_t)list.size()};
         int rc = set_bc_impl(C, list.data(), ptr, list.empty() ? 0 : 1, nullptr);

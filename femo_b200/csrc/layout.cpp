@@ -88,6 +88,43 @@ void make_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2],
         }
 }
 
+void make_box_hex(int nx, int ny, int nz, const double lo[3], const double hi[3], Mesh &m) {
+    m = Mesh();
+    m.kind = MESH_HEX;
+    m.nvpc = 8;
+    m.gdim = 3;
+    m.n[0] = nx; m.n[1] = ny; m.n[2] = nz;
+    for (int d = 0; d < 3; ++d) { m.lo[d] = lo[d]; m.hi[d] = hi[d]; }
+    const int64_t sx = nx + 1, sy = ny + 1;
+    m.nverts = sx * sy * (nz + 1);
+    m.ncells = (int64_t)nx * ny * nz;
+    m.coords.resize(m.nverts * 3);
+    for (int iz = 0; iz <= nz; ++iz)
+        for (int iy = 0; iy <= ny; ++iy)
+            for (int ix = 0; ix <= nx; ++ix) {
+                const int64_t v = ((int64_t)iz * sy + iy) * sx + ix;
+                m.coords[3 * v] = lo[0] + (hi[0] - lo[0]) * (double)ix / (double)nx;
+                m.coords[3 * v + 1] = lo[1] + (hi[1] - lo[1]) * (double)iy / (double)ny;
+                m.coords[3 * v + 2] = lo[2] + (hi[2] - lo[2]) * (double)iz / (double)nz;
+            }
+    m.cells.resize(m.ncells * 8);
+    for (int iz = 0; iz < nz; ++iz)
+        for (int iy = 0; iy < ny; ++iy)
+            for (int ix = 0; ix < nx; ++ix) {
+                const int64_t c = ((int64_t)iz * ny + iy) * nx + ix;
+                const int64_t v0 = ((int64_t)iz * sy + iy) * sx + ix;
+                int32_t *a = &m.cells[c * 8];
+                for (int k = 0; k < 8; ++k)
+                    a[k] = (int32_t)(v0 + (k & 1) + ((k >> 1) & 1) * sx + ((k >> 2) & 1) * sx * sy);
+                if (iz == 0)      { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(0); }
+                if (iy == 0)      { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(1); }
+                if (ix == 0)      { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(2); }
+                if (ix == nx - 1) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(3); }
+                if (iy == ny - 1) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(4); }
+                if (iz == nz - 1) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(5); }
+            }
+}
+
 void make_annulus_tri(int nr, int nth, double r0, double r1, Mesh &m) {
     m = Mesh();
     m.kind = MESH_TRI;

@@ -14,7 +14,7 @@
 
 namespace femo {
 
-enum MeshKind { MESH_INTERVAL = 1, MESH_TRI = 2, MESH_QUAD = 3 };
+enum MeshKind { MESH_INTERVAL = 1, MESH_TRI = 2, MESH_QUAD = 3, MESH_HEX = 4 };
 enum Element { EL_DG0 = 0, EL_VERTEX = 1 /* P1 / Q1: one node per vertex */, EL_HERMITE3 = 2 };
 
 struct Mesh {
@@ -38,6 +38,10 @@ void make_unit_square_tri(int nx, int ny, const double lo[2], const double hi[2]
 void make_unit_square_tri_slab(int nx, int gny, int row0, int nrows, const double lo[2], const double hi[2], Mesh &m);
 void make_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2], Mesh &m);
 void make_interval(int n, double x0, double x1, Mesh &m);
+// (nx x ny x nz)-cell hexahedral lattice on the box [lo,hi]: vertex (ix,iy,iz) -> (iz*(ny+1)+iy)*(nx+1)+ix,
+// cell (ix,iy,iz) -> (iz*ny+iy)*nx+ix with the tensor-product vertex order of basix (x fastest) and
+// facets 0 z=lo, 1 y=lo, 2 x=lo, 3 x=hi, 4 y=hi, 5 z=hi [upstream, from memory]
+void make_box_hex(int nx, int ny, int nz, const double lo[3], const double hi[3], Mesh &m);
 // periodic polar lattice on the annulus r0 <= r <= r1: node (ir, ith) -> ir*nth + ith
 void make_annulus_tri(int nr, int nth, double r0, double r1, Mesh &m);
 

@@ -119,6 +119,109 @@ __global__ void __launch_bounds__(kThreads)
     rc[idx] = cnt ? pow(acc / cnt, 1.0 / p) : 1.0;
 }
 
+// ---- hexahedral lattices (trilinear Q1), same conventions in three dimensions ---------------------
+struct Lattice3 {
+    int nx, ny, nz;  // cells per direction; node id = (k*(ny+1)+j)*(nx+1)+i
+};
+static inline Lattice3 lat3_of(const Mesh &m) { return Lattice3{m.n[0], m.n[1], m.n[2]}; }
+
+__device__ __forceinline__ double hat_1d(double d) {
+    const double a = 1.0 - fabs(d);
+    return a > 0.0 ? a : 0.0;
+}
+
+template <bool ADD>
+__global__ void __launch_bounds__(kThreads)
+    k_lattice3_interp(Lattice3 s, Lattice3 d, int block, const double *__restrict__ src, double *__restrict__ dst,
+                      const uint8_t *__restrict__ dst_mask) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nd = (int64_t)(d.nx + 1) * (d.ny + 1) * (d.nz + 1) * block;
+    if (idx >= nd) return;
+    if (dst_mask && dst_mask[idx]) {
+        if (!ADD) dst[idx] = 0.0;
+        return;
+    }
+    const int64_t node = idx / block;
+    const int comp = (int)(idx % block);
+    const int i = (int)(node % (d.nx + 1)), j = (int)((node / (d.nx + 1)) % (d.ny + 1)), k = (int)(node / ((int64_t)(d.nx + 1) * (d.ny + 1)));
+    const double X = (double)i * ((double)s.nx / (double)d.nx), Y = (double)j * ((double)s.ny / (double)d.ny),
+                 Z = (double)k * ((double)s.nz / (double)d.nz);
+    const int I = min((int)X, s.nx - 1), J = min((int)Y, s.ny - 1), K = min((int)Z, s.nz - 1);
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const double w = hat_1d(X - (double)(I + a)) * hat_1d(Y - (double)(J + b)) * hat_1d(Z - (double)(K + c));
+                if (w > 0.0) acc += w * src[(((int64_t)(K + c) * (s.ny + 1) + (J + b)) * (s.nx + 1) + (I + a)) * block + comp];
+            }
+    if (ADD) dst[idx] += acc;
+    else dst[idx] = acc;
+}
+
+// rc = P^T rf with the weights of k_lattice3_interp<coarse -> fine>
+__global__ void __launch_bounds__(kThreads)
+    k_lattice3_restrict(Lattice3 f, Lattice3 c, int block, const double *__restrict__ rf, double *__restrict__ rc,
+                        const uint8_t *__restrict__ mask_f, const uint8_t *__restrict__ mask_c) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nc = (int64_t)(c.nx + 1) * (c.ny + 1) * (c.nz + 1) * block;
+    if (idx >= nc) return;
+    if (mask_c && mask_c[idx]) {
+        rc[idx] = 0.0;
+        return;
+    }
+    const int64_t node = idx / block;
+    const int comp = (int)(idx % block);
+    const int I = (int)(node % (c.nx + 1)), J = (int)((node / (c.nx + 1)) % (c.ny + 1)), K = (int)(node / ((int64_t)(c.nx + 1) * (c.ny + 1)));
+    const double sx = (double)c.nx / (double)f.nx, sy = (double)c.ny / (double)f.ny, sz = (double)c.nz / (double)f.nz;
+    const int ilo = max(0, (int)floor((double)(I - 1) / sx)), ihi = min(f.nx, (int)ceil((double)(I + 1) / sx));
+    const int jlo = max(0, (int)floor((double)(J - 1) / sy)), jhi = min(f.ny, (int)ceil((double)(J + 1) / sy));
+    const int klo = max(0, (int)floor((double)(K - 1) / sz)), khi = min(f.nz, (int)ceil((double)(K + 1) / sz));
+    double acc = 0.0;
+    for (int k = klo; k <= khi; ++k) {
+        const double Z = (double)k * sz;
+        const int K0 = min((int)Z, c.nz - 1);
+        if (K < K0 || K > K0 + 1) continue;
+        const double wz = hat_1d(Z - (double)K);
+        for (int j = jlo; j <= jhi; ++j) {
+            const double Y = (double)j * sy;
+            const int J0 = min((int)Y, c.ny - 1);
+            if (J < J0 || J > J0 + 1) continue;
+            const double wy = hat_1d(Y - (double)J);
+            for (int i = ilo; i <= ihi; ++i) {
+                const double X = (double)i * sx;
+                const int I0 = min((int)X, c.nx - 1);
+                if (I < I0 || I > I0 + 1) continue;
+                const double w = hat_1d(X - (double)I) * wy * wz;
+                const int64_t fi = (((int64_t)k * (f.ny + 1) + j) * (f.nx + 1) + i) * block + comp;
+                if (w > 0.0 && !(mask_f && mask_f[fi])) acc += w * rf[fi];
+            }
+        }
+    }
+    rc[idx] = acc;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_restrict_cells_power3(Lattice3 f, Lattice3 c, double p, const double *__restrict__ rf, double *__restrict__ rc) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)c.nx * c.ny * c.nz) return;
+    const int I = (int)(idx % c.nx), J = (int)((idx / c.nx) % c.ny), K = (int)(idx / ((int64_t)c.nx * c.ny));
+    const int i0 = (int)ceil(((double)I * f.nx) / c.nx - 0.5), i1 = (int)ceil(((double)(I + 1) * f.nx) / c.nx - 0.5);
+    const int j0 = (int)ceil(((double)J * f.ny) / c.ny - 0.5), j1 = (int)ceil(((double)(J + 1) * f.ny) / c.ny - 0.5);
+    const int k0 = (int)ceil(((double)K * f.nz) / c.nz - 0.5), k1 = (int)ceil(((double)(K + 1) * f.nz) / c.nz - 0.5);
+    double acc = 0.0;
+    int cnt = 0;
+    for (int k = max(k0, 0); k < min(k1, f.nz); ++k)
+        for (int j = max(j0, 0); j < min(j1, f.ny); ++j)
+            for (int i = max(i0, 0); i < min(i1, f.nx); ++i) {
+                acc += pow(rf[((int64_t)k * f.ny + j) * f.nx + i], p);
+                ++cnt;
+            }
+    rc[idx] = cnt ? pow(acc / cnt, 1.0 / p) : 1.0;
+}
+
 // 2:1 nested lattices (the common case), integer-only, slab aware.  A local lattice holds node rows
 // [j0, j0+nrows) of the global lattice; prolongation / restriction / injection address the other
 // level through GLOBAL row indices, so the same kernels serve one GPU (j0 = 0), two distributed
@@ -437,7 +540,10 @@ static int mg_restrict(femo_problem *L, femo_problem *C, double *rf, double *rc_
             if ((rc = gather_rows(L, rc_, (size_t)(C->mesh.n[0] + 1), C->mesh.n[1]))) return rc;
     } else {
         if (L->slab.active) return set_err(FEMO_ESTATE, "distributed multigrid levels must be 2:1 nested");
-        k_lattice_restrict<<<grid_for(nc), kThreads, 0, st>>>(Lattice{L->mesh.n[0], L->mesh.n[1]}, Lattice{C->mesh.n[0], C->mesh.n[1]}, L->state.block, L->mesh.kind == MESH_QUAD, rf, rc_, mf, mc);
+        if (L->mesh.kind == MESH_HEX)
+            k_lattice3_restrict<<<grid_for(nc), kThreads, 0, st>>>(lat3_of(L->mesh), lat3_of(C->mesh), L->state.block, rf, rc_, mf, mc);
+        else
+            k_lattice_restrict<<<grid_for(nc), kThreads, 0, st>>>(Lattice{L->mesh.n[0], L->mesh.n[1]}, Lattice{C->mesh.n[0], C->mesh.n[1]}, L->state.block, L->mesh.kind == MESH_QUAD, rf, rc_, mf, mc);
         L->launches++;
     }
     FEMO_CHECK_LAUNCH();
@@ -452,6 +558,8 @@ static int mg_prolong_add(femo_problem *L, femo_problem *C, double *xc, double *
     if (nested_pair(L, C)) {
         if ((rc = halo_nodes(C, xc))) return rc;                   // fine owned rows read the coarse ghost row above
         k_prolong_nested<<<grid_for(n), kThreads, 0, st>>>(latd_of(L), latd_of(C), xc, xf, mf);
+    } else if (L->mesh.kind == MESH_HEX) {
+        k_lattice3_interp<true><<<grid_for(n), kThreads, 0, st>>>(lat3_of(C->mesh), lat3_of(L->mesh), L->state.block, xc, xf, mf);
     } else {
         k_lattice_interp<true><<<grid_for(n), kThreads, 0, st>>>(Lattice{C->mesh.n[0], C->mesh.n[1]}, Lattice{L->mesh.n[0], L->mesh.n[1]}, L->state.block, L->mesh.kind == MESH_QUAD, xc, xf, mf);
     }
@@ -564,11 +672,23 @@ static int mg_setup(femo_problem *root, const double *vals) {
                 }
             } else {
                 if (F->slab.active) return set_err(FEMO_ESTATE, "distributed multigrid levels must be 2:1 nested");
-                k_lattice_interp<false><<<grid_for(n), kThreads, 0, st>>>(Lattice{F->mesh.n[0], F->mesh.n[1]}, Lattice{L->mesh.n[0], L->mesh.n[1]}, L->state.block, L->mesh.kind == MESH_QUAD, uf, M.u, nullptr);
+                if (L->mesh.kind == MESH_HEX)
+                    k_lattice3_interp<false><<<grid_for(n), kThreads, 0, st>>>(lat3_of(F->mesh), lat3_of(L->mesh), L->state.block, uf, M.u, nullptr);
+                else
+                    k_lattice_interp<false><<<grid_for(n), kThreads, 0, st>>>(Lattice{F->mesh.n[0], F->mesh.n[1]}, Lattice{L->mesh.n[0], L->mesh.n[1]}, L->state.block, L->mesh.kind == MESH_QUAD, uf, M.u, nullptr);
                 L->launches++;
             }
             L->coef[0] = M.u;
             L->coefn[0] = n;
+            if (L->family == FEMO_FAMILY_SIMP_HEX8) {
+                const double *mf_ = (lv == 1) ? root->coef[1] : F->mgl.m;
+                if (!mf_) return set_err(FEMO_ESTATE, "multigrid setup: density coefficient not set");
+                const int64_t ncell = L->mesh.ncells;
+                k_restrict_cells_power3<<<grid_for(ncell), kThreads, 0, st>>>(lat3_of(F->mesh), lat3_of(L->mesh), L->params[4], mf_, M.m);
+                L->launches++;
+                L->coef[1] = M.m;
+                L->coefn[1] = ncell;
+            }
             if (L->family == FEMO_FAMILY_SIMP_Q1) {   // coarse density for the rediscretised stiffness
                 const double *mf_ = (lv == 1) ? root->coef[1] : F->mgl.m;
                 if (!mf_) return set_err(FEMO_ESTATE, "multigrid setup: density coefficient not set");

@@ -16,6 +16,7 @@ FAMILY_SIMP_Q1 = 4
 FAMILY_MASS_P1 = 5
 FAMILY_MOTOR_MM = 6
 FAMILY_MOTOR_EM = 7
+FAMILY_SIMP_HEX8 = 8
 
 
 def device_count():
@@ -50,6 +51,14 @@ class EngineMesh:
         check(lib.femo_mesh_create_rectangle_quad(int(nx), int(ny), (C.c_double * 2)(*lo), (C.c_double * 2)(*hi), C.byref(h)))
         m = cls(h)
         m.shape, m.lo, m.hi = (nx, ny), tuple(lo), tuple(hi)
+        return m
+
+    @classmethod
+    def box_hex(cls, lo, hi, nx, ny, nz):
+        h = C.c_void_p()
+        check(lib.femo_mesh_create_box_hex(int(nx), int(ny), int(nz), (C.c_double * 3)(*lo), (C.c_double * 3)(*hi), C.byref(h)))
+        m = cls(h)
+        m.shape, m.lo, m.hi = (nx, ny, nz), tuple(lo), tuple(hi)
         return m
 
     @classmethod

@@ -45,6 +45,7 @@ typedef struct femo_problem femo_problem;
 #define FEMO_FAMILY_EB_BEAM 3      /* examples/beam_thickness_opt/run_thickness_opt_cantilever_beam.py:71-85 */
 #define FEMO_FAMILY_SIMP_Q1 4      /* examples/beam_topo_opt/run_topo_opt_cantilever_beam.py:62-86 */
 #define FEMO_FAMILY_MOTOR_MM 6     /* examples/em_motor_opt/motor_pde.py:134-183,199-210 (hyperelastic mesh motion, Nitsche on dS/ds(1000)) */
+#define FEMO_FAMILY_SIMP_HEX8 8    /* 3-D extension of examples/beam_topo_opt/run_topo_opt_cantilever_beam.py:62-86 on trilinear hexahedra; params nu, fx, fy, fz, penal */
 #define FEMO_FAMILY_MOTOR_EM 7     /* examples/em_motor_opt/motor_pde.py:12-130,186-197 (nonlinear magnetostatics on a moving mesh) */
 #define FEMO_FAMILY_MASS_P1 5      /* L2 projection, femo/fea/utils_dolfinx.py:549-583; params: target (0 CG1, 1 DG0),
                                       source (0 u_ex, 1 f_ex analytic; 2 DG0 input^power; 3 CG1 input), power */
@@ -61,6 +62,8 @@ int femo_device_count(void);
  * createRectangleMesh).  Canonical lattice numbering, see DESIGN.md. */
 int femo_mesh_create_unit_square(int nx, int ny, const double lo[2], const double hi[2], femo_mesh **out);
 int femo_mesh_create_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2], femo_mesh **out);
+/* hexahedral lattice on a box (dolfinx.mesh.create_box, CellType.hexahedron); vertex (ix,iy,iz) -> (iz*(ny+1)+iy)*(nx+1)+ix */
+int femo_mesh_create_box_hex(int nx, int ny, int nz, const double lo[3], const double hi[3], femo_mesh **out);
 int femo_mesh_create_interval(int n, double x0, double x1, femo_mesh **out);
 /* synthetic stand-in for the motor meshes (git-LFS pointers in the reference): periodic polar lattice on
  * r0 <= r <= r1, node (ir, ith) -> ir*nth + ith */

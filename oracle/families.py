@@ -439,3 +439,105 @@ class SimpQ1:
         if k == 0:
             return [(self.dg_dofs, None, (self.area / self.volume)[:, None])]
         return [(self.dg_dofs, None, np.zeros((self.mesh.ncells, 1)))]
+
+
+class SimpHex8:
+    """3-D extension of SimpQ1 on trilinear hexahedra: same residual
+    R = int sigma(u):eps(v) dx - int_{ds(100)} f.v ds with E = rho^p, 2x2x2 Gauss points in the cells
+    and 2x2 Gauss points on the traction faces; outputs 0 average density, 1 compliance.
+    """
+    name = 'simp_hex8'
+    n_outputs = 2
+
+    def __init__(self, mesh, tagged, nu=0.3, f=(0.0, -0.25, 0.0), penal=3.0):
+        assert mesh.kind == 'hexahedron'
+        self.mesh, self.nu, self.f, self.penal = mesh, nu, np.asarray(f, dtype=np.float64), penal
+        self.cell_dofs, self.N = dofmap(mesh, 'Q', 1, block=3)
+        self.dg_dofs, self.M = dofmap(mesh, 'DG', 0)
+        self.X = mesh.coords[mesh.cells]                           # (nc,8,3)
+        fc, fl = mesh.exterior_facets()
+        self.fc, self.fl = fc[tagged], fl[tagged]
+        self.fdofs = self.cell_dofs[self.fc]
+        self.flv = mesh.local_facets[self.fl]                      # (nf,4)
+        g = np.array([0.5 - 0.5 / np.sqrt(3.0), 0.5 + 0.5 / np.sqrt(3.0)])
+        self.qp = np.array([[g[i], g[j], g[k]] for k in range(2) for j in range(2) for i in range(2)])
+        self.qw = np.full(8, 0.125)
+        self.vol = sum(self.qw[q] * self._geom(self.qp[q])[1] for q in range(8))
+        self.volume = self.vol.sum()
+
+    @staticmethod
+    def _dN(p):
+        out = np.zeros((8, 3))
+        for a in range(8):
+            b = [(a >> d) & 1 for d in range(3)]
+            l = [p[d] if b[d] else 1.0 - p[d] for d in range(3)]
+            s = [1.0 if b[d] else -1.0 for d in range(3)]
+            out[a] = [s[0] * l[1] * l[2], s[1] * l[0] * l[2], s[2] * l[0] * l[1]]
+        return out
+
+    def _geom(self, pt):
+        dN = self._dN(pt)
+        J = np.einsum('cad,ak->cdk', self.X, dN)                    # dx_d/dxi_k
+        det = np.linalg.det(J)
+        Jinv = np.linalg.inv(J)
+        G = np.einsum('ckd,ak->cad', Jinv, dN)                      # (nc,8,3)
+        return G, np.abs(det)
+
+    def _khat(self):
+        lam = self.nu / ((1 + self.nu) * (1 - 2 * self.nu))
+        mu = 1.0 / (2 * (1 + self.nu))
+        K = np.zeros((self.mesh.ncells, 8, 3, 8, 3))
+        I3 = np.eye(3)
+        for q in range(8):
+            G, det = self._geom(self.qp[q])
+            wq = (self.qw[q] * det)[:, None, None, None, None]
+            K += wq * (lam * np.einsum('cai,cbj->caibj', G, G)
+                       + mu * (np.einsum('caj,cbi->caibj', G, G)
+                               + np.einsum('cad,cbd->cab', G, G)[:, :, None, :, None] * I3[None, None, :, None, :]))
+        return K.reshape(self.mesh.ncells, 24, 24)
+
+    def _traction(self):
+        nf = self.fc.size
+        ar = np.arange(nf)
+        Xf = self.X[self.fc[:, None], self.flv]                     # (nf,4,3)
+        g = np.array([0.5 - 0.5 / np.sqrt(3.0), 0.5 + 0.5 / np.sqrt(3.0)])
+        m = np.zeros((nf, 4))
+        for t in g:
+            for s_ in g:
+                N = np.array([(1 - s_) * (1 - t), s_ * (1 - t), (1 - s_) * t, s_ * t])
+                dNs = np.array([-(1 - t), (1 - t), -t, t])
+                dNt = np.array([-(1 - s_), -s_, (1 - s_), s_])
+                xs = np.einsum('fkd,k->fd', Xf, dNs)
+                xt = np.einsum('fkd,k->fd', Xf, dNt)
+                da = 0.25 * np.linalg.norm(np.cross(xs, xt), axis=1)
+                m += da[:, None] * N[None, :]
+        Fe = np.zeros((nf, 8, 3))
+        for k in range(4):
+            Fe[ar, self.flv[:, k]] += m[:, k, None] * self.f[None, :]
+        return Fe.reshape(nf, 24)
+
+    def residual(self, u, rho):
+        Re = (rho ** self.penal)[:, None] * np.einsum('cab,cb->ca', self._khat(), u[self.cell_dofs])
+        return [(self.cell_dofs, None, Re), (self.fdofs, None, -self._traction())]
+
+    def jacobian(self, u, rho):
+        return [(self.cell_dofs, self.cell_dofs, (rho ** self.penal)[:, None, None] * self._khat())]
+
+    def dRdm(self, slot, u, rho):
+        De = (self.penal * rho ** (self.penal - 1))[:, None] * np.einsum('cab,cb->ca', self._khat(), u[self.cell_dofs])
+        return [(self.cell_dofs, self.dg_dofs, De[:, :, None])]
+
+    def output(self, k, u, rho):
+        if k == 0:
+            return [rho * self.vol / self.volume]
+        return [np.einsum('fa,fa->f', self._traction(), u[self.fdofs])]
+
+    def output_du(self, k, u, rho):
+        if k == 0:
+            return [(self.cell_dofs, None, np.zeros((self.mesh.ncells, 24)))]
+        return [(self.fdofs, None, self._traction())]
+
+    def output_dm(self, k, slot, u, rho):
+        if k == 0:
+            return [(self.dg_dofs, None, (self.vol / self.volume)[:, None])]
+        return [(self.dg_dofs, None, np.zeros((self.mesh.ncells, 1)))]

@@ -24,6 +24,8 @@ _SIMPLEX_FACETS = {
     3: np.array([[1, 2], [0, 2], [0, 1]]),        # triangle
 }
 _QUAD_FACETS = np.array([[0, 1], [0, 2], [1, 3], [2, 3]])
+# basix hexahedron facets (tensor order on each face) [upstream, from memory]
+_HEX_FACETS = np.array([[0, 1, 2, 3], [0, 1, 4, 5], [0, 2, 4, 6], [1, 3, 5, 7], [2, 3, 6, 7], [4, 5, 6, 7]])
 
 
 class Mesh:
@@ -42,6 +44,8 @@ class Mesh:
     def local_facets(self):
         if self.kind == 'quadrilateral':
             return _QUAD_FACETS
+        if self.kind == 'hexahedron':
+            return _HEX_FACETS
         return _SIMPLEX_FACETS[self.cells.shape[1]]
 
     def exterior_facets(self):
@@ -90,6 +94,22 @@ def rectangle_quad(lo, hi, nx, ny):
     v0 = (iy * (nx + 1) + ix).ravel()
     cells = np.stack([v0, v0 + 1, v0 + nx + 1, v0 + nx + 2], axis=1)
     return Mesh('quadrilateral', coords, cells, (nx, ny), lo, hi)
+
+
+def box_hex(lo, hi, nx, ny, nz):
+    """dolfinx.mesh.create_box(..., CellType.hexahedron) in lattice order: vertex (ix,iy,iz) ->
+    (iz*(ny+1)+iy)*(nx+1)+ix, cell (ix,iy,iz) -> (iz*ny+iy)*nx+ix, vertices in tensor order (x fastest)."""
+    xs = lo[0] + (hi[0] - lo[0]) * np.arange(nx + 1) / nx
+    ys = lo[1] + (hi[1] - lo[1]) * np.arange(ny + 1) / ny
+    zs = lo[2] + (hi[2] - lo[2]) * np.arange(nz + 1) / nz
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing='ij')
+    coords = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    iz, iy, ix = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing='ij')
+    sx, sy = nx + 1, ny + 1
+    v0 = ((iz * sy + iy) * sx + ix).ravel()
+    off = np.array([(k & 1) + ((k >> 1) & 1) * sx + ((k >> 2) & 1) * sx * sy for k in range(8)])
+    cells = v0[:, None] + off[None, :]
+    return Mesh('hexahedron', coords, cells, (nx, ny, nz), lo, hi)
 
 
 def interval(n, x0, x1):

@@ -83,3 +83,31 @@ def csr(c, which, vals):
     rp, col = c.p.pattern(which)
     i = c.p.pattern_info(which)
     return sp.csr_matrix((vals.cpu().numpy(), col, rp), shape=(i['rows'], i['cols']))
+
+
+class HexCase:
+    """3-D SIMP cantilever (scaled down): box [0,Lx]x[0,Ly]x[0,Lz], clamp x=0,
+    traction on the x=Lx face near mid-height, random density; optionally a sheared (non-axis-aligned) box."""
+
+    def __init__(self, nx=8, ny=4, nz=2, seed=0, upload=True, rho_lo=0.2, shear=0.0):
+        lo, hi = (0.0, 0.0, 0.0), (2.0 * nx, 2.0 * ny, 2.0 * nz)
+        self.emesh = E.EngineMesh.box_hex(lo, hi, nx, ny, nz)
+        self.omesh = om.box_hex(lo, hi, nx, ny, nz)
+        assert shear == 0.0
+        eps = 1e-9
+
+        def traction(x):
+            return abs(x[0] - hi[0]) < eps and abs(x[1] - 0.5 * hi[1]) < 2.0 + eps
+        self.tag = _tagged(self.omesh, traction)
+        self.F = fam.SimpHex8(self.omesh, self.tag)
+        self.p = E.EngineProblem(self.emesh, E.FAMILY_SIMP_HEX8, [0.3, 0.0, -0.25, 0.0, 3.0], tagged=self.tag)
+        nodes = np.nonzero(np.isclose(self.omesh.coords[:, 0], 0.0, atol=1e-9))[0]
+        lists = [np.stack([3 * nodes, 3 * nodes + 1, 3 * nodes + 2], axis=1).ravel()]
+        self.bc = asm.DirichletBC(self.F.N, lists, 0.0)
+        self.p.set_bc(lists)
+        rng = np.random.default_rng(seed)
+        self.u = rng.standard_normal(self.F.N)
+        self.m = rho_lo + (1.0 - rho_lo) * rng.random(self.F.M)
+        self.sp = solvers.StatePath(self.F, self.bc)
+        if upload:
+            _upload(self)
