@@ -56,6 +56,7 @@ __device__ __forceinline__ double block_sum(double v) {
 // keep L1/L2 for the gathered vector instead
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int32_t ld_stream(const int32_t *p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const float *p) { return (double)__ldcs(p); }
 
 // y-slab of a global lattice owned by this rank: global cell rows [crow0, crow0+ncrows) are local,
 // local node row j is global row crow0 + j; node / cell rows [own0,own1) / [cown0,cown1) are owned
@@ -101,6 +102,7 @@ struct femo_mesh {
 // device work vectors of one multigrid level (level 0 is the problem itself)
 struct femo_mg_level {
     double *vals = nullptr;   // matrix values of this level (coarse levels own theirs)
+    float *vals32 = nullptr;  // fp32 copy streamed by the V-cycle's SpMVs (8 instead of 12 bytes per entry)
     double *dinv = nullptr, *x = nullptr, *b = nullptr, *r = nullptr, *d = nullptr, *q = nullptr;
     double *u = nullptr;      // restricted state used to rediscretise the coarse Jacobian
     double *dense = nullptr, *dense_tmp = nullptr;  // coarsest level: explicit inverse
@@ -138,6 +140,9 @@ struct femo_problem {
     femo::Arena st, wk;
     double *d_coords = nullptr;
     int32_t *d_cellsT = nullptr, *d_fb_cell = nullptr, *d_fb_local = nullptr, *d_cell_tag = nullptr;
+    // P2 spaces: edge opposite each local vertex (SoA), edge -> vertices, vertex -> incident edges (CSR)
+    int32_t *d_edgesT = nullptr, *d_edge_verts = nullptr, *d_vptr = nullptr, *d_vedge = nullptr;
+    std::vector<int32_t> vptr, vedge;
     femo::DevPattern dpat[5];
     femo::DevVecMap dvm_state[4], dvm_in[4];
     uint8_t *d_bc_mark = nullptr;

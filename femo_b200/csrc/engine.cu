@@ -12,6 +12,7 @@
 #include "families4.cuh"
 #include "families5.cuh"
 #include "families6.cuh"
+#include "families7.cuh"
 #include "dist.cuh"
 
 namespace femo {
@@ -149,10 +150,10 @@ __device__ __forceinline__ void spmv_row_epilogue(const SpmvEpi &E, int64_t i, d
     }
 }
 
-template <bool DOT, int EPI>
+template <bool DOT, int EPI, class VT>
 __global__ void __launch_bounds__(kThreads)
     k_spmv(const int32_t *__restrict__ rb, int nrb, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-           const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y, SpmvEpi E,
+           const VT *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y, SpmvEpi E,
            double *__restrict__ partials) {
     __shared__ double prod[kSpmvCap];
     __shared__ int32_t rp[kSpmvRows + 1];
@@ -545,6 +546,22 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
             }
             break;
         }
+        case FEMO_FAMILY_NLPOISSON_P2: {
+            P2Args A;
+            A.edgesT = p->d_edgesT;
+            A.nverts = p->mesh.nverts;
+            if (mask & 1) {
+                A.T = tri_args(p, cells_out);
+                FEMO_LAUNCH_OPS(k_nlpoisson_p2_cell, gc, A)
+            }
+            if ((mask & 2) && nf > 0) {
+                A.T = tri_args(p, facets_out);
+                if (op == OP_RES) k_nlpoisson_p2_facet<OP_RES><<<gf, kThreads, 0, st>>>(A);
+                else k_nlpoisson_p2_facet<OP_JAC><<<gf, kThreads, 0, st>>>(A);
+                p->launches++;
+            }
+            break;
+        }
         case FEMO_FAMILY_SIMP_HEX8: {
             if (mask & 1) {
                 HexArgs A = hex_args(p, out_id, cells_out);
@@ -591,9 +608,9 @@ static inline int spmv_grid(const femo_problem *p, int nrb) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(nrb, cap));
 }
 
-template <bool DOT>
+template <bool DOT, class VT>
 static int launch_spmv(femo_problem *p, const int32_t *rb, int nrb, const int32_t *rowptr, const int32_t *col,
-                       const double *vals, const double *x, double *y, const double *bsub, int *np_out,
+                       const VT *vals, const double *x, double *y, const double *bsub, int *np_out,
                        bool halo = true) {
     // every SpMV on the state pattern refreshes the ghost rows of its input first (no-op on one GPU)
     if (halo) {
@@ -605,7 +622,7 @@ static int launch_spmv(femo_problem *p, const int32_t *rb, int nrb, const int32_
     E.b = bsub;
     E.own0 = p->own_off;
     E.own1 = p->own_off + p->own_n;
-    k_spmv<DOT, EPI_PLAIN><<<grid, kThreads, 0, p->stream>>>(rb, nrb, rowptr, col, vals, x, y, E, p->d_partials);
+    k_spmv<DOT, EPI_PLAIN, VT><<<grid, kThreads, 0, p->stream>>>(rb, nrb, rowptr, col, vals, x, y, E, p->d_partials);
     p->launches++;
     if (np_out) *np_out = grid;
     FEMO_CHECK_LAUNCH();
@@ -613,15 +630,16 @@ static int launch_spmv(femo_problem *p, const int32_t *rb, int nrb, const int32_
 }
 
 // SpMV on pattern 0 with a fused Chebyshev epilogue (multigrid smoother)
-static int launch_spmv_cheb(femo_problem *p, int kind, const double *vals, const double *x, const SpmvEpi &E) {
+template <class VT>
+static int launch_spmv_cheb(femo_problem *p, int kind, const VT *vals, const double *x, const SpmvEpi &E) {
     const DevPattern &D = p->dpat[0];
     int rc = halo_nodes(p, const_cast<double *>(x));
     if (rc) return rc;
     const int grid = spmv_grid(p, D.nrb);
     if (kind == EPI_CHEB0)
-        k_spmv<false, EPI_CHEB0><<<grid, kThreads, 0, p->stream>>>(D.rb, D.nrb, D.rowptr, D.col, vals, x, nullptr, E, nullptr);
+        k_spmv<false, EPI_CHEB0, VT><<<grid, kThreads, 0, p->stream>>>(D.rb, D.nrb, D.rowptr, D.col, vals, x, nullptr, E, nullptr);
     else
-        k_spmv<false, EPI_CHEBK><<<grid, kThreads, 0, p->stream>>>(D.rb, D.nrb, D.rowptr, D.col, vals, x, nullptr, E, nullptr);
+        k_spmv<false, EPI_CHEBK, VT><<<grid, kThreads, 0, p->stream>>>(D.rb, D.nrb, D.rowptr, D.col, vals, x, nullptr, E, nullptr);
     p->launches++;
     FEMO_CHECK_LAUNCH();
     return FEMO_OK;
@@ -838,6 +856,26 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
                 p->out_mask[0] = 1; p->out_du_mask[0] = 0; p->out_dm_mask[0] = 1;   // average density
                 p->out_mask[1] = 2; p->out_du_mask[1] = 2; p->out_dm_mask[1] = 0;   // compliance
                 break;
+            case FEMO_FAMILY_NLPOISSON_P2:
+                if (M.kind != MESH_TRI) throw LayoutError{FEMO_EINVAL, "family needs a triangle mesh"};
+                p->mesh.build_edges();
+                p->state.init(M, EL_P2, 1);
+                p->nin = 1;
+                p->in[0].init(M, EL_DG0, 1);
+                p->nout = 1;
+                p->res_mask = 3;
+                p->jac_mask = 3;
+                if (nparams < 1) p->params[0] = 6e-7;
+                if (nparams < 2) p->params[1] = 10.0;
+                {   // vertex -> incident edges, ascending edge ids (restriction to the P1 multigrid level)
+                    p->vptr.assign(M.nverts + 1, 0);
+                    for (int64_t e = 0; e < M.nedges; ++e) { p->vptr[M.edge_verts[2 * e] + 1]++; p->vptr[M.edge_verts[2 * e + 1] + 1]++; }
+                    for (int64_t v = 0; v < M.nverts; ++v) p->vptr[v + 1] += p->vptr[v];
+                    p->vedge.resize(2 * M.nedges);
+                    std::vector<int32_t> pos(p->vptr.begin(), p->vptr.end() - 1);
+                    for (int64_t e = 0; e < M.nedges; ++e) { p->vedge[pos[M.edge_verts[2 * e]]++] = (int32_t)e; p->vedge[pos[M.edge_verts[2 * e + 1]]++] = (int32_t)e; }
+                }
+                break;
             case FEMO_FAMILY_SIMP_HEX8:
                 if (M.kind != MESH_HEX) throw LayoutError{FEMO_EINVAL, "family needs a hexahedral mesh"};
                 p->state.init(M, EL_VERTEX, 3);
@@ -860,7 +898,7 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
                 p->fb_cell.push_back(fcell[k]);
                 p->fb_local.push_back(flocal[k]);
             }
-        } else if (family == FEMO_FAMILY_NLPOISSON_P1 || family == FEMO_FAMILY_MOTOR_EM) {
+        } else if (family == FEMO_FAMILY_NLPOISSON_P1 || family == FEMO_FAMILY_NLPOISSON_P2 || family == FEMO_FAMILY_MOTOR_EM) {
             p->fb_cell = M.bf_cell;
             p->fb_local = M.bf_local;
         } else {
@@ -974,6 +1012,8 @@ int femo_problem_mesh_copy(const femo_problem *p, int what, void *out) {
         case 1: memcpy(out, M.cells.data(), M.cells.size() * sizeof(int32_t)); break;
         case 2: memcpy(out, M.bf_cell.data(), M.bf_cell.size() * sizeof(int32_t)); break;
         case 3: memcpy(out, M.bf_local.data(), M.bf_local.size() * sizeof(int32_t)); break;
+        case 4: memcpy(out, M.edge_verts.data(), M.edge_verts.size() * sizeof(int32_t)); break;   // P2: (nedges,2)
+        case 5: memcpy(out, M.cell_edges.data(), M.cell_edges.size() * sizeof(int32_t)); break;   // P2: (ncells,3)
         default: return set_err(FEMO_EINVAL, "femo_problem_mesh_copy: bad selector");
     }
     (void)tmp;
@@ -1041,11 +1081,23 @@ int femo_problem_enable_multigrid(femo_problem *p) {
     const bool tri = p->mesh.kind == MESH_TRI && p->state.element == EL_VERTEX && p->state.block == 1;
     const bool quad = p->mesh.kind == MESH_QUAD && p->state.element == EL_VERTEX;
     const bool hex = p->mesh.kind == MESH_HEX && p->state.element == EL_VERTEX;
-    if (!tri && !quad && !hex)
+    const bool p2 = p->mesh.kind == MESH_TRI && p->state.element == EL_P2 && !p->slab.active;
+    if (!tri && !quad && !hex && !p2)
         return set_err(FEMO_EINVAL, "multigrid is available for vertex-based states on lattice triangle / quadrilateral / hexahedral meshes");
     if (!p->mg.empty()) return FEMO_OK;
     if (p->slab.active) return enable_multigrid_slab(p);
     int nx = p->mesh.n[0], ny = p->mesh.n[1], nz = p->mesh.n[2];
+    // P2: the first coarse level is the P1 family on the SAME mesh (p-multigrid), then the lattice is coarsened
+    const int child_family = p2 ? FEMO_FAMILY_NLPOISSON_P1 : p->family;
+    if (p2) {
+        Mesh cm;
+        make_unit_square_tri(nx, ny, p->mesh.lo, p->mesh.hi, cm);
+        femo_problem *c = nullptr;
+        int rc = create_problem_impl(cm, child_family, p->params, 32, true, nullptr, 0, &c);
+        if (rc) return rc;
+        c->parent = p;
+        p->mg.push_back(c);
+    }
     // coarsen until the coarsest system fits the explicit inverse (<= 512 dofs)
     const int coarsest = hex ? 4 : ((p->state.block > 1) ? 6 : kMgCoarsest);
     while (nx > coarsest || ny > coarsest || nz > coarsest ||
@@ -1064,7 +1116,7 @@ int femo_problem_enable_multigrid(femo_problem *p) {
         else if (quad) make_rectangle_quad(nx, ny, p->mesh.lo, p->mesh.hi, cm);
         else make_unit_square_tri(nx, ny, p->mesh.lo, p->mesh.hi, cm);
         femo_problem *c = nullptr;
-        int rc = create_problem_impl(cm, p->family, p->params, 32, true, nullptr, 0, &c);
+        int rc = create_problem_impl(cm, child_family, p->params, 32, true, nullptr, 0, &c);
         if (rc) return rc;
         c->parent = p;
         p->mg.push_back(c);
@@ -1219,7 +1271,7 @@ static void child_bytes(const femo_problem *c, bool coarsest, size_t *sb, size_t
     s += Arena::need(std::max<size_t>(1, c->fb_cell.size()), 4) * 2;
     s += pattern_bytes(c->pat[0], true);
     s += Arena::need(N, 1) + 2 * Arena::need(N, 8) + Arena::need(N, 4) + 1024;
-    w += Arena::need(c->pat[0].nnz, 8) + 9 * Arena::need(N, 8) + Arena::need((size_t)c->mesh.ncells, 8);
+    w += Arena::need(c->pat[0].nnz, 8) + Arena::need(c->pat[0].nnz, 4) + 9 * Arena::need(N, 8) + Arena::need((size_t)c->mesh.ncells, 8);
     w += Arena::need(3 * kMaxPartials, 8) + Arena::need(S_COUNT, 8) + 1024;
     if (coarsest) w += 2 * Arena::need(N * N, 8);
     *sb = s;
@@ -1270,6 +1322,7 @@ static int upload_child(femo_problem *root, femo_problem *c, bool coarsest) {
     if (!c->d_lift_rows) return set_err(FEMO_EINVAL, "static arena too small (multigrid level)");
     femo_mg_level &L = c->mgl;
     L.vals = root->wk.take<double>(P.nnz);
+    L.vals32 = root->wk.take<float>(P.nnz);
     L.dinv = root->wk.take<double>(N);
     L.x = root->wk.take<double>(N);
     L.b = root->wk.take<double>(N);
@@ -1303,6 +1356,8 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     size_t s = 0;
     s += Arena::need(M.coords.size(), 8) + Arena::need(M.cells.size(), 4);
     s += 2 * Arena::need(std::max<size_t>(1, p->fb_cell.size()), 4) + Arena::need(std::max<size_t>(1, M.cell_tag.size()), 4);
+    if (p->state.element == EL_P2)
+        s += Arena::need(M.cell_edges.size(), 4) + Arena::need(M.edge_verts.size(), 4) + Arena::need(p->vptr.size(), 4) + Arena::need(p->vedge.size(), 4);
     for (int w = 0; w <= p->nin; ++w) s += pattern_bytes(p->pat[w], w == 0);
     for (int m = 1; m < 4; ++m) s += vecmap_bytes(p->vm_state[m]);
     for (int i = 0; i < p->nin; ++i) s += vecmap_bytes(p->vm_in[i]);
@@ -1323,6 +1378,7 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     w += 2 * Arena::need(p->pat[0].nnz, 8);        // Newton's Jacobian values (plain, BC'd)
     w += Arena::need(tv, 8);                       // transposed values
     w += Arena::need(N, 8);                        // Chebyshev direction of multigrid level 0
+    if (!p->mg.empty()) w += Arena::need(p->pat[0].nnz, 4);   // fp32 copy of the fine-level values for the V-cycle
     if (N <= kMgDenseMax) w += 2 * Arena::need((size_t)N * N, 8);   // explicit inverse (precond 3)
     if (!p->symmetric) w += (size_t)(kGmresRestart + 2) * Arena::need(N, 8) + Arena::need((size_t)(kGmresRestart + 1) * kMaxPartials, 8);
     w += 4096;
@@ -1367,6 +1423,16 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     if ((rc = up(p, p->d_fb_cell, p->fb_cell))) return rc;
     if ((rc = up(p, p->d_fb_local, p->fb_local))) return rc;
     if ((rc = up(p, p->d_cell_tag, M.cell_tag))) return rc;
+    if (p->state.element == EL_P2) {
+        std::vector<int32_t> T(M.cell_edges.size());
+        for (int64_t c = 0; c < M.ncells; ++c)
+            for (int a = 0; a < 3; ++a) T[a * M.ncells + c] = M.cell_edges[c * 3 + a];
+        if ((rc = up(p, p->d_edgesT, T))) return rc;
+        FEMO_CUDA(cudaStreamSynchronize(p->stream));
+        if ((rc = up(p, p->d_edge_verts, M.edge_verts))) return rc;
+        if ((rc = up(p, p->d_vptr, p->vptr))) return rc;
+        if ((rc = up(p, p->d_vedge, p->vedge))) return rc;
+    }
     for (int w = 0; w <= p->nin; ++w) {
         const Pattern &P = p->pat[w];
         DevPattern &D = p->dpat[w];
@@ -1440,6 +1506,20 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
                 t49[7 * i + j][2] = w[i] * w[j] * (1.0 - x[i]);
             }
         FEMO_CUDA(cudaMemcpyToSymbolAsync(c_tri49, t49, sizeof(t49), 0, cudaMemcpyHostToDevice, p->stream));
+        std::vector<double> x5, w5, x6, w6;
+        gauss_legendre_01(5, x5, w5);
+        double t25[25][3];
+        for (int i = 0; i < 5; ++i)
+            for (int j = 0; j < 5; ++j) {
+                t25[5 * i + j][0] = x5[i];
+                t25[5 * i + j][1] = x5[j] * (1.0 - x5[i]);
+                t25[5 * i + j][2] = w5[i] * w5[j] * (1.0 - x5[i]);
+            }
+        FEMO_CUDA(cudaMemcpyToSymbolAsync(c_tri25, t25, sizeof(t25), 0, cudaMemcpyHostToDevice, p->stream));
+        gauss_legendre_01(6, x6, w6);
+        double gl6[6][2];
+        for (int i = 0; i < 6; ++i) { gl6[i][0] = x6[i]; gl6[i][1] = w6[i]; }
+        FEMO_CUDA(cudaMemcpyToSymbolAsync(c_gl6, gl6, sizeof(gl6), 0, cudaMemcpyHostToDevice, p->stream));
         FEMO_CUDA(cudaStreamSynchronize(p->stream));
     }
 
@@ -1469,6 +1549,7 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     p->nt_vals_bc = p->wk.take<double>(p->pat[0].nnz);
     p->d_tvals = p->wk.take<double>(tv);
     p->kr_d = p->wk.take<double>(N);
+    if (!p->mg.empty()) p->mgl.vals32 = p->wk.take<float>(p->pat[0].nnz);
     if (!p->symmetric) {
         p->gm_restart = kGmresRestart;
         p->gm_basis = p->wk.take<double>((size_t)(kGmresRestart + 1) * N);

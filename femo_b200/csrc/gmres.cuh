@@ -84,13 +84,14 @@ static int gmres_solve(femo_problem *p, const double *vals, const double *b, dou
     const int g = red_grid(p, n);
     double *V = p->gm_basis, *w = p->kr_q, *z = p->kr_z, *r = p->kr_r, *t = p->kr_p;
     MgParams mp;
+    mp.fp32 = (o.mg_precision == 0);
     if (o.cheb_degree > 0) mp.degree = o.cheb_degree;
     int rc, spmvs = 0, its = 0;
     p->mgl.dinv = p->kr_dinv; p->mgl.r = p->kr_w; p->mgl.d = p->kr_d; p->mgl.q = p->wk_extra;
     const int cdeg = o.cheb_degree > 0 ? o.cheb_degree : 12;
     const double cratio = o.cheb_ratio > 1.0 ? o.cheb_ratio : 150.0;
     if (pre == 2) {
-        if ((rc = mg_setup(p, vals))) return rc;
+        if ((rc = mg_setup(p, vals, mp.fp32))) return rc;
     } else if (pre == 1) {
         if ((rc = cheb_setup(p, vals))) return rc;
     } else if (pre == 3) {
@@ -104,7 +105,7 @@ static int gmres_solve(femo_problem *p, const double *vals, const double *b, dou
     auto precond = [&](const double *in, double *out) -> int {
         if (pre == 3) k_dense_apply<<<(int)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(p->d_dense, in, out, (int)n);
         else if (pre == 2) return mg_vcycle(p, 0, in, out, mp);
-        else if (pre == 1) return mg_smooth(p, in, out, true, cdeg, cratio);
+        else if (pre == 1) return mg_smooth(p, in, out, true, cdeg, cratio, false);
         else k_hadamard<<<g, kThreads, 0, st>>>(p->kr_dinv, in, out, n);
         p->launches++;
         FEMO_CHECK_LAUNCH();

@@ -178,6 +178,7 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     double *pa = p->d_partials, *pb = p->d_partials + kMaxPartials;
     const int g = red_grid(p, n), go = red_grid(p, p->own_n);
     MgParams mp;
+    mp.fp32 = (o.mg_precision == 0);
     if (o.cheb_degree > 0) mp.degree = o.cheb_degree;
     if (o.cheb_ratio > 1.0) mp.ratio = o.cheb_ratio;
     int rc, np = 0, spmvs = 0;
@@ -189,7 +190,7 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     const int cdeg = o.cheb_degree > 0 ? o.cheb_degree : 8;
     const double cratio = o.cheb_ratio > 1.0 ? o.cheb_ratio : 60.0;
     if (pre == 2) {
-        if ((rc = mg_setup(p, vals))) return rc;
+        if ((rc = mg_setup(p, vals, mp.fp32))) return rc;
     } else if (pre == 1) {
         if ((rc = cheb_setup(p, vals))) return rc;
     } else if (pre == 3) {
@@ -234,7 +235,7 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
                 k_dense_apply<<<(int)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(p->d_dense, p->kr_r, p->kr_z, (int)n);
                 p->launches++;
             } else if (pre == 1) {
-                if ((rc = mg_smooth(p, p->kr_r, p->kr_z, true, cdeg, cratio))) return rc;
+                if ((rc = mg_smooth(p, p->kr_r, p->kr_z, true, cdeg, cratio, false))) return rc;
             } else if ((rc = mg_vcycle(p, 0, p->kr_r, p->kr_z, mp))) return rc;
             k_dot<<<go, kThreads, 0, st>>>(p->kr_r + p->own_off, p->kr_z + p->own_off, p->own_n, pa);
             p->launches++;

@@ -125,6 +125,32 @@ void make_box_hex(int nx, int ny, int nz, const double lo[3], const double hi[3]
             }
 }
 
+void Mesh::build_edges() {
+    if (kind != MESH_TRI) throw LayoutError{FEMO_EINVAL, "edges are built for triangle meshes"};
+    if (!cell_edges.empty()) return;
+    std::vector<int64_t> keys((size_t)ncells * 3);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < ncells; ++c)
+        for (int i = 0; i < 3; ++i) {
+            const int64_t a = cells[c * 3 + (i + 1) % 3], b = cells[c * 3 + (i + 2) % 3];
+            keys[c * 3 + i] = (std::min(a, b) << 32) | std::max(a, b);
+        }
+    std::vector<int64_t> uniq(keys);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    nedges = (int64_t)uniq.size();
+    if (nverts + nedges > kInt32Max) throw LayoutError{FEMO_ELIMIT, "P2 space exceeds int32 dofs"};
+    edge_verts.resize(nedges * 2);
+    for (int64_t e = 0; e < nedges; ++e) {
+        edge_verts[2 * e] = (int32_t)(uniq[e] >> 32);
+        edge_verts[2 * e + 1] = (int32_t)(uniq[e] & 0xffffffffLL);
+    }
+    cell_edges.resize((size_t)ncells * 3);
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < ncells * 3; ++k)
+        cell_edges[k] = (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), keys[k]) - uniq.begin());
+}
+
 void make_annulus_tri(int nr, int nth, double r0, double r1, Mesh &m) {
     m = Mesh();
     m.kind = MESH_TRI;
@@ -186,6 +212,12 @@ void Space::init(const Mesh &m, int element_, int block_) {
     if (element == EL_DG0) {
         ndofs = m.ncells * block;
         ndpc = block;
+    } else if (element == EL_P2) {
+        if (m.kind != MESH_TRI) throw LayoutError{FEMO_EINVAL, "P2 spaces need a triangle mesh"};
+        if (m.cell_edges.empty()) throw LayoutError{FEMO_ESTATE, "P2 space: mesh edges were not built"};
+        block = 1;
+        ndofs = m.nverts + m.nedges;
+        ndpc = 6;
     } else {
         if (element == EL_HERMITE3) block = 2;  // (value, reference derivative) per vertex
         ndofs = m.nverts * block;
@@ -225,9 +257,7 @@ static void build_incidence(const Mesh &m, const Space &s, const std::vector<Int
         for (int a = 0; a < nd; ++a)
             for (int64_t e = 0; e < blocks[b].ne; ++e) {
                 int64_t cell = blocks[b].ent_cell ? blocks[b].ent_cell[e] : e;
-                int32_t dof;
-                if (s.element == EL_DG0) dof = (int32_t)(cell * s.block + a);
-                else dof = m.cells[cell * m.nvpc + a / s.block] * s.block + a % s.block;
+                const int32_t dof = s.cell_dof(m, cell, a);
                 int64_t q = pos[dof]++;
                 inc.ent[q] = (int32_t)e;
                 inc.blk[q] = (int16_t)b;

@@ -15,7 +15,8 @@
 namespace femo {
 
 enum MeshKind { MESH_INTERVAL = 1, MESH_TRI = 2, MESH_QUAD = 3, MESH_HEX = 4 };
-enum Element { EL_DG0 = 0, EL_VERTEX = 1 /* P1 / Q1: one node per vertex */, EL_HERMITE3 = 2 };
+enum Element { EL_DG0 = 0, EL_VERTEX = 1 /* P1 / Q1: one node per vertex */, EL_HERMITE3 = 2,
+               EL_P2 = 3 /* triangles: vertex nodes then edge-midpoint nodes */ };
 
 struct Mesh {
     int kind = 0, gdim = 0, nvpc = 0;
@@ -27,6 +28,12 @@ struct Mesh {
     std::vector<int32_t> bf_cell, bf_local;  // exterior facets, sorted by (cell, local facet)
     std::vector<int32_t> cell_tag;           // optional subdomain id per cell (meshtags of dimension tdim)
     bool lattice = true;                     // (n[0]+1) x (n[1]+1) vertex lattice in row-major order
+    // edges of a triangle mesh (built on demand for P2 spaces): edge e joins edge_verts[2e] < edge_verts[2e+1];
+    // edges are numbered in lexicographic order of that pair; local edge i of a cell is opposite vertex i (basix)
+    int64_t nedges = 0;
+    std::vector<int32_t> edge_verts;         // nedges*2
+    std::vector<int32_t> cell_edges;         // ncells*3
+    void build_edges();
 };
 
 // ext_bottom / ext_top: whether the y = lo / y = hi edge is a true domain boundary (false for the
@@ -55,11 +62,22 @@ struct Space {
     inline void cell_dofs(const Mesh &m, int64_t cell, int32_t *out) const {
         if (element == EL_DG0) {
             for (int c = 0; c < block; ++c) out[c] = (int32_t)(cell * block + c);
+        } else if (element == EL_P2) {
+            for (int a = 0; a < 3; ++a) {
+                out[a] = m.cells[cell * 3 + a];
+                out[3 + a] = (int32_t)(m.nverts + m.cell_edges[cell * 3 + a]);
+            }
         } else {
             const int32_t *v = &m.cells[cell * m.nvpc];
             for (int a = 0; a < m.nvpc; ++a)
                 for (int c = 0; c < block; ++c) out[a * block + c] = v[a] * block + c;
         }
+    }
+    // dof carried by local index a of `cell`
+    inline int32_t cell_dof(const Mesh &m, int64_t cell, int a) const {
+        if (element == EL_DG0) return (int32_t)(cell * block + a);
+        if (element == EL_P2) return a < 3 ? m.cells[cell * 3 + a] : (int32_t)(m.nverts + m.cell_edges[cell * 3 + a - 3]);
+        return m.cells[cell * m.nvpc + a / block] * block + a % block;
     }
 };
 

@@ -431,7 +431,18 @@ __global__ void __launch_bounds__(kThreads)
 
 // Chebyshev smoother of degree `deg` on level problem L: x ~ A^-1 b.  Every step after the
 // first is ONE kernel: the SpMV A d with the residual/direction/solution updates in its row epilogue.
-static int mg_smooth(femo_problem *L, const double *b, double *x, bool zero_guess, int deg, double ratio) {
+__global__ void __launch_bounds__(kThreads) k_to_f32(const double *__restrict__ a, float *__restrict__ o, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) o[i] = (float)a[i];
+}
+
+// the level's SpMV with a fused Chebyshev epilogue, streaming the fp32 copy of the values when requested
+static int mg_spmv_cheb(femo_problem *L, bool fp32, int kind, const double *x, const SpmvEpi &E) {
+    femo_mg_level &M = L->mgl;
+    if (fp32 && M.vals32) return launch_spmv_cheb(L, kind, M.vals32, x, E);
+    return launch_spmv_cheb(L, kind, M.vals, x, E);
+}
+
+static int mg_smooth(femo_problem *L, const double *b, double *x, bool zero_guess, int deg, double ratio, bool fp32) {
     femo_mg_level &M = L->mgl;
     const int64_t n = L->state.ndofs;
     cudaStream_t st = L->stream;
@@ -457,7 +468,7 @@ static int mg_smooth(femo_problem *L, const double *b, double *x, bool zero_gues
     } else {
         SpmvEpi E;                 // r = b - A x ; d0 = dinv r / theta
         E.b = b; E.dinv = M.dinv; E.rout = M.r; E.dout = dcur; E.c1 = 1.0 / theta;
-        if ((rc = launch_spmv_cheb(L, EPI_CHEB0, M.vals, x, E))) return rc;
+        if ((rc = mg_spmv_cheb(L, fp32, EPI_CHEB0, x, E))) return rc;
         if (deg <= 1) {
             k_axpy<<<g, kThreads, 0, st>>>(1.0, dcur, x, n);
             L->launches++;
@@ -472,7 +483,7 @@ static int mg_smooth(femo_problem *L, const double *b, double *x, bool zero_gues
         SpmvEpi E;
         E.dinv = M.dinv; E.rin = rin; E.rout = M.r; E.dout = dnext; E.xacc = x;
         E.c1 = rho_new * rho; E.c2 = 2.0 * rho_new / delta; E.xmode = xmode;
-        if ((rc = launch_spmv_cheb(L, EPI_CHEBK, M.vals, dcur, E))) return rc;
+        if ((rc = mg_spmv_cheb(L, fp32, EPI_CHEBK, dcur, E))) return rc;
         std::swap(dcur, dnext);
         rin = M.r;
         xmode = 0;
@@ -484,6 +495,7 @@ static int mg_smooth(femo_problem *L, const double *b, double *x, bool zero_gues
 struct MgParams {
     int degree = 2;
     double ratio = 4.0;
+    bool fp32 = true;      // V-cycle SpMVs stream fp32 copies of the level matrices (vectors stay fp64)
 };
 
 static inline LatD latd_of(const femo_problem *p) {
@@ -516,13 +528,15 @@ static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, con
     femo_problem *C = root->mg[lv];
     femo_mg_level &MC = C->mgl;
     const DevPattern &D = L->dpat[0];
-    if ((rc = mg_smooth(L, b, x, true, mp.degree, mp.ratio))) return rc;
+    if ((rc = mg_smooth(L, b, x, true, mp.degree, mp.ratio, mp.fp32))) return rc;
     // r = b - A x ; restrict
-    if ((rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, x, M.r, b, nullptr))) return rc;
+    if (mp.fp32 && M.vals32) rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals32, x, M.r, b, nullptr);
+    else rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, x, M.r, b, nullptr);
+    if (rc) return rc;
     if ((rc = mg_restrict(L, C, M.r, MC.b))) return rc;
     if ((rc = mg_vcycle(root, lv + 1, MC.b, MC.x, mp))) return rc;
     if ((rc = mg_prolong_add(L, C, MC.x, x))) return rc;
-    return mg_smooth(L, b, x, false, mp.degree, mp.ratio);
+    return mg_smooth(L, b, x, false, mp.degree, mp.ratio, mp.fp32);
 }
 
 // transfers between level lv (fine) and lv+1 (coarse) of the hierarchy, shared by the V-cycle and the
@@ -532,6 +546,12 @@ static int mg_restrict(femo_problem *L, femo_problem *C, double *rf, double *rc_
     const uint8_t *mf = L->has_bc ? L->d_bc_mark : nullptr, *mc = C->has_bc ? C->d_bc_mark : nullptr;
     cudaStream_t st = L->stream;
     int rc;
+    if (L->state.element == EL_P2) {                               // p-multigrid: P2 -> P1 on the same mesh
+        k_p2_to_p1_restrict<<<grid_for(nc), kThreads, 0, st>>>(L->d_vptr, L->d_vedge, L->mesh.nverts, rf, rc_, mf, mc);
+        L->launches++;
+        FEMO_CHECK_LAUNCH();
+        return FEMO_OK;
+    }
     if (nested_pair(L, C)) {
         if ((rc = halo_nodes(L, rf))) return rc;                  // coarse owned rows read the fine ghost row below
         k_restrict_nested<<<grid_for(nc), kThreads, 0, st>>>(latd_of(L), latd_of(C), rf, rc_, mf, mc);
@@ -555,6 +575,12 @@ static int mg_prolong_add(femo_problem *L, femo_problem *C, double *xc, double *
     const uint8_t *mf = L->has_bc ? L->d_bc_mark : nullptr;
     cudaStream_t st = L->stream;
     int rc;
+    if (L->state.element == EL_P2) {
+        k_p1_to_p2<true><<<grid_for(n), kThreads, 0, st>>>(L->d_edge_verts, L->mesh.nverts, L->mesh.nedges, xc, xf, mf);
+        L->launches++;
+        FEMO_CHECK_LAUNCH();
+        return FEMO_OK;
+    }
     if (nested_pair(L, C)) {
         if ((rc = halo_nodes(C, xc))) return rc;                   // fine owned rows read the coarse ghost row above
         k_prolong_nested<<<grid_for(n), kThreads, 0, st>>>(latd_of(L), latd_of(C), xc, xf, mf);
@@ -645,7 +671,7 @@ static int sync_replicated_bc(femo_problem *root) {
 }
 
 // (re)build the hierarchy for the matrix `vals` of the root at the root's current state
-static int mg_setup(femo_problem *root, const double *vals) {
+static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true) {
     if (root->mg.empty()) return set_err(FEMO_ESTATE, "multigrid requested but femo_problem_enable_multigrid was not called before upload");
     const int nlev = (int)root->mg.size() + 1;
     int rc;
@@ -662,7 +688,9 @@ static int mg_setup(femo_problem *root, const double *vals) {
             femo_problem *F = (lv == 1) ? root : root->mg[lv - 2];
             const double *uf = (lv == 1) ? root->coef[0] : F->mgl.u;
             if (!uf) return set_err(FEMO_ESTATE, "multigrid setup: state coefficient not set");
-            if (nested_pair(F, L)) {
+            if (F->state.element == EL_P2) {                      // vertex values of the P2 state
+                FEMO_CUDA(cudaMemcpyAsync(M.u, uf, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            } else if (nested_pair(F, L)) {
                 k_inject_nested<<<grid_for(n), kThreads, 0, st>>>(latd_of(F), latd_of(L), uf, M.u);
                 L->launches++;
                 if (L->slab.active) {
@@ -701,6 +729,11 @@ static int mg_setup(femo_problem *root, const double *vals) {
             if ((rc = femo_assemble_jacobian(L, L->has_bc ? nullptr : M.vals, L->has_bc ? M.vals : nullptr))) return rc;
         }
         const DevPattern &D = L->dpat[0];
+        if (fp32 && M.vals32 && lv < nlev - 1) {
+            const int64_t nnz = L->pat[0].nnz;
+            k_to_f32<<<(int)std::min<int64_t>((nnz + kThreads - 1) / kThreads, (int64_t)L->num_sms * 16), kThreads, 0, st>>>(M.vals, M.vals32, nnz);
+            L->launches++;
+        }
         if (lv == nlev - 1) {
             if (n > kMgDenseMax) return set_err(FEMO_ELIMIT, "multigrid: coarsest level too large for the dense solve");
             k_dense_inverse<<<1, kThreads, 0, st>>>(D.rowptr, D.col, M.vals, (int)n, M.dense_tmp, M.dense);

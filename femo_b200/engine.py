@@ -17,6 +17,7 @@ FAMILY_MASS_P1 = 5
 FAMILY_MOTOR_MM = 6
 FAMILY_MOTOR_EM = 7
 FAMILY_SIMP_HEX8 = 8
+FAMILY_NLPOISSON_P2 = 9
 
 
 def device_count():
@@ -143,6 +144,18 @@ class EngineProblem:
         self.device = None
 
     # -- host-side layout queries ----------------------------------------
+    def edges(self):
+        """P2 states: (edge -> vertices (nedges,2), cell -> edges (ncells,3)) of the problem's mesh."""
+        s = (C.c_int64 * 6)()
+        check(lib.femo_problem_mesh_sizes(self._h, s))
+        ncells, nverts = int(s[0]), int(s[1])
+        ne = self.N - nverts
+        ev = np.empty((ne, 2), dtype=np.int32)
+        ce = np.empty((ncells, 3), dtype=np.int32)
+        check(lib.femo_problem_mesh_copy(self._h, 4, ev.ctypes.data_as(C.c_void_p)))
+        check(lib.femo_problem_mesh_copy(self._h, 5, ce.ctypes.data_as(C.c_void_p)))
+        return ev, ce
+
     def pattern_info(self, which):
         info = (C.c_int64 * 4)()
         check(lib.femo_problem_pattern_info(self._h, which, info))
@@ -290,11 +303,11 @@ class EngineProblem:
         return y
 
     def linear_solve(self, vals, b, x=None, transpose=False, rtol=1e-10, atol=0.0, max_it=100000, check_every=1,
-                     precond=0, cheb_degree=0, cheb_ratio=0.0, method=0, restart=0):
+                     precond=0, cheb_degree=0, cheb_ratio=0.0, method=0, restart=0, mg_precision=0):
         """method 0 = CG, 1 = restarted GMRES (non-symmetric Jacobians)."""
         x = self.new_vector(self.N, 0.0) if x is None else x
         o = KrylovOpts(rtol=rtol, atol=atol, max_it=max_it, precond=precond, cheb_degree=cheb_degree, method=method,
-                       restart=restart, check_every=check_every, cheb_ratio=cheb_ratio)
+                       restart=restart, check_every=check_every, cheb_ratio=cheb_ratio, mg_precision=mg_precision)
         info = KrylovInfo()
         check(lib.femo_linear_solve(self._h, self._p(vals), self._p(b), self._p(x), 1 if transpose else 0,
                                     C.byref(o), C.byref(info)))
@@ -302,7 +315,8 @@ class EngineProblem:
                        bnorm=info.bnorm, spmv_count=info.spmv_count)
 
     def newton_solve(self, kind='Newton', atol=None, rtol=None, stol=1e-8, max_it=None, krylov_rtol=1e-10,
-                     krylov_max_it=100000, check_every=1, precond=0, cheb_degree=0, cheb_ratio=0.0, method=0):
+                     krylov_max_it=100000, check_every=1, precond=0, cheb_degree=0, cheb_ratio=0.0, method=0,
+                     mg_precision=0):
         """kind 'Newton' = dolfinx NewtonSolver defaults of the reference (3 fixed
         iterations, utils_dolfinx.py:419-425); 'SNES' = PETSc newtonls (:376-416)."""
         snes = (kind == 'SNES')
@@ -314,7 +328,7 @@ class EngineProblem:
         o.max_it = (100 if snes else 3) if max_it is None else max_it
         o.krylov = KrylovOpts(rtol=krylov_rtol, atol=0.0, max_it=krylov_max_it, precond=precond,
                               cheb_degree=cheb_degree, method=method, restart=0, check_every=check_every,
-                              cheb_ratio=cheb_ratio)
+                              cheb_ratio=cheb_ratio, mg_precision=mg_precision)
         info = NewtonInfo()
         check(lib.femo_newton_solve(self._h, C.byref(o), C.byref(info)))
         return dict(iterations=info.iterations, converged=info.converged, fnorm0=info.fnorm0, fnorm=info.fnorm,

@@ -54,7 +54,7 @@ class Mesh:
         x3 = np.zeros((emesh.nverts, 3))
         x3[:, :emesh.gdim] = xy
         self.geometry = _Geometry(x3, emesh.gdim)
-        self.topology = _Topology({'interval': 1}.get(cell_type, 2), emesh.ncells)
+        self.topology = _Topology({'interval': 1, 'hexahedron': 3}.get(cell_type, 2), emesh.ncells)
         self.cells = emesh.cells()
         self.num_cells = emesh.ncells
         self.num_vertices = emesh.nverts
@@ -371,6 +371,8 @@ def _local_facets(mesh):
         return np.array([[1, 2], [0, 2], [0, 1]])
     if mesh.cell_type == 'quadrilateral':
         return np.array([[0, 1], [0, 2], [1, 3], [2, 3]])
+    if mesh.cell_type == 'hexahedron':
+        return np.array([[0, 1, 2, 3], [0, 1, 4, 5], [0, 2, 4, 6], [1, 3, 5, 7], [2, 3, 6, 7], [4, 5, 6, 7]])
     return np.array([[0], [1]])
 
 

@@ -35,6 +35,11 @@ def createRectangleMesh(pt1, pt2, nx, ny):
     return Mesh(_E.EngineMesh.rectangle_quad(tuple(pt1), tuple(pt2), nx, ny), 'quadrilateral')
 
 
+def createBoxMesh(pt1, pt2, nx, ny, nz):
+    """dolfinx.mesh.create_box(..., CellType.hexahedron): the 3-D cantilever of SURVEY.md section 8d (C4-3D)."""
+    return Mesh(_E.EngineMesh.box_hex(tuple(pt1), tuple(pt2), nx, ny, nz), 'hexahedron')
+
+
 def meshSize(mesh):
     """utils_dolfinx.py:526-530"""
     return mesh.h()

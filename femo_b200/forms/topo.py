@@ -1,5 +1,6 @@
 """Forms of examples/beam_topo_opt/run_topo_opt_cantilever_beam.py (config 4):
-SIMP linear elasticity on Q1 quadrilaterals, vector CG1 state, DG0 density.
+SIMP linear elasticity on Q1 quadrilaterals (or, as the 3-D extension, trilinear hexahedra), vector CG1
+state, DG0 density.
 
   pdeRes(u, v, rho_e, f, dss=ds_(100), method='SIMP')   :62-77
   averageFunc(func)                                       :79-83   int rho/|Omega| dx
@@ -22,8 +23,13 @@ def pdeRes(u, v, rho_e, f, E=1, dss=None, method='SIMP'):
     if method != 'SIMP':
         raise NotImplementedError("topology family: only method='SIMP' (E = rho^3) has device kernels")
     fv = _fvec(f)
-    fam = FormFamily.get(_E.FAMILY_SIMP_Q1, u.function_space.mesh, u, [rho_e],
-                         params=[NU, fv[0], fv[1], 3.0], tagged=None if dss is None else dss.facets())
+    mesh = u.function_space.mesh
+    if mesh.cell_type == 'hexahedron':          # 3-D extension
+        fam = FormFamily.get(_E.FAMILY_SIMP_HEX8, mesh, u, [rho_e], params=[NU, fv[0], fv[1], fv[2], 3.0],
+                             tagged=None if dss is None else dss.facets())
+    else:
+        fam = FormFamily.get(_E.FAMILY_SIMP_Q1, mesh, u, [rho_e],
+                             params=[NU, fv[0], fv[1], 3.0], tagged=None if dss is None else dss.facets())
     rho_e.__dict__['_femo_family_of_input'] = fam
     return Form(fam, 'residual')
 

@@ -45,6 +45,7 @@ typedef struct femo_problem femo_problem;
 #define FEMO_FAMILY_EB_BEAM 3      /* examples/beam_thickness_opt/run_thickness_opt_cantilever_beam.py:71-85 */
 #define FEMO_FAMILY_SIMP_Q1 4      /* examples/beam_topo_opt/run_topo_opt_cantilever_beam.py:62-86 */
 #define FEMO_FAMILY_MOTOR_MM 6     /* examples/em_motor_opt/motor_pde.py:134-183,199-210 (hyperelastic mesh motion, Nitsche on dS/ds(1000)) */
+#define FEMO_FAMILY_NLPOISSON_P2 9  /* config 2 with a quadratic Lagrange state (BASELINE.json configs[1] "P1/P2"); params alpha, beta */
 #define FEMO_FAMILY_SIMP_HEX8 8    /* 3-D extension of examples/beam_topo_opt/run_topo_opt_cantilever_beam.py:62-86 on trilinear hexahedra; params nu, fx, fy, fz, penal */
 #define FEMO_FAMILY_MOTOR_EM 7     /* examples/em_motor_opt/motor_pde.py:12-130,186-197 (nonlinear magnetostatics on a moving mesh) */
 #define FEMO_FAMILY_MASS_P1 5      /* L2 projection, femo/fea/utils_dolfinx.py:549-583; params: target (0 CG1, 1 DG0),
@@ -127,7 +128,8 @@ int femo_problem_create_slab(int family, const double *params, int nparams, int 
 /* info: active, rank, nranks, gny, first local cell row, local cell rows, owned node rows [own0,own1),
  * owned cell rows [cown0,cown1) (local indices), own_off, own_n (dofs), cown_off, cown_n (cells), nx, ny_local */
 int femo_problem_slab_info(const femo_problem *p, int64_t info[16]);
-/* the problem's own (local) mesh: same selectors as femo_mesh_sizes / femo_mesh_copy */
+/* the problem's own (local) mesh: same selectors as femo_mesh_sizes / femo_mesh_copy; for P2 states additionally
+ * 4 = edge -> vertices (nedges,2) and 5 = cell -> edges (ncells,3), nedges = state dofs - vertices */
 int femo_problem_mesh_sizes(const femo_problem *p, int64_t sizes[6]);
 int femo_problem_mesh_copy(const femo_problem *p, int what, void *out);
 /* refresh ghost rows of a device vector: kind 0 = state-space (nodes), 1 = cell-wise input */
@@ -208,6 +210,8 @@ typedef struct femo_krylov_opts {
     int restart;      /* GMRES restart; with precond 2: 1 disables the full-multigrid start */
     int check_every;  /* residual-norm host check period (>=1) */
     double cheb_ratio; /* smoother targets [lmax/ratio, lmax] of D^-1 A (default 8) */
+    int mg_precision;  /* precond 2: 0 = the V-cycle streams fp32 copies of the level matrices (vectors, the outer
+                          Krylov recurrence and every residual stay fp64), 1 = fp64 values throughout */
 } femo_krylov_opts;
 
 typedef struct femo_krylov_info {

@@ -541,3 +541,132 @@ class SimpHex8:
         if k == 0:
             return [(self.dg_dofs, None, (self.vol / self.volume)[:, None])]
         return [(self.dg_dofs, None, np.zeros((self.mesh.ncells, 1)))]
+
+
+class NonlinearPoissonP2(_TriP1):
+    """Config 2 with a quadratic Lagrange state (BASELINE.json configs[1] "P1/P2"):
+    the forms of examples/nonlinear_poisson_opt/run_nonlinear_poisson_opt.py:88-116,140-145 with V = CG2.
+
+    cells:  int grad(u).grad(v) + u^3 v - f v dx       (degree 8 -> collapsed Gauss, exact to 9)
+    facets: symmetric Nitsche terms, beta = 10          (6-pt Gauss)
+    output: int 1/2 (u-u_ex)^2 + alpha/2 f^2 dx         (degree-12 rule, u_ex analytic)
+    Basis in barycentric coordinates: phi_i = l_i(2 l_i - 1), phi_{3+i} = 4 l_j l_k (edge opposite vertex i).
+    """
+    name = 'nlpoisson_p2'
+    n_outputs = 1
+
+    def __init__(self, mesh, alpha=6e-7, beta=10.0):
+        super().__init__(mesh)
+        self.alpha, self.beta = alpha, beta
+        self.cell_dofs, self.N = dofmap(mesh, 'CG', 2)
+        self.h = mesh.cell_diameter()
+        fc, fl = mesh.exterior_facets()
+        self.fc, self.fl = fc, fl
+        lf = mesh.local_facets[fl]
+        P, Q, O = self.X[fc, lf[:, 0]], self.X[fc, lf[:, 1]], self.X[fc, fl]
+        t = Q - P
+        self.flen = np.linalg.norm(t, axis=1)
+        nrm = np.stack([t[:, 1], -t[:, 0]], axis=1) / self.flen[:, None]
+        self.fn = nrm * np.sign(np.einsum('fd,fd->f', nrm, P - O))[:, None]
+        self.fP, self.fQ, self.flv = P, Q, lf
+        self.fdofs = self.cell_dofs[fc]
+
+    @staticmethod
+    def _bary(pts):
+        return np.stack([1.0 - pts[..., 0] - pts[..., 1], pts[..., 0], pts[..., 1]], axis=-1)
+
+    @staticmethod
+    def _phi(lam):
+        """(...,3) barycentric -> (...,6) basis values."""
+        out = [lam[..., i] * (2.0 * lam[..., i] - 1.0) for i in range(3)]
+        out += [4.0 * lam[..., (i + 1) % 3] * lam[..., (i + 2) % 3] for i in range(3)]
+        return np.stack(out, axis=-1)
+
+    @staticmethod
+    def _grad(lam, G):
+        """lam (...,3) broadcastable against cells, G (nc,3,2) grad lambda -> (nc,...,6,2)."""
+        g = []
+        for i in range(3):
+            g.append((4.0 * lam[..., i] - 1.0)[..., None] * G[:, i])
+        for i in range(3):
+            j, k = (i + 1) % 3, (i + 2) % 3
+            g.append(4.0 * (lam[..., j][..., None] * G[:, k] + lam[..., k][..., None] * G[:, j]))
+        return np.stack(g, axis=-2)
+
+    def _cells(self, u, f, want):
+        pts, w = quad.triangle(8)
+        ue = u[self.cell_dofs]
+        nc = self.mesh.ncells
+        Re, Ae = np.zeros((nc, 6)), np.zeros((nc, 6, 6))
+        for q in range(len(w)):
+            lam = self._bary(pts[q])
+            ph = self._phi(lam)                                     # (6,)
+            gp = self._grad(np.broadcast_to(lam, (nc, 3)), self.G)  # (nc,6,2)
+            uq = ue @ ph
+            wq = w[q] * self.detJ
+            if want == 'R':
+                gu = np.einsum('ca,cad->cd', ue, gp)
+                Re += wq[:, None] * (np.einsum('cd,cad->ca', gu, gp) + (uq ** 3 - f)[:, None] * ph[None, :])
+            else:
+                Ae += wq[:, None, None] * (np.einsum('cad,cbd->cab', gp, gp)
+                                           + (3.0 * uq * uq)[:, None, None] * np.outer(ph, ph)[None])
+        return Re if want == 'R' else Ae
+
+    def _facets(self, u, want):
+        s, w = quad.interval(11)
+        nf = self.fc.size
+        ar = np.arange(nf)
+        uf = u[self.fdofs]
+        Gf = self.G[self.fc]
+        bh = self.beta / self.h[self.fc]
+        Rf, Af = np.zeros((nf, 6)), np.zeros((nf, 6, 6))
+        for q in range(len(w)):
+            lam = np.zeros((nf, 3))
+            lam[ar, self.flv[:, 0]] = 1.0 - s[q]
+            lam[ar, self.flv[:, 1]] = s[q]
+            ph = self._phi(lam)                                     # (nf,6)
+            gn = np.einsum('fad,fd->fa', self._grad(lam, Gf), self.fn)
+            wq = w[q] * self.flen
+            if want == 'R':
+                uq = np.einsum('fa,fa->f', uf, ph)
+                dudn = np.einsum('fa,fa->f', uf, gn)
+                ex = u_exact_nlp(self.fP + s[q] * (self.fQ - self.fP))
+                Rf += wq[:, None] * (-dudn[:, None] * ph + (ex - uq)[:, None] * gn + (bh * (uq - ex))[:, None] * ph)
+            else:
+                Af += wq[:, None, None] * (-ph[:, :, None] * gn[:, None, :] - gn[:, :, None] * ph[:, None, :]
+                                           + bh[:, None, None] * ph[:, :, None] * ph[:, None, :])
+        return Rf if want == 'R' else Af
+
+    def residual(self, u, f):
+        return [(self.cell_dofs, None, self._cells(u, f, 'R')), (self.fdofs, None, self._facets(u, 'R'))]
+
+    def jacobian(self, u, f):
+        return [(self.cell_dofs, self.cell_dofs, self._cells(u, f, 'J')), (self.fdofs, self.fdofs, self._facets(u, 'J'))]
+
+    def dRdm(self, slot, u, f):
+        pts, w = quad.triangle(2)
+        De = np.zeros((self.mesh.ncells, 6, 1))
+        for q in range(len(w)):
+            De[:, :, 0] -= (w[q] * self.detJ)[:, None] * self._phi(self._bary(pts[q]))[None, :]
+        return [(self.cell_dofs, self.dg_dofs, De)]
+
+    def _out(self, u, f, want):
+        pts, w = quad.triangle(12)
+        ue = u[self.cell_dofs]
+        xq = self.xq(pts)
+        val, ge = np.zeros(self.mesh.ncells), np.zeros((self.mesh.ncells, 6))
+        for q in range(len(w)):
+            ph = self._phi(self._bary(pts[q]))
+            eq = ue @ ph - u_exact_nlp(xq[:, q])
+            val += w[q] * self.detJ * 0.5 * eq * eq
+            ge += (w[q] * self.detJ * eq)[:, None] * ph[None, :]
+        return val if want == 'v' else ge
+
+    def output(self, k, u, f):
+        return [self._out(u, f, 'v') + 0.5 * self.detJ * 0.5 * self.alpha * f * f]
+
+    def output_du(self, k, u, f):
+        return [(self.cell_dofs, None, self._out(u, f, 'g'))]
+
+    def output_dm(self, k, slot, u, f):
+        return [(self.dg_dofs, None, (0.5 * self.detJ * self.alpha * f)[:, None])]

@@ -121,6 +121,18 @@ def interval(n, x0, x1):
 # --------------------------------------------------------------------------
 # dofmaps
 # --------------------------------------------------------------------------
+def triangle_edges(mesh):
+    """Edges of a triangle mesh: (edge -> [min vertex, max vertex]) in lexicographic order of that pair, and
+    cell -> edges with local edge i opposite vertex i (basix).  P2 dofs: vertices, then nverts + edge."""
+    c = mesh.cells.astype(np.int64)
+    a = np.stack([c[:, 1], c[:, 0], c[:, 0]], axis=1)
+    b = np.stack([c[:, 2], c[:, 2], c[:, 1]], axis=1)
+    key = np.minimum(a, b) * (mesh.nverts + 1) + np.maximum(a, b)
+    uniq, inv = np.unique(key.ravel(), return_inverse=True)
+    ev = np.stack([uniq // (mesh.nverts + 1), uniq % (mesh.nverts + 1)], axis=1).astype(np.int32)
+    return ev, inv.reshape(-1, 3).astype(np.int32)
+
+
 def dofmap(mesh, family, degree=1, block=1):
     """cell -> dof table, shape (ncells, ndofs_per_cell), and the space size.
 
@@ -135,6 +147,11 @@ def dofmap(mesh, family, degree=1, block=1):
     elif family in ('CG', 'Q') and degree == 1:
         base = mesh.cells
         n = mesh.nverts
+    elif family == 'CG' and degree == 2:
+        assert mesh.kind == 'triangle' and block == 1
+        _, ce = triangle_edges(mesh)
+        base = np.concatenate([mesh.cells, mesh.nverts + ce], axis=1)
+        n = mesh.nverts + int(ce.max()) + 1
     elif family == 'Hermite' and degree == 3:
         assert mesh.kind == 'interval'
         base = mesh.cells

@@ -25,6 +25,9 @@ class Case:
             x = self.omesh.coords
             self.F.u_ex = 1.0 / (2 * np.pi ** 2) * np.sin(np.pi * x[:, 0]) * np.sin(np.pi * x[:, 1])
             use_bc = bc in ('auto', True)
+        elif famid == E.FAMILY_NLPOISSON_P2:
+            self.F = fam.NonlinearPoissonP2(self.omesh)
+            use_bc = False
         else:
             self.F = fam.NonlinearPoissonP1(self.omesh)
             use_bc = bc is True

@@ -202,3 +202,54 @@ def test_topology_example_with_density_filter(cuda_device):
     assert max(rep.values()) < 1e-5, rep
     rep = sim.check_totals('avg_density', 'density_unfiltered', step=1e-3, compact_print=False)
     assert max(rep.values()) < 1e-8, rep
+
+
+def test_topology_example_3d_hex(cuda_device):
+    """The same script on a hexahedral box (SURVEY.md section 8d, C4-3D scaled down): forward solve vs the oracle
+    (GMG-PCG vs SuperLU), compliance / average-density totals w.r.t. the density vs finite differences."""
+    from femo_b200.fea.fea_b200 import (FEA, createBoxMesh, FunctionSpace, VectorFunctionSpace, Function, TestFunction,
+                                         Constant, locate_dofs_geometrical, locate_entities_boundary, meshtags, Measure,
+                                         DOLFIN_EPS)
+    from femo_b200.forms.topo import pdeRes, averageFunc, compliance
+    from femo_b200.csdl_opt import FEAModel, Simulator
+    from oracle import mesh as om, families as fam, assembly as asm, solvers
+    nx, ny, nz, L = 12, 6, 4, (24., 12., 8.)
+    mesh = createBoxMesh(np.zeros(3), np.array(L), nx, ny, nz)
+    tb = locate_entities_boundary(mesh, 2, lambda x: np.logical_and(abs(x[1] - L[1] / 2) < L[1] / ny + DOLFIN_EPS * 1e10,
+                                                                     abs(x[0] - L[0]) < DOLFIN_EPS * 1e10))
+    assert len(tb) == 2 * nz
+    ds_ = Measure('ds', domain=mesh, subdomain_data=meshtags(mesh, 2, tb, np.full(len(tb), 100, dtype=np.int32)))
+    fea = FEA(mesh)
+    Vr = FunctionSpace(mesh, ('DG', 0))
+    rho = Function(Vr)
+    Vu = VectorFunctionSpace(mesh, ('CG', 1))
+    assert Vu.block == 3
+    u = Function(Vu)
+    f = Constant(mesh, (0, -1 / 4, 0))
+    res = pdeRes(u, TestFunction(Vu), rho, f, dss=ds_(100), method='SIMP')
+    fea.add_input('density', rho)
+    fea.add_state(name='displacements', function=u, residual_form=res, arguments=['density'])
+    fea.add_output(name='avg_density', type='scalar', form=averageFunc(rho), arguments=['density'])
+    fea.add_output(name='compliance', type='scalar', form=compliance(u, f, dss=ds_(100)), arguments=['displacements'])
+    fea.add_strong_bc(Function(Vu), [locate_dofs_geometrical((Vu, Vu), lambda x: np.isclose(x[0], 0., atol=1e-6))], Vu)
+    fea.REPORT = False
+    model = FEAModel(fea=[fea], debug_mode=False)
+    np.random.seed(0)
+    x0 = 0.3 + 0.6 * np.random.random(mesh.num_cells)
+    model.create_input('density', shape=mesh.num_cells, val=x0)
+    sim = Simulator(model)
+    sim.run()
+    assert res.fam.problem.mg_levels >= 2 and res.fam.precond == 2
+    m = om.box_hex((0, 0, 0), L, nx, ny, nz)
+    fc, fl = m.exterior_facets()
+    F = fam.SimpHex8(m, tb)
+    nodes = np.nonzero(np.isclose(m.coords[:, 0], 0.0, atol=1e-6))[0]
+    bc = asm.DirichletBC(F.N, [np.stack([3 * nodes, 3 * nodes + 1, 3 * nodes + 2], axis=1).ravel()], 0.0)
+    uo, _ = solvers.StatePath(F, bc).solve_newton(np.zeros(F.N), [x0])
+    assert relerr(sim['displacements'], uo) < 1e-7
+    Co = asm.assemble_scalar(F.output(1, uo, x0))
+    assert abs(sim['compliance'][0] - Co) < 1e-7 * abs(Co)
+    rep = sim.check_totals('compliance', 'density', step=1e-5, compact_print=False)
+    assert max(rep.values()) < 1e-5, rep
+    rep = sim.check_totals('avg_density', 'density', step=1e-3, compact_print=False)
+    assert max(rep.values()) < 1e-8, rep
