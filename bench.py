@@ -34,7 +34,22 @@ N_DIST = 4096          # per-rank lattice of the multi-GPU runs (partitioned mul
 KRYLOV_RTOL = 1e-10
 
 
-def workload(n):
+def workload(n, kind='p1'):
+    if kind == 'p2':
+        dofs = (n + 1) ** 2 + 2 * n * (n + 1) + n * n
+        return dict(workload='nonlinear_poisson_opt P2 unit square n=%d (%d dofs, %d cells), SNES + adjoint, f=0.1, u0=0'
+                    % (n, dofs, 2 * n * n), n=n, dofs=dofs, cells=2 * n * n,
+                    solver='SNES newtonls atol=rtol=1e-13; p-multigrid (P2 -> P1 -> lattice hierarchy) preconditioned CG '
+                           'rtol=%g replaces LU(MUMPS)' % KRYLOV_RTOL,
+                    cache='working set exceeds the 126 MB L2; no explicit flush')
+    if kind == 'hex':
+        nx, ny, nz = n, n // 2, n // 4
+        dofs = 3 * (nx + 1) * (ny + 1) * (nz + 1)
+        return dict(workload='beam_topo_opt 3-D hexahedral SIMP cantilever %dx%dx%d (%d dofs, %d cells), Newton (3 fixed '
+                             'iterations, reference-faithful) + compliance adjoint, density 0.86*U[0,1) seed 0 clipped to '
+                             '[1e-3,1]' % (nx, ny, nz, dofs, nx * ny * nz), n=n, dofs=dofs, cells=nx * ny * nz,
+                    solver='NewtonSolver max_it=3; GMG-preconditioned CG rtol=%g replaces LU(MUMPS)' % KRYLOV_RTOL,
+                    cache='working set exceeds the 126 MB L2; no explicit flush')
     return dict(workload='nonlinear_poisson_opt P1 unit square n=%d (%d dofs, %d cells), SNES + adjoint, f=0.1, u0=0'
                 % (n, (n + 1) ** 2, 2 * n * n), n=n, dofs=(n + 1) ** 2, cells=2 * n * n,
                 solver='SNES newtonls atol=rtol=1e-13; GMG-preconditioned CG rtol=%g replaces LU(MUMPS)' % KRYLOV_RTOL,
@@ -95,11 +110,27 @@ class EngineStep:
     cells), cut into y-slabs: rank r owns N_DIST cell rows + a one-cell ghost layer; halo exchange per
     SpMV, all-reduced Krylov/Newton scalars, partitioned multigrid -- all inside libfemo_b200 over NCCL."""
 
-    def __init__(self, n, device, rank=0, world=1):
+    def __init__(self, n, device, rank=0, world=1, kind='p1'):
         import torch
         from femo_b200 import engine as E
         self.torch = torch
-        if world == 1:
+        self.kind = kind
+        self.out_id = 0
+        if kind == 'hex':
+            import numpy as np
+            nx, ny, nz = n, n // 2, n // 4
+            mesh = E.EngineMesh.box_hex((0.0, 0.0, 0.0), (2.0 * nx, 2.0 * ny, 2.0 * nz), nx, ny, nz)
+            fc, fl = mesh.exterior_facets()
+            p = E.EngineProblem(mesh, E.FAMILY_SIMP_HEX8, [0.3, 0.0, -0.25, 0.0, 3.0],
+                                tagged=np.nonzero(fl == 3)[0].astype(np.int32))         # traction on x = Lx
+            nodes = np.arange((ny + 1) * (nz + 1)) * (nx + 1)                           # clamp x = 0
+            p.set_bc([np.stack([3 * nodes, 3 * nodes + 1, 3 * nodes + 2], axis=1).ravel().astype(np.int32)])
+            self.global_dofs = 3 * (nx + 1) * (ny + 1) * (nz + 1)
+            self.out_id = 1                                                              # compliance
+        elif kind == 'p2':
+            p = E.EngineProblem(E.EngineMesh.unit_square(n), E.FAMILY_NLPOISSON_P2)
+            self.global_dofs = (n + 1) ** 2 + 2 * n * (n + 1) + n * n
+        elif world == 1:
             p = E.EngineProblem(E.EngineMesh.unit_square(n), E.FAMILY_NLPOISSON_P1)
             self.global_dofs = (n + 1) ** 2
         else:
@@ -111,12 +142,17 @@ class EngineStep:
         p.upload(device)
         self.p = p
         self.u = p.new_vector(p.N, 0.0)
-        self.f = p.new_vector(p.M[0], 0.1)
+        if kind == 'hex':
+            import numpy as np
+            self.f = p.to_device(np.clip(0.86 * np.random.default_rng(0).random(p.M[0]), 1e-3, 1.0))
+        else:
+            self.f = p.new_vector(p.M[0], 0.1)
         p.set_coefficient(0, self.u)
         p.set_coefficient(1, self.f)
         nnz = p.pattern_info(0)['nnz']
         self.nnz = nnz
         self.vals = p.new_vector(nnz)
+        self.vals_bc = p.new_vector(nnz) if kind == 'hex' else None
         self.dv = p.new_vector(p.pattern_info(1)['nnz'])
         self.dJdu = p.new_vector(p.N)
         self.grad = p.new_vector(p.M[0])
@@ -126,19 +162,25 @@ class EngineStep:
 
     def step(self):
         p = self.p
+        k = self.out_id
         self.u.zero_()                                        # same work every step (cudaMemset, not a kernel of ours)
-        ni = p.newton_solve(kind='SNES', krylov_rtol=KRYLOV_RTOL, precond=2, cheb_degree=2)
-        p.assemble_jacobian(plain=True, bc=False, out=self.vals)          # dR/du at the converged state
+        if self.kind == 'hex':     # linear problem through the reference's NewtonSolver (3 fixed iterations, quirk B1)
+            ni = p.newton_solve(kind='Newton', krylov_rtol=KRYLOV_RTOL, precond=2, cheb_degree=2)
+            p.assemble_jacobian(plain=True, bc=True, out=self.vals, out_bc=self.vals_bc)
+        else:
+            ni = p.newton_solve(kind='SNES', krylov_rtol=KRYLOV_RTOL, precond=2, cheb_degree=2)
+            p.assemble_jacobian(plain=True, bc=False, out=self.vals)      # dR/du at the converged state
         p.assemble_dRdm(0, self.dv)                                        # dR/df
-        J = p.assemble_output(0)                                           # objective (host scalar)
-        p.assemble_output_grad(0, 0, self.dJdu)
-        p.assemble_output_grad(0, 1, self.grad)
+        J = p.assemble_output(k)                                           # objective (host scalar)
+        p.assemble_output_grad(k, 0, self.dJdu)
+        p.assemble_output_grad(k, 1, self.grad)
         self.lam.zero_()
-        _, li = p.linear_solve(self.vals, self.dJdu, self.lam, transpose=True, rtol=KRYLOV_RTOL, precond=2, cheb_degree=2)
+        _, li = p.linear_solve(self.vals_bc if self.kind == 'hex' else self.vals, self.dJdu, self.lam, transpose=True,
+                               rtol=KRYLOV_RTOL, precond=2, cheb_degree=2)
         p.spmv(1, self.dv, self.lam, transpose=True, out=self.tmp)
         p.axpy(-1.0, self.tmp, self.grad)                                  # dJ/df = pJ/pf - dRdf^T lambda
         self.info = dict(newton_its=ni['iterations'], krylov_its=ni['krylov_iterations'], adjoint_its=li['iterations'],
-                         converged=bool(ni['converged']) and li['converged'], J=J)
+                         converged=(bool(ni['converged']) or self.kind == 'hex') and li['converged'], J=J)
         return J
 
 
@@ -164,7 +206,7 @@ def time_spmv(es, reps=50):
 # API-level step (host buffers): the call a femo user makes
 # ---------------------------------------------------------------------------
 class ApiStep:
-    def __init__(self, n):
+    def __init__(self, n, degree=1):
         import numpy as np
         from femo_b200.fea.fea_b200 import FEA, createUnitSquareMesh, FunctionSpace, Function, TestFunction
         from femo_b200.forms.nonlinear_poisson import pdeRes, outputForm
@@ -174,7 +216,7 @@ class ApiStep:
         mesh = createUnitSquareMesh(n)
         fea = FEA(mesh)
         f = Function(FunctionSpace(mesh, ('DG', 0)))
-        Vu = FunctionSpace(mesh, ('CG', 1))
+        Vu = FunctionSpace(mesh, ('CG', degree))
         u = Function(Vu)
         res = pdeRes(u, TestFunction(Vu), f)
         fea.add_input('f', f)
@@ -244,7 +286,16 @@ def main():
     ap.add_argument('--n', type=int, default=N_DEFAULT)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--workload', default='p1', choices=['p1', 'p2', 'hex'],
+                    help="p1 = BASELINE.json configs[1] (the metric's config, default); p2 / hex = the P2 and 3-D variants "
+                         "named by configs[1] / configs[3], 1 GPU, for profiles/")
     a = ap.parse_args()
+    if a.workload != 'p1':
+        if a.n == N_DEFAULT:
+            a.n = 2000 if a.workload == 'p2' else 256
+        a.no_cpu = True
+        if a.workload == 'hex':
+            a.no_e2e = True
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -290,7 +341,7 @@ def main():
     if world > 1:
         from femo_b200 import dist as fd
         fd.init(local_rank)
-    es = EngineStep(a.n, local_rank, rank, world)
+    es = EngineStep(a.n, local_rank, rank, world, a.workload)
     for _ in range(W):
         es.step()
     sampler = ClockSampler(local_rank)
@@ -325,7 +376,12 @@ def main():
         if world == 1:
             # through the reference-facing API (FEA + FEAModel + Simulator, numpy in / numpy out)
             del es.vals, es.dv                  # the API path owns its own problem
-            api = ApiStep(a.n)
+            if a.workload != 'p1':
+                es_nnz, es_N = es.nnz, es.p.N
+                es.p = None                     # free the engine-level problem's arenas first
+                es.u = es.f = es.dJdu = es.grad = es.lam = es.tmp = None
+                torch.cuda.empty_cache()
+            api = ApiStep(a.n, 2 if a.workload == 'p2' else 1)
             quiet = contextlib.redirect_stdout(io.StringIO())    # the reference prints "Converged reason" per solve
             quiet.__enter__()
             for _ in range(W):
@@ -380,19 +436,21 @@ def main():
         if os.path.exists(pk):
             peaks = json.load(open(pk))
         peak = float(peaks.get('hbm_gbs', 6650.0))
-        nnz, N = es.nnz, es.p.N
+        nnz, N = es.nnz, (es.p.N if es.p is not None else es_N)
         alg = 12.0 * nnz + 20.0 * N
         ach = alg / t_spmv / 1e9
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=W,
                    ms_per_step=ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
-                   data='synthetic', config=dict(workload(a.n), parallelism='1 GPU' if world == 1 else
+                   data='synthetic', config=dict(workload(a.n, a.workload), parallelism='1 GPU' if world == 1 else
                                                  ('one problem on [0,1]x[0,%d], %d x %d cells (%d dofs), y-slab partition '
                                                   'with one-cell ghost layer over %d GPUs, NCCL halo exchange + all-reduce, '
                                                   'partitioned multigrid; value = solves/s x dofs/dofs(N=1 workload)'
                                                   % (world, N_DIST, N_DIST * world, es.global_dofs, world))),
                    clocks=clocks, gpu_launches=int(launches), e2e=e2e,
                    roofline=dict(bound='hbm', kernel='femo::k_spmv (CSR-stream SpMV, fine-level Jacobian)',
-                                 achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None,
+                                 achieved=ach, peak=peak, unit='GB/s', frac=ach / peak,
+                                 traffic=1.652e9 if (a.workload == 'p1' and a.n == 4000 and world == 1) else None,
+                                 traffic_source='profiles/r01_summary.md: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch',
                                  algorithmic_bytes=alg, launch_ms=t_spmv * 1e3,
                                  peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 (of fallback)'),
                    step_info=es.info)

@@ -70,7 +70,8 @@ class FormFamily:
                                  cell_tags=self.cell_tags)
             # what replaces the reference's LU: GMG-preconditioned CG where a lattice hierarchy exists,
             # the explicit inverse for tiny systems, Jacobi-CG otherwise
-            if self.family_id in (_E.FAMILY_POISSON_P1, _E.FAMILY_NLPOISSON_P1, _E.FAMILY_SIMP_Q1, _E.FAMILY_SIMP_HEX8):
+            if self.family_id in (_E.FAMILY_POISSON_P1, _E.FAMILY_NLPOISSON_P1, _E.FAMILY_SIMP_Q1, _E.FAMILY_SIMP_HEX8,
+                                  _E.FAMILY_NLPOISSON_P2):
                 p.enable_multigrid()
                 self.precond = 2 if p.mg_levels > 1 else (3 if p.N <= 512 else 0)
             elif self.family_id in (_E.FAMILY_MOTOR_EM, _E.FAMILY_MOTOR_MM):

@@ -59,6 +59,18 @@ class Mesh:
         self.num_cells = emesh.ncells
         self.num_vertices = emesh.nverts
 
+    def edges(self):
+        """Triangle meshes: (edge -> [min vertex, max vertex], cell -> edges) in the engine's canonical order
+        (edges sorted lexicographically by that pair; local edge i is opposite local vertex i)."""
+        if getattr(self, '_edges', None) is None:
+            c = self.cells.astype(np.int64)
+            a = np.stack([c[:, 1], c[:, 0], c[:, 0]], axis=1)
+            b = np.stack([c[:, 2], c[:, 2], c[:, 1]], axis=1)
+            base = self.num_vertices + 1
+            uniq, inv = np.unique((np.minimum(a, b) * base + np.maximum(a, b)).ravel(), return_inverse=True)
+            self._edges = (np.stack([uniq // base, uniq % base], axis=1).astype(np.int32), inv.reshape(-1, 3).astype(np.int32))
+        return self._edges
+
     def h(self):
         """Cell diameters (dolfinx.cpp.mesh.h, utils_dolfinx.py:526-530)."""
         x = self.geometry.x[self.cells]
@@ -94,6 +106,10 @@ class FunctionSpace:
             nnodes = mesh.num_cells
         elif (family, degree) == ('CG', 1):
             nnodes = mesh.num_vertices
+        elif (family, degree) == ('CG', 2):
+            if mesh.cell_type != 'triangle' or block != 1:
+                raise ValueError('femo_b200: CG2 kernels exist for scalar spaces on triangles')
+            nnodes = mesh.num_vertices + mesh.edges()[0].shape[0]
         elif (family, degree) == ('Hermite', 3):
             nnodes, block = mesh.num_vertices, 2
         else:
@@ -108,6 +124,10 @@ class FunctionSpace:
     def node_coordinates(self):
         if self.family == 'DG':
             return self.mesh.geometry.x[self.mesh.cells].mean(axis=1)
+        if self.degree == 2:                       # vertices, then edge midpoints (engine's P2 numbering)
+            ev = self.mesh.edges()[0]
+            X = self.mesh.geometry.x
+            return np.concatenate([X, 0.5 * (X[ev[:, 0]] + X[ev[:, 1]])])
         return self.mesh.geometry.x
 
     def tabulate_dof_coordinates(self):

@@ -20,7 +20,9 @@ f_ex_ufl = Expr('f_ex')
 
 
 def _family(u, f):
-    return FormFamily.get(_E.FAMILY_NLPOISSON_P1, u.function_space.mesh, u, [f], params=[ALPHA_1, BETA])
+    # V = CG1 as in the example script, or CG2 (the "P2" variant of BASELINE.json configs[1])
+    fid = _E.FAMILY_NLPOISSON_P2 if u.function_space.degree == 2 else _E.FAMILY_NLPOISSON_P1
+    return FormFamily.get(fid, u.function_space.mesh, u, [f], params=[ALPHA_1, BETA])
 
 
 def pdeRes(u, v, f, u_exact=U_EX_UFL, weak_bc=True, sym=True, overPenalize=False):

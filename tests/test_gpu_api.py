@@ -76,17 +76,18 @@ def test_poisson_opt_forward_and_totals(cuda_device):
     assert relerr(gc, go) > 1e-6
 
 
-def test_nonlinear_poisson_check_totals(cuda_device):
+@pytest.mark.parametrize('degree', [1, 2])
+def test_nonlinear_poisson_check_totals(cuda_device, degree):
     """examples/nonlinear_poisson_opt: SNES state solve, then adjoint totals vs
     central finite differences through the full callback chain (no strong BC, so
-    reference-faithful and consistent totals coincide)."""
+    reference-faithful and consistent totals coincide).  degree 2 = the P2 variant of the same script."""
     from femo_b200.fea.fea_b200 import FEA, createUnitSquareMesh, FunctionSpace, Function, TestFunction
     from femo_b200.forms.nonlinear_poisson import pdeRes, outputForm
     from femo_b200.csdl_opt import FEAModel, Simulator
     mesh = createUnitSquareMesh(12)
     fea = FEA(mesh)
     f = Function(FunctionSpace(mesh, ('DG', 0)))
-    Vu = FunctionSpace(mesh, ('CG', 1))
+    Vu = FunctionSpace(mesh, ('CG', degree))
     u = Function(Vu)
     residual_form = pdeRes(u, TestFunction(Vu), f)
     fea.add_input('f', f)
@@ -101,7 +102,7 @@ def test_nonlinear_poisson_check_totals(cuda_device):
     assert max(rep.values()) < 1e-6
     # and against the oracle's reference-ordered chain
     m = om.unit_square_tri(12)
-    F = fam.NonlinearPoissonP1(m)
+    F = fam.NonlinearPoissonP1(m) if degree == 1 else fam.NonlinearPoissonP2(m)
     sp = solvers.StatePath(F, None)
     f0 = 0.1 * np.ones(F.M)
     uo, _ = sp.solve_snes(np.zeros(F.N), [f0])
