@@ -71,6 +71,8 @@ SIGNATURES = {
     'femo_comm_finalize': (C.c_int, []),
     'femo_comm_stats': (C.c_int, [C.POINTER(C.c_longlong)]),
     'femo_problem_create_slab': (C.c_int, [C.c_int, _DP, C.c_int, C.c_int, C.c_int, _DP, _DP, C.c_int, C.c_int, C.POINTER(_P)]),
+    'femo_problem_create_slab_hex': (C.c_int, [C.c_int, _DP, C.c_int, C.c_int, C.c_int, C.c_int, _DP, _DP, C.c_int, C.c_int,
+                                     C.c_int, C.POINTER(_P)]),
     'femo_problem_slab_info': (C.c_int, [_P, _I64P]),
     'femo_halo_exchange': (C.c_int, [_P, _P, C.c_int]),
     'femo_problem_mesh_sizes': (C.c_int, [_P, _I64P]),

@@ -10,7 +10,7 @@ using namespace femo;
 static int halo_nodes(femo_problem *p, double *v) {
     const SlabInfo &s = p->slab;
     if (!s.active || !g_comm.active) return FEMO_OK;
-    const size_t len = (size_t)(p->mesh.n[0] + 1) * p->state.block;
+    const size_t len = (size_t)(p->mesh.n[0] + 1) * (p->mesh.kind == MESH_HEX ? (size_t)(p->mesh.n[1] + 1) : 1) * p->state.block;
     NcclApi &a = g_comm.api;
     FEMO_NCCL(a.GroupStart());
     if (s.rank > 0) {
@@ -61,5 +61,13 @@ static int gather_rows(femo_problem *p, double *g, size_t len, int gny) {
     FEMO_NCCL(g_comm.api.AllGather(g + (size_t)g_comm.rank * blk, g, blk, ncclDouble, g_comm.comm, p->stream));
     FEMO_NCCL(g_comm.api.Broadcast(g + (size_t)gny * len, g + (size_t)gny * len, len, ncclDouble, R - 1, g_comm.comm,
                                    p->stream));
+    return FEMO_OK;
+}
+
+// Same for a replicated cell-wise vector (no extra top row): rank r has filled cell rows [r*rows, (r+1)*rows).
+static int gather_cell_rows(femo_problem *p, double *g, size_t len, int gn) {
+    if (!g_comm.active) return FEMO_OK;
+    const size_t blk = (size_t)(gn / g_comm.nranks) * len;
+    FEMO_NCCL(g_comm.api.AllGather(g + (size_t)g_comm.rank * blk, g, blk, ncclDouble, g_comm.comm, p->stream));
     return FEMO_OK;
 }

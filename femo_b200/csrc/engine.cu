@@ -988,6 +988,41 @@ static int create_slab_problem(int family, const double *params, int nparams, in
     return FEMO_OK;
 }
 
+// local problem of rank `rank` on its z-slab of the hexahedral box; `face_mask` bit l tags every exterior facet with
+// local facet id l (0 z=lo, 1 y=lo, 2 x=lo, 3 x=hi, 4 y=hi, 5 z=hi) as a traction facet ds(100)
+static int create_slab_problem_hex(int family, const double *params, int nparams, int nx, int ny, int gnz, const double lo[3],
+                                   const double hi[3], int rank, int nranks, bool jac_only, int face_mask, femo_problem **out) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || gnz % nranks != 0 || gnz / nranks < 2)
+        return set_err(FEMO_EINVAL, "slab partition needs gnz divisible by the number of ranks and >= 2 layers per rank");
+    SlabInfo sl = make_slab(gnz, rank, nranks);
+    Mesh m;
+    make_box_hex_slab(nx, ny, gnz, sl.crow0, sl.ncrows, lo, hi, m);
+    std::vector<int32_t> tagged;
+    for (size_t k = 0; k < m.bf_local.size(); ++k)
+        if ((face_mask >> m.bf_local[k]) & 1) tagged.push_back((int32_t)k);
+    int rc = create_problem_impl(m, family, params, nparams, jac_only, tagged.data(), (int)tagged.size(), out);
+    if (rc) return rc;
+    femo_problem *p = *out;
+    p->slab = sl;
+    const int64_t row_len = (int64_t)(nx + 1) * (ny + 1) * p->state.block, crow_len = (int64_t)nx * ny;
+    p->own_off = sl.own0 * row_len;
+    p->own_n = (int64_t)(sl.own1 - sl.own0) * row_len;
+    p->cown_off = sl.cown0 * crow_len;
+    p->cown_n = (int64_t)(sl.cown1 - sl.cown0) * crow_len;
+    p->fown_off = 0;
+    while (p->fown_off < (int64_t)p->fb_cell.size() && p->fb_cell[p->fown_off] < p->cown_off) p->fown_off++;
+    p->face_mask = face_mask;
+    return FEMO_OK;
+}
+
+int femo_problem_create_slab_hex(int family, const double *params, int nparams, int nx, int ny, int gnz, const double lo[3],
+                                 const double hi[3], int rank, int nranks, int face_mask, femo_problem **out) {
+    if (!out || !lo || !hi || nx < 1 || ny < 1 || nparams < 0 || nparams > 8)
+        return set_err(FEMO_EINVAL, "femo_problem_create_slab_hex: bad arguments");
+    if (family != FEMO_FAMILY_SIMP_HEX8) return set_err(FEMO_EINVAL, "z-slab partitioning is available for the hexahedral SIMP family");
+    return create_slab_problem_hex(family, params, nparams, nx, ny, gnz, lo, hi, rank, nranks, false, face_mask, out);
+}
+
 int femo_problem_create_slab(int family, const double *params, int nparams, int nx, int gny, const double lo[2],
                              const double hi[2], int rank, int nranks, femo_problem **out) {
     if (!out || !lo || !hi || nx < 1 || nparams < 0 || nparams > 8) return set_err(FEMO_EINVAL, "femo_problem_create_slab: bad arguments");
@@ -1039,7 +1074,43 @@ static int dist_min_rows() {
     return v < 2 ? 2 : v;
 }
 
+static int enable_multigrid_slab_hex(femo_problem *p) {
+    int nx = p->mesh.n[0], ny = p->mesh.n[1], gnz = p->slab.gny;
+    const int R = p->slab.nranks, rank = p->slab.rank;
+    int rows = gnz / R, rc;
+    const int kDistMinRows = std::max(2, dist_min_rows() / 8);     // a z-layer holds a whole plane of nodes
+    // one more distributed level only if a 2:1 nested replicated level still fits below it
+    while (rows % 4 == 0 && nx % 4 == 0 && ny % 4 == 0 && rows / 2 >= kDistMinRows) {
+        nx /= 2; ny /= 2; gnz /= 2; rows /= 2;
+        femo_problem *c = nullptr;
+        if ((rc = create_slab_problem_hex(p->family, p->params, 32, nx, ny, gnz, p->mesh.lo, p->mesh.hi, rank, R, true, 0, &c))) return rc;
+        c->parent = p;
+        p->mg.push_back(c);
+    }
+    if (rows % 2 != 0 || nx % 2 != 0 || ny % 2 != 0)
+        return set_err(FEMO_EINVAL, "partitioned multigrid needs nx, ny and layers-per-rank divisible by 2 down to the replicated level (use powers of two)");
+    nx /= 2; ny /= 2; gnz /= 2;                                  // replicated levels: the whole coarse box on every rank
+    bool first = true;
+    while (first || nx > 4 || ny > 4 || gnz > 4 || (int64_t)(nx + 1) * (ny + 1) * (gnz + 1) * 3 > kMgDenseMax) {
+        if (!first) {
+            if (nx == 1 && ny == 1 && gnz == 1) break;
+            nx = std::max(1, (nx + 1) / 2); ny = std::max(1, (ny + 1) / 2); gnz = std::max(1, (gnz + 1) / 2);
+        }
+        first = false;
+        Mesh cm;
+        make_box_hex(nx, ny, gnz, p->mesh.lo, p->mesh.hi, cm);
+        femo_problem *c = nullptr;
+        if ((rc = create_problem_impl(cm, p->family, p->params, 32, true, nullptr, 0, &c))) return rc;
+        c->parent = p;
+        c->replicated = true;
+        p->mg.push_back(c);
+    }
+    if (!p->bc_mark.empty()) return propagate_bc(p);
+    return FEMO_OK;
+}
+
 static int enable_multigrid_slab(femo_problem *p) {
+    if (p->mesh.kind == MESH_HEX) return enable_multigrid_slab_hex(p);
     int nx = p->mesh.n[0], gny = p->slab.gny;
     const int R = p->slab.nranks, rank = p->slab.rank;
     int rows = gny / R, rc;
@@ -1219,16 +1290,20 @@ static int propagate_bc(femo_problem *root, int start) {
         }
         std::vector<int32_t> list;
         const int fnx = F->mesh.n[0], fny = F->mesh.n[1], cnx = C->mesh.n[0], cny = C->mesh.n[1];
-        const int fj0 = F->slab.active ? F->slab.crow0 : 0, cj0 = C->slab.active ? C->slab.crow0 : 0;
-        const int fg = F->slab.active ? F->slab.gny : fny, cg = C->slab.active ? C->slab.gny : cny;
         const int fnz = F->mesh.n[2], cnz = C->mesh.n[2];                          // 0 on planar lattices
+        const bool zslab = cnz > 0;                                                 // slabs cut the last lattice axis
+        const int fs0 = F->slab.active ? F->slab.crow0 : 0, cs0 = C->slab.active ? C->slab.crow0 : 0;
+        const int fj0 = zslab ? 0 : fs0, cj0 = zslab ? 0 : cs0, fk0 = zslab ? fs0 : 0, ck0 = zslab ? cs0 : 0;
+        const int fg = (!zslab && F->slab.active) ? F->slab.gny : fny, cg = (!zslab && C->slab.active) ? C->slab.gny : cny;
+        const int fgz = (zslab && F->slab.active) ? F->slab.gny : fnz, cgz = (zslab && C->slab.active) ? C->slab.gny : cnz;
         for (int K = 0; K <= cnz; ++K)
         for (int J = 0; J <= cny; ++J)
             for (int I = 0; I <= cnx; ++I) {
                 const int i = (int)std::llround((double)I * fnx / cnx);
                 int j = (int)std::llround((double)(J + cj0) * fg / cg) - fj0;     // nearest fine row, local index
                 j = std::min(std::max(j, 0), fny);                                 // ghost rows without a local parent: same column
-                const int k = cnz ? (int)std::llround((double)K * fnz / cnz) : 0;
+                int k = cnz ? (int)std::llround((double)(K + ck0) * fgz / cgz) - fk0 : 0;
+                k = std::min(std::max(k, 0), fnz);
                 const int bs = F->state.block;
                 for (int cc = 0; cc < bs; ++cc)
                     if (!F->bc_mark.empty() && F->bc_mark[(((int64_t)k * (fny + 1) + j) * (fnx + 1) + i) * bs + cc])
@@ -1711,9 +1786,15 @@ int femo_assemble_output(femo_problem *p, int out_id, double *h_value) {
     const double *src = p->d_scratch;
     int64_t cnt = n;
     if (p->slab.active) {
-        if (om != 1) return set_err(FEMO_EINVAL, "facet functionals are not partitioned yet");
-        src += p->cown_off;
-        cnt = p->cown_n;
+        if (om == 1) {
+            src += p->cown_off;
+            cnt = p->cown_n;
+        } else if (om == 2) {           // facets are sorted by cell: the owned ones are a suffix
+            src += p->fown_off;
+            cnt = (int64_t)p->fb_cell.size() - p->fown_off;
+        } else {
+            return set_err(FEMO_EINVAL, "mixed cell + facet functionals are not partitioned");
+        }
     }
     int g = red_grid(p, cnt);
     k_sum<<<g, kThreads, 0, p->stream>>>(src, cnt, p->d_partials);

@@ -89,6 +89,10 @@ void make_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2],
 }
 
 void make_box_hex(int nx, int ny, int nz, const double lo[3], const double hi[3], Mesh &m) {
+    make_box_hex_slab(nx, ny, nz, 0, nz, lo, hi, m);
+}
+
+void make_box_hex_slab(int nx, int ny, int gnz, int k0, int nz, const double lo[3], const double hi[3], Mesh &m) {
     m = Mesh();
     m.kind = MESH_HEX;
     m.nvpc = 8;
@@ -105,7 +109,7 @@ void make_box_hex(int nx, int ny, int nz, const double lo[3], const double hi[3]
                 const int64_t v = ((int64_t)iz * sy + iy) * sx + ix;
                 m.coords[3 * v] = lo[0] + (hi[0] - lo[0]) * (double)ix / (double)nx;
                 m.coords[3 * v + 1] = lo[1] + (hi[1] - lo[1]) * (double)iy / (double)ny;
-                m.coords[3 * v + 2] = lo[2] + (hi[2] - lo[2]) * (double)iz / (double)nz;
+                m.coords[3 * v + 2] = lo[2] + (hi[2] - lo[2]) * (double)(k0 + iz) / (double)gnz;
             }
     m.cells.resize(m.ncells * 8);
     for (int iz = 0; iz < nz; ++iz)
@@ -116,12 +120,12 @@ void make_box_hex(int nx, int ny, int nz, const double lo[3], const double hi[3]
                 int32_t *a = &m.cells[c * 8];
                 for (int k = 0; k < 8; ++k)
                     a[k] = (int32_t)(v0 + (k & 1) + ((k >> 1) & 1) * sx + ((k >> 2) & 1) * sx * sy);
-                if (iz == 0)      { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(0); }
+                if (iz == 0 && k0 == 0) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(0); }
                 if (iy == 0)      { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(1); }
                 if (ix == 0)      { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(2); }
                 if (ix == nx - 1) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(3); }
                 if (iy == ny - 1) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(4); }
-                if (iz == nz - 1) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(5); }
+                if (iz == nz - 1 && k0 + nz == gnz) { m.bf_cell.push_back((int32_t)c); m.bf_local.push_back(5); }
             }
 }
 

@@ -49,6 +49,9 @@ void make_interval(int n, double x0, double x1, Mesh &m);
 // cell (ix,iy,iz) -> (iz*ny+iy)*nx+ix with the tensor-product vertex order of basix (x fastest) and
 // facets 0 z=lo, 1 y=lo, 2 x=lo, 3 x=hi, 4 y=hi, 5 z=hi [upstream, from memory]
 void make_box_hex(int nx, int ny, int nz, const double lo[3], const double hi[3], Mesh &m);
+// z-slab of the (nx x ny x gnz)-cell box: cell layers [k0, k0+nk); z coordinates from the GLOBAL formula; the
+// z = lo / z = hi faces carry exterior facets only where the slab touches the true boundary
+void make_box_hex_slab(int nx, int ny, int gnz, int k0, int nk, const double lo[3], const double hi[3], Mesh &m);
 // periodic polar lattice on the annulus r0 <= r <= r1: node (ir, ith) -> ir*nth + ith
 void make_annulus_tri(int nr, int nth, double r0, double r1, Mesh &m);
 

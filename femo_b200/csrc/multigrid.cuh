@@ -279,6 +279,100 @@ __global__ void __launch_bounds__(kThreads)
     uc[idx] = (j >= 0 && j < f.nrows) ? uf[(int64_t)j * fw + 2 * I] : 0.0;
 }
 
+// ---- the same three kernels for 2:1 nested hexahedral lattices cut into z-slabs (trilinear weights) ----------
+struct LatD3 {
+    int nx, ny, nplanes, k0;   // cells in x / y, local node planes, global index of local plane 0
+};
+
+__global__ void __launch_bounds__(kThreads)
+    k_prolong_nested3(LatD3 f, LatD3 c, int block, const double *__restrict__ xc, double *__restrict__ xf,
+                      const uint8_t *__restrict__ mask_f) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int fw = f.nx + 1, fh = f.ny + 1, cw = c.nx + 1, ch = c.ny + 1;
+    if (idx >= (int64_t)fw * fh * f.nplanes * block) return;
+    if (mask_f && mask_f[idx]) return;
+    const int comp = (int)(idx % block);
+    const int64_t node = idx / block;
+    const int i = (int)(node % fw), j = (int)((node / fw) % fh), kl = (int)(node / ((int64_t)fw * fh));
+    const int gk = kl + f.k0;
+    const int I = i >> 1, oi = i & 1, J = j >> 1, oj = j & 1, ok = gk & 1;
+    const int Kl = (gk >> 1) - c.k0;
+    if (Kl < 0 || Kl + ok >= c.nplanes) return;
+    double acc = 0.0;
+    for (int d = 0; d <= ok; ++d)
+        for (int b = 0; b <= oj; ++b)
+            for (int a = 0; a <= oi; ++a) acc += xc[((((int64_t)(Kl + d) * ch) + (J + b)) * cw + (I + a)) * block + comp];
+    const double w = 1.0 / (double)((1 + oi) * (1 + oj) * (1 + ok));
+    xf[idx] += w * acc;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_restrict_nested3(LatD3 f, LatD3 c, int block, const double *__restrict__ rf, double *__restrict__ rc,
+                       const uint8_t *__restrict__ mask_f, const uint8_t *__restrict__ mask_c) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int fw = f.nx + 1, fh = f.ny + 1, cw = c.nx + 1, ch = c.ny + 1;
+    if (idx >= (int64_t)cw * ch * c.nplanes * block) return;
+    if (mask_c && mask_c[idx]) {
+        rc[idx] = 0.0;
+        return;
+    }
+    const int comp = (int)(idx % block);
+    const int64_t node = idx / block;
+    const int I = (int)(node % cw), J = (int)((node / cw) % ch), Kl = (int)(node / ((int64_t)cw * ch));
+    const int i = 2 * I, j = 2 * J, k = 2 * (Kl + c.k0) - f.k0;   // fine LOCAL plane of the coincident node
+    double acc = 0.0;
+    for (int dk = -1; dk <= 1; ++dk) {
+        const int kk = k + dk;
+        if (kk < 0 || kk >= f.nplanes) continue;
+        for (int dj = -1; dj <= 1; ++dj) {
+            const int jj = j + dj;
+            if (jj < 0 || jj > f.ny) continue;
+            for (int di = -1; di <= 1; ++di) {
+                const int ii = i + di;
+                if (ii < 0 || ii > f.nx) continue;
+                const int64_t q = ((((int64_t)kk * fh) + jj) * fw + ii) * block + comp;
+                if (mask_f && mask_f[q]) continue;
+                acc += rf[q] * ((di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * (dk ? 0.5 : 1.0));
+            }
+        }
+    }
+    rc[idx] = acc;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_inject_nested3(LatD3 f, LatD3 c, int block, const double *__restrict__ uf, double *__restrict__ uc) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int fw = f.nx + 1, fh = f.ny + 1, cw = c.nx + 1, ch = c.ny + 1;
+    if (idx >= (int64_t)cw * ch * c.nplanes * block) return;
+    const int comp = (int)(idx % block);
+    const int64_t node = idx / block;
+    const int I = (int)(node % cw), J = (int)((node / cw) % ch), Kl = (int)(node / ((int64_t)cw * ch));
+    const int k = 2 * (Kl + c.k0) - f.k0;
+    uc[idx] = (k >= 0 && k < f.nplanes) ? uf[((((int64_t)k * fh) + 2 * J) * fw + 2 * I) * block + comp] : 0.0;
+}
+
+// power-mean coarse density on 2:1 nested slabs: coarse local cell layer Kl <- fine local layers 2(Kl+ck0)-fk0, +1;
+// layers outside the local slab are skipped (the ghost layer is refreshed by halo_cells afterwards)
+__global__ void __launch_bounds__(kThreads)
+    k_restrict_cells_power_nested3(int cnx, int cny, int cnl, int ck0, int fnl, int fk0, double p, const double *__restrict__ rf,
+                                   double *__restrict__ rc) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)cnx * cny * cnl) return;
+    const int I = (int)(idx % cnx), J = (int)((idx / cnx) % cny), Kl = (int)(idx / ((int64_t)cnx * cny));
+    const int fnx = 2 * cnx, fny = 2 * cny, k = 2 * (Kl + ck0) - fk0;
+    double acc = 0.0;
+    int cnt = 0;
+    for (int d = 0; d < 2; ++d) {
+        if (k + d < 0 || k + d >= fnl) continue;
+        for (int b = 0; b < 2; ++b)
+            for (int a = 0; a < 2; ++a) {
+                acc += pow(rf[((int64_t)(k + d) * fny + (2 * J + b)) * fnx + (2 * I + a)], p);
+                ++cnt;
+            }
+    }
+    rc[idx] = cnt ? pow(acc / cnt, 1.0 / p) : 1.0;
+}
+
 // Gershgorin bound of D^-1 A (max_i sum_j |a_ij| / |a_ii|) and dinv in one pass
 __global__ void __launch_bounds__(kThreads)
     k_diag_gershgorin(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ vals,
@@ -503,7 +597,19 @@ static inline LatD latd_of(const femo_problem *p) {
 }
 // global cell rows of a level (slab: of the partitioned lattice)
 static inline int global_rows(const femo_problem *p) { return p->slab.active ? p->slab.gny : p->mesh.n[1]; }
+static inline LatD3 latd3_of(const femo_problem *p) {
+    return LatD3{p->mesh.n[0], p->mesh.n[1], p->mesh.n[2] + 1, p->slab.active ? p->slab.crow0 : 0};
+}
+// dofs in one slab row (a lattice row in 2-D, a z-plane of nodes for hexahedra)
+static inline size_t slab_row_len(const femo_problem *p) {
+    return (size_t)(p->mesh.n[0] + 1) * (p->mesh.kind == MESH_HEX ? (size_t)(p->mesh.n[1] + 1) : 1) * p->state.block;
+}
+static inline int slab_axis_cells(const femo_problem *p) { return p->mesh.kind == MESH_HEX ? p->mesh.n[2] : p->mesh.n[1]; }
 static inline bool nested_pair(const femo_problem *F, const femo_problem *C) {
+    if (F->mesh.kind == MESH_HEX && F->state.element == EL_VERTEX) {
+        const int gf = F->slab.active ? F->slab.gny : F->mesh.n[2], gc = C->slab.active ? C->slab.gny : C->mesh.n[2];
+        return F->mesh.n[0] == 2 * C->mesh.n[0] && F->mesh.n[1] == 2 * C->mesh.n[1] && gf == 2 * gc;
+    }
     if (F->mesh.kind != MESH_TRI || F->state.block != 1) return false;   // integer-only kernels: scalar P1
     return F->mesh.n[0] == 2 * C->mesh.n[0] && global_rows(F) == 2 * global_rows(C);
 }
@@ -554,10 +660,13 @@ static int mg_restrict(femo_problem *L, femo_problem *C, double *rf, double *rc_
     }
     if (nested_pair(L, C)) {
         if ((rc = halo_nodes(L, rf))) return rc;                  // coarse owned rows read the fine ghost row below
-        k_restrict_nested<<<grid_for(nc), kThreads, 0, st>>>(latd_of(L), latd_of(C), rf, rc_, mf, mc);
+        if (L->mesh.kind == MESH_HEX)
+            k_restrict_nested3<<<grid_for(nc), kThreads, 0, st>>>(latd3_of(L), latd3_of(C), L->state.block, rf, rc_, mf, mc);
+        else
+            k_restrict_nested<<<grid_for(nc), kThreads, 0, st>>>(latd_of(L), latd_of(C), rf, rc_, mf, mc);
         L->launches++;
         if (L->slab.active && !C->slab.active)                     // distributed -> replicated level
-            if ((rc = gather_rows(L, rc_, (size_t)(C->mesh.n[0] + 1), C->mesh.n[1]))) return rc;
+            if ((rc = gather_rows(L, rc_, slab_row_len(C), slab_axis_cells(C)))) return rc;
     } else {
         if (L->slab.active) return set_err(FEMO_ESTATE, "distributed multigrid levels must be 2:1 nested");
         if (L->mesh.kind == MESH_HEX)
@@ -583,7 +692,10 @@ static int mg_prolong_add(femo_problem *L, femo_problem *C, double *xc, double *
     }
     if (nested_pair(L, C)) {
         if ((rc = halo_nodes(C, xc))) return rc;                   // fine owned rows read the coarse ghost row above
-        k_prolong_nested<<<grid_for(n), kThreads, 0, st>>>(latd_of(L), latd_of(C), xc, xf, mf);
+        if (L->mesh.kind == MESH_HEX)
+            k_prolong_nested3<<<grid_for(n), kThreads, 0, st>>>(latd3_of(L), latd3_of(C), L->state.block, xc, xf, mf);
+        else
+            k_prolong_nested<<<grid_for(n), kThreads, 0, st>>>(latd_of(L), latd_of(C), xc, xf, mf);
     } else if (L->mesh.kind == MESH_HEX) {
         k_lattice3_interp<true><<<grid_for(n), kThreads, 0, st>>>(lat3_of(C->mesh), lat3_of(L->mesh), L->state.block, xc, xf, mf);
     } else {
@@ -655,10 +767,13 @@ static int sync_replicated_bc(femo_problem *root) {
     int rc;
     double *tf = F->mgl.r, *tc = C->mgl.x;
     k_u8_to_f64<<<grid_for(nf), kThreads, 0, st>>>(F->d_bc_mark, tf, nf);
-    k_inject_nested<<<grid_for(nc), kThreads, 0, st>>>(latd_of(F), latd_of(C), tf, tc);
+    if (F->mesh.kind == MESH_HEX)
+        k_inject_nested3<<<grid_for(nc), kThreads, 0, st>>>(latd3_of(F), latd3_of(C), F->state.block, tf, tc);
+    else
+        k_inject_nested<<<grid_for(nc), kThreads, 0, st>>>(latd_of(F), latd_of(C), tf, tc);
     root->launches += 2;
     FEMO_CHECK_LAUNCH();
-    if ((rc = gather_rows(F, tc, (size_t)(C->mesh.n[0] + 1), C->mesh.n[1]))) return rc;
+    if ((rc = gather_rows(F, tc, slab_row_len(C), slab_axis_cells(C)))) return rc;
     std::vector<double> h(nc);
     FEMO_CUDA(cudaMemcpyAsync(h.data(), tc, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
     FEMO_CUDA(cudaStreamSynchronize(st));
@@ -691,12 +806,15 @@ static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true) {
             if (F->state.element == EL_P2) {                      // vertex values of the P2 state
                 FEMO_CUDA(cudaMemcpyAsync(M.u, uf, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
             } else if (nested_pair(F, L)) {
-                k_inject_nested<<<grid_for(n), kThreads, 0, st>>>(latd_of(F), latd_of(L), uf, M.u);
+                if (L->mesh.kind == MESH_HEX)
+                    k_inject_nested3<<<grid_for(n), kThreads, 0, st>>>(latd3_of(F), latd3_of(L), L->state.block, uf, M.u);
+                else
+                    k_inject_nested<<<grid_for(n), kThreads, 0, st>>>(latd_of(F), latd_of(L), uf, M.u);
                 L->launches++;
                 if (L->slab.active) {
                     if ((rc = halo_nodes(L, M.u))) return rc;      // the ghost row below has no local fine parent
                 } else if (F->slab.active) {
-                    if ((rc = gather_rows(F, M.u, (size_t)(L->mesh.n[0] + 1), L->mesh.n[1]))) return rc;
+                    if ((rc = gather_rows(F, M.u, slab_row_len(L), slab_axis_cells(L)))) return rc;
                 }
             } else {
                 if (F->slab.active) return set_err(FEMO_ESTATE, "distributed multigrid levels must be 2:1 nested");
@@ -712,7 +830,17 @@ static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true) {
                 const double *mf_ = (lv == 1) ? root->coef[1] : F->mgl.m;
                 if (!mf_) return set_err(FEMO_ESTATE, "multigrid setup: density coefficient not set");
                 const int64_t ncell = L->mesh.ncells;
-                k_restrict_cells_power3<<<grid_for(ncell), kThreads, 0, st>>>(lat3_of(F->mesh), lat3_of(L->mesh), L->params[4], mf_, M.m);
+                if (F->slab.active) {       // distributed fine level: 2:1 nested, addressed through global layers
+                    if (lv == 1 && (rc = halo_cells(F, const_cast<double *>(mf_)))) return rc;
+                    k_restrict_cells_power_nested3<<<grid_for(ncell), kThreads, 0, st>>>(
+                        L->mesh.n[0], L->mesh.n[1], L->mesh.n[2], L->slab.active ? L->slab.crow0 : 0, F->mesh.n[2], F->slab.crow0,
+                        L->params[4], mf_, M.m);
+                    if (L->slab.active) {
+                        if ((rc = halo_cells(L, M.m))) return rc;
+                    } else if ((rc = gather_cell_rows(F, M.m, (size_t)L->mesh.n[0] * L->mesh.n[1], L->mesh.n[2]))) return rc;
+                } else {
+                    k_restrict_cells_power3<<<grid_for(ncell), kThreads, 0, st>>>(lat3_of(F->mesh), lat3_of(L->mesh), L->params[4], mf_, M.m);
+                }
                 L->launches++;
                 L->coef[1] = M.m;
                 L->coefn[1] = ncell;

@@ -47,11 +47,18 @@ class SlabProblem(_E.EngineProblem):
     """The local problem of one rank: y-slab of an (nx x gny)-cell triangle lattice
     on [lo, hi] with a one-cell ghost layer (host-side layout needs no GPU)."""
 
-    def __init__(self, family, nx, gny, rank, nranks, lo=(0.0, 0.0), hi=(1.0, 1.0), params=()):
+    def __init__(self, family, nx, gny, rank, nranks, lo=(0.0, 0.0), hi=(1.0, 1.0), params=(), ny=None, face_mask=0):
+        """Triangle families: y-slab of the (nx x gny) lattice.  Hexahedral SIMP family (pass ny): z-slab of the
+        (nx x ny x gny) box, lo / hi with three entries, face_mask = box faces carrying the traction."""
         h = C.c_void_p()
         pa = (C.c_double * max(1, len(params)))(*params)
-        check(lib.femo_problem_create_slab(int(family), pa, len(params), int(nx), int(gny), (C.c_double * 2)(*lo),
-                                           (C.c_double * 2)(*hi), int(rank), int(nranks), C.byref(h)))
+        if ny is None:
+            check(lib.femo_problem_create_slab(int(family), pa, len(params), int(nx), int(gny), (C.c_double * 2)(*lo),
+                                               (C.c_double * 2)(*hi), int(rank), int(nranks), C.byref(h)))
+        else:
+            check(lib.femo_problem_create_slab_hex(int(family), pa, len(params), int(nx), int(ny), int(gny),
+                                                   (C.c_double * 3)(*lo), (C.c_double * 3)(*hi), int(rank), int(nranks),
+                                                   int(face_mask), C.byref(h)))
         self.mesh = None
         self.family = family
         self._h = h

@@ -125,6 +125,11 @@ int femo_comm_stats(long long stats[2]);   /* [halo exchanges, all-reduces] issu
 /* Host only: the local problem of `rank` on the (nx x gny)-cell triangle lattice over [lo,hi]. */
 int femo_problem_create_slab(int family, const double *params, int nparams, int nx, int gny, const double lo[2],
                              const double hi[2], int rank, int nranks, femo_problem **out);
+/* z-slab of the (nx x ny x gnz)-cell hexahedral box for rank `rank` (cell partition with a one-cell
+ * ghost layer; a z-plane of nodes is contiguous, so halo planes are sent in place).  face_mask bit l tags the exterior
+ * facets with local facet id l (0 z=lo, 1 y=lo, 2 x=lo, 3 x=hi, 4 y=hi, 5 z=hi) as the traction measure ds(100). */
+int femo_problem_create_slab_hex(int family, const double *params, int nparams, int nx, int ny, int gnz, const double lo[3],
+                                 const double hi[3], int rank, int nranks, int face_mask, femo_problem **out);
 /* info: active, rank, nranks, gny, first local cell row, local cell rows, owned node rows [own0,own1),
  * owned cell rows [cown0,cown1) (local indices), own_off, own_n (dofs), cown_off, cown_n (cells), nx, ny_local */
 int femo_problem_slab_info(const femo_problem *p, int64_t info[16]);

@@ -131,3 +131,45 @@ def test_gloo_world2_halo_and_allreduce():
     for p_ in procs:
         p_.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+@pytest.mark.parametrize('R', [2, 4])
+def test_hex_slab_partition_covers_global_numbering(R):
+    """z-slabs of the hexahedral box: local coordinates / connectivity / owned pattern rows are the global ones
+    restricted to the slab (integer ==), every dof, cell and traction facet is owned exactly once."""
+    nx, ny, gnz = 4, 3, 2 * R
+    lo, hi = (0.0, 0.0, 0.0), (4.0, 3.0, float(gnz))
+    m = om.box_hex(lo, hi, nx, ny, gnz)
+    fc, fl = m.exterior_facets()
+    tag = np.nonzero(fl == 3)[0]
+    F = fam.SimpHex8(m, tag)
+    rp, col = asm.pattern(F.jacobian(np.zeros(F.N), np.ones(F.M)), (F.N, F.N))
+    owner_nodes, owner_cells = np.full(F.N, -1), np.full(F.M, -1)
+    pl, cl = (nx + 1) * (ny + 1), nx * ny
+    nfacets_owned = 0
+    for r in range(R):
+        p = SlabProblem(E.FAMILY_SIMP_HEX8, nx, gnz, r, R, lo=lo, hi=hi, ny=ny, face_mask=1 << 3)
+        s = p.slab
+        g0, c0 = s['crow0'] * pl, s['crow0'] * cl
+        assert np.array_equal(p.local_coords(), m.coords[g0:g0 + p.N // 3])
+        assert np.array_equal(p.local_cells() + g0, m.cells[c0:c0 + p.M[0]])
+        gl = 3 * g0 + np.arange(p.N)
+        own = gl[s['own_off']:s['own_off'] + s['own_n']]
+        assert np.all(owner_nodes[own] == -1)
+        owner_nodes[own] = r
+        cown = c0 + np.arange(s['cown_off'], s['cown_off'] + s['cown_n'])
+        assert np.all(owner_cells[cown] == -1)
+        owner_cells[cown] = r
+        lrp, lcol = p.pattern(0)
+        for i in range(s['own_off'], s['own_off'] + s['own_n'], 7):
+            gi = 3 * g0 + i
+            assert np.array_equal(lcol[lrp[i]:lrp[i + 1]] + 3 * g0, col[rp[gi]:rp[gi + 1]])
+        nfacets_owned += ny * (s['cown1'] - s['cown0'])
+    assert np.all(owner_nodes >= 0) and np.all(owner_cells >= 0)
+    assert nfacets_owned == len(tag)
+
+
+def test_hex_partitioned_multigrid_levels(monkeypatch):
+    monkeypatch.setenv('FEMO_DIST_MIN_ROWS', '16')
+    p = SlabProblem(E.FAMILY_SIMP_HEX8, 16, 32, 0, 2, lo=(0, 0, 0), hi=(16., 8., 32.), ny=8, face_mask=8)
+    assert p.enable_multigrid() >= 4
