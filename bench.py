@@ -116,7 +116,20 @@ class EngineStep:
         self.torch = torch
         self.kind = kind
         self.out_id = 0
-        if kind == 'hex':
+        if kind == 'hex' and world > 1:
+            # weak scaling of ONE cantilever: nx x ny x (nz*world) cells cut into z-slabs
+            import numpy as np
+            from femo_b200 import dist as fd
+            nx, ny, nz = n, n // 2, n // 4
+            gnz = nz * world
+            p = fd.SlabProblem(E.FAMILY_SIMP_HEX8, nx, gnz, rank, world, lo=(0.0, 0.0, 0.0), hi=(2.0 * nx, 2.0 * ny, 2.0 * gnz),
+                               params=[0.3, 0.0, -0.25, 0.0, 3.0], ny=ny, face_mask=1 << 3)
+            xl = p.local_coords()
+            nodes = np.nonzero(xl[:, 0] == 0.0)[0]
+            p.set_bc([np.stack([3 * nodes, 3 * nodes + 1, 3 * nodes + 2], axis=1).ravel().astype(np.int32)])
+            self.global_dofs = 3 * (nx + 1) * (ny + 1) * (gnz + 1)
+            self.out_id = 1
+        elif kind == 'hex':
             import numpy as np
             nx, ny, nz = n, n // 2, n // 4
             mesh = E.EngineMesh.box_hex((0.0, 0.0, 0.0), (2.0 * nx, 2.0 * ny, 2.0 * nz), nx, ny, nz)
@@ -144,7 +157,12 @@ class EngineStep:
         self.u = p.new_vector(p.N, 0.0)
         if kind == 'hex':
             import numpy as np
-            self.f = p.to_device(np.clip(0.86 * np.random.default_rng(0).random(p.M[0]), 1e-3, 1.0))
+            nx, ny, nz = n, n // 2, n // 4
+            rho = np.clip(0.86 * np.random.default_rng(0).random(nx * ny * nz * world), 1e-3, 1.0)   # global field, seed 0
+            if world > 1:
+                s = p.slab
+                rho = rho.reshape(nz * world, nx * ny)[s['crow0']:s['crow0'] + s['ncrows']].ravel()
+            self.f = p.to_device(np.ascontiguousarray(rho))
         else:
             self.f = p.new_vector(p.M[0], 0.1)
         p.set_coefficient(0, self.u)
@@ -296,6 +314,8 @@ def main():
         a.no_cpu = True
         if a.workload == 'hex':
             a.no_e2e = True
+        if a.workload == 'p2' and int(os.environ.get('WORLD_SIZE', '1')) > 1:
+            raise SystemExit('the P2 workload runs on one GPU')
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -364,7 +384,8 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = float(tt.item())
     # one partitioned problem with `world` times the dofs: normalise to solves of the N=1 workload
-    norm = es.global_dofs / float((a.n + 1) ** 2) if world > 1 else 1.0
+    base_dofs = (a.n + 1) ** 2 if a.workload == 'p1' else 3 * (a.n + 1) * (a.n // 2 + 1) * (a.n // 4 + 1)
+    norm = es.global_dofs / float(base_dofs) if world > 1 else 1.0
     value = norm * a.steps / (ms * 1e-3)
 
     # e2e: host buffers in, host buffers out, copies inside the timed region
@@ -442,10 +463,12 @@ def main():
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=W,
                    ms_per_step=ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
                    data='synthetic', config=dict(workload(a.n, a.workload), parallelism='1 GPU' if world == 1 else
-                                                 ('one problem on [0,1]x[0,%d], %d x %d cells (%d dofs), y-slab partition '
-                                                  'with one-cell ghost layer over %d GPUs, NCCL halo exchange + all-reduce, '
-                                                  'partitioned multigrid; value = solves/s x dofs/dofs(N=1 workload)'
-                                                  % (world, N_DIST, N_DIST * world, es.global_dofs, world))),
+                                                 (('one cantilever of %d x %d x %d cells (%d dofs), z-slab partition '
+                                                   % (a.n, a.n // 2, a.n // 4 * world, es.global_dofs)) if a.workload == 'hex' else
+                                                  ('one problem on [0,1]x[0,%d], %d x %d cells (%d dofs), y-slab partition '
+                                                   % (world, N_DIST, N_DIST * world, es.global_dofs))) +
+                                                 ('with one-cell ghost layer over %d GPUs, NCCL halo exchange + all-reduce, '
+                                                  'partitioned multigrid; value = solves/s x dofs/dofs(N=1 workload)' % world)),
                    clocks=clocks, gpu_launches=int(launches), e2e=e2e,
                    roofline=dict(bound='hbm', kernel='femo::k_spmv (CSR-stream SpMV, fine-level Jacobian)',
                                  achieved=ach, peak=peak, unit='GB/s', frac=ach / peak,
