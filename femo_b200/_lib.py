@@ -50,6 +50,7 @@ SIGNATURES = {
     'femo_device_count': (C.c_int, []),
     'femo_mesh_create_unit_square': (C.c_int, [C.c_int, C.c_int, _DP, _DP, C.POINTER(_P)]),
     'femo_mesh_create_rectangle_quad': (C.c_int, [C.c_int, C.c_int, _DP, _DP, C.POINTER(_P)]),
+    'femo_mesh_create_from_arrays': (C.c_int, [C.c_int, C.c_int, C.c_int64, _DP, C.c_int64, _I32P, C.POINTER(_P)]),
     'femo_mesh_create_box_hex': (C.c_int, [C.c_int, C.c_int, C.c_int, _DP, _DP, C.POINTER(_P)]),
     'femo_mesh_create_interval': (C.c_int, [C.c_int, C.c_double, C.c_double, C.POINTER(_P)]),
     'femo_mesh_sizes': (C.c_int, [_P, _I64P]),

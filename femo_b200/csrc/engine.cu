@@ -733,6 +733,20 @@ int femo_mesh_create_box_hex(int nx, int ny, int nz, const double lo[3], const d
     *out = m;
     return FEMO_OK;
 }
+int femo_mesh_create_from_arrays(int kind, int gdim, int64_t nverts, const double *coords, int64_t ncells, const int32_t *cells,
+                                 femo_mesh **out) {
+    if (!out || !coords || !cells) return set_err(FEMO_EINVAL, "femo_mesh_create_from_arrays: null");
+    if (nverts * 3 > 2147483647LL || ncells > 2147483647LL) return set_err(FEMO_ELIMIT, "mesh exceeds int32");
+    femo_mesh *m = new femo_mesh();
+    try {
+        make_from_arrays(kind, gdim, nverts, coords, ncells, cells, m->m);
+    } catch (const LayoutError &e) {
+        delete m;
+        return set_err(e.code, e.msg);
+    }
+    *out = m;
+    return FEMO_OK;
+}
 int femo_mesh_create_annulus(int nr, int nth, double r0, double r1, femo_mesh **out) {
     if (!out || nr < 1 || nth < 3 || !(r1 > r0) || !(r0 > 0)) return set_err(FEMO_EINVAL, "femo_mesh_create_annulus: bad arguments");
     femo_mesh *m = new femo_mesh();

@@ -129,6 +129,70 @@ void make_box_hex_slab(int nx, int ny, int gnz, int k0, int nz, const double lo[
             }
 }
 
+void make_from_arrays(int kind, int gdim, int64_t nverts, const double *coords, int64_t ncells, const int32_t *cells, Mesh &m) {
+    static const int tri_f[3][4] = {{1, 2, -1, -1}, {0, 2, -1, -1}, {0, 1, -1, -1}};
+    static const int quad_f[4][4] = {{0, 1, -1, -1}, {0, 2, -1, -1}, {1, 3, -1, -1}, {2, 3, -1, -1}};
+    static const int hex_f[6][4] = {{0, 1, 2, 3}, {0, 1, 4, 5}, {0, 2, 4, 6}, {1, 3, 5, 7}, {2, 3, 6, 7}, {4, 5, 6, 7}};
+    static const int int_f[2][4] = {{0, -1, -1, -1}, {1, -1, -1, -1}};
+    m = Mesh();
+    m.kind = kind;
+    m.gdim = gdim;
+    m.lattice = false;
+    const int (*ft)[4] = nullptr;
+    int nf = 0;
+    switch (kind) {
+        case MESH_INTERVAL: m.nvpc = 2; nf = 2; ft = int_f; break;
+        case MESH_TRI: m.nvpc = 3; nf = 3; ft = tri_f; break;
+        case MESH_QUAD: m.nvpc = 4; nf = 4; ft = quad_f; break;
+        case MESH_HEX: m.nvpc = 8; nf = 6; ft = hex_f; break;
+        default: throw LayoutError{FEMO_EINVAL, "unknown mesh kind"};
+    }
+    if (nverts < 1 || ncells < 1 || gdim < 1 || gdim > 3) throw LayoutError{FEMO_EINVAL, "empty mesh"};
+    m.nverts = nverts;
+    m.ncells = ncells;
+    m.coords.assign(coords, coords + nverts * gdim);
+    m.cells.assign(cells, cells + ncells * m.nvpc);
+    for (int d = 0; d < gdim; ++d) { m.lo[d] = 1e300; m.hi[d] = -1e300; }
+    for (int64_t v = 0; v < nverts; ++v)
+        for (int d = 0; d < gdim; ++d) {
+            m.lo[d] = std::min(m.lo[d], coords[v * gdim + d]);
+            m.hi[d] = std::max(m.hi[d], coords[v * gdim + d]);
+        }
+    for (int64_t k = 0; k < ncells * m.nvpc; ++k)
+        if (cells[k] < 0 || cells[k] >= nverts) throw LayoutError{FEMO_EINVAL, "cell vertex index out of range"};
+    struct Fk { int32_t v[4]; int64_t owner; };
+    std::vector<Fk> f((size_t)ncells * nf);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < ncells; ++c)
+        for (int l = 0; l < nf; ++l) {
+            Fk &e = f[c * nf + l];
+            for (int k = 0; k < 4; ++k) e.v[k] = ft[l][k] < 0 ? -1 : cells[c * m.nvpc + ft[l][k]];
+            std::sort(e.v, e.v + 4);
+            e.owner = c * nf + l;
+        }
+    auto less = [](const Fk &a, const Fk &b) {
+        for (int k = 0; k < 4; ++k)
+            if (a.v[k] != b.v[k]) return a.v[k] < b.v[k];
+        return a.owner < b.owner;
+    };
+    auto same = [](const Fk &a, const Fk &b) { return a.v[0] == b.v[0] && a.v[1] == b.v[1] && a.v[2] == b.v[2] && a.v[3] == b.v[3]; };
+    std::sort(f.begin(), f.end(), less);
+    std::vector<int64_t> ext;
+    for (size_t i = 0; i < f.size();) {
+        size_t j = i + 1;
+        while (j < f.size() && same(f[i], f[j])) ++j;
+        if (j - i == 1) ext.push_back(f[i].owner);
+        i = j;
+    }
+    std::sort(ext.begin(), ext.end());
+    m.bf_cell.reserve(ext.size());
+    m.bf_local.reserve(ext.size());
+    for (int64_t o : ext) {
+        m.bf_cell.push_back((int32_t)(o / nf));
+        m.bf_local.push_back((int32_t)(o % nf));
+    }
+}
+
 void Mesh::build_edges() {
     if (kind != MESH_TRI) throw LayoutError{FEMO_EINVAL, "edges are built for triangle meshes"};
     if (!cell_edges.empty()) return;

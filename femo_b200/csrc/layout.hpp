@@ -52,6 +52,10 @@ void make_box_hex(int nx, int ny, int nz, const double lo[3], const double hi[3]
 // z-slab of the (nx x ny x gnz)-cell box: cell layers [k0, k0+nk); z coordinates from the GLOBAL formula; the
 // z = lo / z = hi faces carry exterior facets only where the slab touches the true boundary
 void make_box_hex_slab(int nx, int ny, int gnz, int k0, int nk, const double lo[3], const double hi[3], Mesh &m);
+// unstructured mesh from caller arrays (what the reference reads from msh2xdmf output, utils_dolfinx.py:69-123):
+// kind = MeshKind, cells with nvpc vertices in basix order; exterior facets = facets owned by exactly one cell,
+// sorted by (cell, local facet); `lattice` is false (no geometric multigrid hierarchy)
+void make_from_arrays(int kind, int gdim, int64_t nverts, const double *coords, int64_t ncells, const int32_t *cells, Mesh &m);
 // periodic polar lattice on the annulus r0 <= r <= r1: node (ir, ith) -> ir*nth + ith
 void make_annulus_tri(int nr, int nth, double r0, double r1, Mesh &m);
 

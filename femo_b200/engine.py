@@ -9,6 +9,8 @@ import numpy as np
 from . import _lib
 from ._lib import lib, check, KrylovOpts, KrylovInfo, NewtonOpts, NewtonInfo
 
+_DP_T = C.POINTER(C.c_double)
+_I32P_T = C.POINTER(C.c_int32)
 FAMILY_POISSON_P1 = 1
 FAMILY_NLPOISSON_P1 = 2
 FAMILY_EB_BEAM = 3
@@ -52,6 +54,20 @@ class EngineMesh:
         check(lib.femo_mesh_create_rectangle_quad(int(nx), int(ny), (C.c_double * 2)(*lo), (C.c_double * 2)(*hi), C.byref(h)))
         m = cls(h)
         m.shape, m.lo, m.hi = (nx, ny), tuple(lo), tuple(hi)
+        return m
+
+    @classmethod
+    def from_arrays(cls, kind, coords, cells):
+        """Unstructured mesh: kind 'interval' | 'triangle' | 'quadrilateral' | 'hexahedron', coords (nverts, gdim),
+        cells (ncells, vertices per cell) in basix vertex order."""
+        k = {'interval': 1, 'triangle': 2, 'quadrilateral': 3, 'hexahedron': 4}[kind]
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        h = C.c_void_p()
+        check(lib.femo_mesh_create_from_arrays(k, coords.shape[1], coords.shape[0], coords.ctypes.data_as(_DP_T), cells.shape[0],
+                                               cells.ctypes.data_as(_I32P_T), C.byref(h)))
+        m = cls(h)
+        m.shape, m.lo, m.hi = None, tuple(coords.min(axis=0)), tuple(coords.max(axis=0))
         return m
 
     @classmethod

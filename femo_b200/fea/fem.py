@@ -426,6 +426,11 @@ class Measure:
     def __call__(self, tag):
         return Measure(self.kind, self.domain, self.subdomain_data, self.metadata, tag)
 
+    @property
+    def sides(self):
+        """One-sided (cell, local facet) pairs of this tag on an imported mesh (interior facets: both sides)."""
+        return self.subdomain_data.sides(self.tag)
+
     def facets(self):
         """Indices into the mesh's exterior-facet list carrying this tag."""
         t = self.subdomain_data

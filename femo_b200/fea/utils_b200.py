@@ -302,6 +302,7 @@ def setUpKSP_MUMPS(A):
 
 
 from .projection import project  # noqa: E402,F401  (utils_dolfinx.py:549-583)
+from .mesh_io import import_mesh, read_msh  # noqa: E402,F401  (utils_dolfinx.py:69-123)
 from .fem import Expr  # noqa: E402,F401
 
 

@@ -63,6 +63,11 @@ int femo_device_count(void);
  * createRectangleMesh).  Canonical lattice numbering, see DESIGN.md. */
 int femo_mesh_create_unit_square(int nx, int ny, const double lo[2], const double hi[2], femo_mesh **out);
 int femo_mesh_create_rectangle_quad(int nx, int ny, const double lo[2], const double hi[2], femo_mesh **out);
+/* unstructured mesh from caller arrays: replaces import_mesh / XDMFFile.read_mesh (utils_dolfinx.py:69-123).
+ * kind: 1 interval, 2 triangle, 3 quadrilateral, 4 hexahedron; cells hold vertex ids in basix order; coords is
+ * (nverts, gdim).  No lattice structure is assumed: every family assembles on it, geometric multigrid is unavailable. */
+int femo_mesh_create_from_arrays(int kind, int gdim, int64_t nverts, const double *coords, int64_t ncells, const int32_t *cells,
+                                 femo_mesh **out);
 /* hexahedral lattice on a box (dolfinx.mesh.create_box, CellType.hexahedron); vertex (ix,iy,iz) -> (iz*(ny+1)+iy)*(nx+1)+ix */
 int femo_mesh_create_box_hex(int nx, int ny, int nz, const double lo[3], const double hi[3], femo_mesh **out);
 int femo_mesh_create_interval(int n, double x0, double x1, femo_mesh **out);
