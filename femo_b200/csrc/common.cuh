@@ -141,6 +141,7 @@ struct femo_problem {
     double *d_coords = nullptr;
     int32_t *d_cellsT = nullptr, *d_fb_cell = nullptr, *d_fb_local = nullptr, *d_cell_tag = nullptr;
     // P2 spaces: edge opposite each local vertex (SoA), edge -> vertices, vertex -> incident edges (CSR)
+    double *d_uex_tab = nullptr;   // angle-addition table of the analytic u_ex on uniform lattices (families 2, 9)
     int32_t *d_edgesT = nullptr, *d_edge_verts = nullptr, *d_vptr = nullptr, *d_vedge = nullptr;
     std::vector<int32_t> vptr, vedge;
     femo::DevPattern dpat[5];

@@ -343,6 +343,7 @@ static TriArgs tri_args(femo_problem *p, double *out) {
     A.alpha = p->params[0];
     A.beta = p->params[1];
     A.out = out;
+    A.uex_tab = p->d_uex_tab;
     return A;
 }
 
@@ -1445,6 +1446,7 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     size_t s = 0;
     s += Arena::need(M.coords.size(), 8) + Arena::need(M.cells.size(), 4);
     s += 2 * Arena::need(std::max<size_t>(1, p->fb_cell.size()), 4) + Arena::need(std::max<size_t>(1, M.cell_tag.size()), 4);
+    s += Arena::need(2 * 49 * 4, 8);      // u_ex table
     if (p->state.element == EL_P2)
         s += Arena::need(M.cell_edges.size(), 4) + Arena::need(M.edge_verts.size(), 4) + Arena::need(p->vptr.size(), 4) + Arena::need(p->vedge.size(), 4);
     for (int w = 0; w <= p->nin; ++w) s += pattern_bytes(p->pat[w], w == 0);
@@ -1512,6 +1514,27 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     if ((rc = up(p, p->d_fb_cell, p->fb_cell))) return rc;
     if ((rc = up(p, p->d_fb_local, p->fb_local))) return rc;
     if ((rc = up(p, p->d_cell_tag, M.cell_tag))) return rc;
+    if ((p->family == FEMO_FAMILY_NLPOISSON_P1 || p->family == FEMO_FAMILY_NLPOISSON_P2) && M.kind == MESH_TRI && M.lattice &&
+        !p->jac_only && !getenv("FEMO_NO_UEX_TABLE")) {
+        // u_ex = sin(2 pi x) sin(pi y) at x0 + dx_q: cos / sin of the offsets of the 49 points in both triangle types
+        const double hx = (M.hi[0] - M.lo[0]) / (double)M.n[0];
+        const double hy = (M.hi[1] - M.lo[1]) / (double)(p->slab.active ? p->slab.gny : M.n[1]);
+        const double pi = 3.141592653589793;
+        std::vector<double> gx, gw, tab(2 * 49 * 4);
+        gauss_legendre_01(7, gx, gw);
+        for (int t = 0; t < 2; ++t)
+            for (int i = 0; i < 7; ++i)
+                for (int j = 0; j < 7; ++j) {
+                    const double xi = gx[i], et = gx[j] * (1.0 - gx[i]);          // same points as c_tri49
+                    const double dx = t == 0 ? hx * (xi + et) : hx * et;          // lower: e1 = (hx,0); upper: e1 = (0,hy); e2 = (hx,hy)
+                    const double dy = t == 0 ? hy * et : hy * (xi + et);
+                    double *o = &tab[((size_t)t * 49 + 7 * i + j) * 4];
+                    o[0] = std::cos(2.0 * pi * dx); o[1] = std::sin(2.0 * pi * dx);
+                    o[2] = std::cos(pi * dy); o[3] = std::sin(pi * dy);
+                }
+        if ((rc = up(p, p->d_uex_tab, tab))) return rc;
+        FEMO_CUDA(cudaStreamSynchronize(p->stream));
+    }
     if (p->state.element == EL_P2) {
         std::vector<int32_t> T(M.cell_edges.size());
         for (int64_t c = 0; c < M.ncells; ++c)

@@ -27,6 +27,9 @@ struct TriArgs {
     const double *u, *f, *uex;
     double alpha, beta;
     double *out;             // scratch base of this block
+    // uniform right-diagonal lattices: u_ex(x0 + dx_q, y0 + dy_q) by angle addition from 2 sincos per cell and a
+    // per-point table tab[(type*49+q)*4] = cos(2 pi dx), sin(2 pi dx), cos(pi dy), sin(pi dy)  (nullptr: general path)
+    const double *uex_tab;
 };
 
 struct Tri {
@@ -59,6 +62,29 @@ __device__ __forceinline__ double uex_nlp(double x, double y) {
     // examples/nonlinear_poisson_opt/run_nonlinear_poisson_opt.py:144-145
     const double pi = 3.141592653589793;
     return sin(2.0 * pi * x) * sin(pi * y);
+}
+
+// u_ex at quadrature point q of the degree-12 rule: table path on uniform lattices, direct evaluation otherwise
+struct UexCell {
+    double S0, C0, S1, C1;
+    const double *tab;
+};
+__device__ __forceinline__ UexCell uex_cell(const TriArgs &A, const Tri &T) {
+    UexCell U;
+    U.tab = nullptr;
+    if (A.uex_tab) {
+        sincospi(2.0 * T.X[0][0], &U.S0, &U.C0);
+        sincospi(T.X[0][1], &U.S1, &U.C1);
+        U.tab = A.uex_tab + ((T.X[1][1] == T.X[0][1]) ? 0 : 49 * 4);   // lower [v0,v1,v3] or upper [v0,v2,v3] triangle
+    }
+    return U;
+}
+__device__ __forceinline__ double uex_q(const UexCell &U, int q, double x, double y) {
+    if (U.tab) {
+        const double *t = U.tab + 4 * q;
+        return (U.S0 * t[0] + U.C0 * t[1]) * (U.S1 * t[2] + U.C1 * t[3]);
+    }
+    return uex_nlp(x, y);
 }
 
 enum CellOp { OP_RES = 0, OP_JAC = 1, OP_DRDM = 2, OP_OUT = 3, OP_OUT_DU = 4, OP_OUT_DM = 5 };
@@ -191,11 +217,12 @@ __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_cell(TriArgs A) {
             for (int b = 0; b < 3; ++b) A.out[(a * 3 + b) * ne + c] = K[a][b];
     } else {  // OP_OUT / OP_OUT_DU : degree-12 rule, u_ex evaluated at the points
         double val = 0.0, ge[3] = {0.0, 0.0, 0.0};
+        const UexCell U = uex_cell(A, T);
         for (int q = 0; q < 49; ++q) {
             const double ph[3] = {1.0 - c_tri49[q][0] - c_tri49[q][1], c_tri49[q][0], c_tri49[q][1]};
             const double x = ph[0] * T.X[0][0] + ph[1] * T.X[1][0] + ph[2] * T.X[2][0];
             const double y = ph[0] * T.X[0][1] + ph[1] * T.X[1][1] + ph[2] * T.X[2][1];
-            const double eq = u[0] * ph[0] + u[1] * ph[1] + u[2] * ph[2] - uex_nlp(x, y);
+            const double eq = u[0] * ph[0] + u[1] * ph[1] + u[2] * ph[2] - uex_q(U, q, x, y);
             const double w = c_tri49[q][2] * T.a2;
             val += w * 0.5 * eq * eq;
 #pragma unroll

@@ -119,13 +119,14 @@ __global__ void __launch_bounds__(kThreads) k_nlpoisson_p2_cell(P2Args A) {
             for (int b = 0; b < 6; ++b) out[(a * 6 + b) * ne + c] = K[a][b];
     } else {  // OP_OUT / OP_OUT_DU
         double val = 0.0, ge[6] = {0, 0, 0, 0, 0, 0};
+        const UexCell U = uex_cell(A.T, T);
         for (int q = 0; q < 49; ++q) {
             const double l[3] = {1.0 - c_tri49[q][0] - c_tri49[q][1], c_tri49[q][0], c_tri49[q][1]};
             double ph[6];
             p2_values(l, ph);
             const double x = l[0] * T.X[0][0] + l[1] * T.X[1][0] + l[2] * T.X[2][0];
             const double y = l[0] * T.X[0][1] + l[1] * T.X[1][1] + l[2] * T.X[2][1];
-            double eq = -uex_nlp(x, y);
+            double eq = -uex_q(U, q, x, y);
 #pragma unroll
             for (int a = 0; a < 6; ++a) eq += u[a] * ph[a];
             const double w = c_tri49[q][2] * T.a2;
