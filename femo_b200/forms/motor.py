@@ -124,3 +124,33 @@ def area_form(uhat, dx, subdomains):
         tags[dx.subdomain_data.indices] = dx.subdomain_data.values
         fam.cell_tags = tags
     return Form(fam, 'output', out_id=table[tuple(ids)])
+
+
+def synthetic_motor_tags(mesh, p=12, s=36):
+    """Subdomain ids of the synthetic annulus standing in for the reference's motor mesh,
+    with the ids of its association table: 51 shaft | 1 rotor core | magnets 3..14 with air (52) between them |
+    53 air gap | windings 15..50 with stator teeth (2) between them | 2 stator yoke; bands are fractions of the
+    radial extent."""
+    X = mesh.geometry.x[:, :2]
+    c = X[mesh.cells].mean(axis=1)
+    r = np.hypot(c[:, 0], c[:, 1])
+    th = np.mod(np.arctan2(c[:, 1], c[:, 0]), 2 * np.pi)
+    r0, r1 = mesh._e.lo[0], mesh._e.hi[0]
+    f = (r - r0) / (r1 - r0)
+    tag = np.full(mesh.num_cells, 52, dtype=np.int32)
+    tag[f < 0.15] = 51
+    tag[(f >= 0.15) & (f < 0.35)] = 1
+    band = (f >= 0.35) & (f < 0.5)
+    sec = th / (2 * np.pi / p)
+    k = np.floor(sec).astype(int)
+    sel = band & (sec - k < 0.75)
+    tag[sel] = (3 + k)[sel]
+    tag[(f >= 0.5) & (f < 0.58)] = 53
+    band = (f >= 0.58) & (f < 0.8)
+    sec = th / (2 * np.pi / s)
+    k = np.floor(sec).astype(int)
+    tag[band] = 2
+    sel = band & (sec - k < 0.6)
+    tag[sel] = (15 + k)[sel]
+    tag[f >= 0.8] = 2
+    return tag
