@@ -107,6 +107,8 @@ struct femo_mg_level {
     double *u = nullptr;      // restricted state used to rediscretise the coarse Jacobian
     double *dense = nullptr, *dense_tmp = nullptr;  // coarsest level: explicit inverse
     double *m = nullptr;                            // restricted cell-wise input (SIMP density)
+    double *ec = nullptr, *k0 = nullptr;            // hexahedral lattices: cell moduli rho^p and the unit-modulus 24x24
+                                                    // element matrix of the level's (congruent) cells: matrix-free V-cycle
     double *fb = nullptr, *fx = nullptr;            // full-multigrid start: restricted right-hand side, nested iterate
     double lmax = 2.0;
 };

@@ -525,6 +525,94 @@ __global__ void __launch_bounds__(kThreads)
 
 // Chebyshev smoother of degree `deg` on level problem L: x ~ A^-1 b.  Every step after the
 // first is ONE kernel: the SpMV A d with the residual/direction/solution updates in its row epilogue.
+// ---- matrix-free SIMP operator on uniform hexahedral lattices ------------------------------------------------
+// y = A x with A = sum_cells rho_c^p K0 (all cells of a level are congruent boxes, so ONE 24x24 unit-modulus element
+// matrix serves the level): no matrix traffic at all, only x, the cell moduli and the Dirichlet marks.  One thread
+// per node gathers its 8 cells (fixed order => deterministic).  Dirichlet dofs follow the assembled BC'd matrix:
+// masked rows are diag * x, masked columns are skipped.  Used for the SpMVs INSIDE the V-cycle only (a
+// preconditioner may be any fixed SPD operator); the Krylov recurrence keeps the assembled matrix it was given.
+struct HexLat {
+    int nx, ny, nzl;   // local cells per direction; nodes (nx+1)(ny+1)(nzl+1), node = (k*(ny+1)+j)*(nx+1)+i
+};
+
+__global__ void __launch_bounds__(kThreads) k_pow_cells(const double *__restrict__ rho, double p, double *__restrict__ ec, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) ec[i] = pow(rho[i], p);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads)
+    k_hex_matfree(HexLat L, const double *__restrict__ k0, const double *__restrict__ ec, const uint8_t *__restrict__ mask,
+                  const double *__restrict__ bcdiag, const double *__restrict__ x, double *__restrict__ y, SpmvEpi E) {
+    __shared__ double K[576];
+    for (int t = threadIdx.x; t < 576; t += blockDim.x) K[t] = k0[t];
+    __syncthreads();
+    const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int sx = L.nx + 1, sy = L.ny + 1;
+    if (node >= (int64_t)sx * sy * (L.nzl + 1)) return;
+    const int i = (int)(node % sx), j = (int)((node / sx) % sy), k = (int)(node / ((int64_t)sx * sy));
+    double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int dk = -1; dk <= 0; ++dk) {
+        const int ck = k + dk;
+        if (ck < 0 || ck >= L.nzl) continue;
+#pragma unroll
+        for (int dj = -1; dj <= 0; ++dj) {
+            const int cj = j + dj;
+            if (cj < 0 || cj >= L.ny) continue;
+#pragma unroll
+            for (int di = -1; di <= 0; ++di) {
+                const int ci = i + di;
+                if (ci < 0 || ci >= L.nx) continue;
+                const double e = ec[((int64_t)ck * L.ny + cj) * L.nx + ci];
+                const int a = (-di) + 2 * (-dj) + 4 * (-dk);              // this node's corner in that cell
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const int64_t q = 3 * ((((int64_t)(ck + (b >> 2)) * sy) + (cj + ((b >> 1) & 1))) * sx + (ci + (b & 1)));
+                    double x0 = __ldg(x + q), x1 = __ldg(x + q + 1), x2 = __ldg(x + q + 2);
+                    if (mask) {
+                        x0 = mask[q] ? 0.0 : x0;
+                        x1 = mask[q + 1] ? 0.0 : x1;
+                        x2 = mask[q + 2] ? 0.0 : x2;
+                    }
+                    const double *Kr = K + (3 * a) * 24 + 3 * b;
+                    s0 += Kr[0] * x0 + Kr[1] * x1 + Kr[2] * x2;
+                    s1 += Kr[24] * x0 + Kr[25] * x1 + Kr[26] * x2;
+                    s2 += Kr[48] * x0 + Kr[49] * x1 + Kr[50] * x2;
+                }
+                acc[0] += e * s0;
+                acc[1] += e * s1;
+                acc[2] += e * s2;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int64_t row = 3 * node + r;
+        const double xi = __ldg(x + row);
+        const double v = (mask && mask[row]) ? bcdiag[row] * xi : acc[r];
+        spmv_row_epilogue<EPI>(E, row, v, xi, y);
+    }
+}
+
+static inline bool hex_matfree_ready(const femo_problem *L) { return L->mgl.ec && L->mgl.k0 && L->family == FEMO_FAMILY_SIMP_HEX8; }
+
+static int launch_hex_matfree(femo_problem *L, int kind, const double *x, double *y, const SpmvEpi &E) {
+    int rc = halo_nodes(L, const_cast<double *>(x));
+    if (rc) return rc;
+    const HexLat H{L->mesh.n[0], L->mesh.n[1], L->mesh.n[2]};
+    const int64_t nn = (int64_t)(H.nx + 1) * (H.ny + 1) * (H.nzl + 1);
+    const uint8_t *mk = L->has_bc ? L->d_bc_mark : nullptr;
+    const int g = grid_for(nn);
+    if (kind == EPI_PLAIN) k_hex_matfree<EPI_PLAIN><<<g, kThreads, 0, L->stream>>>(H, L->mgl.k0, L->mgl.ec, mk, L->d_bc_diag, x, y, E);
+    else if (kind == EPI_CHEB0) k_hex_matfree<EPI_CHEB0><<<g, kThreads, 0, L->stream>>>(H, L->mgl.k0, L->mgl.ec, mk, L->d_bc_diag, x, y, E);
+    else k_hex_matfree<EPI_CHEBK><<<g, kThreads, 0, L->stream>>>(H, L->mgl.k0, L->mgl.ec, mk, L->d_bc_diag, x, y, E);
+    L->launches++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
 __global__ void __launch_bounds__(kThreads) k_to_f32(const double *__restrict__ a, float *__restrict__ o, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) o[i] = (float)a[i];
 }
@@ -532,6 +620,7 @@ __global__ void __launch_bounds__(kThreads) k_to_f32(const double *__restrict__ 
 // the level's SpMV with a fused Chebyshev epilogue, streaming the fp32 copy of the values when requested
 static int mg_spmv_cheb(femo_problem *L, bool fp32, int kind, const double *x, const SpmvEpi &E) {
     femo_mg_level &M = L->mgl;
+    if (fp32 && hex_matfree_ready(L)) return launch_hex_matfree(L, kind, x, nullptr, E);
     if (fp32 && M.vals32) return launch_spmv_cheb(L, kind, M.vals32, x, E);
     return launch_spmv_cheb(L, kind, M.vals, x, E);
 }
@@ -636,7 +725,11 @@ static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, con
     const DevPattern &D = L->dpat[0];
     if ((rc = mg_smooth(L, b, x, true, mp.degree, mp.ratio, mp.fp32))) return rc;
     // r = b - A x ; restrict
-    if (mp.fp32 && M.vals32) rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals32, x, M.r, b, nullptr);
+    if (mp.fp32 && hex_matfree_ready(L)) {
+        SpmvEpi E;
+        E.b = b;
+        rc = launch_hex_matfree(L, EPI_PLAIN, x, M.r, E);
+    } else if (mp.fp32 && M.vals32) rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals32, x, M.r, b, nullptr);
     else rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, x, M.r, b, nullptr);
     if (rc) return rc;
     if ((rc = mg_restrict(L, C, M.r, MC.b))) return rc;
@@ -857,7 +950,11 @@ static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true) {
             if ((rc = femo_assemble_jacobian(L, L->has_bc ? nullptr : M.vals, L->has_bc ? M.vals : nullptr))) return rc;
         }
         const DevPattern &D = L->dpat[0];
-        if (fp32 && M.vals32 && lv < nlev - 1) {
+        if (fp32 && M.ec && M.k0 && L->coef[1] && lv < nlev - 1) {       // matrix-free V-cycle operator of this level
+            const int64_t ncell = L->mesh.ncells;
+            k_pow_cells<<<grid_for(ncell), kThreads, 0, st>>>(L->coef[1], L->params[4], M.ec, ncell);
+            L->launches++;
+        } else if (fp32 && M.vals32 && lv < nlev - 1) {
             const int64_t nnz = L->pat[0].nnz;
             k_to_f32<<<(int)std::min<int64_t>((nnz + kThreads - 1) / kThreads, (int64_t)L->num_sms * 16), kThreads, 0, st>>>(M.vals, M.vals32, nnz);
             L->launches++;
