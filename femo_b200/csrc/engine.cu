@@ -453,6 +453,7 @@ static int setup_hex_matfree(femo_problem *root, femo_problem *L) {
     const double hz = (M.hi[2] - M.lo[2]) / (double)(L->slab.active ? L->slab.gny : M.n[2]);
     std::vector<double> K;
     hex_unit_stiffness(hx, hy, hz, L->params[0], K);
+    L->h_k0 = K;
     L->mgl.k0 = root->st.take<double>(576);
     L->mgl.ec = root->wk.take<double>((size_t)M.ncells);
     if (!L->mgl.k0 || !L->mgl.ec) return set_err(FEMO_EINVAL, "arena too small (matrix-free level)");

@@ -540,17 +540,44 @@ __global__ void __launch_bounds__(kThreads) k_pow_cells(const double *__restrict
     if (i < n) ec[i] = pow(rho[i], p);
 }
 
+// CTA = a 32 x 4 x 2 tile of nodes (a warp = 32 consecutive nodes of one lattice row).  The tile's x values plus a
+// one-node halo are staged in shared memory with coalesced loads, component-major ([s][node]: conflict-free reads),
+// Dirichlet columns zeroed while staging.  K0 travels as a 4.6 KB kernel parameter: with the cell / node loops fully
+// unrolled its entries are constant-bank operands of the FMAs (no load instructions at all).
+struct HexK0 {
+    double k[576];
+};
+constexpr int kMfX = 32, kMfY = 4, kMfZ = 2;
+constexpr int kMfHX = kMfX + 2, kMfHY = kMfY + 2, kMfHZ = kMfZ + 2, kMfHalo = kMfHX * kMfHY * kMfHZ;
+
 template <int EPI>
 __global__ void __launch_bounds__(kThreads)
-    k_hex_matfree(HexLat L, const double *__restrict__ k0, const double *__restrict__ ec, const uint8_t *__restrict__ mask,
-                  const double *__restrict__ bcdiag, const double *__restrict__ x, double *__restrict__ y, SpmvEpi E) {
-    __shared__ double K[576];
-    for (int t = threadIdx.x; t < 576; t += blockDim.x) K[t] = k0[t];
+    k_hex_matfree(HexLat L, const __grid_constant__ HexK0 KP, const double *__restrict__ ec, const uint8_t *__restrict__ mask,
+                  const double *__restrict__ bcdiag, const double *__restrict__ x, double *__restrict__ y, SpmvEpi E, int tiles_x,
+                  int tiles_y) {
+    __shared__ double xs[3 * kMfHalo];
+    const int sx = L.nx + 1, sy = L.ny + 1, sz = L.nzl + 1;
+    const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
+    const int i0 = bx * kMfX - 1, j0 = by * kMfY - 1, k0n = bz * kMfZ - 1;      // lattice index of halo node (0,0,0)
+    // stage: rows of the halo box are contiguous runs of 3*kMfHX doubles in x
+    for (int row = threadIdx.x / 128; row < kMfHY * kMfHZ; row += kThreads / 128) {
+        const int hj = row % kMfHY, hk = row / kMfHY;
+        const int j = j0 + hj, k = k0n + hk;
+        const int t = threadIdx.x % 128;
+        if (t < 3 * kMfHX) {
+            const int hi = t / 3, s = t % 3, i = i0 + hi;
+            double v = 0.0;
+            if (i >= 0 && i < sx && j >= 0 && j < sy && k >= 0 && k < sz) {
+                const int64_t q = 3 * ((((int64_t)k * sy) + j) * sx + i) + s;
+                v = (mask && mask[q]) ? 0.0 : __ldg(x + q);
+            }
+            xs[s * kMfHalo + (hk * kMfHY + hj) * kMfHX + hi] = v;
+        }
+    }
     __syncthreads();
-    const int64_t node = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int sx = L.nx + 1, sy = L.ny + 1;
-    if (node >= (int64_t)sx * sy * (L.nzl + 1)) return;
-    const int i = (int)(node % sx), j = (int)((node / sx) % sy), k = (int)(node / ((int64_t)sx * sy));
+    const int li = threadIdx.x % kMfX, lj = (threadIdx.x / kMfX) % kMfY, lk = threadIdx.x / (kMfX * kMfY);
+    const int i = bx * kMfX + li, j = by * kMfY + lj, k = bz * kMfZ + lk;
+    if (i >= sx || j >= sy || k >= sz) return;
     double acc[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int dk = -1; dk <= 0; ++dk) {
@@ -564,19 +591,16 @@ __global__ void __launch_bounds__(kThreads)
             for (int di = -1; di <= 0; ++di) {
                 const int ci = i + di;
                 if (ci < 0 || ci >= L.nx) continue;
-                const double e = ec[((int64_t)ck * L.ny + cj) * L.nx + ci];
+                const double e = __ldg(ec + ((int64_t)ck * L.ny + cj) * L.nx + ci);
                 const int a = (-di) + 2 * (-dj) + 4 * (-dk);              // this node's corner in that cell
+                // halo-local index of the cell's node 0: (li+1+di, lj+1+dj, lk+1+dk)
+                const int h0 = ((lk + 1 + dk) * kMfHY + (lj + 1 + dj)) * kMfHX + (li + 1 + di);
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    const int64_t q = 3 * ((((int64_t)(ck + (b >> 2)) * sy) + (cj + ((b >> 1) & 1))) * sx + (ci + (b & 1)));
-                    double x0 = __ldg(x + q), x1 = __ldg(x + q + 1), x2 = __ldg(x + q + 2);
-                    if (mask) {
-                        x0 = mask[q] ? 0.0 : x0;
-                        x1 = mask[q + 1] ? 0.0 : x1;
-                        x2 = mask[q + 2] ? 0.0 : x2;
-                    }
-                    const double *Kr = K + (3 * a) * 24 + 3 * b;
+                    const int h = h0 + (b & 1) + ((b >> 1) & 1) * kMfHX + (b >> 2) * kMfHX * kMfHY;
+                    const double x0 = xs[h], x1 = xs[kMfHalo + h], x2 = xs[2 * kMfHalo + h];
+                    const double *Kr = KP.k + (3 * a) * 24 + 3 * b;     // compile-time offsets after unrolling: constant-bank operands
                     s0 += Kr[0] * x0 + Kr[1] * x1 + Kr[2] * x2;
                     s1 += Kr[24] * x0 + Kr[25] * x1 + Kr[26] * x2;
                     s2 += Kr[48] * x0 + Kr[49] * x1 + Kr[50] * x2;
@@ -587,6 +611,7 @@ __global__ void __launch_bounds__(kThreads)
             }
         }
     }
+    const int64_t node = (((int64_t)k * sy) + j) * sx + i;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const int64_t row = 3 * node + r;
@@ -596,18 +621,22 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
-static inline bool hex_matfree_ready(const femo_problem *L) { return L->mgl.ec && L->mgl.k0 && L->family == FEMO_FAMILY_SIMP_HEX8; }
+static inline bool hex_matfree_ready(const femo_problem *L) {
+    return L->mgl.ec && L->mgl.k0 && L->h_k0.size() == 576 && L->family == FEMO_FAMILY_SIMP_HEX8;
+}
 
 static int launch_hex_matfree(femo_problem *L, int kind, const double *x, double *y, const SpmvEpi &E) {
     int rc = halo_nodes(L, const_cast<double *>(x));
     if (rc) return rc;
     const HexLat H{L->mesh.n[0], L->mesh.n[1], L->mesh.n[2]};
-    const int64_t nn = (int64_t)(H.nx + 1) * (H.ny + 1) * (H.nzl + 1);
     const uint8_t *mk = L->has_bc ? L->d_bc_mark : nullptr;
-    const int g = grid_for(nn);
-    if (kind == EPI_PLAIN) k_hex_matfree<EPI_PLAIN><<<g, kThreads, 0, L->stream>>>(H, L->mgl.k0, L->mgl.ec, mk, L->d_bc_diag, x, y, E);
-    else if (kind == EPI_CHEB0) k_hex_matfree<EPI_CHEB0><<<g, kThreads, 0, L->stream>>>(H, L->mgl.k0, L->mgl.ec, mk, L->d_bc_diag, x, y, E);
-    else k_hex_matfree<EPI_CHEBK><<<g, kThreads, 0, L->stream>>>(H, L->mgl.k0, L->mgl.ec, mk, L->d_bc_diag, x, y, E);
+    const int tx = (H.nx + 1 + kMfX - 1) / kMfX, ty = (H.ny + 1 + kMfY - 1) / kMfY, tz = (H.nzl + 1 + kMfZ - 1) / kMfZ;
+    const int g = tx * ty * tz;
+    HexK0 KP;
+    memcpy(KP.k, L->h_k0.data(), sizeof(KP.k));
+    if (kind == EPI_PLAIN) k_hex_matfree<EPI_PLAIN><<<g, kThreads, 0, L->stream>>>(H, KP, L->mgl.ec, mk, L->d_bc_diag, x, y, E, tx, ty);
+    else if (kind == EPI_CHEB0) k_hex_matfree<EPI_CHEB0><<<g, kThreads, 0, L->stream>>>(H, KP, L->mgl.ec, mk, L->d_bc_diag, x, y, E, tx, ty);
+    else k_hex_matfree<EPI_CHEBK><<<g, kThreads, 0, L->stream>>>(H, KP, L->mgl.ec, mk, L->d_bc_diag, x, y, E, tx, ty);
     L->launches++;
     FEMO_CHECK_LAUNCH();
     return FEMO_OK;
