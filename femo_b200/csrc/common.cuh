@@ -165,6 +165,7 @@ struct femo_problem {
     femo::SlabInfo slab;
     int64_t own_off = 0, own_n = 0;        // owned state dofs: [own_off, own_off + own_n)
     int64_t cown_off = 0, cown_n = 0;      // owned cells
+    bool skip_next_halo = false; // set when the next halo_nodes() input provably has fresh ghost rows (consumed by that call)
     int face_mask = 0;           // hexahedral slabs: box faces tagged as traction facets
     int64_t fown_off = 0;        // first facet of block 2 whose cell is owned (facets are sorted by cell)
     bool replicated = false;               // multigrid level held identically by every rank

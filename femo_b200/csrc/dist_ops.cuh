@@ -9,6 +9,10 @@ using namespace femo;
 // utils_dolfinx.py:167): whole lattice rows are contiguous, so rows are sent in place.
 static int halo_nodes(femo_problem *p, double *v) {
     const SlabInfo &s = p->slab;
+    if (p->skip_next_halo) {
+        p->skip_next_halo = false;
+        return FEMO_OK;
+    }
     if (!s.active || !g_comm.active) return FEMO_OK;
     const size_t len = (size_t)(p->mesh.n[0] + 1) * (p->mesh.kind == MESH_HEX ? (size_t)(p->mesh.n[1] + 1) : 1) * p->state.block;
     NcclApi &a = g_comm.api;

@@ -764,6 +764,9 @@ static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, con
     if ((rc = mg_restrict(L, C, M.r, MC.b))) return rc;
     if ((rc = mg_vcycle(root, lv + 1, MC.b, MC.x, mp))) return rc;
     if ((rc = mg_prolong_add(L, C, MC.x, x))) return rc;
+    // x had fresh ghost rows for the residual SpMV and the nested prolongation corrected them from the (exchanged)
+    // coarse ghost rows: the post-smoother's first SpMV needs no halo exchange
+    L->skip_next_halo = L->slab.active && nested_pair(L, C);
     return mg_smooth(L, b, x, false, mp.degree, mp.ratio, mp.fp32);
 }
 
