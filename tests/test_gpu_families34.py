@@ -192,7 +192,6 @@ def test_hex_general_element_kernels(cuda_device, monkeypatch):
     assert relerr(vg.cpu().numpy(), A) < TOL and relerr(vf.cpu().numpy(), A) < TOL
     assert relerr(vfb.cpu().numpy(), vgb.cpu().numpy()) < 1e-13
     # V-cycle with the assembled fp32 copies instead of the matrix-free operator: same solution
-    gen.p.assemble_jacobian  # noqa: B018
     c = HexCase(16, 8, 8, seed=32, upload=False)
     c.p.enable_multigrid()
     from _cases34 import _upload
