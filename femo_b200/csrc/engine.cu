@@ -2057,7 +2057,7 @@ int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton
         // change the SNES convergence decision, so the Krylov solve may stop there
         femo_krylov_opts ko = opts->krylov;
         if (snes) ko.atol = std::max(ko.atol, 0.1 * opts->atol);
-        if ((rc = (ko.method == 1 ? gmres_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki) : cg_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki)))) return rc;
+        if ((rc = (ko.method == 1 ? gmres_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki) : cg_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki, true)))) return rc;
         kit += ki.iterations;
         spmvs += ki.spmv_count;
         k_axpy<<<red_grid(p, n), kThreads, 0, st>>>(-1.0, p->nt_dx, x, n);

@@ -166,8 +166,11 @@ static int norm2_sq(femo_problem *p, const double *a, double *out) {
 
 // Preconditioned CG on the dR/du pattern; `vals` already in the layout to multiply with.
 //   precond 0: Jacobi, 2: multigrid V-cycle, 3: explicit dense inverse
+// op_current: the caller guarantees that `vals` is the (BC'd) Jacobian of the coefficients currently bound to the
+// problem (true inside femo_newton_solve, which assembles it itself): hexahedral lattices then apply the operator
+// matrix-free in the recurrence too.  Matrices handed in through femo_linear_solve are always streamed as given.
 static int cg_solve(femo_problem *p, const double *vals, const double *b, double *x, femo_krylov_opts o,
-                    femo_krylov_info *info) {
+                    femo_krylov_info *info, bool op_current = false) {
     default_krylov(o);
     if (o.precond == 2 && p->mg.empty()) o.precond = 0;
     if (o.precond == 3 && !p->d_dense) return set_err(FEMO_ELIMIT, "precond 3 (dense direct) needs N <= 512 on one GPU");
@@ -208,8 +211,12 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     // multigrid: replace the caller's initial guess by the full-multigrid iterate (discretisation accuracy)
     // full-multigrid start (halves the iteration count here; measured on slabs too: 14 vs 27 iterations per step at N=2)
     if (pre == 2 && o.restart != 1 && (rc = mg_fmg(p, b, x, mp))) return rc;
+    const bool mf_outer = op_current && pre == 2 && mp.fp32 && hex_matfree_ready(p);
     // r = b - A x
-    if ((rc = launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, vals, x, p->kr_q, nullptr, nullptr))) return rc;
+    if (mf_outer) {
+        SpmvEpi E0;
+        if ((rc = launch_hex_matfree(p, EPI_PLAIN, x, p->kr_q, E0))) return rc;
+    } else if ((rc = launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, vals, x, p->kr_q, nullptr, nullptr))) return rc;
     ++spmvs;
     if (pre == 0) {
         k_cg_init<<<g, kThreads, 0, st>>>(b, p->kr_q, p->kr_dinv, p->kr_r, p->kr_p, n, o0, o1, pa, pb);
@@ -249,7 +256,13 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
             p->launches++;
         }
         // q = A p ; alpha = rz / p.q
-        if ((rc = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, nullptr, &np))) return rc;
+        if (mf_outer) {
+            SpmvEpi E0;
+            if ((rc = launch_hex_matfree(p, EPI_PLAIN, p->kr_p, p->kr_q, E0))) return rc;
+            k_dot<<<go, kThreads, 0, st>>>(p->kr_p + p->own_off, p->kr_q + p->own_off, p->own_n, p->d_partials);
+            p->launches++;
+            np = go;
+        } else if ((rc = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, nullptr, &np))) return rc;
         ++spmvs;
         if ((rc = reduce_to(p, p->d_partials, nullptr, np, S_PQ, 0))) return rc;
         if ((rc = scalar_op(p, 0))) return rc;

@@ -71,23 +71,32 @@ def _free_port():
     return port
 
 
-def _gloo_worker(rank, R, port, nx, gny, q):
+def _gloo_worker(rank, R, port, nx, gny, q, hex_ny=None):
     import torch
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=R)
     try:
-        m = om.unit_square_tri(nx, gny)
-        F = fam.NonlinearPoissonP1(m)
         rng = np.random.default_rng(3)
-        u = rng.standard_normal(F.N)
-        A = asm.assemble_matrix(F.jacobian(u, np.zeros(F.M)), (F.N, F.N)).tocsr()
+        if hex_ny is None:
+            m = om.unit_square_tri(nx, gny)
+            F = fam.NonlinearPoissonP1(m)
+            u = rng.standard_normal(F.N)
+            A = asm.assemble_matrix(F.jacobian(u, np.zeros(F.M)), (F.N, F.N)).tocsr()
+            p = SlabProblem(2, nx, gny, rank, R)
+            rowlen = nx + 1
+        else:                                   # hexahedral z-slabs: a "row" is a whole plane of nodes x 3 components
+            lo, hi = (0.0, 0.0, 0.0), (float(nx), float(hex_ny), float(gny))
+            m = om.box_hex(lo, hi, nx, hex_ny, gny)
+            fl = m.exterior_facets()[1]
+            F = fam.SimpHex8(m, np.nonzero(fl == 3)[0])
+            A = asm.assemble_matrix(F.jacobian(np.zeros(F.N), 0.2 + rng.random(F.M)), (F.N, F.N)).tocsr()
+            p = SlabProblem(E.FAMILY_SIMP_HEX8, nx, gny, rank, R, lo=lo, hi=hi, ny=hex_ny, face_mask=8)
+            rowlen = 3 * (nx + 1) * (hex_ny + 1)
         x = rng.standard_normal(F.N)
-        p = SlabProblem(2, nx, gny, rank, R)
         s = p.slab
-        g0 = s['crow0'] * (nx + 1)
-        rowlen = nx + 1
+        g0 = s['crow0'] * rowlen
         # local matrix = the slab's own assembly (oracle on the local sub-mesh would need the same ghost rules);
         # here: global rows of the owned dofs, columns restricted to the local window
         Aloc = A[g0:g0 + p.N, g0:g0 + p.N]
@@ -119,12 +128,14 @@ def _gloo_worker(rank, R, port, nx, gny, q):
         dist.destroy_process_group()
 
 
-def test_gloo_world2_halo_and_allreduce():
+@pytest.mark.parametrize('hex_ny', [None, 3])
+def test_gloo_world2_halo_and_allreduce(hex_ny):
     import torch.multiprocessing as mp
     R, port = 2, _free_port()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_gloo_worker, args=(r, R, port, 8, 16, q)) for r in range(R)]
+    args = (8, 16, q) if hex_ny is None else (4, 6, q, hex_ny)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, R, port) + args) for r in range(R)]
     for p_ in procs:
         p_.start()
     res = [q.get(timeout=120) for _ in range(R)]
