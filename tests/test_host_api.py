@@ -60,3 +60,70 @@ def test_compute_needs_gpu_and_fails_loudly():
     f = Function(FunctionSpace(mesh, ('DG', 0)))
     with pytest.raises(FemoError):
         assembleVector(pdeRes(u, None, f))
+
+
+def test_tracked_sources_skip_only_unchanged_uploads():
+    """update() may skip a source it already holds only when the source is version-tracked storage at the same
+    version; plain arrays, bumped versions and any other write to the Function invalidate the shortcut."""
+    from femo_b200 import _hostops as H
+    mesh = createUnitSquareMesh(3)
+    f = Function(FunctionSpace(mesh, ('DG', 0)))
+    src = H.tracked(np.arange(18.0))
+    update(f, src)
+    v0 = f._host_ver
+    assert np.array_equal(getFuncArray(f), np.arange(18.0)) and f._src is not None
+    update(f, src)                                          # same storage, same version: nothing to do
+    assert f._host_ver == v0
+    np.asarray(src)[:] = 7.0                                # the owner writes ...
+    update(f, src)                                          # ... but forgot to bump: by contract still skipped
+    assert f._host_ver == v0
+    src.bump()
+    update(f, src)
+    assert f._host_ver > v0 and np.all(getFuncArray(f) == 7.0)
+    plain = np.full(18, 3.0)
+    update(f, plain)
+    v1 = f._host_ver
+    update(f, plain)                                        # untracked arrays are always copied
+    assert f._host_ver > v1 and f._src is None
+    update(f, src)                                          # tracked again after something else wrote the Function
+    assert np.all(getFuncArray(f) == 7.0)
+    f.vector.set(1.5)                                       # constant fill invalidates the shortcut as well
+    update(f, src)
+    assert np.all(getFuncArray(f) == 7.0)
+    assert H.tracked(np.zeros(4))[1:].version is None       # views are never tracked
+
+
+def test_simulator_storage_versions(monkeypatch):
+    """The Simulator stand-in bumps a variable's version on every write it performs and whenever it hands out a
+    writable reference, so operations never see stale device copies."""
+    from femo_b200.csdl_opt._csdl_compat import Simulator, Model
+    from femo_b200 import _hostops as H
+
+    class M(Model):
+        def define(self):
+            self.create_input('x', shape=5, val=1.0)
+    sim = Simulator(M())
+    x = sim.vars['x']
+    assert isinstance(x, H.TrackedArray) and x.version == 1
+    sim['x'] = np.arange(5.0)
+    assert sim.vars['x'].version == 2
+    ref = sim['x']                                          # writable reference leaves the simulator
+    assert sim.vars['x'].version == 3 and ref is sim.vars['x']
+
+
+def test_hostops_bulk_helpers_match_numpy():
+    from femo_b200 import _hostops as H
+    rng = np.random.default_rng(0)
+    for n in (7, H.BIG + 3):
+        a, b = rng.standard_normal(n), rng.standard_normal(n)
+        d = a.copy()
+        H.iadd(d, b, -2.5)
+        assert np.allclose(d, a - 2.5 * b, rtol=1e-15, atol=1e-15)
+        H.scaled_copy(d, b, 3.0)
+        assert np.array_equal(d, 3.0 * b)
+        H.copy(d, a)
+        assert np.array_equal(d, a)
+        H.fill(d, 4.0)
+        assert np.all(d == 4.0)
+        H.copy(d, np.array([2.0]))
+        assert np.all(d == 2.0)
