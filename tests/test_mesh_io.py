@@ -145,3 +145,27 @@ def test_gpu_assembly_on_unstructured_mesh(cuda_device):
         b = rng.standard_normal(F.N)
         x, info = p.linear_solve(vals, p.to_device(b), rtol=1e-12, precond=0, max_it=20000, check_every=20)
         assert info['converged'] and relerr(x.cpu().numpy(), spla.spsolve(A.tocsc(), b)) < 1e-8
+
+
+def test_gmsh_vertex_order_is_converted_to_tensor_order(tmp_path):
+    """Gmsh lists quadrilateral (and hexahedron) vertices counter-clockwise; the engine and basix use tensor-product
+    order.  A 2x1 quadrilateral mesh written in Gmsh order must come back with positive Jacobians everywhere."""
+    from femo_b200.fea.mesh_io import read_msh
+    pts = np.array([[0, 0], [1, 0], [2, 0], [0, 1], [1, 1], [2, 1]], dtype=float)
+    quads_ccw = [(0, 1, 4, 3), (1, 2, 5, 4)]
+    with open(tmp_path / 'q.msh', 'w') as f:
+        f.write('$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n6\n')
+        for i, x in enumerate(pts):
+            f.write('%d %g %g 0\n' % (i + 1, x[0], x[1]))
+        f.write('$EndNodes\n$Elements\n2\n')
+        for k, q in enumerate(quads_ccw):
+            f.write('%d 3 2 1 1 %d %d %d %d\n' % (k + 1, *(v + 1 for v in q)))
+        f.write('$EndElements\n')
+    p, cells, _ = read_msh(str(tmp_path / 'q.msh'))
+    conn, tags = cells['quadrilateral']
+    assert conn.tolist() == [[0, 1, 3, 4], [1, 2, 4, 5]] and tags.tolist() == [1, 1]
+    X = p[conn][:, :, :2]
+    e1, e2 = X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]                      # tensor order: v1 along xi, v2 along eta
+    assert np.all(e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0] > 0)
+    em = E.EngineMesh.from_arrays('quadrilateral', p[:, :2], conn)
+    assert em.nbfacets == 6

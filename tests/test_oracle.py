@@ -174,3 +174,32 @@ def test_oracle_reproduces_golden_fixtures(path):
     assert np.allclose(A.data, z['Jbc'], rtol=1e-13, atol=1e-15)
     assert np.allclose(asm.assemble_vector(F.residual(u, f), F.N), z['R'], rtol=1e-13, atol=1e-15)
     assert np.isclose(asm.assemble_scalar(F.output(0, u, f)), float(z['out']), rtol=1e-13)
+
+
+def test_hex_oracle_patch_test_and_rigid_modes():
+    """Pins for the hexahedral SIMP oracle (no reference fixture exists): rigid-body motions carry no stress, a
+    linear displacement field gives constant stress and therefore zero interior nodal forces (patch test), and
+    the element matrices are symmetric positive semi-definite with exactly 6 zero modes."""
+    m = om.box_hex((0.0, 0.0, 0.0), (3.0, 2.0, 1.5), 4, 3, 2)
+    fc, fl = m.exterior_facets()
+    F = fam.SimpHex8(m, np.nonzero(fl == 3)[0])
+    rho = np.full(F.M, 0.7)
+    X = m.coords
+    A = asm.assemble_matrix(F.jacobian(np.zeros(F.N), rho), (F.N, F.N), None)
+    for u in (np.tile([1.0, -2.0, 0.5], m.nverts),                                   # translation
+              np.stack([-X[:, 1], X[:, 0], 0 * X[:, 0]], axis=1).ravel()):           # rotation about z
+        assert np.abs(A @ u).max() < 1e-12 * np.abs(A.data).max() * np.abs(u).max()
+    G = np.array([[0.3, -0.1, 0.2], [0.05, 0.4, -0.3], [0.1, 0.2, -0.25]])
+    u = (X @ G.T).ravel()
+    r = A @ u
+    on_boundary = np.zeros(m.nverts, dtype=bool)
+    on_boundary[np.unique(m.cells[fc][np.arange(fc.size)[:, None], m.local_facets[fl]])] = True
+    assert np.abs(r.reshape(-1, 3)[~on_boundary]).max() < 1e-12 * np.abs(r).max()
+    K = F._khat()[0]
+    assert np.allclose(K, K.T, atol=1e-14)
+    w = np.linalg.eigvalsh(K)
+    assert (np.abs(w) < 1e-12 * w.max()).sum() == 6 and w.min() > -1e-12 * w.max()
+    # total traction equals f times the tagged area
+    Fe = asm.assemble_vector([(F.fdofs, None, F._traction())], F.N).reshape(-1, 3).sum(axis=0)
+    area = 2.0 * 1.5
+    assert np.allclose(Fe, np.array([0.0, -0.25, 0.0]) * area, atol=1e-13)
