@@ -203,3 +203,25 @@ def test_hex_oracle_patch_test_and_rigid_modes():
     Fe = asm.assemble_vector([(F.fdofs, None, F._traction())], F.N).reshape(-1, 3).sum(axis=0)
     area = 2.0 * 1.5
     assert np.allclose(Fe, np.array([0.0, -0.25, 0.0]) * area, atol=1e-13)
+
+
+@pytest.mark.parametrize('Family', [fam.NonlinearPoissonP1, fam.NonlinearPoissonP2])
+def test_nonlinear_poisson_oracles_converge_to_the_manufactured_solution(Family):
+    """The example's manufactured solution u_ex = sin(2 pi x) sin(pi y) (run_nonlinear_poisson_opt.py:144-145, 165-169) with
+    f = -lap(u_ex) + u_ex^3 averaged per cell: the Nitsche-SNES state must converge to u_ex at second order in L2 for P1
+    and P2 alike (the DG0 source limits both).  Pins assembly + boundary terms + solver of both oracles at once."""
+    errs = []
+    for n in (8, 16, 32):
+        m = om.unit_square_tri(n)
+        F = Family(m)
+        pts, w = quad.triangle(6)
+        xq = np.einsum('qa,cad->cqd', np.stack([1 - pts[:, 0] - pts[:, 1], pts[:, 0], pts[:, 1]], axis=1), m.coords[m.cells])
+        ue = np.sin(2 * np.pi * xq[..., 0]) * np.sin(np.pi * xq[..., 1])
+        fq = 5 * np.pi ** 2 * ue + ue ** 3                       # -lap(u_ex) + u_ex^3
+        f = (fq * w[None, :]).sum(axis=1) / w.sum()
+        u, info = solvers.StatePath(F, None).solve_snes(np.zeros(F.N), [f])
+        J = asm.assemble_scalar(F.output(0, u, f))
+        reg = 0.5 * F.alpha * float((0.5 * F.detJ * f * f).sum())
+        errs.append(np.sqrt(2.0 * (J - reg)))
+    rates = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
+    assert errs[-1] < 5e-3 and min(rates) > 1.8, (errs, rates)
