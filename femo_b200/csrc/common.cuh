@@ -29,7 +29,7 @@ constexpr int kMaxPartials = 4096;   // upper bound on CTAs of any reducing kern
 constexpr int kMaxSlots = 12;
 
 // device scalar slots (doubles) used by the Krylov / Newton drivers
-enum Scalar { S_ALPHA = 0, S_BETA, S_RZ, S_RR, S_PQ, S_TMP0, S_TMP1, S_TMP2, S_BB, S_GM = 16, S_COUNT = 128 };
+enum Scalar { S_ALPHA = 0, S_BETA, S_RZ, S_RR, S_PQ, S_TMP0, S_TMP1, S_TMP2, S_BB, S_FLAG /* int flag raised by k_csr_to_dia */, S_GM = 16, S_COUNT = 128 };
 
 // ---- reductions (deterministic: fixed assignment, fixed tree) ---------------
 __device__ __forceinline__ double warp_sum(double v) {
@@ -93,6 +93,15 @@ struct Arena {
     static size_t need(size_t count, size_t elem) { return (count * elem + 255) & ~size_t(255); }
 };
 
+// DIA (diagonal) storage of a lattice operator: nd planes of np fp32 values, plane s holds a(i, i + off[s])
+constexpr int kDiaMax = 9;
+struct DiaMat {
+    const float *v = nullptr;
+    int64_t np = 0, n = 0;
+    int nd = 0, sdiag = 0;      // sdiag: the plane with off == 0
+    int off[kDiaMax] = {0};
+};
+
 }  // namespace femo
 
 struct femo_mesh {
@@ -111,6 +120,8 @@ struct femo_mg_level {
                                                     // element matrix of the level's (congruent) cells: matrix-free V-cycle
     double *fb = nullptr, *fx = nullptr;            // full-multigrid start: restricted right-hand side, nested iterate
     double lmax = 2.0;
+    femo::DiaMat dia;                               // lattice stencil levels: the V-cycle streams DIA planes (stencil.cuh);
+    bool dia_valid = false;                         // they alias the vals32 buffer
 };
 
 struct femo_problem {
@@ -182,4 +193,5 @@ struct femo_problem {
     int gm_restart = 0;
     // counters (bench: how many of our kernels were launched)
     long long launches = 0;
+    long long dia_count[4] = {0, 0, 0, 0};   // launches of the DIA operator kernel on this level, by mode
 };

@@ -30,6 +30,26 @@ static int halo_nodes(femo_problem *p, double *v) {
     return FEMO_OK;
 }
 
+// Same for an fp32 node vector (the diagonal plane of a DIA level: ghost rows are only partially assembled locally)
+static int halo_nodes_f32(femo_problem *p, float *v) {
+    const SlabInfo &s = p->slab;
+    if (!s.active || !g_comm.active) return FEMO_OK;
+    const size_t len = (size_t)(p->mesh.n[0] + 1) * (p->mesh.kind == MESH_HEX ? (size_t)(p->mesh.n[1] + 1) : 1) * p->state.block;
+    NcclApi &a = g_comm.api;
+    FEMO_NCCL(a.GroupStart());
+    if (s.rank > 0) {
+        FEMO_NCCL(a.Send(v + (size_t)s.own0 * len, len, ncclFloat, s.rank - 1, g_comm.comm, p->stream));
+        FEMO_NCCL(a.Recv(v + (size_t)(s.own0 - 1) * len, len, ncclFloat, s.rank - 1, g_comm.comm, p->stream));
+    }
+    if (s.rank < s.nranks - 1) {
+        FEMO_NCCL(a.Send(v + (size_t)(s.own1 - 1) * len, len, ncclFloat, s.rank + 1, g_comm.comm, p->stream));
+        FEMO_NCCL(a.Recv(v + (size_t)s.own1 * len, len, ncclFloat, s.rank + 1, g_comm.comm, p->stream));
+    }
+    FEMO_NCCL(a.GroupEnd());
+    g_comm.halo_exchanges++;
+    return FEMO_OK;
+}
+
 // Refresh the ghost cell row (below) of a cell-wise (DG0) vector.
 static int halo_cells(femo_problem *p, double *v) {
     const SlabInfo &s = p->slab;

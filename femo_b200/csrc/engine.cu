@@ -760,6 +760,7 @@ static int propagate_bc(femo_problem *root, int start = 0);
 static int set_bc_impl(femo_problem *p, const int32_t *dofs, const int32_t *list_ptr, int nlists, const double *g);
 }
 
+#include "stencil.cuh"
 #include "multigrid.cuh"
 #include "krylov.cuh"
 #include "gmres.cuh"
@@ -1433,7 +1434,7 @@ static void child_bytes(const femo_problem *c, bool coarsest, size_t *sb, size_t
     s += pattern_bytes(c->pat[0], true);
     s += Arena::need(N, 1) + 2 * Arena::need(N, 8) + Arena::need(N, 4) + 1024;
     if (hex_matfree_level(c)) { s += Arena::need(576, 8); w += Arena::need((size_t)c->mesh.ncells, 8); }
-    w += Arena::need(c->pat[0].nnz, 8) + Arena::need(c->pat[0].nnz, 4) + 9 * Arena::need(N, 8) + Arena::need((size_t)c->mesh.ncells, 8);
+    w += Arena::need(c->pat[0].nnz, 8) + Arena::need(fp32_copy_len(c), 4) + 9 * Arena::need(N, 8) + Arena::need((size_t)c->mesh.ncells, 8);
     w += Arena::need(3 * kMaxPartials, 8) + Arena::need(S_COUNT, 8) + 1024;
     if (coarsest) w += 2 * Arena::need(N * N, 8);
     *sb = s;
@@ -1484,7 +1485,7 @@ static int upload_child(femo_problem *root, femo_problem *c, bool coarsest) {
     if (!c->d_lift_rows) return set_err(FEMO_EINVAL, "static arena too small (multigrid level)");
     femo_mg_level &L = c->mgl;
     L.vals = root->wk.take<double>(P.nnz);
-    L.vals32 = root->wk.take<float>(P.nnz);
+    L.vals32 = root->wk.take<float>(fp32_copy_len(c));
     if ((rc = setup_hex_matfree(root, c))) return rc;
     L.dinv = root->wk.take<double>(N);
     L.x = root->wk.take<double>(N);
@@ -1498,6 +1499,7 @@ static int upload_child(femo_problem *root, femo_problem *c, bool coarsest) {
     L.fx = root->wk.take<double>(N);
     c->d_partials = root->wk.take<double>(3 * kMaxPartials);
     c->d_scalars = root->wk.take<double>(S_COUNT);
+    if (c->d_scalars) FEMO_CUDA(cudaMemsetAsync(c->d_scalars, 0, sizeof(double) * S_COUNT, root->stream));
     if (coarsest) {
         L.dense = root->wk.take<double>((size_t)N * N);
         L.dense_tmp = root->wk.take<double>((size_t)N * N);
@@ -1542,7 +1544,7 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     w += 2 * Arena::need(p->pat[0].nnz, 8);        // Newton's Jacobian values (plain, BC'd)
     w += Arena::need(tv, 8);                       // transposed values
     w += Arena::need(N, 8);                        // Chebyshev direction of multigrid level 0
-    if (!p->mg.empty()) w += Arena::need(p->pat[0].nnz, 4);   // fp32 copy of the fine-level values for the V-cycle
+    if (!p->mg.empty()) w += Arena::need(fp32_copy_len(p), 4);   // fp32 copy (CSR order or DIA planes) of the fine-level values for the V-cycle
     if (hex_matfree_level(p)) { s += Arena::need(576, 8); w += Arena::need((size_t)M.ncells, 8); }
     if (N <= kMgDenseMax) w += 2 * Arena::need((size_t)N * N, 8);   // explicit inverse (precond 3)
     if (!p->symmetric) w += (size_t)(kGmresRestart + 2) * Arena::need(N, 8) + Arena::need((size_t)(kGmresRestart + 1) * kMaxPartials, 8);
@@ -1735,7 +1737,7 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     p->nt_vals_bc = p->wk.take<double>(p->pat[0].nnz);
     p->d_tvals = p->wk.take<double>(tv);
     p->kr_d = p->wk.take<double>(N);
-    if (!p->mg.empty()) p->mgl.vals32 = p->wk.take<float>(p->pat[0].nnz);
+    if (!p->mg.empty()) p->mgl.vals32 = p->wk.take<float>(fp32_copy_len(p));
     if ((rc = setup_hex_matfree(p, p))) return rc;
     if (!p->symmetric) {
         p->gm_restart = kGmresRestart;
@@ -2018,6 +2020,27 @@ int femo_linear_solve(femo_problem *p, const double *d_vals, const double *d_b, 
     return o.method == 1 ? gmres_solve(p, vals, d_b, d_x, o, info) : cg_solve(p, vals, d_b, d_x, o, info);
 }
 
+/* measurement hook (bench.py roofline): ONE launch of the fine-level V-cycle operator kernel in `mode`
+ * (0 residual, 1 first / 2 later Chebyshev step, 3 fused zero-guess pre-smoother) on the hierarchy the last
+ * multigrid-preconditioned solve set up; vectors are the solver's own work vectors.  info[0] = algorithmic bytes of the
+ * launch, info[1] = fine-level launches of this mode so far (before this one). */
+int femo_vcycle_op_probe(femo_problem *p, int mode, int64_t info[2]) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (mode < 0 || mode > 3) return set_err(FEMO_EINVAL, "femo_vcycle_op_probe: mode 0..3");
+    if (!dia_ready(p)) return set_err(FEMO_ESTATE, "femo_vcycle_op_probe: no DIA hierarchy (run a precond=2 solve on a lattice P1 problem first)");
+    DiaEpi E;
+    E.b = p->kr_r; E.rin = p->kr_r; E.c0 = 0.5; E.c1 = 0.25; E.c2 = 0.125;
+    const int64_t N = p->state.ndofs;
+    int64_t bytes = 28 * N;                                   // 7 fp32 planes
+    if (mode == DIA_PLAIN) bytes += 24 * N;                   // x, b read; r written
+    if (mode == DIA_CHEB0) { E.rout = p->kr_w; E.dout = p->kr_q; bytes += 32 * N; }     // x, b read; r, d written
+    if (mode == DIA_CHEBK) { E.xacc = p->kr_z; E.xmode = 0; bytes += 32 * N; }          // d, r read; x read + written
+    if (mode == DIA_PRE2) bytes += 16 * N;                    // b read; x written
+    if (info) { info[0] = bytes; info[1] = p->dia_count[mode]; }
+    return launch_dia(p, mode, p->kr_d, mode == DIA_PRE2 ? p->kr_z : p->kr_w, E);
+}
+
 int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton_info *info) {
     int rc;
     if ((rc = need_device(p))) return rc;
@@ -2060,11 +2083,20 @@ int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton
         if ((rc = (ko.method == 1 ? gmres_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki) : cg_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki, true)))) return rc;
         kit += ki.iterations;
         spmvs += ki.spmv_count;
+        // the reference's LU cannot fail; a Krylov solve can (max_it, breakdown, NaN): never apply such a step silently
+        if (!ki.converged || !(ki.rnorm == ki.rnorm)) {
+            if (info) {
+                info->iterations = it; info->converged = -1; info->fnorm0 = f0; info->fnorm = fn;
+                info->krylov_iterations = kit; info->spmv_count = spmvs;
+            }
+            return set_err(FEMO_ENOCONV, "linear solve inside the Newton iteration did not converge (Krylov max_it reached or non-finite residual)");
+        }
         k_axpy<<<red_grid(p, n), kThreads, 0, st>>>(-1.0, p->nt_dx, x, n);
         p->launches++;
         FEMO_CHECK_LAUNCH();
         if ((rc = eval_F())) return rc;
         ++it;
+        if (!(fn == fn) || std::isinf(fn)) return set_err(FEMO_ENOCONV, "Newton iteration produced a non-finite residual norm");
         if (fn < opts->atol) reason = 1;
         else if (snes ? (fn <= opts->rtol * f0) : (f0 > 0 && fn / f0 < opts->rtol)) reason = 2;
         else if (snes) {

@@ -646,10 +646,82 @@ __global__ void __launch_bounds__(kThreads) k_to_f32(const double *__restrict__ 
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) o[i] = (float)a[i];
 }
 
+// ---- DIA (stencil) levels ------------------------------------------------------------------------------------
+static inline bool dia_ready(const femo_problem *L) { return L->mgl.dia_valid; }
+
+// column offsets of a scalar vertex space on a right-diagonal triangle lattice: the node itself, its x / y
+// neighbours and the two ends of the cell diagonals
+static inline bool dia_offsets(const femo_problem *L, DiaMat &A) {
+    if (getenv("FEMO_NO_DIA")) return false;
+    if (!(L->mesh.lattice && L->mesh.kind == MESH_TRI && L->state.element == EL_VERTEX && L->state.block == 1)) return false;
+    const int w = L->mesh.n[0] + 1;
+    const int off[7] = {-w - 1, -w, -1, 0, 1, w, w + 1};
+    A.nd = 7;
+    A.sdiag = 3;
+    for (int s = 0; s < 7; ++s) A.off[s] = off[s];
+    A.n = L->state.ndofs;
+    A.np = (A.n + 31) & ~(int64_t)31;
+    return true;
+}
+// floats reserved for the fp32 operator copy of a level: the CSR copy or the DIA planes, whichever is larger
+static inline size_t fp32_copy_len(const femo_problem *L) {
+    DiaMat A;
+    size_t n = (size_t)L->pat[0].nnz;
+    if (dia_offsets(L, A)) n = std::max<size_t>(n, (size_t)A.nd * (size_t)A.np);
+    return n;
+}
+
+// re-layout the level's assembled (BC'd) values as DIA planes in the fp32 buffer
+static int dia_convert(femo_problem *L) {
+    femo_mg_level &M = L->mgl;
+    DiaMat A;
+    if (!dia_offsets(L, A) || !M.vals32) return FEMO_OK;
+    const DevPattern &D = L->dpat[0];
+    A.v = M.vals32;
+    // one pass: planes, dinv and the Gershgorin partial maxima (needs <= kMaxPartials CTAs: finalised in chunks below)
+    const int g = grid_for(A.n);
+    double *part = L->d_scratch ? L->d_scratch : L->d_partials;      // per-CTA maxima: the element scratch is free here
+    if ((size_t)g > L->scratch_len) return set_err(FEMO_ESTATE, "DIA conversion: scratch too small for the partial maxima");
+    k_csr_to_dia<7><<<g, kThreads, 0, L->stream>>>(D.rowptr, D.col, M.vals, A, M.vals32,
+                                                   reinterpret_cast<int *>(L->d_scalars + S_FLAG), M.dinv, L->own_off,
+                                                   L->own_off + L->own_n, part);
+    k_max_finalize<<<1, kThreads, 0, L->stream>>>(part, g, L->d_scalars, S_TMP2);
+    L->launches += 2;
+    FEMO_CHECK_LAUNCH();
+    M.dia = A;
+    M.dia_valid = true;
+    // the fused pre-smoother scales NEIGHBOUR entries by their 1/a_jj: ghost rows need the owner's diagonal
+    return halo_nodes_f32(L, M.vals32 + (size_t)A.sdiag * A.np);
+}
+
+static int launch_dia(femo_problem *L, int mode, const double *x, double *y, const DiaEpi &E) {
+    int rc = halo_nodes(L, const_cast<double *>(mode == DIA_PRE2 ? E.b : x));
+    if (rc) return rc;
+    const DiaMat &A = L->mgl.dia;
+    const int g = grid_for(A.n);
+    cudaStream_t st = L->stream;
+    switch (mode) {
+        case DIA_PLAIN: k_dia_apply<DIA_PLAIN, 7><<<g, kThreads, 0, st>>>(A, x, y, E); break;
+        case DIA_CHEB0: k_dia_apply<DIA_CHEB0, 7><<<g, kThreads, 0, st>>>(A, x, y, E); break;
+        case DIA_CHEBK: k_dia_apply<DIA_CHEBK, 7><<<g, kThreads, 0, st>>>(A, x, y, E); break;
+        default: k_dia_pre2<<<g, kThreads, 0, st>>>(A, E.b, y, E); break;
+    }
+    L->launches++;
+    L->dia_count[mode & 3]++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
 // the level's SpMV with a fused Chebyshev epilogue, streaming the fp32 copy of the values when requested
 static int mg_spmv_cheb(femo_problem *L, bool fp32, int kind, const double *x, const SpmvEpi &E) {
     femo_mg_level &M = L->mgl;
     if (fp32 && hex_matfree_ready(L)) return launch_hex_matfree(L, kind, x, nullptr, E);
+    if (fp32 && dia_ready(L)) {
+        DiaEpi De;
+        De.b = E.b; De.rin = E.rin; De.rout = E.rout; De.dout = E.dout; De.xacc = E.xacc;
+        De.c1 = E.c1; De.c2 = E.c2; De.xmode = E.xmode;
+        return launch_dia(L, kind == EPI_CHEB0 ? DIA_CHEB0 : DIA_CHEBK, x, nullptr, De);
+    }
     if (fp32 && M.vals32) return launch_spmv_cheb(L, kind, M.vals32, x, E);
     return launch_spmv_cheb(L, kind, M.vals, x, E);
 }
@@ -666,6 +738,13 @@ static int mg_smooth(femo_problem *L, const double *b, double *x, bool zero_gues
     double *dcur = M.d, *dnext = M.q;
     const double *rin;
     int xmode;
+    const bool dia = fp32 && dia_ready(L) && !hex_matfree_ready(L);
+    if (zero_guess && deg == 2 && dia) {     // d0, the operator and both updates in one kernel
+        const double rho1 = 1.0 / (2.0 * sigma - rho);
+        DiaEpi E;
+        E.b = b; E.c0 = 1.0 / theta; E.c1 = rho1 * rho; E.c2 = 2.0 * rho1 / delta;
+        return launch_dia(L, DIA_PRE2, nullptr, x, E);
+    }
     if (zero_guess) {
         if (deg <= 1) {
             k_cheb_first<true><<<g, kThreads, 0, st>>>(b, M.dinv, 1.0 / theta, dcur, x, n);
@@ -695,6 +774,7 @@ static int mg_smooth(femo_problem *L, const double *b, double *x, bool zero_gues
         SpmvEpi E;
         E.dinv = M.dinv; E.rin = rin; E.rout = M.r; E.dout = dnext; E.xacc = x;
         E.c1 = rho_new * rho; E.c2 = 2.0 * rho_new / delta; E.xmode = xmode;
+        if (dia && k == deg) E.rout = E.dout = nullptr;      // nobody reads the last residual / direction
         if ((rc = mg_spmv_cheb(L, fp32, EPI_CHEBK, dcur, E))) return rc;
         std::swap(dcur, dnext);
         rin = M.r;
@@ -758,6 +838,10 @@ static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, con
         SpmvEpi E;
         E.b = b;
         rc = launch_hex_matfree(L, EPI_PLAIN, x, M.r, E);
+    } else if (mp.fp32 && dia_ready(L)) {
+        DiaEpi E;
+        E.b = b;
+        rc = launch_dia(L, DIA_PLAIN, x, M.r, E);
     } else if (mp.fp32 && M.vals32) rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals32, x, M.r, b, nullptr);
     else rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, x, M.r, b, nullptr);
     if (rc) return rc;
@@ -982,11 +1066,16 @@ static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true) {
             if ((rc = femo_assemble_jacobian(L, L->has_bc ? nullptr : M.vals, L->has_bc ? M.vals : nullptr))) return rc;
         }
         const DevPattern &D = L->dpat[0];
+        bool dia_setup = false;
         if (fp32 && M.ec && M.k0 && L->coef[1] && lv < nlev - 1) {       // matrix-free V-cycle operator of this level
             const int64_t ncell = L->mesh.ncells;
             k_pow_cells<<<grid_for(ncell), kThreads, 0, st>>>(L->coef[1], L->params[4], M.ec, ncell);
             L->launches++;
+        } else if (fp32 && M.vals32 && lv < nlev - 1 && dia_offsets(L, M.dia)) {
+            if ((rc = dia_convert(L))) return rc;
+            dia_setup = true;
         } else if (fp32 && M.vals32 && lv < nlev - 1) {
+            M.dia_valid = false;
             const int64_t nnz = L->pat[0].nnz;
             k_to_f32<<<(int)std::min<int64_t>((nnz + kThreads - 1) / kThreads, (int64_t)L->num_sms * 16), kThreads, 0, st>>>(M.vals, M.vals32, nnz);
             L->launches++;
@@ -996,15 +1085,18 @@ static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true) {
             k_dense_inverse<<<1, kThreads, 0, st>>>(D.rowptr, D.col, M.vals, (int)n, M.dense_tmp, M.dense);
             L->launches++;
         } else {
-            const int g = red_grid(L, n);
-            k_diag_gershgorin<<<g, kThreads, 0, st>>>(D.rowptr, D.col, M.vals, M.dinv, n, L->own_off, L->own_off + L->own_n, L->d_partials);
-            k_max_finalize<<<1, kThreads, 0, st>>>(L->d_partials, g, L->d_scalars, S_TMP2);
-            L->launches += 2;
-            FEMO_CHECK_LAUNCH();
+            if (!dia_setup) {
+                const int g = red_grid(L, n);
+                k_diag_gershgorin<<<g, kThreads, 0, st>>>(D.rowptr, D.col, M.vals, M.dinv, n, L->own_off, L->own_off + L->own_n, L->d_partials);
+                k_max_finalize<<<1, kThreads, 0, st>>>(L->d_partials, g, L->d_scalars, S_TMP2);
+                L->launches += 2;
+                FEMO_CHECK_LAUNCH();
+            }
             if ((rc = allreduce_scalars(L, S_TMP2, 1, true))) return rc;
-            double lm;
-            if ((rc = read_scalars(L, S_TMP2, 1, &lm))) return rc;
-            M.lmax = lm;
+            double lm[3];
+            if ((rc = read_scalars(L, S_TMP2, 3, lm))) return rc;
+            M.lmax = lm[0];
+            if (lm[2] != 0.0) return set_err(FEMO_ESTATE, "DIA conversion met a column offset outside the lattice stencil");
         }
         FEMO_CHECK_LAUNCH();
     }

@@ -314,6 +314,12 @@ class EngineProblem:
         check(lib.femo_spmv(self._h, which, self._p(vals), self._p(x), self._p(out), 1 if transpose else 0))
         return out
 
+    def vcycle_op_probe(self, mode):
+        """One launch of the fine-level V-cycle operator kernel (bench.py roofline); returns (algorithmic bytes, fine-level launches of this mode so far)."""
+        info = (C.c_int64 * 2)()
+        check(lib.femo_vcycle_op_probe(self._h, int(mode), info))
+        return int(info[0]), int(info[1])
+
     def axpy(self, a, x, y):
         check(lib.femo_axpy(self._h, float(a), self._p(x), self._p(y), x.numel()))
         return y

@@ -32,11 +32,26 @@ class FormFamily:
     # -- registry: forms built from the same (state, inputs) share one family --
     @classmethod
     def get(cls, family_id, mesh, state, inputs, params=(), tagged=None):
+        """Forms over the same (state, inputs, tagged facets) share one engine problem.  Parameters that
+        fix the LAYOUT (the projection family's target / source kinds) are part of the key; the others are
+        coefficients the kernels read at launch time, so a rebuilt form with new constants (a new load, a
+        new power, a new current) updates them on the existing problem instead of silently keeping the old."""
         reg = state.__dict__.setdefault('_femo_families', {})
-        key = (family_id,) + tuple(id(f) for f in inputs)
+        params = [float(v) for v in params]
+        tsig = None if tagged is None else hash(np.asarray(tagged, dtype=np.int32).tobytes())
+        layout = tuple(params[:2]) if family_id == _E.FAMILY_MASS_P1 else ()
+        key = (family_id,) + tuple(id(f) for f in inputs) + (tsig, layout)
         fam = reg.get(key)
         if fam is None:
             fam = reg[key] = cls(family_id, mesh, state, inputs, params, tagged)
+            fam._key_inputs = list(inputs)         # keeps id() of the inputs from being recycled
+        else:
+            # only what THIS builder passes differently from its previous call (constants set through
+            # other forms of the family, e.g. the output's alpha, are not reset)
+            for i, v in enumerate(params):
+                if i >= len(fam._get_params) or fam._get_params[i] != v:
+                    fam.set_param(i, v)
+        fam._get_params = params
         return fam
 
     def set_aux(self, index, function):
@@ -47,9 +62,12 @@ class FormFamily:
     def set_param(self, index, value):
         while len(self.params) <= index:
             self.params.append(0.0)
+        value = float(value)
         if self._prob is not None and self.params[index] != value:
-            raise RuntimeError('family parameters cannot change after the engine problem was built')
-        self.params[index] = float(value)
+            if self.family_id == _E.FAMILY_SIMP_HEX8 and index == 0:
+                raise RuntimeError("Poisson's ratio is baked into the uploaded unit element matrix; build a new form family")
+            self._prob.set_param(index, value)       # kernels read the parameter vector at launch time
+        self.params[index] = value
 
     def slot_of(self, function):
         if function is self.state:
@@ -102,14 +120,17 @@ class FormFamily:
         """Install the dirichletbc objects of this call (fea_dolfinx.py:169-176)."""
         p = self.problem
         bcs = list(bcs or [])
-        sig = tuple((id(b), b.dofs.size) for b in bcs)
+        # value-aware signature (dolfinx reads the live bc values on every solve): dof lists AND the values
+        # at those dofs; O(boundary dofs) per call
+        vals = [b.dof_values() for b in bcs]
+        sig = tuple((b.dofs.size, hash(b.dofs.tobytes()), hash(v.tobytes())) for b, v in zip(bcs, vals))
         if sig == self._bc_sig:
             return
         if not bcs:
             p.set_bc([], None)
         else:
             g = np.zeros(p.N)
-            for b in bcs:
-                g[b.dofs] = b.values(p.N)[b.dofs]
+            for b, v in zip(bcs, vals):
+                g[b.dofs] = v
             p.set_bc([b.dofs for b in bcs], g)
         self._bc_sig = sig

@@ -344,6 +344,12 @@ class DirichletBC:
             return self.value._host_array()
         return np.full(n, float(np.ravel(getattr(self.value, 'value', self.value))[0]))
 
+    def dof_values(self):
+        """Current prescribed values at this condition's dofs (read live, as dolfinx does on every solve)."""
+        if isinstance(self.value, Function):
+            return np.ascontiguousarray(self.value._host_array()[self.dofs], dtype=np.float64)
+        return np.full(self.dofs.size, float(np.ravel(getattr(self.value, 'value', self.value))[0]))
+
 
 def dirichletbc(value, dofs, V=None):
     """dolfinx.fem.dirichletbc as used at fea_dolfinx.py:169-176."""

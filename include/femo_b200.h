@@ -233,8 +233,14 @@ typedef struct femo_krylov_info {
 
 /* Replaces KSP preonly + LU(MUMPS): solveKSP_mumps / setUpKSP_MUMPS and the
  * explicit transpose(A) (utils_dolfinx.py:241-245,476-512; fea_dolfinx.py:
- * 192-222).  Solves A x = b or A^T x = b on the dR/du pattern; x is the
- * initial guess on entry.  Synchronises. */
+ * 192-222).  Solves A x = b or A^T x = b on the dR/du pattern.  x is the
+ * initial guess on entry for precond 0/1/3; with the multigrid preconditioner
+ * (precond 2) the full-multigrid iterate REPLACES the caller's x unless
+ * opts.restart == 1 (then x is honoured as x0).  Synchronises. */
+int femo_vcycle_op_probe(femo_problem *p, int mode, int64_t info[2]);
+/* ^ measurement hook for bench.py's roofline: one launch of the fine-level V-cycle operator kernel (mode 0 residual,
+ *   1 / 2 Chebyshev steps, 3 fused pre-smoother) on the hierarchy of the last precond=2 solve; info[0] receives the
+ *   algorithmic bytes of that launch, info[1] the fine-level launches of that mode so far. */
 int femo_linear_solve(femo_problem *p, const double *d_vals, const double *d_b, double *d_x, int transpose,
                       const femo_krylov_opts *opts, femo_krylov_info *info);
 

@@ -15,11 +15,27 @@ def square_boundary_lists(coords):
 
 
 class Case:
-    def __init__(self, famid, n, ny=None, seed=0, bc='auto', g=None, upload=True, device=0, mg=False):
+    def __init__(self, famid, n, ny=None, seed=0, bc='auto', g=None, upload=True, device=0, mg=False, oracle=True):
         self.famid, self.n = famid, n
         self.emesh = E.EngineMesh.unit_square(n, ny)
-        self.omesh = om.unit_square_tri(n, ny)
         rng = np.random.default_rng(seed)
+        if not oracle:              # large meshes: engine only (property tests), no oracle family
+            self.p = E.EngineProblem(self.emesh, famid)
+            if mg:
+                self.p.enable_multigrid()
+            self.coords = self.emesh.coords()
+            self.bc = None
+            if famid == 1 and bc in ('auto', True):
+                self.p.set_bc(square_boundary_lists(self.coords), None)
+            self.u = rng.standard_normal(self.p.N)
+            self.f = rng.standard_normal(self.p.M[0])
+            self.uex = 1.0 / (2 * np.pi ** 2) * np.sin(np.pi * self.coords[:, 0]) * np.sin(np.pi * self.coords[:, 1])
+            self.F = self.sp = None
+            if upload:
+                self.upload(device)
+            return
+        self.omesh = om.unit_square_tri(n, ny)
+        self.coords = self.omesh.coords
         if famid == 1:
             self.F = fam.PoissonP1(self.omesh)
             x = self.omesh.coords
@@ -54,7 +70,7 @@ class Case:
         p.set_coefficient(0, self.d_u)
         p.set_coefficient(1, self.d_f)
         if self.famid == 1:
-            self.d_uex = p.to_device(self.F.u_ex)
+            self.d_uex = p.to_device(self.F.u_ex if self.F is not None else self.uex)
             p.set_coefficient(2, self.d_uex)
 
     def set_state(self, u):

@@ -1,0 +1,110 @@
+"""Correctness of the BENCHED solver configuration (bench.py: fp32 DIA V-cycle, full-multigrid start,
+inexact Newton, Krylov rtol 1e-10) at sizes well above the unit-test meshes:
+
+  * n = 512 against the oracle's SuperLU path (state, adjoint, dJ/df)            -- the oracle finishes in seconds
+  * n = 1024 / 2048 through size-independent properties: fp64 residual norms of the state and adjoint
+    systems recomputed with the assembled fp64 operator, and a directional finite difference of dJ/df
+  * the three V-cycle operator layouts (DIA fp32, CSR fp32, CSR fp64) agree
+
+Everything goes through the C ABI (femo_b200.engine)."""
+import os
+
+import numpy as np
+import pytest
+
+from _cases import Case, relerr
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def bench_step(c, f):
+    """bench.py's EngineStep.step for the nonlinear Poisson family, returning everything it computes."""
+    p = c.p
+    c.set_input(f)
+    c.set_state(np.zeros(c.p.N))
+    ni = p.newton_solve(kind='SNES', krylov_rtol=RTOL, precond=2, cheb_degree=2)
+    vals, _ = p.assemble_jacobian(plain=True, bc=False)
+    dv = p.assemble_dRdm(0)
+    J = p.assemble_output(0)
+    dJdu = p.assemble_output_grad(0, 0)
+    grad = p.assemble_output_grad(0, 1)
+    lam, li = p.linear_solve(vals, dJdu, transpose=True, rtol=RTOL, precond=2, cheb_degree=2)
+    p.axpy(-1.0, p.spmv(1, dv, lam, transpose=True), grad)
+    return dict(ni=ni, li=li, vals=vals, J=J, dJdu=dJdu, lam=lam, grad=grad)
+
+
+def test_bench_settings_match_direct_solve_n512(cuda_device):
+    c = Case(2, 512, seed=0, mg=True)
+    f = 0.1 * np.ones(c.F.M)
+    r = bench_step(c, f)
+    assert r['ni']['converged'] and r['li']['converged']
+    u = c.d_u.cpu().numpy()
+    uo, oinfo = c.sp.solve_snes(np.zeros(c.F.N), [f])
+    assert relerr(u, uo) < 1e-8
+    (go,), lamo = c.sp.total_derivative(0, uo, [f])
+    assert relerr(r['lam'].cpu().numpy(), lamo) < 1e-8
+    assert relerr(r['grad'].cpu().numpy(), go) < 1e-8
+
+
+@pytest.mark.parametrize('n', [1024, 2048])
+def test_bench_settings_residuals_and_fd(cuda_device, n):
+    c = Case(2, n, seed=0, mg=True, oracle=False)
+    p = c.p
+    M = p.M[0]
+    f = 0.1 * np.ones(M)
+    r = bench_step(c, f)
+    assert r['ni']['converged'] and r['li']['converged']
+    # nonlinear residual at the returned state, fp64 assembly
+    R = p.assemble_residual()
+    print('n=%d: ||F(u)|| = %.3e (||F(u0)|| = %.3e), newton its %d, krylov its %d + %d' % (
+        n, float(R.norm()), r['ni']['fnorm0'], r['ni']['iterations'], r['ni']['krylov_iterations'], r['li']['iterations']))
+    assert float(R.norm()) <= 1e-7 * r['ni']['fnorm0']
+    # adjoint system: || A^T lam - dJ/du || / || dJ/du || with the assembled fp64 operator
+    res = p.spmv(0, r['vals'], r['lam'], transpose=True)
+    res -= r['dJdu']
+    assert float(res.norm()) <= 10 * RTOL * float(r['dJdu'].norm())
+    # directional finite difference of the reduced functional along a smooth direction
+    d = 1.0 + 0.5 * np.sin(2 * np.pi * np.arange(M) / M)
+    g = r['grad'].cpu().numpy()
+    h = 1e-4
+    Jp = bench_step(c, f + h * d)['J']
+    Jm = bench_step(c, f - h * d)['J']
+    fd = (Jp - Jm) / (2 * h)
+    assert abs(fd - g @ d) <= 1e-5 * abs(fd), (fd, g @ d)
+
+
+def test_vcycle_layouts_agree(cuda_device):
+    """DIA fp32 planes, the fp32 CSR copy and the assembled fp64 values inside the V-cycle give the same
+    solution (to the Krylov tolerance) in the same number of iterations (+-1)."""
+    sols, its = [], []
+    for mode in ('dia', 'csr32', 'csr64'):
+        if mode == 'csr32':
+            os.environ['FEMO_NO_DIA'] = '1'
+        try:
+            c = Case(2, 200, 136, seed=5, mg=True, oracle=False)
+            c.set_state(0.2 * np.sin(3 * c.coords[:, 0]) * np.cos(2 * c.coords[:, 1]))
+            vals, _ = c.p.assemble_jacobian(plain=True, bc=False)
+            b = c.p.to_device(np.random.default_rng(2).standard_normal(c.p.N))
+            x, info = c.p.linear_solve(vals, b, rtol=1e-12, precond=2, cheb_degree=2,
+                                       mg_precision=1 if mode == 'csr64' else 0)
+        finally:
+            os.environ.pop('FEMO_NO_DIA', None)
+        assert info['converged'], (mode, info)
+        sols.append(x.cpu().numpy())
+        its.append(info['iterations'])
+    assert relerr(sols[0], sols[2]) < 1e-9 and relerr(sols[1], sols[2]) < 1e-9
+    assert max(its) - min(its) <= 1, its
+
+
+@pytest.mark.parametrize('deg', [1, 2, 3, 4])
+def test_dia_smoother_degrees(cuda_device, deg):
+    """Every Chebyshev degree takes a different kernel path (fused degree-2 pre-smoother, chained steps)."""
+    c = Case(1, 96, 80, seed=1, mg=True, oracle=False)
+    _, vbc = c.p.assemble_jacobian(plain=False, bc=True)
+    b = c.p.to_device(np.random.default_rng(4).standard_normal(c.p.N))
+    x, info = c.p.linear_solve(vbc, b, rtol=1e-11, precond=2, cheb_degree=deg)
+    x64, info64 = c.p.linear_solve(vbc, b, rtol=1e-11, precond=2, cheb_degree=deg, mg_precision=1)
+    assert info['converged'] and info64['converged']
+    assert relerr(x.cpu().numpy(), x64.cpu().numpy()) < 1e-8
+    assert abs(info['iterations'] - info64['iterations']) <= 1
