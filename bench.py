@@ -189,8 +189,7 @@ class EngineStep:
             ni = p.newton_solve(kind='SNES', krylov_rtol=KRYLOV_RTOL, precond=2, cheb_degree=2)
             p.assemble_jacobian(plain=True, bc=False, out=self.vals)      # dR/du at the converged state
         p.assemble_dRdm(0, self.dv)                                        # dR/df
-        J = p.assemble_output(k)                                           # objective (host scalar)
-        p.assemble_output_grad(k, 0, self.dJdu)
+        J, _ = p.assemble_output_and_grad(k, self.dJdu)                   # objective (host scalar) + dJ/du, one pass
         p.assemble_output_grad(k, 1, self.grad)
         self.lam.zero_()
         _, li = p.linear_solve(self.vals_bc if self.kind == 'hex' else self.vals, self.dJdu, self.lam, transpose=True,
@@ -198,26 +197,78 @@ class EngineStep:
         p.spmv(1, self.dv, self.lam, transpose=True, out=self.tmp)
         p.axpy(-1.0, self.tmp, self.grad)                                  # dJ/df = pJ/pf - dRdf^T lambda
         self.info = dict(newton_its=ni['iterations'], krylov_its=ni['krylov_iterations'], adjoint_its=li['iterations'],
+                         fnorm0=ni['fnorm0'], fnorm=ni['fnorm'],
                          converged=(bool(ni['converged']) or self.kind == 'hex') and li['converged'], J=J)
         return J
 
 
-def time_spmv(es, reps=50):
-    """Average launch duration of the dominant kernel (fine-level CSR SpMV) with CUDA events."""
-    torch = es.torch
-    p = es.p
-    x = p.new_vector(p.N, 1.0)
-    y = p.new_vector(p.N)
+def verify(es):
+    """Correctness of the timed configuration at its full size, outside the timed region: fp64 residual norm of the
+    returned state, fp64 residual of the adjoint system, and a central finite difference of the reduced functional along
+    a smooth direction against the adjoint gradient (BASELINE.json: derivatives cross-checked by finite differences)."""
+    torch, p = es.torch, es.p
+    es.step()
+    g = es.grad.clone()
+    R = p.assemble_residual()
+    fnorm = float(R.norm())
+    res = p.spmv(0, es.vals, es.lam, transpose=True)
+    res -= es.dJdu
+    adj = float(res.norm()) / float(es.dJdu.norm())
+    M = p.M[0]
+    d = 1.0 + 0.5 * torch.sin(2 * torch.pi * torch.arange(M, device=g.device, dtype=torch.float64) / M)
+    gd = float(g @ d)
+    f0 = es.f.clone()
+    h = 1e-4
+    es.f.copy_(f0 + h * d)
+    Jp = es.step()
+    es.f.copy_(f0 - h * d)
+    Jm = es.step()
+    es.f.copy_(f0)
+    fd = (Jp - Jm) / (2 * h)
+    out = dict(state_residual_norm=fnorm, adjoint_relative_residual=adj, dJdf_dot_d=gd, finite_difference=fd,
+               fd_relative_error=abs(fd - gd) / abs(fd))
+    out['ok'] = bool(fnorm <= 1e-6 * es.info['fnorm0'] and adj < 10 * KRYLOV_RTOL and out['fd_relative_error'] < 1e-5)
+    return out
+
+
+VCYCLE_KERNELS = {0: 'femo::k_dia_apply<DIA_PLAIN,7> (V-cycle residual r = b - A x, fp32 DIA planes)',
+                  1: 'femo::k_dia_apply<DIA_CHEB0,7> (post-smoother first Chebyshev step)',
+                  2: 'femo::k_dia_apply<DIA_CHEBK,7> (post-smoother second Chebyshev step)',
+                  3: 'femo::k_dia_pre2 (fused zero-guess degree-2 pre-smoother)'}
+
+
+def _time_launches(torch, fn, reps):
     for _ in range(5):
-        p.spmv(0, es.vals, x, out=y)
+        fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        p.spmv(0, es.vals, x, out=y)
+        fn()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def time_kernels(es, counts, steps, reps=50):
+    """Average launch duration (CUDA events on the launching stream, inputs > L2) of the hot kernels at the fine
+    level: the four instantiations of the V-cycle operator and the fp64 CSR SpMV of the CG recurrence.
+    counts[mode] = fine-level launches during the timed steps -> share of the step."""
+    torch, p = es.torch, es.p
+    out = []
+    if counts is not None:
+        for mode in range(4):
+            alg, _ = p.vcycle_op_probe(mode)
+            t = _time_launches(torch, lambda: p.vcycle_op_probe(mode), reps)
+            out.append(dict(kernel=VCYCLE_KERNELS[mode], launch_ms=t * 1e3, algorithmic_bytes=alg,
+                            launches_per_step=counts[mode] / float(steps)))
+    x = p.new_vector(p.N, 1.0)
+    y = p.new_vector(p.N)
+    t = _time_launches(torch, lambda: p.spmv(0, es.vals, x, out=y), reps)
+    out.append(dict(kernel='femo::k_spmv<double> (CSR-stream SpMV of the CG recurrence, fine-level Jacobian)',
+                    launch_ms=t * 1e3, algorithmic_bytes=12 * es.nnz + 20 * p.N,
+                    launches_per_step=es.info.get('krylov_its', 0) + es.info.get('adjoint_its', 0) + 5.0))
+    return out
 
 
 # ---------------------------------------------------------------------------
@@ -260,38 +311,33 @@ class ApiStep:
 
 
 # ---------------------------------------------------------------------------
-# CPU reference arm: the oracle's direct-solve path on a bounded sample
+# CPU arm: oracle/cpu_path.cpp, the C++/OpenMP restatement of the same step with the same GMG-PCG algorithm
+# (the reference's dolfinx + MUMPS path is not installable offline), on all host cores, at the FULL workload size
 # ---------------------------------------------------------------------------
-def cpu_step(n_sample):
-    import numpy as np
-    from oracle import mesh as om, families as fam, assembly as asm, solvers
-    key = ('cpu', n_sample)
-    if key not in _CACHE:
-        m = om.unit_square_tri(n_sample)
-        F = fam.NonlinearPoissonP1(m)
-        _CACHE[key] = (F, solvers.StatePath(F, None))
-    F, sp = _CACHE[key]
-    f = np.full(F.M, 0.1)
+def cpu_step(n):
+    from oracle import cpu_path
     t = time.perf_counter()
-    u, _ = sp.solve_snes(np.zeros(F.N), [f])
-    J = asm.assemble_scalar(F.output(0, u, f))
-    g, _ = sp.total_derivative(0, u, [f])
-    return time.perf_counter() - t, J
+    r = cpu_path.step(n, 0.1, krylov_rtol=KRYLOV_RTOL)
+    dt = time.perf_counter() - t
+    if not r['converged']:
+        raise RuntimeError('cpu_path: SNES / Krylov did not converge')
+    return dt, r
 
 
-_CACHE = {}
-
-
-def cpu_baseline(n, n_sample=256, steps=1):
-    """Oracle port (numpy assembly + SuperLU, single thread) on an n_sample mesh,
-    scaled to the n-mesh LINEARLY in dofs (generous to the CPU: sparse LU is
-    superlinear).  solves/s on the full workload = (1/t) * dofs_sample/dofs_full."""
-    ts = [cpu_step(n_sample)[0] for _ in range(steps)]
+def cpu_baseline(n, steps=1):
+    """One warm-up (page faults of the persistent workspace) + `steps` timed state+adjoint solves at the full size."""
+    cpu_step(n)
+    ts = []
+    for _ in range(steps):
+        dt, r = cpu_step(n)
+        ts.append(dt)
     t = sum(ts) / len(ts)
-    scale = (n_sample + 1) ** 2 / float((n + 1) ** 2)
-    return dict(value=scale / t, unit=UNIT, cores=1, kind='port',
-                sample='oracle (numpy assembly + SuperLU direct solves) on an n=%d mesh (%d dofs): %.2f s per '
-                       'state+adjoint solve, scaled linearly in dofs to n=%d' % (n_sample, (n_sample + 1) ** 2, t, n))
+    return dict(value=1.0 / t, unit=UNIT, cores=r['threads'], kind='port',
+                sample='oracle/cpu_path.cpp (C++/OpenMP, %d threads): %d full state+adjoint solve(s) at n=%d (%d dofs) after one '
+                       'warm-up, %.2f s each, same SNES + FMG/GMG-PCG algorithm and tolerances as the GPU arm (Newton its %d, '
+                       'Krylov its %d + %d), no extrapolation' % (r['threads'], steps, n, (n + 1) ** 2, t, r['newton_its'],
+                                                                   r['krylov_its'], r['adjoint_its']),
+                J=r['J'])
 
 
 # ---------------------------------------------------------------------------
@@ -324,22 +370,24 @@ def main():
     if a.impl == 'reference':
         if rank != 0:
             return 0
-        n_sample = 256
-        for _ in range(W):
-            cpu_step(n_sample)
+        # every step is one FULL state+adjoint solve of the metric's config on all host cores (about 12-18 s each);
+        # one warm-up is enough on a CPU (it only absorbs the page faults of the persistent workspace)
+        cpu_step(a.n)
         t0 = time.perf_counter()
         for _ in range(a.steps):
-            cpu_step(n_sample)
+            _, r = cpu_step(a.n)
         dt = (time.perf_counter() - t0) / a.steps
-        scale = (n_sample + 1) ** 2 / float((a.n + 1) ** 2)
-        val = scale / dt
-        sample = ('oracle direct-solve path (numpy assembly + SuperLU; the reference runs dolfinx + MUMPS, not '
-                  'installable offline) on an n=%d mesh (%d dofs), %.2f s per state+adjoint solve, scaled linearly '
-                  'in dofs to n=%d' % (n_sample, (n_sample + 1) ** 2, dt, a.n))
-        print(json.dumps(dict(metric=METRIC, value=val, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=W,
+        val = 1.0 / dt
+        sample = ('oracle/cpu_path.cpp: C++/OpenMP restatement of the reference path (the reference itself needs dolfinx + '
+                  'PETSc/MUMPS, not installable offline) with the GPU arm\'s algorithm (SNES + FMG/GMG-PCG rtol %g) on %d host '
+                  'threads; every step is a full n=%d solve (%d dofs), %.2f s per state+adjoint solve, 1 warm-up, no '
+                  'extrapolation; J=%.13g, Newton its %d, Krylov its %d + %d'
+                  % (KRYLOV_RTOL, r['threads'], a.n, (a.n + 1) ** 2, dt, r['J'], r['newton_its'], r['krylov_its'], r['adjoint_its']))
+        print(json.dumps(dict(metric=METRIC, value=val, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=1,
                               ms_per_step=1e3 / val, higher_is_better=True, scaling='weak', vs_baseline=None,
-                              dtype='f64', data='synthetic', config=workload(a.n), impl='reference',
-                              cpu_baseline=dict(value=val, unit=UNIT, cores=1, kind='port', sample=sample),
+                              dtype='f64', data='synthetic', config=dict(workload(a.n), parallelism='%d host threads' % r['threads']),
+                              impl='reference',
+                              cpu_baseline=dict(value=val, unit=UNIT, cores=r['threads'], kind='port', sample=sample),
                               e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return 0
 
@@ -368,6 +416,8 @@ def main():
     barrier()
     sampler.start()
     l0 = es.p.launch_count()
+    has_dia = a.workload == 'p1' and not os.environ.get('FEMO_NO_DIA')
+    c0 = [es.p.vcycle_op_probe(m)[1] for m in range(4)] if has_dia else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -376,9 +426,13 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = es.p.launch_count() - l0
-    t_spmv = time_spmv(es)
+    launches = es.p.launch_count() - l0 - (4 if has_dia else 0)
+    counts = [es.p.vcycle_op_probe(m)[1] - c0[m] - 1 for m in range(4)] if has_dia else None
     clocks = sampler.stop()
+    kernels = time_kernels(es, counts, a.steps)
+    step_info = dict(es.info)
+    check = verify(es) if (a.workload == 'p1' and world == 1) else None
+    es.info = step_info
     tt = torch.tensor([ms], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -457,28 +511,51 @@ def main():
         if os.path.exists(pk):
             peaks = json.load(open(pk))
         peak = float(peaks.get('hbm_gbs', 6650.0))
-        nnz, N = es.nnz, (es.p.N if es.p is not None else es_N)
-        alg = 12.0 * nnz + 20.0 * N
-        ach = alg / t_spmv / 1e9
+        # roofline of the instantiation with the largest share of the step (launches x duration, measured live)
+        step_ms = ms / a.steps
+        traffic = {}
+        tp = os.path.join(ROOT, 'profiles', 'r02_kernel_traffic.json')
+        if os.path.exists(tp) and a.workload == 'p1' and a.n == 4000 and world == 1:
+            traffic = json.load(open(tp))
+        for k in kernels:
+            k['achieved_gbs'] = k['algorithmic_bytes'] / (k['launch_ms'] * 1e-3) / 1e9
+            k['frac'] = k['achieved_gbs'] / peak
+            k['share_of_step'] = k['launches_per_step'] * k['launch_ms'] / step_ms
+            k['traffic'] = traffic.get(k['kernel'].split(' ')[0])
+        dom = max(kernels, key=lambda k: k['share_of_step'])
+        cfg = workload(a.n, a.workload)
+        if world > 1:
+            cfg['workload'] = ('weak-scaled %s: %d dofs over %d GPUs (the N=1 workload has %d)'
+                               % (cfg['workload'].split(' n=')[0] if a.workload == 'p1' else cfg['workload'].split(' (')[0],
+                                  es.global_dofs, world, base_dofs))
+            cfg['dofs'] = es.global_dofs
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=W,
                    ms_per_step=ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
-                   data='synthetic', config=dict(workload(a.n, a.workload), parallelism='1 GPU' if world == 1 else
+                   data='synthetic', config=dict(cfg, parallelism='1 GPU' if world == 1 else
                                                  (('one cantilever of %d x %d x %d cells (%d dofs), z-slab partition '
                                                    % (a.n, a.n // 2, a.n // 4 * world, es.global_dofs)) if a.workload == 'hex' else
                                                   ('one problem on [0,1]x[0,%d], %d x %d cells (%d dofs), y-slab partition '
                                                    % (world, N_DIST, N_DIST * world, es.global_dofs))) +
-                                                 ('with one-cell ghost layer over %d GPUs, NCCL halo exchange + all-reduce, '
+                                                 ('with one-cell ghost layer over %d GPUs, halo exchange + all-reduce, '
                                                   'partitioned multigrid; value = solves/s x dofs/dofs(N=1 workload)' % world)),
                    clocks=clocks, gpu_launches=int(launches), e2e=e2e,
-                   roofline=dict(bound='hbm', kernel='femo::k_spmv (CSR-stream SpMV, fine-level Jacobian)',
-                                 achieved=ach, peak=peak, unit='GB/s', frac=ach / peak,
-                                 traffic=1.652e9 if (a.workload == 'p1' and a.n == 4000 and world == 1) else None,
-                                 traffic_source='profiles/r01_summary.md: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch',
-                                 algorithmic_bytes=alg, launch_ms=t_spmv * 1e3,
-                                 peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 (of fallback)'),
-                   step_info=es.info)
+                   roofline=dict(bound='hbm', kernel=dom['kernel'], achieved=dom['achieved_gbs'], peak=peak, unit='GB/s',
+                                 frac=dom['frac'], traffic=dom['traffic'],
+                                 traffic_source='profiles/r02_summary.md: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch',
+                                 algorithmic_bytes=dom['algorithmic_bytes'], launch_ms=dom['launch_ms'],
+                                 share_of_step=dom['share_of_step'],
+                                 peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 (of fallback)',
+                                 kernels=kernels),
+                   step_info=dict(es.info, verify=check))
+        if check is not None and not check['ok']:
+            out['error'] = 'verification failed: %r' % (check,)
         if not a.no_cpu:
             out['cpu_baseline'] = cpu_baseline(a.n)
+            # same workload, two independent implementations: the functional must agree
+            Jc, Jg = out['cpu_baseline']['J'], es.info.get('J')
+            out['step_info']['J_cpu_port'] = Jc
+            if Jg is not None and abs(Jg - Jc) > 1e-9 * abs(Jc):
+                out['error'] = 'GPU and CPU-port functionals differ: %r vs %r' % (Jg, Jc)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

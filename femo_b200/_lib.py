@@ -70,6 +70,9 @@ SIGNATURES = {
     'femo_comm_unique_id': (C.c_int, [C.c_char_p]),
     'femo_comm_init': (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int]),
     'femo_comm_finalize': (C.c_int, []),
+    'femo_link_create': (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, C.c_char_p]),
+    'femo_link_open': (C.c_int, [C.c_char_p, C.c_int, C.c_int]),
+    'femo_link_error': (C.c_int, []),
     'femo_comm_stats': (C.c_int, [C.POINTER(C.c_longlong)]),
     'femo_problem_create_slab': (C.c_int, [C.c_int, _DP, C.c_int, C.c_int, C.c_int, _DP, _DP, C.c_int, C.c_int, C.POINTER(_P)]),
     'femo_problem_create_slab_hex': (C.c_int, [C.c_int, _DP, C.c_int, C.c_int, C.c_int, C.c_int, _DP, _DP, C.c_int, C.c_int,
@@ -91,6 +94,7 @@ SIGNATURES = {
     'femo_assemble_system_rhs': (C.c_int, [_P, _P, _P]),
     'femo_assemble_output': (C.c_int, [_P, C.c_int, _DP]),
     'femo_assemble_output_grad': (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    'femo_assemble_output_and_grad': (C.c_int, [_P, C.c_int, _DP, _P]),
     'femo_spmv': (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int]),
     'femo_axpy': (C.c_int, [_P, C.c_double, _P, _P, C.c_int64]),
     'femo_filter_apply': (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, _P, C.c_int]),

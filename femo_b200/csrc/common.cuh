@@ -56,7 +56,8 @@ __device__ __forceinline__ double block_sum(double v) {
 // keep L1/L2 for the gathered vector instead
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int32_t ld_stream(const int32_t *p) { return __ldcs(p); }
-__device__ __forceinline__ double ld_stream(const float *p) { return (double)__ldcs(p); }
+__device__ __forceinline__ double f2d(float f) { return (double)f; }
+__device__ __forceinline__ double ld_stream(const float *p) { return f2d(__ldcs(p)); }
 
 // y-slab of a global lattice owned by this rank: global cell rows [crow0, crow0+ncrows) are local,
 // local node row j is global row crow0 + j; node / cell rows [own0,own1) / [cown0,cown1) are owned
@@ -93,7 +94,8 @@ struct Arena {
     static size_t need(size_t count, size_t elem) { return (count * elem + 255) & ~size_t(255); }
 };
 
-// DIA (diagonal) storage of a lattice operator: nd planes of np fp32 values, plane s holds a(i, i + off[s])
+// DIA (diagonal) storage of a lattice operator: nd planes of np fp32 values, plane s holds a(i, i + off[s]);
+// plane nd holds the Jacobi scaling (float)(1 / a_ii) used by every smoother step
 constexpr int kDiaMax = 9;
 struct DiaMat {
     const float *v = nullptr;
@@ -124,6 +126,35 @@ struct femo_mg_level {
     bool dia_valid = false;                         // they alias the vals32 buffer
 };
 
+namespace femo {
+// ops of the cooperative coarse V-cycle kernel (mgfused.cuh)
+enum MgOpType {
+    MGO_PRE2 = 0,       // x = fused zero-guess degree-2 Chebyshev smoother of b
+    MGO_RESID = 1,      // y = b - A x
+    MGO_RESTRICT = 2,   // coarse b = P^T r          (nested 2:1 or general lattices)
+    MGO_DENSE = 3,      // x = Inv b                 (coarsest level)
+    MGO_PROLONG = 4,    // x += P xc
+    MGO_CHEB0 = 5,      // r = b - A x ; d = c1 r / a_ii
+    MGO_CHEBK = 6       // r' = r - A d ; x += d + c1 d + c2 r' / a_ii     (last step: r', d' not stored)
+};
+
+struct MgOp {
+    int type = 0, nested = 0, n = 0, pad = 0;
+    DiaMat A;
+    const double *b = nullptr, *x = nullptr, *src = nullptr, *inv = nullptr;
+    double *y = nullptr, *r = nullptr, *d = nullptr, *dst = nullptr;
+    const uint8_t *mask_f = nullptr, *mask_c = nullptr;
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    int fnx = 0, fny = 0, cnx = 0, cny = 0;     // fine / coarse lattice of a transfer
+};
+
+}  // namespace femo
+// program of the cooperative coarse V-cycle kernel (mgfused.cuh): levels [k0, nlev-1] in one launch
+struct MgFusedProg {
+    bool valid = false, dirty = true;
+    int k0 = 0, nops = 0, nlev = 0;
+};
+
 struct femo_problem {
     femo::Mesh mesh;
     int family = 0;
@@ -136,6 +167,7 @@ struct femo_problem {
     int out_du_mask[4] = {1, 1, 1, 1};     // blocks of d(output k)/d(state); 0 = identically zero
     int out_dm_mask[4] = {1, 1, 1, 1};     // same wrt input 0
     bool symmetric = true;
+    bool lattice_fast = false;              // Jacobian rows assembled node-centrically on the lattice (lattice_asm.cuh)
     std::vector<int32_t> fb_cell, fb_local;   // the facets of block 2 (all exterior, or the tagged subset)
     std::vector<femo::IntegralBlock> blk[4];
     femo::Pattern pat[5];
@@ -192,6 +224,9 @@ struct femo_problem {
     double *d_partials_big = nullptr, *wk_extra = nullptr; // multi-dot partials; spare N-vector
     int gm_restart = 0;
     // counters (bench: how many of our kernels were launched)
+    MgFusedProg mgprog;
+    femo::MgOp *d_mgops = nullptr;
+    std::vector<femo::MgOp> h_mgops;
     long long launches = 0;
     long long dia_count[4] = {0, 0, 0, 0};   // launches of the DIA operator kernel on this level, by mode
 };

@@ -2,8 +2,54 @@
 // All calls enqueue on the problem's stream; nothing synchronises the host.
 #pragma once
 #include "dist.cuh"
+#include "link.cuh"
 
 using namespace femo;
+
+// ---- peer-memory transport (link.cuh) ------------------------------------------------------------------------
+static inline int link_chunks(size_t len) {
+    const size_t c = (len + 2047) / 2048;
+    return (int)std::max<size_t>(1, std::min<size_t>(c, kLinkMaxChunks));
+}
+
+// symmetric exchange of slab rows of T: send [send_lo, +len_lo_s) down / [send_hi, +len_hi_s) up, receive into
+// [recv_lo, ...) from below / [recv_hi, ...) from above (lengths in elements of T; zero-length directions still flag)
+template <class T>
+static int link_halo(femo_problem *p, T *v, size_t send_lo, size_t recv_lo, size_t send_hi, size_t recv_hi, size_t slen_lo,
+                     size_t rlen_lo, size_t slen_hi, size_t rlen_hi) {
+    const size_t mx = std::max(std::max(slen_lo, rlen_lo), std::max(slen_hi, rlen_hi));
+    if (mx * sizeof(T) > g_link.lay.halo_cap * sizeof(double))
+        return set_err(FEMO_ELIMIT, "halo row exceeds the link window (femo_link_create halo capacity)");
+    const int nch = link_chunks(mx);
+    const unsigned long long seq = ++g_link.seq;
+    k_link_halo<T><<<2 * nch, kThreads, 0, p->stream>>>(g_link.dev(), v, send_lo, recv_lo, send_hi, recv_hi, slen_lo, rlen_lo,
+                                                         slen_hi, rlen_hi, nch, seq);
+    p->launches++;
+    g_comm.halo_exchanges++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
+static int link_allreduce(femo_problem *p, double *scalars, int count, bool is_max) {
+    if (count > kLinkArMax) return set_err(FEMO_ELIMIT, "all-reduce of more than 16 scalars");
+    const unsigned long long seq = ++g_link.seq;
+    k_link_allreduce<<<1, kThreads, 0, p->stream>>>(g_link.dev(), scalars, count, is_max ? 1 : 0, nullptr, nullptr, 0, 0, 0, seq);
+    p->launches++;
+    g_comm.allreduces++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
+static int link_gather(femo_problem *p, double *g, size_t blk, size_t tail) {
+    const size_t total = blk * g_link.nranks + tail;
+    if (total > g_link.lay.gather_cap) return set_err(FEMO_ELIMIT, "gathered level exceeds the link window (femo_link_create gather capacity)");
+    const unsigned long long seq = ++g_link.seq;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((blk + tail + kThreads - 1) / kThreads, 64));
+    k_link_gather<<<grid, kThreads, 0, p->stream>>>(g_link.dev(), g, blk, tail, seq);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
 
 // Refresh the ghost node rows of a state-space vector (ghostUpdate FORWARD of the reference,
 // utils_dolfinx.py:167): whole lattice rows are contiguous, so rows are sent in place.
@@ -15,6 +61,9 @@ static int halo_nodes(femo_problem *p, double *v) {
     }
     if (!s.active || !g_comm.active) return FEMO_OK;
     const size_t len = (size_t)(p->mesh.n[0] + 1) * (p->mesh.kind == MESH_HEX ? (size_t)(p->mesh.n[1] + 1) : 1) * p->state.block;
+    if (g_link.active)
+        return link_halo<double>(p, v, (size_t)s.own0 * len, (size_t)(s.own0 - 1) * len, (size_t)(s.own1 - 1) * len,
+                                 (size_t)s.own1 * len, len, len, len, len);
     NcclApi &a = g_comm.api;
     FEMO_NCCL(a.GroupStart());
     if (s.rank > 0) {
@@ -35,6 +84,9 @@ static int halo_nodes_f32(femo_problem *p, float *v) {
     const SlabInfo &s = p->slab;
     if (!s.active || !g_comm.active) return FEMO_OK;
     const size_t len = (size_t)(p->mesh.n[0] + 1) * (p->mesh.kind == MESH_HEX ? (size_t)(p->mesh.n[1] + 1) : 1) * p->state.block;
+    if (g_link.active)
+        return link_halo<float>(p, v, (size_t)s.own0 * len, (size_t)(s.own0 - 1) * len, (size_t)(s.own1 - 1) * len,
+                                (size_t)s.own1 * len, len, len, len, len);
     NcclApi &a = g_comm.api;
     FEMO_NCCL(a.GroupStart());
     if (s.rank > 0) {
@@ -55,6 +107,8 @@ static int halo_cells(femo_problem *p, double *v) {
     const SlabInfo &s = p->slab;
     if (!s.active || !g_comm.active) return FEMO_OK;
     const size_t len = (size_t)(p->mesh.ncells / s.ncrows) * p->in[0].block;   // cells per lattice row
+    if (g_link.active)     // cell rows travel upwards only; the downward direction exchanges flags (symmetry)
+        return link_halo<double>(p, v, 0, (size_t)(s.cown0 - 1) * len, (size_t)(s.cown1 - 1) * len, 0, 0, len, len, 0);
     NcclApi &a = g_comm.api;
     FEMO_NCCL(a.GroupStart());
     if (s.rank < s.nranks - 1)
@@ -69,6 +123,7 @@ static int halo_cells(femo_problem *p, double *v) {
 // Sum (or max) `count` device scalars starting at `slot` over all ranks, in place.
 static int allreduce_scalars(femo_problem *p, int slot, int count, bool is_max = false) {
     if (!g_comm.active || (!p->slab.active)) return FEMO_OK;
+    if (g_link.active) return link_allreduce(p, p->d_scalars + slot, count, is_max);
     FEMO_NCCL(g_comm.api.AllReduce(p->d_scalars + slot, p->d_scalars + slot, (size_t)count, ncclDouble,
                                    is_max ? ncclMax : ncclSum, g_comm.comm, p->stream));
     g_comm.allreduces++;
@@ -82,6 +137,7 @@ static int gather_rows(femo_problem *p, double *g, size_t len, int gny) {
     if (!g_comm.active) return FEMO_OK;
     const int R = g_comm.nranks, rows = gny / R;
     const size_t blk = (size_t)rows * len;
+    if (g_link.active) return link_gather(p, g, blk, len);       // the top row rides with the last rank's block
     FEMO_NCCL(g_comm.api.AllGather(g + (size_t)g_comm.rank * blk, g, blk, ncclDouble, g_comm.comm, p->stream));
     FEMO_NCCL(g_comm.api.Broadcast(g + (size_t)gny * len, g + (size_t)gny * len, len, ncclDouble, R - 1, g_comm.comm,
                                    p->stream));
@@ -92,6 +148,7 @@ static int gather_rows(femo_problem *p, double *g, size_t len, int gny) {
 static int gather_cell_rows(femo_problem *p, double *g, size_t len, int gn) {
     if (!g_comm.active) return FEMO_OK;
     const size_t blk = (size_t)(gn / g_comm.nranks) * len;
+    if (g_link.active) return link_gather(p, g, blk, 0);
     FEMO_NCCL(g_comm.api.AllGather(g + (size_t)g_comm.rank * blk, g, blk, ncclDouble, g_comm.comm, p->stream));
     return FEMO_OK;
 }

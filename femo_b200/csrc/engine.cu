@@ -13,6 +13,7 @@
 #include "families5.cuh"
 #include "families6.cuh"
 #include "families7.cuh"
+#include "lattice_asm.cuh"
 #include "dist.cuh"
 
 namespace femo {
@@ -762,6 +763,7 @@ static int set_bc_impl(femo_problem *p, const int32_t *dofs, const int32_t *list
 
 #include "stencil.cuh"
 #include "multigrid.cuh"
+#include "mgfused.cuh"
 #include "krylov.cuh"
 #include "gmres.cuh"
 
@@ -996,6 +998,8 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
                 p->fb_local.push_back(M.bf_local[tagged[k]]);
             }
         }
+        // node-centric Jacobian rows (lattice_asm.cuh): nonlinear Poisson P1 with Nitsche terms on ALL exterior facets
+        p->lattice_fast = family == FEMO_FAMILY_NLPOISSON_P1 && M.lattice && M.kind == MESH_TRI && !fcell && p->jac_mask == 3;
         p->own_off = 0;
         p->own_n = p->state.ndofs;
         p->cown_off = 0;
@@ -1544,7 +1548,8 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     w += 2 * Arena::need(p->pat[0].nnz, 8);        // Newton's Jacobian values (plain, BC'd)
     w += Arena::need(tv, 8);                       // transposed values
     w += Arena::need(N, 8);                        // Chebyshev direction of multigrid level 0
-    if (!p->mg.empty()) w += Arena::need(fp32_copy_len(p), 4);   // fp32 copy (CSR order or DIA planes) of the fine-level values for the V-cycle
+    if (!p->mg.empty()) w += Arena::need(fp32_copy_len(p), 4);   // fp32 copy (CSR order or DIA planes)
+    if (!p->mg.empty()) w += Arena::need(kMgFusedMaxOps, sizeof(MgOp));   // op list of the cooperative coarse V-cycle
     if (hex_matfree_level(p)) { s += Arena::need(576, 8); w += Arena::need((size_t)M.ncells, 8); }
     if (N <= kMgDenseMax) w += 2 * Arena::need((size_t)N * N, 8);   // explicit inverse (precond 3)
     if (!p->symmetric) w += (size_t)(kGmresRestart + 2) * Arena::need(N, 8) + Arena::need((size_t)(kGmresRestart + 1) * kMaxPartials, 8);
@@ -1738,6 +1743,7 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     p->d_tvals = p->wk.take<double>(tv);
     p->kr_d = p->wk.take<double>(N);
     if (!p->mg.empty()) p->mgl.vals32 = p->wk.take<float>(fp32_copy_len(p));
+    if (!p->mg.empty()) p->d_mgops = p->wk.take<MgOp>(kMgFusedMaxOps);
     if ((rc = setup_hex_matfree(p, p))) return rc;
     if (!p->symmetric) {
         p->gm_restart = kGmresRestart;
@@ -1802,7 +1808,71 @@ int femo_comm_init(const char id[128], int rank, int nranks, int device) {
     return FEMO_OK;
 }
 
+/* peer-memory transport (link.cuh): every rank creates its window and publishes the 64-byte IPC handle ... */
+int femo_link_create(int device, size_t halo_cap, size_t gather_cap, char handle[64]) {
+    if (!handle) return set_err(FEMO_EINVAL, "femo_link_create: null handle");
+    if (femo_device_count() <= device || device < 0) return set_err(FEMO_ENODEVICE, "femo_link_create: no such CUDA device");
+    if (g_link.local) return set_err(FEMO_ESTATE, "femo_link_create: window already created");
+    FEMO_CUDA(cudaSetDevice(device));
+    g_link.lay.halo_cap = halo_cap ? halo_cap : ((size_t)1 << 20);
+    g_link.lay.gather_cap = gather_cap ? gather_cap : ((size_t)1 << 22);
+    const size_t bytes = g_link.lay.bytes();
+    FEMO_CUDA(cudaMalloc((void **)&g_link.local, bytes));
+    FEMO_CUDA(cudaMemset(g_link.local, 0, bytes));
+    FEMO_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    FEMO_CUDA(cudaIpcGetMemHandle(&h, g_link.local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    memcpy(handle, &h, 64);
+    g_link.device = device;
+    return FEMO_OK;
+}
+
+/* ... and maps the windows of all ranks (handles = nranks x 64 bytes, rank-major; the own entry is not opened). */
+int femo_link_open(const char *handles, int rank, int nranks) {
+    if (!handles || nranks < 1 || nranks > kLinkMaxRanks || rank < 0 || rank >= nranks)
+        return set_err(FEMO_EINVAL, "femo_link_open: bad arguments (at most 16 ranks)");
+    if (!g_link.local) return set_err(FEMO_ESTATE, "femo_link_open: call femo_link_create first");
+    if (g_comm.active) return set_err(FEMO_ESTATE, "femo_link_open: a communicator is already active");
+    FEMO_CUDA(cudaSetDevice(g_link.device));
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            g_link.win[r] = g_link.local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)r, 64);
+        void *ptr = nullptr;
+        FEMO_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        g_link.win[r] = (char *)ptr;
+    }
+    g_link.rank = rank;
+    g_link.nranks = nranks;
+    g_link.seq = 0;
+    g_link.active = nranks > 1;
+    g_comm.rank = rank;
+    g_comm.nranks = nranks;
+    g_comm.active = nranks > 1;
+    return FEMO_OK;
+}
+
+/* 1 when a spin of the transport timed out since the window was created (the results after that are invalid) */
+int femo_link_error(void) {
+    if (!g_link.local) return 0;
+    int e = 0;
+    if (cudaMemcpy(&e, g_link.local + LinkLayout::kErr, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    return e;
+}
+
 int femo_comm_finalize(void) {
+    if (g_link.local) {
+        cudaSetDevice(g_link.device);
+        cudaDeviceSynchronize();
+        for (int r = 0; r < g_link.nranks; ++r)
+            if (r != g_link.rank && g_link.win[r]) cudaIpcCloseMemHandle(g_link.win[r]);
+        cudaFree(g_link.local);
+        g_link = Link();
+    }
     if (g_comm.comm) {
         g_comm.api.CommDestroy(g_comm.comm);
         g_comm.comm = nullptr;
@@ -1848,6 +1918,20 @@ int femo_assemble_jacobian(femo_problem *p, double *d_vals, double *d_vals_bc) {
         k_segreduce_jac_k0<<<grid_for(nnz), kThreads, 0, p->stream>>>(D.gptr, D.gsrc, p->mgl.k0, p->mgl.ec, (uint32_t)nc, D.bcflag,
                                                                       D.col, p->d_bc_diag, d_vals, d_vals_bc, nnz);
         p->launches += 2;
+        FEMO_CHECK_LAUNCH();
+        return FEMO_OK;
+    }
+    if (p->lattice_fast && !getenv("FEMO_NO_LATTICE_ASM")) {   // right-diagonal lattice: node-centric rows, no scratch round trip
+        if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
+        LatJacArgs A;
+        A.T = tri_args(p, nullptr);
+        A.nx = p->mesh.n[0]; A.ny = p->mesh.n[1];
+        A.ext_bottom = !p->slab.active || p->slab.rank == 0;
+        A.ext_top = !p->slab.active || p->slab.rank == p->slab.nranks - 1;
+        A.rowptr = D.rowptr; A.col = D.col; A.bcflag = D.bcflag; A.bc_diag = p->d_bc_diag;
+        A.out = d_vals; A.out_bc = d_vals_bc;
+        k_nlpoisson_p1_node_jac<<<grid_for(p->state.ndofs), kThreads, 0, p->stream>>>(A);
+        p->launches++;
         FEMO_CHECK_LAUNCH();
         return FEMO_OK;
     }
@@ -1945,6 +2029,36 @@ int femo_assemble_output_grad(femo_problem *p, int out_id, int slot, double *d_o
     }
     if ((rc = run_elements(p, OP_OUT_DM, mask, out_id))) return rc;
     return segreduce(p, p->dvm_in[slot - 1], n, d_out);
+}
+
+/* OutputOperation.compute + compute_derivatives wrt the state (output_model.py:69-87) in ONE quadrature pass:
+ * functional value and dJ/du share every evaluation point, so the fused pass halves the most expensive element
+ * kernel of the nonlinear Poisson family (49-point rule, analytic u_ex).  Other families run the two passes. */
+int femo_assemble_output_and_grad(femo_problem *p, int out_id, double *h_value, double *d_dJdu) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (out_id < 0 || out_id >= p->nout || !h_value || !d_dJdu) return set_err(FEMO_EINVAL, "femo_assemble_output_and_grad: bad arguments");
+    if (p->family != FEMO_FAMILY_NLPOISSON_P1 || p->out_mask[out_id] != 1 || p->out_du_mask[out_id] != 1) {
+        if ((rc = femo_assemble_output(p, out_id, h_value))) return rc;
+        return femo_assemble_output_grad(p, out_id, 0, d_dJdu);
+    }
+    if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
+    if ((rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
+    const int64_t nc = p->mesh.ncells;
+    if ((size_t)(4 * nc) > p->scratch_len) return set_err(FEMO_ESTATE, "scratch too small for the fused functional pass");
+    TriArgs A = tri_args(p, p->d_scratch);
+    k_nlpoisson_p1_cell<OP_OUT_BOTH><<<grid_for(nc), kThreads, 0, p->stream>>>(A);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    if ((rc = segreduce(p, p->dvm_state[1], p->state.ndofs, d_dJdu))) return rc;
+    const double *src = p->d_scratch + 3 * nc + (p->slab.active ? p->cown_off : 0);
+    const int64_t cnt = p->slab.active ? p->cown_n : nc;
+    const int g = red_grid(p, cnt);
+    k_sum<<<g, kThreads, 0, p->stream>>>(src, cnt, p->d_partials);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    if ((rc = reduce_to(p, p->d_partials, nullptr, g, S_TMP1, 0))) return rc;
+    return read_scalars(p, S_TMP1, 1, h_value);
 }
 
 // ---- linear algebra -------------------------------------------------------

@@ -87,7 +87,8 @@ __device__ __forceinline__ double uex_q(const UexCell &U, int q, double x, doubl
     return uex_nlp(x, y);
 }
 
-enum CellOp { OP_RES = 0, OP_JAC = 1, OP_DRDM = 2, OP_OUT = 3, OP_OUT_DU = 4, OP_OUT_DM = 5 };
+enum CellOp { OP_RES = 0, OP_JAC = 1, OP_DRDM = 2, OP_OUT = 3, OP_OUT_DU = 4, OP_OUT_DM = 5,
+              OP_OUT_BOTH = 6 /* functional (plane 3) and its state gradient (planes 0-2) in one quadrature pass */ };
 
 // ---------------------------------------------------------------------------
 // family 1: Poisson, P1 state, DG0 source  (examples/poisson_opt/run_poisson_opt.py)
@@ -228,10 +229,11 @@ __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_cell(TriArgs A) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) ge[a] += w * eq * ph[a];
         }
-        if (OP == OP_OUT) {
+        if (OP == OP_OUT || OP == OP_OUT_BOTH) {
             const double f = A.f[c];
-            A.out[c] = val + 0.5 * T.a2 * 0.5 * A.alpha * f * f;
-        } else {
+            A.out[(OP == OP_OUT_BOTH ? 3 * ne : 0) + c] = val + 0.5 * T.a2 * 0.5 * A.alpha * f * f;
+        }
+        if (OP == OP_OUT_DU || OP == OP_OUT_BOTH) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) A.out[a * ne + c] = ge[a];
         }

@@ -1,0 +1,123 @@
+// lattice_asm.cuh -- node-centric Jacobian assembly on right-diagonal triangle lattices.
+//
+// The general path (families.cuh + the sorted segmented reduction of engine.cu) writes every element matrix to
+// scratch planes and gathers them through an index map: 8*9 bytes per cell out, the same back in, plus 4 bytes of map
+// per contribution -- 4.8 GB for the 16M-dof benchmark Jacobian (1.45 ms + 0.62 ms).  On a lattice the cells around a
+// node and the node's local index in each of them are index arithmetic, so one thread per node evaluates the ROWS it
+// owns of its <= 6 incident element matrices (and of the Nitsche facet matrices of boundary triangles) and writes the
+// <= 7 CSR values of its row directly: no scratch, no map, u and f read once through the cache.  The total flop count
+// equals the cell-centric kernel's (every element row is computed exactly once).  Values agree with the general path to
+// round-off (different, but fixed, summation order => still bit-reproducible run to run); both are tested against the
+// oracle at 1e-12.  Replaces assemble_matrix(form(J)) of the reference (femo/fea/utils_dolfinx.py:181-202) for
+// examples/nonlinear_poisson_opt/run_nonlinear_poisson_opt.py:88-116.
+#pragma once
+#include "families.cuh"
+
+namespace femo {
+
+struct LatJacArgs {
+    TriArgs T;
+    int nx, ny;                 // local lattice (cells)
+    int ext_bottom, ext_top;    // whether local rows 0 / ny are true domain boundaries (slabs: only on the end ranks)
+    const int32_t *rowptr, *col;
+    const uint8_t *bcflag;
+    const double *bc_diag;
+    double *out, *out_bc;
+};
+
+// row a of the cell matrix  int grad(phi_a).grad(phi_b) + 3 u^2 phi_a phi_b dx  (degree-4 rule, as k_nlpoisson_p1_cell<OP_JAC>)
+__device__ __forceinline__ void nlp_cell_jac_row(const Tri &T, const double u[3], int a, double row[3]) {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) row[b] = 0.5 * T.a2 * (T.g[a][0] * T.g[b][0] + T.g[a][1] * T.g[b][1]);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const double ph[3] = {1.0 - c_tri6[q][0] - c_tri6[q][1], c_tri6[q][0], c_tri6[q][1]};
+        const double uq = u[0] * ph[0] + u[1] * ph[1] + u[2] * ph[2];
+        const double s = c_tri6[q][2] * T.a2 * 3.0 * uq * uq * ph[a];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) row[b] += s * ph[b];
+    }
+}
+
+// row a of the symmetric-Nitsche matrix of exterior facet l (opposite local vertex l), as k_nlpoisson_p1_facet<OP_JAC>
+__device__ __forceinline__ void nlp_facet_jac_row(const Tri &T, int l, double beta, int a, double row[3]) {
+    const int la = (l == 0) ? 1 : 0, lb = (l == 2) ? 1 : 2;
+    const double tx = T.X[lb][0] - T.X[la][0], ty = T.X[lb][1] - T.X[la][1];
+    const double len = sqrt(tx * tx + ty * ty);
+    double nx = ty / len, ny = -tx / len;
+    if (nx * (T.X[la][0] - T.X[l][0]) + ny * (T.X[la][1] - T.X[l][1]) < 0.0) { nx = -nx; ny = -ny; }
+    double h2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int d = (c + 1) % 3;
+        const double dx = T.X[c][0] - T.X[d][0], dy = T.X[c][1] - T.X[d][1];
+        h2 = fmax(h2, dx * dx + dy * dy);
+    }
+    const double bh = beta / sqrt(h2);
+    double gn[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gn[c] = T.g[c][0] * nx + T.g[c][1] * ny;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const double s = c_gl5[q][0], w = c_gl5[q][1] * len;
+        double ph[3] = {0.0, 0.0, 0.0};
+        ph[la] = 1.0 - s;
+        ph[lb] = s;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) row[b] += w * (-ph[a] * gn[b] - gn[a] * ph[b] + bh * ph[a] * ph[b]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A) {
+    const int w = A.nx + 1;
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= (int64_t)w * (A.ny + 1)) return;
+    const int i = (int)(r % w), j = (int)(r / w);
+    double v[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};      // slots of offsets {-w-1, -w, -1, 0, 1, w, w+1}
+    // incident triangles: (cell dx, cell dy, upper?, local index of this node)
+    const int tri[6][4] = {{0, 0, 0, 0}, {0, 0, 1, 0}, {-1, 0, 0, 1}, {0, -1, 1, 1}, {-1, -1, 0, 2}, {-1, -1, 1, 2}};
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+        const int ci = i + tri[t][0], cj = j + tri[t][1], up = tri[t][2], a = tri[t][3];
+        if (ci < 0 || cj < 0 || ci >= A.nx || cj >= A.ny) continue;
+        Tri T;
+        tri_load(A.T, 2 * ((int64_t)cj * A.nx + ci) + up, T);
+        double u[3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) u[b] = __ldg(A.T.u + T.v[b]);
+        double row[3];
+        nlp_cell_jac_row(T, u, a, row);
+        // exterior facets of this triangle: lower: l = 2 (edge v0-v1, bottom), l = 0 (edge v1-v3, right);
+        //                                   upper: l = 2 (edge v0-v2, left),   l = 0 (edge v2-v3, top)
+        if (!up) {
+            if (cj == 0 && A.ext_bottom) nlp_facet_jac_row(T, 2, A.T.beta, a, row);
+            if (ci == A.nx - 1) nlp_facet_jac_row(T, 0, A.T.beta, a, row);
+        } else {
+            if (ci == 0) nlp_facet_jac_row(T, 2, A.T.beta, a, row);
+            if (cj == A.ny - 1 && A.ext_top) nlp_facet_jac_row(T, 0, A.T.beta, a, row);
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const int d = T.v[b] - (int)r;
+            const int s = d == 0 ? 3 : d == 1 ? 4 : d == -1 ? 2 : d == w ? 5 : d == w + 1 ? 6 : d == -w ? 1 : 0;
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+                if (k == s) v[k] += row[b];
+        }
+    }
+    // CSR positions: the row holds the slots whose neighbour exists on the local lattice, in ascending column order
+    const bool present[7] = {i > 0 && j > 0, j > 0, i > 0, true, i < A.nx, j < A.ny, i < A.nx && j < A.ny};
+    int32_t pos = A.rowptr[r];
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+        if (!present[s]) continue;
+        if (A.out) A.out[pos] = v[s];
+        if (A.out_bc) {
+            const uint8_t fl = A.bcflag ? A.bcflag[pos] : 0;
+            A.out_bc[pos] = (fl == 0) ? v[s] : (fl == 1 ? 0.0 : A.bc_diag[A.col[pos]]);
+        }
+        ++pos;
+    }
+}
+
+}  // namespace femo

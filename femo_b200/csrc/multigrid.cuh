@@ -39,15 +39,16 @@ __device__ __forceinline__ double hat_q1(double dx, double dy) {
 }
 __device__ __forceinline__ double hat_of(int kind, double dx, double dy) { return kind ? hat_q1(dx, dy) : hat_p1(dx, dy); }
 
+// vector loads of the transfer bodies: CG = true reads through L2 only (ld.global.cg) -- used by the fused cooperative
+// V-cycle kernel, where the vector was written earlier in the SAME kernel by other SMs
+template <bool CG>
+__device__ __forceinline__ double ldv(const double *p) { return CG ? __ldcg(p) : *p; }
+
 // dst(dof) (+)= sum_k phi^src_k(x_node) src(k): prolongation (src = coarse) and state interpolation
-// (src = fine) share this kernel.  `block` interleaved components per node, hat 0 = P1 right-diagonal, 1 = Q1.
-template <bool ADD>
-__global__ void __launch_bounds__(kThreads)
-    k_lattice_interp(Lattice s, Lattice d, int block, int hat, const double *__restrict__ src, double *__restrict__ dst,
-                     const uint8_t *__restrict__ dst_mask) {
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t nd = (int64_t)(d.nx + 1) * (d.ny + 1) * block;
-    if (idx >= nd) return;
+// (src = fine) share this body.  `block` interleaved components per node, hat 0 = P1 right-diagonal, 1 = Q1.
+template <bool ADD, bool CG = false>
+__device__ __forceinline__ void lattice_interp_at(Lattice s, Lattice d, int block, int hat, const double *src, double *dst,
+                                                  const uint8_t *dst_mask, int64_t idx) {
     if (dst_mask && dst_mask[idx]) {
         if (!ADD) dst[idx] = 0.0;
         return;
@@ -63,19 +64,26 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             const double w = hat_of(hat, X - (double)(I + a), Y - (double)(J + b));
-            if (w > 0.0) acc += w * src[((int64_t)(J + b) * (s.nx + 1) + (I + a)) * block + comp];
+            if (w > 0.0) acc += w * ldv<CG>(src + ((int64_t)(J + b) * (s.nx + 1) + (I + a)) * block + comp);
         }
-    if (ADD) dst[idx] += acc;
+    if (ADD) dst[idx] = ldv<CG>(dst + idx) + acc;
     else dst[idx] = acc;
 }
 
-// rc = P^T rf with the same weights as k_lattice_interp<coarse -> fine>
+template <bool ADD>
 __global__ void __launch_bounds__(kThreads)
-    k_lattice_restrict(Lattice f, Lattice c, int block, int hat, const double *__restrict__ rf, double *__restrict__ rc,
-                       const uint8_t *__restrict__ mask_f, const uint8_t *__restrict__ mask_c) {
+    k_lattice_interp(Lattice s, Lattice d, int block, int hat, const double *__restrict__ src, double *__restrict__ dst,
+                     const uint8_t *__restrict__ dst_mask) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t nc = (int64_t)(c.nx + 1) * (c.ny + 1) * block;
-    if (idx >= nc) return;
+    const int64_t nd = (int64_t)(d.nx + 1) * (d.ny + 1) * block;
+    if (idx >= nd) return;
+    lattice_interp_at<ADD>(s, d, block, hat, src, dst, dst_mask, idx);
+}
+
+// rc = P^T rf with the same weights as lattice_interp_at<coarse -> fine>
+template <bool CG = false>
+__device__ __forceinline__ void lattice_restrict_at(Lattice f, Lattice c, int block, int hat, const double *rf, double *rc,
+                                                    const uint8_t *mask_f, const uint8_t *mask_c, int64_t idx) {
     if (mask_c && mask_c[idx]) {
         rc[idx] = 0.0;
         return;
@@ -95,9 +103,18 @@ __global__ void __launch_bounds__(kThreads)
             if (I < I0 || I > I0 + 1 || J < J0 || J > J0 + 1) continue;
             const double w = hat_of(hat, X - (double)I, Y - (double)J);
             const int64_t fi = ((int64_t)j * (f.nx + 1) + i) * block + comp;
-            if (w > 0.0 && !(mask_f && mask_f[fi])) acc += w * rf[fi];
+            if (w > 0.0 && !(mask_f && mask_f[fi])) acc += w * ldv<CG>(rf + fi);
         }
     rc[idx] = acc;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_lattice_restrict(Lattice f, Lattice c, int block, int hat, const double *__restrict__ rf, double *__restrict__ rc,
+                       const uint8_t *__restrict__ mask_f, const uint8_t *__restrict__ mask_c) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nc = (int64_t)(c.nx + 1) * (c.ny + 1) * block;
+    if (idx >= nc) return;
+    lattice_restrict_at(f, c, block, hat, rf, rc, mask_f, mask_c, idx);
 }
 
 // coarse cell-wise coefficient for the rediscretised SIMP operator: power mean of the fine densities whose
@@ -232,28 +249,31 @@ struct LatD {
 };
 
 // weights of the right-diagonal P1 hat: 1 at coincident nodes, 1/2 along x, y and the (1,1) diagonal
-__global__ void __launch_bounds__(kThreads)
-    k_prolong_nested(LatD f, LatD c, const double *__restrict__ xc, double *__restrict__ xf,
-                     const uint8_t *__restrict__ mask_f) {
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+template <bool CG = false>
+__device__ __forceinline__ void prolong_nested_at(LatD f, LatD c, const double *xc, double *xf, const uint8_t *mask_f, int64_t idx) {
     const int fw = f.nx + 1, cw = c.nx + 1;
-    if (idx >= (int64_t)fw * f.nrows) return;
     if (mask_f && mask_f[idx]) return;
     const int i = (int)(idx % fw), jl = (int)(idx / fw);
     const int gj = jl + f.j0;
     const int I = i >> 1, oi = i & 1, oj = gj & 1;
     const int Jl = (gj >> 1) - c.j0;
     if (Jl < 0 || Jl + oj >= c.nrows) return;
-    const double a = xc[(int64_t)Jl * cw + I];
-    xf[idx] += (oi | oj) ? 0.5 * (a + xc[(int64_t)(Jl + oj) * cw + (I + oi)]) : a;
+    const double a = ldv<CG>(xc + (int64_t)Jl * cw + I);
+    xf[idx] = ldv<CG>(xf + idx) + ((oi | oj) ? 0.5 * (a + ldv<CG>(xc + (int64_t)(Jl + oj) * cw + (I + oi))) : a);
 }
 
 __global__ void __launch_bounds__(kThreads)
-    k_restrict_nested(LatD f, LatD c, const double *__restrict__ rf, double *__restrict__ rc,
-                      const uint8_t *__restrict__ mask_f, const uint8_t *__restrict__ mask_c) {
-    const int cw = c.nx + 1, fw = f.nx + 1;
+    k_prolong_nested(LatD f, LatD c, const double *__restrict__ xc, double *__restrict__ xf,
+                     const uint8_t *__restrict__ mask_f) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)cw * c.nrows) return;
+    if (idx >= (int64_t)(f.nx + 1) * f.nrows) return;
+    prolong_nested_at(f, c, xc, xf, mask_f, idx);
+}
+
+template <bool CG = false>
+__device__ __forceinline__ void restrict_nested_at(LatD f, LatD c, const double *rf, double *rc, const uint8_t *mask_f,
+                                                   const uint8_t *mask_c, int64_t idx) {
+    const int cw = c.nx + 1, fw = f.nx + 1;
     if (mask_c && mask_c[idx]) {
         rc[idx] = 0.0;
         return;
@@ -263,9 +283,17 @@ __global__ void __launch_bounds__(kThreads)
     auto at = [&](int ii, int jj) -> double {
         if (ii < 0 || jj < 0 || ii > f.nx || jj >= f.nrows) return 0.0;
         const int64_t k = (int64_t)jj * fw + ii;
-        return (mask_f && mask_f[k]) ? 0.0 : rf[k];
+        return (mask_f && mask_f[k]) ? 0.0 : ldv<CG>(rf + k);
     };
     rc[idx] = at(i, j) + 0.5 * (at(i - 1, j) + at(i + 1, j) + at(i, j - 1) + at(i, j + 1) + at(i - 1, j - 1) + at(i + 1, j + 1));
+}
+
+__global__ void __launch_bounds__(kThreads)
+    k_restrict_nested(LatD f, LatD c, const double *__restrict__ rf, double *__restrict__ rc,
+                      const uint8_t *__restrict__ mask_f, const uint8_t *__restrict__ mask_c) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)(c.nx + 1) * c.nrows) return;
+    restrict_nested_at(f, c, rf, rc, mask_f, mask_c, idx);
 }
 
 // coarse state = fine state at the coincident nodes (rediscretisation of the coarse Jacobian)
@@ -667,7 +695,7 @@ static inline bool dia_offsets(const femo_problem *L, DiaMat &A) {
 static inline size_t fp32_copy_len(const femo_problem *L) {
     DiaMat A;
     size_t n = (size_t)L->pat[0].nnz;
-    if (dia_offsets(L, A)) n = std::max<size_t>(n, (size_t)A.nd * (size_t)A.np);
+    if (dia_offsets(L, A)) n = std::max<size_t>(n, (size_t)(A.nd + 1) * (size_t)A.np);   // + the dinv plane
     return n;
 }
 
@@ -690,8 +718,8 @@ static int dia_convert(femo_problem *L) {
     FEMO_CHECK_LAUNCH();
     M.dia = A;
     M.dia_valid = true;
-    // the fused pre-smoother scales NEIGHBOUR entries by their 1/a_jj: ghost rows need the owner's diagonal
-    return halo_nodes_f32(L, M.vals32 + (size_t)A.sdiag * A.np);
+    // the fused pre-smoother scales NEIGHBOUR entries by their 1/a_jj: ghost rows need the owner's scaling
+    return halo_nodes_f32(L, M.vals32 + (size_t)A.nd * A.np);
 }
 
 static int launch_dia(femo_problem *L, int mode, const double *x, double *y, const DiaEpi &E) {
@@ -704,7 +732,7 @@ static int launch_dia(femo_problem *L, int mode, const double *x, double *y, con
         case DIA_PLAIN: k_dia_apply<DIA_PLAIN, 7><<<g, kThreads, 0, st>>>(A, x, y, E); break;
         case DIA_CHEB0: k_dia_apply<DIA_CHEB0, 7><<<g, kThreads, 0, st>>>(A, x, y, E); break;
         case DIA_CHEBK: k_dia_apply<DIA_CHEBK, 7><<<g, kThreads, 0, st>>>(A, x, y, E); break;
-        default: k_dia_pre2<<<g, kThreads, 0, st>>>(A, E.b, y, E); break;
+        default: k_dia_apply<DIA_PRE2, 7><<<g, kThreads, 0, st>>>(A, x, y, E); break;
     }
     L->launches++;
     L->dia_count[mode & 3]++;
@@ -814,6 +842,7 @@ static inline bool nested_pair(const femo_problem *F, const femo_problem *C) {
 
 static int mg_restrict(femo_problem *L, femo_problem *C, double *rf, double *rc_);
 static int mg_prolong_add(femo_problem *L, femo_problem *C, double *xc, double *xf);
+static int mgfused_vcycle(femo_problem *root, int lv, const double *b, double *x, const MgParams &mp, bool *done);
 
 // one V-cycle: level lv solves A x = b approximately from a zero initial guess
 static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, const MgParams &mp) {
@@ -828,6 +857,11 @@ static int mg_vcycle(femo_problem *root, int lv, const double *b, double *x, con
         L->launches++;
         FEMO_CHECK_LAUNCH();
         return FEMO_OK;
+    }
+    {   // coarse levels: the whole sub-V-cycle in one cooperative kernel (mgfused.cuh)
+        bool done = false;
+        if ((rc = mgfused_vcycle(root, lv, b, x, mp, &done))) return rc;
+        if (done) return FEMO_OK;
     }
     femo_problem *C = root->mg[lv];
     femo_mg_level &MC = C->mgl;
@@ -1100,5 +1134,6 @@ static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true) {
         }
         FEMO_CHECK_LAUNCH();
     }
+    root->mgprog.dirty = true;       // level bounds changed: the fused coarse V-cycle program is rebuilt on first use
     return FEMO_OK;
 }

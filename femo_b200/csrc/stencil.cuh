@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kThreads)
         for (int s = 0; s < D; ++s) planes[(int64_t)s * A.np + i] = a[s];
         const double di = (diag != 0.0) ? 1.0 / diag : 1.0;
         dinv[i] = di;
+        planes[(int64_t)D * A.np + i] = (float)di;
         if (i >= o0 && i < o1) g = sabs * fabs(di);
     }
     __shared__ double sh[kThreads];
@@ -78,95 +79,67 @@ struct DiaEpi {
     int xmode = 0;
 };
 
-__device__ __forceinline__ double dia_rcp(float d) { return d != 0.0f ? (double)(1.0f / d) : 1.0; }
-
+// One thread per row, 32-bit index arithmetic (int32 dofs), and an interior fast path without per-neighbour range
+// checks (only the first and last w+1 rows of a lattice can reach outside [0,n)).  PRE2 gathers the scaled right-hand
+// side c0 * dinv_j * b_j at the 7 neighbours from the dinv plane (no reciprocals, no staging).
 template <int MODE, int D>
 __global__ void __launch_bounds__(kThreads)
     k_dia_apply(DiaMat A, const double *__restrict__ x, double *__restrict__ y, DiaEpi E) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= A.n) return;
+    constexpr int SD = D / 2;           // the diagonal sits in the middle plane (offsets are symmetric about 0)
+    const int n = (int)A.n;
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const float *__restrict__ v = A.v + i;
+    const size_t np = (size_t)A.np;
     float a[D];
 #pragma unroll
-    for (int s = 0; s < D; ++s) a[s] = __ldcs(A.v + (int64_t)s * A.np + i);
-    float ad = 0.0f;             // a_ii (selected under unrolling: no dynamically indexed registers)
+    for (int s = 0; s < D; ++s) a[s] = __ldcs(v + s * np);
+    const float *__restrict__ dinvp = A.v + (size_t)D * np;
+    const double di = (double)__ldcs(dinvp + i);
+    const double *__restrict__ src = (MODE == DIA_PRE2) ? E.b : x;
+    const bool interior = i + A.off[0] >= 0 && i + A.off[D - 1] < n;
+    double xv[D];
+    if (interior) {
 #pragma unroll
-    for (int s = 0; s < D; ++s)
-        if (s == A.sdiag) ad = a[s];
-    double acc = 0.0;
-    if (MODE == DIA_PRE2) {
-        const float *dg = A.v + (int64_t)A.sdiag * A.np;
-        double d0i = 0.0;
+        for (int s = 0; s < D; ++s) xv[s] = __ldg(src + (i + A.off[s]));
+        if (MODE == DIA_PRE2) {
+#pragma unroll
+            for (int s = 0; s < D; ++s) xv[s] *= (s == SD) ? di : (double)__ldg(dinvp + (i + A.off[s]));
+        }
+    } else {
 #pragma unroll
         for (int s = 0; s < D; ++s) {
-            const int64_t j = i + A.off[s];
-            double v = 0.0;
-            if (j >= 0 && j < A.n) v = E.c0 * dia_rcp(s == A.sdiag ? ad : __ldg(dg + j)) * __ldg(E.b + j);
-            if (s == A.sdiag) d0i = v;
-            acc = fma((double)a[s], v, acc);
+            const int j = i + A.off[s];
+            const bool ok = j >= 0 && j < n;
+            xv[s] = ok ? __ldg(src + j) : 0.0;
+            if (MODE == DIA_PRE2) xv[s] *= ok ? (double)__ldg(dinvp + j) : 0.0;
         }
-        const double r = __ldg(E.b + i) - acc;
-        y[i] = d0i + E.c1 * d0i + E.c2 * dia_rcp(ad) * r;
-        return;
     }
-    double xi = 0.0;
+    double acc = 0.0, xi = 0.0;
 #pragma unroll
     for (int s = 0; s < D; ++s) {
-        const int64_t j = i + A.off[s];
-        const double v = (j >= 0 && j < A.n) ? __ldg(x + j) : 0.0;
-        if (s == A.sdiag) xi = v;
-        acc = fma((double)a[s], v, acc);
+        if (s == SD) xi = xv[s];
+        acc = fma((double)a[s], xv[s], acc);
     }
-    if (MODE == DIA_PLAIN) {
+    if (MODE == DIA_PRE2) {             // xv = dinv_j b_j ; d0 = c0 xv ; r = b_i - A d0 ; x = d0 + c1 d0 + c2 dinv_i r
+        const double d0i = E.c0 * xi;
+        const double r = __ldg(E.b + i) - E.c0 * acc;
+        y[i] = d0i + E.c1 * d0i + E.c2 * di * r;
+    } else if (MODE == DIA_PLAIN) {
         y[i] = E.b ? E.b[i] - acc : acc;
     } else if (MODE == DIA_CHEB0) {
         const double r = E.b[i] - acc;
         E.rout[i] = r;
-        E.dout[i] = E.c1 * dia_rcp(ad) * r;
+        E.dout[i] = E.c1 * di * r;
     } else {
         const double r = E.rin[i] - acc;
         if (E.rout) E.rout[i] = r;
-        const double dn = E.c1 * xi + E.c2 * dia_rcp(ad) * r;
+        const double dn = E.c1 * xi + E.c2 * di * r;
         if (E.dout) E.dout[i] = dn;
         if (E.xmode == 0) E.xacc[i] += dn;
         else if (E.xmode == 1) E.xacc[i] += xi + dn;
         else E.xacc[i] = xi + dn;
     }
-}
-
-// Zero-guess degree-2 pre-smoother of the 7-point lattice stencil (offsets {-w-1,-w | -1,0,1 | w,w+1}) with the scaled
-// right-hand side d0 = c0 b / a_jj staged in shared memory: a CTA of 256 consecutive rows needs d0 on three contiguous
-// index ranges (the lattice rows below / of / above), each computed ONCE per CTA (one b load, one diagonal load, one
-// reciprocal per entry) instead of 7 gathers + 7 reciprocals per row.
-__global__ void __launch_bounds__(kThreads)
-    k_dia_pre2(DiaMat A, const double *__restrict__ b, double *__restrict__ x, DiaEpi E) {
-    __shared__ double sd[3][kThreads + 2];
-    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x;
-    const int w = A.off[5];
-    const float *dg = A.v + 3 * A.np;
-    const int64_t start[3] = {i0 - w - 1, i0 - 1, i0 + w};
-#pragma unroll
-    for (int g = 0; g < 3; ++g)
-        for (int t = threadIdx.x; t < kThreads + 2; t += kThreads) {
-            const int64_t j = start[g] + t;
-            sd[g][t] = (j >= 0 && j < A.n) ? E.c0 * dia_rcp(__ldg(dg + j)) * __ldg(b + j) : 0.0;
-        }
-    __syncthreads();
-    const int64_t i = i0 + threadIdx.x;
-    if (i >= A.n) return;
-    const int t = threadIdx.x;
-    float a[7];
-#pragma unroll
-    for (int s = 0; s < 7; ++s) a[s] = __ldcs(A.v + (int64_t)s * A.np + i);
-    double acc = (double)a[0] * sd[0][t];
-    acc = fma((double)a[1], sd[0][t + 1], acc);
-    acc = fma((double)a[2], sd[1][t], acc);
-    const double d0i = sd[1][t + 1];
-    acc = fma((double)a[3], d0i, acc);
-    acc = fma((double)a[4], sd[1][t + 2], acc);
-    acc = fma((double)a[5], sd[2][t], acc);
-    acc = fma((double)a[6], sd[2][t + 1], acc);
-    const double r = __ldg(b + i) - acc;
-    x[i] = d0i + E.c1 * d0i + E.c2 * dia_rcp(a[3]) * r;
 }
 
 }  // namespace femo

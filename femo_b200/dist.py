@@ -1,6 +1,7 @@
-"""Multi-GPU plumbing on the Python side: one process per GPU (torchrun),
-torch.distributed only ships the NCCL unique id; all data-path communication is
-issued by libfemo_b200 on its own stream (include/femo_b200.h, "multi-GPU")."""
+"""Multi-GPU plumbing on the Python side: one process per GPU (torchrun).
+torch.distributed only ships 64-byte IPC handles (or the 128-byte NCCL id); all data-path communication is issued by
+libfemo_b200 on its own stream (include/femo_b200.h, "multi-GPU"): by default through the engine's own peer-memory
+transport (csrc/link.cuh; FEMO_COMM=link), optionally through NCCL (FEMO_COMM=nccl)."""
 import ctypes as C
 import os
 
@@ -12,22 +13,37 @@ from . import engine as _E
 _state = dict(initialised=False, rank=0, nranks=1)
 
 
-def init(device=None):
-    """Create the engine's NCCL communicator from the torch.distributed world."""
+def init(device=None, backend=None):
+    """Create the engine's communicator from the torch.distributed world (any torch backend: it only carries the
+    handles).  backend 'link' (default): peer-memory windows, also valid for several ranks on one device;
+    'nccl': ncclSend/Recv + ncclAllReduce."""
     import torch
     import torch.distributed as dist
     if _state['initialised']:
         return _state['rank'], _state['nranks']
     rank, nranks = dist.get_rank(), dist.get_world_size()
     device = int(os.environ.get('LOCAL_RANK', rank)) if device is None else device
+    backend = backend or os.environ.get('FEMO_COMM', 'link')
+    on_gpu = dist.get_backend() == 'nccl'
+    tdev = torch.device('cuda', device) if on_gpu else torch.device('cpu')
+    if backend == 'link':
+        h = C.create_string_buffer(64)
+        check(lib.femo_link_create(device, 0, 0, h))
+        mine = torch.tensor(list(h.raw), dtype=torch.uint8, device=tdev)
+        parts = [torch.empty_like(mine) for _ in range(nranks)]
+        dist.all_gather(parts, mine)
+        raw = b''.join(bytes(t.cpu().tolist()) for t in parts)
+        check(lib.femo_link_open(raw, rank, nranks))
+        _state.update(initialised=True, rank=rank, nranks=nranks, backend='link')
+        return rank, nranks
     buf = C.create_string_buffer(128)
     if rank == 0:
         check(lib.femo_comm_unique_id(buf))
-    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=torch.device('cuda', device))
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=tdev)
     dist.broadcast(t, 0)
     raw = bytes(t.cpu().tolist())
     check(lib.femo_comm_init(raw, rank, nranks, device))
-    _state.update(initialised=True, rank=rank, nranks=nranks)
+    _state.update(initialised=True, rank=rank, nranks=nranks, backend='nccl')
     return rank, nranks
 
 
@@ -40,7 +56,8 @@ def finalize():
 def stats():
     s = (C.c_longlong * 2)()
     check(lib.femo_comm_stats(s))
-    return dict(halo_exchanges=int(s[0]), allreduces=int(s[1]))
+    return dict(halo_exchanges=int(s[0]), allreduces=int(s[1]), backend=_state.get('backend'),
+                link_error=int(lib.femo_link_error()))
 
 
 class SlabProblem(_E.EngineProblem):

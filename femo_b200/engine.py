@@ -307,6 +307,13 @@ class EngineProblem:
         check(lib.femo_assemble_output_grad(self._h, k, slot, self._p(out)))
         return out
 
+    def assemble_output_and_grad(self, k=0, out=None):
+        """J_k and dJ_k/du in one quadrature pass; returns (J, dJdu tensor)."""
+        out = self.new_vector(self.N) if out is None else out
+        v = C.c_double()
+        check(lib.femo_assemble_output_and_grad(self._h, k, C.byref(v), self._p(out)))
+        return v.value, out
+
     def spmv(self, which, vals, x, transpose=False, out=None):
         i = self.pattern_info(which)
         n = i['cols'] if transpose else i['rows']

@@ -125,6 +125,14 @@ int femo_problem_set_bc(femo_problem *p, const int32_t *dofs, const int32_t *lis
  * every rank then calls femo_comm_init once. */
 int femo_comm_unique_id(char id[128]);
 int femo_comm_init(const char id[128], int rank, int nranks, int device);
+/* The engine's own transport over peer memory (csrc/link.cuh): halo exchanges, scalar all-reduces and level gathers are
+ * single kernels that store into IPC-mapped windows of the peer GPUs (NVLink / NVSwitch) and spin on sequence flags.
+ * femo_link_create allocates this rank's window (capacities in doubles; 0 = defaults) and returns its 64-byte IPC
+ * handle; after an all-gather of the handles (any host channel) femo_link_open maps the peers and activates the
+ * communicator.  Works for several ranks on ONE device as well.  femo_comm_init (NCCL) remains as an alternative. */
+int femo_link_create(int device, size_t halo_cap, size_t gather_cap, char handle[64]);
+int femo_link_open(const char *handles, int rank, int nranks);
+int femo_link_error(void);
 int femo_comm_finalize(void);
 int femo_comm_stats(long long stats[2]);   /* [halo exchanges, all-reduces] issued so far */
 /* Host only: the local problem of `rank` on the (nx x gny)-cell triangle lattice over [lo,hi]. */
@@ -190,6 +198,8 @@ int femo_assemble_output(femo_problem *p, int out_id, double *h_value);
 /* assemble(derivative(form, arg), dim=1) (output_model.py:77-87); slot as in
  * femo_set_coefficient (0 = wrt state). */
 int femo_assemble_output_grad(femo_problem *p, int out_id, int slot, double *d_out);
+/* J and dJ/du in one quadrature pass (output_model.py:69-87 call both on the same state); synchronises. */
+int femo_assemble_output_and_grad(femo_problem *p, int out_id, double *h_value, double *d_dJdu);
 
 /* ---- linear algebra --------------------------------------------------------*/
 /* computeMatVecProductFwd / Bwd (utils_dolfinx.py:256-264,275-287):

@@ -20,9 +20,13 @@ def relerr(a, b):
 
 
 def main():
-    lr = int(os.environ.get('LOCAL_RANK', '0'))
+    same = os.environ.get('FEMO_DIST_SAME_DEVICE') == '1'      # all ranks on cuda:0 (link transport, 1-GPU boxes)
+    lr = 0 if same else int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(lr)
-    dist.init_process_group('nccl', device_id=torch.device('cuda', lr))
+    if same:
+        dist.init_process_group('gloo')
+    else:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', lr))
     rank, R = fd.init(lr)
     famid = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     nx = int(sys.argv[2]) if len(sys.argv) > 2 else 64
@@ -132,7 +136,9 @@ def main():
     pg.axpy(-1.0, pg.spmv(1, pg.assemble_dRdm(0), lamg, transpose=True), gg)
     check('total derivative', own_cells_l(g), own_cells_g(gg.cpu().numpy()), 1e-7)
     torch.cuda.synchronize()
-    flag = torch.tensor([len(fails)], device='cuda')
+    if fd.stats()['link_error']:
+        fails.append('link transport timed out')
+    flag = torch.tensor([len(fails)], device='cpu' if same else 'cuda')
     dist.all_reduce(flag)
     for f in fails:
         print('[rank %d] FAIL %s' % (rank, f), flush=True)

@@ -1,5 +1,10 @@
-"""Multi-GPU path on real GPUs: runs tests/dist_check.py under torchrun when the box
-has at least two devices (the driver's 1-GPU test box skips it; gpurun --gpus 2 runs it)."""
+"""Multi-rank path on real GPUs: tests/dist_check*.py under torchrun compare the slab-partitioned engine with the
+unpartitioned problem (assembly 1e-12, SpMV with poisoned ghosts 1e-13, GMG-PCG, SNES state, total derivative).
+
+  * on a 1-GPU box (the driver's test box) the ranks share cuda:0: the engine's own peer-memory transport
+    (csrc/link.cuh) maps its windows between processes on the same device, so the whole distributed code path --
+    slab layouts, halo exchange, fused all-reduces, partitioned multigrid, level gathers -- is exercised;
+  * with >= 2 GPUs both transports run: link over NVLink peer memory and NCCL."""
 import os
 import subprocess
 import sys
@@ -10,32 +15,30 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize('famid', [2, 1])
-def test_slab_partition_matches_single_gpu(cuda_device, famid):
+def _modes():
     import torch
-    n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip('needs >= 2 GPUs')
+    if torch.cuda.device_count() < 2:
+        return [dict(FEMO_DIST_SAME_DEVICE='1', FEMO_COMM='link')]
+    return [dict(FEMO_COMM='link'), dict(FEMO_COMM='nccl')]
+
+
+def _run(script, args, port, extra):
     R = 2
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(R),
-           '--master-addr', '127.0.0.1', '--master-port', '29611', os.path.join(ROOT, 'tests', 'dist_check.py'),
-           str(famid), '64', str(64 * R)]
-    env = dict(os.environ, FEMO_DIST_MIN_ROWS='16')     # several distributed levels even on this small mesh
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+           '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', script)] + [str(a) for a in args]
+    env = dict(os.environ, FEMO_DIST_MIN_ROWS='16', **extra)     # several distributed levels even on these small meshes
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert 'OK' in out.stdout
+
+
+@pytest.mark.parametrize('famid', [2, 1])
+def test_slab_partition_matches_single_gpu(cuda_device, famid):
+    for k, mode in enumerate(_modes()):
+        _run('dist_check.py', [famid, 64, 128], 29611 + 10 * k + famid, mode)
 
 
 def test_hex_slab_partition_matches_single_gpu(cuda_device):
     """z-slab partition of the hexahedral SIMP family vs the unpartitioned box."""
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs >= 2 GPUs')
-    R = 2
-    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(R),
-           '--master-addr', '127.0.0.1', '--master-port', '29613', os.path.join(ROOT, 'tests', 'dist_check_hex.py'),
-           '16', '8', str(16 * R)]
-    env = dict(os.environ, FEMO_DIST_MIN_ROWS='16')
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert 'OK' in out.stdout
+    for k, mode in enumerate(_modes()):
+        _run('dist_check_hex.py', [16, 8, 32], 29641 + 10 * k, mode)

@@ -108,3 +108,51 @@ def test_dia_smoother_degrees(cuda_device, deg):
     assert info['converged'] and info64['converged']
     assert relerr(x.cpu().numpy(), x64.cpu().numpy()) < 1e-8
     assert abs(info['iterations'] - info64['iterations']) <= 1
+
+
+@pytest.mark.parametrize('n,ny', [(1, 1), (2, 3), (33, 7), (128, 96)])
+def test_node_centric_jacobian_matches_general_path(cuda_device, n, ny):
+    """lattice_asm.cuh (one thread per node, rows written straight into the CSR values) against the general
+    cell-kernel + sorted-segmented-reduction path, plain and BC'd copies."""
+    from _cases import square_boundary_lists
+    c = Case(2, n, ny, seed=n, oracle=False)
+    c.p.set_bc(square_boundary_lists(c.coords), None)
+    v1, b1 = c.p.assemble_jacobian(plain=True, bc=True)
+    os.environ['FEMO_NO_LATTICE_ASM'] = '1'
+    try:
+        v0, b0 = c.p.assemble_jacobian(plain=True, bc=True)
+    finally:
+        os.environ.pop('FEMO_NO_LATTICE_ASM', None)
+    assert relerr(v1.cpu().numpy(), v0.cpu().numpy()) < 1e-13
+    assert relerr(b1.cpu().numpy(), b0.cpu().numpy()) < 1e-13
+
+
+def test_fused_output_and_gradient(cuda_device):
+    c = Case(2, 40, 24, seed=3, oracle=False)
+    J, g = c.p.assemble_output_and_grad(0)
+    assert abs(J - c.p.assemble_output(0)) <= 1e-15 * abs(J)
+    assert np.array_equal(g.cpu().numpy(), c.p.assemble_output_grad(0, 0).cpu().numpy())
+    c1 = Case(1, 12, seed=3, oracle=False)                      # families without a fused kernel take the two passes
+    J1, g1 = c1.p.assemble_output_and_grad(0)
+    assert J1 == c1.p.assemble_output(0) and np.array_equal(g1.cpu().numpy(), c1.p.assemble_output_grad(0, 0).cpu().numpy())
+
+
+def test_fused_coarse_vcycle_matches_per_level_kernels(cuda_device):
+    """mgfused.cuh: the cooperative coarse V-cycle kernel against the per-level launches (same row arithmetic)."""
+    res = []
+    for fused in (True, False):
+        if not fused:
+            os.environ['FEMO_NO_MGFUSED'] = '1'
+        try:
+            c = Case(1, 300, 212, seed=2, mg=True, oracle=False)
+            _, vbc = c.p.assemble_jacobian(plain=False, bc=True)
+            b = c.p.to_device(np.random.default_rng(7).standard_normal(c.p.N))
+            l0 = c.p.launch_count()
+            x, info = c.p.linear_solve(vbc, b, rtol=1e-11, precond=2, cheb_degree=2)
+            res.append((x.cpu().numpy(), info, c.p.launch_count() - l0))
+        finally:
+            os.environ.pop('FEMO_NO_MGFUSED', None)
+    assert res[0][1]['converged'] and res[1][1]['converged']
+    assert res[0][1]['iterations'] == res[1][1]['iterations']
+    assert relerr(res[0][0], res[1][0]) < 1e-10
+    assert res[0][2] < res[1][2] / 2, (res[0][2], res[1][2])          # far fewer launches
