@@ -124,6 +124,8 @@ struct femo_mg_level {
     double lmax = 2.0;
     femo::DiaMat dia;                               // lattice stencil levels: the V-cycle streams DIA planes (stencil.cuh);
     bool dia_valid = false;                         // they alias the vals32 buffer
+    double *dia64 = nullptr;                        // level 0: fp64 planes of the operator the Krylov recurrence applies
+    bool dia64_valid = false;
 };
 
 namespace femo {

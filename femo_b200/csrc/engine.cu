@@ -284,42 +284,47 @@ __global__ void __launch_bounds__(kThreads)
 
 // Cone density filter on the lattice of cell centres (examples/beam_topo_opt/pre_processor/
 // general_filter_model.py:67-90): W_ij = (R - d_ij) / sum_k (R - d_ik) over centres with d <= R.
-// The neighbour search is index arithmetic on the lattice; den_i = sum_k (R - d_ik) is geometry only.
-__global__ void __launch_bounds__(kThreads)
-    k_filter_den(int nx, int ny, double dx, double dy, double R, double *__restrict__ den) {
+// The neighbour search is index arithmetic on the lattice (2-D: nz = 1); den_i = sum_k (R - d_ik) is geometry only.
+struct FilterLat {
+    int nx, ny, nz;
+    double dx, dy, dz, R;
+};
+
+__global__ void __launch_bounds__(kThreads) k_filter_den(FilterLat L, double *__restrict__ den) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)nx * ny) return;
-    const int i = (int)(idx % nx), j = (int)(idx / nx);
-    const int kx = (int)floor(R / dx), ky = (int)floor(R / dy);
+    if (idx >= (int64_t)L.nx * L.ny * L.nz) return;
+    const int i = (int)(idx % L.nx), j = (int)((idx / L.nx) % L.ny), k = (int)(idx / ((int64_t)L.nx * L.ny));
+    const int kx = (int)floor(L.R / L.dx), ky = (int)floor(L.R / L.dy), kz = L.nz > 1 ? (int)floor(L.R / L.dz) : 0;
     double s = 0.0;
-    for (int b = max(j - ky, 0); b <= min(j + ky, ny - 1); ++b)
-        for (int a = max(i - kx, 0); a <= min(i + kx, nx - 1); ++a) {
-            const double ex = (a - i) * dx, ey = (b - j) * dy;
-            const double d = sqrt(ex * ex + ey * ey);
-            if (d <= R) s += R - d;
-        }
+    for (int c = max(k - kz, 0); c <= min(k + kz, L.nz - 1); ++c)
+        for (int b = max(j - ky, 0); b <= min(j + ky, L.ny - 1); ++b)
+            for (int a = max(i - kx, 0); a <= min(i + kx, L.nx - 1); ++a) {
+                const double ex = (a - i) * L.dx, ey = (b - j) * L.dy, ez = (c - k) * L.dz;
+                const double d = sqrt(ex * ex + ey * ey + ez * ez);
+                if (d <= L.R) s += L.R - d;
+            }
     den[idx] = s;
 }
 
 // out = W in (TRANSPOSE = false) or out = W^T in (true: weights normalised by the NEIGHBOUR's den)
 template <bool TRANSPOSE>
 __global__ void __launch_bounds__(kThreads)
-    k_filter_apply(int nx, int ny, double dx, double dy, double R, const double *__restrict__ den,
-                   const double *__restrict__ in, double *__restrict__ out) {
+    k_filter_apply(FilterLat L, const double *__restrict__ den, const double *__restrict__ in, double *__restrict__ out) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)nx * ny) return;
-    const int i = (int)(idx % nx), j = (int)(idx / nx);
-    const int kx = (int)floor(R / dx), ky = (int)floor(R / dy);
+    if (idx >= (int64_t)L.nx * L.ny * L.nz) return;
+    const int i = (int)(idx % L.nx), j = (int)((idx / L.nx) % L.ny), k = (int)(idx / ((int64_t)L.nx * L.ny));
+    const int kx = (int)floor(L.R / L.dx), ky = (int)floor(L.R / L.dy), kz = L.nz > 1 ? (int)floor(L.R / L.dz) : 0;
     double s = 0.0;
-    for (int b = max(j - ky, 0); b <= min(j + ky, ny - 1); ++b)
-        for (int a = max(i - kx, 0); a <= min(i + kx, nx - 1); ++a) {
-            const double ex = (a - i) * dx, ey = (b - j) * dy;
-            const double d = sqrt(ex * ex + ey * ey);
-            if (d <= R) {
-                const int64_t k = (int64_t)b * nx + a;
-                s += TRANSPOSE ? (R - d) * in[k] / den[k] : (R - d) * in[k];
+    for (int c = max(k - kz, 0); c <= min(k + kz, L.nz - 1); ++c)
+        for (int b = max(j - ky, 0); b <= min(j + ky, L.ny - 1); ++b)
+            for (int a = max(i - kx, 0); a <= min(i + kx, L.nx - 1); ++a) {
+                const double ex = (a - i) * L.dx, ey = (b - j) * L.dy, ez = (c - k) * L.dz;
+                const double d = sqrt(ex * ex + ey * ey + ez * ez);
+                if (d <= L.R) {
+                    const int64_t q = ((int64_t)c * L.ny + b) * L.nx + a;
+                    s += TRANSPOSE ? (L.R - d) * in[q] / den[q] : (L.R - d) * in[q];
+                }
             }
-        }
     out[idx] = TRANSPOSE ? s : s / den[idx];
 }
 
@@ -1550,6 +1555,10 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     w += Arena::need(N, 8);                        // Chebyshev direction of multigrid level 0
     if (!p->mg.empty()) w += Arena::need(fp32_copy_len(p), 4);   // fp32 copy (CSR order or DIA planes)
     if (!p->mg.empty()) w += Arena::need(kMgFusedMaxOps, sizeof(MgOp));   // op list of the cooperative coarse V-cycle
+    {
+        DiaMat A;
+        if (!p->mg.empty() && dia_offsets(p, A)) w += Arena::need((size_t)A.nd * (size_t)A.np, 8);   // fp64 planes (Krylov operator)
+    }
     if (hex_matfree_level(p)) { s += Arena::need(576, 8); w += Arena::need((size_t)M.ncells, 8); }
     if (N <= kMgDenseMax) w += 2 * Arena::need((size_t)N * N, 8);   // explicit inverse (precond 3)
     if (!p->symmetric) w += (size_t)(kGmresRestart + 2) * Arena::need(N, 8) + Arena::need((size_t)(kGmresRestart + 1) * kMaxPartials, 8);
@@ -1744,6 +1753,10 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     p->kr_d = p->wk.take<double>(N);
     if (!p->mg.empty()) p->mgl.vals32 = p->wk.take<float>(fp32_copy_len(p));
     if (!p->mg.empty()) p->d_mgops = p->wk.take<MgOp>(kMgFusedMaxOps);
+    {   // fp64 planes of the fine-level operator for the Krylov recurrence (lattice stencil problems)
+        DiaMat A;
+        if (!p->mg.empty() && dia_offsets(p, A)) p->mgl.dia64 = p->wk.take<double>((size_t)A.nd * (size_t)A.np);
+    }
     if ((rc = setup_hex_matfree(p, p))) return rc;
     if (!p->symmetric) {
         p->gm_restart = kGmresRestart;
@@ -1930,7 +1943,17 @@ int femo_assemble_jacobian(femo_problem *p, double *d_vals, double *d_vals_bc) {
         A.ext_top = !p->slab.active || p->slab.rank == p->slab.nranks - 1;
         A.rowptr = D.rowptr; A.col = D.col; A.bcflag = D.bcflag; A.bc_diag = p->d_bc_diag;
         A.out = d_vals; A.out_bc = d_vals_bc;
-        k_nlpoisson_p1_node_jac<<<grid_for(p->state.ndofs), kThreads, 0, p->stream>>>(A);
+        LatGeom G;
+        {   // P1 gradients of the two congruent triangle types of the uniform lattice
+            const double hx = (p->mesh.hi[0] - p->mesh.lo[0]) / (double)p->mesh.n[0];
+            const double hy = (p->mesh.hi[1] - p->mesh.lo[1]) / (double)(p->slab.active ? p->slab.gny : p->mesh.n[1]);
+            const double gl[3][2] = {{-1.0 / hx, 0.0}, {1.0 / hx, -1.0 / hy}, {0.0, 1.0 / hy}};
+            const double gu[3][2] = {{0.0, -1.0 / hy}, {-1.0 / hx, 1.0 / hy}, {1.0 / hx, 0.0}};
+            memcpy(G.gl, gl, sizeof(gl));
+            memcpy(G.gu, gu, sizeof(gu));
+            G.a2 = hx * hy;
+        }
+        k_nlpoisson_p1_node_jac<<<grid_for(p->state.ndofs), kThreads, 0, p->stream>>>(A, G);
         p->launches++;
         FEMO_CHECK_LAUNCH();
         return FEMO_OK;
@@ -2079,20 +2102,26 @@ int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_
     return launch_spmv<false>(p, D.t_rb, D.t_nrb, D.t_rowptr, D.t_col, p->d_tvals, d_x, d_y, nullptr, nullptr, false);
 }
 
-int femo_filter_apply(int device, void *stream, int nx, int ny, double dx, double dy, double radius,
-                      const double *d_in, double *d_out, double *d_den, int transpose) {
-    if (nx < 1 || ny < 1 || !(dx > 0) || !(dy > 0) || !(radius > 0) || !d_in || !d_out || !d_den)
+int femo_filter_apply3(int device, void *stream, int nx, int ny, int nz, double dx, double dy, double dz, double radius,
+                       const double *d_in, double *d_out, double *d_den, int transpose) {
+    if (nx < 1 || ny < 1 || nz < 1 || !(dx > 0) || !(dy > 0) || !(dz > 0) || !(radius > 0) || !d_in || !d_out || !d_den)
         return set_err(FEMO_EINVAL, "femo_filter_apply: bad arguments");
     if (femo_device_count() <= device || device < 0)
         return set_err(FEMO_ENODEVICE, "femo_filter_apply: no such CUDA device; this engine has no CPU path");
     FEMO_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n = (int64_t)nx * ny;
-    k_filter_den<<<grid_for(n), kThreads, 0, st>>>(nx, ny, dx, dy, radius, d_den);
-    if (transpose) k_filter_apply<true><<<grid_for(n), kThreads, 0, st>>>(nx, ny, dx, dy, radius, d_den, d_in, d_out);
-    else k_filter_apply<false><<<grid_for(n), kThreads, 0, st>>>(nx, ny, dx, dy, radius, d_den, d_in, d_out);
+    const int64_t n = (int64_t)nx * ny * nz;
+    const FilterLat L{nx, ny, nz, dx, dy, dz, radius};
+    k_filter_den<<<grid_for(n), kThreads, 0, st>>>(L, d_den);
+    if (transpose) k_filter_apply<true><<<grid_for(n), kThreads, 0, st>>>(L, d_den, d_in, d_out);
+    else k_filter_apply<false><<<grid_for(n), kThreads, 0, st>>>(L, d_den, d_in, d_out);
     FEMO_CHECK_LAUNCH();
     return FEMO_OK;
+}
+
+int femo_filter_apply(int device, void *stream, int nx, int ny, double dx, double dy, double radius,
+                      const double *d_in, double *d_out, double *d_den, int transpose) {
+    return femo_filter_apply3(device, stream, nx, ny, 1, dx, dy, 1.0, radius, d_in, d_out, d_den, transpose);
 }
 
 int femo_pointwise_divide(femo_problem *p, double a, const double *d_num, const double *d_den, double *d_out, int64_t n) {

@@ -162,7 +162,13 @@ __global__ void __launch_bounds__(kThreads) k_poisson_p1_cell(TriArgs A) {
 // ---------------------------------------------------------------------------
 template <int OP>
 __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_cell(TriArgs A) {
-    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if ((OP == OP_OUT || OP == OP_OUT_DU || OP == OP_OUT_BOTH) && A.uex_tab) {
+        // lattice meshes alternate lower / upper triangles: let each half of the CTA take one type so that the
+        // angle-addition table reads of the 49-point rule are warp-uniform (even cells: warps 0-3, odd cells: warps 4-7)
+        const int t = threadIdx.x;
+        c = blockIdx.x * (int64_t)blockDim.x + 2 * (t % (kThreads / 2)) + t / (kThreads / 2);
+    }
     if (c >= A.ncells) return;
     const int64_t ne = A.ncells;
     Tri T;
@@ -219,6 +225,7 @@ __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_cell(TriArgs A) {
     } else {  // OP_OUT / OP_OUT_DU : degree-12 rule, u_ex evaluated at the points
         double val = 0.0, ge[3] = {0.0, 0.0, 0.0};
         const UexCell U = uex_cell(A, T);
+#pragma unroll 7
         for (int q = 0; q < 49; ++q) {
             const double ph[3] = {1.0 - c_tri49[q][0] - c_tri49[q][1], c_tri49[q][0], c_tri49[q][1]};
             const double x = ph[0] * T.X[0][0] + ph[1] * T.X[1][0] + ph[2] * T.X[2][0];

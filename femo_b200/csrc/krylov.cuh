@@ -221,10 +221,13 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     // full-multigrid start (halves the iteration count here; measured on slabs too: 14 vs 27 iterations per step at N=2)
     if (pre == 2 && o.restart != 1 && (rc = mg_fmg(p, b, x, mp))) return rc;
     const bool mf_outer = op_current && pre == 2 && mp.fp32 && hex_matfree_ready(p);
+    const bool dia_outer = pre == 2 && mp.fp32 && p->mgl.dia64_valid && dia_ready(p);     // fp64 planes of `vals` (set-up)
     // r = b - A x
     if (mf_outer) {
         SpmvEpi E0;
         if ((rc = launch_hex_matfree(p, EPI_PLAIN, x, p->kr_q, E0))) return rc;
+    } else if (dia_outer) {
+        if ((rc = launch_dia64<false>(p, x, p->kr_q, nullptr, nullptr))) return rc;
     } else if ((rc = launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, vals, x, p->kr_q, nullptr, nullptr))) return rc;
     ++spmvs;
     if (pre == 0) {
@@ -271,6 +274,8 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
             k_dot<<<go, kThreads, 0, st>>>(p->kr_p + p->own_off, p->kr_q + p->own_off, p->own_n, p->d_partials);
             p->launches++;
             np = go;
+        } else if (dia_outer) {
+            if ((rc = launch_dia64<true>(p, p->kr_p, p->kr_q, nullptr, &np))) return rc;
         } else if ((rc = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, nullptr, &np))) return rc;
         ++spmvs;
         if ((rc = reduce_to(p, p->d_partials, nullptr, np, S_PQ, 0))) return rc;

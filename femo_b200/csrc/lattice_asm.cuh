@@ -68,45 +68,67 @@ __device__ __forceinline__ void nlp_facet_jac_row(const Tri &T, int l, double be
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A) {
+// Uniform lattice: all lower triangles are congruent and so are all upper ones, so the P1 gradients and |det J| are
+// two constant sets (computed on the host from the lattice spacing, passed as kernel arguments) -- no connectivity or
+// coordinate loads and no divisions in the interior.  The 7 state values of the node's stencil are loaded once and
+// every incident triangle picks its three by compile-time slot; element rows land in compile-time slots as well.
+// Boundary triangles add their Nitsche facet rows through the general geometry path (tri_load), O(boundary) work.
+struct LatGeom {
+    double gl[3][2], gu[3][2];   // gradients of the lower [v0,v1,v3] / upper [v0,v2,v3] triangle
+    double a2;                   // |det J| = hx * hy
+};
+
+__device__ __forceinline__ void nlp_cell_jac_row_const(const double g[3][2], double a2, const double u[3], int a, double row[3]) {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) row[b] = 0.5 * a2 * (g[a][0] * g[b][0] + g[a][1] * g[b][1]);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const double ph[3] = {1.0 - c_tri6[q][0] - c_tri6[q][1], c_tri6[q][0], c_tri6[q][1]};
+        const double uq = u[0] * ph[0] + u[1] * ph[1] + u[2] * ph[2];
+        const double s = c_tri6[q][2] * a2 * 3.0 * uq * uq * ph[a];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) row[b] += s * ph[b];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A, LatGeom G) {
     const int w = A.nx + 1;
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= (int64_t)w * (A.ny + 1)) return;
     const int i = (int)(r % w), j = (int)(r / w);
-    double v[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};      // slots of offsets {-w-1, -w, -1, 0, 1, w, w+1}
-    // incident triangles: (cell dx, cell dy, upper?, local index of this node)
-    const int tri[6][4] = {{0, 0, 0, 0}, {0, 0, 1, 0}, {-1, 0, 0, 1}, {0, -1, 1, 1}, {-1, -1, 0, 2}, {-1, -1, 1, 2}};
+    // stencil slots {-w-1, -w, -1, 0, 1, w, w+1} and which of them exist on the local lattice
+    const bool present[7] = {i > 0 && j > 0, j > 0, i > 0, true, i < A.nx, j < A.ny, i < A.nx && j < A.ny};
+    const int off[7] = {-w - 1, -w, -1, 0, 1, w, w + 1};
+    double u7[7], v[7];
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+        u7[s] = present[s] ? __ldg(A.T.u + (r + off[s])) : 0.0;
+        v[s] = 0.0;
+    }
+    // incident triangles: cell offset, upper?, local index of this node, stencil slots of the triangle's vertices
+    constexpr int TRI[6][7] = {{0, 0, 0, 0, 3, 4, 6}, {0, 0, 1, 0, 3, 5, 6}, {-1, 0, 0, 1, 2, 3, 5},
+                               {0, -1, 1, 1, 1, 3, 4}, {-1, -1, 0, 2, 0, 1, 3}, {-1, -1, 1, 2, 0, 2, 3}};
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
-        const int ci = i + tri[t][0], cj = j + tri[t][1], up = tri[t][2], a = tri[t][3];
+        const int ci = i + TRI[t][0], cj = j + TRI[t][1];
         if (ci < 0 || cj < 0 || ci >= A.nx || cj >= A.ny) continue;
-        Tri T;
-        tri_load(A.T, 2 * ((int64_t)cj * A.nx + ci) + up, T);
-        double u[3];
-#pragma unroll
-        for (int b = 0; b < 3; ++b) u[b] = __ldg(A.T.u + T.v[b]);
+        const int up = TRI[t][2], a = TRI[t][3];
+        const double u[3] = {u7[TRI[t][4]], u7[TRI[t][5]], u7[TRI[t][6]]};
         double row[3];
-        nlp_cell_jac_row(T, u, a, row);
-        // exterior facets of this triangle: lower: l = 2 (edge v0-v1, bottom), l = 0 (edge v1-v3, right);
-        //                                   upper: l = 2 (edge v0-v2, left),   l = 0 (edge v2-v3, top)
-        if (!up) {
-            if (cj == 0 && A.ext_bottom) nlp_facet_jac_row(T, 2, A.T.beta, a, row);
-            if (ci == A.nx - 1) nlp_facet_jac_row(T, 0, A.T.beta, a, row);
-        } else {
-            if (ci == 0) nlp_facet_jac_row(T, 2, A.T.beta, a, row);
-            if (cj == A.ny - 1 && A.ext_top) nlp_facet_jac_row(T, 0, A.T.beta, a, row);
+        nlp_cell_jac_row_const(up ? G.gu : G.gl, G.a2, u, a, row);
+        const bool fb = !up && cj == 0 && A.ext_bottom, fr = !up && ci == A.nx - 1;
+        const bool fl = up && ci == 0, ft = up && cj == A.ny - 1 && A.ext_top;
+        if (fb || fr || fl || ft) {      // boundary triangle: Nitsche facet rows with the cell's own geometry
+            Tri T;
+            tri_load(A.T, 2 * ((int64_t)cj * A.nx + ci) + up, T);
+            if (fb || fl) nlp_facet_jac_row(T, 2, A.T.beta, a, row);
+            if (fr || ft) nlp_facet_jac_row(T, 0, A.T.beta, a, row);
         }
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            const int d = T.v[b] - (int)r;
-            const int s = d == 0 ? 3 : d == 1 ? 4 : d == -1 ? 2 : d == w ? 5 : d == w + 1 ? 6 : d == -w ? 1 : 0;
-#pragma unroll
-            for (int k = 0; k < 7; ++k)
-                if (k == s) v[k] += row[b];
-        }
+        v[TRI[t][4]] += row[0];
+        v[TRI[t][5]] += row[1];
+        v[TRI[t][6]] += row[2];
     }
-    // CSR positions: the row holds the slots whose neighbour exists on the local lattice, in ascending column order
-    const bool present[7] = {i > 0 && j > 0, j > 0, i > 0, true, i < A.nx, j < A.ny, i < A.nx && j < A.ny};
+    // CSR positions: the row holds the present slots in ascending column order
     int32_t pos = A.rowptr[r];
 #pragma unroll
     for (int s = 0; s < 7; ++s) {

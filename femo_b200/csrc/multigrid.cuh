@@ -712,7 +712,8 @@ static int dia_convert(femo_problem *L) {
     if ((size_t)g > L->scratch_len) return set_err(FEMO_ESTATE, "DIA conversion: scratch too small for the partial maxima");
     k_csr_to_dia<7><<<g, kThreads, 0, L->stream>>>(D.rowptr, D.col, M.vals, A, M.vals32,
                                                    reinterpret_cast<int *>(L->d_scalars + S_FLAG), M.dinv, L->own_off,
-                                                   L->own_off + L->own_n, part);
+                                                   L->own_off + L->own_n, part, M.dia64);
+    M.dia64_valid = M.dia64 != nullptr;
     k_max_finalize<<<1, kThreads, 0, L->stream>>>(part, g, L->d_scalars, S_TMP2);
     L->launches += 2;
     FEMO_CHECK_LAUNCH();
@@ -736,6 +737,20 @@ static int launch_dia(femo_problem *L, int mode, const double *x, double *y, con
     }
     L->launches++;
     L->dia_count[mode & 3]++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
+// y = A x (or bsub - A x) with the level's fp64 planes; DOT: fused partial sums of x.y over the owned rows
+template <bool DOT>
+static int launch_dia64(femo_problem *L, const double *x, double *y, const double *bsub, int *np_out) {
+    int rc = halo_nodes(L, const_cast<double *>(x));
+    if (rc) return rc;
+    const DiaMat &A = L->mgl.dia;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(A.n), std::min<int64_t>((int64_t)L->num_sms * 8, kMaxPartials)));
+    k_dia_spmv64<DOT, 7><<<grid, kThreads, 0, L->stream>>>(L->mgl.dia64, A, x, y, bsub, L->own_off, L->own_off + L->own_n, L->d_partials);
+    L->launches++;
+    if (np_out) *np_out = grid;
     FEMO_CHECK_LAUNCH();
     return FEMO_OK;
 }
@@ -982,7 +997,15 @@ static int mg_fmg(femo_problem *root, const double *b, double *x, const MgParams
         // residual of the prolonged iterate into M.b (free at this level), V-cycle correction into M.x
         const DevPattern &D = L->dpat[0];
         double *rl = (lv == 0) ? root->kr_r : M.b, *el = (lv == 0) ? root->kr_z : M.x;
-        if ((rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, xl, rl, bl, nullptr))) return rc;
+        // residual of the nested iterate: fp64 planes on the fine level, the V-cycle's fp32 planes below (the
+        // full-multigrid iterate is only the Krylov method's initial guess)
+        if (mp.fp32 && M.dia64_valid && dia_ready(L)) rc = launch_dia64<false>(L, xl, rl, bl, nullptr);
+        else if (mp.fp32 && dia_ready(L) && lv > 0) {
+            DiaEpi E;
+            E.b = bl;
+            rc = launch_dia(L, DIA_PLAIN, xl, rl, E);
+        } else rc = launch_spmv<false>(L, D.rb, D.nrb, D.rowptr, D.col, M.vals, xl, rl, bl, nullptr);
+        if (rc) return rc;
         if ((rc = mg_vcycle(root, lv, rl, el, mp))) return rc;
         k_axpy<<<red_grid(L, n), kThreads, 0, st>>>(1.0, el, xl, n);
         L->launches++;
@@ -1110,6 +1133,7 @@ static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true) {
             dia_setup = true;
         } else if (fp32 && M.vals32 && lv < nlev - 1) {
             M.dia_valid = false;
+            M.dia64_valid = false;
             const int64_t nnz = L->pat[0].nnz;
             k_to_f32<<<(int)std::min<int64_t>((nnz + kThreads - 1) / kThreads, (int64_t)L->num_sms * 16), kThreads, 0, st>>>(M.vals, M.vals32, nnz);
             L->launches++;

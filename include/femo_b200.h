@@ -215,6 +215,10 @@ int femo_axpy(femo_problem *p, double a, const double *d_x, double *d_y, int64_t
  * for d <= R, or out = W^T in (the constant Jacobian's transpose action).  d_den: nx*ny doubles of scratch. */
 int femo_filter_apply(int device, void *stream, int nx, int ny, double dx, double dy, double radius,
                       const double *d_in, double *d_out, double *d_den, int transpose);
+/* The same filter on a 3-D lattice of cell centres (nx x ny x nz, cell id = (k*ny + j)*nx + i): the pre-processor of
+ * the 16.8M-cell cantilever; d_den: nx*ny*nz doubles of scratch. */
+int femo_filter_apply3(int device, void *stream, int nx, int ny, int nz, double dx, double dy, double dz, double radius,
+                       const double *d_in, double *d_out, double *d_den, int transpose);
 /* out = a * num / den (Vec.pointwiseDivide of the lumped projection, utils_dolfinx.py:566-569) */
 int femo_pointwise_divide(femo_problem *p, double a, const double *d_num, const double *d_den, double *d_out, int64_t n);
 

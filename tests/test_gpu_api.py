@@ -254,3 +254,22 @@ def test_topology_example_3d_hex(cuda_device):
     assert max(rep.values()) < 1e-5, rep
     rep = sim.check_totals('avg_density', 'density', step=1e-3, compact_print=False)
     assert max(rep.values()) < 1e-8, rep
+
+
+def test_density_filter_3d_matches_kdtree_oracle(cuda_device):
+    """femo_filter_apply3 (the 3-D pre-processor of the hexahedral cantilever) against the oracle's KD-tree weights:
+    W x and the reverse-mode action W^T y."""
+    from femo_b200.csdl_opt.pre_processor.general_filter_model import GeneralFilterOperation
+    from oracle.filter import weight_matrix
+    nx, ny, nz, h = 9, 6, 5, (2.0, 2.0, 1.5)
+    K, J, I = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing='ij')
+    coords = np.stack([(I.ravel() + 0.5) * h[0], (J.ravel() + 0.5) * h[1], (K.ravel() + 0.5) * h[2]], axis=1)
+    op = GeneralFilterOperation(nel=coords.shape[0], beta=2.0, coordinates=coords, h_avg=1.9)
+    op.define()
+    W = weight_matrix(coords, 1.9, 2.0)
+    rng = np.random.default_rng(0)
+    x, y = rng.random(coords.shape[0]), rng.standard_normal(coords.shape[0])
+    out = {}
+    op.compute({'density_unfiltered': x}, out)
+    assert np.max(np.abs(out['density'] - W @ x)) < 1e-13
+    assert np.max(np.abs(op.vjp('density', 'density_unfiltered', y) - W.T @ y)) < 1e-13

@@ -127,3 +127,22 @@ def test_hostops_bulk_helpers_match_numpy():
         assert np.all(d == 4.0)
         H.copy(d, np.array([2.0]))
         assert np.all(d == 2.0)
+
+
+def test_density_filter_lattice_detection_and_weights_3d():
+    """GeneralFilterOperation on a 3-D lattice of hexahedron centres: lattice detection and the sparse Jacobian
+    (weight_triplets) against the oracle's KD-tree restatement of general_filter_model.py:67-90."""
+    import scipy.sparse as sp
+    from femo_b200.csdl_opt.pre_processor.general_filter_model import GeneralFilterOperation, _lattice
+    from oracle.filter import weight_matrix
+    nx, ny, nz, h = 7, 5, 4, (2.0, 1.5, 1.0)
+    K, J, I = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing='ij')
+    coords = np.stack([(I.ravel() + 0.5) * h[0], (J.ravel() + 0.5) * h[1], (K.ravel() + 0.5) * h[2]], axis=1)
+    assert _lattice(coords) == (nx, ny, nz, h[0], h[1], h[2])
+    assert _lattice(coords[:nx * ny, :2]) == (nx, ny, 1, h[0], h[1], 1.0)
+    op = GeneralFilterOperation(nel=nx * ny * nz, beta=2.0, coordinates=coords, h_avg=1.6)
+    op.define()
+    r, c, v = op.weight_triplets()
+    W = sp.csr_matrix((v, (r, c)), shape=(nx * ny * nz,) * 2)
+    Wo = weight_matrix(coords, 1.6, 2.0)
+    assert abs(W - Wo).max() < 1e-14
