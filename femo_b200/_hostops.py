@@ -34,9 +34,22 @@ def _t(a):
     return torch.from_numpy(a)
 
 
+def _ptr(a):
+    return a.ctypes.data
+
+
+def _lib():
+    from ._lib import lib
+    return lib
+
+
 def _big(a):
     return (isinstance(a, np.ndarray) and a.size >= BIG and a.dtype == np.float64 and a.flags.c_contiguous
             and a.flags.writeable)
+
+
+def _big_src(a):
+    return isinstance(a, np.ndarray) and a.size >= BIG and a.dtype == np.float64 and a.flags.c_contiguous
 
 
 def pinned_empty(n):
@@ -58,8 +71,8 @@ def is_pinned(a):
 
 def copy(dst, src):
     src = np.asarray(src, dtype=np.float64)
-    if _big(dst) and _big(src) and src.size == dst.size:
-        _t(dst).view(-1).copy_(_t(src).view(-1))
+    if _big(dst) and _big_src(src) and src.size == dst.size:
+        _lib().femo_host_scaled_copy(_ptr(dst), _ptr(src), dst.size, 1.0)       # all host cores (csrc/hostops.cpp)
     elif src.size == 1:
         dst.fill(float(src.ravel()[0]))
     else:
@@ -68,7 +81,7 @@ def copy(dst, src):
 
 def fill(dst, value):
     if _big(dst):
-        _t(dst).fill_(float(value))
+        _lib().femo_host_fill(_ptr(dst), dst.size, float(value))
     else:
         dst.fill(value)
 
@@ -76,8 +89,8 @@ def fill(dst, value):
 def iadd(dst, src, alpha=1.0):
     """dst += alpha * src in place."""
     src = np.asarray(src, dtype=np.float64)
-    if _big(dst) and _big(src) and src.size == dst.size:
-        _t(dst).view(-1).add_(_t(src).view(-1), alpha=float(alpha))
+    if _big(dst) and _big_src(src) and src.size == dst.size:
+        _lib().femo_host_axpy(_ptr(dst), _ptr(src), dst.size, float(alpha))
     elif alpha == 1.0:
         dst += src.reshape(dst.shape)
     else:
@@ -89,8 +102,7 @@ def scaled_copy(dst, src, alpha=1.0):
     src = np.asarray(src, dtype=np.float64)
     if alpha == 1.0:
         copy(dst, src)
-    elif _big(dst) and _big(src) and src.size == dst.size:
-        import torch
-        torch.mul(_t(src).view(-1), float(alpha), out=_t(dst).view(-1))
+    elif _big(dst) and _big_src(src) and src.size == dst.size:
+        _lib().femo_host_scaled_copy(_ptr(dst), _ptr(src), dst.size, float(alpha))
     else:
         np.multiply(src.reshape(dst.shape), alpha, out=dst)

@@ -99,6 +99,9 @@ SIGNATURES = {
     'femo_axpy': (C.c_int, [_P, C.c_double, _P, _P, C.c_int64]),
     'femo_filter_apply': (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, _P, C.c_int]),
     'femo_filter_apply3': (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, _P, C.c_int]),
+    'femo_host_scaled_copy': (None, [_P, _P, C.c_int64, C.c_double]),
+    'femo_host_axpy': (None, [_P, _P, C.c_int64, C.c_double]),
+    'femo_host_fill': (None, [_P, C.c_int64, C.c_double]),
     'femo_pointwise_divide': (C.c_int, [_P, C.c_double, _P, _P, _P, C.c_int64]),
     'femo_vcycle_op_probe': (C.c_int, [_P, C.c_int, _I64P]),
     'femo_linear_solve': (C.c_int, [_P, _P, _P, _P, C.c_int, C.POINTER(KrylovOpts), C.POINTER(KrylovInfo)]),

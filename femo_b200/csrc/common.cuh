@@ -182,6 +182,8 @@ struct femo_problem {
     // device
     int device = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // high-priority side stream: halo exchange + slab-boundary rows (overlap)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool uploaded = false;
     int num_sms = 148;
     femo::Arena st, wk;

@@ -16,13 +16,14 @@ static inline int link_chunks(size_t len) {
 // [recv_lo, ...) from below / [recv_hi, ...) from above (lengths in elements of T; zero-length directions still flag)
 template <class T>
 static int link_halo(femo_problem *p, T *v, size_t send_lo, size_t recv_lo, size_t send_hi, size_t recv_hi, size_t slen_lo,
-                     size_t rlen_lo, size_t slen_hi, size_t rlen_hi) {
+                     size_t rlen_lo, size_t slen_hi, size_t rlen_hi, cudaStream_t st = nullptr) {
+    if (!st) st = p->stream;
     const size_t mx = std::max(std::max(slen_lo, rlen_lo), std::max(slen_hi, rlen_hi));
     if (mx * sizeof(T) > g_link.lay.halo_cap * sizeof(double))
         return set_err(FEMO_ELIMIT, "halo row exceeds the link window (femo_link_create halo capacity)");
     const int nch = link_chunks(mx);
     const unsigned long long seq = ++g_link.seq;
-    k_link_halo<T><<<2 * nch, kThreads, 0, p->stream>>>(g_link.dev(), v, send_lo, recv_lo, send_hi, recv_hi, slen_lo, rlen_lo,
+    k_link_halo<T><<<2 * nch, kThreads, 0, st>>>(g_link.dev(), v, send_lo, recv_lo, send_hi, recv_hi, slen_lo, rlen_lo,
                                                          slen_hi, rlen_hi, nch, seq);
     p->launches++;
     g_comm.halo_exchanges++;
@@ -53,29 +54,65 @@ static int link_gather(femo_problem *p, double *g, size_t blk, size_t tail) {
 
 // Refresh the ghost node rows of a state-space vector (ghostUpdate FORWARD of the reference,
 // utils_dolfinx.py:167): whole lattice rows are contiguous, so rows are sent in place.
-static int halo_nodes(femo_problem *p, double *v) {
+static int halo_nodes(femo_problem *p, double *v, cudaStream_t st = nullptr) {
     const SlabInfo &s = p->slab;
     if (p->skip_next_halo) {
         p->skip_next_halo = false;
         return FEMO_OK;
     }
     if (!s.active || !g_comm.active) return FEMO_OK;
+    if (!st) st = p->stream;
     const size_t len = (size_t)(p->mesh.n[0] + 1) * (p->mesh.kind == MESH_HEX ? (size_t)(p->mesh.n[1] + 1) : 1) * p->state.block;
     if (g_link.active)
         return link_halo<double>(p, v, (size_t)s.own0 * len, (size_t)(s.own0 - 1) * len, (size_t)(s.own1 - 1) * len,
-                                 (size_t)s.own1 * len, len, len, len, len);
+                                 (size_t)s.own1 * len, len, len, len, len, st);
     NcclApi &a = g_comm.api;
     FEMO_NCCL(a.GroupStart());
     if (s.rank > 0) {
-        FEMO_NCCL(a.Send(v + (size_t)s.own0 * len, len, ncclDouble, s.rank - 1, g_comm.comm, p->stream));
-        FEMO_NCCL(a.Recv(v + (size_t)(s.own0 - 1) * len, len, ncclDouble, s.rank - 1, g_comm.comm, p->stream));
+        FEMO_NCCL(a.Send(v + (size_t)s.own0 * len, len, ncclDouble, s.rank - 1, g_comm.comm, st));
+        FEMO_NCCL(a.Recv(v + (size_t)(s.own0 - 1) * len, len, ncclDouble, s.rank - 1, g_comm.comm, st));
     }
     if (s.rank < s.nranks - 1) {
-        FEMO_NCCL(a.Send(v + (size_t)(s.own1 - 1) * len, len, ncclDouble, s.rank + 1, g_comm.comm, p->stream));
-        FEMO_NCCL(a.Recv(v + (size_t)s.own1 * len, len, ncclDouble, s.rank + 1, g_comm.comm, p->stream));
+        FEMO_NCCL(a.Send(v + (size_t)(s.own1 - 1) * len, len, ncclDouble, s.rank + 1, g_comm.comm, st));
+        FEMO_NCCL(a.Recv(v + (size_t)s.own1 * len, len, ncclDouble, s.rank + 1, g_comm.comm, st));
     }
     FEMO_NCCL(a.GroupEnd());
     g_comm.halo_exchanges++;
+    return FEMO_OK;
+}
+
+// Overlap of a slab level's halo exchange with its interior rows (K11 of SURVEY.md section 8a): rows of the first and
+// last OWNED lattice row read ghost values, all other owned rows do not.  `overlap_begin` forks the side stream behind
+// everything enqueued so far and runs the exchange there; the caller then launches the boundary rows on the side stream
+// and the interior rows on the main stream, and `overlap_end` joins.  Returns false when the level is not split
+// (one GPU, small level, ghost rows provably fresh) -- the caller then takes the plain path.
+static int64_t overlap_min_rows() {          // owned dofs below which a level is not split (FEMO_OVERLAP_MIN_ROWS overrides)
+    const char *e = getenv("FEMO_OVERLAP_MIN_ROWS");
+    return e ? atoll(e) : ((int64_t)1 << 18);
+}
+struct RowSplit {
+    int b0 = 0, nb0 = 0, b1 = 0, nb1 = 0;   // boundary segments (first / last owned lattice row)
+    int i0 = 0, ni = 0;                     // interior rows
+};
+static bool overlap_begin(femo_problem *p, double *v, RowSplit &R, int *rc) {
+    *rc = FEMO_OK;
+    const SlabInfo &s = p->slab;
+    if (!s.active || !g_comm.active || p->skip_next_halo || !p->stream2 || p->mesh.kind == MESH_HEX || getenv("FEMO_NO_OVERLAP")) return false;
+    const int64_t len = (int64_t)(p->mesh.n[0] + 1) * p->state.block;
+    const int64_t rows = s.own1 - s.own0;
+    if (rows < 4 || rows * len < overlap_min_rows()) return false;
+    R.b0 = (int)(s.own0 * len); R.nb0 = (int)len;
+    R.b1 = (int)((s.own1 - 1) * len); R.nb1 = (int)len;
+    R.i0 = (int)((s.own0 + 1) * len); R.ni = (int)((rows - 2) * len);
+    cudaError_t e = cudaEventRecord(p->ev_fork, p->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(p->stream2, p->ev_fork, 0);
+    if (e != cudaSuccess) { *rc = set_err(FEMO_ECUDA, cudaGetErrorString(e)); return false; }
+    *rc = halo_nodes(p, v, p->stream2);
+    return *rc == FEMO_OK;
+}
+static int overlap_end(femo_problem *p) {
+    FEMO_CUDA(cudaEventRecord(p->ev_join, p->stream2));
+    FEMO_CUDA(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
     return FEMO_OK;
 }
 

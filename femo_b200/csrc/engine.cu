@@ -764,6 +764,7 @@ static int push_bc(femo_problem *p) {
 extern "C" {
 static int propagate_bc(femo_problem *root, int start = 0);
 static int set_bc_impl(femo_problem *p, const int32_t *dofs, const int32_t *list_ptr, int nlists, const double *g);
+static int lattice_jacobian(femo_problem *p, double *d_vals, double *d_vals_bc, bool with_dia, bool dia_bc);
 }
 
 #include "stencil.cuh"
@@ -1298,6 +1299,11 @@ void femo_problem_destroy(femo_problem *p) {
     if (!p) return;
     for (femo_problem *c : p->mg) femo_problem_destroy(c);
     if (p->h_pinned) cudaFreeHost(p->h_pinned);
+    if (!p->parent && p->stream2) {
+        cudaStreamDestroy(p->stream2);
+        cudaEventDestroy(p->ev_fork);
+        cudaEventDestroy(p->ev_join);
+    }
     delete p;
 }
 
@@ -1454,6 +1460,9 @@ static void child_bytes(const femo_problem *c, bool coarsest, size_t *sb, size_t
 static int upload_child(femo_problem *root, femo_problem *c, bool coarsest) {
     c->device = root->device;
     c->stream = root->stream;
+    c->stream2 = root->stream2;
+    c->ev_fork = root->ev_fork;
+    c->ev_join = root->ev_join;
     c->num_sms = root->num_sms;
     const Mesh &M = c->mesh;
     const int64_t N = c->state.ndofs;
@@ -1590,6 +1599,13 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     p->num_sms = prop.multiProcessorCount;
     p->st.reset(d_static, static_bytes);
     p->wk.reset(d_work, work_bytes);
+    if (!p->stream2) {
+        int lo_prio = 0, hi_prio = 0;
+        FEMO_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        FEMO_CUDA(cudaStreamCreateWithPriority(&p->stream2, cudaStreamNonBlocking, hi_prio));
+        FEMO_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+        FEMO_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    }
     const Mesh &M = p->mesh;
     const int64_t N = p->state.ndofs;
     int rc;
@@ -1909,11 +1925,77 @@ int femo_halo_exchange(femo_problem *p, double *d_v, int kind) {
     return kind == 0 ? halo_nodes(p, d_v) : halo_cells(p, d_v);
 }
 
+// arguments of the node-centric lattice kernels (lattice_asm.cuh)
+static void lattice_args(femo_problem *p, LatJacArgs &A, LatGeom &G) {
+    const DevPattern &D = p->dpat[0];
+    A.T = tri_args(p, nullptr);
+    A.nx = p->mesh.n[0]; A.ny = p->mesh.n[1];
+    A.ext_bottom = !p->slab.active || p->slab.rank == 0;
+    A.ext_top = !p->slab.active || p->slab.rank == p->slab.nranks - 1;
+    A.rowptr = D.rowptr; A.col = D.col; A.bcflag = D.bcflag; A.bc_diag = p->d_bc_diag;
+    A.out = A.out_bc = nullptr;
+    // P1 gradients of the two congruent triangle types of the uniform lattice
+    const double hx = (p->mesh.hi[0] - p->mesh.lo[0]) / (double)p->mesh.n[0];
+    const double hy = (p->mesh.hi[1] - p->mesh.lo[1]) / (double)(p->slab.active ? p->slab.gny : p->mesh.n[1]);
+    const double gl[3][2] = {{-1.0 / hx, 0.0}, {1.0 / hx, -1.0 / hy}, {0.0, 1.0 / hy}};
+    const double gu[3][2] = {{0.0, -1.0 / hy}, {-1.0 / hx, 1.0 / hy}, {1.0 / hx, 0.0}};
+    memcpy(G.gl, gl, sizeof(gl));
+    memcpy(G.gu, gu, sizeof(gu));
+    G.a2 = hx * hy;
+}
+
+// Node-centric Jacobian of a lattice level.  with_dia: also write the level operator straight into the DIA planes of
+// the multigrid solve (fp32 + scaling plane, dinv, Gershgorin maxima -> S_TMP2; fp64 planes on level 0), BC'd copy when
+// dia_bc.  d_vals / d_vals_bc may both be null then (the CSR values are not needed by a DIA-only level).
+static int lattice_jacobian(femo_problem *p, double *d_vals, double *d_vals_bc, bool with_dia, bool dia_bc) {
+    int rc;
+    if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
+    LatJacArgs A;
+    LatGeom G;
+    lattice_args(p, A, G);
+    A.out = d_vals; A.out_bc = d_vals_bc;
+    LatDiaOut O;
+    femo_mg_level &M = p->mgl;
+    const int g = grid_for(p->state.ndofs);
+    if (with_dia) {
+        DiaMat D;
+        if (!dia_offsets(p, D) || !M.vals32 || !M.dinv) return set_err(FEMO_ESTATE, "lattice_jacobian: level has no DIA storage");
+        if ((size_t)g > p->scratch_len) return set_err(FEMO_ESTATE, "lattice_jacobian: scratch too small for the partial maxima");
+        D.v = M.vals32;
+        O.planes32 = M.vals32; O.planes64 = M.dia64; O.dinv = M.dinv; O.gpart = p->d_scratch;
+        O.np = D.np; O.o0 = p->own_off; O.o1 = p->own_off + p->own_n; O.use_bc = dia_bc ? 1 : 0;
+        M.dia = D;
+    }
+    k_nlpoisson_p1_node_jac<<<g, kThreads, 0, p->stream>>>(A, G, O);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    if (with_dia) {
+        k_max_finalize<<<1, kThreads, 0, p->stream>>>(p->d_scratch, g, p->d_scalars, S_TMP2);
+        p->launches++;
+        FEMO_CHECK_LAUNCH();
+        M.dia_valid = true;
+        M.dia64_valid = M.dia64 != nullptr;
+        return halo_nodes_f32(p, M.vals32 + (size_t)M.dia.nd * M.dia.np);
+    }
+    return FEMO_OK;
+}
+
 // ---- assembly -------------------------------------------------------------
 int femo_assemble_residual(femo_problem *p, double *d_out) {
     int rc;
     if ((rc = need_device(p))) return rc;
     if (!d_out) return set_err(FEMO_EINVAL, "femo_assemble_residual: null output");
+    if (p->lattice_fast && p->res_mask == 3 && !getenv("FEMO_NO_LATTICE_ASM")) {
+        if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
+        if ((rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
+        LatJacArgs A;
+        LatGeom G;
+        lattice_args(p, A, G);
+        k_nlpoisson_p1_node_res<<<grid_for(p->state.ndofs), kThreads, 0, p->stream>>>(A, G, d_out);
+        p->launches++;
+        FEMO_CHECK_LAUNCH();
+        return FEMO_OK;
+    }
     if ((rc = run_elements(p, OP_RES, p->res_mask))) return rc;
     return segreduce(p, p->dvm_state[p->res_mask], p->state.ndofs, d_out);
 }
@@ -1936,27 +2018,7 @@ int femo_assemble_jacobian(femo_problem *p, double *d_vals, double *d_vals_bc) {
     }
     if (p->lattice_fast && !getenv("FEMO_NO_LATTICE_ASM")) {   // right-diagonal lattice: node-centric rows, no scratch round trip
         if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
-        LatJacArgs A;
-        A.T = tri_args(p, nullptr);
-        A.nx = p->mesh.n[0]; A.ny = p->mesh.n[1];
-        A.ext_bottom = !p->slab.active || p->slab.rank == 0;
-        A.ext_top = !p->slab.active || p->slab.rank == p->slab.nranks - 1;
-        A.rowptr = D.rowptr; A.col = D.col; A.bcflag = D.bcflag; A.bc_diag = p->d_bc_diag;
-        A.out = d_vals; A.out_bc = d_vals_bc;
-        LatGeom G;
-        {   // P1 gradients of the two congruent triangle types of the uniform lattice
-            const double hx = (p->mesh.hi[0] - p->mesh.lo[0]) / (double)p->mesh.n[0];
-            const double hy = (p->mesh.hi[1] - p->mesh.lo[1]) / (double)(p->slab.active ? p->slab.gny : p->mesh.n[1]);
-            const double gl[3][2] = {{-1.0 / hx, 0.0}, {1.0 / hx, -1.0 / hy}, {0.0, 1.0 / hy}};
-            const double gu[3][2] = {{0.0, -1.0 / hy}, {-1.0 / hx, 1.0 / hy}, {1.0 / hx, 0.0}};
-            memcpy(G.gl, gl, sizeof(gl));
-            memcpy(G.gu, gu, sizeof(gu));
-            G.a2 = hx * hy;
-        }
-        k_nlpoisson_p1_node_jac<<<grid_for(p->state.ndofs), kThreads, 0, p->stream>>>(A, G);
-        p->launches++;
-        FEMO_CHECK_LAUNCH();
-        return FEMO_OK;
+        return lattice_jacobian(p, d_vals, d_vals_bc, false, false);
     }
     if ((rc = run_elements(p, OP_JAC, p->jac_mask))) return rc;
     k_segreduce_jac<<<grid_for(nnz), kThreads, 0, p->stream>>>(D.gptr, D.gsrc, p->d_scratch,
@@ -2197,11 +2259,19 @@ int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton
     int it = 0, kit = 0, spmvs = 0, reason = 0;
     double f0 = 0, fn = 0;
     bool jac_valid = false;
+    // lattice P1 problems solved by GMG-PCG: the Jacobian rows go straight into the DIA planes of the solve
+    DiaMat dtmp;
+    const bool lat_direct = p->lattice_fast && opts->krylov.precond == 2 && opts->krylov.mg_precision == 0 &&
+                            opts->krylov.method == 0 && !p->mg.empty() && p->mgl.vals32 && dia_offsets(p, dtmp) &&
+                            !getenv("FEMO_NO_LATTICE_ASM");
+    p->mgl.dinv = p->kr_dinv;
     auto eval_F = [&]() -> int {
         int r;
         jac_valid = false;
         if (p->has_bc) {  // lifting needs the element columns of Dirichlet dofs at this state
-            if ((r = femo_assemble_jacobian(p, p->nt_vals, p->nt_vals_bc))) return r;
+            if (lat_direct) r = lattice_jacobian(p, p->nt_vals, p->nt_vals_bc, true, true);
+            else r = femo_assemble_jacobian(p, p->nt_vals, p->nt_vals_bc);
+            if (r) return r;
             jac_valid = true;
         }
         if ((r = femo_newton_rhs(p, p->nt_vals, p->nt_b))) return r;
@@ -2214,7 +2284,8 @@ int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton
     f0 = fn;
     if (fn < opts->atol) reason = 1;
     while (!reason && it < opts->max_it) {
-        if (!jac_valid && (rc = femo_assemble_jacobian(p, p->nt_vals, nullptr))) return rc;
+        if (!jac_valid && (rc = lat_direct ? lattice_jacobian(p, nullptr, nullptr, true, false)   // no CSR copy needed
+                                           : femo_assemble_jacobian(p, p->nt_vals, nullptr))) return rc;
         k_fill<<<red_grid(p, n), kThreads, 0, st>>>(0.0, p->nt_dx, n);
         p->launches++;
         femo_krylov_info ki;
@@ -2223,7 +2294,7 @@ int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton
         // change the SNES convergence decision, so the Krylov solve may stop there
         femo_krylov_opts ko = opts->krylov;
         if (snes) ko.atol = std::max(ko.atol, 0.1 * opts->atol);
-        if ((rc = (ko.method == 1 ? gmres_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki) : cg_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki, true)))) return rc;
+        if ((rc = (ko.method == 1 ? gmres_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki) : cg_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki, true, lat_direct)))) return rc;
         kit += ki.iterations;
         spmvs += ki.spmv_count;
         // the reference's LU cannot fail; a Krylov solve can (max_it, breakdown, NaN): never apply such a step silently

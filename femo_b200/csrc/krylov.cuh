@@ -179,7 +179,7 @@ static int norm2_sq(femo_problem *p, const double *a, double *out) {
 // problem (true inside femo_newton_solve, which assembles it itself): hexahedral lattices then apply the operator
 // matrix-free in the recurrence too.  Matrices handed in through femo_linear_solve are always streamed as given.
 static int cg_solve(femo_problem *p, const double *vals, const double *b, double *x, femo_krylov_opts o,
-                    femo_krylov_info *info, bool op_current = false) {
+                    femo_krylov_info *info, bool op_current = false, bool dia_prepared = false) {
     default_krylov(o);
     if (o.precond == 2 && p->mg.empty()) o.precond = 0;
     if (o.precond == 3 && !p->d_dense) return set_err(FEMO_ELIMIT, "precond 3 (dense direct) needs N <= 512 on one GPU");
@@ -202,7 +202,7 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     const int cdeg = o.cheb_degree > 0 ? o.cheb_degree : 8;
     const double cratio = o.cheb_ratio > 1.0 ? o.cheb_ratio : 60.0;
     if (pre == 2) {
-        if ((rc = mg_setup(p, vals, mp.fp32))) return rc;
+        if ((rc = mg_setup(p, vals, mp.fp32, dia_prepared))) return rc;
     } else if (pre == 1) {
         if ((rc = cheb_setup(p, vals))) return rc;
     } else if (pre == 3) {

@@ -91,10 +91,22 @@ __device__ __forceinline__ void nlp_cell_jac_row_const(const double g[3][2], dou
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A, LatGeom G) {
+// optional extra outputs of the node-centric Jacobian: the row directly in the layouts the multigrid-preconditioned
+// Krylov solve consumes (stencil.cuh) -- 7 fp32 planes + the fp32 Jacobi scaling plane for the V-cycle, 7 fp64 planes
+// for the recurrence, 1/a_ii in fp64 and the per-CTA Gershgorin maxima -- so no CSR -> DIA conversion pass is needed
+struct LatDiaOut {
+    float *planes32 = nullptr;
+    double *planes64 = nullptr, *dinv = nullptr, *gpart = nullptr;
+    int64_t np = 0, o0 = 0, o1 = 0;
+    int use_bc = 0;             // the level matrix is the BC'd copy (rows / columns of Dirichlet dofs replaced)
+};
+
+__global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A, LatGeom G, LatDiaOut O) {
     const int w = A.nx + 1;
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= (int64_t)w * (A.ny + 1)) return;
+    __shared__ double sh_g[kThreads];
+    double gersh = 0.0;
+    if (r < (int64_t)w * (A.ny + 1)) {
     const int i = (int)(r % w), j = (int)(r / w);
     // stencil slots {-w-1, -w, -1, 0, 1, w, w+1} and which of them exist on the local lattice
     const bool present[7] = {i > 0 && j > 0, j > 0, i > 0, true, i < A.nx, j < A.ny, i < A.nx && j < A.ny};
@@ -130,16 +142,125 @@ __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A
     }
     // CSR positions: the row holds the present slots in ascending column order
     int32_t pos = A.rowptr[r];
+    double sabs = 0.0, diag = 1.0;
 #pragma unroll
     for (int s = 0; s < 7; ++s) {
-        if (!present[s]) continue;
-        if (A.out) A.out[pos] = v[s];
-        if (A.out_bc) {
-            const uint8_t fl = A.bcflag ? A.bcflag[pos] : 0;
-            A.out_bc[pos] = (fl == 0) ? v[s] : (fl == 1 ? 0.0 : A.bc_diag[A.col[pos]]);
+        double m = 0.0;                     // entry of the level matrix (plain or BC'd) in slot s
+        if (present[s]) {
+            double vb = v[s];
+            if (A.out_bc || O.use_bc) {
+                const uint8_t fl = A.bcflag ? A.bcflag[pos] : 0;
+                vb = (fl == 0) ? v[s] : (fl == 1 ? 0.0 : A.bc_diag[A.col[pos]]);
+            }
+            if (A.out) A.out[pos] = v[s];
+            if (A.out_bc) A.out_bc[pos] = vb;
+            m = O.use_bc ? vb : v[s];
+            ++pos;
         }
-        ++pos;
+        if (O.planes32) {
+            O.planes32[(int64_t)s * O.np + r] = (float)m;
+            if (O.planes64) O.planes64[(int64_t)s * O.np + r] = m;
+            sabs += fabs(m);
+            if (s == 3) diag = m;
+        }
     }
+    if (O.planes32) {
+        const double di = (diag != 0.0) ? 1.0 / diag : 1.0;
+        O.planes32[(int64_t)7 * O.np + r] = (float)di;
+        O.dinv[r] = di;
+        if (r >= O.o0 && r < O.o1) gersh = sabs * fabs(di);
+    }
+    }
+    if (O.gpart) {                          // per-CTA maximum of the Gershgorin bound (uniform branch)
+        sh_g[threadIdx.x] = gersh;
+        __syncthreads();
+        for (int o = kThreads / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) sh_g[threadIdx.x] = fmax(sh_g[threadIdx.x], sh_g[threadIdx.x + o]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) O.gpart[blockIdx.x] = sh_g[0];
+    }
+}
+
+// ---- residual rows, same node-centric scheme --------------------------------------------------------------------
+// entry a of the cell vector  int grad(u).grad(phi_a) + (u^3 - f) phi_a dx  (as k_nlpoisson_p1_cell<OP_RES>)
+__device__ __forceinline__ double nlp_cell_res_entry(const double g[3][2], double a2, const double u[3], double f, int a) {
+    const double gu0 = u[0] * g[0][0] + u[1] * g[1][0] + u[2] * g[2][0];
+    const double gu1 = u[0] * g[0][1] + u[1] * g[1][1] + u[2] * g[2][1];
+    double R = 0.5 * a2 * (gu0 * g[a][0] + gu1 * g[a][1]);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const double ph[3] = {1.0 - c_tri6[q][0] - c_tri6[q][1], c_tri6[q][0], c_tri6[q][1]};
+        const double uq = u[0] * ph[0] + u[1] * ph[1] + u[2] * ph[2];
+        R += c_tri6[q][2] * a2 * (uq * uq * uq - f) * ph[a];
+    }
+    return R;
+}
+
+// entry a of the Nitsche vector of exterior facet l (as k_nlpoisson_p1_facet<OP_RES>)
+__device__ __forceinline__ double nlp_facet_res_entry(const Tri &T, int l, double beta, const double u[3], int a) {
+    const int la = (l == 0) ? 1 : 0, lb = (l == 2) ? 1 : 2;
+    const double tx = T.X[lb][0] - T.X[la][0], ty = T.X[lb][1] - T.X[la][1];
+    const double len = sqrt(tx * tx + ty * ty);
+    double nx = ty / len, ny = -tx / len;
+    if (nx * (T.X[la][0] - T.X[l][0]) + ny * (T.X[la][1] - T.X[l][1]) < 0.0) { nx = -nx; ny = -ny; }
+    double h2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int d = (c + 1) % 3;
+        const double dx = T.X[c][0] - T.X[d][0], dy = T.X[c][1] - T.X[d][1];
+        h2 = fmax(h2, dx * dx + dy * dy);
+    }
+    const double bh = beta / sqrt(h2);
+    double gn[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gn[c] = T.g[c][0] * nx + T.g[c][1] * ny;
+    const double dudn = u[0] * gn[0] + u[1] * gn[1] + u[2] * gn[2];
+    double R = 0.0;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const double s = c_gl5[q][0], w = c_gl5[q][1] * len;
+        double ph[3] = {0.0, 0.0, 0.0};
+        ph[la] = 1.0 - s;
+        ph[lb] = s;
+        const double uq = u[la] * (1.0 - s) + u[lb] * s;
+        const double ex = uex_nlp(T.X[la][0] + s * tx, T.X[la][1] + s * ty);
+        R += w * (-dudn * ph[a] + (ex - uq) * gn[a] + bh * (uq - ex) * ph[a]);
+    }
+    return R;
+}
+
+__global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_res(LatJacArgs A, LatGeom G, double *__restrict__ out) {
+    const int w = A.nx + 1;
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= (int64_t)w * (A.ny + 1)) return;
+    const int i = (int)(r % w), j = (int)(r / w);
+    const bool present[7] = {i > 0 && j > 0, j > 0, i > 0, true, i < A.nx, j < A.ny, i < A.nx && j < A.ny};
+    const int off[7] = {-w - 1, -w, -1, 0, 1, w, w + 1};
+    double u7[7];
+#pragma unroll
+    for (int s = 0; s < 7; ++s) u7[s] = present[s] ? __ldg(A.T.u + (r + off[s])) : 0.0;
+    constexpr int TRI[6][7] = {{0, 0, 0, 0, 3, 4, 6}, {0, 0, 1, 0, 3, 5, 6}, {-1, 0, 0, 1, 2, 3, 5},
+                               {0, -1, 1, 1, 1, 3, 4}, {-1, -1, 0, 2, 0, 1, 3}, {-1, -1, 1, 2, 0, 2, 3}};
+    double R = 0.0;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+        const int ci = i + TRI[t][0], cj = j + TRI[t][1];
+        if (ci < 0 || cj < 0 || ci >= A.nx || cj >= A.ny) continue;
+        const int up = TRI[t][2], a = TRI[t][3];
+        const int64_t c = 2 * ((int64_t)cj * A.nx + ci) + up;
+        const double u[3] = {u7[TRI[t][4]], u7[TRI[t][5]], u7[TRI[t][6]]};
+        R += nlp_cell_res_entry(up ? G.gu : G.gl, G.a2, u, __ldg(A.T.f + c), a);
+        const bool fb = !up && cj == 0 && A.ext_bottom, fr = !up && ci == A.nx - 1;
+        const bool fl = up && ci == 0, ft = up && cj == A.ny - 1 && A.ext_top;
+        if (fb || fr || fl || ft) {
+            Tri T;
+            tri_load(A.T, c, T);
+            if (fb || fl) R += nlp_facet_res_entry(T, 2, A.T.beta, u, a);
+            if (fr || ft) R += nlp_facet_res_entry(T, 0, A.T.beta, u, a);
+        }
+    }
+    out[r] = R;
 }
 
 }  // namespace femo

@@ -723,18 +723,36 @@ static int dia_convert(femo_problem *L) {
     return halo_nodes_f32(L, M.vals32 + (size_t)A.nd * A.np);
 }
 
-static int launch_dia(femo_problem *L, int mode, const double *x, double *y, const DiaEpi &E) {
-    int rc = halo_nodes(L, const_cast<double *>(mode == DIA_PRE2 ? E.b : x));
-    if (rc) return rc;
-    const DiaMat &A = L->mgl.dia;
-    const int g = grid_for(A.n);
-    cudaStream_t st = L->stream;
+static void dia_dispatch(int mode, const DiaMat &A, const double *x, double *y, const DiaEpi &E, int nrows, cudaStream_t st) {
+    const int g = grid_for(nrows);
     switch (mode) {
         case DIA_PLAIN: k_dia_apply<DIA_PLAIN, 7><<<g, kThreads, 0, st>>>(A, x, y, E); break;
         case DIA_CHEB0: k_dia_apply<DIA_CHEB0, 7><<<g, kThreads, 0, st>>>(A, x, y, E); break;
         case DIA_CHEBK: k_dia_apply<DIA_CHEBK, 7><<<g, kThreads, 0, st>>>(A, x, y, E); break;
         default: k_dia_apply<DIA_PRE2, 7><<<g, kThreads, 0, st>>>(A, x, y, E); break;
     }
+}
+
+static int launch_dia(femo_problem *L, int mode, const double *x, double *y, const DiaEpi &E) {
+    const DiaMat &A = L->mgl.dia;
+    double *in = const_cast<double *>(mode == DIA_PRE2 ? E.b : x);
+    int rc;
+    RowSplit R;
+    if (overlap_begin(L, in, R, &rc)) {
+        // slab level: boundary rows behind the exchange on the side stream, interior rows at once on the main stream
+        DiaEpi Eb = E, Ei = E;
+        Eb.a0 = R.b0; Eb.n0 = R.nb0; Eb.a1 = R.b1; Eb.n1 = R.nb1;
+        Ei.a0 = R.i0; Ei.n0 = R.ni; Ei.a1 = 0; Ei.n1 = 0;
+        dia_dispatch(mode, A, x, y, Eb, R.nb0 + R.nb1, L->stream2);
+        dia_dispatch(mode, A, x, y, Ei, R.ni, L->stream);
+        L->launches += 2;
+        L->dia_count[mode & 3]++;
+        FEMO_CHECK_LAUNCH();
+        return overlap_end(L);
+    }
+    if (rc) return rc;
+    if ((rc = halo_nodes(L, in))) return rc;
+    dia_dispatch(mode, A, x, y, E, (int)A.n, L->stream);
     L->launches++;
     L->dia_count[mode & 3]++;
     FEMO_CHECK_LAUNCH();
@@ -744,11 +762,28 @@ static int launch_dia(femo_problem *L, int mode, const double *x, double *y, con
 // y = A x (or bsub - A x) with the level's fp64 planes; DOT: fused partial sums of x.y over the owned rows
 template <bool DOT>
 static int launch_dia64(femo_problem *L, const double *x, double *y, const double *bsub, int *np_out) {
-    int rc = halo_nodes(L, const_cast<double *>(x));
-    if (rc) return rc;
     const DiaMat &A = L->mgl.dia;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(A.n), std::min<int64_t>((int64_t)L->num_sms * 8, kMaxPartials)));
-    k_dia_spmv64<DOT, 7><<<grid, kThreads, 0, L->stream>>>(L->mgl.dia64, A, x, y, bsub, L->own_off, L->own_off + L->own_n, L->d_partials);
+    const int64_t cap = std::min<int64_t>((int64_t)L->num_sms * 8, kMaxPartials - 64);
+    int rc;
+    RowSplit R;
+    if (overlap_begin(L, const_cast<double *>(x), R, &rc)) {
+        // interior partial sums first, the boundary launch's behind them: fixed layout => deterministic reduction
+        const int gi = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(R.ni), cap));
+        const int gb = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(R.nb0 + R.nb1), 64));
+        k_dia_spmv64<DOT, 7><<<gb, kThreads, 0, L->stream2>>>(L->mgl.dia64, A, x, y, bsub, L->own_off, L->own_off + L->own_n,
+                                                              L->d_partials + gi, R.b0, R.nb0, R.b1, R.nb1);
+        k_dia_spmv64<DOT, 7><<<gi, kThreads, 0, L->stream>>>(L->mgl.dia64, A, x, y, bsub, L->own_off, L->own_off + L->own_n,
+                                                             L->d_partials, R.i0, R.ni, 0, 0);
+        L->launches += 2;
+        if (np_out) *np_out = gi + gb;
+        FEMO_CHECK_LAUNCH();
+        return overlap_end(L);
+    }
+    if (rc) return rc;
+    if ((rc = halo_nodes(L, const_cast<double *>(x)))) return rc;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(A.n), cap));
+    k_dia_spmv64<DOT, 7><<<grid, kThreads, 0, L->stream>>>(L->mgl.dia64, A, x, y, bsub, L->own_off, L->own_off + L->own_n,
+                                                           L->d_partials, 0, -1, 0, 0);
     L->launches++;
     if (np_out) *np_out = grid;
     FEMO_CHECK_LAUNCH();
@@ -1052,7 +1087,9 @@ static int sync_replicated_bc(femo_problem *root) {
 }
 
 // (re)build the hierarchy for the matrix `vals` of the root at the root's current state
-static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true) {
+// level0_dia: the caller has just assembled `vals` with lattice_jacobian(..., with_dia = true): the fine level's DIA
+// planes, dinv and Gershgorin maximum are already in place
+static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true, bool level0_dia = false) {
     if (root->mg.empty()) return set_err(FEMO_ESTATE, "multigrid requested but femo_problem_enable_multigrid was not called before upload");
     const int nlev = (int)root->mg.size() + 1;
     int rc;
@@ -1063,6 +1100,7 @@ static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true) {
         femo_mg_level &M = L->mgl;
         cudaStream_t st = L->stream;
         const int64_t n = L->state.ndofs;
+        bool direct = lv == 0 && level0_dia && fp32 && dia_ready(L);     // DIA planes written by the assembly itself
         if (lv == 0) {
             M.vals = const_cast<double *>(vals);
         } else {
@@ -1120,11 +1158,17 @@ static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true) {
                 L->coef[1] = M.m;
                 L->coefn[1] = ncell;
             }
-            if ((rc = femo_assemble_jacobian(L, L->has_bc ? nullptr : M.vals, L->has_bc ? M.vals : nullptr))) return rc;
+            DiaMat tmp;
+            direct = fp32 && lv < nlev - 1 && L->lattice_fast && M.vals32 && dia_offsets(L, tmp) && !getenv("FEMO_NO_LATTICE_ASM");
+            if (direct) rc = lattice_jacobian(L, nullptr, nullptr, true, L->has_bc);      // no CSR values on DIA-only levels
+            else rc = femo_assemble_jacobian(L, L->has_bc ? nullptr : M.vals, L->has_bc ? M.vals : nullptr);
+            if (rc) return rc;
         }
         const DevPattern &D = L->dpat[0];
-        bool dia_setup = false;
-        if (fp32 && M.ec && M.k0 && L->coef[1] && lv < nlev - 1) {       // matrix-free V-cycle operator of this level
+        bool dia_setup = direct;
+        if (direct) {
+            // nothing to convert
+        } else if (fp32 && M.ec && M.k0 && L->coef[1] && lv < nlev - 1) {       // matrix-free V-cycle operator of this level
             const int64_t ncell = L->mesh.ncells;
             k_pow_cells<<<grid_for(ncell), kThreads, 0, st>>>(L->coef[1], L->params[4], M.ec, ncell);
             L->launches++;

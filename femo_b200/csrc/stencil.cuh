@@ -83,6 +83,10 @@ struct DiaEpi {
     double *rout = nullptr, *dout = nullptr, *xacc = nullptr;
     double c0 = 0.0, c1 = 0.0, c2 = 0.0;
     int xmode = 0;
+    // rows this launch covers: [a0, a0+n0) then [a1, a1+n1); n0 < 0 = all rows.  Slab problems split every operator
+    // application into the two lattice rows next to the ghost rows (launched behind the halo exchange on a second
+    // stream) and the interior (launched at once, overlapping the exchange).
+    int a0 = 0, n0 = -1, a1 = 0, n1 = 0;
 };
 
 // One thread per row, 32-bit index arithmetic (int32 dofs), and an interior fast path without per-neighbour range
@@ -93,7 +97,11 @@ __global__ void __launch_bounds__(kThreads)
     k_dia_apply(DiaMat A, const double *__restrict__ x, double *__restrict__ y, DiaEpi E) {
     constexpr int SD = D / 2;           // the diagonal sits in the middle plane (offsets are symmetric about 0)
     const int n = (int)A.n;
-    const int i = blockIdx.x * kThreads + threadIdx.x;
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    if (E.n0 >= 0) {                    // row selection (two segments)
+        if (i >= E.n0 + E.n1) return;
+        i = i < E.n0 ? E.a0 + i : E.a1 + (i - E.n0);
+    }
     if (i >= n) return;
     const float *__restrict__ v = A.v + i;
     const size_t np = (size_t)A.np;
@@ -155,11 +163,14 @@ __global__ void __launch_bounds__(kThreads)
 template <bool DOT, int D>
 __global__ void __launch_bounds__(kThreads)
     k_dia_spmv64(const double *__restrict__ planes, DiaMat A, const double *__restrict__ x, double *__restrict__ y,
-                 const double *__restrict__ b, int64_t o0, int64_t o1, double *__restrict__ partials) {
+                 const double *__restrict__ b, int64_t o0, int64_t o1, double *__restrict__ partials, int a0, int n0, int a1,
+                 int n1) {
     const int n = (int)A.n;
     const size_t np = (size_t)A.np;
     double dot = 0.0;
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const int total = n0 >= 0 ? n0 + n1 : n;
+    for (int t = blockIdx.x * kThreads + threadIdx.x; t < total; t += gridDim.x * kThreads) {
+        const int i = n0 < 0 ? t : (t < n0 ? a0 + t : a1 + (t - n0));
         double a[D];
 #pragma unroll
         for (int s = 0; s < D; ++s) a[s] = __ldcs(planes + s * np + i);

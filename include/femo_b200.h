@@ -222,6 +222,12 @@ int femo_filter_apply3(int device, void *stream, int nx, int ny, int nz, double 
 /* out = a * num / den (Vec.pointwiseDivide of the lumped projection, utils_dolfinx.py:566-569) */
 int femo_pointwise_divide(femo_problem *p, double a, const double *d_num, const double *d_den, double *d_out, int64_t n);
 
+/* Host-side bulk helpers for the API boundary (no device code): the femo callbacks assign and accumulate dense fp64
+ * numpy vectors (state_model.py:75-200); these run dst = alpha*src, dst += alpha*src and dst = value on all host cores. */
+void femo_host_scaled_copy(double *dst, const double *src, int64_t n, double alpha);
+void femo_host_axpy(double *dst, const double *src, int64_t n, double alpha);
+void femo_host_fill(double *dst, int64_t n, double value);
+
 typedef struct femo_krylov_opts {
     double rtol;      /* ||r|| <= rtol*||b||   */
     double atol;      /* or ||r|| <= atol      */

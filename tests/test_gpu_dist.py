@@ -26,7 +26,8 @@ def _run(script, args, port, extra):
     R = 2
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(R),
            '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', script)] + [str(a) for a in args]
-    env = dict(os.environ, FEMO_DIST_MIN_ROWS='16', **extra)     # several distributed levels even on these small meshes
+    # several distributed levels and the halo / interior overlap path even on these small meshes
+    env = dict(os.environ, FEMO_DIST_MIN_ROWS='16', FEMO_OVERLAP_MIN_ROWS='256', **extra)
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert 'OK' in out.stdout

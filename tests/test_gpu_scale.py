@@ -118,13 +118,16 @@ def test_node_centric_jacobian_matches_general_path(cuda_device, n, ny):
     c = Case(2, n, ny, seed=n, oracle=False)
     c.p.set_bc(square_boundary_lists(c.coords), None)
     v1, b1 = c.p.assemble_jacobian(plain=True, bc=True)
+    r1 = c.p.assemble_residual()
     os.environ['FEMO_NO_LATTICE_ASM'] = '1'
     try:
         v0, b0 = c.p.assemble_jacobian(plain=True, bc=True)
+        r0 = c.p.assemble_residual()
     finally:
         os.environ.pop('FEMO_NO_LATTICE_ASM', None)
     assert relerr(v1.cpu().numpy(), v0.cpu().numpy()) < 1e-13
     assert relerr(b1.cpu().numpy(), b0.cpu().numpy()) < 1e-13
+    assert relerr(r1.cpu().numpy(), r0.cpu().numpy()) < 1e-13
 
 
 def test_fused_output_and_gradient(cuda_device):
