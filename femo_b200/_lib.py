@@ -87,6 +87,7 @@ SIGNATURES = {
     'femo_problem_upload': (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t]),
     'femo_set_coefficient': (C.c_int, [_P, C.c_int, _P, C.c_int64]),
     'femo_problem_launch_count': (C.c_int, [_P, C.POINTER(C.c_longlong)]),
+    'femo_problem_graph_replays': (C.c_int, [_P, C.POINTER(C.c_longlong)]),
     'femo_assemble_residual': (C.c_int, [_P, _P]),
     'femo_assemble_jacobian': (C.c_int, [_P, _P, _P]),
     'femo_assemble_dRdm': (C.c_int, [_P, C.c_int, _P]),

@@ -24,6 +24,15 @@ int set_err(int code, const std::string &msg);
 
 #define FEMO_CHECK_LAUNCH() FEMO_CUDA(cudaGetLastError())
 
+// Environment switches (debug / test toggles) are looked up once per C-ABI call, not per kernel launch: getenv is a
+// linear scan of the environment and the solver enqueues a few thousand launches per step.
+struct EnvFlags {
+    bool no_dia = false, no_overlap = false, no_mgfused = false, no_lattice_asm = false, no_graph = false, force_graph = false;
+    long long overlap_min_rows = 1 << 20, mgfused_max_rows = 20000, graph_max_rows = 1 << 20;
+};
+extern EnvFlags g_env;
+void refresh_env();
+
 constexpr int kThreads = 256;
 constexpr int kMaxPartials = 4096;   // upper bound on CTAs of any reducing kernel
 constexpr int kMaxSlots = 12;
@@ -232,5 +241,6 @@ struct femo_problem {
     femo::MgOp *d_mgops = nullptr;
     std::vector<femo::MgOp> h_mgops;
     long long launches = 0;
+    long long graph_replays = 0;             // PCG iterations replayed from a captured CUDA graph
     long long dia_count[4] = {0, 0, 0, 0};   // launches of the DIA operator kernel on this level, by mode
 };

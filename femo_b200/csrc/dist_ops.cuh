@@ -19,10 +19,10 @@ static int link_halo(femo_problem *p, T *v, size_t send_lo, size_t recv_lo, size
                      size_t rlen_lo, size_t slen_hi, size_t rlen_hi, cudaStream_t st = nullptr) {
     if (!st) st = p->stream;
     const size_t mx = std::max(std::max(slen_lo, rlen_lo), std::max(slen_hi, rlen_hi));
-    if (mx * sizeof(T) > g_link.lay.halo_cap * sizeof(double))
+    if ((mx * sizeof(T) + 7) / 8 + 1 > g_link.lay.halo_cap)
         return set_err(FEMO_ELIMIT, "halo row exceeds the link window (femo_link_create halo capacity)");
     const int nch = link_chunks(mx);
-    const unsigned long long seq = ++g_link.seq;
+    const unsigned int seq = ++g_link.seq_halo;
     k_link_halo<T><<<2 * nch, kThreads, 0, st>>>(g_link.dev(), v, send_lo, recv_lo, send_hi, recv_hi, slen_lo, rlen_lo,
                                                          slen_hi, rlen_hi, nch, seq);
     p->launches++;
@@ -33,7 +33,7 @@ static int link_halo(femo_problem *p, T *v, size_t send_lo, size_t recv_lo, size
 
 static int link_allreduce(femo_problem *p, double *scalars, int count, bool is_max) {
     if (count > kLinkArMax) return set_err(FEMO_ELIMIT, "all-reduce of more than 16 scalars");
-    const unsigned long long seq = ++g_link.seq;
+    const unsigned int seq = ++g_link.seq_ar;
     k_link_allreduce<<<1, kThreads, 0, p->stream>>>(g_link.dev(), scalars, count, is_max ? 1 : 0, nullptr, nullptr, 0, 0, 0, seq);
     p->launches++;
     g_comm.allreduces++;
@@ -44,8 +44,8 @@ static int link_allreduce(femo_problem *p, double *scalars, int count, bool is_m
 static int link_gather(femo_problem *p, double *g, size_t blk, size_t tail) {
     const size_t total = blk * g_link.nranks + tail;
     if (total > g_link.lay.gather_cap) return set_err(FEMO_ELIMIT, "gathered level exceeds the link window (femo_link_create gather capacity)");
-    const unsigned long long seq = ++g_link.seq;
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((blk + tail + kThreads - 1) / kThreads, 64));
+    const unsigned int seq = ++g_link.seq_gather;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((blk + tail + kThreads - 1) / kThreads, 296));
     k_link_gather<<<grid, kThreads, 0, p->stream>>>(g_link.dev(), g, blk, tail, seq);
     p->launches++;
     FEMO_CHECK_LAUNCH();
@@ -86,10 +86,7 @@ static int halo_nodes(femo_problem *p, double *v, cudaStream_t st = nullptr) {
 // everything enqueued so far and runs the exchange there; the caller then launches the boundary rows on the side stream
 // and the interior rows on the main stream, and `overlap_end` joins.  Returns false when the level is not split
 // (one GPU, small level, ghost rows provably fresh) -- the caller then takes the plain path.
-static int64_t overlap_min_rows() {          // owned dofs below which a level is not split (FEMO_OVERLAP_MIN_ROWS overrides)
-    const char *e = getenv("FEMO_OVERLAP_MIN_ROWS");
-    return e ? atoll(e) : ((int64_t)1 << 18);
-}
+static int64_t overlap_min_rows() { return g_env.overlap_min_rows; }   // owned dofs below which a level is not split (FEMO_OVERLAP_MIN_ROWS)
 struct RowSplit {
     int b0 = 0, nb0 = 0, b1 = 0, nb1 = 0;   // boundary segments (first / last owned lattice row)
     int i0 = 0, ni = 0;                     // interior rows
@@ -97,7 +94,7 @@ struct RowSplit {
 static bool overlap_begin(femo_problem *p, double *v, RowSplit &R, int *rc) {
     *rc = FEMO_OK;
     const SlabInfo &s = p->slab;
-    if (!s.active || !g_comm.active || p->skip_next_halo || !p->stream2 || p->mesh.kind == MESH_HEX || getenv("FEMO_NO_OVERLAP")) return false;
+    if (!s.active || !g_comm.active || p->skip_next_halo || !p->stream2 || p->mesh.kind == MESH_HEX || g_env.no_overlap) return false;
     const int64_t len = (int64_t)(p->mesh.n[0] + 1) * p->state.block;
     const int64_t rows = s.own1 - s.own0;
     if (rows < 4 || rows * len < overlap_min_rows()) return false;

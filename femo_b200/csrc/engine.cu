@@ -13,12 +13,26 @@
 #include "families5.cuh"
 #include "families6.cuh"
 #include "families7.cuh"
+#include "families8.cuh"
 #include "lattice_asm.cuh"
 #include "dist.cuh"
 
 namespace femo {
 
 thread_local std::string g_err;
+EnvFlags g_env;
+void refresh_env() {
+    auto num = [](const char *name, long long dflt) { const char *e = getenv(name); return e ? atoll(e) : dflt; };
+    g_env.no_dia = getenv("FEMO_NO_DIA") != nullptr;
+    g_env.no_overlap = getenv("FEMO_NO_OVERLAP") != nullptr;
+    g_env.no_mgfused = getenv("FEMO_NO_MGFUSED") != nullptr;
+    g_env.no_lattice_asm = getenv("FEMO_NO_LATTICE_ASM") != nullptr;
+    g_env.no_graph = getenv("FEMO_NO_GRAPH") != nullptr;
+    g_env.force_graph = getenv("FEMO_GRAPH") != nullptr;
+    g_env.overlap_min_rows = num("FEMO_OVERLAP_MIN_ROWS", 1 << 20);
+    g_env.mgfused_max_rows = num("FEMO_MGFUSED_MAX_ROWS", 20000);
+    g_env.graph_max_rows = num("FEMO_GRAPH_MAX_ROWS", 1 << 20);
+}
 int set_err(int code, const std::string &msg) {
     g_err = msg;
     return code;
@@ -350,6 +364,7 @@ static inline int red_grid(const femo_problem *p, int64_t n) {
 
 static int need_device(femo_problem *p) {
     if (!p) return set_err(FEMO_EINVAL, "null problem");
+    refresh_env();
     if (!p->uploaded) return set_err(FEMO_ESTATE, "problem not uploaded to a CUDA device (femo_problem_upload); there is no CPU path");
     cudaError_t e = cudaSetDevice(p->device);
     if (e != cudaSuccess) return set_err(FEMO_ECUDA, cudaGetErrorString(e));
@@ -490,7 +505,7 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
     if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
     const bool analytic_src = p->family == FEMO_FAMILY_MASS_P1 && p->params[1] < 1.5;
     const bool jac_reads_input = p->family == FEMO_FAMILY_SIMP_Q1 || p->family == FEMO_FAMILY_EB_BEAM ||
-                                 p->family == FEMO_FAMILY_SIMP_HEX8 ||
+                                 p->family == FEMO_FAMILY_SIMP_HEX8 || p->family == FEMO_FAMILY_RM_PLATE ||
                                  p->family == FEMO_FAMILY_MOTOR_EM || p->family == FEMO_FAMILY_MOTOR_MM;
     if ((op != OP_JAC || jac_reads_input) && !analytic_src && (rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
     double *cells_out = p->d_scratch;
@@ -636,6 +651,36 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
                 A.T = tri_args(p, facets_out);
                 if (op == OP_RES) k_nlpoisson_p2_facet<OP_RES><<<gf, kThreads, 0, st>>>(A);
                 else k_nlpoisson_p2_facet<OP_JAC><<<gf, kThreads, 0, st>>>(A);
+                p->launches++;
+            }
+            break;
+        }
+        case FEMO_FAMILY_RM_PLATE: {
+            if ((rc = need_coef(p, 2, p->in[1].ndofs, "input 1 (load)"))) return rc;
+            RmArgs A;
+            A.edgesT = p->d_edgesT;
+            A.nverts = p->mesh.nverts; A.nedges = p->mesh.nedges;
+            A.t = p->coef[1]; A.f = p->coef[2];
+            A.E = p->params[0]; A.nu = p->params[1]; A.pen = p->params[2]; A.rho = p->params[3];
+            A.out_id = out_id; A.slot = out_id;           // OP_DRDM: out_id carries the input slot
+            const int g1 = (int)((nc + 127) / 128), g2 = (int)((std::max<int64_t>(nf, 1) + 127) / 128);
+            if (mask & 1) {
+                A.T = tri_args(p, cells_out);
+                switch (op) {
+                    case OP_RES: k_rm_plate_cell<OP_RES><<<g1, 128, 0, st>>>(A); break;
+                    case OP_JAC: k_rm_plate_cell<OP_JAC><<<g1, 128, 0, st>>>(A); break;
+                    case OP_DRDM: k_rm_plate_cell<OP_DRDM><<<g1, 128, 0, st>>>(A); break;
+                    case OP_OUT: k_rm_plate_cell<OP_OUT><<<g1, 128, 0, st>>>(A); break;
+                    case OP_OUT_DU: k_rm_plate_cell<OP_OUT_DU><<<g1, 128, 0, st>>>(A); break;
+                    case OP_OUT_DM: k_rm_plate_cell<OP_OUT_DM><<<g1, 128, 0, st>>>(A); break;
+                }
+                p->launches++;
+            }
+            if ((mask & 2) && nf > 0) {
+                A.T = tri_args(p, facets_out);
+                if (op == OP_RES) k_rm_plate_facet<OP_RES><<<g2, 128, 0, st>>>(A);
+                else if (op == OP_JAC) k_rm_plate_facet<OP_JAC><<<g2, 128, 0, st>>>(A);
+                else return set_err(FEMO_EINVAL, "RM plate family: the penalty facets carry residual and Jacobian terms only");
                 p->launches++;
             }
             break;
@@ -971,6 +1016,21 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
                     for (int64_t e = 0; e < M.nedges; ++e) { p->vedge[pos[M.edge_verts[2 * e]]++] = (int32_t)e; p->vedge[pos[M.edge_verts[2 * e + 1]]++] = (int32_t)e; }
                 }
                 break;
+            case FEMO_FAMILY_RM_PLATE:
+                if (M.kind != MESH_TRI) throw LayoutError{FEMO_EINVAL, "family needs a triangle mesh"};
+                p->mesh.build_edges();
+                p->state.init(M, EL_RMP, 1);
+                p->nin = 2;
+                p->in[0].init(M, EL_VERTEX, 1);                  // thickness (CG1)
+                p->in[1].init(M, EL_VERTEX, 1);                  // transverse load (CG1)
+                p->nout = 3;
+                if (nparams < 4) { p->params[0] = 1.0e4; p->params[1] = 0.3; p->params[2] = 1.0e8; p->params[3] = 1.0; }   // E, nu, pen, rho
+                p->res_mask = p->jac_mask = 3;                   // cells + penalty clamp on the facets of block 2
+                p->drdm_mask = 1;
+                p->out_mask[0] = 1; p->out_du_mask[0] = 1; p->out_dm_mask[0] = 0;   // compliance 1/2 int w^2
+                p->out_mask[1] = 1; p->out_du_mask[1] = 0; p->out_dm_mask[1] = 1;   // mass
+                p->out_mask[2] = 1; p->out_du_mask[2] = 1; p->out_dm_mask[2] = 1;   // elastic energy
+                break;
             case FEMO_FAMILY_SIMP_HEX8:
                 if (M.kind != MESH_HEX) throw LayoutError{FEMO_EINVAL, "family needs a hexahedral mesh"};
                 p->state.init(M, EL_VERTEX, 3);
@@ -993,7 +1053,8 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
                 p->fb_cell.push_back(fcell[k]);
                 p->fb_local.push_back(flocal[k]);
             }
-        } else if (family == FEMO_FAMILY_NLPOISSON_P1 || family == FEMO_FAMILY_NLPOISSON_P2 || family == FEMO_FAMILY_MOTOR_EM) {
+        } else if (family == FEMO_FAMILY_NLPOISSON_P1 || family == FEMO_FAMILY_NLPOISSON_P2 || family == FEMO_FAMILY_MOTOR_EM ||
+                   (family == FEMO_FAMILY_RM_PLATE && !tagged)) {
             p->fb_cell = M.bf_cell;
             p->fb_local = M.bf_local;
         } else {
@@ -1211,8 +1272,14 @@ static int enable_multigrid_slab(femo_problem *p) {
     int nx = p->mesh.n[0], gny = p->slab.gny;
     const int R = p->slab.nranks, rank = p->slab.rank;
     int rows = gny / R, rc;
-    const int kDistMinRows = dist_min_rows();
-    while (rows % 2 == 0 && nx % 2 == 0 && rows / 2 >= kDistMinRows && nx / 2 >= 2) {
+    // A distributed level costs ~5 neighbour synchronisations per V-cycle (about 13 us each, measured on 2 B200s:
+    // profiles/r02_summary.md), a replicated one costs its redundant arithmetic on every rank: levels stay distributed
+    // while their global lattice has more than ~600k nodes (FEMO_DIST_MIN_ROWS fixes the cut instead).
+    const bool fixed_cut = getenv("FEMO_DIST_MIN_ROWS") != nullptr;
+    const int kDistMinRows = fixed_cut ? dist_min_rows() : 2;
+    auto keep_distributed = [&](int cnx, int cgny) { return fixed_cut || (int64_t)(cnx + 1) * (cgny + 1) > 600000; };
+    while (rows % 2 == 0 && nx % 2 == 0 && rows / 2 >= kDistMinRows && nx / 2 >= 2 && (rows / 2) % 2 == 0 && (nx / 2) % 2 == 0 &&
+           keep_distributed(nx / 2, gny / 2)) {
         nx /= 2; gny /= 2; rows /= 2;
         femo_problem *c = nullptr;
         if ((rc = create_slab_problem(p->family, p->params, 32, nx, gny, p->mesh.lo, p->mesh.hi, rank, R, true, &c))) return rc;
@@ -1534,6 +1601,7 @@ static int upload_child(femo_problem *root, femo_problem *c, bool coarsest) {
 
 int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_t *work_bytes) {
     if (!p || !static_bytes || !work_bytes) return set_err(FEMO_EINVAL, "femo_problem_device_bytes: null");
+    refresh_env();
     const Mesh &M = p->mesh;
     const int64_t N = p->state.ndofs;
     size_t s = 0;
@@ -1542,6 +1610,7 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     s += Arena::need(2 * 49 * 4, 8);      // u_ex table
     if (p->state.element == EL_P2)
         s += Arena::need(M.cell_edges.size(), 4) + Arena::need(M.edge_verts.size(), 4) + Arena::need(p->vptr.size(), 4) + Arena::need(p->vedge.size(), 4);
+    if (p->state.element == EL_RMP) s += Arena::need(M.cell_edges.size(), 4);
     for (int w = 0; w <= p->nin; ++w) s += pattern_bytes(p->pat[w], w == 0);
     for (int m = 1; m < 4; ++m) s += vecmap_bytes(p->vm_state[m]);
     for (int i = 0; i < p->nin; ++i) s += vecmap_bytes(p->vm_in[i]);
@@ -1641,6 +1710,13 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
         if ((rc = up(p, p->d_uex_tab, tab))) return rc;
         FEMO_CUDA(cudaStreamSynchronize(p->stream));
     }
+    if (p->state.element == EL_RMP) {
+        std::vector<int32_t> T(M.cell_edges.size());
+        for (int64_t c = 0; c < M.ncells; ++c)
+            for (int a = 0; a < 3; ++a) T[a * M.ncells + c] = M.cell_edges[c * 3 + a];
+        if ((rc = up(p, p->d_edgesT, T))) return rc;
+        FEMO_CUDA(cudaStreamSynchronize(p->stream));
+    }
     if (p->state.element == EL_P2) {
         std::vector<int32_t> T(M.cell_edges.size());
         for (int64_t c = 0; c < M.ncells; ++c)
@@ -1710,6 +1786,8 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
             }
         }
         FEMO_CUDA(cudaMemcpyToSymbolAsync(c_tri6, tri6, sizeof(tri6), 0, cudaMemcpyHostToDevice, p->stream));
+        const double tri3[3][3] = {{1.0 / 6.0, 1.0 / 6.0, 1.0 / 6.0}, {1.0 / 6.0, 2.0 / 3.0, 1.0 / 6.0}, {2.0 / 3.0, 1.0 / 6.0, 1.0 / 6.0}};
+        FEMO_CUDA(cudaMemcpyToSymbolAsync(c_tri3, tri3, sizeof(tri3), 0, cudaMemcpyHostToDevice, p->stream));
         std::vector<double> x, w;
         gauss_legendre_01(5, x, w);
         double gl5[5][2];
@@ -1810,6 +1888,12 @@ int femo_problem_launch_count(const femo_problem *p, long long *count) {
     return FEMO_OK;
 }
 
+int femo_problem_graph_replays(const femo_problem *p, long long *count) {
+    if (!p || !count) return set_err(FEMO_EINVAL, "femo_problem_graph_replays: null");
+    *count = p->graph_replays;
+    return FEMO_OK;
+}
+
 // ---- multi-GPU communicator ------------------------------------------------
 int femo_comm_unique_id(char id[128]) {
     int rc = nccl_load();
@@ -1843,8 +1927,8 @@ int femo_link_create(int device, size_t halo_cap, size_t gather_cap, char handle
     if (femo_device_count() <= device || device < 0) return set_err(FEMO_ENODEVICE, "femo_link_create: no such CUDA device");
     if (g_link.local) return set_err(FEMO_ESTATE, "femo_link_create: window already created");
     FEMO_CUDA(cudaSetDevice(device));
-    g_link.lay.halo_cap = halo_cap ? halo_cap : ((size_t)1 << 20);
-    g_link.lay.gather_cap = gather_cap ? gather_cap : ((size_t)1 << 22);
+    g_link.lay.halo_cap = halo_cap ? halo_cap : ((size_t)1 << 18);       // 16-byte lines: 4 slots x 4 MB
+    g_link.lay.gather_cap = gather_cap ? gather_cap : ((size_t)1 << 21);   // 2 buffers x 32 MB
     const size_t bytes = g_link.lay.bytes();
     FEMO_CUDA(cudaMalloc((void **)&g_link.local, bytes));
     FEMO_CUDA(cudaMemset(g_link.local, 0, bytes));
@@ -1877,7 +1961,7 @@ int femo_link_open(const char *handles, int rank, int nranks) {
     }
     g_link.rank = rank;
     g_link.nranks = nranks;
-    g_link.seq = 0;
+    g_link.seq_halo = g_link.seq_ar = g_link.seq_gather = 0;
     g_link.active = nranks > 1;
     g_comm.rank = rank;
     g_comm.nranks = nranks;
@@ -1985,7 +2069,7 @@ int femo_assemble_residual(femo_problem *p, double *d_out) {
     int rc;
     if ((rc = need_device(p))) return rc;
     if (!d_out) return set_err(FEMO_EINVAL, "femo_assemble_residual: null output");
-    if (p->lattice_fast && p->res_mask == 3 && !getenv("FEMO_NO_LATTICE_ASM")) {
+    if (p->lattice_fast && p->res_mask == 3 && !g_env.no_lattice_asm) {
         if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
         if ((rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
         LatJacArgs A;
@@ -2016,7 +2100,7 @@ int femo_assemble_jacobian(femo_problem *p, double *d_vals, double *d_vals_bc) {
         FEMO_CHECK_LAUNCH();
         return FEMO_OK;
     }
-    if (p->lattice_fast && !getenv("FEMO_NO_LATTICE_ASM")) {   // right-diagonal lattice: node-centric rows, no scratch round trip
+    if (p->lattice_fast && !g_env.no_lattice_asm) {   // right-diagonal lattice: node-centric rows, no scratch round trip
         if ((rc = need_coef(p, 0, p->state.ndofs, "state"))) return rc;
         return lattice_jacobian(p, d_vals, d_vals_bc, false, false);
     }
@@ -2033,7 +2117,7 @@ int femo_assemble_dRdm(femo_problem *p, int slot, double *d_vals) {
     int rc;
     if ((rc = need_device(p))) return rc;
     if (slot < 0 || slot >= p->nin || !d_vals) return set_err(FEMO_EINVAL, "femo_assemble_dRdm: bad slot/output");
-    if ((rc = run_elements(p, OP_DRDM, p->drdm_mask))) return rc;
+    if ((rc = run_elements(p, OP_DRDM, p->drdm_mask, slot))) return rc;     // multi-input families read the slot
     const DevPattern &D = p->dpat[1 + slot];
     const int64_t nnz = p->pat[1 + slot].nnz;
     k_segreduce<<<grid_for(nnz), kThreads, 0, p->stream>>>(D.gptr, D.gsrc, p->d_scratch, d_vals, nnz);
@@ -2102,7 +2186,8 @@ int femo_assemble_output_grad(femo_problem *p, int out_id, int slot, double *d_o
     if ((rc = need_device(p))) return rc;
     if (out_id < 0 || out_id >= p->nout || !d_out || slot < 0 || slot > p->nin)
         return set_err(FEMO_EINVAL, "femo_assemble_output_grad: bad arguments");
-    const int mask = (slot == 0) ? p->out_du_mask[out_id] : p->out_dm_mask[out_id];
+    int mask = (slot == 0) ? p->out_du_mask[out_id] : p->out_dm_mask[out_id];
+    if (p->family == FEMO_FAMILY_RM_PLATE && slot == 2) mask = 0;          // no output depends on the load
     const int64_t n = (slot == 0) ? p->state.ndofs : p->in[slot - 1].ndofs;
     if (mask == 0) {   // the functional does not depend on this argument
         FEMO_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * n, p->stream));
@@ -2263,7 +2348,7 @@ int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton
     DiaMat dtmp;
     const bool lat_direct = p->lattice_fast && opts->krylov.precond == 2 && opts->krylov.mg_precision == 0 &&
                             opts->krylov.method == 0 && !p->mg.empty() && p->mgl.vals32 && dia_offsets(p, dtmp) &&
-                            !getenv("FEMO_NO_LATTICE_ASM");
+                            !g_env.no_lattice_asm;
     p->mgl.dinv = p->kr_dinv;
     auto eval_F = [&]() -> int {
         int r;

@@ -128,6 +128,9 @@ using namespace femo;
 
 static int cheb_setup(femo_problem *p, const double *vals);
 
+// fine-level rows up to which the PCG iteration is replayed as a CUDA graph (FEMO_GRAPH_MAX_ROWS overrides)
+static int64_t graph_max_rows() { return g_env.graph_max_rows; }
+
 static void default_krylov(femo_krylov_opts &o) {
     if (o.rtol <= 0) o.rtol = 1e-10;
     if (o.atol < 0) o.atol = 0;
@@ -139,7 +142,7 @@ static void default_krylov(femo_krylov_opts &o) {
 static int reduce_to(femo_problem *p, const double *pa, const double *pb, int np, int slotA, int slotB) {
     if (g_link.active && g_comm.active && p->slab.active && (!pb || slotB == slotA + 1)) {
         // block sums of the partials and the all-reduce over the ranks in ONE kernel (link.cuh)
-        const unsigned long long seq = ++g_link.seq;
+        const unsigned int seq = ++g_link.seq_ar;
         k_link_allreduce<<<1, kThreads, 0, p->stream>>>(g_link.dev(), p->d_scalars, pb ? 2 : 1, 0, pa, pb, np, slotA, slotB, seq);
         p->launches++;
         g_comm.allreduces++;
@@ -248,59 +251,110 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     const double tol = std::max(o.rtol * bnorm, o.atol);
     int it = 0;
     bool conv = rnorm <= tol;
-    while (!conv && it < o.max_it) {
+    // one PCG iteration: everything is enqueued on the stream with device-resident scalars, no host synchronisation
+    auto iteration = [&](bool first) -> int {
+        int r;
         if (pre != 0) {
             // z = M^-1 r ; rz' = r.z ; p = z + beta p
             if (pre == 3) {
                 k_dense_apply<<<(int)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(p->d_dense, p->kr_r, p->kr_z, (int)n);
                 p->launches++;
             } else if (pre == 1) {
-                if ((rc = mg_smooth(p, p->kr_r, p->kr_z, true, cdeg, cratio, false))) return rc;
-            } else if ((rc = mg_vcycle(p, 0, p->kr_r, p->kr_z, mp))) return rc;
+                if ((r = mg_smooth(p, p->kr_r, p->kr_z, true, cdeg, cratio, false))) return r;
+            } else if ((r = mg_vcycle(p, 0, p->kr_r, p->kr_z, mp))) return r;
             k_dot<<<go, kThreads, 0, st>>>(p->kr_r + p->own_off, p->kr_z + p->own_off, p->own_n, pa);
             p->launches++;
-            if ((rc = reduce_to(p, pa, nullptr, go, S_TMP0, 0))) return rc;
-            if ((rc = scalar_op(p, it == 0 ? 3 : 2))) return rc;
-            k_cg_dir<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_r, nullptr, p->kr_z, p->kr_p, n, it == 0);
+            if ((r = reduce_to(p, pa, nullptr, go, S_TMP0, 0))) return r;
+            if ((r = scalar_op(p, first ? 3 : 2))) return r;
+            k_cg_dir<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_r, nullptr, p->kr_z, p->kr_p, n, first);
             p->launches++;
-        } else if (it > 0) {
+        } else if (!first) {
             k_cg_dir<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_r, p->kr_dinv, nullptr, p->kr_p, n, 0);
             p->launches++;
         }
         // q = A p ; alpha = rz / p.q
         if (mf_outer) {
             SpmvEpi E0;
-            if ((rc = launch_hex_matfree(p, EPI_PLAIN, p->kr_p, p->kr_q, E0))) return rc;
+            if ((r = launch_hex_matfree(p, EPI_PLAIN, p->kr_p, p->kr_q, E0))) return r;
             k_dot<<<go, kThreads, 0, st>>>(p->kr_p + p->own_off, p->kr_q + p->own_off, p->own_n, p->d_partials);
             p->launches++;
             np = go;
         } else if (dia_outer) {
-            if ((rc = launch_dia64<true>(p, p->kr_p, p->kr_q, nullptr, &np))) return rc;
-        } else if ((rc = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, nullptr, &np))) return rc;
+            if ((r = launch_dia64<true>(p, p->kr_p, p->kr_q, nullptr, &np))) return r;
+        } else if ((r = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, nullptr, &np))) return r;
         ++spmvs;
-        if ((rc = reduce_to(p, p->d_partials, nullptr, np, S_PQ, 0))) return rc;
-        if ((rc = scalar_op(p, 0))) return rc;
+        if ((r = reduce_to(p, p->d_partials, nullptr, np, S_PQ, 0))) return r;
+        if ((r = scalar_op(p, 0))) return r;
         // x += alpha p ; r -= alpha q
         if (pre == 0) {
             k_cg_update<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_p, p->kr_q, p->kr_dinv, x, p->kr_r, n, o0, o1, pa, pb);
             p->launches++;
-            if ((rc = reduce_to(p, pa, pb, g, S_TMP0, S_TMP1))) return rc;
-            if ((rc = scalar_op(p, 1))) return rc;
+            if ((r = reduce_to(p, pa, pb, g, S_TMP0, S_TMP1))) return r;
+            if ((r = scalar_op(p, 1))) return r;
         } else {
             k_cg_update<<<g, kThreads, 0, st>>>(p->d_scalars, p->kr_p, p->kr_q, nullptr, x, p->kr_r, n, o0, o1, pa, pb);
             p->launches++;
-            if ((rc = reduce_to(p, pb, nullptr, g, S_RR, 0))) return rc;
+            if ((r = reduce_to(p, pb, nullptr, g, S_RR, 0))) return r;
+        }
+        FEMO_CHECK_LAUNCH();
+        return FEMO_OK;
+    };
+    // Launch-bound problems (every kernel of an iteration runs a few microseconds): the iteration body -- identical from
+    // the second iteration on -- is captured into a CUDA graph once per solve and replayed (K9 of SURVEY.md section 8a).
+    // One GPU only: the transport's kernels take a per-launch sequence number.
+    const bool use_graph = !g_comm.active && pre == 2 && !g_env.no_graph &&
+                           (n <= graph_max_rows() || g_env.force_graph);
+    cudaGraphExec_t gexec = nullptr;
+    long long body_launches = 0;
+    int body_spmvs = 0;
+    bool graph_failed = false;
+    while (!conv && it < o.max_it) {
+        if (it >= 1 && use_graph && !graph_failed) {
+            if (!gexec) {
+                const long long l0 = total_launches(p);
+                const int s0 = spmvs;
+                cudaGraph_t graph = nullptr;
+                bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                int brc = FEMO_OK;
+                if (ok) brc = iteration(false);
+                cudaError_t ce = ok ? cudaStreamEndCapture(st, &graph) : cudaErrorUnknown;
+                ok = ok && brc == FEMO_OK && ce == cudaSuccess && graph;
+                if (ok) ok = cudaGraphInstantiate(&gexec, graph, 0) == cudaSuccess;
+                if (graph) cudaGraphDestroy(graph);
+                body_launches = total_launches(p) - l0;
+                body_spmvs = spmvs - s0;
+                if (!ok) {           // not capturable on this driver: fall back to plain launches for good
+                    cudaGetLastError();
+                    graph_failed = true;
+                    gexec = nullptr;
+                    p->launches -= body_launches;
+                    spmvs = s0;
+                    continue;
+                }
+                p->launches -= body_launches;     // the capture pass did not execute anything
+                spmvs = s0;
+            }
+            FEMO_CUDA(cudaGraphLaunch(gexec, st));
+            p->launches += body_launches;
+            p->graph_replays++;
+            spmvs += body_spmvs;
+        } else if ((rc = iteration(it == 0))) {
+            if (gexec) cudaGraphExecDestroy(gexec);
+            return rc;
         }
         ++it;
-        FEMO_CHECK_LAUNCH();
         if (it % o.check_every == 0 || it >= o.max_it) {
             double rr;
-            if ((rc = read_scalars(p, S_RR, 1, &rr))) return rc;
+            if ((rc = read_scalars(p, S_RR, 1, &rr))) {
+                if (gexec) cudaGraphExecDestroy(gexec);
+                return rc;
+            }
             rnorm = std::sqrt(rr);
             if (!(rnorm == rnorm)) break;  // NaN
             conv = rnorm <= tol;
         }
     }
+    if (gexec) cudaGraphExecDestroy(gexec);
     if ((rc = halo_nodes(p, x))) return rc;   // hand back a solution that is valid on the ghost rows too
     if (info) {
         info->iterations = it;

@@ -286,6 +286,12 @@ void Space::init(const Mesh &m, int element_, int block_) {
         block = 1;
         ndofs = m.nverts + m.nedges;
         ndpc = 6;
+    } else if (element == EL_RMP) {
+        if (m.kind != MESH_TRI) throw LayoutError{FEMO_EINVAL, "Reissner-Mindlin plate spaces need a triangle mesh"};
+        if (m.cell_edges.empty()) throw LayoutError{FEMO_ESTATE, "RM plate space: mesh edges were not built"};
+        block = 1;
+        ndofs = 3 * m.nverts + m.nedges;
+        ndpc = 12;
     } else {
         if (element == EL_HERMITE3) block = 2;  // (value, reference derivative) per vertex
         ndofs = m.nverts * block;

@@ -16,7 +16,9 @@ namespace femo {
 
 enum MeshKind { MESH_INTERVAL = 1, MESH_TRI = 2, MESH_QUAD = 3, MESH_HEX = 4 };
 enum Element { EL_DG0 = 0, EL_VERTEX = 1 /* P1 / Q1: one node per vertex */, EL_HERMITE3 = 2,
-               EL_P2 = 3 /* triangles: vertex nodes then edge-midpoint nodes */ };
+               EL_P2 = 3 /* triangles: vertex nodes then edge-midpoint nodes */,
+               EL_RMP = 4 /* Reissner-Mindlin plate, mixed P2 (deflection) x P1^2 (rotations) on triangles:
+                             [w vertices | w edge midpoints | (theta_x, theta_y) per vertex], 12 dofs per cell */ };
 
 struct Mesh {
     int kind = 0, gdim = 0, nvpc = 0;
@@ -74,6 +76,8 @@ struct Space {
                 out[a] = m.cells[cell * 3 + a];
                 out[3 + a] = (int32_t)(m.nverts + m.cell_edges[cell * 3 + a]);
             }
+        } else if (element == EL_RMP) {
+            for (int a = 0; a < 12; ++a) out[a] = cell_dof(m, cell, a);
         } else {
             const int32_t *v = &m.cells[cell * m.nvpc];
             for (int a = 0; a < m.nvpc; ++a)
@@ -84,6 +88,11 @@ struct Space {
     inline int32_t cell_dof(const Mesh &m, int64_t cell, int a) const {
         if (element == EL_DG0) return (int32_t)(cell * block + a);
         if (element == EL_P2) return a < 3 ? m.cells[cell * 3 + a] : (int32_t)(m.nverts + m.cell_edges[cell * 3 + a - 3]);
+        if (element == EL_RMP) {
+            if (a < 3) return m.cells[cell * 3 + a];
+            if (a < 6) return (int32_t)(m.nverts + m.cell_edges[cell * 3 + a - 3]);
+            return (int32_t)(m.nverts + m.nedges + 2 * (int64_t)m.cells[cell * 3 + (a - 6) / 2] + (a - 6) % 2);
+        }
         return m.cells[cell * m.nvpc + a / block] * block + a % block;
     }
 };

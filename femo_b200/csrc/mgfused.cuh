@@ -147,10 +147,7 @@ using namespace femo;
 
 // ---- host side -----------------------------------------------------------------------------------------------
 // levels up to this many rows join the cooperative kernel (FEMO_MGFUSED_MAX_ROWS overrides; measured trade-off in DESIGN.md)
-static int64_t mgfused_max_rows() {
-    const char *e = getenv("FEMO_MGFUSED_MAX_ROWS");
-    return e ? atoll(e) : 20000;
-}
+static int64_t mgfused_max_rows() { return g_env.mgfused_max_rows; }
 
 static inline femo_problem *mg_level(femo_problem *root, int lv) { return lv == 0 ? root : root->mg[lv - 1]; }
 
@@ -161,7 +158,7 @@ static int mgfused_build(femo_problem *root, const MgParams &mp) {
     P.valid = false;
     P.dirty = false;
     const int nlev = (int)root->mg.size() + 1;
-    if (nlev < 2 || mp.degree != 2 || !mp.fp32 || !root->d_mgops || getenv("FEMO_NO_MGFUSED")) return FEMO_OK;
+    if (nlev < 2 || mp.degree != 2 || !mp.fp32 || !root->d_mgops || g_env.no_mgfused) return FEMO_OK;
     int coop = 0;
     FEMO_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, root->device));
     if (!coop) return FEMO_OK;

@@ -680,7 +680,7 @@ static inline bool dia_ready(const femo_problem *L) { return L->mgl.dia_valid; }
 // column offsets of a scalar vertex space on a right-diagonal triangle lattice: the node itself, its x / y
 // neighbours and the two ends of the cell diagonals
 static inline bool dia_offsets(const femo_problem *L, DiaMat &A) {
-    if (getenv("FEMO_NO_DIA")) return false;
+    if (g_env.no_dia) return false;
     if (!(L->mesh.lattice && L->mesh.kind == MESH_TRI && L->state.element == EL_VERTEX && L->state.block == 1)) return false;
     const int w = L->mesh.n[0] + 1;
     const int off[7] = {-w - 1, -w, -1, 0, 1, w, w + 1};
@@ -1159,7 +1159,7 @@ static int mg_setup(femo_problem *root, const double *vals, bool fp32 = true, bo
                 L->coefn[1] = ncell;
             }
             DiaMat tmp;
-            direct = fp32 && lv < nlev - 1 && L->lattice_fast && M.vals32 && dia_offsets(L, tmp) && !getenv("FEMO_NO_LATTICE_ASM");
+            direct = fp32 && lv < nlev - 1 && L->lattice_fast && M.vals32 && dia_offsets(L, tmp) && !g_env.no_lattice_asm;
             if (direct) rc = lattice_jacobian(L, nullptr, nullptr, true, L->has_bc);      // no CSR values on DIA-only levels
             else rc = femo_assemble_jacobian(L, L->has_bc ? nullptr : M.vals, L->has_bc ? M.vals : nullptr);
             if (rc) return rc;

@@ -20,6 +20,7 @@ FAMILY_MOTOR_MM = 6
 FAMILY_MOTOR_EM = 7
 FAMILY_SIMP_HEX8 = 8
 FAMILY_NLPOISSON_P2 = 9
+FAMILY_RM_PLATE = 10
 
 
 def device_count():
@@ -261,6 +262,11 @@ class EngineProblem:
     def launch_count(self):
         n = C.c_longlong()
         check(lib.femo_problem_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def graph_replays(self):
+        n = C.c_longlong()
+        check(lib.femo_problem_graph_replays(self._h, C.byref(n)))
         return n.value
 
     @staticmethod

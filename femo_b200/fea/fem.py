@@ -110,6 +110,11 @@ class FunctionSpace:
             if mesh.cell_type != 'triangle' or block != 1:
                 raise ValueError('femo_b200: CG2 kernels exist for scalar spaces on triangles')
             nnodes = mesh.num_vertices + mesh.edges()[0].shape[0]
+        elif family == 'RMPlate':
+            # mixed Reissner-Mindlin plate space: CG2 deflection, then CG1^2 rotations (forms/shell.py)
+            if mesh.cell_type != 'triangle':
+                raise ValueError('femo_b200: the RM plate space needs a triangle mesh')
+            nnodes, block = 3 * mesh.num_vertices + mesh.edges()[0].shape[0], 1
         elif (family, degree) == ('Hermite', 3):
             nnodes, block = mesh.num_vertices, 2
         else:
@@ -124,6 +129,10 @@ class FunctionSpace:
     def node_coordinates(self):
         if self.family == 'DG':
             return self.mesh.geometry.x[self.mesh.cells].mean(axis=1)
+        if self.family == 'RMPlate':                # w at vertices, w at edge midpoints, rotations at the vertices (x2)
+            ev = self.mesh.edges()[0]
+            X = self.mesh.geometry.x
+            return np.concatenate([X, 0.5 * (X[ev[:, 0]] + X[ev[:, 1]]), np.repeat(X, 2, axis=0)])
         if self.degree == 2:                       # vertices, then edge midpoints (engine's P2 numbering)
             ev = self.mesh.edges()[0]
             X = self.mesh.geometry.x

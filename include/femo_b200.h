@@ -48,6 +48,9 @@ typedef struct femo_problem femo_problem;
 #define FEMO_FAMILY_NLPOISSON_P2 9  /* config 2 with a quadratic Lagrange state (BASELINE.json configs[1] "P1/P2"); params alpha, beta */
 #define FEMO_FAMILY_SIMP_HEX8 8    /* 3-D extension of examples/beam_topo_opt/run_topo_opt_cantilever_beam.py:62-86 on trilinear hexahedra; params nu, fx, fy, fz, penal */
 #define FEMO_FAMILY_MOTOR_EM 7     /* examples/em_motor_opt/motor_pde.py:12-130,186-197 (nonlinear magnetostatics on a moving mesh) */
+#define FEMO_FAMILY_RM_PLATE 10     /* Reissner-Mindlin plate (flat case of examples/test_shell_m3l/shell_pde.py:219-311): CG2 deflection x CG1^2
+                                      rotations, reduced shear integration, penalty clamp; inputs thickness (CG1), load (CG1);
+                                      outputs compliance, mass, elastic energy; params E, nu, pen, rho */
 #define FEMO_FAMILY_MASS_P1 5      /* L2 projection, femo/fea/utils_dolfinx.py:549-583; params: target (0 CG1, 1 DG0),
                                       source (0 u_ex, 1 f_ex analytic; 2 DG0 input^power; 3 CG1 input), power */
 
@@ -173,6 +176,8 @@ int femo_set_coefficient(femo_problem *p, int slot, const double *d_values, int6
 
 /* number of kernels this problem has launched so far (bench.py's gpu_launches) */
 int femo_problem_launch_count(const femo_problem *p, long long *count);
+/* PCG iterations replayed from a captured CUDA graph so far (launch-bound problems, csrc/krylov.cuh) */
+int femo_problem_graph_replays(const femo_problem *p, long long *count);
 
 /* ---- assembly --------------------------------------------------------------*/
 /* assembleVector(residual_form): no BC applied (utils_dolfinx.py:175-179,

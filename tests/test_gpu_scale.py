@@ -159,3 +159,24 @@ def test_fused_coarse_vcycle_matches_per_level_kernels(cuda_device):
     assert res[0][1]['iterations'] == res[1][1]['iterations']
     assert relerr(res[0][0], res[1][0]) < 1e-10
     assert res[0][2] < res[1][2] / 2, (res[0][2], res[1][2])          # far fewer launches
+
+
+def test_cuda_graph_replay_matches_plain_launches(cuda_device):
+    """Launch-bound solves replay the PCG iteration from a captured CUDA graph (krylov.cuh): same iterates, bit for bit."""
+    res = []
+    for graph in (True, False):
+        if not graph:
+            os.environ['FEMO_NO_GRAPH'] = '1'
+        try:
+            c = Case(2, 160, 120, seed=2, mg=True, oracle=False)
+            c.set_state(0.1 * np.sin(2 * c.coords[:, 0]))
+            vals, _ = c.p.assemble_jacobian(plain=True, bc=False)
+            b = c.p.to_device(np.random.default_rng(9).standard_normal(c.p.N))
+            x, info = c.p.linear_solve(vals, b, rtol=1e-12, precond=2, cheb_degree=2)
+            res.append((x.cpu().numpy(), info, c.p.graph_replays()))
+        finally:
+            os.environ.pop('FEMO_NO_GRAPH', None)
+    assert res[0][1]['converged'] and res[0][1]['iterations'] == res[1][1]['iterations']
+    assert np.array_equal(res[0][0], res[1][0])
+    assert res[1][2] == 0
+    assert res[0][2] == res[0][1]['iterations'] - 1, res[0][2]        # every iteration after the first is a replay
