@@ -58,7 +58,8 @@ def test_partitioned_multigrid_needs_powers_of_two(monkeypatch):
     monkeypatch.setenv('FEMO_DIST_MIN_ROWS', '16')
     p = SlabProblem(2, 64, 128, 0, 2)
     assert p.enable_multigrid() >= 3
-    q = SlabProblem(2, 60, 100, 0, 2)                         # 50 rows per rank -> 25: cannot reach the replicated level
+    assert SlabProblem(2, 60, 100, 0, 2).enable_multigrid() >= 2   # 50 rows per rank: replicated from the 30 x 50 level on
+    q = SlabProblem(2, 60, 50, 0, 2)                          # 25 rows per rank: no 2:1 nested coarse level at all
     with pytest.raises(FemoError):
         q.enable_multigrid()
 
