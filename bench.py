@@ -46,8 +46,8 @@ def workload(n, kind='p1'):
         nx, ny, nz = n, n // 2, n // 4
         dofs = 3 * (nx + 1) * (ny + 1) * (nz + 1)
         return dict(workload='beam_topo_opt 3-D hexahedral SIMP cantilever %dx%dx%d (%d dofs, %d cells), Newton (3 fixed '
-                             'iterations, reference-faithful) + compliance adjoint, density 0.86*U[0,1) seed 0 clipped to '
-                             '[1e-3,1]' % (nx, ny, nz, dofs, nx * ny * nz), n=n, dofs=dofs, cells=nx * ny * nz,
+                             'iterations, reference-faithful) + compliance adjoint, density = cone filter (beta 2) of 0.86*random(nel), '
+                             'np.random.seed(0), bounds [1e-4,1]' % (nx, ny, nz, dofs, nx * ny * nz), n=n, dofs=dofs, cells=nx * ny * nz,
                     solver='NewtonSolver max_it=3; GMG-preconditioned CG rtol=%g replaces LU(MUMPS)' % KRYLOV_RTOL,
                     cache='working set exceeds the 126 MB L2; no explicit flush')
     return dict(workload='nonlinear_poisson_opt P1 unit square n=%d (%d dofs, %d cells), SNES + adjoint, f=0.1, u0=0'
@@ -158,11 +158,23 @@ class EngineStep:
         if kind == 'hex':
             import numpy as np
             nx, ny, nz = n, n // 2, n // 4
-            rho = np.clip(0.86 * np.random.default_rng(0).random(nx * ny * nz * world), 1e-3, 1.0)   # global field, seed 0
+            # the reference's initial design (run_topo_opt_cantilever_beam.py:175-180): np.random.seed(0),
+            # density_unfiltered = 0.86 * random(nel) within the design bounds [1e-4, 1], passed through the cone filter
+            # of the pre-processor (general_filter_model.py:67-90, beta = 2, h_avg = cell size) before it enters the PDE
+            import ctypes as C
+            from femo_b200._lib import lib, check
+            gnz = nz * world
+            np.random.seed(0)
+            unf = np.clip(0.86 * np.random.random(nx * ny * gnz), 1e-4, 1.0)
+            d_unf, d_rho, d_den = p.to_device(unf), p.new_vector(unf.size), p.new_vector(unf.size)
+            check(lib.femo_filter_apply3(device, C.c_void_p(torch.cuda.current_stream().cuda_stream), nx, ny, gnz, 2.0, 2.0, 2.0,
+                                         4.0, C.c_void_p(d_unf.data_ptr()), C.c_void_p(d_rho.data_ptr()),
+                                         C.c_void_p(d_den.data_ptr()), 0))
             if world > 1:
                 s = p.slab
-                rho = rho.reshape(nz * world, nx * ny)[s['crow0']:s['crow0'] + s['ncrows']].ravel()
-            self.f = p.to_device(np.ascontiguousarray(rho))
+                d_rho = d_rho.reshape(gnz, nx * ny)[s['crow0']:s['crow0'] + s['ncrows']].reshape(-1)
+            self.f = d_rho.contiguous().clone()
+            del d_unf, d_den
         else:
             self.f = p.new_vector(p.M[0], 0.1)
         p.set_coefficient(0, self.u)
@@ -264,6 +276,13 @@ def time_kernels(es, counts, steps, reps=50):
                             launches_per_step=counts[mode] / float(steps)))
     x = p.new_vector(p.N, 1.0)
     y = p.new_vector(p.N)
+    if es.kind == 'hex':      # the CG recurrence of 3-component states streams the 3x3-block copy of the values
+        vv = es.vals_bc if es.vals_bc is not None else es.vals
+        p.spmv_bsr3(vv, x, out=y, convert=True)
+        t = _time_launches(torch, lambda: p.spmv_bsr3(vv, x, out=y, convert=False), reps)
+        out.append(dict(kernel='femo::k_spmv_bsr3 (BSR-3 SpMV of the CG recurrence, fine-level Jacobian)', launch_ms=t * 1e3,
+                        algorithmic_bytes=8 * es.nnz + 4 * (es.nnz // 9) + 16 * p.N + 4 * (p.N // 3),
+                        launches_per_step=es.info.get('adjoint_its', 0) + 1.0))
     t = _time_launches(torch, lambda: p.spmv(0, es.vals, x, out=y), reps)
     out.append(dict(kernel='femo::k_spmv<double> (CSR-stream SpMV of the CG recurrence, fine-level Jacobian)',
                     launch_ms=t * 1e3, algorithmic_bytes=12 * es.nnz + 20 * p.N,
@@ -275,7 +294,7 @@ def time_kernels(es, counts, steps, reps=50):
 # API-level step (host buffers): the call a femo user makes
 # ---------------------------------------------------------------------------
 class ApiStep:
-    def __init__(self, n, degree=1):
+    def __init__(self, n, degree=1, pinned=True):
         import numpy as np
         from femo_b200.fea.fea_b200 import FEA, createUnitSquareMesh, FunctionSpace, Function, TestFunction
         from femo_b200.forms.nonlinear_poisson import pdeRes, outputForm
@@ -295,7 +314,7 @@ class ApiStep:
         fea.REPORT = False
         model = FEAModel(fea=[fea], debug_mode=False)
         model.create_input('f', shape=fea.inputs_dict['f']['shape'], val=0.1)
-        self.sim = Simulator(model)
+        self.sim = Simulator(model, pinned=pinned)
         self.f0 = np.full(fea.inputs_dict['f']['shape'], 0.1)
         self.u0 = np.zeros(fea.states_dict['u']['shape'])
         self.fam = res.fam
@@ -471,7 +490,30 @@ def main():
             dt = time.perf_counter() - t0
             quiet.__exit__(None, None, None)
             h2d, d2h = (prob.h2d_bytes - h0) // a.steps, (prob.d2h_bytes - d0) // a.steps
-            how = 'FEAModel + Simulator (numpy in/out)'
+            how = 'FEAModel + Simulator (numpy in/out; page-locked, version-tracked variable storage)'
+            # the same chain with plain pageable, untracked numpy variables (what python_csdl_backend hands over)
+            pageable = None
+            if a.workload == 'p1':
+                api = prob = None
+                torch.cuda.empty_cache()
+                api2 = ApiStep(a.n, 1, pinned=False)
+                quiet = contextlib.redirect_stdout(io.StringIO())
+                quiet.__enter__()
+                for _ in range(W):
+                    api2.step()
+                prob2 = api2.fam.problem
+                h0, d0 = prob2.h2d_bytes, prob2.d2h_bytes
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                for _ in range(a.steps):
+                    api2.step()
+                torch.cuda.synchronize()
+                dt2 = time.perf_counter() - t1
+                quiet.__exit__(None, None, None)
+                pageable = dict(value=a.steps / dt2, unit=UNIT, ms_per_step=dt2 * 1e3 / a.steps,
+                                h2d_bytes_per_step=int((prob2.h2d_bytes - h0) // a.steps),
+                                d2h_bytes_per_step=int((prob2.d2h_bytes - d0) // a.steps),
+                                path='FEAModel + Simulator with pageable, untracked numpy variables')
         else:
             # partitioned run: every rank feeds its slab of f from pinned host memory and reads back its
             # slab of the state, the gradient and J (the CSDL layer above is single-process in the reference)
@@ -503,6 +545,8 @@ def main():
         dt = float(td.item())
         e2e = dict(value=norm * a.steps / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                    ms_per_step=dt * 1e3 / a.steps, path=how)
+        if world == 1 and pageable is not None:
+            e2e['pageable'] = pageable
         es.info = info
 
     if rank == 0:

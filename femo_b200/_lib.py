@@ -97,6 +97,7 @@ SIGNATURES = {
     'femo_assemble_output_grad': (C.c_int, [_P, C.c_int, C.c_int, _P]),
     'femo_assemble_output_and_grad': (C.c_int, [_P, C.c_int, _DP, _P]),
     'femo_spmv': (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int]),
+    'femo_spmv_bsr3': (C.c_int, [_P, _P, _P, _P, C.c_int]),
     'femo_axpy': (C.c_int, [_P, C.c_double, _P, _P, C.c_int64]),
     'femo_filter_apply': (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, _P, C.c_int]),
     'femo_filter_apply3': (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, _P, C.c_int]),

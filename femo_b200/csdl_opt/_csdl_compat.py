@@ -123,6 +123,16 @@ except Exception:
     csdl = _Csdl()
 
 
+class _Plain(np.ndarray):
+    """Plain pageable variable storage (no version tracking): `bump` is a no-op so the simulator code is shared."""
+
+    def __new__(cls, a):
+        return np.asarray(a).view(cls)
+
+    def bump(self):
+        pass
+
+
 class Simulator:
     """python_csdl_backend.Simulator stand-in for models made of femo operations.
 
@@ -130,9 +140,12 @@ class Simulator:
     examples; `sim['submodel.var']` resolves by the last path component.
     """
 
-    def __init__(self, model, analytics=False, **kw):
+    def __init__(self, model, analytics=False, pinned=True, **kw):
+        """pinned=False keeps every variable in plain pageable, untracked numpy arrays -- what python_csdl_backend
+        hands to the operations -- instead of page-locked, version-tracked storage (bench.py reports both)."""
         model._ensure_defined()
         self.model = model
+        self.pinned = bool(pinned)
         self.vars = {k: self._store(np.asarray(v, dtype=np.float64)) for k, v in model.inputs.items()}
         for op, args, out in model.ops:
             for a in args:
@@ -145,9 +158,10 @@ class Simulator:
                 self.vars[out] = self._store(np.zeros(op.output_meta[out]['shape']))
         self._work = {}
 
-    @staticmethod
-    def _store(value):
+    def _store(self, value):
         """Variable storage: page-locked for large vectors so the operations' uploads are plain DMA."""
+        if not getattr(self, 'pinned', True):
+            return _Plain(np.array(value, dtype=np.float64, copy=True))
         buf = _H.pinned_empty(value.size).reshape(value.shape)
         np.copyto(buf, value)
         return _H.tracked(buf)
@@ -155,7 +169,7 @@ class Simulator:
     def _buffer(self, tag, like):
         buf = self._work.get(tag)
         if buf is None or buf.shape != like.shape:
-            buf = self._work[tag] = _H.pinned_empty(like.size).reshape(like.shape)
+            buf = self._work[tag] = (_H.pinned_empty(like.size) if self.pinned else np.empty(like.size)).reshape(like.shape)
         return buf
 
     def _scratch(self, tag, like):

@@ -27,7 +27,7 @@ int set_err(int code, const std::string &msg);
 // Environment switches (debug / test toggles) are looked up once per C-ABI call, not per kernel launch: getenv is a
 // linear scan of the environment and the solver enqueues a few thousand launches per step.
 struct EnvFlags {
-    bool no_dia = false, no_overlap = false, no_mgfused = false, no_lattice_asm = false, no_graph = false, force_graph = false;
+    bool no_bsr = false, no_dia = false, no_overlap = false, no_mgfused = false, no_lattice_asm = false, no_graph = false, force_graph = false;
     long long overlap_min_rows = 1 << 20, mgfused_max_rows = 20000, graph_max_rows = 1 << 20;
 };
 extern EnvFlags g_env;
@@ -83,6 +83,8 @@ struct DevPattern {
     uint8_t *bcflag = nullptr;
     int32_t *rb = nullptr, *t_rb = nullptr;  // SpMV row blocks
     int nrb = 0, t_nrb = 0;
+    int32_t *b_rowptr = nullptr, *b_col = nullptr, *b_perm = nullptr, *b_rb = nullptr;   // 3x3 block view (layout.hpp)
+    int nbrb = 0;
 };
 struct DevVecMap {
     int32_t *ptr = nullptr, *src = nullptr;
@@ -232,6 +234,7 @@ struct femo_problem {
     femo_mg_level mgl;
     femo_problem *parent = nullptr;
     double *kr_d = nullptr;
+    double *d_bvals = nullptr;               // values re-laid out as 3x3 blocks for the Krylov recurrence (BSR-3 SpMV)
     double *d_dense = nullptr, *d_dense_tmp = nullptr;   // explicit inverse for small systems (precond 3)
     double *gm_basis = nullptr;                          // GMRES Krylov basis, (restart+1) vectors
     double *d_partials_big = nullptr, *wk_extra = nullptr; // multi-dot partials; spare N-vector

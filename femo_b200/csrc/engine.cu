@@ -24,6 +24,9 @@ EnvFlags g_env;
 void refresh_env() {
     auto num = [](const char *name, long long dflt) { const char *e = getenv(name); return e ? atoll(e) : dflt; };
     g_env.no_dia = getenv("FEMO_NO_DIA") != nullptr;
+    // BSR-3 is opt-in for the Krylov recurrence: measured on B200 (hexahedra, 6.5M dofs) 1.32 ms against 1.20 ms of the
+    // CSR-stream kernel although it moves 29 % fewer bytes (latency-bound per block row; profiles/r02_summary.md)
+    g_env.no_bsr = getenv("FEMO_BSR") == nullptr || getenv("FEMO_NO_BSR") != nullptr;
     g_env.no_overlap = getenv("FEMO_NO_OVERLAP") != nullptr;
     g_env.no_mgfused = getenv("FEMO_NO_MGFUSED") != nullptr;
     g_env.no_lattice_asm = getenv("FEMO_NO_LATTICE_ASM") != nullptr;
@@ -272,6 +275,70 @@ __global__ void __launch_bounds__(kThreads)
     k_permute(const int32_t *__restrict__ perm, const double *__restrict__ in, double *__restrict__ out, int64_t n) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t < n) out[t] = in[perm[t]];
+}
+
+// ===========================================================================
+// BSR-3 SpMV (K7): vector states in 3-D couple nodes through complete 3x3 blocks, so one column index serves nine
+// values: 72 + 4 bytes per block = 8.44 bytes per entry instead of the 12 of scalar CSR.
+// Same CSR-stream scheme as k_spmv: a CTA owns consecutive block rows (<= kBsrBlocks blocks); phase 1 streams the
+// block values coalesced into shared memory, phase 2 forms the three row-products of every block (one thread per
+// (block, row)), phase 3 sums each scalar row over its blocks in a fixed order.  Optional fused dot(x, y).
+// ===========================================================================
+template <bool DOT>
+__global__ void __launch_bounds__(kThreads)
+    k_spmv_bsr3(int64_t nbrows, const int32_t *__restrict__ browptr, const int32_t *__restrict__ bcol,
+                const double *__restrict__ bvals, const double *__restrict__ x, double *__restrict__ y,
+                const double *__restrict__ bsub, int64_t own0, int64_t own1, double *__restrict__ partials) {
+    // One warp per block row (3 scalar rows, ~27 blocks = 243 contiguous values): lanes stream the values of the block
+    // row fully coalesced with 8 independent loads in flight, each value meets its x component (the three rows of a
+    // block share the x triple through the cache), three accumulators per lane, fixed butterfly => deterministic.
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * kThreads) >> 5;
+    double dot = 0.0;
+    for (int64_t I = warp; I < nbrows; I += nwarps) {
+        const int32_t s = __ldg(browptr + I), e = __ldg(browptr + I + 1);
+        const double *v = bvals + (int64_t)s * 9;
+        const int nv = (e - s) * 9;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int t0 = 0; t0 < nv; t0 += 32 * 4) {
+            double vv[4], xx[4];
+            int rr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = t0 + j * 32 + lane;
+                vv[j] = 0.0; xx[j] = 0.0; rr[j] = 0;
+                if (t < nv) {
+                    const int k = t / 9, q = t - 9 * k;
+                    rr[j] = q / 3;
+                    vv[j] = ld_stream(v + t);
+                    xx[j] = __ldg(x + 3 * (int64_t)__ldg(bcol + s + k) + (q - 3 * rr[j]));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double pr = vv[j] * xx[j];
+                a0 += rr[j] == 0 ? pr : 0.0;
+                a1 += rr[j] == 1 ? pr : 0.0;
+                a2 += rr[j] == 2 ? pr : 0.0;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (lane < 3) {
+            const double acc = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+            const int64_t row = 3 * I + lane;
+            y[row] = bsub ? bsub[row] - acc : acc;
+            if (DOT && row >= own0 && row < own1) dot += acc * __ldg(x + row);
+        }
+    }
+    if (DOT) {
+        dot = block_sum(dot);
+        if (threadIdx.x == 0) partials[blockIdx.x] = dot;
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -752,6 +819,30 @@ static int launch_spmv(femo_problem *p, const int32_t *rb, int nrb, const int32_
     return FEMO_OK;
 }
 
+// BSR-3 view of the dR/du values: re-layout once per solve, then every SpMV of the recurrence streams 8.44 B / entry
+static inline bool bsr3_ready(const femo_problem *p) { return p->dpat[0].b_perm && p->d_bvals && !g_env.no_bsr; }
+static int bsr3_convert(femo_problem *p, const double *vals) {
+    const int64_t nnz = p->pat[0].nnz;
+    k_permute<<<grid_for(nnz), kThreads, 0, p->stream>>>(p->dpat[0].b_perm, vals, p->d_bvals, nnz);
+    p->launches++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+template <bool DOT>
+static int launch_spmv_bsr3(femo_problem *p, const double *x, double *y, const double *bsub, int *np_out) {
+    int rc = halo_nodes(p, const_cast<double *>(x));
+    if (rc) return rc;
+    const DevPattern &D = p->dpat[0];
+    const int64_t nbrows = p->pat[0].nrows / 3;
+    const int grid = spmv_grid(p, (int)std::min<int64_t>((nbrows + 7) / 8, 1 << 30));
+    k_spmv_bsr3<DOT><<<grid, kThreads, 0, p->stream>>>(nbrows, D.b_rowptr, D.b_col, p->d_bvals, x, y, bsub, p->own_off,
+                                                       p->own_off + p->own_n, p->d_partials);
+    p->launches++;
+    if (np_out) *np_out = grid;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
 // SpMV on pattern 0 with a fused Chebyshev epilogue (multigrid smoother)
 template <class VT>
 static int launch_spmv_cheb(femo_problem *p, int kind, const VT *vals, const double *x, const SpmvEpi &E) {
@@ -1079,6 +1170,7 @@ static int create_problem_impl(const Mesh &mesh, int family, const double *param
         p->blk[2] = {facets};
         p->blk[3] = {cells, facets};
         build_pattern(M, p->state, p->state, p->blk[p->jac_mask], p->pat[0]);
+        if (!jac_only && p->state.element == EL_VERTEX && p->state.block == 3) build_bsr3(p->pat[0]);   // K7
         if (!jac_only) {  // coarse multigrid levels only ever assemble dR/du
             for (int s = 0; s < p->nin; ++s) build_pattern(M, p->state, p->in[s], p->blk[p->drdm_mask], p->pat[1 + s]);
             bool need[4] = {false, false, false, false};
@@ -1614,6 +1706,9 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     for (int w = 0; w <= p->nin; ++w) s += pattern_bytes(p->pat[w], w == 0);
     for (int m = 1; m < 4; ++m) s += vecmap_bytes(p->vm_state[m]);
     for (int i = 0; i < p->nin; ++i) s += vecmap_bytes(p->vm_in[i]);
+    if (!p->pat[0].b_perm.empty())
+        s += Arena::need(p->pat[0].b_rowptr.size(), 4) + Arena::need(p->pat[0].b_col.size(), 4) +
+             Arena::need(p->pat[0].b_perm.size(), 4) + Arena::need(p->pat[0].b_rb.size(), 4);
     s += Arena::need(N, 1) + 2 * Arena::need(N, 8) + Arena::need(N, 4);  // Dirichlet arrays (settable after upload)
     s += 4096;
     size_t scratch = 0, tv = 0;
@@ -1630,6 +1725,7 @@ int femo_problem_device_bytes(const femo_problem *p, size_t *static_bytes, size_
     w += 8 * Arena::need(N, 8);                    // r p q dinv z w b dx
     w += 2 * Arena::need(p->pat[0].nnz, 8);        // Newton's Jacobian values (plain, BC'd)
     w += Arena::need(tv, 8);                       // transposed values
+    if (!p->pat[0].b_perm.empty()) w += Arena::need(p->pat[0].nnz, 8);   // values as 3x3 blocks
     w += Arena::need(N, 8);                        // Chebyshev direction of multigrid level 0
     if (!p->mg.empty()) w += Arena::need(fp32_copy_len(p), 4);   // fp32 copy (CSR order or DIA planes)
     if (!p->mg.empty()) w += Arena::need(kMgFusedMaxOps, sizeof(MgOp));   // op list of the cooperative coarse V-cycle
@@ -1752,6 +1848,15 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
             D.t_nrb = (int)P.t_rb.size() - 1;
         }
     }
+    if (!p->pat[0].b_perm.empty()) {
+        const Pattern &P = p->pat[0];
+        DevPattern &D = p->dpat[0];
+        if ((rc = up(p, D.b_rowptr, P.b_rowptr))) return rc;
+        if ((rc = up(p, D.b_col, P.b_col))) return rc;
+        if ((rc = up(p, D.b_perm, P.b_perm))) return rc;
+        if ((rc = up(p, D.b_rb, P.b_rb))) return rc;
+        D.nbrb = (int)P.b_rb.size() - 1;
+    }
     for (int m = 1; m < 4; ++m) {
         if (p->vm_state[m].ptr.empty()) continue;
         if ((rc = up(p, p->dvm_state[m].ptr, p->vm_state[m].ptr))) return rc;
@@ -1844,6 +1949,7 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
     p->nt_vals = p->wk.take<double>(p->pat[0].nnz);
     p->nt_vals_bc = p->wk.take<double>(p->pat[0].nnz);
     p->d_tvals = p->wk.take<double>(tv);
+    if (!p->pat[0].b_perm.empty()) p->d_bvals = p->wk.take<double>(p->pat[0].nnz);
     p->kr_d = p->wk.take<double>(N);
     if (!p->mg.empty()) p->mgl.vals32 = p->wk.take<float>(fp32_copy_len(p));
     if (!p->mg.empty()) p->d_mgops = p->wk.take<MgOp>(kMgFusedMaxOps);
@@ -2247,6 +2353,17 @@ int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_
     p->launches++;
     FEMO_CHECK_LAUNCH();
     return launch_spmv<false>(p, D.t_rb, D.t_nrb, D.t_rowptr, D.t_col, p->d_tvals, d_x, d_y, nullptr, nullptr, false);
+}
+
+/* y = A x with the dR/du values re-laid out as 3x3 blocks (BSR-3, K7 of SURVEY.md section 8a); convert != 0 refreshes
+ * the block copy from d_vals first.  Only for states with 3 components per vertex (FEMO_ELIMIT otherwise). */
+int femo_spmv_bsr3(femo_problem *p, const double *d_vals, const double *d_x, double *d_y, int convert) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!d_x || !d_y || (convert && !d_vals)) return set_err(FEMO_EINVAL, "femo_spmv_bsr3: null pointer");
+    if (!p->dpat[0].b_perm || !p->d_bvals) return set_err(FEMO_ELIMIT, "femo_spmv_bsr3: the dR/du pattern is not made of complete 3x3 blocks");
+    if (convert && (rc = bsr3_convert(p, d_vals))) return rc;
+    return launch_spmv_bsr3<false>(p, d_x, d_y, nullptr, nullptr);
 }
 
 int femo_filter_apply3(int device, void *stream, int nx, int ny, int nz, double dx, double dy, double dz, double radius,

@@ -131,6 +131,33 @@ static int cheb_setup(femo_problem *p, const double *vals);
 // fine-level rows up to which the PCG iteration is replayed as a CUDA graph (FEMO_GRAPH_MAX_ROWS overrides)
 static int64_t graph_max_rows() { return g_env.graph_max_rows; }
 
+// Runs a solve on the problem's side stream: fork behind the caller's stream on construction, join on destruction.
+struct StreamSwap {
+    femo_problem *p;
+    cudaStream_t old = nullptr;
+    bool active = false;
+    StreamSwap(femo_problem *p_, bool on) : p(p_) {
+        if (!on || p->stream == p->stream2) return;
+        old = p->stream;
+        if (cudaEventRecord(p->ev_fork, old) != cudaSuccess || cudaStreamWaitEvent(p->stream2, p->ev_fork, 0) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        set(p->stream2);
+        active = true;
+    }
+    void set(cudaStream_t s) {
+        p->stream = s;
+        for (femo_problem *c : p->mg) c->stream = s;
+    }
+    ~StreamSwap() {
+        if (!active) return;
+        cudaEventRecord(p->ev_join, p->stream2);
+        cudaStreamWaitEvent(old, p->ev_join, 0);
+        set(old);
+    }
+};
+
 static void default_krylov(femo_krylov_opts &o) {
     if (o.rtol <= 0) o.rtol = 1e-10;
     if (o.atol < 0) o.atol = 0;
@@ -189,6 +216,10 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     const int pre = o.precond;
     const int64_t n = p->state.ndofs, o0 = p->own_off, o1 = p->own_off + p->own_n;
     const DevPattern &D = p->dpat[0];
+    // Launch-bound problems replay the PCG iteration from a CUDA graph (below).  The legacy default stream cannot be
+    // captured, so such a solve runs on the problem's own side stream, ordered after / before the caller's stream by events.
+    const bool use_graph = !g_comm.active && pre == 2 && !g_env.no_graph && (n <= graph_max_rows() || g_env.force_graph);
+    StreamSwap swap(p, use_graph && p->stream2);
     cudaStream_t st = p->stream;
     double *pa = p->d_partials, *pb = p->d_partials + kMaxPartials;
     const int g = red_grid(p, n), go = red_grid(p, p->own_n);
@@ -225,12 +256,16 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     if (pre == 2 && o.restart != 1 && (rc = mg_fmg(p, b, x, mp))) return rc;
     const bool mf_outer = op_current && pre == 2 && mp.fp32 && hex_matfree_ready(p);
     const bool dia_outer = pre == 2 && mp.fp32 && p->mgl.dia64_valid && dia_ready(p);     // fp64 planes of `vals` (set-up)
+    const bool bsr_outer = !mf_outer && !dia_outer && bsr3_ready(p);                     // vector states in 3-D: 3x3 blocks
+    if (bsr_outer && (rc = bsr3_convert(p, vals))) return rc;
     // r = b - A x
     if (mf_outer) {
         SpmvEpi E0;
         if ((rc = launch_hex_matfree(p, EPI_PLAIN, x, p->kr_q, E0))) return rc;
     } else if (dia_outer) {
         if ((rc = launch_dia64<false>(p, x, p->kr_q, nullptr, nullptr))) return rc;
+    } else if (bsr_outer) {
+        if ((rc = launch_spmv_bsr3<false>(p, x, p->kr_q, nullptr, nullptr))) return rc;
     } else if ((rc = launch_spmv<false>(p, D.rb, D.nrb, D.rowptr, D.col, vals, x, p->kr_q, nullptr, nullptr))) return rc;
     ++spmvs;
     if (pre == 0) {
@@ -281,6 +316,8 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
             np = go;
         } else if (dia_outer) {
             if ((r = launch_dia64<true>(p, p->kr_p, p->kr_q, nullptr, &np))) return r;
+        } else if (bsr_outer) {
+            if ((r = launch_spmv_bsr3<true>(p, p->kr_p, p->kr_q, nullptr, &np))) return r;
         } else if ((r = launch_spmv<true>(p, D.rb, D.nrb, D.rowptr, D.col, vals, p->kr_p, p->kr_q, nullptr, &np))) return r;
         ++spmvs;
         if ((r = reduce_to(p, p->d_partials, nullptr, np, S_PQ, 0))) return r;
@@ -302,8 +339,6 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     // Launch-bound problems (every kernel of an iteration runs a few microseconds): the iteration body -- identical from
     // the second iteration on -- is captured into a CUDA graph once per solve and replayed (K9 of SURVEY.md section 8a).
     // One GPU only: the transport's kernels take a per-launch sequence number.
-    const bool use_graph = !g_comm.active && pre == 2 && !g_env.no_graph &&
-                           (n <= graph_max_rows() || g_env.force_graph);
     cudaGraphExec_t gexec = nullptr;
     long long body_launches = 0;
     int body_spmvs = 0;

@@ -78,18 +78,34 @@ struct LatGeom {
     double a2;                   // |det J| = hx * hy
 };
 
-__device__ __forceinline__ void nlp_cell_jac_row_const(const double g[3][2], double a2, const double u[3], int a, double row[3]) {
+// Exact integrals of barycentric monomials on a triangle: int l0^m0 l1^m1 l2^m2 dx = |det J| m0! m1! m2! / (m0+m1+m2+2)!.
+// The degree-4 quadrature rule of the cell kernels integrates the quartic integrands u^2 phi_a phi_b and u^3 phi_a
+// exactly, so the closed forms below give the same element rows up to round-off at a third of the arithmetic.
+__host__ __device__ constexpr int tri_fact(int n) { return n <= 1 ? 1 : n * tri_fact(n - 1); }
+// 720 * int_ref (l_i l_j l_a l_b) / |det J| for vertex indices i, j, a, b in {0,1,2}
+__host__ __device__ constexpr int tri_quartic(int i, int j, int a, int b) {
+    const int m0 = (i == 0) + (j == 0) + (a == 0) + (b == 0), m1 = (i == 1) + (j == 1) + (a == 1) + (b == 1);
+    return tri_fact(m0) * tri_fact(m1) * tri_fact(4 - m0 - m1);
+}
+
+template <int a>
+__device__ __forceinline__ void nlp_cell_jac_row_const(const double g[3][2], double a2, const double u[3], double row[3]) {
+    const double u2[6] = {u[0] * u[0], u[1] * u[1], u[2] * u[2], u[0] * u[1], u[0] * u[2], u[1] * u[2]};
+    constexpr int PI[6] = {0, 1, 2, 0, 0, 1}, PJ[6] = {0, 1, 2, 1, 2, 2};
+    const double c = 3.0 * a2 / 720.0;
 #pragma unroll
-    for (int b = 0; b < 3; ++b) row[b] = 0.5 * a2 * (g[a][0] * g[b][0] + g[a][1] * g[b][1]);
+    for (int b = 0; b < 3; ++b) {
+        double m = 0.0;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {
-        const double ph[3] = {1.0 - c_tri6[q][0] - c_tri6[q][1], c_tri6[q][0], c_tri6[q][1]};
-        const double uq = u[0] * ph[0] + u[1] * ph[1] + u[2] * ph[2];
-        const double s = c_tri6[q][2] * a2 * 3.0 * uq * uq * ph[a];
-#pragma unroll
-        for (int b = 0; b < 3; ++b) row[b] += s * ph[b];
+        for (int p = 0; p < 6; ++p) m += (double)((PI[p] == PJ[p] ? 1 : 2) * tri_quartic(PI[p], PJ[p], a, b)) * u2[p];
+        row[b] = 0.5 * a2 * (g[a][0] * g[b][0] + g[a][1] * g[b][1]) + c * m;
     }
 }
+
+// the six triangles around a lattice node: cell offset (dx, dy), upper?, local index of the node in the triangle, and
+// the stencil slots {-w-1, -w, -1, 0, 1, w, w+1} of the triangle's three vertices
+__device__ constexpr int kNodeTri[6][7] = {{0, 0, 0, 0, 3, 4, 6}, {0, 0, 1, 0, 3, 5, 6}, {-1, 0, 0, 1, 2, 3, 5},
+                                           {0, -1, 1, 1, 1, 3, 4}, {-1, -1, 0, 2, 0, 1, 3}, {-1, -1, 1, 2, 0, 2, 3}};
 
 // optional extra outputs of the node-centric Jacobian: the row directly in the layouts the multigrid-preconditioned
 // Krylov solve consumes (stencil.cuh) -- 7 fp32 planes + the fp32 Jacobi scaling plane for the V-cycle, 7 fp64 planes
@@ -100,6 +116,28 @@ struct LatDiaOut {
     int64_t np = 0, o0 = 0, o1 = 0;
     int use_bc = 0;             // the level matrix is the BC'd copy (rows / columns of Dirichlet dofs replaced)
 };
+
+// contribution of incident triangle T (compile-time: local index and slots fold into the closed-form coefficients)
+template <int T>
+__device__ __forceinline__ void node_jac_tri(const LatJacArgs &A, const LatGeom &G, int i, int j, const double u7[7], double v[7]) {
+    constexpr int up = kNodeTri[T][2], a = kNodeTri[T][3], s0 = kNodeTri[T][4], s1 = kNodeTri[T][5], s2 = kNodeTri[T][6];
+    const int ci = i + kNodeTri[T][0], cj = j + kNodeTri[T][1];
+    if (ci < 0 || cj < 0 || ci >= A.nx || cj >= A.ny) return;
+    const double u[3] = {u7[s0], u7[s1], u7[s2]};
+    double row[3];
+    nlp_cell_jac_row_const<a>(up ? G.gu : G.gl, G.a2, u, row);
+    const bool fb = !up && cj == 0 && A.ext_bottom, fr = !up && ci == A.nx - 1;
+    const bool fl = up && ci == 0, ft = up && cj == A.ny - 1 && A.ext_top;
+    if (fb || fr || fl || ft) {      // boundary triangle: Nitsche facet rows with the cell's own geometry
+        Tri Tg;
+        tri_load(A.T, 2 * ((int64_t)cj * A.nx + ci) + up, Tg);
+        if (fb || fl) nlp_facet_jac_row(Tg, 2, A.T.beta, a, row);
+        if (fr || ft) nlp_facet_jac_row(Tg, 0, A.T.beta, a, row);
+    }
+    v[s0] += row[0];
+    v[s1] += row[1];
+    v[s2] += row[2];
+}
 
 __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A, LatGeom G, LatDiaOut O) {
     const int w = A.nx + 1;
@@ -117,29 +155,12 @@ __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A
         u7[s] = present[s] ? __ldg(A.T.u + (r + off[s])) : 0.0;
         v[s] = 0.0;
     }
-    // incident triangles: cell offset, upper?, local index of this node, stencil slots of the triangle's vertices
-    constexpr int TRI[6][7] = {{0, 0, 0, 0, 3, 4, 6}, {0, 0, 1, 0, 3, 5, 6}, {-1, 0, 0, 1, 2, 3, 5},
-                               {0, -1, 1, 1, 1, 3, 4}, {-1, -1, 0, 2, 0, 1, 3}, {-1, -1, 1, 2, 0, 2, 3}};
-#pragma unroll
-    for (int t = 0; t < 6; ++t) {
-        const int ci = i + TRI[t][0], cj = j + TRI[t][1];
-        if (ci < 0 || cj < 0 || ci >= A.nx || cj >= A.ny) continue;
-        const int up = TRI[t][2], a = TRI[t][3];
-        const double u[3] = {u7[TRI[t][4]], u7[TRI[t][5]], u7[TRI[t][6]]};
-        double row[3];
-        nlp_cell_jac_row_const(up ? G.gu : G.gl, G.a2, u, a, row);
-        const bool fb = !up && cj == 0 && A.ext_bottom, fr = !up && ci == A.nx - 1;
-        const bool fl = up && ci == 0, ft = up && cj == A.ny - 1 && A.ext_top;
-        if (fb || fr || fl || ft) {      // boundary triangle: Nitsche facet rows with the cell's own geometry
-            Tri T;
-            tri_load(A.T, 2 * ((int64_t)cj * A.nx + ci) + up, T);
-            if (fb || fl) nlp_facet_jac_row(T, 2, A.T.beta, a, row);
-            if (fr || ft) nlp_facet_jac_row(T, 0, A.T.beta, a, row);
-        }
-        v[TRI[t][4]] += row[0];
-        v[TRI[t][5]] += row[1];
-        v[TRI[t][6]] += row[2];
-    }
+    node_jac_tri<0>(A, G, i, j, u7, v);
+    node_jac_tri<1>(A, G, i, j, u7, v);
+    node_jac_tri<2>(A, G, i, j, u7, v);
+    node_jac_tri<3>(A, G, i, j, u7, v);
+    node_jac_tri<4>(A, G, i, j, u7, v);
+    node_jac_tri<5>(A, G, i, j, u7, v);
     // CSR positions: the row holds the present slots in ascending column order
     int32_t pos = A.rowptr[r];
     double sabs = 0.0, diag = 1.0;
@@ -184,17 +205,28 @@ __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A
 
 // ---- residual rows, same node-centric scheme --------------------------------------------------------------------
 // entry a of the cell vector  int grad(u).grad(phi_a) + (u^3 - f) phi_a dx  (as k_nlpoisson_p1_cell<OP_RES>)
-__device__ __forceinline__ double nlp_cell_res_entry(const double g[3][2], double a2, const double u[3], double f, int a) {
+template <int a>
+__device__ __forceinline__ double nlp_cell_res_entry(const double g[3][2], double a2, const double u[3], double f) {
     const double gu0 = u[0] * g[0][0] + u[1] * g[1][0] + u[2] * g[2][0];
     const double gu1 = u[0] * g[0][1] + u[1] * g[1][1] + u[2] * g[2][1];
-    double R = 0.5 * a2 * (gu0 * g[a][0] + gu1 * g[a][1]);
+    // int u^3 phi_a dx = |det J| / 720 * sum_{i,j,k} u_i u_j u_k * tri_quartic(i, j; k, a): contract j,k first
+    double m = 0.0;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {
-        const double ph[3] = {1.0 - c_tri6[q][0] - c_tri6[q][1], c_tri6[q][0], c_tri6[q][1]};
-        const double uq = u[0] * ph[0] + u[1] * ph[1] + u[2] * ph[2];
-        R += c_tri6[q][2] * a2 * (uq * uq * uq - f) * ph[a];
+    for (int i = 0; i < 3; ++i) {
+        double mi = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double mij = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int m0 = (i == 0) + (j == 0) + (k == 0) + (a == 0), m1 = (i == 1) + (j == 1) + (k == 1) + (a == 1);
+                mij += (double)(tri_fact(m0) * tri_fact(m1) * tri_fact(4 - m0 - m1)) * u[k];
+            }
+            mi += mij * u[j];
+        }
+        m += mi * u[i];
     }
-    return R;
+    return 0.5 * a2 * (gu0 * g[a][0] + gu1 * g[a][1]) + a2 * (m / 720.0 - f / 6.0);
 }
 
 // entry a of the Nitsche vector of exterior facet l (as k_nlpoisson_p1_facet<OP_RES>)
@@ -230,6 +262,25 @@ __device__ __forceinline__ double nlp_facet_res_entry(const Tri &T, int l, doubl
     return R;
 }
 
+template <int T>
+__device__ __forceinline__ double node_res_tri(const LatJacArgs &A, const LatGeom &G, int i, int j, const double u7[7]) {
+    constexpr int up = kNodeTri[T][2], a = kNodeTri[T][3];
+    const int ci = i + kNodeTri[T][0], cj = j + kNodeTri[T][1];
+    if (ci < 0 || cj < 0 || ci >= A.nx || cj >= A.ny) return 0.0;
+    const int64_t c = 2 * ((int64_t)cj * A.nx + ci) + up;
+    const double u[3] = {u7[kNodeTri[T][4]], u7[kNodeTri[T][5]], u7[kNodeTri[T][6]]};
+    double R = nlp_cell_res_entry<a>(up ? G.gu : G.gl, G.a2, u, __ldg(A.T.f + c));
+    const bool fb = !up && cj == 0 && A.ext_bottom, fr = !up && ci == A.nx - 1;
+    const bool fl = up && ci == 0, ft = up && cj == A.ny - 1 && A.ext_top;
+    if (fb || fr || fl || ft) {
+        Tri Tg;
+        tri_load(A.T, c, Tg);
+        if (fb || fl) R += nlp_facet_res_entry(Tg, 2, A.T.beta, u, a);
+        if (fr || ft) R += nlp_facet_res_entry(Tg, 0, A.T.beta, u, a);
+    }
+    return R;
+}
+
 __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_res(LatJacArgs A, LatGeom G, double *__restrict__ out) {
     const int w = A.nx + 1;
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -240,26 +291,13 @@ __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_res(LatJacArgs A
     double u7[7];
 #pragma unroll
     for (int s = 0; s < 7; ++s) u7[s] = present[s] ? __ldg(A.T.u + (r + off[s])) : 0.0;
-    constexpr int TRI[6][7] = {{0, 0, 0, 0, 3, 4, 6}, {0, 0, 1, 0, 3, 5, 6}, {-1, 0, 0, 1, 2, 3, 5},
-                               {0, -1, 1, 1, 1, 3, 4}, {-1, -1, 0, 2, 0, 1, 3}, {-1, -1, 1, 2, 0, 2, 3}};
     double R = 0.0;
-#pragma unroll
-    for (int t = 0; t < 6; ++t) {
-        const int ci = i + TRI[t][0], cj = j + TRI[t][1];
-        if (ci < 0 || cj < 0 || ci >= A.nx || cj >= A.ny) continue;
-        const int up = TRI[t][2], a = TRI[t][3];
-        const int64_t c = 2 * ((int64_t)cj * A.nx + ci) + up;
-        const double u[3] = {u7[TRI[t][4]], u7[TRI[t][5]], u7[TRI[t][6]]};
-        R += nlp_cell_res_entry(up ? G.gu : G.gl, G.a2, u, __ldg(A.T.f + c), a);
-        const bool fb = !up && cj == 0 && A.ext_bottom, fr = !up && ci == A.nx - 1;
-        const bool fl = up && ci == 0, ft = up && cj == A.ny - 1 && A.ext_top;
-        if (fb || fr || fl || ft) {
-            Tri T;
-            tri_load(A.T, c, T);
-            if (fb || fl) R += nlp_facet_res_entry(T, 2, A.T.beta, u, a);
-            if (fr || ft) R += nlp_facet_res_entry(T, 0, A.T.beta, u, a);
-        }
-    }
+    R += node_res_tri<0>(A, G, i, j, u7);
+    R += node_res_tri<1>(A, G, i, j, u7);
+    R += node_res_tri<2>(A, G, i, j, u7);
+    R += node_res_tri<3>(A, G, i, j, u7);
+    R += node_res_tri<4>(A, G, i, j, u7);
+    R += node_res_tri<5>(A, G, i, j, u7);
     out[r] = R;
 }
 

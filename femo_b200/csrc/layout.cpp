@@ -466,6 +466,45 @@ void build_pattern(const Mesh &m, const Space &rs, const Space &cs, const std::v
     if (!out.square_symmetric) build_rowblocks(out.t_rowptr, out.ncols, out.t_rb);
 }
 
+void build_bsr3(Pattern &P) {
+    P.b_rowptr.clear(); P.b_col.clear(); P.b_perm.clear(); P.b_rb.clear();
+    if (P.nrows != P.ncols || P.nrows % 3 != 0 || P.nnz % 9 != 0) return;
+    const int64_t nb = P.nrows / 3;
+    std::vector<int32_t> brp(nb + 1, 0), bcol, bperm;
+    bcol.reserve(P.nnz / 9);
+    bperm.reserve(P.nnz);
+    for (int64_t I = 0; I < nb; ++I) {
+        const int32_t s0 = P.rowptr[3 * I], s1 = P.rowptr[3 * I + 1], s2 = P.rowptr[3 * I + 2], e2 = P.rowptr[3 * I + 3];
+        const int32_t len = s1 - s0;
+        if (len % 3 != 0 || s2 - s1 != len || e2 - s2 != len) return;          // rows of a triple must match
+        for (int32_t k = 0; k < len; k += 3) {
+            const int32_t c = P.col[s0 + k];
+            if (c % 3 != 0) return;
+            for (int r = 0; r < 3; ++r) {
+                const int32_t base = P.rowptr[3 * I + r] + k;
+                for (int j = 0; j < 3; ++j) {
+                    if (P.col[base + j] != c + j) return;                       // incomplete block: keep CSR only
+                    bperm.push_back(base + j);
+                }
+            }
+            bcol.push_back(c / 3);
+        }
+        if (len / 3 > kBsrBlocks) return;                                      // a block row must fit one CTA
+        brp[I + 1] = (int32_t)bcol.size();
+    }
+    P.b_rowptr = std::move(brp);
+    P.b_col = std::move(bcol);
+    P.b_perm = std::move(bperm);
+    P.b_rb.push_back(0);
+    int64_t r = 0;
+    while (r < nb) {
+        int64_t e = r + 1;
+        while (e < nb && e - r < kBsrRows && P.b_rowptr[e + 1] - P.b_rowptr[r] <= kBsrBlocks) ++e;
+        P.b_rb.push_back((int32_t)e);
+        r = e;
+    }
+}
+
 void build_rowblocks(const std::vector<int32_t> &rowptr, int64_t nrows, std::vector<int32_t> &rb) {
     rb.clear();
     rb.push_back(0);

@@ -120,7 +120,15 @@ struct Pattern {
     std::vector<int32_t> t_perm;           // transposed entry tt takes vals[t_perm[tt]]
     // SpMV row blocks: block k covers rows [rb[k], rb[k+1]) with <= kSpmvCap nnz and <= kSpmvRows rows
     std::vector<int32_t> rb, t_rb;
+    // 3x3 block view of a square pattern whose rows / columns come in complete node triples (vector states in 3-D):
+    // block row I has blocks b_rowptr[I] .. b_rowptr[I+1], block k couples node I with node b_col[k]; its 9 values
+    // (row-major) are the CSR values at b_perm[9k .. 9k+9).  b_rb: CTA work units (<= kBsrBlocks blocks each).
+    std::vector<int32_t> b_rowptr, b_col, b_perm, b_rb;
 };
+constexpr int kBsrBlocks = 224;   // 3x3 blocks staged per CTA (224 * 72 B = 15.75 KB of values)
+constexpr int kBsrRows = 64;      // block rows per CTA
+// fills the BSR view of `p` (no-op unless the pattern is made of complete 3x3 blocks)
+void build_bsr3(Pattern &p);
 
 constexpr int kSpmvCap = 2048;   // products staged in shared memory per row block
 constexpr int kSpmvRows = 512;   // rows per block (row pointers staged too)

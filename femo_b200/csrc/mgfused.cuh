@@ -238,6 +238,11 @@ static int mgfused_vcycle(femo_problem *root, int lv, const double *b, double *x
     int rc;
     if (P.dirty && (rc = mgfused_build(root, mp))) return rc;
     if (!P.valid || lv < P.k0 || lv >= P.nlev - 1 || mp.degree != 2 || !mp.fp32) return FEMO_OK;
+    {   // inside a stream capture (CUDA-graph replay of the PCG iteration) the per-level kernels are recorded instead:
+        // a cooperative launch is not capturable, and a graph has no launch overhead to save anyway
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(root->stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return FEMO_OK;
+    }
     femo_problem *L = mg_level(root, lv);
     // ops of the first level of the (sub-)program take b / x from the launch; deeper starts must match the level's own vectors
     int first = 3 * (lv - P.k0), count = P.nops - 6 * (lv - P.k0);

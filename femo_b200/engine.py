@@ -333,6 +333,12 @@ class EngineProblem:
         check(lib.femo_vcycle_op_probe(self._h, int(mode), info))
         return int(info[0]), int(info[1])
 
+    def spmv_bsr3(self, vals, x, out=None, convert=True):
+        """y = A x through the 3x3-block copy of the dR/du values (3-component vertex states)."""
+        out = self.new_vector(self.N) if out is None else out
+        check(lib.femo_spmv_bsr3(self._h, self._p(vals), self._p(x), self._p(out), 1 if convert else 0))
+        return out
+
     def axpy(self, a, x, y):
         check(lib.femo_axpy(self._h, float(a), self._p(x), self._p(y), x.numel()))
         return y

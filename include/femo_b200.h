@@ -211,6 +211,11 @@ int femo_assemble_output_and_grad(femo_problem *p, int out_id, double *h_value, 
  * y = A x (transpose=0) or y = A^T x (transpose=1). */
 int femo_spmv(femo_problem *p, int which, const double *d_vals, const double *d_x, double *d_y, int transpose);
 
+/* The same product with the values re-laid out as 3x3 blocks (BSR-3: one column index per nine values, 8.44 instead of
+ * 12 bytes per entry; what the CG recurrence streams for vector states in 3-D).  convert != 0 refreshes the block
+ * copy from d_vals first. */
+int femo_spmv_bsr3(femo_problem *p, const double *d_vals, const double *d_x, double *d_y, int convert);
+
 /* y += a x on the problem's stream (the d_inputs accumulation of
  * compute_jacvec_product, state_model.py:180-199, kept on the device). */
 int femo_axpy(femo_problem *p, double a, const double *d_x, double *d_y, int64_t n);

@@ -91,3 +91,13 @@ def relerr(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     den = np.max(np.abs(b))
     return np.max(np.abs(a - b)) / (den if den > 0 else 1.0)
+
+
+def relerr_entry(a, b, floor=1e-9):
+    """ENTRYWISE relative error max_i |a_i - b_i| / max(|b_i|, floor * max|b|): BASELINE.json asks for assembled values
+    within 1e-12 relative; entries that are (near) zero through exact cancellation are measured against floor * max|b|."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if b.size == 0:
+        return 0.0
+    den = np.maximum(np.abs(b), floor * max(np.max(np.abs(b)), 1e-300))
+    return float(np.max(np.abs(a - b) / den))

@@ -203,3 +203,25 @@ def test_hex_general_element_kernels(cuda_device, monkeypatch):
     x2, i2 = c.p.linear_solve(vb, c.p.to_device(b), rtol=1e-11, precond=2, max_it=300, mg_precision=1)
     assert i1['converged'] and i2['converged'] and abs(i1['iterations'] - i2['iterations']) <= 2
     assert relerr(x1.cpu().numpy(), x2.cpu().numpy()) < 1e-8
+
+
+def test_hex_bsr3_spmv_and_solve(cuda_device, monkeypatch):
+    """BSR-3 (K7): the 3x3-block copy of the hexahedral dR/du values gives the CSR product, and the CG recurrence that
+    streams it converges to the same solution in the same number of iterations as the scalar-CSR recurrence."""
+    from _cases34 import csr, _upload
+    c = HexCase(12, 7, 5, seed=5, upload=False)
+    c.p.enable_multigrid()
+    _upload(c)
+    _, vb = c.p.assemble_jacobian(plain=False, bc=True)
+    A = csr(c, 0, vb)
+    x = np.random.default_rng(3).standard_normal(c.F.N)
+    y = c.p.spmv_bsr3(vb, c.p.to_device(x)).cpu().numpy()
+    assert relerr(y, A @ x) < 1e-13
+    b = np.random.default_rng(4).standard_normal(c.F.N)
+    b[c.bc.dofs] = 0.0
+    monkeypatch.setenv('FEMO_BSR', '1')                     # opt-in: the recurrence streams the 3x3-block copy
+    x1, i1 = c.p.linear_solve(vb, c.p.to_device(b), rtol=1e-11, precond=2, max_it=300)
+    monkeypatch.delenv('FEMO_BSR')
+    x0, i0 = c.p.linear_solve(vb, c.p.to_device(b), rtol=1e-11, precond=2, max_it=300)
+    assert i1['converged'] and i0['converged'] and i1['iterations'] == i0['iterations']
+    assert relerr(x1.cpu().numpy(), x0.cpu().numpy()) < 1e-9

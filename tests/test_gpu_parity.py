@@ -7,7 +7,7 @@ import pytest
 import scipy.sparse.linalg as spla
 
 from oracle import assembly as asm
-from _cases import Case, relerr
+from _cases import Case, relerr, relerr_entry
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -27,6 +27,11 @@ def test_assembly_matches_oracle(cuda_device, famid, n, ny):
     assert relerr(vals_bc.cpu().numpy(), Abc.data) < TOL
     D = asm.assemble_matrix(F.dRdm(0, c.u, *m), (F.N, F.M), None)
     assert relerr(p.assemble_dRdm(0).cpu().numpy(), D.data) < TOL
+    # entrywise (not max-norm) relative agreement of every assembled value
+    assert relerr_entry(R, asm.assemble_vector(F.residual(c.u, *m), F.N)) < 1e-11
+    assert relerr_entry(vals.cpu().numpy(), A.data) < 1e-11
+    assert relerr_entry(vals_bc.cpu().numpy(), Abc.data) < 1e-11
+    assert relerr_entry(p.assemble_dRdm(0).cpu().numpy(), D.data) < 1e-12
     J = p.assemble_output(0)
     Jo = asm.assemble_scalar(F.output(0, c.u, *m))
     assert abs(J - Jo) <= TOL * abs(Jo)

