@@ -204,6 +204,7 @@ struct femo_problem {
     double *d_uex_tab = nullptr;   // angle-addition table of the analytic u_ex on uniform lattices (families 2, 9)
     int32_t *d_edgesT = nullptr, *d_edge_verts = nullptr, *d_vptr = nullptr, *d_vedge = nullptr;
     std::vector<int32_t> vptr, vedge;
+    std::vector<double> h_uex_tab;   // host copy of the u_ex angle-addition table (copied to constant memory before its kernels)
     std::vector<double> h_k0;    // hexahedral lattices: host copy of the unit element matrix (kernel parameter of the matrix-free operator)
     femo::DevPattern dpat[5];
     femo::DevVecMap dvm_state[4], dvm_in[4];

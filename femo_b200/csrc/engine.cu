@@ -550,6 +550,13 @@ static int setup_hex_matfree(femo_problem *root, femo_problem *L) {
     return FEMO_OK;
 }
 
+// the analytic-u_ex table of THIS problem into constant memory, stream-ordered before the kernel that reads it
+static int push_uex_table(femo_problem *p) {
+    if (p->h_uex_tab.size() == 2 * 49 * 4)
+        FEMO_CUDA(cudaMemcpyToSymbolAsync(c_uex49, p->h_uex_tab.data(), sizeof(double) * 2 * 49 * 4, 0, cudaMemcpyHostToDevice, p->stream));
+    return FEMO_OK;
+}
+
 // number of scratch planes per entity of an op
 static int op_planes(const femo_problem *p, int op) {
     const int nd = p->state.ndpc;
@@ -597,6 +604,7 @@ static int run_elements(femo_problem *p, int op, int mask, int out_id = 0) {
             break;
         }
         case FEMO_FAMILY_NLPOISSON_P1: {
+            if ((op == OP_OUT || op == OP_OUT_DU) && (rc = push_uex_table(p))) return rc;
             if (mask & 1) {
                 TriArgs A = tri_args(p, cells_out);
                 FEMO_LAUNCH_OPS(k_nlpoisson_p1_cell, gc, A)
@@ -1805,6 +1813,7 @@ int femo_problem_upload(femo_problem *p, int device, void *stream, void *d_stati
                 }
         if ((rc = up(p, p->d_uex_tab, tab))) return rc;
         FEMO_CUDA(cudaStreamSynchronize(p->stream));
+        p->h_uex_tab = tab;
     }
     if (p->state.element == EL_RMP) {
         std::vector<int32_t> T(M.cell_edges.size());
@@ -2322,6 +2331,7 @@ int femo_assemble_output_and_grad(femo_problem *p, int out_id, double *h_value, 
     if ((rc = need_coef(p, 1, p->in[0].ndofs, "input 0"))) return rc;
     const int64_t nc = p->mesh.ncells;
     if ((size_t)(4 * nc) > p->scratch_len) return set_err(FEMO_ESTATE, "scratch too small for the fused functional pass");
+    if ((rc = push_uex_table(p))) return rc;
     TriArgs A = tri_args(p, p->d_scratch);
     k_nlpoisson_p1_cell<OP_OUT_BOTH><<<grid_for(nc), kThreads, 0, p->stream>>>(A);
     p->launches++;

@@ -17,6 +17,10 @@ namespace femo {
 __constant__ double c_tri6[6][3];     // degree-4 rule: xi, eta, w   (sum w = 1/2)
 __constant__ double c_gl5[5][2];      // 5-pt Gauss-Legendre on [0,1]: s, w
 __constant__ double c_tri49[49][3];   // collapsed 7x7 Gauss rule, degree 12
+// angle-addition table of the analytic u_ex on the current problem's uniform lattice (refreshed before every launch that
+// reads it): [triangle type][point] = cos(2 pi dx), sin(2 pi dx), cos(pi dy), sin(pi dy).  With the point loop fully
+// unrolled and one code path per triangle type every entry is a constant-bank operand of an FMA (no load instructions).
+__constant__ double c_uex49[2][49][4];
 
 struct TriArgs {
     const double *coords;    // (nverts,2) AoS
@@ -222,6 +226,31 @@ __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_cell(TriArgs A) {
         for (int a = 0; a < 3; ++a)
 #pragma unroll
             for (int b = 0; b < 3; ++b) A.out[(a * 3 + b) * ne + c] = K[a][b];
+    } else if (A.uex_tab) {  // OP_OUT / OP_OUT_DU on a uniform lattice: u_ex by angle addition from the constant table
+        double val = 0.0, ge[3] = {0.0, 0.0, 0.0};
+        double S0, C0, S1, C1;
+        sincospi(2.0 * T.X[0][0], &S0, &C0);
+        sincospi(T.X[0][1], &S1, &C1);
+        const bool upper = T.X[1][1] != T.X[0][1];          // lower [v0,v1,v3] or upper [v0,v2,v3] triangle (warp-uniform)
+#define FEMO_OUT49(TY)                                                                                              \
+        _Pragma("unroll") for (int q = 0; q < 49; ++q) {                                                            \
+            const double ph1 = c_tri49[q][0], ph2 = c_tri49[q][1], ph0 = 1.0 - ph1 - ph2;                           \
+            const double ex = (S0 * c_uex49[TY][q][0] + C0 * c_uex49[TY][q][1]) * (S1 * c_uex49[TY][q][2] + C1 * c_uex49[TY][q][3]); \
+            const double eq = u[0] * ph0 + u[1] * ph1 + u[2] * ph2 - ex;                                            \
+            const double w = c_tri49[q][2] * T.a2;                                                                  \
+            val += w * 0.5 * eq * eq;                                                                               \
+            ge[0] += w * eq * ph0; ge[1] += w * eq * ph1; ge[2] += w * eq * ph2;                                    \
+        }
+        if (upper) { FEMO_OUT49(1) } else { FEMO_OUT49(0) }
+#undef FEMO_OUT49
+        if (OP == OP_OUT || OP == OP_OUT_BOTH) {
+            const double f = A.f[c];
+            A.out[(OP == OP_OUT_BOTH ? 3 * ne : 0) + c] = val + 0.5 * T.a2 * 0.5 * A.alpha * f * f;
+        }
+        if (OP == OP_OUT_DU || OP == OP_OUT_BOTH) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) A.out[a * ne + c] = ge[a];
+        }
     } else {  // OP_OUT / OP_OUT_DU : degree-12 rule, u_ex evaluated at the points
         double val = 0.0, ge[3] = {0.0, 0.0, 0.0};
         const UexCell U = uex_cell(A, T);

@@ -40,7 +40,7 @@ __device__ __forceinline__ void nlp_cell_jac_row(const Tri &T, const double u[3]
 }
 
 // row a of the symmetric-Nitsche matrix of exterior facet l (opposite local vertex l), as k_nlpoisson_p1_facet<OP_JAC>
-__device__ __forceinline__ void nlp_facet_jac_row(const Tri &T, int l, double beta, int a, double row[3]) {
+__device__ __noinline__ void nlp_facet_jac_row(const Tri &T, int l, double beta, int a, double row[3]) {
     const int la = (l == 0) ? 1 : 0, lb = (l == 2) ? 1 : 2;
     const double tx = T.X[lb][0] - T.X[la][0], ty = T.X[lb][1] - T.X[la][1];
     const double len = sqrt(tx * tx + ty * ty);
@@ -81,23 +81,20 @@ struct LatGeom {
 // Exact integrals of barycentric monomials on a triangle: int l0^m0 l1^m1 l2^m2 dx = |det J| m0! m1! m2! / (m0+m1+m2+2)!.
 // The degree-4 quadrature rule of the cell kernels integrates the quartic integrands u^2 phi_a phi_b and u^3 phi_a
 // exactly, so the closed forms below give the same element rows up to round-off at a third of the arithmetic.
-__host__ __device__ constexpr int tri_fact(int n) { return n <= 1 ? 1 : n * tri_fact(n - 1); }
-// 720 * int_ref (l_i l_j l_a l_b) / |det J| for vertex indices i, j, a, b in {0,1,2}
-__host__ __device__ constexpr int tri_quartic(int i, int j, int a, int b) {
-    const int m0 = (i == 0) + (j == 0) + (a == 0) + (b == 0), m1 = (i == 1) + (j == 1) + (a == 1) + (b == 1);
-    return tri_fact(m0) * tri_fact(m1) * tri_fact(4 - m0 - m1);
-}
-
+// kQuartJac[a][b][p]: 720 / |det J| * (coefficient of the p-th product of {u0u0, u1u1, u2u2, u0u1, u0u2, u1u2} in
+// int u^2 phi_a phi_b dx); kQuartRes[a][m]: the same for the m-th cubic monomial u_i u_j u_k (i <= j <= k, lexicographic)
+// in int u^3 phi_a dx.  Indexed with compile-time constants only (fully unrolled loops): folded into immediates.
+__device__ constexpr double kQuartJac[3][3][6] = {{{24.0, 4.0, 4.0, 12.0, 12.0, 4.0}, {6.0, 6.0, 2.0, 8.0, 4.0, 4.0}, {6.0, 2.0, 6.0, 4.0, 8.0, 4.0}}, {{6.0, 6.0, 2.0, 8.0, 4.0, 4.0}, {4.0, 24.0, 4.0, 12.0, 4.0, 12.0}, {2.0, 6.0, 6.0, 4.0, 4.0, 8.0}}, {{6.0, 2.0, 6.0, 4.0, 8.0, 4.0}, {2.0, 6.0, 6.0, 4.0, 4.0, 8.0}, {4.0, 4.0, 24.0, 4.0, 12.0, 12.0}}};
+__device__ constexpr double kQuartRes[3][10] = {{24.0, 18.0, 18.0, 12.0, 12.0, 12.0, 6.0, 6.0, 6.0, 6.0}, {6.0, 12.0, 6.0, 18.0, 12.0, 6.0, 24.0, 18.0, 12.0, 6.0}, {6.0, 6.0, 12.0, 6.0, 12.0, 18.0, 6.0, 12.0, 18.0, 24.0}};
 template <int a>
 __device__ __forceinline__ void nlp_cell_jac_row_const(const double g[3][2], double a2, const double u[3], double row[3]) {
     const double u2[6] = {u[0] * u[0], u[1] * u[1], u[2] * u[2], u[0] * u[1], u[0] * u[2], u[1] * u[2]};
-    constexpr int PI[6] = {0, 1, 2, 0, 0, 1}, PJ[6] = {0, 1, 2, 1, 2, 2};
     const double c = 3.0 * a2 / 720.0;
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
         double m = 0.0;
 #pragma unroll
-        for (int p = 0; p < 6; ++p) m += (double)((PI[p] == PJ[p] ? 1 : 2) * tri_quartic(PI[p], PJ[p], a, b)) * u2[p];
+        for (int p = 0; p < 6; ++p) m = fma(kQuartJac[a][b][p], u2[p], m);
         row[b] = 0.5 * a2 * (g[a][0] * g[b][0] + g[a][1] * g[b][1]) + c * m;
     }
 }
@@ -117,6 +114,15 @@ struct LatDiaOut {
     int use_bc = 0;             // the level matrix is the BC'd copy (rows / columns of Dirichlet dofs replaced)
 };
 
+// boundary triangles (O(perimeter) of them): the Nitsche facet rows with the cell's own geometry, kept out of line so
+// that the interior path of the node kernels stays a few hundred instructions
+__device__ __noinline__ void node_facet_jac(const TriArgs &A, int64_t cell, int first, int second, int a, double row[3]) {
+    Tri Tg;
+    tri_load(A, cell, Tg);
+    if (first) nlp_facet_jac_row(Tg, 2, A.beta, a, row);
+    if (second) nlp_facet_jac_row(Tg, 0, A.beta, a, row);
+}
+
 // contribution of incident triangle T (compile-time: local index and slots fold into the closed-form coefficients)
 template <int T>
 __device__ __forceinline__ void node_jac_tri(const LatJacArgs &A, const LatGeom &G, int i, int j, const double u7[7], double v[7]) {
@@ -128,12 +134,7 @@ __device__ __forceinline__ void node_jac_tri(const LatJacArgs &A, const LatGeom 
     nlp_cell_jac_row_const<a>(up ? G.gu : G.gl, G.a2, u, row);
     const bool fb = !up && cj == 0 && A.ext_bottom, fr = !up && ci == A.nx - 1;
     const bool fl = up && ci == 0, ft = up && cj == A.ny - 1 && A.ext_top;
-    if (fb || fr || fl || ft) {      // boundary triangle: Nitsche facet rows with the cell's own geometry
-        Tri Tg;
-        tri_load(A.T, 2 * ((int64_t)cj * A.nx + ci) + up, Tg);
-        if (fb || fl) nlp_facet_jac_row(Tg, 2, A.T.beta, a, row);
-        if (fr || ft) nlp_facet_jac_row(Tg, 0, A.T.beta, a, row);
-    }
+    if (fb || fr || fl || ft) node_facet_jac(A.T, 2 * (cj * A.nx + ci) + up, fb || fl, fr || ft, a, row);
     v[s0] += row[0];
     v[s1] += row[1];
     v[s2] += row[2];
@@ -141,11 +142,11 @@ __device__ __forceinline__ void node_jac_tri(const LatJacArgs &A, const LatGeom 
 
 __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A, LatGeom G, LatDiaOut O) {
     const int w = A.nx + 1;
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int r = blockIdx.x * kThreads + threadIdx.x;           // int32 dofs everywhere (FEMO_ELIMIT otherwise)
     __shared__ double sh_g[kThreads];
     double gersh = 0.0;
-    if (r < (int64_t)w * (A.ny + 1)) {
-    const int i = (int)(r % w), j = (int)(r / w);
+    if (r < w * (A.ny + 1)) {
+    const int j = r / w, i = r - j * w;
     // stencil slots {-w-1, -w, -1, 0, 1, w, w+1} and which of them exist on the local lattice
     const bool present[7] = {i > 0 && j > 0, j > 0, i > 0, true, i < A.nx, j < A.ny, i < A.nx && j < A.ny};
     const int off[7] = {-w - 1, -w, -1, 0, 1, w, w + 1};
@@ -209,28 +210,18 @@ template <int a>
 __device__ __forceinline__ double nlp_cell_res_entry(const double g[3][2], double a2, const double u[3], double f) {
     const double gu0 = u[0] * g[0][0] + u[1] * g[1][0] + u[2] * g[2][0];
     const double gu1 = u[0] * g[0][1] + u[1] * g[1][1] + u[2] * g[2][1];
-    // int u^3 phi_a dx = |det J| / 720 * sum_{i,j,k} u_i u_j u_k * tri_quartic(i, j; k, a): contract j,k first
+    const double u00 = u[0] * u[0], u11 = u[1] * u[1], u22 = u[2] * u[2], u01 = u[0] * u[1];
+    // cubic monomials u_i u_j u_k, i <= j <= k, lexicographic
+    const double cub[10] = {u00 * u[0], u00 * u[1], u00 * u[2], u01 * u[1], u01 * u[2], u[0] * u22,
+                            u11 * u[1], u11 * u[2], u[1] * u22, u22 * u[2]};
     double m = 0.0;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        double mi = 0.0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            double mij = 0.0;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int m0 = (i == 0) + (j == 0) + (k == 0) + (a == 0), m1 = (i == 1) + (j == 1) + (k == 1) + (a == 1);
-                mij += (double)(tri_fact(m0) * tri_fact(m1) * tri_fact(4 - m0 - m1)) * u[k];
-            }
-            mi += mij * u[j];
-        }
-        m += mi * u[i];
-    }
-    return 0.5 * a2 * (gu0 * g[a][0] + gu1 * g[a][1]) + a2 * (m / 720.0 - f / 6.0);
+    for (int k = 0; k < 10; ++k) m = fma(kQuartRes[a][k], cub[k], m);
+    return 0.5 * a2 * (gu0 * g[a][0] + gu1 * g[a][1]) + a2 * (m * (1.0 / 720.0) - f * (1.0 / 6.0));
 }
 
 // entry a of the Nitsche vector of exterior facet l (as k_nlpoisson_p1_facet<OP_RES>)
-__device__ __forceinline__ double nlp_facet_res_entry(const Tri &T, int l, double beta, const double u[3], int a) {
+__device__ __noinline__ double nlp_facet_res_entry(const Tri &T, int l, double beta, const double u[3], int a) {
     const int la = (l == 0) ? 1 : 0, lb = (l == 2) ? 1 : 2;
     const double tx = T.X[lb][0] - T.X[la][0], ty = T.X[lb][1] - T.X[la][1];
     const double len = sqrt(tx * tx + ty * ty);
@@ -262,30 +253,34 @@ __device__ __forceinline__ double nlp_facet_res_entry(const Tri &T, int l, doubl
     return R;
 }
 
+__device__ __noinline__ double node_facet_res(const TriArgs &A, int64_t cell, int first, int second, const double u[3], int a) {
+    Tri Tg;
+    tri_load(A, cell, Tg);
+    double R = 0.0;
+    if (first) R += nlp_facet_res_entry(Tg, 2, A.beta, u, a);
+    if (second) R += nlp_facet_res_entry(Tg, 0, A.beta, u, a);
+    return R;
+}
+
 template <int T>
 __device__ __forceinline__ double node_res_tri(const LatJacArgs &A, const LatGeom &G, int i, int j, const double u7[7]) {
     constexpr int up = kNodeTri[T][2], a = kNodeTri[T][3];
     const int ci = i + kNodeTri[T][0], cj = j + kNodeTri[T][1];
     if (ci < 0 || cj < 0 || ci >= A.nx || cj >= A.ny) return 0.0;
-    const int64_t c = 2 * ((int64_t)cj * A.nx + ci) + up;
+    const int c = 2 * (cj * A.nx + ci) + up;
     const double u[3] = {u7[kNodeTri[T][4]], u7[kNodeTri[T][5]], u7[kNodeTri[T][6]]};
     double R = nlp_cell_res_entry<a>(up ? G.gu : G.gl, G.a2, u, __ldg(A.T.f + c));
     const bool fb = !up && cj == 0 && A.ext_bottom, fr = !up && ci == A.nx - 1;
     const bool fl = up && ci == 0, ft = up && cj == A.ny - 1 && A.ext_top;
-    if (fb || fr || fl || ft) {
-        Tri Tg;
-        tri_load(A.T, c, Tg);
-        if (fb || fl) R += nlp_facet_res_entry(Tg, 2, A.T.beta, u, a);
-        if (fr || ft) R += nlp_facet_res_entry(Tg, 0, A.T.beta, u, a);
-    }
+    if (fb || fr || fl || ft) R += node_facet_res(A.T, c, fb || fl, fr || ft, u, a);
     return R;
 }
 
 __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_res(LatJacArgs A, LatGeom G, double *__restrict__ out) {
     const int w = A.nx + 1;
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= (int64_t)w * (A.ny + 1)) return;
-    const int i = (int)(r % w), j = (int)(r / w);
+    const int r = blockIdx.x * kThreads + threadIdx.x;
+    if (r >= w * (A.ny + 1)) return;
+    const int j = r / w, i = r - j * w;
     const bool present[7] = {i > 0 && j > 0, j > 0, i > 0, true, i < A.nx, j < A.ny, i < A.nx && j < A.ny};
     const int off[7] = {-w - 1, -w, -1, 0, 1, w, w + 1};
     double u7[7];

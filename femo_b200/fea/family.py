@@ -84,8 +84,16 @@ class FormFamily:
     @property
     def problem(self):
         if self._prob is None:
-            p = _E.EngineProblem(self.mesh._e, self.family_id, self.params, self.tagged, facets=self.facets,
-                                 cell_tags=self.cell_tags)
+            slab = getattr(self.mesh, 'slab', None)
+            if slab is not None:
+                # one rank's y-slab of the partitioned lattice: the engine exchanges halos / all-reduces inside
+                from .. import dist as _D
+                if self.family_id not in (_E.FAMILY_POISSON_P1, _E.FAMILY_NLPOISSON_P1):
+                    raise NotImplementedError('partitioned meshes: slab layouts exist for the P1 triangle families')
+                p = _D.SlabProblem(self.family_id, slab['nx'], slab['gny'], slab['rank'], slab['nranks'], params=self.params)
+            else:
+                p = _E.EngineProblem(self.mesh._e, self.family_id, self.params, self.tagged, facets=self.facets,
+                                     cell_tags=self.cell_tags)
             # what replaces the reference's LU: GMG-preconditioned CG where a lattice hierarchy exists,
             # the explicit inverse for tiny systems, Jacobi-CG otherwise
             if self.family_id in (_E.FAMILY_POISSON_P1, _E.FAMILY_NLPOISSON_P1, _E.FAMILY_SIMP_Q1, _E.FAMILY_SIMP_HEX8,
@@ -99,7 +107,9 @@ class FormFamily:
                 self.krylov_extra = dict(cheb_degree=24, cheb_ratio=600.0)
             else:
                 self.precond = 3 if p.N <= 512 else 0
-            p.upload(0)                      # raises FemoError without a CUDA device
+            import torch
+            # the rank's device (torch.cuda.set_device(LOCAL_RANK) under torchrun); raises FemoError without CUDA
+            p.upload(torch.cuda.current_device() if torch.cuda.is_available() else 0)
             self._prob = p
         return self._prob
 

@@ -47,9 +47,13 @@ class _Geometry:
 class Mesh:
     """Structured mesh in canonical lattice numbering ("Numbering")."""
 
-    def __init__(self, emesh, cell_type):
+    def __init__(self, emesh, cell_type, slab=None):
+        """slab: dict(nx, gny, rank, nranks, own0, own1, cown0, cown1) when this is one rank's y-slab of a partitioned
+        lattice (local mesh = owned rows + one ghost cell row below + one ghost node row above, csrc/dist.cuh): the
+        API-level arrays of Functions then hold the OWNED dofs only, as dolfinx's Vec.getArray does under MPI."""
         self._e = emesh
         self.cell_type = cell_type
+        self.slab = slab
         xy = emesh.coords()
         x3 = np.zeros((emesh.nverts, 3))
         x3[:, :emesh.gdim] = xy
@@ -125,6 +129,22 @@ class FunctionSpace:
         self.dim = nnodes * block
         self.dofmap = _DofMap(nnodes, block)
         self.num_sub_spaces = block if block > 1 and family != 'Hermite' else 0
+        self.own = None                       # slice of the owned dofs inside the local (owned + ghost) vector
+        self.halo_kind = 0
+        if mesh.slab is not None:
+            sl = mesh.slab
+            if (family, degree) == ('CG', 1):
+                w = (sl['nx'] + 1) * block
+                self.own = slice(sl['own0'] * w, sl['own1'] * w)
+            elif (family, degree) == ('DG', 0):
+                w = 2 * sl['nx'] * block
+                self.own = slice(sl['cown0'] * w, sl['cown1'] * w)
+                self.halo_kind = 1
+            else:
+                raise ValueError('femo_b200: partitioned meshes carry CG1 and DG0 spaces')
+        self.local_dim = self.dim
+        if self.own is not None:
+            self.dim = self.own.stop - self.own.start
 
     def node_coordinates(self):
         if self.family == 'DG':
@@ -161,7 +181,10 @@ class Vector:
         self._f = func
 
     def getArray(self):
-        return self._f._host_array()
+        """Owned dofs (the whole vector on one rank), as Vec.getArray; a view into the host mirror."""
+        a = self._f._host_array()
+        own = self._f.function_space.own
+        return a if own is None else a[own]
 
     array = property(getArray)
 
@@ -175,12 +198,12 @@ class Vector:
         if isinstance(key, slice) and key == slice(None) and isinstance(values, np.ndarray):
             self._f._assign(values)              # whole-vector assignment: no D2H refresh needed first
             return
-        a = self._f._host_array()
+        a = self.getArray()
         a[key] = values
         self._f._host_changed()
 
     def __getitem__(self, key):
-        return self._f._host_array()[key]
+        return self.getArray()[key]
 
     def assemble(self):
         pass
@@ -189,7 +212,7 @@ class Vector:
         pass
 
     def norm(self):
-        return float(np.linalg.norm(self._f._host_array()))
+        return float(np.linalg.norm(self.getArray()))
 
     def __len__(self):
         return self._f.function_space.dim
@@ -211,7 +234,7 @@ class Function:
     def __init__(self, V, name=None):
         self.function_space = V
         self.name = name
-        self._host = np.zeros(V.dim)
+        self._host = np.zeros(V.local_dim)      # local vector: owned dofs + ghosts on a partitioned mesh
         self._dev = None            # torch tensor on the problem's device (a buffer, nothing more)
         self._prob = None
         self._host_ver = 1          # bumped on every host write
@@ -246,8 +269,16 @@ class Function:
     def _assign(self, values):
         ver = values.version if isinstance(values, _H.TrackedArray) else None
         v = np.asarray(values, dtype=np.float64).ravel()
+        own = self.function_space.own
         if v.size == 1:
             return self._fill(float(v[0]))
+        elif own is not None and v.size == own.stop - own.start and v.size != self._host.size:
+            # one rank's OWNED values: into the owned block of the local vector; the ghost rows are refreshed by a halo
+            # exchange after the next upload (device_tensor)
+            self._host_array()
+            _H.copy(self._host[own], v)
+            self._src = None
+            ver = None
         else:
             src = (v.__array_interface__['data'][0], ver)
             if ver is not None and src == self._src:
@@ -285,6 +316,8 @@ class Function:
             self._dev.copy_(torch.from_numpy(self._host), non_blocking=False)
             self._dev_ver = self._host_ver
             prob.h2d_bytes += self._host.nbytes
+            if self.function_space.own is not None:       # partitioned: neighbours' owned rows into our ghost rows
+                prob.halo(self._dev, self.function_space.halo_kind)
         return self._dev
 
     def mark_device_written(self):

@@ -24,7 +24,24 @@ KRYLOV = dict(rtol=1e-12, max_it=200000, check_every=1, precond=2, cheb_degree=2
 
 # ---- meshes (utils_dolfinx.py:136-153) -------------------------------------
 def createUnitSquareMesh(n):
-    return Mesh(_E.EngineMesh.unit_square(n), 'triangle')
+    """One process: the n x n unit square.  Under torchrun with femo_b200.dist.init() done (the reference's nominal
+    MPI.COMM_WORLD, utils_dolfinx.py:32,140-153): this rank's y-slab of the same lattice -- owned rows plus a one-cell
+    ghost layer -- and every Function on it exposes the rank's OWNED dofs."""
+    from .. import dist as _D
+    R, rank = _D._state.get('nranks', 1), _D._state.get('rank', 0)
+    if not _D._state.get('initialised') or R == 1:
+        return Mesh(_E.EngineMesh.unit_square(n), 'triangle')
+    if n % R:
+        raise ValueError('createUnitSquareMesh: n must be divisible by the number of ranks')
+    rows = n // R
+    a, b = rank * rows, rank * rows + rows
+    crow0 = a - 1 if a > 0 else 0
+    ncrows = b - crow0
+    own0 = a - crow0
+    slab = dict(nx=n, gny=n, rank=rank, nranks=R, crow0=crow0, ncrows=ncrows, own0=own0,
+                own1=own0 + rows + (1 if rank == R - 1 else 0), cown0=own0, cown1=own0 + rows)
+    em = _E.EngineMesh.unit_square(n, ncrows, lo=(0.0, crow0 / n), hi=(1.0, (crow0 + ncrows) / n))
+    return Mesh(em, 'triangle', slab=slab)
 
 
 def createIntervalMesh(n, x0, x1):
@@ -133,6 +150,12 @@ def _download(prob, tensor):
     return a
 
 
+def _own(fam, slot, a):
+    """Owned block of a local vector living in the space of `slot` (0 state, 1+s input s); identity on one rank."""
+    own = fam.function_of(slot).function_space.own
+    return a if own is None else a[own]
+
+
 # ---- assembly (utils_dolfinx.py:169-222) -----------------------------------------
 def assembleScalar(c):
     p = c.fam.sync()
@@ -143,9 +166,9 @@ def assembleVector(v):
     """Residual / gradient vector; Dirichlet values are NOT applied (quirk B11)."""
     p = v.fam.sync()
     if v.kind == 'residual':
-        return _download(p, p.assemble_residual())
+        return _own(v.fam, 0, _download(p, p.assemble_residual()))
     if v.kind == 'output_grad':
-        return _download(p, p.assemble_output_grad(v.out_id, v.slot))
+        return _own(v.fam, v.slot, _download(p, p.assemble_output_grad(v.out_id, v.slot)))
     raise TypeError('form of kind %r does not assemble to a vector' % v.kind)
 
 
@@ -183,7 +206,7 @@ def assembleSystem(J, F, bcs=[], rhs=True):
     if not rhs:
         return A, None
     b = p.system_rhs(vals) if bcs else p.assemble_residual()
-    return A, _download(p, b)
+    return A, _own(fam, 0, _download(p, b))
 
 
 def assemble(f, dim=0, bcs=[]):
@@ -221,13 +244,13 @@ def convertToDense(A_petsc):
 def computeMatVecProductFwd(A, x):
     """y = A x, x a Function (utils_dolfinx.py:256-264)."""
     p = A.fam.problem
-    return _download(p, A.mult(x.device_tensor(p)))
+    return _own(A.fam, A.which if A.transposed else 0, _download(p, A.mult(x.device_tensor(p))))
 
 
 def computeMatVecProductBwd(A, R):
     """y = A^T R (utils_dolfinx.py:275-287)."""
     p = A.fam.problem
-    return _download(p, A.multTranspose(R.device_tensor(p)))
+    return _own(A.fam, 0 if A.transposed else A.which, _download(p, A.multTranspose(R.device_tensor(p))))
 
 
 # ---- nonlinear solves (utils_dolfinx.py:319-449) ----------------------------------

@@ -43,3 +43,10 @@ def test_hex_slab_partition_matches_single_gpu(cuda_device):
     """z-slab partition of the hexahedral SIMP family vs the unpartitioned box."""
     for k, mode in enumerate(_modes()):
         _run('dist_check_hex.py', [16, 8, 32], 29641 + 10 * k, mode)
+
+
+def test_femo_api_on_a_partitioned_mesh(cuda_device):
+    """FEA + FEAModel + Simulator with one slab per rank (createUnitSquareMesh under femo_b200.dist): owned-dof arrays at
+    the API, halo exchanges / all-reduces inside the engine; state, functional and adjoint totals vs one GPU."""
+    for k, mode in enumerate(_modes()):
+        _run('dist_check_api.py', [64], 29671 + 10 * k, mode)
