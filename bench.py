@@ -246,7 +246,10 @@ def verify(es):
 VCYCLE_KERNELS = {0: 'femo::k_dia_apply<DIA_PLAIN,7> (V-cycle residual r = b - A x, fp32 DIA planes)',
                   1: 'femo::k_dia_apply<DIA_CHEB0,7> (post-smoother first Chebyshev step)',
                   2: 'femo::k_dia_apply<DIA_CHEBK,7> (post-smoother second Chebyshev step)',
-                  3: 'femo::k_dia_pre2 (fused zero-guess degree-2 pre-smoother)'}
+                  3: 'femo::k_dia_apply<DIA_PRE2,7> (fused zero-guess degree-2 pre-smoother)',
+                  4: 'femo::k_dia_spmv64<DOT,7> (CG recurrence q = A p with fused p.q, fp64 DIA planes)',
+                  5: 'femo::k_dia_spmv64<PLAIN,7> (fp64 residuals of the CG start and the full-multigrid levels)'}
+PROBE_MODES = tuple(sorted(VCYCLE_KERNELS))
 
 
 def _time_launches(torch, fn, reps):
@@ -264,12 +267,13 @@ def _time_launches(torch, fn, reps):
 
 def time_kernels(es, counts, steps, reps=50):
     """Average launch duration (CUDA events on the launching stream, inputs > L2) of the hot kernels at the fine
-    level: the four instantiations of the V-cycle operator and the fp64 CSR SpMV of the CG recurrence.
-    counts[mode] = fine-level launches during the timed steps -> share of the step."""
+    level: the four instantiations of the V-cycle operator (fp32 DIA planes), the two of the fp64 DIA SpMV the CG
+    recurrence applies, and the CSR-stream SpMV behind `femo_spmv` (the operator kernel of non-lattice problems).
+    counts[mode] = fine-level launches during the timed steps (counted by the engine) -> share of the step."""
     torch, p = es.torch, es.p
     out = []
     if counts is not None:
-        for mode in range(4):
+        for mode in PROBE_MODES:
             alg, _ = p.vcycle_op_probe(mode)
             t = _time_launches(torch, lambda: p.vcycle_op_probe(mode), reps)
             out.append(dict(kernel=VCYCLE_KERNELS[mode], launch_ms=t * 1e3, algorithmic_bytes=alg,
@@ -284,9 +288,11 @@ def time_kernels(es, counts, steps, reps=50):
                         algorithmic_bytes=8 * es.nnz + 4 * (es.nnz // 9) + 16 * p.N + 4 * (p.N // 3),
                         launches_per_step=es.info.get('adjoint_its', 0) + 1.0))
     t = _time_launches(torch, lambda: p.spmv(0, es.vals, x, out=y), reps)
-    out.append(dict(kernel='femo::k_spmv<double> (CSR-stream SpMV of the CG recurrence, fine-level Jacobian)',
-                    launch_ms=t * 1e3, algorithmic_bytes=12 * es.nnz + 20 * p.N,
-                    launches_per_step=es.info.get('krylov_its', 0) + es.info.get('adjoint_its', 0) + 5.0))
+    # lattice P1 problems apply the fine-level operator from DIA planes (rows above): the CSR kernel is then not part of
+    # the step; the other workloads run one per Krylov iteration plus the residual checks
+    per_step = 0.0 if counts is not None else es.info.get('krylov_its', 0) + es.info.get('adjoint_its', 0) + 5.0
+    out.append(dict(kernel='femo::k_spmv<double> (CSR-stream SpMV, fine-level Jacobian; femo_spmv and non-lattice operators)',
+                    launch_ms=t * 1e3, algorithmic_bytes=12 * es.nnz + 20 * p.N, launches_per_step=per_step))
     return out
 
 
@@ -436,7 +442,7 @@ def main():
     sampler.start()
     l0 = es.p.launch_count()
     has_dia = a.workload == 'p1' and not os.environ.get('FEMO_NO_DIA')
-    c0 = [es.p.vcycle_op_probe(m)[1] for m in range(4)] if has_dia else None
+    c0 = [es.p.vcycle_op_probe(m)[1] for m in PROBE_MODES] if has_dia else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -445,8 +451,8 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = es.p.launch_count() - l0 - (4 if has_dia else 0)
-    counts = [es.p.vcycle_op_probe(m)[1] - c0[m] - 1 for m in range(4)] if has_dia else None
+    launches = es.p.launch_count() - l0 - (len(PROBE_MODES) if has_dia else 0)
+    counts = [es.p.vcycle_op_probe(m)[1] - c0[m] - 1 for m in PROBE_MODES] if has_dia else None
     clocks = sampler.stop()
     kernels = time_kernels(es, counts, a.steps)
     step_info = dict(es.info)

@@ -247,4 +247,5 @@ struct femo_problem {
     long long launches = 0;
     long long graph_replays = 0;             // PCG iterations replayed from a captured CUDA graph
     long long dia_count[4] = {0, 0, 0, 0};   // launches of the DIA operator kernel on this level, by mode
+    long long dia64_count[2] = {0, 0};       // launches of the fp64 DIA SpMV on this level: with / without the fused dot
 };

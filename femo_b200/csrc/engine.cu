@@ -2444,16 +2444,22 @@ int femo_linear_solve(femo_problem *p, const double *d_vals, const double *d_b, 
 int femo_vcycle_op_probe(femo_problem *p, int mode, int64_t info[2]) {
     int rc;
     if ((rc = need_device(p))) return rc;
-    if (mode < 0 || mode > 3) return set_err(FEMO_EINVAL, "femo_vcycle_op_probe: mode 0..3");
+    if (mode < 0 || mode > 5) return set_err(FEMO_EINVAL, "femo_vcycle_op_probe: mode 0..5");
     if (!dia_ready(p)) return set_err(FEMO_ESTATE, "femo_vcycle_op_probe: no DIA hierarchy (run a precond=2 solve on a lattice P1 problem first)");
+    const int64_t N = p->state.ndofs;
+    if (mode >= 4) {
+        // fp64 planes of the CG recurrence: 7 x 8 B values + x read + y written; mode 4 = fused dot(x, y), 5 = plain
+        if (!p->mgl.dia64) return set_err(FEMO_ESTATE, "femo_vcycle_op_probe: no fp64 DIA planes on this problem");
+        if (info) { info[0] = 72 * N; info[1] = p->dia64_count[mode - 4]; }
+        return mode == 4 ? launch_dia64<true>(p, p->kr_d, p->kr_w, nullptr, nullptr) : launch_dia64<false>(p, p->kr_d, p->kr_w, nullptr, nullptr);
+    }
     DiaEpi E;
     E.b = p->kr_r; E.rin = p->kr_r; E.c0 = 0.5; E.c1 = 0.25; E.c2 = 0.125;
-    const int64_t N = p->state.ndofs;
     int64_t bytes = 28 * N;                                   // 7 fp32 planes
     if (mode == DIA_PLAIN) bytes += 24 * N;                   // x, b read; r written
-    if (mode == DIA_CHEB0) { E.rout = p->kr_w; E.dout = p->kr_q; bytes += 32 * N; }     // x, b read; r, d written
-    if (mode == DIA_CHEBK) { E.xacc = p->kr_z; E.xmode = 0; bytes += 32 * N; }          // d, r read; x read + written
-    if (mode == DIA_PRE2) bytes += 16 * N;                    // b read; x written
+    if (mode == DIA_CHEB0) { E.rout = p->kr_w; E.dout = p->kr_q; bytes += 36 * N; }     // scaling plane; x, b read; r, d written
+    if (mode == DIA_CHEBK) { E.xacc = p->kr_z; E.xmode = 0; bytes += 36 * N; }          // scaling plane; d, r read; x read + written
+    if (mode == DIA_PRE2) bytes += 20 * N;                    // scaling plane; b read; x written
     if (info) { info[0] = bytes; info[1] = p->dia_count[mode]; }
     return launch_dia(p, mode, p->kr_d, mode == DIA_PRE2 ? p->kr_z : p->kr_w, E);
 }

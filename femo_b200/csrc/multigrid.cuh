@@ -775,6 +775,7 @@ static int launch_dia64(femo_problem *L, const double *x, double *y, const doubl
         k_dia_spmv64<DOT, 7><<<gi, kThreads, 0, L->stream>>>(L->mgl.dia64, A, x, y, bsub, L->own_off, L->own_off + L->own_n,
                                                              L->d_partials, R.i0, R.ni, 0, 0);
         L->launches += 2;
+        L->dia64_count[DOT ? 0 : 1]++;
         if (np_out) *np_out = gi + gb;
         FEMO_CHECK_LAUNCH();
         return overlap_end(L);
@@ -785,6 +786,7 @@ static int launch_dia64(femo_problem *L, const double *x, double *y, const doubl
     k_dia_spmv64<DOT, 7><<<grid, kThreads, 0, L->stream>>>(L->mgl.dia64, A, x, y, bsub, L->own_off, L->own_off + L->own_n,
                                                            L->d_partials, 0, -1, 0, 0);
     L->launches++;
+    L->dia64_count[DOT ? 0 : 1]++;
     if (np_out) *np_out = grid;
     FEMO_CHECK_LAUNCH();
     return FEMO_OK;

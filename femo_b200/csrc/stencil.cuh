@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
     for (int s = 0; s < D; ++s) a[s] = __ldcs(v + s * np);
     const float *__restrict__ dinvp = A.v + (size_t)D * np;
-    const double di = (double)__ldcs(dinvp + i);
+    const double di = (MODE == DIA_PLAIN) ? 0.0 : (double)__ldcs(dinvp + i);      // Jacobi scaling 1/a_ii (not needed by the residual)
     const double *__restrict__ src = (MODE == DIA_PRE2) ? E.b : x;
     const bool interior = i + A.off[0] >= 0 && i + A.off[D - 1] < n;
     double xv[D];

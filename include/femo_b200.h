@@ -267,12 +267,15 @@ typedef struct femo_krylov_info {
  * initial guess on entry for precond 0/1/3; with the multigrid preconditioner
  * (precond 2) the full-multigrid iterate REPLACES the caller's x unless
  * opts.restart == 1 (then x is honoured as x0).  Synchronises. */
-int femo_vcycle_op_probe(femo_problem *p, int mode, int64_t info[2]);
-/* ^ measurement hook for bench.py's roofline: one launch of the fine-level V-cycle operator kernel (mode 0 residual,
- *   1 / 2 Chebyshev steps, 3 fused pre-smoother) on the hierarchy of the last precond=2 solve; info[0] receives the
- *   algorithmic bytes of that launch, info[1] the fine-level launches of that mode so far. */
 int femo_linear_solve(femo_problem *p, const double *d_vals, const double *d_b, double *d_x, int transpose,
                       const femo_krylov_opts *opts, femo_krylov_info *info);
+
+/* Measurement hook for bench.py's roofline (no reference counterpart): ONE launch of a fine-level operator kernel of
+ * the last precond=2 solve on the solver's own work vectors.  mode 0 residual, 1 / 2 Chebyshev steps, 3 fused
+ * zero-guess pre-smoother (fp32 DIA planes of the V-cycle); 4 / 5 the fp64 DIA SpMV of the CG recurrence with / without
+ * the fused dot product.  info[0] receives the algorithmic bytes of that launch, info[1] the
+ * fine-level launches of that mode so far. */
+int femo_vcycle_op_probe(femo_problem *p, int mode, int64_t info[2]);
 
 typedef struct femo_newton_opts {
     int kind;        /* 0 = dolfinx NewtonSolver (utils_dolfinx.py:419-449), 1 = PETSc SNES newtonls (:376-416) */
