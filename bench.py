@@ -42,6 +42,16 @@ def workload(n, kind='p1'):
                     solver='SNES newtonls atol=rtol=1e-13; p-multigrid (P2 -> P1 -> lattice hierarchy) preconditioned CG '
                            'rtol=%g replaces LU(MUMPS)' % KRYLOV_RTOL,
                     cache='working set exceeds the 126 MB L2; no explicit flush')
+    if kind == 'motor':
+        nr, nth = n, 4 * n
+        dofs = (nr + 1) * nth
+        return dict(workload='em_motor_opt on the synthetic annulus %dx%d (magnetostatics %d dofs + mesh motion %d dofs, %d cells, '
+                             '216-subdomain tag layout): edge displacement -> mesh motion (2-step incremental SNES) -> '
+                             'magnetostatics (5-step load ramp, SNES) -> B influence, chained EM + mesh-motion adjoints'
+                             % (nr, nth, dofs, 2 * dofs, 2 * nr * nth), n=n, dofs=3 * dofs, cells=2 * nr * nth,
+                    solver='SNES newtonls; GMRES(70) right-preconditioned by a smoothed-aggregation AMG V-cycle rtol=%g replaces '
+                           'LU(MUMPS)' % KRYLOV_RTOL,
+                    cache='working set exceeds the 126 MB L2; no explicit flush')
     if kind == 'hex':
         nx, ny, nz = n, n // 2, n // 4
         dofs = 3 * (nx + 1) * (ny + 1) * (nz + 1)
@@ -190,6 +200,9 @@ class EngineStep:
         self.tmp = p.new_vector(p.M[0])
         self.info = {}
 
+    def launch_count(self):
+        return self.p.launch_count()
+
     def step(self):
         p = self.p
         k = self.out_id
@@ -211,6 +224,97 @@ class EngineStep:
         self.info = dict(newton_its=ni['iterations'], krylov_its=ni['krylov_iterations'], adjoint_its=li['iterations'],
                          fnorm0=ni['fnorm0'], fnorm=ni['fnorm'],
                          converged=(bool(ni['converged']) or self.kind == 'hex') and li['converged'], J=J)
+        return J
+
+
+class MotorStep:
+    """BASELINE.json configs[4] (examples/em_motor_opt/run_motor_opt.py:94-317) at engine level on the synthetic annulus:
+    one step = mesh-motion state (2 incremental SNES solves) + magnetostatic state (5-step ramp of the sources) + the
+    chained total derivative of the B-influence functional w.r.t. the prescribed edge displacement (EM adjoint solve,
+    dR_em/duhat^T, mesh-motion adjoint solve, dR_mm/dg^T)."""
+    kind = 'motor'
+
+    def __init__(self, nr, device, precond='amg'):
+        import numpy as np
+        import torch
+        from femo_b200 import engine as E
+        from femo_b200.forms import motor as pde
+        from femo_b200.fea.fem import Mesh
+        self.torch = torch
+        nth = 4 * nr
+        em = E.EngineMesh.annulus(nr, nth)
+        mesh = Mesh(em, 'triangle')
+        tags = pde.synthetic_motor_tags(mesh)
+        mid = nr // 2
+        sides = [pde.annulus_circle_sides(mesh, k) for k in (0, mid, nr)]
+        fc, fl = np.concatenate([q[0] for q in sides]), np.concatenate([q[1] for q in sides])
+        o = np.lexsort((fl, fc))
+        self.mm = E.EngineProblem(em, E.FAMILY_MOTOR_MM, [5e3], facets=(fc[o], fl[o]), cell_tags=tags)
+        self.em = E.EngineProblem(em, E.FAMILY_MOTOR_EM,
+                                  pde.em_params(838.e3, 12, 36, 4e-7 * np.pi, 0.0, 282.2 / 0.00016231), cell_tags=tags)
+        self.mm.upload(device)
+        self.em.upload(device)
+        self.p = self.em
+        X = em.coords()
+        g = np.zeros(2 * X.shape[0])
+        nodes = mid * nth + np.arange(nth)
+        frac = 0.1 * (0.06 / nr) / 0.09                      # the interior circle (r = 0.09) grows by a tenth of a radial cell
+        g[2 * nodes], g[2 * nodes + 1] = frac * X[nodes, 0], frac * X[nodes, 1]
+        self.g = self.mm.to_device(g)
+        self.gs = self.mm.new_vector(g.size, 0.0)
+        self.uhat = self.mm.new_vector(self.mm.N, 0.0)
+        self.A = self.em.new_vector(self.em.N, 0.0)
+        self.mm.set_coefficient(0, self.uhat); self.mm.set_coefficient(1, self.gs)
+        self.em.set_coefficient(0, self.A); self.em.set_coefficient(1, self.uhat)
+        self.global_dofs = self.mm.N + self.em.N
+        self.nnz = self.em.pattern_info(0)['nnz']
+        self.vals = self.em.new_vector(self.nnz)
+        self.vals_mm = self.mm.new_vector(self.mm.pattern_info(0)['nnz'])
+        self.vals_bc = None
+        if precond == 'amg':
+            self.kw = dict(method=1, precond=4, cheb_degree=2, cheb_ratio=4.0)
+            t0 = time.perf_counter()
+            self.em.set_param(6, 0.2)
+            self.em.assemble_jacobian(out=self.vals)
+            self.em.enable_amg(self.vals)
+            self.mm.assemble_jacobian(out=self.vals_mm)
+            self.mm.enable_amg(self.vals_mm, omega_scale=0.0)        # plain aggregation + degree-4 smoother (family.py)
+            self.kw_mm = dict(method=1, precond=4, cheb_degree=4, cheb_ratio=8.0)
+            self.setup = dict(seconds=time.perf_counter() - t0, em=self.em.amg, mm=self.mm.amg)
+        else:
+            self.kw = self.kw_mm = dict(method=1, precond=1, cheb_degree=24, cheb_ratio=600.0)
+            self.setup = None
+        self.info = {}
+
+    def launch_count(self):
+        return self.em.launch_count() + self.mm.launch_count()
+
+    def step(self):
+        em, mm, kw = self.em, self.mm, self.kw
+        its = dict(mm_newton=0, mm_krylov=0, em_newton=0, em_krylov=0)
+        self.uhat.zero_()
+        for i in (1, 2):                                            # solveIncremental, run_motor_opt.py:120-142
+            self.torch.mul(self.g, i / 2.0, out=self.gs)
+            ni = mm.newton_solve(kind='SNES', krylov_rtol=KRYLOV_RTOL, krylov_max_it=40000, **self.kw_mm)
+            its['mm_newton'] += ni['iterations']; its['mm_krylov'] += ni['krylov_iterations']
+        self.A.zero_()
+        for st in range(1, 6):                                      # solveIncrementalEM, :231-250
+            em.set_param(6, st / 5.0)
+            ne = em.newton_solve(kind='SNES', krylov_rtol=KRYLOV_RTOL, krylov_max_it=40000, **kw)
+            its['em_newton'] += ne['iterations']; its['em_krylov'] += ne['krylov_iterations']
+        em.assemble_jacobian(out=self.vals)
+        J, dJdA = em.assemble_output_and_grad(0)
+        lam_e, le = em.linear_solve(self.vals, dJdA, transpose=True, rtol=KRYLOV_RTOL, max_it=40000, **kw)
+        dJduh = em.assemble_output_grad(0, 1)
+        em.axpy(-1.0, em.spmv(1, em.assemble_dRdm(0), lam_e, transpose=True), dJduh)
+        mm.assemble_jacobian(out=self.vals_mm)
+        lam_m, lm = mm.linear_solve(self.vals_mm, dJduh, transpose=True, rtol=KRYLOV_RTOL, max_it=40000, **self.kw_mm)
+        self.grad = mm.spmv(1, mm.assemble_dRdm(0), lam_m, transpose=True)
+        self.grad.neg_()
+        self.info = dict(its, krylov_its=its['em_krylov'] + its['mm_krylov'], adjoint_its=le['iterations'] + lm['iterations'],
+                         em_adjoint_its=le['iterations'], mm_adjoint_its=lm['iterations'], newton_its=its['em_newton'] + its['mm_newton'],
+                         converged=bool(ne['converged'] and ni['converged'] and le['converged'] and lm['converged']),
+                         fnorm=ne['fnorm'], J=J)
         return J
 
 
@@ -375,16 +479,19 @@ def main():
     ap.add_argument('--n', type=int, default=N_DEFAULT)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--workload', default='p1', choices=['p1', 'p2', 'hex'],
-                    help="p1 = BASELINE.json configs[1] (the metric's config, default); p2 / hex = the P2 and 3-D variants "
-                         "named by configs[1] / configs[3], 1 GPU, for profiles/")
+    ap.add_argument('--workload', default='p1', choices=['p1', 'p2', 'hex', 'motor'],
+                    help="p1 = BASELINE.json configs[1] (the metric's config, default); p2 / hex / motor = the P2 variant of "
+                         "configs[1], the 3-D cantilever of configs[3] and the chained motor problem of configs[4], for profiles/")
+    ap.add_argument('--precond', default='amg', choices=['amg', 'cheb'], help='motor workload: AMG V-cycle or the round-1 polynomial')
     a = ap.parse_args()
     if a.workload != 'p1':
         if a.n == N_DEFAULT:
-            a.n = 2000 if a.workload == 'p2' else 256
+            a.n = dict(p2=2000, hex=256, motor=512)[a.workload]
         a.no_cpu = True
-        if a.workload == 'hex':
+        if a.workload in ('hex', 'motor'):
             a.no_e2e = True
+        if a.workload == 'motor' and int(os.environ.get('WORLD_SIZE', '1')) > 1:
+            raise SystemExit('the motor workload runs on one GPU')
         if a.workload == 'p2' and int(os.environ.get('WORLD_SIZE', '1')) > 1:
             raise SystemExit('the P2 workload runs on one GPU')
     rank = int(os.environ.get('RANK', '0'))
@@ -434,13 +541,13 @@ def main():
     if world > 1:
         from femo_b200 import dist as fd
         fd.init(local_rank)
-    es = EngineStep(a.n, local_rank, rank, world, a.workload)
+    es = MotorStep(a.n, local_rank, a.precond) if a.workload == 'motor' else EngineStep(a.n, local_rank, rank, world, a.workload)
     for _ in range(W):
         es.step()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    l0 = es.p.launch_count()
+    l0 = es.launch_count()
     has_dia = a.workload == 'p1' and not os.environ.get('FEMO_NO_DIA')
     c0 = [es.p.vcycle_op_probe(m)[1] for m in PROBE_MODES] if has_dia else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -451,7 +558,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = es.p.launch_count() - l0 - (len(PROBE_MODES) if has_dia else 0)
+    launches = es.launch_count() - l0 - (len(PROBE_MODES) if has_dia else 0)
     counts = [es.p.vcycle_op_probe(m)[1] - c0[m] - 1 for m in PROBE_MODES] if has_dia else None
     clocks = sampler.stop()
     kernels = time_kernels(es, counts, a.steps)
@@ -463,7 +570,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = float(tt.item())
     # one partitioned problem with `world` times the dofs: normalise to solves of the N=1 workload
-    base_dofs = (a.n + 1) ** 2 if a.workload == 'p1' else 3 * (a.n + 1) * (a.n // 2 + 1) * (a.n // 4 + 1)
+    base_dofs = (a.n + 1) ** 2 if a.workload in ('p1', 'motor') else 3 * (a.n + 1) * (a.n // 2 + 1) * (a.n // 4 + 1)
     norm = es.global_dofs / float(base_dofs) if world > 1 else 1.0
     value = norm * a.steps / (ms * 1e-3)
 
@@ -596,7 +703,7 @@ def main():
                                  share_of_step=dom['share_of_step'],
                                  peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 (of fallback)',
                                  kernels=kernels),
-                   step_info=dict(es.info, verify=check))
+                   step_info=dict(es.info, verify=check, **({'amg_pattern_phase': es.setup} if a.workload == 'motor' else {})))
         if check is not None and not check['ok']:
             out['error'] = 'verification failed: %r' % (check,)
         if not a.no_cpu:

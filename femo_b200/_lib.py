@@ -28,6 +28,11 @@ class KrylovInfo(C.Structure):
                 ('spmv_count', C.c_int)]
 
 
+class AmgOpts(C.Structure):
+    _fields_ = [('theta', C.c_double), ('theta_decay', C.c_double), ('max_levels', C.c_int), ('coarse_size', C.c_int),
+                ('block', C.c_int), ('omega_scale_set', C.c_int), ('omega_scale', C.c_double)]
+
+
 class NewtonOpts(C.Structure):
     _fields_ = [('kind', C.c_int), ('atol', C.c_double), ('rtol', C.c_double), ('stol', C.c_double),
                 ('max_it', C.c_int), ('krylov', KrylovOpts)]
@@ -106,6 +111,12 @@ SIGNATURES = {
     'femo_host_fill': (None, [_P, C.c_int64, C.c_double]),
     'femo_pointwise_divide': (C.c_int, [_P, C.c_double, _P, _P, _P, C.c_int64]),
     'femo_vcycle_op_probe': (C.c_int, [_P, C.c_int, _I64P]),
+    'femo_amg_symbolic': (C.c_int, [_P, _P, C.POINTER(AmgOpts), _I64P]),
+    'femo_amg_attach': (C.c_int, [_P, _P, C.c_int64]),
+    'femo_amg_numeric': (C.c_int, [_P, _P]),
+    'femo_amg_level_info': (C.c_int, [_P, C.c_int, _I64P, _DP]),
+    'femo_amg_level_array': (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64]),
+    'femo_amg_level_values': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int64]),
     'femo_linear_solve': (C.c_int, [_P, _P, _P, _P, C.c_int, C.POINTER(KrylovOpts), C.POINTER(KrylovInfo)]),
     'femo_newton_solve': (C.c_int, [_P, C.POINTER(NewtonOpts), C.POINTER(NewtonInfo)]),
 }

@@ -168,6 +168,7 @@ struct MgFusedProg {
     int k0 = 0, nops = 0, nlev = 0;
 };
 
+struct femo_amg;
 struct femo_problem {
     femo::Mesh mesh;
     int family = 0;
@@ -244,6 +245,7 @@ struct femo_problem {
     MgFusedProg mgprog;
     femo::MgOp *d_mgops = nullptr;
     std::vector<femo::MgOp> h_mgops;
+    struct femo_amg *amg = nullptr;          // smoothed-aggregation hierarchy (precond 4; amg.cuh), owned
     long long launches = 0;
     long long graph_replays = 0;             // PCG iterations replayed from a captured CUDA graph
     long long dia_count[4] = {0, 0, 0, 0};   // launches of the DIA operator kernel on this level, by mode

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kThreads) k_finalize(const double *__restrict_
 //   EPI_CHEB0   r_i = b_i - acc ; d_i = c1 dinv_i r_i                      (first Chebyshev step, x untouched)
 //   EPI_CHEBK   r_i = rin_i - acc ; dn = c1 x_i + c2 dinv_i r_i ; dout_i = dn   (x is the previous direction)
 //               xacc_i: mode 0 += dn ; mode 1 += x_i + dn ; mode 2 = x_i + dn
-enum SpmvEpiKind { EPI_PLAIN = 0, EPI_CHEB0 = 1, EPI_CHEBK = 2 };
+enum SpmvEpiKind { EPI_PLAIN = 0, EPI_CHEB0 = 1, EPI_CHEBK = 2, EPI_ADD = 3 /* y_i += acc (prolongation x += P xc, amg.cuh) */ };
 struct SpmvEpi {
     const double *b = nullptr, *dinv = nullptr, *rin = nullptr;
     double *rout = nullptr, *dout = nullptr, *xacc = nullptr;
@@ -180,6 +180,8 @@ template <int EPI>
 __device__ __forceinline__ void spmv_row_epilogue(const SpmvEpi &E, int64_t i, double acc, double xi, double *y) {
     if (EPI == EPI_PLAIN) {
         y[i] = E.b ? E.b[i] - acc : acc;
+    } else if (EPI == EPI_ADD) {
+        y[i] += acc;
     } else if (EPI == EPI_CHEB0) {
         const double r = E.b[i] - acc;
         E.rout[i] = r;
@@ -914,6 +916,7 @@ static int lattice_jacobian(femo_problem *p, double *d_vals, double *d_vals_bc, 
 #include "stencil.cuh"
 #include "multigrid.cuh"
 #include "mgfused.cuh"
+#include "amg.cuh"
 #include "krylov.cuh"
 #include "gmres.cuh"
 
@@ -1465,6 +1468,7 @@ int femo_problem_mg_levels(const femo_problem *p) { return p ? (int)p->mg.size()
 void femo_problem_destroy(femo_problem *p) {
     if (!p) return;
     for (femo_problem *c : p->mg) femo_problem_destroy(c);
+    delete p->amg;
     if (p->h_pinned) cudaFreeHost(p->h_pinned);
     if (!p->parent && p->stream2) {
         cudaStreamDestroy(p->stream2);
@@ -2435,6 +2439,109 @@ int femo_linear_solve(femo_problem *p, const double *d_vals, const double *d_b, 
         vals = p->d_tvals;
     }
     return o.method == 1 ? gmres_solve(p, vals, d_b, d_x, o, info) : cg_solve(p, vals, d_b, d_x, o, info);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Smoothed-aggregation AMG (precond 4): pattern phase on the host, arena handed in by the caller, numeric phase and
+// V-cycle on the device (amg_setup.cpp, amg.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+int femo_amg_symbolic(femo_problem *p, const double *h_vals, const femo_amg_opts *opts, int64_t info[4]) {
+    if (!p) return set_err(FEMO_EINVAL, "femo_amg_symbolic: null problem");
+    if (p->slab.active) return set_err(FEMO_ESTATE, "femo_amg_symbolic: slab problems use the lattice hierarchy");
+    const Pattern &P = p->pat[0];
+    if (P.nrows != P.ncols || P.nrows <= 0) return set_err(FEMO_ESTATE, "femo_amg_symbolic: no square state pattern");
+    AmgOpts o;
+    o.block = p->state.block;
+    if (opts) {
+        if (opts->theta >= 0.0) o.theta = opts->theta;
+        if (opts->theta_decay > 0.0) o.theta_decay = opts->theta_decay;
+        if (opts->max_levels > 0) o.max_levels = std::min(opts->max_levels, 24);
+        if (opts->coarse_size > 0) o.coarse_size = std::min(opts->coarse_size, kMgDenseMax);
+        if (opts->block > 0) o.block = opts->block;
+        if (opts->omega_scale_set) o.omega_scale = opts->omega_scale;
+    }
+    delete p->amg;
+    p->amg = new femo_amg();
+    try {
+        amg_build(P.rowptr.data(), P.col.data(), P.nrows, h_vals, p->has_bc && !p->bc_mark.empty() ? p->bc_mark.data() : nullptr, o,
+                  p->amg->host);
+    } catch (const LayoutError &e) {
+        delete p->amg;
+        p->amg = nullptr;
+        return set_err(e.code, e.msg);
+    }
+    if (info) {
+        int64_t tot = 0;
+        for (const AmgLevelHost &L : p->amg->host.lv) tot += L.nnz;
+        info[0] = (int64_t)p->amg->host.lv.size();
+        info[1] = (int64_t)amg_arena_bytes(p->amg->host);
+        info[2] = tot;
+        info[3] = p->amg->host.lv.back().n;
+    }
+    return FEMO_OK;
+}
+
+int femo_amg_attach(femo_problem *p, void *d_arena, int64_t bytes) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!p->amg) return set_err(FEMO_ESTATE, "femo_amg_attach: run femo_amg_symbolic first");
+    if (!d_arena || bytes < (int64_t)amg_arena_bytes(p->amg->host)) return set_err(FEMO_EINVAL, "femo_amg_attach: arena too small");
+    return amg_attach(p, p->amg, d_arena, (size_t)bytes);
+}
+
+int femo_amg_numeric(femo_problem *p, const double *d_vals) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!d_vals) return set_err(FEMO_EINVAL, "femo_amg_numeric: null values");
+    return amg_numeric(p, p->amg, d_vals);
+}
+
+int femo_amg_level_info(const femo_problem *p, int level, int64_t info[8], double dinfo[2]) {
+    if (!p || !p->amg || level < 0 || level >= (int)p->amg->host.lv.size()) return set_err(FEMO_EINVAL, "femo_amg_level_info: no such level");
+    const AmgLevelHost &L = p->amg->host.lv[level];
+    if (info) {
+        info[0] = L.n; info[1] = L.nnz; info[2] = L.nc; info[3] = L.nnzP; info[4] = L.nnzAP;
+        info[5] = (int64_t)L.ap_ia.size(); info[6] = (int64_t)L.ac_ia.size(); info[7] = (int64_t)L.pp_src.size();
+    }
+    if (dinfo) {
+        dinfo[0] = L.lmax;                                                           // host numeric phase
+        dinfo[1] = (p->amg->attached && level < (int)p->amg->lv.size()) ? p->amg->lv[level].lmax : 0.0;   // device numeric phase
+    }
+    return FEMO_OK;
+}
+
+int femo_amg_level_array(const femo_problem *p, int level, int which, int32_t *h_out, int64_t cap) {
+    if (!p || !p->amg || level < 0 || level >= (int)p->amg->host.lv.size()) return set_err(FEMO_EINVAL, "femo_amg_level_array: no such level");
+    const AmgLevelHost &L = p->amg->host.lv[level];
+    const std::vector<int32_t> *v[] = {&L.rowptr, &L.col, &L.agg, &L.p_rowptr, &L.p_col, &L.pp_ptr, &L.pp_src, &L.r_rowptr, &L.r_col,
+                                       &L.r_perm, &L.ap_rowptr, &L.ap_col, &L.ap_ptr, &L.ap_ia, &L.ap_ib, &L.ac_ptr, &L.ac_ia, &L.ac_ib};
+    if (which < 0 || which >= (int)(sizeof(v) / sizeof(v[0]))) return set_err(FEMO_EINVAL, "femo_amg_level_array: which 0..17");
+    if (!h_out || cap < (int64_t)v[which]->size()) return set_err(FEMO_EINVAL, "femo_amg_level_array: output too small");
+    if (!v[which]->empty()) memcpy(h_out, v[which]->data(), v[which]->size() * sizeof(int32_t));
+    return (int)FEMO_OK;
+}
+
+int femo_amg_level_values(femo_problem *p, int level, int which, int from_device, double *h_out, int64_t cap) {
+    if (!p || !p->amg || level < 0 || level >= (int)p->amg->host.lv.size()) return set_err(FEMO_EINVAL, "femo_amg_level_values: no such level");
+    const AmgLevelHost &L = p->amg->host.lv[level];
+    if (which < 0 || which > 3) return set_err(FEMO_EINVAL, "femo_amg_level_values: which 0 operator, 1 prolongator, 2 A*P, 3 inverse diagonal");
+    const int64_t len = which == 0 ? L.nnz : which == 1 ? L.nnzP : which == 2 ? L.nnzAP : L.n;
+    if (!h_out || cap < len) return set_err(FEMO_EINVAL, "femo_amg_level_values: output too small");
+    if (!from_device) {
+        const std::vector<double> &v = which == 0 ? L.vals : which == 1 ? L.p_vals : which == 2 ? L.ap_vals : L.dinv;
+        if ((int64_t)v.size() != len) return set_err(FEMO_ESTATE, "femo_amg_level_values: the hierarchy was built from the pattern only (no host values)");
+        if (len) memcpy(h_out, v.data(), len * sizeof(double));
+        return FEMO_OK;
+    }
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!p->amg->attached || !p->amg->numeric_setups) return set_err(FEMO_ESTATE, "femo_amg_level_values: no numeric phase has run on the device");
+    const AmgLevelDev &D = p->amg->lv[level];
+    const double *src = which == 0 ? D.vals : which == 1 ? D.p_vals : which == 2 ? D.ap_vals : D.dinv;
+    if (!src) return set_err(FEMO_ESTATE, "femo_amg_level_values: array does not exist on this level");
+    FEMO_CUDA(cudaStreamSynchronize(p->stream));
+    FEMO_CUDA(cudaMemcpy(h_out, src, len * sizeof(double), cudaMemcpyDeviceToHost));
+    return FEMO_OK;
 }
 
 /* measurement hook (bench.py roofline): ONE launch of the fine-level V-cycle operator kernel in `mode`

@@ -1,5 +1,5 @@
 // gmres.cuh -- restarted GMRES(m) for the non-symmetric Jacobians (motor families), right
-// preconditioned (Jacobi, explicit dense inverse, or the multigrid V-cycle), classical Gram-Schmidt
+// preconditioned (Jacobi, Chebyshev polynomial, explicit dense inverse, geometric or algebraic multigrid V-cycle), classical Gram-Schmidt
 // with re-orthogonalisation (CGS2: two batched dot passes per iteration, one host read each).
 // Together with krylov.cuh this replaces KSP preonly + LU(MUMPS), utils_dolfinx.py:405-408,476-512.
 #pragma once
@@ -90,8 +90,13 @@ static int gmres_solve(femo_problem *p, const double *vals, const double *b, dou
     p->mgl.dinv = p->kr_dinv; p->mgl.r = p->kr_w; p->mgl.d = p->kr_d; p->mgl.q = p->wk_extra;
     const int cdeg = o.cheb_degree > 0 ? o.cheb_degree : 12;
     const double cratio = o.cheb_ratio > 1.0 ? o.cheb_ratio : 150.0;
+    AmgParams ap;
+    if (o.cheb_degree > 0) ap.degree = o.cheb_degree;
+    if (o.cheb_ratio > 1.0) ap.ratio = o.cheb_ratio;
     if (pre == 2) {
         if ((rc = mg_setup(p, vals, mp.fp32))) return rc;
+    } else if (pre == 4) {
+        if ((rc = amg_numeric(p, p->amg, vals))) return rc;
     } else if (pre == 1) {
         if ((rc = cheb_setup(p, vals))) return rc;
     } else if (pre == 3) {
@@ -105,6 +110,7 @@ static int gmres_solve(femo_problem *p, const double *vals, const double *b, dou
     auto precond = [&](const double *in, double *out) -> int {
         if (pre == 3) k_dense_apply<<<(int)((n * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(p->d_dense, in, out, (int)n);
         else if (pre == 2) return mg_vcycle(p, 0, in, out, mp);
+        else if (pre == 4) return amg_vcycle(p, p->amg, 0, in, out, ap);
         else if (pre == 1) return mg_smooth(p, in, out, true, cdeg, cratio, false);
         else k_hadamard<<<g, kThreads, 0, st>>>(p->kr_dinv, in, out, n);
         p->launches++;

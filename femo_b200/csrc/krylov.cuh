@@ -204,7 +204,8 @@ static int norm2_sq(femo_problem *p, const double *a, double *out) {
 }
 
 // Preconditioned CG on the dR/du pattern; `vals` already in the layout to multiply with.
-//   precond 0: Jacobi, 2: multigrid V-cycle, 3: explicit dense inverse
+//   precond 0: Jacobi, 1: Chebyshev polynomial, 2: geometric multigrid V-cycle, 3: explicit dense inverse,
+//   4: smoothed-aggregation AMG V-cycle (amg.cuh)
 // op_current: the caller guarantees that `vals` is the (BC'd) Jacobian of the coefficients currently bound to the
 // problem (true inside femo_newton_solve, which assembles it itself): hexahedral lattices then apply the operator
 // matrix-free in the recurrence too.  Matrices handed in through femo_linear_solve are always streamed as given.
@@ -235,8 +236,13 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
     p->mgl.q = p->kr_q;
     const int cdeg = o.cheb_degree > 0 ? o.cheb_degree : 8;
     const double cratio = o.cheb_ratio > 1.0 ? o.cheb_ratio : 60.0;
+    AmgParams ap;
+    if (o.cheb_degree > 0) ap.degree = o.cheb_degree;
+    if (o.cheb_ratio > 1.0) ap.ratio = o.cheb_ratio;
     if (pre == 2) {
         if ((rc = mg_setup(p, vals, mp.fp32, dia_prepared))) return rc;
+    } else if (pre == 4) {
+        if ((rc = amg_numeric(p, p->amg, vals))) return rc;
     } else if (pre == 1) {
         if ((rc = cheb_setup(p, vals))) return rc;
     } else if (pre == 3) {
@@ -296,6 +302,8 @@ static int cg_solve(femo_problem *p, const double *vals, const double *b, double
                 p->launches++;
             } else if (pre == 1) {
                 if ((r = mg_smooth(p, p->kr_r, p->kr_z, true, cdeg, cratio, false))) return r;
+            } else if (pre == 4) {
+                if ((r = amg_vcycle(p, p->amg, 0, p->kr_r, p->kr_z, ap))) return r;
             } else if ((r = mg_vcycle(p, 0, p->kr_r, p->kr_z, mp))) return r;
             k_dot<<<go, kThreads, 0, st>>>(p->kr_r + p->own_off, p->kr_z + p->own_off, p->own_n, pa);
             p->launches++;

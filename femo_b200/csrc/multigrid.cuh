@@ -481,15 +481,29 @@ __global__ void __launch_bounds__(kThreads)
     for (int i = tid; i < n; i += kThreads)
         for (int32_t t = rowptr[i]; t < rowptr[i + 1]; ++t) A[i * n + col[t]] = vals[t];
     __syncthreads();
+    __shared__ double pvv[kThreads];
+    __shared__ int pvi[kThreads];
     for (int k = 0; k < n; ++k) {
-        if (tid == 0) {
+        // pivot = first row of maximal |A[i][k]|, i >= k: block-wide argmax (ties to the lower index, as a serial scan would)
+        {
+            double bv = -1.0;
             int best = k;
-            double bv = fabs(A[k * n + k]);
-            for (int i = k + 1; i < n; ++i) {
+            for (int i = k + tid; i < n; i += kThreads) {
                 const double v = fabs(A[i * n + k]);
                 if (v > bv) { bv = v; best = i; }
             }
-            piv = best;
+            pvv[tid] = bv;
+            pvi[tid] = best;
+            __syncthreads();
+            for (int o = kThreads / 2; o > 0; o >>= 1) {
+                if (tid < o) {
+                    const double v2 = pvv[tid + o];
+                    const int i2 = pvi[tid + o];
+                    if (v2 > pvv[tid] || (v2 == pvv[tid] && i2 < pvi[tid])) { pvv[tid] = v2; pvi[tid] = i2; }
+                }
+                __syncthreads();
+            }
+            if (tid == 0) piv = pvi[0];
         }
         __syncthreads();
         const int pr = piv;

@@ -343,6 +343,74 @@ class EngineProblem:
         check(lib.femo_axpy(self._h, float(a), self._p(x), self._p(y), x.numel()))
         return y
 
+    # -- algebraic multigrid (precond 4): meshes without a lattice hierarchy ------------------------------------
+    AMG_ARRAYS = ('rowptr', 'col', 'agg', 'p_rowptr', 'p_col', 'pp_ptr', 'pp_src', 'r_rowptr', 'r_col', 'r_perm',
+                  'ap_rowptr', 'ap_col', 'ap_ptr', 'ap_ia', 'ap_ib', 'ac_ptr', 'ac_ia', 'ac_ib')
+    AMG_VALUES = ('vals', 'p_vals', 'ap_vals', 'dinv')
+
+    def amg_symbolic(self, vals=None, theta=-1.0, theta_decay=0.0, max_levels=0, coarse_size=0, block=0, omega_scale=None):
+        """Pattern phase of the smoothed-aggregation hierarchy (host only).  vals: host copy of a BC'd Jacobian for
+        the strength-of-connection test (None: every connection strong).  Returns levels / bytes / complexity."""
+        from ._lib import AmgOpts
+        o = AmgOpts(theta=theta, theta_decay=theta_decay, max_levels=max_levels, coarse_size=coarse_size, block=block,
+                    omega_scale_set=0 if omega_scale is None else 1, omega_scale=0.0 if omega_scale is None else float(omega_scale))
+        vp = None
+        if vals is not None:
+            vals = np.ascontiguousarray(vals, dtype=np.float64)
+            assert vals.size == self.pattern_info(0)['nnz']
+            vp = _np_ptr(vals)
+        info = (C.c_int64 * 4)()
+        check(lib.femo_amg_symbolic(self._h, vp, C.byref(o), info))
+        self.amg = dict(levels=int(info[0]), bytes=int(info[1]), total_nnz=int(info[2]), coarsest=int(info[3]),
+                        operator_complexity=int(info[2]) / float(self.pattern_info(0)['nnz']))
+        return self.amg
+
+    def amg_attach(self):
+        """Upload the index lists of the hierarchy into a device buffer of this problem's device."""
+        import torch
+        self._amg_arena = torch.empty(self.amg['bytes'], dtype=torch.uint8, device=self.device)
+        check(lib.femo_amg_attach(self._h, C.c_void_p(self._amg_arena.data_ptr()), self.amg['bytes']))
+        return self
+
+    def enable_amg(self, vals=None, **kw):
+        """amg_symbolic + amg_attach; vals may be a device tensor (copied to the host for the strength test)."""
+        if vals is not None and hasattr(vals, 'cpu'):
+            vals = vals.cpu().numpy()
+        self.amg_symbolic(vals, **kw)
+        return self.amg_attach()
+
+    def amg_numeric(self, vals):
+        check(lib.femo_amg_numeric(self._h, self._p(vals)))
+
+    def amg_level_info(self, level):
+        info, dinfo = (C.c_int64 * 8)(), (C.c_double * 2)()
+        check(lib.femo_amg_level_info(self._h, level, info, dinfo))
+        keys = ('n', 'nnz', 'nc', 'nnzP', 'nnzAP', 'pairs_ap', 'pairs_ac', 'p_sources')
+        d = {k: int(info[i]) for i, k in enumerate(keys)}
+        d['lmax_host'], d['lmax_device'] = float(dinfo[0]), float(dinfo[1])
+        return d
+
+    def amg_level_array(self, level, name):
+        i = self.amg_level_info(level)
+        sizes = dict(rowptr=i['n'] + 1, col=i['nnz'], agg=i['n'] if i['nc'] else 0, p_rowptr=i['n'] + 1, p_col=i['nnzP'],
+                     pp_ptr=i['nnzP'] + 1, pp_src=i['p_sources'], r_rowptr=i['nc'] + 1, r_col=i['nnzP'], r_perm=i['nnzP'],
+                     ap_rowptr=i['n'] + 1, ap_col=i['nnzAP'], ap_ptr=i['nnzAP'] + 1, ap_ia=i['pairs_ap'], ap_ib=i['pairs_ap'],
+                     ac_ia=i['pairs_ac'], ac_ib=i['pairs_ac'])
+        if name == 'ac_ptr':
+            n = self.amg_level_info(level + 1)['nnz'] + 1
+        else:
+            n = sizes[name] if (i['nc'] or name in ('rowptr', 'col')) else 0
+        out = np.empty(n, dtype=np.int32)
+        check(lib.femo_amg_level_array(self._h, level, self.AMG_ARRAYS.index(name), _np_ptr(out), n))
+        return out
+
+    def amg_level_values(self, level, name, from_device=False):
+        i = self.amg_level_info(level)
+        n = dict(vals=i['nnz'], p_vals=i['nnzP'], ap_vals=i['nnzAP'], dinv=i['n'])[name]
+        out = np.empty(n, dtype=np.float64)
+        check(lib.femo_amg_level_values(self._h, level, self.AMG_VALUES.index(name), 1 if from_device else 0, _np_ptr(out), n))
+        return out
+
     def linear_solve(self, vals, b, x=None, transpose=False, rtol=1e-10, atol=0.0, max_it=100000, check_every=1,
                      precond=0, cheb_degree=0, cheb_ratio=0.0, method=0, restart=0, mg_precision=0):
         """method 0 = CG, 1 = restarted GMRES (non-symmetric Jacobians)."""

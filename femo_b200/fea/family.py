@@ -27,6 +27,7 @@ class FormFamily:
         self.facets = None           # explicit one-sided facets (cells, locals)
         self._prob = None
         self._bc_sig = None
+        self._amg_ready = False
         self._ptrs = {}
 
     # -- registry: forms built from the same (state, inputs) share one family --
@@ -99,19 +100,41 @@ class FormFamily:
             if self.family_id in (_E.FAMILY_POISSON_P1, _E.FAMILY_NLPOISSON_P1, _E.FAMILY_SIMP_Q1, _E.FAMILY_SIMP_HEX8,
                                   _E.FAMILY_NLPOISSON_P2):
                 p.enable_multigrid()
-                self.precond = 2 if p.mg_levels > 1 else (3 if p.N <= 512 else 0)
+                # meshes without a lattice hierarchy (Gmsh / array meshes): smoothed-aggregation AMG (precond 4)
+                self.precond = 2 if p.mg_levels > 1 else (3 if p.N <= 512 else 4)
             elif self.family_id in (_E.FAMILY_MOTOR_EM, _E.FAMILY_MOTOR_MM):
-                # non-symmetric Jacobian (nonlinear Nitsche coefficient): Chebyshev-preconditioned GMRES
+                # non-symmetric Jacobian (nonlinear Nitsche coefficient): GMRES, right-preconditioned by the AMG V-cycle
+                # (round 1: a degree-24 Chebyshev-Jacobi polynomial whose iteration count grew with the mesh)
                 self.method = 1
-                self.precond = 3 if p.N <= 512 else 1
-                self.krylov_extra = dict(cheb_degree=24, cheb_ratio=600.0)
+                self.precond = 3 if p.N <= 512 else 4
             else:
                 self.precond = 3 if p.N <= 512 else 0
+            self.amg_opts = {}
+            if self.precond == 4:
+                self.krylov_extra = dict(cheb_degree=2, cheb_ratio=4.0)
+                if self.family_id == _E.FAMILY_MOTOR_MM:
+                    # one-sided Nitsche terms make the first Jacobian of every increment far from symmetric: damped-Jacobi
+                    # smoothing of the prolongator then produces coarse rows with vanishing diagonals (Gershgorin bounds
+                    # of 1e3 - 1e5), plain aggregation with a degree-4 smoother stays bounded
+                    self.amg_opts = dict(omega_scale=0.0)
+                    self.krylov_extra = dict(cheb_degree=4, cheb_ratio=8.0)
             import torch
             # the rank's device (torch.cuda.set_device(LOCAL_RANK) under torchrun); raises FemoError without CUDA
             p.upload(torch.cuda.current_device() if torch.cuda.is_available() else 0)
             self._prob = p
         return self._prob
+
+    def ensure_amg(self, vals=None):
+        """Pattern phase of the AMG hierarchy, once per (pattern, Dirichlet set): strength of connection from `vals` (a
+        device tensor on the dR/du pattern) or from the BC'd Jacobian at the coefficients currently bound."""
+        if self.precond != 4 or self._amg_ready:
+            return
+        p = self.problem
+        if vals is None:
+            plain, bcv = p.assemble_jacobian(plain=not self._bc_sig, bc=bool(self._bc_sig))
+            vals = bcv if self._bc_sig else plain
+        p.enable_amg(vals, **getattr(self, 'amg_opts', {}))
+        self._amg_ready = True
 
     def sync(self):
         """Make the engine's coefficient slots point at up-to-date device copies."""
@@ -136,6 +159,8 @@ class FormFamily:
         sig = tuple((b.dofs.size, hash(b.dofs.tobytes()), hash(v.tobytes())) for b, v in zip(bcs, vals))
         if sig == self._bc_sig:
             return
+        if self._bc_sig is None or tuple(t[:2] for t in sig) != tuple(t[:2] for t in self._bc_sig):
+            self._amg_ready = False          # a new Dirichlet set: the aggregates leave those rows out
         if not bcs:
             p.set_bc([], None)
         else:

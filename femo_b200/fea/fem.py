@@ -272,9 +272,11 @@ class Function:
         own = self.function_space.own
         if v.size == 1:
             return self._fill(float(v[0]))
-        elif own is not None and v.size == own.stop - own.start and v.size != self._host.size:
+        elif own is not None and v.size == own.stop - own.start:
             # one rank's OWNED values: into the owned block of the local vector; the ghost rows are refreshed by a halo
-            # exchange after the next upload (device_tensor)
+            # exchange after the next upload (device_tensor).  Also taken when the rank has no ghost entries in this space
+            # (rank 0 holds no ghost cell row): the exchange is collective, every rank must reach it (its neighbours
+            # need this rank's rows)
             self._host_array()
             _H.copy(self._host[own], v)
             self._src = None

@@ -263,6 +263,7 @@ def solveNonlinear(res, func, bc, solver, report, initialize):
         func.vector.set(0.1)                                   # utils_dolfinx.py:433-435
     p = fam.sync()
     fam.apply_bcs(bc)
+    fam.ensure_amg()
     try:
         info = p.newton_solve(kind=solver, krylov_rtol=KRYLOV['rtol'], krylov_max_it=KRYLOV['max_it'],
                               check_every=KRYLOV['check_every'],
@@ -301,6 +302,7 @@ def _solve_into(A, b, x):
     bf, xf = _as_function(b), _as_function(x)
     xt = xf.device_tensor(p)
     xt.zero_()
+    fam.ensure_amg(A.vals)
     _, info = p.linear_solve(A.vals, bf.device_tensor(p), xt, transpose=A.transposed, rtol=KRYLOV['rtol'],
                              max_it=KRYLOV['max_it'], check_every=KRYLOV['check_every'],
                              precond=KRYLOV['precond'] if fam.precond is None else fam.precond,

@@ -5,7 +5,7 @@
   B_power_form(A_z, uhat, n, dx, subdomains)                                                     :186-197
 `dx` is the Measure whose subdomain_data carries the cell tags (meshtags of the cells).  The piecewise
 mu_r(|B|) of RelativePermeability (:12-35) uses the coefficients in bh_fit.json (tests/golden/make_bh_fit.py).
-The mesh-motion family (pdeResMM :134-183) is not implemented yet.
+The mesh-motion family (pdeResMM :134-183, area_form :199-210) follows below (csrc/families5.cuh).
 """
 import json
 import os

@@ -244,8 +244,10 @@ typedef struct femo_krylov_opts {
     int max_it;
     int precond;      /* 0 Jacobi, 1 Chebyshev polynomial of the Jacobi-scaled operator (cheb_degree, cheb_ratio),
                          2 geometric multigrid V-cycle (Chebyshev-Jacobi smoothing),
-                         3 explicit dense inverse (N <= 512; the direct-solve analogue) */
-    int cheb_degree;  /* smoother degree of the V-cycle (default 2) */
+                         3 explicit dense inverse (N <= 512; the direct-solve analogue),
+                         4 smoothed-aggregation algebraic multigrid V-cycle (femo_amg_symbolic + femo_amg_attach first;
+                           meshes without a lattice hierarchy) */
+    int cheb_degree;  /* smoother degree of the V-cycle, precond 2 and 4 (default 2) */
     int method;       /* 0 CG, 1 restarted GMRES (right-preconditioned, CGS2; non-symmetric Jacobians) */
     int restart;      /* GMRES restart; with precond 2: 1 disables the full-multigrid start */
     int check_every;  /* residual-norm host check period (>=1) */
@@ -269,6 +271,37 @@ typedef struct femo_krylov_info {
  * opts.restart == 1 (then x is honoured as x0).  Synchronises. */
 int femo_linear_solve(femo_problem *p, const double *d_vals, const double *d_b, double *d_x, int transpose,
                       const femo_krylov_opts *opts, femo_krylov_info *info);
+
+/* ---- algebraic multigrid for problems without a lattice hierarchy (unstructured meshes, the motor annulus) -------
+ * The reference factorises every Jacobian with MUMPS (utils_dolfinx.py:405-408,476-512); precond 4 replaces that by a
+ * smoothed-aggregation V-cycle.  femo_amg_symbolic (host only, once per pattern): strength graph, aggregates, the
+ * patterns of P, R = P^T, A P, P^T A P on every level and the index lists of the numeric phase.  h_vals: host copy of
+ * a (BC'd) Jacobian on the state pattern for the strength-of-connection test, or NULL (every connection strong).
+ * Dirichlet rows (femo_problem_set_bc) are left out of the aggregates.  info[0] levels, info[1] bytes of device memory
+ * femo_amg_attach needs, info[2] sum of nnz over the levels, info[3] dofs of the coarsest level.  femo_amg_attach
+ * uploads the lists into the caller's buffer (a torch tensor, like the problem arenas).  The numeric phase (diagonals,
+ * Gershgorin bounds, prolongator values, Galerkin products: sorted segmented reductions, no atomics) runs on the
+ * device at the start of every precond-4 solve; femo_amg_numeric runs it alone. */
+typedef struct femo_amg_opts {
+    double theta;        /* strength threshold |a_ij| >= theta sqrt(a_ii a_jj) on level 0 (default 0.08; < 0 keeps it) */
+    double theta_decay;  /* factor per coarser level (default 0.5) */
+    int max_levels;      /* default 10 */
+    int coarse_size;     /* stop coarsening at this many dofs (default 200, dense inverse up to 512) */
+    int block;           /* dofs per node (default: the state space's block size) */
+    int omega_scale_set; /* nonzero: use omega_scale below */
+    double omega_scale;  /* prolongator smoothing P = (I - omega_scale * 4/(3 lmax) D^-1 A) T (default 1; 0 = plain aggregation) */
+} femo_amg_opts;
+int femo_amg_symbolic(femo_problem *p, const double *h_vals, const femo_amg_opts *opts, int64_t info[4]);
+int femo_amg_attach(femo_problem *p, void *d_arena, int64_t bytes);
+int femo_amg_numeric(femo_problem *p, const double *d_vals);
+/* Introspection for the tests: sizes (n, nnz, coarse n, nnz(P), nnz(AP), pairs of A P, pairs of P^T A P, sources of P) and
+ * Gershgorin bounds (host phase, device phase); the integer lists (which: 0 rowptr, 1 col, 2 aggregate of each dof,
+ * 3 p_rowptr, 4 p_col, 5 pp_ptr, 6 pp_src, 7 r_rowptr, 8 r_col, 9 r_perm, 10 ap_rowptr, 11 ap_col, 12 ap_ptr, 13 ap_ia,
+ * 14 ap_ib, 15 ac_ptr, 16 ac_ia, 17 ac_ib); the values (which: 0 operator, 1 prolongator, 2 A P, 3 inverse diagonal) of
+ * the host numeric phase or, from_device = 1, of the last device numeric phase. */
+int femo_amg_level_info(const femo_problem *p, int level, int64_t info[8], double dinfo[2]);
+int femo_amg_level_array(const femo_problem *p, int level, int which, int32_t *h_out, int64_t cap);
+int femo_amg_level_values(femo_problem *p, int level, int which, int from_device, double *h_out, int64_t cap);
 
 /* Measurement hook for bench.py's roofline (no reference counterpart): ONE launch of a fine-level operator kernel of
  * the last precond=2 solve on the solver's own work vectors.  mode 0 residual, 1 / 2 Chebyshev steps, 3 fused

@@ -1,5 +1,6 @@
-"""Motor magnetostatics (config 5b) at growing sizes on the synthetic annulus: 5-step load ramp (SNES + GMRES with the
-Chebyshev-Jacobi polynomial) + adjoint of the flux-density functional.  Prints times and iteration counts."""
+"""Motor magnetostatics (config 5b) at growing sizes on the synthetic annulus: 5-step load ramp (SNES + GMRES) + adjoint
+of the flux-density functional.  PRECOND=cheb: degree-24 Chebyshev-Jacobi polynomial (round 1); PRECOND=amg (default):
+smoothed-aggregation V-cycle (csrc/amg.cuh).  Prints times and iteration counts."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -8,7 +9,8 @@ from femo_b200.forms import motor as pde
 from femo_b200.fea.fem import Mesh
 
 sizes = [(int(a), int(b)) for a, b in (s.split('x') for s in (sys.argv[1:] or ['128x512', '256x1024']))]
-kw = dict(method=1, precond=1, cheb_degree=24, cheb_ratio=600.0)
+amg = os.environ.get('PRECOND', 'amg') == 'amg'
+kw = dict(method=1, precond=4, cheb_degree=2, cheb_ratio=4.0) if amg else dict(method=1, precond=1, cheb_degree=24, cheb_ratio=600.0)
 for nr, nth in sizes:
     em = E.EngineMesh.annulus(nr, nth)
     tags = pde.synthetic_motor_tags(Mesh(em, 'triangle'))
@@ -16,6 +18,13 @@ for nr, nth in sizes:
     p.upload(0)
     u, uh = p.new_vector(p.N, 0.0), p.new_vector(p.M[0], 0.0)
     p.set_coefficient(0, u); p.set_coefficient(1, uh)
+    if amg:
+        t0 = time.perf_counter()
+        p.set_param(6, 0.2)
+        vbc, _ = p.assemble_jacobian()          # no Dirichlet rows in this family (penalty / Nitsche terms)
+        p.enable_amg(vbc)
+        torch.cuda.synchronize()
+        print('AMG pattern phase %.2f s: %r' % (time.perf_counter() - t0, p.amg), flush=True)
     for rep in range(2):
         u.zero_()
         torch.cuda.synchronize(); t0 = time.perf_counter(); l0 = p.launch_count()

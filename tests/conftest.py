@@ -12,6 +12,14 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
+def pytest_collection_modifyitems(config, items):
+    # the multi-process tests (torchrun, two ranks; on a 1-GPU box both ranks time-share cuda:0) run last: every
+    # single-process parity test is through before the slowest, most environment-dependent ones start
+    last = [it for it in items if 'test_gpu_dist' in it.nodeid]
+    if last:
+        items[:] = [it for it in items if 'test_gpu_dist' not in it.nodeid] + last
+
+
 @pytest.fixture(scope='session')
 def cuda_device():
     import torch

@@ -28,7 +28,7 @@ def _run(script, args, port, extra):
            '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', script)] + [str(a) for a in args]
     # several distributed levels and the halo / interior overlap path even on these small meshes
     env = dict(os.environ, FEMO_DIST_MIN_ROWS='16', FEMO_OVERLAP_MIN_ROWS='256', **extra)
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert 'OK' in out.stdout
 
