@@ -698,7 +698,7 @@ def main():
                    clocks=clocks, gpu_launches=int(launches), e2e=e2e,
                    roofline=dict(bound='hbm', kernel=dom['kernel'], achieved=dom['achieved_gbs'], peak=peak, unit='GB/s',
                                  frac=dom['frac'], traffic=dom['traffic'],
-                                 traffic_source='profiles/r02_summary.md: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch',
+                                 traffic_source='profiles/r02_ncu_full_probe.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch) -> profiles/r02_kernel_traffic.json',
                                  algorithmic_bytes=dom['algorithmic_bytes'], launch_ms=dom['launch_ms'],
                                  share_of_step=dom['share_of_step'],
                                  peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 (of fallback)',

@@ -1,9 +1,10 @@
 """Unstructured mesh ingest without dolfinx / meshio / h5py.
 
-The reference imports meshes converted by msh2xdmf (`import_mesh`, femo/fea/utils_dolfinx.py:69-123: an XDMF/HDF5
-pair for the domain and the boundaries plus `<prefix>_association_table.ini`).  HDF5 cannot be read offline, so
-`import_mesh` here goes back to the Gmsh file the XDMF pair was made from (`<prefix>.msh`, ASCII format 2.2 or
-4.1 [upstream layouts, from memory]) and returns the same tuple.  Gmsh's vertex order is converted to the
+The reference imports meshes converted by msh2xdmf (`import_mesh`, femo/fea/utils_dolfinx.py:69-123: an XDMF
+pair `<prefix>_domain.xdmf` / `<prefix>_boundaries.xdmf` plus `<prefix>_association_table.ini`).  `read_xdmf` reads that
+pair when its data items are inline XML or raw binary files (meshio's data_format "XML" / "Binary"); heavy data in HDF5
+(meshio's default) needs h5py, which is absent offline -- `import_mesh` then goes back to the Gmsh file the pair was made
+from (`<prefix>.msh`, ASCII format 2.2 or 4.1 [upstream layouts, from memory]).  Either way it returns the reference's tuple.  Gmsh's vertex order is converted to the
 tensor-product order basix uses for quadrilaterals and hexahedra.
 """
 import os
@@ -106,6 +107,55 @@ def read_msh(path):
     return pts, cells, names
 
 
+_XDMF_TOPO = {'triangle': ('triangle', 3), 'polyline': ('line', 2), 'quadrilateral': ('quadrilateral', 4),
+              'hexahedron': ('hexahedron', 8), 'polyvertex': ('point', 1)}
+# XDMF / VTK vertex order -> basix tensor-product order
+_XDMF_PERM = {'quadrilateral': [0, 1, 3, 2], 'hexahedron': [0, 1, 3, 2, 4, 5, 7, 6]}
+
+
+def _xdmf_item(item, directory):
+    fmt = item.get('Format', 'XML').upper()
+    dims = [int(d) for d in item.get('Dimensions').split()]
+    kind = item.get('DataType', item.get('NumberType', 'Float'))
+    prec = int(item.get('Precision', '4'))
+    dt = np.dtype({('Float', 4): '<f4', ('Float', 8): '<f8', ('Int', 4): '<i4', ('Int', 8): '<i8', ('UInt', 4): '<u4',
+                   ('UInt', 8): '<u8'}[(kind, prec)])
+    text = (item.text or '').strip()
+    if fmt == 'XML':
+        a = np.array(text.split(), dtype=np.float64 if kind == 'Float' else np.int64)
+    elif fmt == 'BINARY':
+        a = np.fromfile(os.path.join(directory, text), dtype=dt)
+    else:
+        raise NotImplementedError('XDMF data item in %s format (%s): HDF5 heavy data cannot be read without h5py; convert with '
+                                  'meshio data_format="XML" or keep the .msh next to the XDMF pair' % (fmt, text))
+    return a.reshape(dims)
+
+
+def read_xdmf(path, attribute=None):
+    """One <Grid> of an XDMF 3 file as meshio / msh2xdmf write it -> points (n, gdim), (cell type, connectivity in basix
+    vertex order), cell attribute values (the first Cell-centred <Attribute>, or the one named `attribute`), or None."""
+    import xml.etree.ElementTree as ET
+    directory = os.path.dirname(os.path.abspath(path))
+    grid = ET.parse(path).getroot().find('.//Grid')
+    if grid is None:
+        raise ValueError('%s: no <Grid>' % path)
+    pts = _xdmf_item(grid.find('Geometry').find('DataItem'), directory).astype(np.float64)
+    topo = grid.find('Topology')
+    tname = (topo.get('TopologyType') or topo.get('Type')).lower()
+    if tname not in _XDMF_TOPO:
+        raise NotImplementedError('XDMF topology %r' % tname)
+    kind, nn = _XDMF_TOPO[tname]
+    conn = _xdmf_item(topo.find('DataItem'), directory).astype(np.int64).reshape(-1, nn)
+    if kind in _XDMF_PERM:
+        conn = conn[:, _XDMF_PERM[kind]]
+    vals = None
+    for att in grid.findall('Attribute'):
+        if att.get('Center', 'Cell') == 'Cell' and (attribute is None or att.get('Name') == attribute):
+            vals = _xdmf_item(att.find('DataItem'), directory).astype(np.int64).ravel()
+            break
+    return pts, (kind, conn), vals
+
+
 class FacetTags:
     """Tagged facets of an imported mesh (`boundaries_mf` of the reference): each tagged line / face element is
     matched to the cell facets with the same vertex set.  `sides(tag)` lists them as one-sided (cell, local facet)
@@ -143,7 +193,20 @@ def import_mesh(prefix="mesh", subdomains=False, dim=2, directory="."):
     """utils_dolfinx.py:69-123 with the Gmsh file as the source.  Returns (mesh, boundaries_mf, association_table) or
     (mesh, boundaries_mf, subdomains_mf, association_table) exactly like the reference."""
     from .fem import Mesh, meshtags
-    pts, cells, names = read_msh(os.path.join(directory, prefix + '.msh'))
+    names = {}
+    dom, bnd = (os.path.join(directory, '%s_%s.xdmf' % (prefix, w)) for w in ('domain', 'boundaries'))
+    cells = None
+    if os.path.exists(dom) and os.path.exists(bnd):
+        try:                                           # the reference's own inputs, when their heavy data is readable
+            pts, (kind, conn), ctags = read_xdmf(dom)
+            _, (fk, fconn), ftags = read_xdmf(bnd)
+            cells = {kind: (conn, np.zeros(conn.shape[0], dtype=np.int32) if ctags is None else ctags.astype(np.int32)),
+                     fk: (fconn, np.zeros(fconn.shape[0], dtype=np.int32) if ftags is None else ftags.astype(np.int32))}
+        except NotImplementedError:
+            if not os.path.exists(os.path.join(directory, prefix + '.msh')):
+                raise
+    if cells is None:
+        pts, cells, names = read_msh(os.path.join(directory, prefix + '.msh'))
     kind = next(k for k in ('triangle', 'quadrilateral') if k in cells) if dim == 2 else 'hexahedron'
     conn, ctags = cells[kind]
     used = np.unique(conn)                          # drop geometry-only points (arc centres ...)

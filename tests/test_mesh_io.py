@@ -169,3 +169,52 @@ def test_gmsh_vertex_order_is_converted_to_tensor_order(tmp_path):
     assert np.all(e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0] > 0)
     em = E.EngineMesh.from_arrays('quadrilateral', p[:, :2], conn)
     assert em.nbfacets == 6
+
+
+def _write_xdmf(path, pts, topo, conn, attr_name, values, binary_dir=None):
+    """The XDMF 3 layout meshio / msh2xdmf write (one uniform Grid, Geometry XY, one cell attribute), inline XML or raw binary."""
+    def item(a, kind, prec, name):
+        dims = ' '.join(str(d) for d in a.shape)
+        if binary_dir is None:
+            body = '\n'.join(' '.join(repr(float(v)) if kind == 'Float' else str(int(v)) for v in row) for row in np.atleast_2d(a))
+            return '<DataItem DataType="%s" Dimensions="%s" Format="XML" Precision="%d">\n%s\n</DataItem>' % (kind, dims, prec, body)
+        fn = '%s_%s.bin' % (path.name, name)
+        np.asarray(a, dtype='<f8' if kind == 'Float' else '<i8').tofile(binary_dir / fn)
+        return '<DataItem DataType="%s" Dimensions="%s" Format="Binary" Precision="%d">%s</DataItem>' % (kind, dims, prec, fn)
+    path.write_text('<Xdmf Version="3.0"><Domain><Grid Name="Grid">'
+                    '<Geometry GeometryType="XY">%s</Geometry>'
+                    '<Topology TopologyType="%s" NumberOfElements="%d" NodesPerElement="%d">%s</Topology>'
+                    '<Attribute Name="%s" AttributeType="Scalar" Center="Cell">%s</Attribute>'
+                    '</Grid></Domain></Xdmf>'
+                    % (item(pts[:, :2], 'Float', 8, 'geo'), topo, conn.shape[0], conn.shape[1], item(conn, 'Int', 8, 'topo'),
+                       attr_name, item(np.asarray(values).reshape(-1, 1), 'Int', 8, 'attr')))
+
+
+@pytest.mark.parametrize('binary', [False, True])
+def test_import_mesh_from_the_xdmf_pair(tmp_path, binary):
+    """The reference's own inputs (utils_dolfinx.py:92-107: <prefix>_domain.xdmf with the cell tags, <prefix>_boundaries.xdmf
+    with the tagged lines) when their data items are inline XML or raw binary; HDF5 items fall back to the .msh or raise."""
+    from femo_b200.fea.utils_b200 import import_mesh
+    from femo_b200.fea.fem import Measure
+    m = om.unit_square_tri(4, 4)
+    cx = m.coords[m.cells].mean(axis=1)[:, 0]
+    tri_tags = np.where(cx < 0.5, 1, 3)
+    col = np.nonzero(np.isclose(m.coords[:, 0], 0.5))[0]
+    col = col[np.argsort(m.coords[col, 1])]
+    lines = np.array([(int(a), int(b)) for a, b in zip(col[:-1], col[1:])])
+    bd = tmp_path if binary else None
+    _write_xdmf(tmp_path / 'motor_domain.xdmf', m.coords, 'Triangle', m.cells, 'name_to_read', tri_tags, bd)
+    _write_xdmf(tmp_path / 'motor_boundaries.xdmf', m.coords, 'Polyline', lines, 'name_to_read', [1000] * len(lines), bd)
+    (tmp_path / 'motor_association_table.ini').write_text('[ASSOCIATION TABLE]\ninterface = 1000\nsteel = 1\nmagnet = 3\n')
+    mesh, boundaries_mf, subdomains_mf, table = import_mesh(prefix='motor', subdomains=True, dim=2, directory=str(tmp_path))
+    assert table == dict(interface=1000, steel=1, magnet=3)
+    assert np.array_equal(mesh.cells, m.cells) and np.array_equal(mesh.geometry.x[:, :2], m.coords[:, :2])
+    assert np.array_equal(subdomains_mf.values, tri_tags)
+    fc, fl = Measure('dS', domain=mesh, subdomain_data=boundaries_mf)(1000).sides
+    assert len(fc) == 2 * len(lines)
+    # HDF5 heavy data: a clear error when there is no .msh to fall back to
+    (tmp_path / 'h_domain.xdmf').write_text((tmp_path / 'motor_domain.xdmf').read_text().replace('Format="XML"', 'Format="HDF"')
+                                            .replace('Format="Binary"', 'Format="HDF"'))
+    (tmp_path / 'h_boundaries.xdmf').write_text((tmp_path / 'motor_boundaries.xdmf').read_text())
+    with pytest.raises(NotImplementedError, match='h5py'):
+        import_mesh(prefix='h', subdomains=True, dim=2, directory=str(tmp_path))
