@@ -251,7 +251,11 @@ static int mgfused_vcycle(femo_problem *root, int lv, const double *b, double *x
     if (lv > P.k0 && (b != L->mgl.b || x != L->mgl.x)) return FEMO_OK;
     const MgOp *ops = root->d_mgops + first;
     void *args[] = {(void *)&ops, (void *)&count, (void *)&b0, (void *)&x0};
-    FEMO_CUDA(cudaLaunchCooperativeKernel((const void *)k_mg_fused, dim3(root->num_sms), dim3(kMgFusedThreads), args, 0, root->stream));
+    // grid: one thread per row of the largest fused level is enough (a grid-wide barrier costs more the more CTAs arrive);
+    // never more than one CTA per SM (co-residency of the cooperative launch)
+    int64_t ctas = g_env.mgfused_ctas > 0 ? g_env.mgfused_ctas : (mg_level(root, P.k0)->state.ndofs + kMgFusedThreads - 1) / kMgFusedThreads;
+    ctas = std::max<int64_t>(8, std::min<int64_t>(ctas, root->num_sms));
+    FEMO_CUDA(cudaLaunchCooperativeKernel((const void *)k_mg_fused, dim3((unsigned)ctas), dim3(kMgFusedThreads), args, 0, root->stream));
     L->launches++;
     *done = true;
     return FEMO_OK;

@@ -91,16 +91,12 @@ struct DiaEpi {
 
 // One thread per row, 32-bit index arithmetic (int32 dofs), and an interior fast path without per-neighbour range
 // checks (only the first and last w+1 rows of a lattice can reach outside [0,n)).  PRE2 gathers the scaled right-hand
-// side c0 * dinv_j * b_j at the 7 neighbours from the dinv plane (no reciprocals, no staging).
-// per-thread asynchronous global -> shared copies (LDGSTS): in flight without occupying registers
-__device__ __forceinline__ void cp_async8(double *smem, const double *g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async4(float *smem, const float *g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
+// side c0 * dinv_j * b_j at the 7 neighbours from the dinv plane (no reciprocals, no staging).  PRE2 runs at 0.77 of
+// the HBM peak where the other epilogues reach 0.95 - 1.00; ncu (profiles/r02_ncu_full_probe.csv) shows no saturated
+// unit (DRAM 61 %, L2 40 %, L1 45 %, issue 39 %): the 14 gathers are consumed pairwise by their products, so a row
+// exposes several memory round trips.  Two restructurings were measured and dropped (profiles/r02_summary.md): staging
+// the gathers with 4 / 8-byte cp.async (211 us against 152 us) and a shared-memory tile of the three neighbour runs
+// with coalesced loads (158 us).
 template <int MODE, int D>
 __global__ void __launch_bounds__(kThreads)
     k_dia_apply(DiaMat A, const double *__restrict__ x, double *__restrict__ y, DiaEpi E) {
@@ -122,33 +118,13 @@ __global__ void __launch_bounds__(kThreads)
     const double *__restrict__ src = (MODE == DIA_PRE2) ? E.b : x;
     const bool interior = i + A.off[0] >= 0 && i + A.off[D - 1] < n;
     double xv[D];
-    double bi = 0.0;
-    if constexpr (MODE == DIA_PRE2) {
-        // The 7 + 6 neighbour gathers (b_j and the scaling 1/a_jj) go through per-thread shared-memory slots with
-        // cp.async: all of them are in flight at once without holding registers.  Written as plain loads the compiler
-        // keeps the kernel at 32 registers by interleaving load pairs with their products, which exposes 7 memory round
-        // trips per row (ncu r2y: 61 % DRAM utilisation, long-scoreboard bound, 151 us against 108 us of traffic).
-        __shared__ double sb[D][kThreads];
-        __shared__ float sd[D][kThreads];
-        const int tid = threadIdx.x;
-#pragma unroll
-        for (int s = 0; s < D; ++s) {
-            const int j = i + A.off[s];
-            if (interior || (j >= 0 && j < n)) {
-                cp_async8(&sb[s][tid], src + j);
-                if (s != SD) cp_async4(&sd[s][tid], dinvp + j);
-            } else {
-                sb[s][tid] = 0.0;
-                sd[s][tid] = 0.0f;
-            }
-        }
-        cp_async_wait_all();
-#pragma unroll
-        for (int s = 0; s < D; ++s) xv[s] = sb[s][tid] * ((s == SD) ? di : (double)sd[s][tid]);
-        bi = sb[SD][tid];
-    } else if (interior) {
+    if (interior) {
 #pragma unroll
         for (int s = 0; s < D; ++s) xv[s] = __ldg(src + (i + A.off[s]));
+        if (MODE == DIA_PRE2) {
+#pragma unroll
+            for (int s = 0; s < D; ++s) xv[s] *= (s == SD) ? di : (double)__ldg(dinvp + (i + A.off[s]));
+        }
     } else {
 #pragma unroll
         for (int s = 0; s < D; ++s) {
@@ -166,7 +142,7 @@ __global__ void __launch_bounds__(kThreads)
     }
     if (MODE == DIA_PRE2) {             // xv = dinv_j b_j ; d0 = c0 xv ; r = b_i - A d0 ; x = d0 + c1 d0 + c2 dinv_i r
         const double d0i = E.c0 * xi;
-        const double r = bi - E.c0 * acc;
+        const double r = __ldg(E.b + i) - E.c0 * acc;
         y[i] = d0i + E.c1 * d0i + E.c2 * di * r;
     } else if (MODE == DIA_PLAIN) {
         y[i] = E.b ? E.b[i] - acc : acc;
