@@ -84,6 +84,7 @@ SIGNATURES = {
                                      C.c_int, C.POINTER(_P)]),
     'femo_problem_slab_info': (C.c_int, [_P, _I64P]),
     'femo_halo_exchange': (C.c_int, [_P, _P, C.c_int]),
+    'femo_problem_set_partition': (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, _P, _P, _I64P]),
     'femo_problem_mesh_sizes': (C.c_int, [_P, _I64P]),
     'femo_problem_mesh_copy': (C.c_int, [_P, C.c_int, _P]),
     'femo_problem_enable_multigrid': (C.c_int, [_P]),

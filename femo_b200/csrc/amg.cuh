@@ -57,6 +57,7 @@ struct AmgLevelDev {
     int p_nrb = 0, r_nrb = 0;
     double *p_vals = nullptr, *r_vals = nullptr, *ap_vals = nullptr;
     double *dense = nullptr, *dense_tmp = nullptr;
+    bool halo = false;                      // level 0 of an unstructured partition: refresh the ghost dofs before every operator application
 };
 
 struct femo_amg {
@@ -142,7 +143,11 @@ static int amg_attach(femo_problem *p, femo_amg *G, void *d_arena, size_t bytes)
 
 // one operator application of a level with the epilogue `epi` (CSR-stream SpMV of engine.cu)
 static int amg_apply(femo_problem *p, const int32_t *rb, int nrb, const int32_t *rowptr, const int32_t *col, const double *vals,
-                     int epi, const double *x, double *y, const SpmvEpi &E) {
+                     int epi, const double *x, double *y, const SpmvEpi &E, bool halo = false) {
+    if (halo) {
+        int rc = halo_nodes(p, const_cast<double *>(x));
+        if (rc) return rc;
+    }
     const int grid = spmv_grid(p, nrb);
     cudaStream_t st = p->stream;
     if (epi == EPI_PLAIN) k_spmv<false, EPI_PLAIN, double><<<grid, kThreads, 0, st>>>(rb, nrb, rowptr, col, vals, x, y, E, nullptr);
@@ -157,10 +162,15 @@ static int amg_apply(femo_problem *p, const int32_t *rb, int nrb, const int32_t 
 // numeric phase: every level's diagonal / Gershgorin bound, prolongator, restriction and Galerkin operator from `vals`
 static int amg_numeric(femo_problem *p, femo_amg *G, const double *vals) {
     if (!G || !G->attached) return set_err(FEMO_ESTATE, "precond 4 (AMG) needs femo_amg_symbolic + femo_amg_attach first");
-    if (p->slab.active) return set_err(FEMO_ESTATE, "the AMG preconditioner runs on one GPU (slab problems use the lattice hierarchy)");
+    if (p->slab.active) return set_err(FEMO_ESTATE, "slab problems use the lattice hierarchy, not the AMG preconditioner");
     cudaStream_t st = p->stream;
     const int nl = (int)G->lv.size();
     G->lv[0].vals = const_cast<double *>(vals);
+    // Unstructured partition: level 0 is the distributed operator itself (its smoother exchanges halos and uses the global
+    // Gershgorin bound, so every rank runs the same Chebyshev polynomial on its owned rows); the coarse correction is local
+    // to the rank -- ghost rows have empty prolongator rows, so they neither restrict nor receive corrections: a symmetric
+    // two-level additive-in-the-coarse-space preconditioner without communication below level 0.
+    G->lv[0].halo = p->gpart.active;
     int rc;
     for (int l = 0; l < nl; ++l) {
         AmgLevelDev &L = G->lv[l];
@@ -168,6 +178,7 @@ static int amg_numeric(femo_problem *p, femo_amg *G, const double *vals) {
         k_diag_gershgorin<<<g, kThreads, 0, st>>>(L.rowptr, L.col, L.vals, L.dinv, L.n, 0, L.n, p->d_partials);
         k_max_finalize<<<1, kThreads, 0, st>>>(p->d_partials, g, p->d_scalars, S_GM + l);
         p->launches += 2;
+        if (l == 0 && p->gpart.active && (rc = allreduce_scalars(p, S_GM, 1, true))) return rc;
         if (l + 1 < nl) {
             AmgLevelDev &C = G->lv[l + 1];
             k_amg_prolongator<<<grid_for(L.nnzP), kThreads, 0, st>>>(L.pp_ptr, L.pp_src, L.p_row, L.col, L.vals, L.dinv, p->d_scalars,
@@ -214,7 +225,7 @@ static int amg_smooth(femo_problem *p, AmgLevelDev &L, const double *b, double *
     } else {
         SpmvEpi E;
         E.b = b; E.dinv = L.dinv; E.rout = L.r; E.dout = dcur; E.c1 = 1.0 / theta;
-        if ((rc = amg_apply(p, L.rb, L.nrb, L.rowptr, L.col, L.vals, EPI_CHEB0, x, nullptr, E))) return rc;
+        if ((rc = amg_apply(p, L.rb, L.nrb, L.rowptr, L.col, L.vals, EPI_CHEB0, x, nullptr, E, L.halo))) return rc;
         if (deg <= 1) {
             k_axpy<<<g, kThreads, 0, st>>>(1.0, dcur, x, n);
             p->launches++;
@@ -229,7 +240,7 @@ static int amg_smooth(femo_problem *p, AmgLevelDev &L, const double *b, double *
         SpmvEpi E;
         E.dinv = L.dinv; E.rin = rin; E.rout = L.r; E.dout = dnext; E.xacc = x;
         E.c1 = rho_new * rho; E.c2 = 2.0 * rho_new / delta; E.xmode = xmode;
-        if ((rc = amg_apply(p, L.rb, L.nrb, L.rowptr, L.col, L.vals, EPI_CHEBK, dcur, nullptr, E))) return rc;
+        if ((rc = amg_apply(p, L.rb, L.nrb, L.rowptr, L.col, L.vals, EPI_CHEBK, dcur, nullptr, E, L.halo))) return rc;
         std::swap(dcur, dnext);
         rin = L.r;
         xmode = 0;
@@ -261,7 +272,7 @@ static int amg_vcycle(femo_problem *p, femo_amg *G, int l, const double *b, doub
     if ((rc = amg_smooth(p, L, b, x, true, ap.degree, ap.ratio))) return rc;
     SpmvEpi E;
     E.b = b;
-    if ((rc = amg_apply(p, L.rb, L.nrb, L.rowptr, L.col, L.vals, EPI_PLAIN, x, L.r, E))) return rc;                    // r = b - A x
+    if ((rc = amg_apply(p, L.rb, L.nrb, L.rowptr, L.col, L.vals, EPI_PLAIN, x, L.r, E, L.halo))) return rc;            // r = b - A x
     if ((rc = amg_apply(p, L.r_rb, L.r_nrb, L.r_rowptr, L.r_col, L.r_vals, EPI_PLAIN, L.r, C.b, SpmvEpi()))) return rc;   // bc = P^T r
     if ((rc = amg_vcycle(p, G, l + 1, C.b, C.x, ap))) return rc;
     if ((rc = amg_apply(p, L.p_rb, L.p_nrb, L.p_rowptr, L.p_col, L.p_vals, EPI_ADD, C.x, x, SpmvEpi()))) return rc;       // x += P xc

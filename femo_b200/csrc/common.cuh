@@ -78,6 +78,18 @@ struct SlabInfo {
     int own0 = 0, own1 = 0, cown0 = 0, cown1 = 0;
 };
 
+// General cell partition of an unstructured mesh (femo_b200/partition.py): this rank's problem lives on its LOCAL mesh --
+// owned dofs first ([0, n_owned_dofs)), ghost dofs after them, owned cells first.  A halo exchange packs the owned values the
+// neighbours hold as ghosts, all-gathers the (equal-sized, boundary-sized) send buffers of all ranks and scatters the
+// entries this rank's ghosts need: one pack kernel, one collective of the existing transports, one unpack kernel.
+struct GenPart {
+    bool active = false;
+    int64_t n_owned_dofs = 0, n_owned_cells = 0, blk = 0;     // blk: doubles per rank in the gathered buffer
+    std::vector<int32_t> send_idx, ghost_src;                  // local dof -> send slot ; ghost dof k -> index into the gathered buffer
+    int32_t *d_send_idx = nullptr, *d_ghost_src = nullptr;
+    double *d_gather = nullptr;
+};
+
 struct DevPattern {
     int32_t *rowptr = nullptr, *col = nullptr, *gptr = nullptr, *gsrc = nullptr;
     int32_t *t_rowptr = nullptr, *t_col = nullptr, *t_perm = nullptr;
@@ -246,6 +258,7 @@ struct femo_problem {
     MgFusedProg mgprog;
     femo::MgOp *d_mgops = nullptr;
     std::vector<femo::MgOp> h_mgops;
+    femo::GenPart gpart;                     // unstructured partition (inactive on lattices / one GPU)
     struct femo_amg *amg = nullptr;          // smoothed-aggregation hierarchy (precond 4; amg.cuh), owned
     long long launches = 0;
     long long graph_replays = 0;             // PCG iterations replayed from a captured CUDA graph

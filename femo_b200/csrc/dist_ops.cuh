@@ -52,6 +52,38 @@ static int link_gather(femo_problem *p, double *g, size_t blk, size_t tail) {
     return FEMO_OK;
 }
 
+namespace femo {
+__global__ void __launch_bounds__(kThreads)
+    k_gpart_pack(const double *__restrict__ v, const int32_t *__restrict__ idx, int64_t n, double *__restrict__ out) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) out[t] = v[idx[t]];
+}
+__global__ void __launch_bounds__(kThreads)
+    k_gpart_unpack(const double *__restrict__ gathered, const int32_t *__restrict__ src, int64_t n, double *__restrict__ ghosts) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) ghosts[t] = gathered[src[t]];
+}
+}  // namespace femo
+
+static inline bool partitioned(const femo_problem *p) { return p->slab.active || p->gpart.active; }
+static int gather_cell_rows(femo_problem *p, double *g, size_t len, int gn);
+
+// ghost refresh of an unstructured partition: pack -> all-gather of the ranks' send buffers -> scatter into the ghost range
+static int gpart_halo(femo_problem *p, double *v) {
+    GenPart &G = p->gpart;
+    if (!g_comm.active) return FEMO_OK;
+    if (!G.d_gather) return set_err(FEMO_ESTATE, "partitioned problem: upload before exchanging halos");
+    const int64_t ns = (int64_t)G.send_idx.size(), ng = (int64_t)G.ghost_src.size();
+    if (ns) k_gpart_pack<<<(int)((ns + kThreads - 1) / kThreads), kThreads, 0, p->stream>>>(v, G.d_send_idx, ns, G.d_gather + (size_t)g_comm.rank * G.blk);
+    int rc = gather_cell_rows(p, G.d_gather, (size_t)G.blk, g_comm.nranks);
+    if (rc) return rc;
+    if (ng) k_gpart_unpack<<<(int)((ng + kThreads - 1) / kThreads), kThreads, 0, p->stream>>>(G.d_gather, G.d_ghost_src, ng, v + G.n_owned_dofs);
+    p->launches += (ns ? 1 : 0) + (ng ? 1 : 0);
+    g_comm.halo_exchanges++;
+    FEMO_CHECK_LAUNCH();
+    return FEMO_OK;
+}
+
 // Refresh the ghost node rows of a state-space vector (ghostUpdate FORWARD of the reference,
 // utils_dolfinx.py:167): whole lattice rows are contiguous, so rows are sent in place.
 static int halo_nodes(femo_problem *p, double *v, cudaStream_t st = nullptr) {
@@ -60,6 +92,7 @@ static int halo_nodes(femo_problem *p, double *v, cudaStream_t st = nullptr) {
         p->skip_next_halo = false;
         return FEMO_OK;
     }
+    if (p->gpart.active) return gpart_halo(p, v);
     if (!s.active || !g_comm.active) return FEMO_OK;
     if (!st) st = p->stream;
     const size_t len = (size_t)(p->mesh.n[0] + 1) * (p->mesh.kind == MESH_HEX ? (size_t)(p->mesh.n[1] + 1) : 1) * p->state.block;
@@ -156,7 +189,7 @@ static int halo_cells(femo_problem *p, double *v) {
 
 // Sum (or max) `count` device scalars starting at `slot` over all ranks, in place.
 static int allreduce_scalars(femo_problem *p, int slot, int count, bool is_max = false) {
-    if (!g_comm.active || (!p->slab.active)) return FEMO_OK;
+    if (!g_comm.active || !partitioned(p)) return FEMO_OK;
     if (g_link.active) return link_allreduce(p, p->d_scalars + slot, count, is_max);
     FEMO_NCCL(g_comm.api.AllReduce(p->d_scalars + slot, p->d_scalars + slot, (size_t)count, ncclDouble,
                                    is_max ? ncclMax : ncclSum, g_comm.comm, p->stream));

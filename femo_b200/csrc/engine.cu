@@ -2121,6 +2121,61 @@ int femo_comm_stats(long long stats[2]) {
     return FEMO_OK;
 }
 
+/* Unstructured partitions (femo_b200/partition.py): see include/femo_b200.h. */
+int femo_problem_set_partition(femo_problem *p, int64_t n_owned_nodes, int64_t n_owned_cells, int64_t blk_nodes, int64_t n_send,
+                               const int32_t *send_nodes, int64_t n_ghost, const int32_t *ghost_src_nodes, void *d_buf,
+                               int64_t *bytes) {
+    int rc;
+    if ((rc = need_device(p))) return rc;
+    if (!bytes || n_owned_nodes < 0 || n_owned_cells < 0 || blk_nodes < 0 || (n_send && !send_nodes) || (n_ghost && !ghost_src_nodes))
+        return set_err(FEMO_EINVAL, "femo_problem_set_partition: bad arguments");
+    if (p->slab.active) return set_err(FEMO_ESTATE, "femo_problem_set_partition: slab problems carry their own partition");
+    const int b = p->state.block;
+    const int64_t N = p->state.ndofs, nn = N / b;
+    if (n_owned_nodes + n_ghost != nn || n_owned_cells > p->mesh.ncells)
+        return set_err(FEMO_EINVAL, "femo_problem_set_partition: owned + ghost nodes must cover the local mesh (owned first)");
+    const int R = std::max(1, g_comm.nranks);
+    const int64_t ns = n_send * b, ng = n_ghost * b, blk = std::max<int64_t>(1, blk_nodes * b);
+    const size_t need = Arena::need(std::max<int64_t>(ns, 1), 4) + Arena::need(std::max<int64_t>(ng, 1), 4) +
+                        Arena::need((size_t)blk * R, 8) + 1024;
+    if (!d_buf) {
+        *bytes = (int64_t)need;
+        return FEMO_OK;
+    }
+    if (*bytes < (int64_t)need) return set_err(FEMO_EINVAL, "femo_problem_set_partition: buffer smaller than the size query reported");
+    GenPart &G = p->gpart;
+    G.send_idx.resize(ns);
+    G.ghost_src.resize(ng);
+    for (int64_t k = 0; k < n_send; ++k) {
+        if (send_nodes[k] < 0 || send_nodes[k] >= n_owned_nodes) return set_err(FEMO_EINVAL, "femo_problem_set_partition: send list entry is not an owned node");
+        for (int c = 0; c < b; ++c) G.send_idx[k * b + c] = send_nodes[k] * b + c;
+    }
+    for (int64_t k = 0; k < n_ghost; ++k) {
+        const int64_t q = blk_nodes ? ghost_src_nodes[k] / blk_nodes : 0, pos = blk_nodes ? ghost_src_nodes[k] % blk_nodes : 0;
+        if (q < 0 || q >= R) return set_err(FEMO_EINVAL, "femo_problem_set_partition: ghost source outside the gathered buffer");
+        for (int c = 0; c < b; ++c) G.ghost_src[k * b + c] = (int32_t)(q * blk + pos * b + c);
+    }
+    G.n_owned_dofs = n_owned_nodes * b;
+    G.n_owned_cells = n_owned_cells;
+    G.blk = blk;
+    Arena A;
+    A.reset(d_buf, (size_t)*bytes);
+    G.d_send_idx = A.take<int32_t>(std::max<int64_t>(ns, 1));
+    G.d_ghost_src = A.take<int32_t>(std::max<int64_t>(ng, 1));
+    G.d_gather = A.take<double>((size_t)blk * R);
+    if (!G.d_send_idx || !G.d_ghost_src || !G.d_gather) return set_err(FEMO_EINVAL, "femo_problem_set_partition: buffer too small");
+    FEMO_CUDA(cudaSetDevice(p->device));
+    if (ns) FEMO_CUDA(cudaMemcpy(G.d_send_idx, G.send_idx.data(), ns * 4, cudaMemcpyHostToDevice));
+    if (ng) FEMO_CUDA(cudaMemcpy(G.d_ghost_src, G.ghost_src.data(), ng * 4, cudaMemcpyHostToDevice));
+    FEMO_CUDA(cudaMemset(G.d_gather, 0, (size_t)blk * R * 8));
+    p->own_off = 0;
+    p->own_n = G.n_owned_dofs;
+    p->cown_off = 0;
+    p->cown_n = n_owned_cells;
+    G.active = true;
+    return FEMO_OK;
+}
+
 /* refresh the ghost rows of a state-space (kind 0) or cell-wise input (kind 1) vector */
 int femo_halo_exchange(femo_problem *p, double *d_v, int kind) {
     int rc;
@@ -2282,10 +2337,12 @@ int femo_assemble_output(femo_problem *p, int out_id, double *h_value) {
     // on several GPUs every cell is summed by the rank that owns it
     const double *src = p->d_scratch;
     int64_t cnt = n;
-    if (p->slab.active) {
+    if (partitioned(p)) {
         if (om == 1) {
             src += p->cown_off;
             cnt = p->cown_n;
+        } else if (p->gpart.active) {
+            return set_err(FEMO_EINVAL, "facet functionals are not partitioned on unstructured meshes");
         } else if (om == 2) {           // facets are sorted by cell: the owned ones are a suffix
             src += p->fown_off;
             cnt = (int64_t)p->fb_cell.size() - p->fown_off;
@@ -2342,8 +2399,8 @@ int femo_assemble_output_and_grad(femo_problem *p, int out_id, double *h_value, 
     p->launches++;
     FEMO_CHECK_LAUNCH();
     if ((rc = segreduce(p, p->dvm_state[1], p->state.ndofs, d_dJdu))) return rc;
-    const double *src = p->d_scratch + 3 * nc + (p->slab.active ? p->cown_off : 0);
-    const int64_t cnt = p->slab.active ? p->cown_n : nc;
+    const double *src = p->d_scratch + 3 * nc + (partitioned(p) ? p->cown_off : 0);
+    const int64_t cnt = partitioned(p) ? p->cown_n : nc;
     const int g = red_grid(p, cnt);
     k_sum<<<g, kThreads, 0, p->stream>>>(src, cnt, p->d_partials);
     p->launches++;
@@ -2463,9 +2520,17 @@ int femo_amg_symbolic(femo_problem *p, const double *h_vals, const femo_amg_opts
     }
     delete p->amg;
     p->amg = new femo_amg();
+    std::vector<uint8_t> iso;
+    if ((p->has_bc && !p->bc_mark.empty()) || p->gpart.active) {
+        // rows the coarse correction leaves alone: Dirichlet rows, and on a partition the ghost rows (below level 0 the
+        // hierarchy is local to the rank, amg.cuh)
+        iso.assign(P.nrows, 0);
+        if (p->has_bc && !p->bc_mark.empty()) iso = p->bc_mark;
+        if (p->gpart.active)
+            for (int64_t r = p->gpart.n_owned_dofs; r < P.nrows; ++r) iso[r] = 1;
+    }
     try {
-        amg_build(P.rowptr.data(), P.col.data(), P.nrows, h_vals, p->has_bc && !p->bc_mark.empty() ? p->bc_mark.data() : nullptr, o,
-                  p->amg->host);
+        amg_build(P.rowptr.data(), P.col.data(), P.nrows, h_vals, iso.empty() ? nullptr : iso.data(), o, p->amg->host);
     } catch (const LayoutError &e) {
         delete p->amg;
         p->amg = nullptr;

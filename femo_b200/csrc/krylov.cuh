@@ -167,7 +167,7 @@ static void default_krylov(femo_krylov_opts &o) {
 
 // sum of partials -> scalar slot(s) -> all ranks
 static int reduce_to(femo_problem *p, const double *pa, const double *pb, int np, int slotA, int slotB) {
-    if (g_link.active && g_comm.active && p->slab.active && (!pb || slotB == slotA + 1)) {
+    if (g_link.active && g_comm.active && partitioned(p) && (!pb || slotB == slotA + 1)) {
         // block sums of the partials and the all-reduce over the ranks in ONE kernel (link.cuh)
         const unsigned int seq = ++g_link.seq_ar;
         k_link_allreduce<<<1, kThreads, 0, p->stream>>>(g_link.dev(), p->d_scalars, pb ? 2 : 1, 0, pa, pb, np, slotA, slotB, seq);

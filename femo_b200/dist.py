@@ -115,3 +115,41 @@ class SlabProblem(_E.EngineProblem):
     def owned(self, tensor):
         """The owned block of a local state-space vector."""
         return tensor[self.slab['own_off']:self.slab['own_off'] + self.slab['own_n']]
+
+
+class PartProblem(_E.EngineProblem):
+    """One rank's problem on an unstructured partition (femo_b200/partition.py): the local mesh -- owned cells + the
+    ghost cells around the owned vertices, owned vertices numbered first -- as an ordinary engine problem plus the
+    scatter lists of the ghost refresh (femo_problem_set_partition).  Assembly needs no communication; SpMV / Krylov /
+    Newton exchange halos and all-reduce inside the engine exactly as on slabs."""
+
+    def __init__(self, family, views, rank, kind='triangle', params=(), tagged=None):
+        from . import partition as _P
+        self.view = views[rank]
+        self.views = views
+        self._layout = _P.gather_layout(views)
+        mesh = _E.EngineMesh.from_arrays(kind, self.view.coords, self.view.cells)
+        super().__init__(mesh, family, params, tagged)
+
+    def upload(self, device=0):
+        import torch
+        super().upload(device)
+        v = self.view
+        blk, send_nodes, ghost_src = self._layout
+        sn = np.ascontiguousarray(send_nodes[v.rank], dtype=np.int32)
+        gs = np.ascontiguousarray(ghost_src[v.rank], dtype=np.int32)
+        nbytes = C.c_int64(0)
+        args = (self._h, int(v.n_owned_verts), int(v.n_owned_cells), int(blk), sn.size, sn.ctypes.data_as(C.c_void_p), gs.size,
+                gs.ctypes.data_as(C.c_void_p))
+        check(lib.femo_problem_set_partition(*args, None, C.byref(nbytes)))
+        self._part_buf = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        check(lib.femo_problem_set_partition(*args, C.c_void_p(self._part_buf.data_ptr()), C.byref(nbytes)))
+        return self
+
+    def owned(self, tensor):
+        b = self.N // self.view.verts_global.size
+        return tensor[:self.view.n_owned_verts * b]
+
+    def halo(self, tensor, kind=0):
+        check(lib.femo_halo_exchange(self._h, C.c_void_p(tensor.data_ptr()), 0))
+        return tensor

@@ -144,3 +144,28 @@ def exchange(views_or_view, vec, block=1, group=None):
     for q, (a, b) in recv.items():
         t[a:b] = bufs[q]
     return vec
+
+
+def gather_layout(views):
+    """Index lists of the engine's ghost refresh (csrc/dist_ops.cuh, gpart_halo): every rank packs the owned values its
+    neighbours need into a send buffer (segments ordered by destination rank), the buffers of all ranks -- padded to the
+    longest, `blk` nodes -- are all-gathered, and ghost j of rank r reads entry q*blk + offset(q -> r) + position.
+    -> blk, [send_nodes of rank r], [ghost_src of rank r] (node level; the engine expands by the block size)."""
+    R = len(views)
+    send_nodes, offsets = [], []
+    for m in views:
+        off, parts, o = {}, [], 0
+        for q in sorted(m.send):
+            off[q] = o
+            parts.append(m.send[q])
+            o += m.send[q].size
+        send_nodes.append(np.concatenate(parts).astype(np.int32) if parts else np.zeros(0, dtype=np.int32))
+        offsets.append(off)
+    blk = max([s.size for s in send_nodes] + [1])
+    ghost_src = []
+    for m in views:
+        g = np.zeros(m.verts_global.size - m.n_owned_verts, dtype=np.int32)
+        for q, (a, b) in m.recv.items():
+            g[a - m.n_owned_verts:b - m.n_owned_verts] = q * blk + offsets[q][m.rank] + np.arange(b - a)
+        ghost_src.append(g)
+    return blk, send_nodes, ghost_src

@@ -153,6 +153,18 @@ int femo_problem_slab_info(const femo_problem *p, int64_t info[16]);
  * 4 = edge -> vertices (nedges,2) and 5 = cell -> edges (ncells,3), nedges = state dofs - vertices */
 int femo_problem_mesh_sizes(const femo_problem *p, int64_t sizes[6]);
 int femo_problem_mesh_copy(const femo_problem *p, int what, void *out);
+/* Unstructured partitions (the engine-side counterpart of dolfinx's partitioner + index maps under MPI.COMM_WORLD,
+ * utils_dolfinx.py:32,140-153; lists from femo_b200/partition.py).  The problem was created on this rank's LOCAL mesh:
+ * owned nodes first, ghost nodes after them, owned cells first.  After femo_problem_upload: reductions and cell
+ * functionals run over the owned ranges, every operator application refreshes the ghost dofs of its input (pack the
+ * `n_send` owned nodes `send_nodes` the neighbours hold as ghosts -> all-gather of the ranks' send buffers, `blk_nodes`
+ * nodes each -> ghost k reads gathered node `ghost_src_nodes[k]` = owner * blk_nodes + position), Krylov scalars are
+ * all-reduced, and the AMG preconditioner (precond 4) smooths on the distributed level 0 (halo exchanges, global Chebyshev
+ * bound) with a coarse correction local to the rank.
+ * d_buf: caller-provided device buffer; call with d_buf = NULL to get the required size in *bytes. */
+int femo_problem_set_partition(femo_problem *p, int64_t n_owned_nodes, int64_t n_owned_cells, int64_t blk_nodes, int64_t n_send,
+                               const int32_t *send_nodes, int64_t n_ghost, const int32_t *ghost_src_nodes, void *d_buf,
+                               int64_t *bytes);
 /* refresh ghost rows of a device vector: kind 0 = state-space (nodes), 1 = cell-wise input */
 int femo_halo_exchange(femo_problem *p, double *d_v, int kind);
 

@@ -1,0 +1,130 @@
+"""Multi-rank run on an UNSTRUCTURED partition (torchrun, one rank per GPU or all ranks on cuda:0): a perturbed, cell-shuffled
+triangle mesh cut by femo_b200.partition (RCB, owned-first numbering, one-cell ghost layer), the Poisson family of
+examples/poisson_opt with Dirichlet rows, against the unpartitioned problem on the same GPU: owned rows of the residual
+and of an SpMV with poisoned ghosts, the all-reduced functional, the AMG-preconditioned CG solve, the Newton state and the
+adjoint total derivative dJ/df on the owned cells.  Exit code 0 = every rank agrees."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+from femo_b200 import engine as E  # noqa: E402
+from femo_b200 import dist as fd  # noqa: E402
+from femo_b200 import partition as P  # noqa: E402
+
+
+def relerr(a, b):
+    den = np.max(np.abs(b))
+    return np.max(np.abs(a - b)) / (den if den > 0 else 1.0)
+
+
+def boundary_nodes(x):
+    return np.nonzero((np.abs(x[:, 0]) < 1e-9) | (np.abs(x[:, 0] - 1) < 1e-9) | (np.abs(x[:, 1]) < 1e-9) | (np.abs(x[:, 1] - 1) < 1e-9))[0]
+
+
+def main():
+    same = os.environ.get('FEMO_DIST_SAME_DEVICE') == '1'
+    lr = 0 if same else int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(lr)
+    dist.init_process_group('gloo' if same else 'nccl', **({} if same else dict(device_id=torch.device('cuda', lr))))
+    rank, R = fd.init(lr)
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 48
+    from oracle import mesh as om                           # test infrastructure: only the lattice generator
+    m0 = om.unit_square_tri(n, n + 5)
+    rng = np.random.default_rng(3)
+    x = m0.coords.copy()
+    inner = np.ones(x.shape[0], dtype=bool)
+    inner[boundary_nodes(x)] = False
+    x[inner] += 0.3 / n * (rng.random((inner.sum(), 2)) - 0.5)
+    cells = m0.cells[rng.permutation(m0.cells.shape[0])].astype(np.int64)
+    _, _, views = P.partition_mesh(x, cells, R)
+    v = views[rank]
+    # global fields (replicated), restricted to the local numbering
+    fg = 1.0 + 0.5 * np.sin(np.arange(cells.shape[0]) * 0.37)
+    ug = rng.standard_normal(x.shape[0])
+    uex = np.sin(np.pi * x[:, 0]) * np.sin(np.pi * x[:, 1]) / (2 * np.pi ** 2)
+    bg = boundary_nodes(x)
+
+    def build(prob, lx, lverts, lcells):
+        prob.set_bc([boundary_nodes(lx).astype(np.int32)])
+        prob.upload(lr)
+        u, f, ue = prob.to_device(ug[lverts]), prob.to_device(fg[lcells]), prob.to_device(uex[lverts])
+        prob.set_coefficient(0, u); prob.set_coefficient(1, f); prob.set_coefficient(2, ue)
+        return u, f, ue
+
+    p = fd.PartProblem(E.FAMILY_POISSON_P1, views, rank)
+    u, f, ue = build(p, v.coords, v.verts_global, v.cells_global)
+    pg = E.EngineProblem(E.EngineMesh.from_arrays('triangle', x, cells), E.FAMILY_POISSON_P1)
+    gu, gf, gue = build(pg, x, np.arange(x.shape[0]), np.arange(cells.shape[0]))
+    no, nc = v.n_owned_verts, v.n_owned_cells
+    own_v, own_c = v.verts_global[:no], v.cells_global[:nc]
+    fails = []
+
+    def chk(name, a, b, tol):
+        e = relerr(a, b)
+        if not e < tol:
+            fails.append('%s %.3e' % (name, e))
+
+    # assembly: owned rows complete without communication
+    chk('residual', p.assemble_residual().cpu().numpy()[:no], pg.assemble_residual().cpu().numpy()[own_v], 1e-12)
+    vals, vbc = p.assemble_jacobian(plain=True, bc=True)
+    gvals, gvbc = pg.assemble_jacobian(plain=True, bc=True)
+    # SpMV with poisoned ghosts: the engine refreshes them
+    xs = rng.standard_normal(x.shape[0])
+    xl = p.to_device(xs[v.verts_global])
+    xl[no:] = float('nan')
+    chk('spmv', p.spmv(0, vals, xl).cpu().numpy()[:no], pg.spmv(0, gvals, pg.to_device(xs)).cpu().numpy()[own_v], 1e-13)
+    J, Jg = p.assemble_output(0), pg.assemble_output(0)
+    if not abs(J - Jg) <= 1e-12 * abs(Jg):
+        fails.append('functional %r vs %r' % (J, Jg))
+    # AMG-preconditioned CG (per-rank block preconditioner) against the unpartitioned AMG-CG solve
+    p.enable_amg(vbc)
+    pg.enable_amg(gvbc)
+    b = rng.standard_normal(x.shape[0])
+    b[bg] = 0.0
+    xs1, i1 = p.linear_solve(vbc, p.to_device(b[v.verts_global]), rtol=1e-11, precond=4, cheb_degree=2, cheb_ratio=4.0)
+    xs2, i2 = pg.linear_solve(gvbc, pg.to_device(b), rtol=1e-11, precond=4, cheb_degree=2, cheb_ratio=4.0)
+    if not (i1['converged'] and i2['converged']):
+        fails.append('CG did not converge %r %r' % (i1, i2))
+    chk('linear solve', xs1.cpu().numpy()[:no], xs2.cpu().numpy()[own_v], 1e-8)
+    chk('linear solve ghosts', xs1.cpu().numpy()[no:], xs2.cpu().numpy()[v.verts_global[no:]], 1e-8)
+    if i1['iterations'] > 2 * i2['iterations'] + 10:
+        fails.append('block preconditioner too weak: %d vs %d iterations' % (i1['iterations'], i2['iterations']))
+    # state (reference's NewtonSolver, 3 fixed iterations) and the adjoint total derivative dJ/df
+    kw = dict(kind='Newton', krylov_rtol=1e-11, precond=4, cheb_degree=2, cheb_ratio=4.0)
+    p.newton_solve(**kw)
+    pg.newton_solve(**kw)
+    chk('state', u.cpu().numpy()[:no], gu.cpu().numpy()[own_v], 1e-8)
+
+    def total(prob):
+        _, a = prob.assemble_jacobian(plain=False, bc=True)
+        lam, li = prob.linear_solve(a, prob.assemble_output_grad(0, 0), transpose=True, rtol=1e-11, precond=4, cheb_degree=2,
+                                    cheb_ratio=4.0)
+        g = prob.assemble_output_grad(0, 1)
+        prob.axpy(-1.0, prob.spmv(1, prob.assemble_dRdm(0), lam, transpose=True), g)
+        return g.cpu().numpy(), li
+    gl, li = total(p)
+    gg, _ = total(pg)
+    chk('dJ/df', gl[:nc], gg[own_c], 1e-7)
+    if fd.stats()['link_error']:
+        fails.append('link transport timed out')
+    torch.cuda.synchronize()
+    flag = torch.tensor([len(fails)], device='cpu' if same else 'cuda')
+    dist.all_reduce(flag)
+    for msg in fails:
+        print('[rank %d] FAIL %s' % (rank, msg), flush=True)
+    if rank == 0:
+        print('dist_check_part n=%d ranks=%d: %s (CG iterations %d partitioned / %d single, adjoint %d)'
+              % (n, R, 'OK' if flag.item() == 0 else 'FAILED', i1['iterations'], i2['iterations'], li['iterations']), flush=True)
+    fd.finalize()
+    dist.destroy_process_group()
+    return 1 if flag.item() else 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

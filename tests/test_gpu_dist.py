@@ -50,3 +50,10 @@ def test_femo_api_on_a_partitioned_mesh(cuda_device):
     the API, halo exchanges / all-reduces inside the engine; state, functional and adjoint totals vs one GPU."""
     for k, mode in enumerate(_modes()):
         _run('dist_check_api.py', [64], 29671 + 10 * k, mode)
+
+
+def test_unstructured_partition_matches_single_gpu(cuda_device):
+    """RCB partition of a perturbed, cell-shuffled triangle mesh (femo_b200/partition.py + femo_problem_set_partition): assembly,
+    SpMV with poisoned ghosts, functional, AMG-preconditioned CG, Newton state and adjoint gradient vs the unpartitioned mesh."""
+    for k, mode in enumerate(_modes()):
+        _run('dist_check_part.py', [48], 29701 + 10 * k, mode)

@@ -101,6 +101,32 @@ def test_views_against_brute_force(R):
         assert np.array_equal(v[0::2], m.verts_global) and np.array_equal(v[1::2], m.verts_global + 0.5)
 
 
+@pytest.mark.parametrize('R', [2, 3, 4])
+def test_gather_layout_reproduces_the_exchange(R):
+    """The engine's ghost refresh (csrc/dist_ops.cuh gpart_halo) = pack, all-gather of equal blocks, scatter: emulated
+    here with the index lists handed to femo_problem_set_partition, block size 2."""
+    x, cells = _mesh(10, seed=10 + R)
+    _, _, views = P.partition_mesh(x, cells, R)
+    blk, send_nodes, ghost_src = P.gather_layout(views)
+    b = 2
+    gathered = np.full(R * blk * b, np.nan)
+    vecs = []
+    for m in views:
+        v = np.full(b * m.verts_global.size, -7.0)
+        no = m.n_owned_verts
+        v[0:b * no:b] = m.verts_global[:no]
+        v[1:b * no:b] = -m.verts_global[:no] - 0.25
+        vecs.append(v)
+        assert send_nodes[m.rank].size <= blk and np.all(send_nodes[m.rank] < no)
+        sd = (send_nodes[m.rank][:, None] * b + np.arange(b)[None, :]).ravel()          # the engine's expansion by the block size
+        gathered[m.rank * blk * b:m.rank * blk * b + sd.size] = v[sd]
+    for m, v in zip(views, vecs):
+        q, pos = ghost_src[m.rank] // blk, ghost_src[m.rank] % blk
+        gd = ((q * blk * b + pos * b)[:, None] + np.arange(b)[None, :]).ravel()
+        v[b * m.n_owned_verts:] = gathered[gd]
+        assert np.array_equal(v[0::b], m.verts_global) and np.array_equal(v[1::b], -m.verts_global - 0.25)
+
+
 def _worker(rank, R, port, q):
     import torch.distributed as dist
     dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=R)
