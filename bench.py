@@ -49,8 +49,8 @@ def workload(n, kind='p1'):
                              '216-subdomain tag layout): edge displacement -> mesh motion (2-step incremental SNES) -> '
                              'magnetostatics (5-step load ramp, SNES) -> B influence, chained EM + mesh-motion adjoints'
                              % (nr, nth, dofs, 2 * dofs, 2 * nr * nth), n=n, dofs=3 * dofs, cells=2 * nr * nth,
-                    solver='SNES newtonls; GMRES(70) right-preconditioned by a smoothed-aggregation AMG V-cycle rtol=%g replaces '
-                           'LU(MUMPS)' % KRYLOV_RTOL,
+                    solver='SNES newtonls, inexact (Eisenstat-Walker forcing, eta_max --forcing); GMRES(70) right-preconditioned by a '
+                           'smoothed-aggregation AMG V-cycle, adjoints to rtol=%g; replaces LU(MUMPS)' % KRYLOV_RTOL,
                     cache='working set exceeds the 126 MB L2; no explicit flush')
     if kind == 'hex':
         nx, ny, nz = n, n // 2, n // 4
@@ -234,7 +234,7 @@ class MotorStep:
     dR_em/duhat^T, mesh-motion adjoint solve, dR_mm/dg^T)."""
     kind = 'motor'
 
-    def __init__(self, nr, device, precond='amg'):
+    def __init__(self, nr, device, precond='amg', forcing=0.0):
         import numpy as np
         import torch
         from femo_b200 import engine as E
@@ -284,6 +284,7 @@ class MotorStep:
         else:
             self.kw = self.kw_mm = dict(method=1, precond=1, cheb_degree=24, cheb_ratio=600.0)
             self.setup = None
+        self.forcing = float(forcing)
         self.info = {}
 
     def launch_count(self):
@@ -295,12 +296,12 @@ class MotorStep:
         self.uhat.zero_()
         for i in (1, 2):                                            # solveIncremental, run_motor_opt.py:120-142
             self.torch.mul(self.g, i / 2.0, out=self.gs)
-            ni = mm.newton_solve(kind='SNES', krylov_rtol=KRYLOV_RTOL, krylov_max_it=40000, **self.kw_mm)
+            ni = mm.newton_solve(kind='SNES', krylov_rtol=KRYLOV_RTOL, krylov_max_it=40000, forcing=self.forcing, **self.kw_mm)
             its['mm_newton'] += ni['iterations']; its['mm_krylov'] += ni['krylov_iterations']
         self.A.zero_()
         for st in range(1, 6):                                      # solveIncrementalEM, :231-250
             em.set_param(6, st / 5.0)
-            ne = em.newton_solve(kind='SNES', krylov_rtol=KRYLOV_RTOL, krylov_max_it=40000, **kw)
+            ne = em.newton_solve(kind='SNES', krylov_rtol=KRYLOV_RTOL, krylov_max_it=40000, forcing=self.forcing, **kw)
             its['em_newton'] += ne['iterations']; its['em_krylov'] += ne['krylov_iterations']
         em.assemble_jacobian(out=self.vals)
         J, dJdA = em.assemble_output_and_grad(0)
@@ -515,6 +516,7 @@ def main():
                     help="p1 = BASELINE.json configs[1] (the metric's config, default); p2 / hex / motor = the P2 variant of "
                          "configs[1], the 3-D cantilever of configs[3] and the chained motor problem of configs[4], for profiles/")
     ap.add_argument('--precond', default='amg', choices=['amg', 'cheb'], help='motor workload: AMG V-cycle or the round-1 polynomial')
+    ap.add_argument('--forcing', type=float, default=0.01, help='motor workload: eta_max of the Eisenstat-Walker inexact Newton (0: every linear solve to rtol)')
     a = ap.parse_args()
     if a.workload != 'p1':
         if a.n == N_DEFAULT:
@@ -573,7 +575,7 @@ def main():
     if world > 1:
         from femo_b200 import dist as fd
         fd.init(local_rank)
-    es = MotorStep(a.n, local_rank, a.precond) if a.workload == 'motor' else EngineStep(a.n, local_rank, rank, world, a.workload)
+    es = MotorStep(a.n, local_rank, a.precond, a.forcing) if a.workload == 'motor' else EngineStep(a.n, local_rank, rank, world, a.workload)
     for _ in range(W):
         es.step()
     sampler = ClockSampler(local_rank)

@@ -20,7 +20,7 @@ class FemoError(RuntimeError):
 class KrylovOpts(C.Structure):
     _fields_ = [('rtol', C.c_double), ('atol', C.c_double), ('max_it', C.c_int), ('precond', C.c_int),
                 ('cheb_degree', C.c_int), ('method', C.c_int), ('restart', C.c_int), ('check_every', C.c_int),
-                ('cheb_ratio', C.c_double), ('mg_precision', C.c_int)]
+                ('cheb_ratio', C.c_double), ('mg_precision', C.c_int), ('forcing', C.c_double)]
 
 
 class KrylovInfo(C.Structure):

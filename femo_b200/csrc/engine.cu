@@ -2648,7 +2648,7 @@ int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton
     const bool snes = opts->kind == 1;
     double *vals_bc = p->has_bc ? p->nt_vals_bc : p->nt_vals;
     int it = 0, kit = 0, spmvs = 0, reason = 0;
-    double f0 = 0, fn = 0;
+    double f0 = 0, fn = 0, f_prev = 0, eta_prev = 0;
     bool jac_valid = false;
     // lattice P1 problems solved by GMG-PCG: the Jacobian rows go straight into the DIA planes of the solve
     DiaMat dtmp;
@@ -2685,6 +2685,20 @@ int femo_newton_solve(femo_problem *p, const femo_newton_opts *opts, femo_newton
         // change the SNES convergence decision, so the Krylov solve may stop there
         femo_krylov_opts ko = opts->krylov;
         if (snes) ko.atol = std::max(ko.atol, 0.1 * opts->atol);
+        if (opts->krylov.forcing > 0.0) {
+            // Eisenstat-Walker forcing (choice 2, gamma 0.9, alpha 2, with their safeguard): the linear tolerance follows
+            // the observed nonlinear contraction, never looser than `forcing`, never tighter than the caller's rtol
+            double eta = opts->krylov.forcing;
+            if (it > 0 && f_prev > 0.0) {
+                eta = 0.9 * (fn / f_prev) * (fn / f_prev);
+                const double guard = 0.9 * eta_prev * eta_prev;
+                if (guard > 0.1) eta = std::max(eta, guard);
+                eta = std::min(eta, opts->krylov.forcing);
+            }
+            ko.rtol = std::max(eta, opts->krylov.rtol > 0 ? opts->krylov.rtol : 1e-10);
+            eta_prev = ko.rtol;
+        }
+        f_prev = fn;
         if ((rc = (ko.method == 1 ? gmres_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki) : cg_solve(p, vals_bc, p->nt_b, p->nt_dx, ko, &ki, true, lat_direct)))) return rc;
         kit += ki.iterations;
         spmvs += ki.spmv_count;

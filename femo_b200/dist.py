@@ -123,13 +123,27 @@ class PartProblem(_E.EngineProblem):
     scatter lists of the ghost refresh (femo_problem_set_partition).  Assembly needs no communication; SpMV / Krylov /
     Newton exchange halos and all-reduce inside the engine exactly as on slabs."""
 
-    def __init__(self, family, views, rank, kind='triangle', params=(), tagged=None):
+    def __init__(self, family, views, rank, kind='triangle', params=(), cell_tags=None, facets=None):
+        """cell_tags: one subdomain id per GLOBAL cell.  facets: (global cells, local facet ids) of the one-sided facets that
+        carry facet integrals -- pass the GLOBAL mesh's exterior_facets() for forms with boundary terms (the cut faces of a
+        local mesh are not boundaries); they are restricted to this rank's local cells here."""
         from . import partition as _P
-        self.view = views[rank]
+        self.view = v = views[rank]
         self.views = views
         self._layout = _P.gather_layout(views)
-        mesh = _E.EngineMesh.from_arrays(kind, self.view.coords, self.view.cells)
-        super().__init__(mesh, family, params, tagged)
+        mesh = _E.EngineMesh.from_arrays(kind, v.coords, v.cells)
+        lt = None if cell_tags is None else np.asarray(cell_tags, dtype=np.int32)[v.cells_global]
+        lf = None
+        if facets is not None:
+            gc, gl = np.asarray(facets[0], dtype=np.int64), np.asarray(facets[1], dtype=np.int32)
+            ncg = 1 + max(int(m.cells_global.max()) for m in views)
+            g2l = np.full(ncg, -1, dtype=np.int64)
+            g2l[v.cells_global] = np.arange(v.cells_global.size)
+            keep = g2l[gc] >= 0
+            lc, ll = g2l[gc[keep]], gl[keep]
+            o = np.lexsort((ll, lc))
+            lf = (lc[o].astype(np.int32), ll[o])
+        super().__init__(mesh, family, params, facets=lf, cell_tags=lt)
 
     def upload(self, device=0):
         import torch

@@ -425,7 +425,7 @@ class EngineProblem:
 
     def newton_solve(self, kind='Newton', atol=None, rtol=None, stol=1e-8, max_it=None, krylov_rtol=1e-10,
                      krylov_max_it=100000, check_every=1, precond=0, cheb_degree=0, cheb_ratio=0.0, method=0,
-                     mg_precision=0):
+                     mg_precision=0, forcing=0.0):
         """kind 'Newton' = dolfinx NewtonSolver defaults of the reference (3 fixed
         iterations, utils_dolfinx.py:419-425); 'SNES' = PETSc newtonls (:376-416)."""
         snes = (kind == 'SNES')
@@ -437,7 +437,7 @@ class EngineProblem:
         o.max_it = (100 if snes else 3) if max_it is None else max_it
         o.krylov = KrylovOpts(rtol=krylov_rtol, atol=0.0, max_it=krylov_max_it, precond=precond,
                               cheb_degree=cheb_degree, method=method, restart=0, check_every=check_every,
-                              cheb_ratio=cheb_ratio, mg_precision=mg_precision)
+                              cheb_ratio=cheb_ratio, mg_precision=mg_precision, forcing=forcing)
         info = NewtonInfo()
         check(lib.femo_newton_solve(self._h, C.byref(o), C.byref(info)))
         return dict(iterations=info.iterations, converged=info.converged, fnorm0=info.fnorm0, fnorm=info.fnorm,

@@ -268,7 +268,8 @@ def solveNonlinear(res, func, bc, solver, report, initialize):
         info = p.newton_solve(kind=solver, krylov_rtol=KRYLOV['rtol'], krylov_max_it=KRYLOV['max_it'],
                               check_every=KRYLOV['check_every'],
                               precond=KRYLOV['precond'] if fam.precond is None else fam.precond,
-                              method=fam.method, **dict(dict(cheb_degree=KRYLOV['cheb_degree']), **fam.krylov_extra))
+                              method=fam.method, **dict(dict(cheb_degree=KRYLOV['cheb_degree']), **fam.krylov_extra),
+                              **getattr(fam, 'newton_extra', {}))
     finally:
         func.mark_device_written()
     if solver == 'SNES':

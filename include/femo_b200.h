@@ -266,6 +266,8 @@ typedef struct femo_krylov_opts {
     double cheb_ratio; /* smoother targets [lmax/ratio, lmax] of D^-1 A (default 8) */
     int mg_precision;  /* precond 2: 0 = the V-cycle streams fp32 copies of the level matrices (vectors, the outer
                           Krylov recurrence and every residual stay fp64), 1 = fp64 values throughout */
+    double forcing;    /* femo_newton_solve only: > 0 = inexact Newton, the relative tolerance of each linear solve follows
+                          Eisenstat-Walker's choice 2 between rtol and this eta_max (0: every solve to rtol) */
 } femo_krylov_opts;
 
 typedef struct femo_krylov_info {

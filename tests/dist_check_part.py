@@ -34,6 +34,7 @@ def main():
     dist.init_process_group('gloo' if same else 'nccl', **({} if same else dict(device_id=torch.device('cuda', lr))))
     rank, R = fd.init(lr)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 48
+    famid = int(sys.argv[2]) if len(sys.argv) > 2 else E.FAMILY_POISSON_P1
     from oracle import mesh as om                           # test infrastructure: only the lattice generator
     m0 = om.unit_square_tri(n, n + 5)
     rng = np.random.default_rng(3)
@@ -50,17 +51,25 @@ def main():
     uex = np.sin(np.pi * x[:, 0]) * np.sin(np.pi * x[:, 1]) / (2 * np.pi ** 2)
     bg = boundary_nodes(x)
 
-    def build(prob, lx, lverts, lcells):
-        prob.set_bc([boundary_nodes(lx).astype(np.int32)])
-        prob.upload(lr)
-        u, f, ue = prob.to_device(ug[lverts]), prob.to_device(fg[lcells]), prob.to_device(uex[lverts])
-        prob.set_coefficient(0, u); prob.set_coefficient(1, f); prob.set_coefficient(2, ue)
-        return u, f, ue
+    linear = famid == E.FAMILY_POISSON_P1
 
-    p = fd.PartProblem(E.FAMILY_POISSON_P1, views, rank)
-    u, f, ue = build(p, v.coords, v.verts_global, v.cells_global)
-    pg = E.EngineProblem(E.EngineMesh.from_arrays('triangle', x, cells), E.FAMILY_POISSON_P1)
-    gu, gf, gue = build(pg, x, np.arange(x.shape[0]), np.arange(cells.shape[0]))
+    def build(prob, lx, lverts, lcells):
+        if linear:
+            prob.set_bc([boundary_nodes(lx).astype(np.int32)])
+        prob.upload(lr)
+        u, f = prob.to_device((ug if linear else 0.2 * ug)[lverts]), prob.to_device(fg[lcells])
+        prob.set_coefficient(0, u); prob.set_coefficient(1, f)
+        if linear:
+            prob.set_coefficient(2, prob.to_device(uex[lverts]))
+        return u, f
+
+    gmesh = E.EngineMesh.from_arrays('triangle', x, cells)
+    # the nonlinear Poisson form carries Nitsche terms on the TRUE boundary: the global mesh's exterior facets, restricted per rank
+    gfac = None if linear else gmesh.exterior_facets()
+    p = fd.PartProblem(famid, views, rank, facets=gfac)
+    u, f = build(p, v.coords, v.verts_global, v.cells_global)
+    pg = E.EngineProblem(gmesh, famid, facets=gfac)
+    gu, gf = build(pg, x, np.arange(x.shape[0]), np.arange(cells.shape[0]))
     no, nc = v.n_owned_verts, v.n_owned_cells
     own_v, own_c = v.verts_global[:no], v.cells_global[:nc]
     fails = []
@@ -72,8 +81,10 @@ def main():
 
     # assembly: owned rows complete without communication
     chk('residual', p.assemble_residual().cpu().numpy()[:no], pg.assemble_residual().cpu().numpy()[own_v], 1e-12)
-    vals, vbc = p.assemble_jacobian(plain=True, bc=True)
-    gvals, gvbc = pg.assemble_jacobian(plain=True, bc=True)
+    vals, vbc = p.assemble_jacobian(plain=True, bc=linear)
+    gvals, gvbc = pg.assemble_jacobian(plain=True, bc=linear)
+    if not linear:
+        vbc, gvbc = vals, gvals
     # SpMV with poisoned ghosts: the engine refreshes them
     xs = rng.standard_normal(x.shape[0])
     xl = p.to_device(xs[v.verts_global])
@@ -86,7 +97,8 @@ def main():
     p.enable_amg(vbc)
     pg.enable_amg(gvbc)
     b = rng.standard_normal(x.shape[0])
-    b[bg] = 0.0
+    if linear:
+        b[bg] = 0.0
     xs1, i1 = p.linear_solve(vbc, p.to_device(b[v.verts_global]), rtol=1e-11, precond=4, cheb_degree=2, cheb_ratio=4.0)
     xs2, i2 = pg.linear_solve(gvbc, pg.to_device(b), rtol=1e-11, precond=4, cheb_degree=2, cheb_ratio=4.0)
     if not (i1['converged'] and i2['converged']):
@@ -96,13 +108,14 @@ def main():
     if i1['iterations'] > 2 * i2['iterations'] + 10:
         fails.append('block preconditioner too weak: %d vs %d iterations' % (i1['iterations'], i2['iterations']))
     # state (reference's NewtonSolver, 3 fixed iterations) and the adjoint total derivative dJ/df
-    kw = dict(kind='Newton', krylov_rtol=1e-11, precond=4, cheb_degree=2, cheb_ratio=4.0)
+    kw = dict(kind='Newton' if linear else 'SNES', krylov_rtol=1e-11, precond=4, cheb_degree=2, cheb_ratio=4.0)
     p.newton_solve(**kw)
     pg.newton_solve(**kw)
     chk('state', u.cpu().numpy()[:no], gu.cpu().numpy()[own_v], 1e-8)
 
     def total(prob):
-        _, a = prob.assemble_jacobian(plain=False, bc=True)
+        pl, a = prob.assemble_jacobian(plain=True, bc=linear)
+        a = a if linear else pl
         lam, li = prob.linear_solve(a, prob.assemble_output_grad(0, 0), transpose=True, rtol=1e-11, precond=4, cheb_degree=2,
                                     cheb_ratio=4.0)
         g = prob.assemble_output_grad(0, 1)
@@ -119,8 +132,8 @@ def main():
     for msg in fails:
         print('[rank %d] FAIL %s' % (rank, msg), flush=True)
     if rank == 0:
-        print('dist_check_part n=%d ranks=%d: %s (CG iterations %d partitioned / %d single, adjoint %d)'
-              % (n, R, 'OK' if flag.item() == 0 else 'FAILED', i1['iterations'], i2['iterations'], li['iterations']), flush=True)
+        print('dist_check_part n=%d family=%d ranks=%d: %s (CG iterations %d partitioned / %d single, adjoint %d)'
+              % (n, famid, R, 'OK' if flag.item() == 0 else 'FAILED', i1['iterations'], i2['iterations'], li['iterations']), flush=True)
     fd.finalize()
     dist.destroy_process_group()
     return 1 if flag.item() else 0

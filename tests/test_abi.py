@@ -32,9 +32,9 @@ def test_ctypes_table_matches_header():
     names = declared_symbols()
     assert sorted(_lib.SIGNATURES) == names, (sorted(set(names) - set(_lib.SIGNATURES)), sorted(set(_lib.SIGNATURES) - set(names)))
     # struct layouts the header declares
-    assert C.sizeof(_lib.KrylovOpts) == 56 and C.sizeof(_lib.KrylovInfo) == 32
+    assert C.sizeof(_lib.KrylovOpts) == 64 and C.sizeof(_lib.KrylovInfo) == 32       # 56 + the forcing field
     assert [f[0] for f in _lib.KrylovOpts._fields_] == ['rtol', 'atol', 'max_it', 'precond', 'cheb_degree', 'method', 'restart',
-                                                        'check_every', 'cheb_ratio', 'mg_precision']
+                                                        'check_every', 'cheb_ratio', 'mg_precision', 'forcing']
 
 
 def test_host_side_entry_points_work_without_gpu():

@@ -52,8 +52,10 @@ def test_femo_api_on_a_partitioned_mesh(cuda_device):
         _run('dist_check_api.py', [64], 29671 + 10 * k, mode)
 
 
-def test_unstructured_partition_matches_single_gpu(cuda_device):
+@pytest.mark.parametrize('famid', [1, 2])
+def test_unstructured_partition_matches_single_gpu(cuda_device, famid):
     """RCB partition of a perturbed, cell-shuffled triangle mesh (femo_b200/partition.py + femo_problem_set_partition): assembly,
-    SpMV with poisoned ghosts, functional, AMG-preconditioned CG, Newton state and adjoint gradient vs the unpartitioned mesh."""
+    SpMV with poisoned ghosts, functional, AMG-preconditioned CG, Newton / SNES state and adjoint gradient vs the unpartitioned
+    mesh; family 1 = Poisson with Dirichlet rows, family 2 = nonlinear Poisson with Nitsche terms on the true boundary facets."""
     for k, mode in enumerate(_modes()):
-        _run('dist_check_part.py', [48], 29701 + 10 * k, mode)
+        _run('dist_check_part.py', [48, famid], 29701 + 10 * k + famid, mode)
