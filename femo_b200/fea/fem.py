@@ -341,6 +341,17 @@ class Function:
     def __pow__(self, p):
         return Expr('pow', self, p)
 
+    # cell-wise algebra of DG0 functions (the UFL expressions the examples hand to `project`, e.g. the RAMP interpolation
+    # rho / (1 + 8 (1 - rho)) of examples/beam_topo_opt/run_topo_opt_cantilever_beam.py:259): evaluated pointwise per cell
+    def __add__(self, o): return Expr('op', np.add, self, o)
+    def __radd__(self, o): return Expr('op', np.add, o, self)
+    def __sub__(self, o): return Expr('op', np.subtract, self, o)
+    def __rsub__(self, o): return Expr('op', np.subtract, o, self)
+    def __mul__(self, o): return Expr('op', np.multiply, self, o)
+    def __rmul__(self, o): return Expr('op', np.multiply, o, self)
+    def __truediv__(self, o): return Expr('op', np.divide, self, o)
+    def __rtruediv__(self, o): return Expr('op', np.divide, o, self)
+
     def copy(self):
         g = Function(self.function_space, self.name)
         g._assign(self._host_array())
@@ -349,10 +360,38 @@ class Function:
 
 class Expr:
     """Stand-in for the UFL expressions handed to `project`: ('u_ex'|'f_ex') analytic fields,
-    ('pow', function, exponent)."""
+    ('pow', function, exponent), ('op', numpy ufunc, a, b) cell-wise arithmetic of DG0 functions and numbers."""
 
     def __init__(self, kind, *args):
         self.kind, self.args = kind, args
+
+    def __add__(self, o): return Expr('op', np.add, self, o)
+    def __radd__(self, o): return Expr('op', np.add, o, self)
+    def __sub__(self, o): return Expr('op', np.subtract, self, o)
+    def __rsub__(self, o): return Expr('op', np.subtract, o, self)
+    def __mul__(self, o): return Expr('op', np.multiply, self, o)
+    def __rmul__(self, o): return Expr('op', np.multiply, o, self)
+    def __truediv__(self, o): return Expr('op', np.divide, self, o)
+    def __rtruediv__(self, o): return Expr('op', np.divide, o, self)
+    def __pow__(self, p): return Expr('op', np.power, self, p)
+
+    def cellwise(self, V):
+        """Value per cell when every leaf is a DG0 function on V's mesh or a number (None otherwise)."""
+        def ev(a):
+            if isinstance(a, Function):
+                if a.function_space.family != 'DG' or a.function_space.mesh is not V.mesh:
+                    return None
+                return a._host_array()
+            if isinstance(a, Expr):
+                return a.cellwise(V)
+            return float(a) if np.ndim(a) == 0 else None
+        if self.kind == 'pow':
+            b = ev(self.args[0])
+            return None if b is None else np.power(b, float(self.args[1]))
+        if self.kind == 'op':
+            x, y = ev(self.args[1]), ev(self.args[2])
+            return None if x is None or y is None else self.args[0](x, y)
+        return None
 
 
 class Constant:

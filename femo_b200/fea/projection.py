@@ -4,6 +4,8 @@ an expression onto a CG1 / DG0 function, on the device.
 Expressions (the UFL objects the reference passes) are one of
   Expr('u_ex') / Expr('f_ex')   the analytic fields of examples/nonlinear_poisson_opt
   func ** p                     a DG0 function to a power (examples/beam_topo_opt:264-268)
+  cell-wise arithmetic          of DG0 functions and numbers, e.g. rho / (1 + 8 * (1 - rho)) (RAMP, :259): onto a DG0 target on
+                                ANY cell type (exact: the DG0 mass matrix is diagonal)
   func                          a CG1 or DG0 function
 The mass matrix and right-hand side are assembled by the projection family's kernels
 and solved with Jacobi-CG (the reference uses PETSc's default KSP at rtol 1e-5);
@@ -34,6 +36,13 @@ def project(v, target_func, bcs=[], lump_mass=False):
     if bcs:
         raise NotImplementedError('project: Dirichlet conditions are not supported')
     V = target_func.function_space
+    if V.family == 'DG' and V.block == 1 and isinstance(v, Expr):
+        # piecewise-constant expression onto DG0, any cell type (quadrilaterals / hexahedra of the topology example): the
+        # mass matrix is diag(cell volume), so the L2 projection IS the cell-wise value of the expression
+        vals = v.cellwise(V)
+        if vals is not None:
+            target_func._assign(np.ascontiguousarray(np.broadcast_to(vals, (V.local_dim,)), dtype=np.float64))
+            return target_func
     if V.mesh.cell_type != 'triangle' or V.block != 1:
         raise NotImplementedError('project: scalar CG1 / DG0 targets on triangle meshes')
     source, power, func = _source(v, target_func)

@@ -146,3 +146,22 @@ def test_density_filter_lattice_detection_and_weights_3d():
     W = sp.csr_matrix((v, (r, c)), shape=(nx * ny * nz,) * 2)
     Wo = weight_matrix(coords, 1.6, 2.0)
     assert abs(W - Wo).max() < 1e-14
+
+
+def test_project_cellwise_expressions_onto_dg0_on_quadrilaterals():
+    """examples/beam_topo_opt/run_topo_opt_cantilever_beam.py:255-260: project(rho**3, penalized) and the RAMP interpolation
+    project(rho / (1 + 8 (1 - rho)), penalized) on the quadrilateral design mesh; onto DG0 the L2 projection is cell-wise
+    exact (diagonal mass matrix), no device needed."""
+    from femo_b200.fea.fea_b200 import FunctionSpace, Function
+    from femo_b200.fea.fem import Mesh
+    from femo_b200.fea.utils_b200 import project, getFuncArray, setFuncArray
+    from femo_b200 import engine as E
+    mesh = Mesh(E.EngineMesh.rectangle_quad((0.0, 0.0), (2.0, 1.0), 8, 4), 'quadrilateral')
+    V = FunctionSpace(mesh, ('DG', 0))
+    rho, out = Function(V), Function(V)
+    r = np.linspace(0.1, 1.0, 32)
+    setFuncArray(rho, r)
+    project(rho ** 3, out)
+    assert np.allclose(getFuncArray(out), r ** 3, rtol=1e-15)
+    project(rho / (1 + 8. * (1. - rho)), out)
+    assert np.allclose(getFuncArray(out), r / (1 + 8 * (1 - r)), rtol=1e-15)
