@@ -184,3 +184,40 @@ def test_cuda_graph_replay_matches_plain_launches(cuda_device):
     assert relerr(res[0][0], res[1][0]) < 1e-11
     assert res[1][2] == 0
     assert res[0][2] == res[0][1]['iterations'] - 1, res[0][2]        # every iteration after the first is a replay
+
+
+def test_hex_bench_settings_match_direct_solve(cuda_device):
+    """bench.py --workload hex at a size the oracle's SuperLU path still factorises (32 x 16 x 8 cells, 15 147 dofs): the
+    reference's three fixed Newton iterations with the matrix-free fp32 V-cycle / CG recurrence, density in [1e-4, 1]
+    (stiffness contrast 1e-12) smoothed by the engine's 3-D cone filter, compliance and its adjoint total derivative."""
+    import ctypes as C
+    import torch
+    from _cases34 import HexCase, _upload
+    from femo_b200._lib import lib, check
+    nx, ny, nz = 32, 16, 8
+    c = HexCase(nx, ny, nz, seed=3, upload=False)
+    assert c.p.enable_multigrid() >= 3
+    _upload(c)
+    p = c.p
+    np.random.seed(0)
+    unf = np.clip(0.86 * np.random.random(nx * ny * nz), 1e-4, 1.0)          # run_topo_opt_cantilever_beam.py:175-180
+    d_unf, d_rho, d_den = p.to_device(unf), p.new_vector(unf.size), p.new_vector(unf.size)
+    check(lib.femo_filter_apply3(0, C.c_void_p(torch.cuda.current_stream().cuda_stream), nx, ny, nz, 2.0, 2.0, 2.0, 4.0,
+                                 C.c_void_p(d_unf.data_ptr()), C.c_void_p(d_rho.data_ptr()), C.c_void_p(d_den.data_ptr()), 0))
+    rho = d_rho.cpu().numpy()
+    assert rho.min() >= 1e-4 and rho.max() <= 1.0
+    c.d_m.copy_(d_rho)
+    c.d_u.zero_()
+    ni = p.newton_solve(kind='Newton', krylov_rtol=RTOL, precond=2, cheb_degree=2)
+    assert ni['iterations'] == 3                                             # quirk B1
+    vals, vals_bc = p.assemble_jacobian(plain=True, bc=True)
+    J, dJdu = p.assemble_output_and_grad(1)
+    grad = p.assemble_output_grad(1, 1)
+    lam, li = p.linear_solve(vals_bc, dJdu, transpose=True, rtol=RTOL, precond=2, cheb_degree=2)
+    assert li['converged']
+    p.axpy(-1.0, p.spmv(1, p.assemble_dRdm(0), lam, transpose=True), grad)
+    uo, _ = c.sp.solve_newton(np.zeros(c.F.N), [rho])
+    assert relerr(c.d_u.cpu().numpy(), uo) < 1e-7
+    (go,), lamo = c.sp.total_derivative(1, uo, [rho])
+    assert relerr(lam.cpu().numpy(), lamo) < 1e-7
+    assert relerr(grad.cpu().numpy(), go) < 1e-7
