@@ -190,7 +190,15 @@ static int halo_cells(femo_problem *p, double *v) {
 // Sum (or max) `count` device scalars starting at `slot` over all ranks, in place.
 static int allreduce_scalars(femo_problem *p, int slot, int count, bool is_max = false) {
     if (!g_comm.active || !partitioned(p)) return FEMO_OK;
-    if (g_link.active) return link_allreduce(p, p->d_scalars + slot, count, is_max);
+    if (g_link.active) {
+        // the link all-reduce carries up to kLinkArMax scalars per collective: GMRES' batched dot products (up to restart + 1)
+        // go in chunks
+        for (int o = 0; o < count; o += kLinkArMax) {
+            int rc = link_allreduce(p, p->d_scalars + slot + o, std::min(kLinkArMax, count - o), is_max);
+            if (rc) return rc;
+        }
+        return FEMO_OK;
+    }
     FEMO_NCCL(g_comm.api.AllReduce(p->d_scalars + slot, p->d_scalars + slot, (size_t)count, ncclDouble,
                                    is_max ? ncclMax : ncclSum, g_comm.comm, p->stream));
     g_comm.allreduces++;

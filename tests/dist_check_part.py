@@ -139,5 +139,89 @@ def main():
     return 1 if flag.item() else 0
 
 
+def main_motor():
+    """Config 5b on a partition: nonlinear magnetostatics on the synthetic annulus (216 tagged subdomains, Nitsche terms on
+    the two boundary circles, non-symmetric Jacobian), RCB-partitioned as a plain array mesh; SNES + GMRES with the
+    distributed AMG against the same problem on one GPU."""
+    same = os.environ.get('FEMO_DIST_SAME_DEVICE') == '1'
+    lr = 0 if same else int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(lr)
+    dist.init_process_group('gloo' if same else 'nccl', **({} if same else dict(device_id=torch.device('cuda', lr))))
+    rank, R = fd.init(lr)
+    from femo_b200.forms import motor as pde
+    from femo_b200.fea.fem import Mesh
+    nr, nth = 24, 96
+    am = E.EngineMesh.annulus(nr, nth)
+    x, cells = am.coords(), am.cells().astype(np.int64)
+    tags = pde.synthetic_motor_tags(Mesh(am, 'triangle'))
+    gmesh = E.EngineMesh.from_arrays('triangle', x, cells)
+    gfac = gmesh.exterior_facets()
+    params = pde.em_params(838.e3, 12, 36, 4e-7 * np.pi, 0.0, 282.2 / 0.00016231)
+    _, _, views = P.partition_mesh(x, cells, R)
+    v = views[rank]
+    rng = np.random.default_rng(5)
+    uh = 2e-4 * rng.standard_normal(2 * x.shape[0])                       # mesh displacement (input), 2 dofs per vertex
+
+    def build(prob, lverts):
+        prob.upload(lr)
+        prob.set_param(6, 0.2)                                             # first step of the load ramp
+        idx = (2 * lverts[:, None] + np.arange(2)[None, :]).ravel()
+        u, m = prob.new_vector(prob.N, 0.0), prob.to_device(uh[idx])
+        prob.set_coefficient(0, u); prob.set_coefficient(1, m)
+        return u, m
+
+    p = fd.PartProblem(E.FAMILY_MOTOR_EM, views, rank, params=params, cell_tags=tags, facets=gfac)
+    pg = E.EngineProblem(gmesh, E.FAMILY_MOTOR_EM, params, facets=gfac, cell_tags=tags)
+    u, m = build(p, v.verts_global)
+    gu, gm = build(pg, np.arange(x.shape[0]))
+    no = v.n_owned_verts
+    own_v = v.verts_global[:no]
+    own_d = (2 * own_v[:, None] + np.arange(2)[None, :]).ravel()
+    fails = []
+
+    def chk(name, a, b, tol):
+        e = relerr(a, b)
+        if not e < tol:
+            fails.append('%s %.3e' % (name, e))
+    chk('residual', p.assemble_residual().cpu().numpy()[:no], pg.assemble_residual().cpu().numpy()[own_v], 1e-11)
+    vals, _ = p.assemble_jacobian()
+    gvals, _ = pg.assemble_jacobian()
+    p.enable_amg(vals)
+    pg.enable_amg(gvals)
+    kw = dict(kind='SNES', krylov_rtol=1e-11, krylov_max_it=3000, method=1, precond=4, cheb_degree=2, cheb_ratio=4.0)
+    ni, nig = p.newton_solve(**kw), pg.newton_solve(**kw)
+    chk('state', u.cpu().numpy()[:no], gu.cpu().numpy()[own_v], 1e-7)
+    J, Jg = p.assemble_output(0), pg.assemble_output(0)
+    if not abs(J - Jg) <= 1e-8 * abs(Jg):
+        fails.append('functional %r vs %r' % (J, Jg))
+
+    def total(prob):
+        a, _ = prob.assemble_jacobian()
+        lam, li = prob.linear_solve(a, prob.assemble_output_grad(0, 0), transpose=True, rtol=1e-11, max_it=3000, method=1,
+                                    precond=4, cheb_degree=2, cheb_ratio=4.0)
+        g = prob.assemble_output_grad(0, 1)
+        prob.axpy(-1.0, prob.spmv(1, prob.assemble_dRdm(0), lam, transpose=True), g)
+        return g.cpu().numpy(), li
+    gl, li = total(p)
+    gg, lig = total(pg)
+    if not (li['converged'] and lig['converged']):
+        fails.append('adjoint GMRES did not converge')
+    chk('dJ/duhat', gl[:2 * no], gg[own_d], 1e-6)
+    if fd.stats()['link_error']:
+        fails.append('link transport timed out')
+    torch.cuda.synchronize()
+    flag = torch.tensor([len(fails)], device='cpu' if same else 'cuda')
+    dist.all_reduce(flag)
+    for msg in fails:
+        print('[rank %d] FAIL %s' % (rank, msg), flush=True)
+    if rank == 0:
+        print('dist_check_part motor %dx%d ranks=%d: %s (GMRES iterations %d partitioned / %d single over %d Newton steps, adjoint %d / %d)'
+              % (nr, nth, R, 'OK' if flag.item() == 0 else 'FAILED', ni['krylov_iterations'], nig['krylov_iterations'], ni['iterations'],
+                 li['iterations'], lig['iterations']), flush=True)
+    fd.finalize()
+    dist.destroy_process_group()
+    return 1 if flag.item() else 0
+
+
 if __name__ == '__main__':
-    sys.exit(main())
+    sys.exit(main_motor() if len(sys.argv) > 2 and sys.argv[2] == 'motor' else main())

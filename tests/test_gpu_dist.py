@@ -52,10 +52,11 @@ def test_femo_api_on_a_partitioned_mesh(cuda_device):
         _run('dist_check_api.py', [64], 29671 + 10 * k, mode)
 
 
-@pytest.mark.parametrize('famid', [1, 2])
+@pytest.mark.parametrize('famid', [1, 2, 'motor'])
 def test_unstructured_partition_matches_single_gpu(cuda_device, famid):
     """RCB partition of a perturbed, cell-shuffled triangle mesh (femo_b200/partition.py + femo_problem_set_partition): assembly,
     SpMV with poisoned ghosts, functional, AMG-preconditioned CG, Newton / SNES state and adjoint gradient vs the unpartitioned
-    mesh; family 1 = Poisson with Dirichlet rows, family 2 = nonlinear Poisson with Nitsche terms on the true boundary facets."""
+    mesh; family 1 = Poisson with Dirichlet rows, family 2 = nonlinear Poisson with Nitsche terms on the true boundary facets,
+    'motor' = nonlinear magnetostatics on the annulus (cell tags, boundary facets, GMRES with the distributed AMG)."""
     for k, mode in enumerate(_modes()):
-        _run('dist_check_part.py', [48, famid], 29701 + 10 * k + famid, mode)
+        _run('dist_check_part.py', [48, famid], 29701 + 10 * k + (7 if famid == 'motor' else famid), mode)
