@@ -11,8 +11,10 @@ solve), linearisation (dR/du, dR/dm), output J, dJ/du, dJ/dm, one transposed
   value  engine-level step, every input resident in HBM, CUDA events
   e2e    the same step through the reference-facing API (FEAModel + Simulator:
          numpy in, numpy out), host<->device copies inside the timed region
-  --impl reference   the oracle's direct-solve path (numpy assembly + SuperLU,
-         the reference's algorithm class) on host cores, bounded sample
+  --impl reference   oracle/cpu_path.cpp, the C++/OpenMP restatement of the same step (the reference's
+         dolfinx + MUMPS path is not installable offline) on all host cores, full workload size
+  --workload p2|hex|motor   the P2 variant, the 3-D cantilever (configs[3]) and the chained motor problem
+         (configs[4]) on one GPU (hex also on N), each verified by residual norms + a finite difference
 
 Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 4000]
 """
