@@ -742,7 +742,7 @@ def main():
                    step_info=dict(es.info, verify=check, **({'amg_pattern_phase': es.setup} if a.workload == 'motor' else {})))
         if check is not None and not check['ok']:
             out['error'] = 'verification failed: %r' % (check,)
-        if not a.no_cpu:
+        if not a.no_cpu and world == 1:          # the CPU baseline is the N=1 workload: timed at N=1 only
             out['cpu_baseline'] = cpu_baseline(a.n)
             # same workload, two independent implementations: the functional must agree
             Jc, Jg = out['cpu_baseline']['J'], es.info.get('J')
