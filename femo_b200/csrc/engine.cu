@@ -2225,11 +2225,16 @@ static int lattice_jacobian(femo_problem *p, double *d_vals, double *d_vals_bc, 
         O.np = D.np; O.o0 = p->own_off; O.o1 = p->own_off + p->own_n; O.use_bc = dia_bc ? 1 : 0;
         M.dia = D;
     }
-    k_nlpoisson_p1_node_jac<<<g, kThreads, 0, p->stream>>>(A, G, O);
-    p->launches++;
+    // interior nodes (lean instantiation) + the two outer rings with the Nitsche facet rows (lattice_asm.cuh)
+    const int gp = grid_for(lattice_band_count(A.nx, A.ny));
+    if (with_dia && (size_t)(g + gp) > p->scratch_len) return set_err(FEMO_ESTATE, "lattice_jacobian: scratch too small for the partial maxima");
+    k_nlpoisson_p1_node_jac<false><<<g, kThreads, 0, p->stream>>>(A, G, O);
+    O.gpart_off = g;
+    k_nlpoisson_p1_node_jac<true><<<gp, kThreads, 0, p->stream>>>(A, G, O);
+    p->launches += 2;
     FEMO_CHECK_LAUNCH();
     if (with_dia) {
-        k_max_finalize<<<1, kThreads, 0, p->stream>>>(p->d_scratch, g, p->d_scalars, S_TMP2);
+        k_max_finalize<<<1, kThreads, 0, p->stream>>>(p->d_scratch, g + gp, p->d_scalars, S_TMP2);
         p->launches++;
         FEMO_CHECK_LAUNCH();
         M.dia_valid = true;
@@ -2250,8 +2255,9 @@ int femo_assemble_residual(femo_problem *p, double *d_out) {
         LatJacArgs A;
         LatGeom G;
         lattice_args(p, A, G);
-        k_nlpoisson_p1_node_res<<<grid_for(p->state.ndofs), kThreads, 0, p->stream>>>(A, G, d_out);
-        p->launches++;
+        k_nlpoisson_p1_node_res<false><<<grid_for(p->state.ndofs), kThreads, 0, p->stream>>>(A, G, d_out);
+        k_nlpoisson_p1_node_res<true><<<grid_for(lattice_band_count(A.nx, A.ny)), kThreads, 0, p->stream>>>(A, G, d_out);
+        p->launches += 2;
         FEMO_CHECK_LAUNCH();
         return FEMO_OK;
     }

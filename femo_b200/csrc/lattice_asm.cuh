@@ -112,6 +112,7 @@ struct LatDiaOut {
     double *planes64 = nullptr, *dinv = nullptr, *gpart = nullptr;
     int64_t np = 0, o0 = 0, o1 = 0;
     int use_bc = 0;             // the level matrix is the BC'd copy (rows / columns of Dirichlet dofs replaced)
+    int gpart_off = 0;          // first slot of this launch's per-CTA maxima (the perimeter launch writes behind the interior's)
 };
 
 // boundary triangles (O(perimeter) of them): the Nitsche facet rows with the cell's own geometry, kept out of line so
@@ -123,32 +124,86 @@ __device__ __noinline__ void node_facet_jac(const TriArgs &A, int64_t cell, int 
     if (second) nlp_facet_jac_row(Tg, 0, A.beta, a, row);
 }
 
+// The node kernels run as two launches.  BND = false: the nodes at least two lattice rows / columns away from the boundary
+// -- all six incident triangles exist and none of them owns a boundary facet (the symmetric Nitsche terms involve the
+// normal derivative of the test function, so the vertex OPPOSITE a boundary facet, one ring inside, gets facet rows
+// too) -- so the instantiation holds no range checks, no facet code, no calls and no stack frame (round 2 ncu / ptxas:
+// the single kernel needed 80 - 88 registers and a 400-byte frame because of the out-of-line Nitsche path, 2 CTAs per
+// SM, 1.18 / 0.87 ms for 1.3 / 0.4 GB of traffic).  BND = true: the two outer rings (all nodes on lattices narrower
+// than 4 cells) with the complete general code.  Thread t of the band launch -> node (i, j):
+__host__ __device__ __forceinline__ bool lattice_small(int nx, int ny) { return nx < 4 || ny < 4; }
+__device__ __forceinline__ bool lattice_band_node(int t, int nx, int ny, int &i, int &j) {
+    const int w = nx + 1, h = ny + 1;
+    if (lattice_small(nx, ny)) {
+        if (t >= w * h) return false;
+        j = t / w;
+        i = t - j * w;
+        return true;
+    }
+    if (t < 4 * w) {                        // rows 0, 1, ny - 1, ny
+        const int k = t / w;
+        i = t - k * w;
+        j = k < 2 ? k : ny - 3 + k;
+        return true;
+    }
+    t -= 4 * w;
+    const int hh = h - 4;                   // columns 0, 1, nx - 1, nx of the rows 2 .. ny - 2
+    if (t < 4 * hh) {
+        const int k = t / hh;
+        j = 2 + (t - k * hh);
+        i = k < 2 ? k : nx - 3 + k;
+        return true;
+    }
+    return false;
+}
+static inline int lattice_band_count(int nx, int ny) {
+    return lattice_small(nx, ny) ? (nx + 1) * (ny + 1) : 4 * (nx + 1) + 4 * (ny - 3);
+}
+// node of thread (blockIdx, threadIdx) in the interior / band launch; false = idle thread
+template <bool BND>
+__device__ __forceinline__ bool lattice_node_of_thread(int nx, int ny, int &i, int &j, int &r) {
+    const int w = nx + 1, t = blockIdx.x * kThreads + threadIdx.x;
+    if (BND) {
+        if (!lattice_band_node(t, nx, ny, i, j)) return false;
+        r = j * w + i;
+        return true;
+    }
+    if (t >= w * (ny + 1) || lattice_small(nx, ny)) return false;
+    r = t;
+    j = t / w;
+    i = t - j * w;
+    return i >= 2 && j >= 2 && i <= nx - 2 && j <= ny - 2;
+}
+
 // contribution of incident triangle T (compile-time: local index and slots fold into the closed-form coefficients)
-template <int T>
+template <int T, bool BND>
 __device__ __forceinline__ void node_jac_tri(const LatJacArgs &A, const LatGeom &G, int i, int j, const double u7[7], double v[7]) {
     constexpr int up = kNodeTri[T][2], a = kNodeTri[T][3], s0 = kNodeTri[T][4], s1 = kNodeTri[T][5], s2 = kNodeTri[T][6];
     const int ci = i + kNodeTri[T][0], cj = j + kNodeTri[T][1];
-    if (ci < 0 || cj < 0 || ci >= A.nx || cj >= A.ny) return;
+    if (BND && (ci < 0 || cj < 0 || ci >= A.nx || cj >= A.ny)) return;
     const double u[3] = {u7[s0], u7[s1], u7[s2]};
     double row[3];
     nlp_cell_jac_row_const<a>(up ? G.gu : G.gl, G.a2, u, row);
-    const bool fb = !up && cj == 0 && A.ext_bottom, fr = !up && ci == A.nx - 1;
-    const bool fl = up && ci == 0, ft = up && cj == A.ny - 1 && A.ext_top;
-    if (fb || fr || fl || ft) node_facet_jac(A.T, 2 * (cj * A.nx + ci) + up, fb || fl, fr || ft, a, row);
+    if (BND) {
+        const bool fb = !up && cj == 0 && A.ext_bottom, fr = !up && ci == A.nx - 1;
+        const bool fl = up && ci == 0, ft = up && cj == A.ny - 1 && A.ext_top;
+        if (fb || fr || fl || ft) node_facet_jac(A.T, 2 * (cj * A.nx + ci) + up, fb || fl, fr || ft, a, row);
+    }
     v[s0] += row[0];
     v[s1] += row[1];
     v[s2] += row[2];
 }
 
+template <bool BND>
 __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A, LatGeom G, LatDiaOut O) {
     const int w = A.nx + 1;
-    const int r = blockIdx.x * kThreads + threadIdx.x;           // int32 dofs everywhere (FEMO_ELIMIT otherwise)
+    int i, j, r;                                                  // int32 dofs everywhere (FEMO_ELIMIT otherwise)
     __shared__ double sh_g[kThreads];
     double gersh = 0.0;
-    if (r < w * (A.ny + 1)) {
-    const int j = r / w, i = r - j * w;
+    if (lattice_node_of_thread<BND>(A.nx, A.ny, i, j, r)) {
     // stencil slots {-w-1, -w, -1, 0, 1, w, w+1} and which of them exist on the local lattice
-    const bool present[7] = {i > 0 && j > 0, j > 0, i > 0, true, i < A.nx, j < A.ny, i < A.nx && j < A.ny};
+    const bool present[7] = {!BND || (i > 0 && j > 0), !BND || j > 0, !BND || i > 0, true, !BND || i < A.nx, !BND || j < A.ny,
+                             !BND || (i < A.nx && j < A.ny)};
     const int off[7] = {-w - 1, -w, -1, 0, 1, w, w + 1};
     double u7[7], v[7];
 #pragma unroll
@@ -156,12 +211,12 @@ __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A
         u7[s] = present[s] ? __ldg(A.T.u + (r + off[s])) : 0.0;
         v[s] = 0.0;
     }
-    node_jac_tri<0>(A, G, i, j, u7, v);
-    node_jac_tri<1>(A, G, i, j, u7, v);
-    node_jac_tri<2>(A, G, i, j, u7, v);
-    node_jac_tri<3>(A, G, i, j, u7, v);
-    node_jac_tri<4>(A, G, i, j, u7, v);
-    node_jac_tri<5>(A, G, i, j, u7, v);
+    node_jac_tri<0, BND>(A, G, i, j, u7, v);
+    node_jac_tri<1, BND>(A, G, i, j, u7, v);
+    node_jac_tri<2, BND>(A, G, i, j, u7, v);
+    node_jac_tri<3, BND>(A, G, i, j, u7, v);
+    node_jac_tri<4, BND>(A, G, i, j, u7, v);
+    node_jac_tri<5, BND>(A, G, i, j, u7, v);
     // CSR positions: the row holds the present slots in ascending column order
     int32_t pos = A.rowptr[r];
     double sabs = 0.0, diag = 1.0;
@@ -200,7 +255,7 @@ __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_jac(LatJacArgs A
             if (threadIdx.x < o) sh_g[threadIdx.x] = fmax(sh_g[threadIdx.x], sh_g[threadIdx.x + o]);
             __syncthreads();
         }
-        if (threadIdx.x == 0) O.gpart[blockIdx.x] = sh_g[0];
+        if (threadIdx.x == 0) O.gpart[O.gpart_off + blockIdx.x] = sh_g[0];
     }
 }
 
@@ -262,37 +317,40 @@ __device__ __noinline__ double node_facet_res(const TriArgs &A, int64_t cell, in
     return R;
 }
 
-template <int T>
+template <int T, bool BND>
 __device__ __forceinline__ double node_res_tri(const LatJacArgs &A, const LatGeom &G, int i, int j, const double u7[7]) {
     constexpr int up = kNodeTri[T][2], a = kNodeTri[T][3];
     const int ci = i + kNodeTri[T][0], cj = j + kNodeTri[T][1];
-    if (ci < 0 || cj < 0 || ci >= A.nx || cj >= A.ny) return 0.0;
+    if (BND && (ci < 0 || cj < 0 || ci >= A.nx || cj >= A.ny)) return 0.0;
     const int c = 2 * (cj * A.nx + ci) + up;
     const double u[3] = {u7[kNodeTri[T][4]], u7[kNodeTri[T][5]], u7[kNodeTri[T][6]]};
     double R = nlp_cell_res_entry<a>(up ? G.gu : G.gl, G.a2, u, __ldg(A.T.f + c));
-    const bool fb = !up && cj == 0 && A.ext_bottom, fr = !up && ci == A.nx - 1;
-    const bool fl = up && ci == 0, ft = up && cj == A.ny - 1 && A.ext_top;
-    if (fb || fr || fl || ft) R += node_facet_res(A.T, c, fb || fl, fr || ft, u, a);
+    if (BND) {
+        const bool fb = !up && cj == 0 && A.ext_bottom, fr = !up && ci == A.nx - 1;
+        const bool fl = up && ci == 0, ft = up && cj == A.ny - 1 && A.ext_top;
+        if (fb || fr || fl || ft) R += node_facet_res(A.T, c, fb || fl, fr || ft, u, a);
+    }
     return R;
 }
 
+template <bool BND>
 __global__ void __launch_bounds__(kThreads) k_nlpoisson_p1_node_res(LatJacArgs A, LatGeom G, double *__restrict__ out) {
     const int w = A.nx + 1;
-    const int r = blockIdx.x * kThreads + threadIdx.x;
-    if (r >= w * (A.ny + 1)) return;
-    const int j = r / w, i = r - j * w;
-    const bool present[7] = {i > 0 && j > 0, j > 0, i > 0, true, i < A.nx, j < A.ny, i < A.nx && j < A.ny};
+    int i, j, r;
+    if (!lattice_node_of_thread<BND>(A.nx, A.ny, i, j, r)) return;
+    const bool present[7] = {!BND || (i > 0 && j > 0), !BND || j > 0, !BND || i > 0, true, !BND || i < A.nx, !BND || j < A.ny,
+                             !BND || (i < A.nx && j < A.ny)};
     const int off[7] = {-w - 1, -w, -1, 0, 1, w, w + 1};
     double u7[7];
 #pragma unroll
     for (int s = 0; s < 7; ++s) u7[s] = present[s] ? __ldg(A.T.u + (r + off[s])) : 0.0;
     double R = 0.0;
-    R += node_res_tri<0>(A, G, i, j, u7);
-    R += node_res_tri<1>(A, G, i, j, u7);
-    R += node_res_tri<2>(A, G, i, j, u7);
-    R += node_res_tri<3>(A, G, i, j, u7);
-    R += node_res_tri<4>(A, G, i, j, u7);
-    R += node_res_tri<5>(A, G, i, j, u7);
+    R += node_res_tri<0, BND>(A, G, i, j, u7);
+    R += node_res_tri<1, BND>(A, G, i, j, u7);
+    R += node_res_tri<2, BND>(A, G, i, j, u7);
+    R += node_res_tri<3, BND>(A, G, i, j, u7);
+    R += node_res_tri<4, BND>(A, G, i, j, u7);
+    R += node_res_tri<5, BND>(A, G, i, j, u7);
     out[r] = R;
 }
 
