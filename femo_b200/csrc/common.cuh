@@ -29,6 +29,8 @@ int set_err(int code, const std::string &msg);
 struct EnvFlags {
     bool no_bsr = false, no_dia = false, no_overlap = false, no_mgfused = false, no_lattice_asm = false, no_graph = false, force_graph = false;
     long long overlap_min_rows = 1 << 20, mgfused_max_rows = 20000, graph_max_rows = 1 << 20;
+    long long mgfused_small_rows = 0;        // fused V-cycle ops up to this many rows run on ONE CTA (FEMO_MGFUSED_SMALL_ROWS); off:
+                                             // measured slower (4096: 50.5 ms against 46.9 ms per step, profiles/r02_summary.md)
     long long mgfused_ctas = 0;              // CTAs of the cooperative coarse V-cycle (0: rows of its largest level / 512, FEMO_MGFUSED_CTAS)
 };
 extern EnvFlags g_env;

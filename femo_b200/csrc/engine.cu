@@ -35,6 +35,7 @@ void refresh_env() {
     g_env.overlap_min_rows = num("FEMO_OVERLAP_MIN_ROWS", 1 << 20);
     g_env.mgfused_max_rows = num("FEMO_MGFUSED_MAX_ROWS", 20000);
     g_env.mgfused_ctas = num("FEMO_MGFUSED_CTAS", 0);
+    g_env.mgfused_small_rows = num("FEMO_MGFUSED_SMALL_ROWS", 0);
     g_env.graph_max_rows = num("FEMO_GRAPH_MAX_ROWS", 1 << 20);
 }
 int set_err(int code, const std::string &msg) {

@@ -125,8 +125,24 @@ __device__ void mg_run_op(const MgOp &o, int64_t tid, int64_t nth) {
 
 // b0 / x0: right-hand side and solution of the first level of the program (they change from call to call);
 // ops that refer to them carry the sentinel pointers (1 = b0, 2 = x0)
+// work items of an op (rows it writes)
+__device__ __forceinline__ int64_t mg_op_work(const MgOp &o) {
+    switch (o.type) {
+        case MGO_RESTRICT: return (int64_t)(o.cnx + 1) * (o.cny + 1);
+        case MGO_PROLONG: return (int64_t)(o.fnx + 1) * (o.fny + 1);
+        case MGO_DENSE: return o.n;
+        default: return o.A.n;
+    }
+}
+
+// Ops that write at most `small_rows` rows (the bottom of the hierarchy: a few thousand rows and the dense coarsest solve)
+// are executed by CTA 0 alone, ordered by __syncthreads(); the other CTAs skip them and wait at the next grid-wide
+// barrier.  A run of small ops therefore costs two grid barriers (entering and leaving it) instead of one per op.
+// Measured on the B200 with small_rows = 4096 (levels of 3969 and 1024 rows + the dense solve on one CTA): 50.5 ms per
+// step against 46.9 ms with every op grid-wide -- one SM's L2 latency chain is slower than 13 grid barriers -- so the
+// default is 0 (off); FEMO_MGFUSED_SMALL_ROWS enables it.
 __global__ void __launch_bounds__(kMgFusedThreads)
-    k_mg_fused(const MgOp *__restrict__ ops, int nops, const double *b0, double *x0) {
+    k_mg_fused(const MgOp *__restrict__ ops, int nops, const double *b0, double *x0, int small_rows) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
@@ -136,8 +152,16 @@ __global__ void __launch_bounds__(kMgFusedThreads)
         if (op.x == (const double *)2) op.x = x0;
         if (op.y == (double *)2) op.y = x0;
         if (op.dst == (double *)2) op.dst = x0;
-        mg_run_op(op, tid, nth);
-        if (k + 1 < nops) grid.sync();
+        const bool small = mg_op_work(op) <= small_rows;
+        if (!small) mg_run_op(op, tid, nth);
+        else if (blockIdx.x == 0) mg_run_op(op, threadIdx.x, blockDim.x);
+        if (k + 1 < nops) {
+            if (small && mg_op_work(ops[k + 1]) <= small_rows) {
+                if (blockIdx.x == 0) __syncthreads();       // CTA 0 continues alone (block-uniform branch)
+            } else {
+                grid.sync();
+            }
+        }
     }
 }
 
@@ -250,7 +274,8 @@ static int mgfused_vcycle(femo_problem *root, int lv, const double *b, double *x
     double *x0 = x;
     if (lv > P.k0 && (b != L->mgl.b || x != L->mgl.x)) return FEMO_OK;
     const MgOp *ops = root->d_mgops + first;
-    void *args[] = {(void *)&ops, (void *)&count, (void *)&b0, (void *)&x0};
+    int small_rows = (int)g_env.mgfused_small_rows;
+    void *args[] = {(void *)&ops, (void *)&count, (void *)&b0, (void *)&x0, (void *)&small_rows};
     // grid: one thread per row of the largest fused level is enough (a grid-wide barrier costs more the more CTAs arrive);
     // never more than one CTA per SM (co-residency of the cooperative launch)
     int64_t ctas = g_env.mgfused_ctas > 0 ? g_env.mgfused_ctas : (mg_level(root, P.k0)->state.ndofs + kMgFusedThreads - 1) / kMgFusedThreads;
