@@ -430,8 +430,18 @@ __global__ void __launch_bounds__(kThreads)
 
 __global__ void __launch_bounds__(kThreads) k_max_finalize(const double *__restrict__ partials, int np, double *scalars, int slot) {
     __shared__ double sh[kThreads];
-    double mx = 0.0;
-    for (int i = threadIdx.x; i < np; i += blockDim.x) mx = fmax(mx, partials[i]);
+    // four independent loads in flight per thread: the node-centric Jacobian hands over one partial per CTA (62 k of them
+    // at n=4000) and a single dependent chain of L2 loads took 114 us (ncu launch list r3n); max is order-independent
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+    const int bd = blockDim.x;
+    for (int i = threadIdx.x; i < np; i += 4 * bd) {
+        const double a = partials[i];
+        const double b = i + bd < np ? partials[i + bd] : 0.0;
+        const double c = i + 2 * bd < np ? partials[i + 2 * bd] : 0.0;
+        const double d = i + 3 * bd < np ? partials[i + 3 * bd] : 0.0;
+        m0 = fmax(m0, a); m1 = fmax(m1, b); m2 = fmax(m2, c); m3 = fmax(m3, d);
+    }
+    const double mx = fmax(fmax(m0, m1), fmax(m2, m3));
     sh[threadIdx.x] = mx;
     __syncthreads();
     for (int o = kThreads / 2; o > 0; o >>= 1) {
