@@ -14,6 +14,7 @@ conventions of oracle/families.py all have to be right for that.
 The non-polynomial data of config 2 (u_ex = sin 2 pi x sin pi y) is swapped for a cubic polynomial in the exact tests; a
 separate test keeps the true u_ex and integrates it with mpmath to show the size of the quadrature error the documented
 rules leave on a coarse mesh ('non-polynomial integrands')."""
+import os
 from fractions import Fraction
 
 import numpy as np
@@ -75,6 +76,12 @@ def _dyadic(rng, n, scale=8):
     return rng.integers(-2 * scale, 2 * scale + 1, size=n) / float(scale)
 
 
+def _dyadic_small(rng, n, bound):
+    """Dyadic values in [-bound, bound] on a 1/1024 grid (mesh displacements that keep det F well inside (0, 2))."""
+    k = int(round(bound * 1024))
+    return rng.integers(-k, k + 1, size=n) / 1024.0
+
+
 class _SymTri:
     """P1 / P2 triangle mesh in sympy: per cell the affine map, physical gradients and |det J|; exterior facets from
     edge counts; everything rational."""
@@ -126,6 +133,7 @@ def _close(got, exact, tol=1e-13):
     ex = np.array(sp.Matrix(exact).evalf(30), dtype=np.float64).reshape(got.shape)
     scale = max(np.abs(ex).max(), 1e-300)
     assert np.abs(got - ex).max() <= tol * scale, (np.abs(got - ex).max() / scale)
+    return ex
 
 
 def _jac_at(exprs, syms, table):
@@ -154,6 +162,58 @@ def _subs_all(exprs, table):
     return [sp.sympify(e).xreplace(table) for e in exprs]
 
 
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'symbolic')
+
+
+def _record(name, mesh, state, inputs, exact, meta):
+    """The exact values are also the committed fixtures tests/golden/symbolic/<name>.npz (consumed by the GPU parity test
+    tests/test_gpu_exact.py, which cannot run sympy-sized jobs per launch and must not need /root/reference):
+    FEMO_SYMBOLIC_DUMP=1 rewrites them (scripts/make_symbolic_golden.py); otherwise the values computed now must
+    reproduce the committed file, so a fixture can never drift from the derivation in this module."""
+    rec = dict(kind=np.array(mesh.kind), coords=mesh.coords, cells=mesh.cells, state=np.asarray(state, dtype=np.float64))
+    for k, a in enumerate(inputs):
+        rec['input%d' % k] = np.asarray(a, dtype=np.float64)
+    for k, v in (meta or {}).items():
+        rec['meta_' + k] = np.asarray(v)
+    rec.update(exact)
+    path = os.path.join(GOLD, name + '.npz')
+    if os.environ.get('FEMO_SYMBOLIC_DUMP'):
+        os.makedirs(GOLD, exist_ok=True)
+        np.savez_compressed(path, **rec)
+        return
+    assert os.path.exists(path), 'missing fixture %s: run scripts/make_symbolic_golden.py' % path
+    with np.load(path) as z:
+        assert sorted(z.files) == sorted(rec)
+        for k in rec:
+            a, b = np.asarray(rec[k]), z[k]
+            if a.dtype.kind == 'f':
+                assert a.shape == b.shape and np.abs(a - b).max(initial=0.0) <= 1e-14 * max(np.abs(b).max(initial=0.0), 1e-300), k
+            else:
+                assert np.array_equal(a, b), k
+
+
+def _check(name, mesh, F, state, inputs, R, Js, Usym, Msyms, tab, tol=1e-13, numeric_jac=False, meta=None):
+    """Oracle family F at (state, inputs) against the exact residual expressions R (one per dof), functionals Js and their
+    derivatives with respect to the state symbols Usym and the input symbols Msyms[slot]; records the exact values."""
+    if numeric_jac:
+        jac = lambda ex, sy: _jac_at(ex, sy, tab)                                     # noqa: E731
+    else:
+        jac = lambda ex, sy: sp.Matrix([sp.sympify(e) for e in ex]).jacobian(list(sy)).xreplace(tab)   # noqa: E731
+    N = F.N
+    ex = {}
+    ex['R'] = _close(asm.assemble_vector(F.residual(state, *inputs), N), _subs_all(R, tab), tol)
+    ex['A'] = _close(asm.assemble_matrix(F.jacobian(state, *inputs), (N, N)).toarray(), jac(R, Usym), tol)
+    for s_, Ms in enumerate(Msyms):
+        ex['D%d' % s_] = _close(asm.assemble_matrix(F.dRdm(s_, state, *inputs), (N, len(Ms))).toarray(), jac(R, Ms), tol)
+    for k, Jf in enumerate(Js):
+        ex['J%d' % k] = _close([asm.assemble_scalar(F.output(k, state, *inputs))], [sp.sympify(Jf).xreplace(tab)], tol)
+        ex['Ju%d' % k] = _close(asm.assemble_vector(F.output_du(k, state, *inputs), N), list(jac([Jf], Usym)), tol)
+        for s_, Ms in enumerate(Msyms):
+            ex['Jm%d_%d' % (k, s_)] = _close(asm.assemble_vector(F.output_dm(k, s_, state, *inputs), len(Ms)),
+                                             list(jac([Jf], Ms)), tol)
+    _record(name, mesh, state, inputs, ex, meta)
+
+
 # ------------------------------------------------------------------ config 1
 def test_poisson_p1_against_exact_integrals():
     """examples/poisson_opt/run_poisson_opt.py:32-38 (R = inner(grad u, grad v) dx - f v dx) and :74-76
@@ -179,13 +239,7 @@ def test_poisson_p1_against_exact_integrals():
         Jf += _tri_int((sp.Rational(1, 2) * (uh - ue) ** 2 + alpha / 2 * Fm[c] ** 2) * adet)
     tab = {U[i]: _rat(u[i]) for i in range(F.N)}
     tab.update({Fm[i]: _rat(f[i]) for i in range(F.M)})
-    _close(asm.assemble_vector(F.residual(u, f), F.N), _subs_all(R, tab))
-    _close(asm.assemble_matrix(F.jacobian(u, f), (F.N, F.N)).toarray(),
-           sp.Matrix(R).jacobian(U).xreplace(tab))
-    _close(asm.assemble_matrix(F.dRdm(0, u, f), (F.N, F.M)).toarray(), sp.Matrix(R).jacobian(Fm).xreplace(tab))
-    _close([asm.assemble_scalar(F.output(0, u, f))], [Jf.xreplace(tab)])
-    _close(asm.assemble_vector(F.output_du(0, u, f), F.N), [sp.diff(Jf, s).xreplace(tab) for s in U])
-    _close(asm.assemble_vector(F.output_dm(0, 0, u, f), F.M), [sp.diff(Jf, s).xreplace(tab) for s in Fm])
+    _check('poisson_p1', m, F, u, [f], R, [Jf], U, [Fm], tab, meta=dict(u_ex=uex, alpha=1e-6))
 
 
 # ------------------------------------------------------------------ config 2
@@ -237,15 +291,11 @@ def _p1_basis(T):
     return lambda c, lam: (T.cells[c], lam)
 
 
-def _compare_family(F, R, Jf, U, Fm, u, f, tol=1e-13):
+def _compare_family(name, m, F, R, Jf, U, Fm, u, f, tol=1e-13):
     tab = {U[i]: _rat(u[i]) for i in range(F.N)}
     tab.update({Fm[i]: _rat(f[i]) for i in range(F.M)})
-    _close(asm.assemble_vector(F.residual(u, f), F.N), _subs_all(R, tab), tol)
-    _close(asm.assemble_matrix(F.jacobian(u, f), (F.N, F.N)).toarray(), sp.Matrix(R).jacobian(U).xreplace(tab), tol)
-    _close(asm.assemble_matrix(F.dRdm(0, u, f), (F.N, F.M)).toarray(), sp.Matrix(R).jacobian(Fm).xreplace(tab), tol)
-    _close([asm.assemble_scalar(F.output(0, u, f))], [Jf.xreplace(tab)], tol)
-    _close(asm.assemble_vector(F.output_du(0, u, f), F.N), [sp.diff(Jf, s).xreplace(tab) for s in U], tol)
-    _close(asm.assemble_vector(F.output_dm(0, 0, u, f), F.M), [sp.diff(Jf, s).xreplace(tab) for s in Fm], tol)
+    # the Jacobian and dR/df do not involve u_ex, so the recorded A and D0 are exact for the TRUE family as well
+    _check(name, m, F, u, [f], R, [Jf], U, [Fm], tab, tol, meta=dict(u_ex=np.array('x^2 y - 3 x y + y^3 / 4 + 1 / 2')))
 
 
 def test_nonlinear_poisson_p1_against_exact_integrals(monkeypatch):
@@ -259,7 +309,7 @@ def test_nonlinear_poisson_p1_against_exact_integrals(monkeypatch):
     U = sp.symbols('U0:%d' % F.N)
     Fm = sp.symbols('F0:%d' % F.M)
     R, Jf = _nlp_symbolic(T, U, Fm, _p1_basis(T), _uex_poly, 10, sp.Rational(6, 10 ** 7))
-    _compare_family(F, R, Jf, U, Fm, u, f)
+    _compare_family('nlpoisson_p1', m, F, R, Jf, U, Fm, u, f)
 
 
 def test_nonlinear_poisson_p2_against_exact_integrals(monkeypatch):
@@ -284,7 +334,7 @@ def test_nonlinear_poisson_p2_against_exact_integrals(monkeypatch):
     U = sp.symbols('U0:%d' % F.N)
     Fm = sp.symbols('F0:%d' % F.M)
     R, Jf = _nlp_symbolic(T, U, Fm, basis, _uex_poly, 10, sp.Rational(6, 10 ** 7))
-    _compare_family(F, R, Jf, U, Fm, u, f, tol=2e-13)
+    _compare_family('nlpoisson_p2', m, F, R, Jf, U, Fm, u, f, tol=2e-13)
 
 
 def test_nonlinear_poisson_true_u_ex_within_quadrature_error():
@@ -382,13 +432,7 @@ def test_hermite_beam_against_exact_integrals():
     vol = sum(Tm[c] * _rat(width) * _rat(L) * _rat(xs[c + 1] - xs[c]) for c in range(5))
     tab = {U[i]: _rat(u[i]) for i in range(F.N)}
     tab.update({Tm[i]: _rat(t[i]) for i in range(F.M)})
-    _close(asm.assemble_vector(F.residual(u, t), F.N), _subs_all(R, tab))
-    _close(asm.assemble_matrix(F.jacobian(u, t), (F.N, F.N)).toarray(), sp.Matrix(R).jacobian(U).xreplace(tab))
-    _close(asm.assemble_matrix(F.dRdm(0, u, t), (F.N, F.M)).toarray(), sp.Matrix(R).jacobian(Tm).xreplace(tab))
-    for k, Jf in enumerate((comp, vol)):
-        _close([asm.assemble_scalar(F.output(k, u, t))], [sp.sympify(Jf).xreplace(tab)])
-        _close(asm.assemble_vector(F.output_du(k, u, t), F.N), [sp.diff(Jf, s).xreplace(tab) for s in U])
-        _close(asm.assemble_vector(F.output_dm(k, 0, u, t), F.M), [sp.diff(Jf, s).xreplace(tab) for s in Tm])
+    _check('eb_beam', m, F, u, [t], R, [comp, vol], U, [Tm], tab, meta=dict(params=[E, width, L, fload], tagged=tip))
 
 
 # ------------------------------------------------------------------ config 4 (2-D reference size family and 3-D extension)
@@ -473,14 +517,8 @@ def test_simp_elasticity_against_exact_integrals(d):
     R, avg, comp = _simp_symbolic(m, d, U, Rho, [_rat(v) for v in fvec], {int(c) for c in fc[on_right]})
     tab = {U[i]: _rat(u[i]) for i in range(F.N)}
     tab.update({Rho[i]: _rat(rho[i]) for i in range(F.M)})
-    tol = 2e-13
-    _close(asm.assemble_vector(F.residual(u, rho), F.N), _subs_all(R, tab), tol)
-    _close(asm.assemble_matrix(F.jacobian(u, rho), (F.N, F.N)).toarray(), sp.Matrix(R).jacobian(U).xreplace(tab), tol)
-    _close(asm.assemble_matrix(F.dRdm(0, u, rho), (F.N, F.M)).toarray(), sp.Matrix(R).jacobian(Rho).xreplace(tab), tol)
-    for k, Jf in enumerate((avg, comp)):
-        _close([asm.assemble_scalar(F.output(k, u, rho))], [sp.sympify(Jf).xreplace(tab)], tol)
-        _close(asm.assemble_vector(F.output_du(k, u, rho), F.N), [sp.diff(Jf, s).xreplace(tab) for s in U], tol)
-        _close(asm.assemble_vector(F.output_dm(k, 0, u, rho), F.M), [sp.diff(Jf, s).xreplace(tab) for s in Rho], tol)
+    _check('simp_q1' if d == 2 else 'simp_hex8', m, F, u, [rho], R, [avg, comp], U, [Rho], tab, 2e-13,
+           meta=dict(params=[0.3] + list(fvec) + [3.0], tagged=on_right))
 
 
 # ------------------------------------------------------------------ config 5a
@@ -505,7 +543,7 @@ def test_mesh_motion_against_exact_integrals():
     tags = np.array([15, 1])
     F = MotorMM(m, (fc, fl), tags)
     rng = np.random.default_rng(10)
-    uh, g = _dyadic(rng, F.N, 64), _dyadic(rng, F.N, 64)
+    uh, g = _dyadic_small(rng, F.N, 1 / 16), _dyadic_small(rng, F.N, 1 / 16)
     U = sp.symbols('U0:%d' % F.N)
     Gs = sp.symbols('G0:%d' % F.N)
     eps = sp.Symbol('eps')
@@ -568,13 +606,9 @@ def test_mesh_motion_against_exact_integrals():
                     R[2 * v[a] + k] += simpson * length
     tab = {U[i]: _rat(uh[i]) for i in range(F.N)}
     tab.update({Gs[i]: _rat(g[i]) for i in range(F.N)})
-    tol = 1e-12                     # beta = 5e3: the penalty rows dominate the scale; cancellation in the others
-    _close(asm.assemble_vector(F.residual(uh, g), F.N), _subs_all(R, tab), tol)
-    _close(asm.assemble_matrix(F.jacobian(uh, g), (F.N, F.N)).toarray(), _jac_at(R, U, tab), tol)
-    _close(asm.assemble_matrix(F.dRdm(0, uh, g), (F.N, F.N)).toarray(), _jac_at(R, Gs, tab), tol)
-    for k in range(3):
-        _close([asm.assemble_scalar(F.output(k, uh, g))], [sp.sympify(areas[k]).xreplace(tab)], tol)
-        _close(asm.assemble_vector(F.output_du(k, uh, g), F.N), list(_jac_at([areas[k]], U, tab)), tol)
+    # beta = 5e3: the penalty rows dominate the scale (tolerance 1e-12)
+    _check('motor_mm', m, F, uh, [g], R, areas, U, [Gs], tab, 1e-12, numeric_jac=True,
+           meta=dict(params=[5e3], facet_cells=fc, facet_locals=fl, cell_tags=tags))
 
 
 # ------------------------------------------------------------------ config 5b
@@ -597,8 +631,8 @@ def test_magnetostatics_against_exact_integrals():
     tags = np.array([1, 2, 3, 4, 15, 16, 20, 53])
     p_, s_n, Hc, angle, iq, beta = 12, 36, 838e3, 0.3, 282.2 / 0.00016231, 1e4
     Fo = MotorEM(m, tags, Hc=Hc, p=p_, s=s_n, angle=angle, iq=iq, beta=beta)
-    rng = np.random.default_rng(12)
-    u, uh = _dyadic(rng, Fo.N, 8), _dyadic(rng, Fo.M, 64)
+    rng = np.random.default_rng(16)                      # |B| per cell 0.5 ... 2.4: all three pieces of the curve
+    u, uh = _dyadic(rng, Fo.N, 8) / 4, _dyadic_small(rng, Fo.M, 1 / 32)
     U = sp.symbols('U0:%d' % Fo.N)
     W = sp.symbols('W0:%d' % Fo.M)
     tab = {U[i]: _rat(u[i]) for i in range(Fo.N)}
@@ -682,15 +716,9 @@ def test_magnetostatics_against_exact_integrals():
                         return coeff * (-gu.dot(nN) * vv - gvn * uu) + sp.Integer(10) ** 4 / h * coeff * nrm * vv * uu
 
                     R[v[a]] += (integrand(0) + 4 * integrand(sp.Rational(1, 2)) + integrand(1)) / 6 * length
-    assert len(branches) >= 2, branches                       # more than one piece of the B-H curve is exercised
-    tol = 1e-11
-    _close(asm.assemble_vector(Fo.residual(u, uh), Fo.N), _subs_all(R, tab), tol)
-    _close(asm.assemble_matrix(Fo.jacobian(u, uh), (Fo.N, Fo.N)).toarray(), _jac_at(R, U, tab), tol)
-    _close(asm.assemble_matrix(Fo.dRdm(0, u, uh), (Fo.N, Fo.M)).toarray(), _jac_at(R, W, tab), tol)
-    for k in range(2):
-        _close([asm.assemble_scalar(Fo.output(k, u, uh))], [sp.sympify(outs[k]).xreplace(tab)], tol)
-        _close(asm.assemble_vector(Fo.output_du(k, u, uh), Fo.N), list(_jac_at([outs[k]], U, tab)), tol)
-        _close(asm.assemble_vector(Fo.output_dm(k, 0, u, uh), Fo.M), list(_jac_at([outs[k]], W, tab)), tol)
+    assert branches == {'linear', 'cubic', 'exp'}, branches   # every piece of the B-H curve is exercised
+    _check('motor_em', m, Fo, u, [uh], R, outs, U, [W], tab, 1e-11, numeric_jac=True,
+           meta=dict(cell_tags=tags, Hc=Hc, p=p_, s=s_n, angle=angle, iq=iq, beta=beta))
 
 
 # ------------------------------------------------------------------ Reissner-Mindlin plate
@@ -751,12 +779,6 @@ def test_reissner_mindlin_plate_against_the_energy_functional():
     tab = {U[i]: _rat(u[i]) for i in range(F.N)}
     tab.update({Ts[i]: _rat(t[i]) for i in range(F.M)})
     tab.update({Fs[i]: _rat(f[i]) for i in range(F.M)})
-    tol = 1e-12                    # the 1e6 penalty rows set the scale of the matrix
-    _close(asm.assemble_vector(F.residual(u, t, f), F.N), _subs_all(R, tab), tol)
-    _close(asm.assemble_matrix(F.jacobian(u, t, f), (F.N, F.N)).toarray(), sp.Matrix(R).jacobian(U).xreplace(tab), tol)
-    _close(asm.assemble_matrix(F.dRdm(0, u, t, f), (F.N, F.M)).toarray(), sp.Matrix(R).jacobian(Ts).xreplace(tab), tol)
-    _close(asm.assemble_matrix(F.dRdm(1, u, t, f), (F.N, F.M)).toarray(), sp.Matrix(R).jacobian(Fs).xreplace(tab), tol)
-    for k, Jf in enumerate((comp, mass, energy)):
-        _close([asm.assemble_scalar(F.output(k, u, t, f))], [sp.sympify(Jf).xreplace(tab)], tol)
-        _close(asm.assemble_vector(F.output_du(k, u, t, f), F.N), [sp.diff(Jf, s).xreplace(tab) for s in U], tol)
-        _close(asm.assemble_vector(F.output_dm(k, 0, u, t, f), F.M), [sp.diff(Jf, s).xreplace(tab) for s in Ts], tol)
+    # the 1e6 penalty rows set the scale of the matrix (tolerance 1e-12)
+    _check('rm_plate', m, F, u, [t, f], R, [comp, mass, energy], U, [Ts, Fs], tab, 1e-12,
+           meta=dict(params=[E_, nu_, pen_, rho_]))
