@@ -2,8 +2,8 @@
 
 The reference imports meshes converted by msh2xdmf (`import_mesh`, femo/fea/utils_dolfinx.py:69-123: an XDMF
 pair `<prefix>_domain.xdmf` / `<prefix>_boundaries.xdmf` plus `<prefix>_association_table.ini`).  `read_xdmf` reads that
-pair when its data items are inline XML or raw binary files (meshio's data_format "XML" / "Binary"); heavy data in HDF5
-(meshio's default) needs h5py, which is absent offline -- `import_mesh` then goes back to the Gmsh file the pair was made
+pair with inline XML, raw binary or HDF5 data items (meshio's data_format "XML" / "Binary" / "HDF"; HDF5 through the
+pure-Python reader hdf5_lite.py, no h5py needed); if the pair cannot be read `import_mesh` goes back to the Gmsh file the pair was made
 from (`<prefix>.msh`, ASCII format 2.2 or 4.1 [upstream layouts, from memory]).  Either way it returns the reference's tuple.  Gmsh's vertex order is converted to the
 tensor-product order basix uses for quadrilaterals and hexahedra.
 """
@@ -125,9 +125,12 @@ def _xdmf_item(item, directory):
         a = np.array(text.split(), dtype=np.float64 if kind == 'Float' else np.int64)
     elif fmt == 'BINARY':
         a = np.fromfile(os.path.join(directory, text), dtype=dt)
+    elif fmt in ('HDF', 'H5'):                      # "file.h5:/path/to/dataset" (meshio: /data0 ...; dolfinx: /Mesh/<name>/geometry ...)
+        fname, _, dset = text.partition(':')
+        from . import hdf5_lite
+        a = hdf5_lite.read_dataset(os.path.join(directory, fname.strip()), dset.strip())
     else:
-        raise NotImplementedError('XDMF data item in %s format (%s): HDF5 heavy data cannot be read without h5py; convert with '
-                                  'meshio data_format="XML" or keep the .msh next to the XDMF pair' % (fmt, text))
+        raise NotImplementedError('XDMF data item format %r (%s)' % (fmt, text))
     return a.reshape(dims)
 
 
@@ -202,7 +205,7 @@ def import_mesh(prefix="mesh", subdomains=False, dim=2, directory="."):
             _, (fk, fconn), ftags = read_xdmf(bnd)
             cells = {kind: (conn, np.zeros(conn.shape[0], dtype=np.int32) if ctags is None else ctags.astype(np.int32)),
                      fk: (fconn, np.zeros(fconn.shape[0], dtype=np.int32) if ftags is None else ftags.astype(np.int32))}
-        except NotImplementedError:
+        except (NotImplementedError, ValueError, KeyError, OSError):        # e.g. git-LFS pointers instead of the HDF5 files
             if not os.path.exists(os.path.join(directory, prefix + '.msh')):
                 raise
     if cells is None:

@@ -171,10 +171,18 @@ def test_gmsh_vertex_order_is_converted_to_tensor_order(tmp_path):
     assert em.nbfacets == 6
 
 
-def _write_xdmf(path, pts, topo, conn, attr_name, values, binary_dir=None):
-    """The XDMF 3 layout meshio / msh2xdmf write (one uniform Grid, Geometry XY, one cell attribute), inline XML or raw binary."""
+def _write_xdmf(path, pts, topo, conn, attr_name, values, binary_dir=None, hdf=None):
+    """The XDMF 3 layout meshio / msh2xdmf write (one uniform Grid, Geometry XY, one cell attribute): inline XML, raw binary,
+    or -- meshio's default -- HDF5 heavy data `<file>.h5:/data<k>` (hdf = keyword arguments of tests/_hdf5_writer.write)."""
+    h5 = {}
+
     def item(a, kind, prec, name):
         dims = ' '.join(str(d) for d in a.shape)
+        if hdf is not None:
+            key = 'data%d' % len(h5)
+            h5[key] = np.asarray(a, dtype='<f8' if kind == 'Float' else '<i8')
+            return '<DataItem DataType="%s" Dimensions="%s" Format="HDF" Precision="%d">%s:/%s</DataItem>' % (
+                kind, dims, prec, path.with_suffix('.h5').name, key)
         if binary_dir is None:
             body = '\n'.join(' '.join(repr(float(v)) if kind == 'Float' else str(int(v)) for v in row) for row in np.atleast_2d(a))
             return '<DataItem DataType="%s" Dimensions="%s" Format="XML" Precision="%d">\n%s\n</DataItem>' % (kind, dims, prec, body)
@@ -188,12 +196,16 @@ def _write_xdmf(path, pts, topo, conn, attr_name, values, binary_dir=None):
                     '</Grid></Domain></Xdmf>'
                     % (item(pts[:, :2], 'Float', 8, 'geo'), topo, conn.shape[0], conn.shape[1], item(conn, 'Int', 8, 'topo'),
                        attr_name, item(np.asarray(values).reshape(-1, 1), 'Int', 8, 'attr')))
+    if hdf is not None:
+        from _hdf5_writer import write
+        write(str(path.with_suffix('.h5')), h5, **hdf)
 
 
-@pytest.mark.parametrize('binary', [False, True])
-def test_import_mesh_from_the_xdmf_pair(tmp_path, binary):
+@pytest.mark.parametrize('fmt', ['xml', 'binary', 'hdf', 'hdf-gzip'])
+def test_import_mesh_from_the_xdmf_pair(tmp_path, fmt):
     """The reference's own inputs (utils_dolfinx.py:92-107: <prefix>_domain.xdmf with the cell tags, <prefix>_boundaries.xdmf
-    with the tagged lines) when their data items are inline XML or raw binary; HDF5 items fall back to the .msh or raise."""
+    with the tagged lines) with inline XML, raw binary or HDF5 heavy data (contiguous, and chunked + shuffled + gzip-compressed
+    as meshio writes it), read without h5py; unreadable heavy data falls back to the .msh or raises."""
     from femo_b200.fea.utils_b200 import import_mesh
     from femo_b200.fea.fem import Measure
     m = om.unit_square_tri(4, 4)
@@ -202,9 +214,11 @@ def test_import_mesh_from_the_xdmf_pair(tmp_path, binary):
     col = np.nonzero(np.isclose(m.coords[:, 0], 0.5))[0]
     col = col[np.argsort(m.coords[col, 1])]
     lines = np.array([(int(a), int(b)) for a, b in zip(col[:-1], col[1:])])
-    bd = tmp_path if binary else None
-    _write_xdmf(tmp_path / 'motor_domain.xdmf', m.coords, 'Triangle', m.cells, 'name_to_read', tri_tags, bd)
-    _write_xdmf(tmp_path / 'motor_boundaries.xdmf', m.coords, 'Polyline', lines, 'name_to_read', [1000] * len(lines), bd)
+    bd = tmp_path if fmt == 'binary' else None
+    hdf = None if not fmt.startswith('hdf') else (dict() if fmt == 'hdf' else
+                                                  dict(chunks=lambda a: (min(7, a.shape[0]), a.shape[1]), gzip=4, shuffle=True))
+    _write_xdmf(tmp_path / 'motor_domain.xdmf', m.coords, 'Triangle', m.cells, 'name_to_read', tri_tags, bd, hdf)
+    _write_xdmf(tmp_path / 'motor_boundaries.xdmf', m.coords, 'Polyline', lines, 'name_to_read', [1000] * len(lines), bd, hdf)
     (tmp_path / 'motor_association_table.ini').write_text('[ASSOCIATION TABLE]\ninterface = 1000\nsteel = 1\nmagnet = 3\n')
     mesh, boundaries_mf, subdomains_mf, table = import_mesh(prefix='motor', subdomains=True, dim=2, directory=str(tmp_path))
     assert table == dict(interface=1000, steel=1, magnet=3)
@@ -212,9 +226,10 @@ def test_import_mesh_from_the_xdmf_pair(tmp_path, binary):
     assert np.array_equal(subdomains_mf.values, tri_tags)
     fc, fl = Measure('dS', domain=mesh, subdomain_data=boundaries_mf)(1000).sides
     assert len(fc) == 2 * len(lines)
-    # HDF5 heavy data: a clear error when there is no .msh to fall back to
-    (tmp_path / 'h_domain.xdmf').write_text((tmp_path / 'motor_domain.xdmf').read_text().replace('Format="XML"', 'Format="HDF"')
-                                            .replace('Format="Binary"', 'Format="HDF"'))
-    (tmp_path / 'h_boundaries.xdmf').write_text((tmp_path / 'motor_boundaries.xdmf').read_text())
-    with pytest.raises(NotImplementedError, match='h5py'):
-        import_mesh(prefix='h', subdomains=True, dim=2, directory=str(tmp_path))
+    if fmt != 'hdf':
+        return
+    # what the reference checkout holds: git-LFS pointers in place of the .h5 files, and no .msh to fall back to
+    for w in ('domain', 'boundaries'):
+        (tmp_path / ('motor_%s.h5' % w)).write_text('version https://git-lfs.github.com/spec/v1\noid sha256:00\nsize 1\n')
+    with pytest.raises(ValueError, match='not an HDF5 file'):
+        import_mesh(prefix='motor', subdomains=True, dim=2, directory=str(tmp_path))
