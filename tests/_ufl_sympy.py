@@ -27,8 +27,8 @@ def rat(v):
 
 # ------------------------------------------------------------------------------------------------- cells
 class Facet:
-    def __init__(self, restrict, params, normal, measure, tag=None):
-        self.restrict, self.params, self.normal, self.measure, self.tag = restrict, params, normal, measure, tag
+    def __init__(self, restrict, params, normal, measure, tag=None, interior=False):
+        self.restrict, self.params, self.normal, self.measure, self.tag, self.interior = restrict, params, normal, measure, tag, interior
 
 
 def exactify(expr):
@@ -38,7 +38,26 @@ def exactify(expr):
     return expr.xreplace({f: rat(f) for f in expr.atoms(sp.Float)})
 
 
-def _poly_int(expr, gens, weight):
+POLYNOMIAL_COEFFICIENTS = True      # False for the motor families: coefficients are rational / sqrt / exp expressions of the dofs
+
+
+def _rule_int(expr, gens, triangle):
+    """Integration by substitution for integrands that are polynomials of LOW degree in the reference coordinates with
+    arbitrary coefficient expressions (P1 fields on affine cells): the edge-midpoint rule on the reference triangle (exact to
+    degree 2) and Simpson's rule per direction elsewhere (exact to degree 3).  The degree is checked at the numeric point."""
+    half = sp.Rational(1, 2)
+    if triangle:
+        rule, maxdeg = [((half, 0), sp.Rational(1, 6)), ((0, half), sp.Rational(1, 6)), ((half, half), sp.Rational(1, 6))], 2
+    else:
+        rule, maxdeg = [((), sp.Integer(1))], 3
+        for _ in gens:
+            rule = [(p + (x,), w * wx) for p, w in rule for x, wx in ((0, sp.Rational(1, 6)), (half, sp.Rational(2, 3)), (1, sp.Rational(1, 6)))]
+    num = sp.Poly(sp.N(expr.xreplace(NUMERIC), 30), *gens)
+    assert num.total_degree() <= maxdeg, 'integrand of degree %d in the reference coordinates' % num.total_degree()
+    return sp.Add(*[w * expr.xreplace(dict(zip(gens, p))) for p, w in rule])
+
+
+def _poly_int(expr, gens, weight, triangle=False):
     """Exact integral of a polynomial in `gens`; weight(monomial exponents) is the integral of that monomial."""
     expr = exactify(expr)
     if not gens:
@@ -47,18 +66,22 @@ def _poly_int(expr, gens, weight):
     irr = {a: sp.Dummy('c') for a in expr.atoms(sp.Pow) if a.is_number and not a.is_Rational}
     expr = expr.xreplace(irr)
     others = sorted(expr.free_symbols - set(gens), key=str)
+    if not POLYNOMIAL_COEFFICIENTS:
+        return _rule_int(expr.xreplace({v: a for a, v in irr.items()}), gens, triangle)
     p = sp.poly(expr, *gens, *others, domain='QQ')
     k = len(gens)
     tot = 0
     for mon, c in p.terms():
-        tot += c * weight(mon[:k]) * sp.Mul(*[g ** e for g, e in zip(others, mon[k:]) if e])
+        tot += sp.sympify(c) * weight(mon[:k]) * sp.Mul(*[g ** e for g, e in zip(others, mon[k:]) if e])
     return sp.sympify(tot).xreplace({v: a for a, v in irr.items()})
 
 
 class Cell:
     """kind 'triangle' | 'interval' | 'box'; X = vertex coordinates (sympy Matrices); tags = {facet key: tag}."""
 
-    def __init__(self, kind, X, exterior=(), cell_tag=None):
+    def __init__(self, kind, X, exterior=(), cell_tag=None, interior=()):
+        """exterior / interior: [(facet key, tag)] of this cell's tagged facets on the boundary / inside the mesh (an interior
+        facet is listed by BOTH cells that share it: each contributes its own side of a `dS` integral)."""
         self.kind, self.X, self.cell_tag = kind, X, cell_tag
         d = X[0].rows
         self.d = d
@@ -79,7 +102,7 @@ class Cell:
         self.facets = []
         s = sp.Symbol('s')
         ref = {0: (0, 0), 1: (1, 0), 2: (0, 1)}
-        for key, tag in exterior:
+        for key, tag, inside in [(k, t, False) for k, t in exterior] + [(k, t, True) for k, t in interior]:
             if kind == 'triangle':
                 a, b, o = key                                     # local vertices of the facet, opposite vertex
                 t = X[b] - X[a]
@@ -88,20 +111,20 @@ class Cell:
                 if n.dot(X[a] - X[o]) < 0:
                     n = -n
                 restrict = {self.xi[0]: ref[a][0] * (1 - s) + ref[b][0] * s, self.xi[1]: ref[a][1] * (1 - s) + ref[b][1] * s}
-                self.facets.append(Facet(restrict, (s,), n, length, tag))
+                self.facets.append(Facet(restrict, (s,), n, length, tag, inside))
             else:
                 k, side = key                                     # axis, 0 / 1
                 n = sp.zeros(d, 1)
                 n[k] = 1 if side else -1
                 params = tuple(x for j, x in enumerate(self.xi) if j != k)
-                self.facets.append(Facet({self.xi[k]: side}, params, n, sp.Mul(*[h[j] for j in range(d) if j != k]), tag))
+                self.facets.append(Facet({self.xi[k]: side}, params, n, sp.Mul(*[h[j] for j in range(d) if j != k]), tag, inside))
 
     def integrate(self, expr):
         if self.kind == 'triangle':
             w = lambda m: sp.Rational(int(sp.factorial(m[0]) * sp.factorial(m[1])), int(sp.factorial(m[0] + m[1] + 2)))   # noqa: E731
         else:
             w = lambda m: sp.Rational(1, int(sp.Mul(*[e + 1 for e in m])))                                              # noqa: E731
-        return _poly_int(sp.sympify(expr).xreplace({HSYM: self.diameter}) * self.absdet, self.xi, w)
+        return _poly_int(sp.sympify(expr).xreplace({HSYM: self.diameter}) * self.absdet, self.xi, w, self.kind == 'triangle')
 
     def integrate_facet(self, f, expr):
         tab = {NSYM[i]: f.normal[i] for i in range(self.d)}
@@ -156,6 +179,17 @@ class Field:
         return -self.e
 
 
+class Restricted:
+    """`expr("+")` / `expr("-")` of UFL (load_defs rewrites that call syntax into restricted(expr, side))."""
+
+    def __init__(self, e, side):
+        self.e, self.side = E(e), side
+
+    def __mul__(self, measure):
+        assert measure.kind == 'dS'
+        return Form([(Measure('dS' + self.side, measure.tag), self.e)])
+
+
 class Measure:
     def __init__(self, kind, tag=None):
         self.kind, self.tag = kind, tag
@@ -203,8 +237,16 @@ class Form:
                     tot += CTX.integrate(e)
             elif m.kind == 'ds':
                 for f in CTX.facets:
-                    if m.tag is None or m.tag == f.tag:
+                    if not f.interior and (m.tag is None or m.tag == f.tag):
                         tot += CTX.integrate_facet(f, e)
+            elif m.kind == 'dS+':
+                # an interior facet is visited from both of its cells; the current cell plays the "+" side on its visit and
+                # the other cell's visit supplies the "-" term (the reference's forms restrict the SAME expression both ways)
+                for f in CTX.facets:
+                    if f.interior and (m.tag is None or m.tag == f.tag):
+                        tot += CTX.integrate_facet(f, e)
+            elif m.kind == 'dS-':
+                pass
             else:
                 raise NotImplementedError(m.kind)
         return tot
@@ -256,13 +298,36 @@ def Constant(mesh, value):
     return E(value) if not isinstance(value, (list, tuple)) else sp.Matrix([E(v) for v in value])
 
 
+NUMERIC = {}                    # symbol -> value: where `conditional` picks its branch
+_MEMO = {}
+
+
+def _memo(op, m):
+    """The motor forms invert / take the determinant of the same deformation gradient hundreds of times per cell."""
+    key = (op, sp.ImmutableMatrix(m))
+    if key not in _MEMO:
+        if len(_MEMO) > 4096:
+            _MEMO.clear()
+        _MEMO[key] = getattr(m, op)()
+    return _MEMO[key]
+
+
+
+def conditional(cond, a, b):
+    op, l, r = cond
+    assert op == 'lt'
+    return E(a) if float(sp.N((E(l) - E(r)).xreplace(NUMERIC), 30)) < 0 else E(b)
+
+
 NAMESPACE = dict(
+    conditional=conditional, lt=lambda a, b: ('lt', a, b), restricted=Restricted,
     grad=grad, div=div, inner=inner, dot=dot, derivative=derivative, Constant=Constant,
     dx=Measure('dx'), ds=Measure('ds'), dS=Measure('dS'),
     FacetNormal=lambda mesh: sp.Matrix(NSYM[:CTX.d]), CellDiameter=lambda mesh: HSYM, SpatialCoordinate=lambda mesh: CTX.x,
-    Identity=lambda d: sp.eye(d), tr=lambda a: E(a).trace(), det=lambda a: E(a).det(), inv=lambda a: E(a).inv(),
+    Identity=lambda d: sp.eye(d), tr=lambda a: E(a).trace(), det=lambda a: _memo('det', E(a)), inv=lambda a: _memo('inv', E(a)),
     sqrt=lambda a: sp.sqrt(E(a)), exp=lambda a: sp.exp(E(a)), as_vector=lambda a: sp.Matrix([E(v) for v in a]),
-    ufl=types.SimpleNamespace(ds=Measure('ds'), dx=Measure('dx'), pi=sp.pi, sin=lambda a: sp.sin(E(a)), cos=lambda a: sp.cos(E(a))),
+    ufl=types.SimpleNamespace(ds=Measure('ds'), dx=Measure('dx'), pi=sp.pi, sin=lambda a: sp.sin(E(a)), cos=lambda a: sp.cos(E(a)),
+                              sqrt=lambda a: sp.sqrt(E(a)), dot=dot),
 )
 
 
@@ -272,7 +337,14 @@ def load_defs(path, extra=None):
     import numpy as np
     ns = dict(NAMESPACE, np=np)
     ns.update(extra or {})
-    tree = ast.parse(open(path).read())
+    class Restrict(ast.NodeTransformer):          # X("+") -> restricted(X, "+"): sympy expressions are not callable
+        def visit_Call(self, node):
+            self.generic_visit(node)
+            if (len(node.args) == 1 and not node.keywords and isinstance(node.args[0], ast.Constant)
+                    and node.args[0].value in ('+', '-')):
+                return ast.copy_location(ast.Call(ast.Name('restricted', ast.Load()), [node.func, node.args[0]], []), node)
+            return node
+    tree = ast.fix_missing_locations(Restrict().visit(ast.parse(open(path).read())))
     for node in tree.body:
         if isinstance(node, ast.FunctionDef):
             exec(compile(ast.Module([node], []), path, 'exec'), ns)
@@ -282,3 +354,23 @@ def load_defs(path, extra=None):
             except Exception:
                 pass
     return ns
+
+
+def jac_numeric(exprs, syms, table):
+    """d exprs / d syms at the rational point `table` by 80-digit central differences of step 1e-25 (the expressions of the
+    motor families are too large for sympy.diff): truncation error ~1e-50 x the third derivative."""
+    import mpmath as mp
+    keys = list(table)
+    f = sp.lambdify(keys, [exactify(e) for e in exprs], 'mpmath', cse=True)
+    with mp.workdps(80):
+        x0 = [mp.mpf(int(table[k].p)) / mp.mpf(int(table[k].q)) for k in keys]
+        h = mp.mpf(10) ** -25
+        cols = []
+        for s_ in syms:
+            j = keys.index(s_)
+            xp, xm = list(x0), list(x0)
+            xp[j] += h
+            xm[j] -= h
+            cols.append([float((a - b) / (2 * h)) for a, b in zip(f(*xp), f(*xm))])
+    import numpy as np
+    return np.array(cols, dtype=np.float64).T

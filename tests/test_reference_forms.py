@@ -19,6 +19,14 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason='no reference che
 TOL = 1e-13
 
 
+@pytest.fixture(autouse=True)
+def _reset_flags():
+    U.POLYNOMIAL_COEFFICIENTS = True
+    U.NUMERIC = {}
+    yield
+    U.POLYNOMIAL_COEFFICIENTS = True
+
+
 def _num(exprs, tab):
     return np.array([float(sp.N(U.exactify(e).xreplace(tab), 30)) for e in exprs], dtype=np.float64)
 
@@ -191,3 +199,129 @@ def test_simp_forms_as_written_in_the_example(name):
         avg += ns['averageFunc'](rho).value()
         comp += ns['compliance'](u, fvec, dss=ds100).value()
     _compare(z, R, [avg, comp], Us, Rs, _table(z, Us, Rs))
+
+
+# ------------------------------------------------------------------------------------------------- config 5 (motor)
+def _motor_namespace():
+    """examples/em_motor_opt/motor_pde.py with what it star-imports: the ALE kinematics gradx / J / F and DOLFIN_EPS from
+    femo/fea/utils_dolfinx.py:30-66 (the reference's own definitions, executed), and the B-H curve pieces of
+    permeability/piecewise_permeability.py fed with the fitted constants of femo_b200/forms/bh_fit.json (that module fits them
+    from a data table at import time)."""
+    import json
+    fit = json.load(open(os.path.join(os.path.dirname(GOLD), '..', '..', 'femo_b200', 'forms', 'bh_fit.json')))
+    utils = U.load_defs('/root/reference/femo/fea/utils_dolfinx.py')
+    perm = U.load_defs(os.path.join(REF, 'em_motor_opt', 'permeability', 'piecewise_permeability.py'),
+                       extra=dict(linearA=fit['lin'][0], linearB=fit['lin'][1], cubicA=fit['cubic'][0], cubicB=fit['cubic'][1],
+                                  cubicC=fit['cubic'][2], cubicD=fit['cubic'][3], popt_exp=fit['exp'], x1=fit['x1'], x2=fit['x2']))
+    extra = {k: utils[k] for k in ('gradx', 'J', 'F', 'DOLFIN_EPS')}
+    extra.update({k: perm[k] for k in ('linearPortion', 'cubicPortion')})
+    extra.update(exp_coeff=perm['extractexpDecayCoeff'](), cubic_bounds=perm['extractCubicBounds']())
+    return U.load_defs(os.path.join(REF, 'em_motor_opt', 'motor_pde.py'), extra=extra)
+
+
+def _motor_cells(z, tagged):
+    """Triangle cells with their tagged facets: `tagged` = set of (cell, local facet) pairs (local facet i is opposite local
+    vertex i) carrying tag 1000, or None for every exterior facet untagged (`ds` without a subdomain id)."""
+    cells = [tuple(int(v) for v in c) for c in z['cells']]
+    X = [sp.Matrix([U.rat(a), U.rat(b)]) for a, b in z['coords']]
+    cnt = {}
+    for c in cells:
+        for a in range(3):
+            e = tuple(sorted((c[a], c[(a + 1) % 3])))
+            cnt[e] = cnt.get(e, 0) + 1
+    tags = z['meta_cell_tags']
+    out = []
+    for ci, c in enumerate(cells):
+        ext, inner = [], []
+        for o in range(3):
+            a, b = [k for k in range(3) if k != o]
+            boundary = cnt[tuple(sorted((c[a], c[b])))] == 1
+            if tagged is None:
+                if boundary:
+                    ext.append(((a, b, o), None))
+            elif (ci, o) in tagged:
+                (ext if boundary else inner).append(((a, b, o), 1000))
+        out.append((c, U.Cell('triangle', [X[v] for v in c], ext, cell_tag=int(tags[ci]), interior=inner)))
+    return out
+
+
+MESH2D = __import__('types').SimpleNamespace(topology=__import__('types').SimpleNamespace(dim=2))
+
+
+def _vector_p1(cell, v, syms):
+    coeffs = [syms[2 * v[a] + k] for a in range(3) for k in range(2)]
+    return U.Field(sp.Matrix([sum(syms[2 * v[a] + k] * cell.lam[a] for a in range(3)) for k in range(2)]), coeffs=coeffs, mesh=MESH2D)
+
+
+def _compare_numeric(z, R, Js, Usym, Msym, tab, tol):
+    def same(got, exact, what):
+        exact = np.asarray(exact, dtype=np.float64).reshape(np.shape(got))
+        scale = max(np.abs(exact).max(), 1e-300)
+        assert np.abs(np.asarray(got) - exact).max() <= tol * scale, (what, np.abs(np.asarray(got) - exact).max() / scale)
+    same(_num(R, tab), z['R'], 'R')
+    same(U.jac_numeric(R, Usym, tab), z['A'], 'dR/du')
+    same(U.jac_numeric(R, Msym, tab), z['D0'], 'dR/dm')
+    for k, Jf in enumerate(Js):
+        same(_num([Jf], tab), z['J%d' % k], 'J%d' % k)
+        same(U.jac_numeric([Jf], Usym, tab)[0], z['Ju%d' % k], 'dJ%d/du' % k)
+        same(U.jac_numeric([Jf], Msym, tab)[0], z['Jm%d_0' % k], 'dJ%d/dm' % k)
+
+
+def test_mesh_motion_forms_as_written_in_the_example():
+    """motor_pde.pdeResMM(uhat, v, g=..., nitsche=True, sym=True, overpenalty=False, dS_=dS(1000), ds_=ds(1000)) and
+    area_form(uhat, dx, ids) as run_motor_opt.py:176-187 calls them; `X("+")` restrictions are rewritten to restricted(X, "+")."""
+    ns = _motor_namespace()
+    z = np.load(os.path.join(GOLD, 'motor_mm.npz'))
+    tagged = {(int(c), int(l)) for c, l in zip(z['meta_facet_cells'], z['meta_facet_locals'])}
+    cells = _motor_cells(z, tagged)
+    N = z['state'].size
+    Us, Gs = sp.symbols('U0:%d' % N), sp.symbols('G0:%d' % N)
+    tab = _table(z, Us, Gs)
+    U.NUMERIC = tab
+    U.POLYNOMIAL_COEFFICIENTS = False
+    dx, dS, ds = U.NAMESPACE['dx'], U.NAMESPACE['dS'], U.NAMESPACE['ds']
+    R, areas = [0] * N, [0, 0, 0]
+    for v, cell in cells:
+        U.CTX = cell
+        uhat, g = _vector_p1(cell, v, Us), _vector_p1(cell, v, Gs)
+        for a in range(3):
+            for k in range(2):
+                test = U.Field(sp.Matrix([cell.lam[a] if i == k else 0 for i in range(2)]),
+                               values=[1 if (b, j) == (a, k) else 0 for b in range(3) for j in range(2)], mesh=MESH2D)
+                R[2 * v[a] + k] += ns['pdeResMM'](uhat, test, g=g, nitsche=True, sym=True, overpenalty=False,
+                                                  dS_=dS(1000), ds_=ds(1000)).value()
+        for k, ids in enumerate((15, 3, [1, 2])):                       # winding_id, magnet_id, steel_id (run_motor_opt.py:68-70)
+            areas[k] += ns['area_form'](uhat, dx, ids).value()
+    _compare_numeric(z, R, areas, Us, Gs, tab, 1e-12)
+
+
+def test_magnetostatics_forms_as_written_in_the_example():
+    """motor_pde.pdeResEM(u, v, uhat, iq, dx, p, s, Hc, vacuum_perm, angle, g=0, nitsche=True, sym=True, overpenalty=False, ds_=ds)
+    and B_power_form(u, uhat, n, dx, [1, 2]) as run_motor_opt.py:276-291 calls them -- RelativePermeability, JS, the 216
+    subdomain integrals and the Nanson-normal Nitsche terms all come from the reference's code."""
+    ns = _motor_namespace()
+    z = np.load(os.path.join(GOLD, 'motor_em.npz'))
+    cells = _motor_cells(z, None)
+    N, M = z['state'].size, z['input0'].size
+    Us, Ws = sp.symbols('U0:%d' % N), sp.symbols('W0:%d' % M)
+    tab = _table(z, Us, Ws)
+    U.NUMERIC = tab
+    U.POLYNOMIAL_COEFFICIENTS = False
+    dx, ds = U.NAMESPACE['dx'], U.NAMESPACE['ds']
+    prm = {k: float(z['meta_' + k]) for k in ('Hc', 'angle', 'iq')}
+    p_, s_ = int(z['meta_p']), int(z['meta_s'])
+    assert float(z['meta_beta']) == 1e4                               # hard-coded in pdeResEM
+    mu0 = 4e-7 * np.pi
+    R, outs = [0] * N, [0, 0]
+    for v, cell in cells:
+        U.CTX = cell
+        u = U.Field(sum(Us[v[a]] * cell.lam[a] for a in range(3)), coeffs=[Us[i] for i in v], mesh=MESH2D)
+        uhat = _vector_p1(cell, v, Ws)
+        zero = U.Field(sp.Integer(0), mesh=MESH2D)
+        for a in range(3):
+            test = U.Field(cell.lam[a], values=[1 if b == a else 0 for b in range(3)], mesh=MESH2D)
+            R[v[a]] += ns['pdeResEM'](u, test, uhat, prm['iq'], dx, p_, s_, prm['Hc'], mu0, prm['angle'],
+                                      g=zero, nitsche=True, sym=True, overpenalty=False, ds_=ds).value()
+        for k, n_ in enumerate((2, 1.76835)):
+            outs[k] += ns['B_power_form'](u, uhat, n_, dx, [1, 2]).value()
+    _compare_numeric(z, R, outs, Us, Ws, tab, 1e-11)
