@@ -176,3 +176,27 @@ def test_measures_projection_and_constants(ref):
     assert ref['DOLFIN_EPS'] == 3e-16
     from oracle import motor
     assert motor.DOLFIN_EPS == ref['DOLFIN_EPS']
+
+
+def test_locate_dofs_equals_the_reference_function():
+    """locateDOFs / findNodeIndices (utils_dolfinx.py:126-134,617-641) are plain numpy + KDTree code: the reference's own
+    functions are CALLED here (polar and cartesian input) and the mirror must return the same dof indices.  The reference
+    converts the caller's array to cartesian IN PLACE as a side effect; the mirror leaves its argument alone."""
+    if not os.path.isdir(os.path.join(L.REFERENCE, 'femo')):
+        pytest.skip('no reference checkout')
+    import types
+    ref = L.load_reference_utils([])
+    from femo_b200.fea import utils_b200 as ub
+    rng = np.random.default_rng(4)
+    th, r = rng.uniform(0, 2 * np.pi, 40), rng.uniform(0.06, 0.12, 40)
+    nodes = np.stack([r * np.cos(th), r * np.sin(th), np.zeros(40)], axis=1)
+    V = types.SimpleNamespace(tabulate_dof_coordinates=lambda: nodes)
+    pick = rng.choice(40, 11, replace=False)
+    polar = np.stack([th[pick], r[pick]], axis=1) + rng.normal(0, 1e-4, (11, 2))
+    a0, b0 = polar.ravel().copy(), polar.ravel().copy()
+    ia, ib = ref.locateDOFs(a0, V, input='polar'), ub.locateDOFs(b0, V, input='polar')
+    assert np.array_equal(ia, ib) and np.array_equal(ib[0::2] // 2, pick)
+    assert not np.array_equal(a0, polar.ravel()) and np.array_equal(b0, polar.ravel())
+    cart = nodes[pick, :2] + rng.normal(0, 1e-5, (11, 2))
+    assert np.array_equal(ref.locateDOFs(cart.copy(), V, input='cartesian'), ub.locateDOFs(cart.copy(), V, input='cartesian'))
+    assert np.array_equal(ref.findNodeIndices(cart, nodes[:, :2]), ub.findNodeIndices(cart, nodes[:, :2]))
