@@ -63,9 +63,12 @@ class OutputOperation(CustomExplicitOperation):
 
     def compute_derivatives(self, inputs, derivatives):                  # :77-87
         self._push(inputs)
+        # vectors come back in a ring of three page-locked staging buffers per size (utils_b200._download): with more than
+        # three partials a fourth result could land on the first one's buffer while a backend still holds it -- own the data then
+        own = len(self.args_dict) > 3
         for arg_name, arg in self.args_dict.items():
-            derivatives[self.output_name, arg_name] = assemble(
-                computePartials(self.output['form'], arg['function']), dim=self.output_dim + 1)
+            g = assemble(computePartials(self.output['form'], arg['function']), dim=self.output_dim + 1)
+            derivatives[self.output_name, arg_name] = np.array(g) if own else g
 
 
 class OutputFieldModel(Model):
