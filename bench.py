@@ -68,6 +68,38 @@ def workload(n, kind='p1'):
                 cache='working set (>10 GB) exceeds the 126 MB L2; no explicit flush')
 
 
+def base_dofs_of(n, kind):
+    return (n + 1) ** 2 if kind in ('p1', 'motor') else 3 * (n + 1) * (n // 2 + 1) * (n // 4 + 1)
+
+
+def global_dofs_of(n, kind, world):
+    """dofs of the ONE partitioned problem `--gpus world` runs (EngineStep builds exactly this)."""
+    if world == 1:
+        return workload(n, kind)['dofs']
+    if kind == 'hex':
+        return 3 * (n + 1) * (n // 2 + 1) * (n // 4 * world + 1)
+    return (N_DIST + 1) * (N_DIST * world + 1)
+
+
+def arm_config(n, kind, world):
+    """`config` of the JSON line, one function for BOTH arms: `--impl reference` must describe the same workload as the
+    femo_b200 arm launched with the same flags."""
+    cfg = workload(n, kind)
+    gd = global_dofs_of(n, kind, world)
+    if world > 1:
+        cfg['workload'] = ('weak-scaled %s: %d dofs over %d GPUs (the N=1 workload has %d)'
+                           % (cfg['workload'].split(' n=')[0] if kind == 'p1' else cfg['workload'].split(' (')[0],
+                              gd, world, base_dofs_of(n, kind)))
+        cfg['dofs'] = gd
+    cfg['parallelism'] = ('1 GPU' if world == 1 else
+                          (('one cantilever of %d x %d x %d cells (%d dofs), z-slab partition ' % (n, n // 2, n // 4 * world, gd))
+                           if kind == 'hex' else
+                           ('one problem on [0,1]x[0,%d], %d x %d cells (%d dofs), y-slab partition ' % (world, N_DIST, N_DIST * world, gd))) +
+                          ('with one-cell ghost layer over %d GPUs, halo exchange + all-reduce, '
+                           'partitioned multigrid; value = solves/s x dofs/dofs(N=1 workload)' % world))
+    return cfg
+
+
 # ---------------------------------------------------------------------------
 # clocks sampling (B200_PROFILING.md recipe)
 # ---------------------------------------------------------------------------
@@ -551,9 +583,13 @@ def main():
     if a.impl == 'reference':
         if rank != 0:
             return 0
-        # every step is one FULL state+adjoint solve of the metric's config on all host cores (about 12-18 s each);
-        # one warm-up is enough on a CPU (it only absorbs the page faults of the persistent workspace)
-        cpu_step(a.n)
+        # every step is one FULL state+adjoint solve of the N=1 workload (n=4000, 16M dofs) on all host cores, about 3 - 4 s
+        # each on the GPU box: --steps 20 --warmup 5 ends within two minutes.  Under --gpus N > 1 the femo_b200 arm solves ONE
+        # N-times larger problem and normalises its value to solves of the N=1 workload; the bounded CPU sample of that
+        # workload is the N=1-sized problem itself, in the same normalised unit, so `config` is the GPU arm's for the same flags
+        wr = max(int(a.warmup), 1)
+        for _ in range(wr):
+            cpu_step(a.n)
         t0 = time.perf_counter()
         for _ in range(a.steps):
             _, r = cpu_step(a.n)
@@ -561,12 +597,14 @@ def main():
         val = 1.0 / dt
         sample = ('oracle/cpu_path.cpp: C++/OpenMP restatement of the reference path (the reference itself needs dolfinx + '
                   'PETSc/MUMPS, not installable offline) with the GPU arm\'s algorithm (SNES + FMG/GMG-PCG rtol %g) on %d host '
-                  'threads; every step is a full n=%d solve (%d dofs), %.2f s per state+adjoint solve, 1 warm-up, no '
-                  'extrapolation; J=%.13g, Newton its %d, Krylov its %d + %d'
-                  % (KRYLOV_RTOL, r['threads'], a.n, (a.n + 1) ** 2, dt, r['J'], r['newton_its'], r['krylov_its'], r['adjoint_its']))
-        print(json.dumps(dict(metric=METRIC, value=val, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=1,
+                  'threads; every step is a full n=%d solve (%d dofs = the N=1 workload%s), %.2f s per state+adjoint solve, %d '
+                  'warm-up(s), no extrapolation; J=%.13g, Newton its %d, Krylov its %d + %d'
+                  % (KRYLOV_RTOL, r['threads'], a.n, (a.n + 1) ** 2,
+                     '' if world == 1 else '; the %d-GPU arm\'s value is normalised to solves of this workload' % world,
+                     dt, wr, r['J'], r['newton_its'], r['krylov_its'], r['adjoint_its']))
+        print(json.dumps(dict(metric=METRIC, value=val, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=wr,
                               ms_per_step=1e3 / val, higher_is_better=True, scaling='weak', vs_baseline=None,
-                              dtype='f64', data='synthetic', config=dict(workload(a.n), parallelism='%d host threads' % r['threads']),
+                              dtype='f64', data='synthetic', config=arm_config(a.n, a.workload, max(world, a.gpus)),
                               impl='reference',
                               cpu_baseline=dict(value=val, unit=UNIT, cores=r['threads'], kind='port', sample=sample),
                               e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
@@ -619,7 +657,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = float(tt.item())
     # one partitioned problem with `world` times the dofs: normalise to solves of the N=1 workload
-    base_dofs = (a.n + 1) ** 2 if a.workload in ('p1', 'motor') else 3 * (a.n + 1) * (a.n // 2 + 1) * (a.n // 4 + 1)
+    base_dofs = base_dofs_of(a.n, a.workload)
     norm = es.global_dofs / float(base_dofs) if world > 1 else 1.0
     value = norm * a.steps / (ms * 1e-3)
 
@@ -729,21 +767,9 @@ def main():
             k['share_of_step'] = k['launches_per_step'] * k['launch_ms'] / step_ms
             k['traffic'] = traffic.get(k['kernel'].split(' ')[0])
         dom = max((k for k in kernels if 'fp64-pipe bound' not in k['kernel']), key=lambda k: k['share_of_step'])
-        cfg = workload(a.n, a.workload)
-        if world > 1:
-            cfg['workload'] = ('weak-scaled %s: %d dofs over %d GPUs (the N=1 workload has %d)'
-                               % (cfg['workload'].split(' n=')[0] if a.workload == 'p1' else cfg['workload'].split(' (')[0],
-                                  es.global_dofs, world, base_dofs))
-            cfg['dofs'] = es.global_dofs
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=W,
                    ms_per_step=ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
-                   data='synthetic', config=dict(cfg, parallelism='1 GPU' if world == 1 else
-                                                 (('one cantilever of %d x %d x %d cells (%d dofs), z-slab partition '
-                                                   % (a.n, a.n // 2, a.n // 4 * world, es.global_dofs)) if a.workload == 'hex' else
-                                                  ('one problem on [0,1]x[0,%d], %d x %d cells (%d dofs), y-slab partition '
-                                                   % (world, N_DIST, N_DIST * world, es.global_dofs))) +
-                                                 ('with one-cell ghost layer over %d GPUs, halo exchange + all-reduce, '
-                                                  'partitioned multigrid; value = solves/s x dofs/dofs(N=1 workload)' % world)),
+                   data='synthetic', config=arm_config(a.n, a.workload, world),
                    clocks=clocks, gpu_launches=int(launches), e2e=e2e,
                    roofline=dict(bound='hbm', kernel=dom['kernel'], achieved=dom['achieved_gbs'], peak=peak, unit='GB/s',
                                  frac=dom['frac'], traffic=dom['traffic'],
