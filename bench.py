@@ -523,10 +523,19 @@ class ApiStep:
 # CPU arm: oracle/cpu_path.cpp, the C++/OpenMP restatement of the same step with the same GMG-PCG algorithm
 # (the reference's dolfinx + MUMPS path is not installable offline), on all host cores, at the FULL workload size
 # ---------------------------------------------------------------------------
+def host_threads():
+    """All host threads this process may use.  Passed explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers when
+    it starts more than one, which would silently turn the CPU arm of a --gpus N run into a single-threaded one."""
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except AttributeError:
+        return max(os.cpu_count() or 1, 1)
+
+
 def cpu_step(n):
     from oracle import cpu_path
     t = time.perf_counter()
-    r = cpu_path.step(n, 0.1, krylov_rtol=KRYLOV_RTOL)
+    r = cpu_path.step(n, 0.1, krylov_rtol=KRYLOV_RTOL, nthreads=host_threads())
     dt = time.perf_counter() - t
     if not r['converged']:
         raise RuntimeError('cpu_path: SNES / Krylov did not converge')
