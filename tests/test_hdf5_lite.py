@@ -75,3 +75,29 @@ def test_xdmf_with_dolfinx_style_items(tmp_path):
         '</Grid></Domain></Xdmf>')
     p, (kind, c), vals = read_xdmf(str(tmp_path / 'm.xdmf'))
     assert kind == 'triangle' and vals is None and np.array_equal(p, pts) and np.array_equal(c, conn)
+
+
+def test_random_round_trips(tmp_path):
+    """Seeded sweep over ranks 1 - 3, dtypes, chunk shapes (smaller than, equal to and larger than the array), filters and
+    one- / two-level chunk B-trees."""
+    rng = np.random.default_rng(7)
+    dtypes = ['<f8', '<f4', '<i8', '<i4', '<u2', '>i4', '>f4', '<i1']
+    for case in range(60):
+        rank = int(rng.integers(1, 4))
+        shape = tuple(int(v) for v in rng.integers(1, 9, rank))
+        dt = np.dtype(dtypes[int(rng.integers(len(dtypes)))])
+        a = (rng.standard_normal(shape) * 100).astype(dt)
+        kw = {}
+        if rng.random() < 0.75:
+            kw['chunks'] = tuple(int(v) for v in rng.integers(1, 11, rank))
+            if rng.random() < 0.6:
+                kw['gzip'] = int(rng.integers(1, 10))
+            kw['shuffle'] = bool(rng.random() < 0.5)
+            kw['two_level'] = bool(rng.random() < 0.5)
+        path = str(tmp_path / ('r%d.h5' % case))
+        write(path, {'g': {'d': a}, 'top': a[..., :1]}, userblock=int(rng.choice([0, 512, 2048])), **kw)
+        f = hdf5_lite.File(path)
+        for name, ref in (('/g/d', a), ('top', a[..., :1])):
+            b = f[name]
+            assert b.shape == ref.shape and b.dtype.kind == ref.dtype.kind and b.dtype.itemsize == ref.dtype.itemsize, (case, kw)
+            assert np.array_equal(b, ref), (case, shape, dt, kw)
